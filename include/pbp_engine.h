@@ -1,0 +1,157 @@
+/*
+ * pbp_engine.h -- C ABI of the B200 batched collision-validation engine (libpbp_engine.so).
+ *
+ * This is the drop-in boundary for pyroboplan's collision hot path.  The reference has no
+ * native FFI of its own for this path: it reaches Pinocchio/coal through boost.python from
+ * the free functions in src/pyroboplan/core/utils.py and src/pyroboplan/planning/utils.py.
+ * Each entry point below cites the reference call it replaces (paths relative to
+ * /root/reference/).  The Python host side (pyroboplan_b200/engine.py) binds exactly these
+ * symbols with ctypes; INTEGRATION.md shows the stub a pyroboplan maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types in signatures;
+ *  - every function returns 0 on success, a negative pbp_status otherwise, and
+ *    pbp_last_error() returns a thread-local message for the last failure;
+ *  - "_dev" arguments are CUDA device pointers on the engine's device, "_host" arguments
+ *    are host pointers; `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *  - device-pointer entry points are asynchronous on `stream`; host-pointer entry points
+ *    (suffix _host) copy in, run, copy out and synchronise before returning;
+ *  - configurations are row-major float32 [N, nq]; SE(3) placements are 12 floats:
+ *    rotation row-major (9) then translation (3);
+ *  - there is NO CPU fallback: without a CUDA device creation fails with PBP_ERR_CUDA.
+ */
+#ifndef PBP_ENGINE_H
+#define PBP_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBP_ABI_VERSION 1
+
+typedef enum {
+    PBP_OK = 0,
+    PBP_ERR_ARG = -1,      /* bad argument (null pointer, negative size, unsupported value) */
+    PBP_ERR_CUDA = -2,     /* CUDA runtime error, including "no device" */
+    PBP_ERR_CAPACITY = -3, /* model exceeds a compiled-in table limit */
+    PBP_ERR_ALLOC = -4     /* device or pinned-host allocation failed */
+} pbp_status;
+
+typedef enum { PBP_SHAPE_SPHERE = 0, PBP_SHAPE_BOX = 1, PBP_SHAPE_CYLINDER = 2, PBP_SHAPE_CAPSULE = 3, PBP_SHAPE_CONVEX = 4 } pbp_shape_type;
+typedef enum { PBP_JOINT_FIXED = 0, PBP_JOINT_REVOLUTE = 1, PBP_JOINT_PRISMATIC = 2 } pbp_joint_type;
+
+/* Compile-time table limits of the kernels. */
+#define PBP_MAX_JOINTS 64
+#define PBP_MAX_GEOMS 128
+#define PBP_MAX_PAIRS 4096
+#define PBP_MAX_NQ 64
+
+/*
+ * Flat model description (host pointers, copied at creation).  Replaces the pinocchio.Model /
+ * pinocchio.GeometryModel pair every reference hot-path function takes
+ * (src/pyroboplan/core/utils.py:8-15).  Joint 0 is the universe; joints are topologically
+ * ordered (parent < child).  Geometry g is rigidly attached to joint geom_parent[g] with
+ * placement geom_placement[g] (for geom_parent == 0 that is its world placement).
+ */
+typedef struct {
+    int32_t nq, njoints, ngeoms, npairs, nverts, nframes;
+    const int32_t *joint_parent;   /* [njoints] */
+    const int32_t *joint_type;     /* [njoints] pbp_joint_type */
+    const int32_t *joint_idx_q;    /* [njoints] index into q, -1 for the universe */
+    const float *joint_placement;  /* [njoints][12] placement in the parent joint frame */
+    const float *joint_axis;       /* [njoints][3] unit axis */
+    const float *q_lower;          /* [nq] */
+    const float *q_upper;          /* [nq] */
+    const int32_t *geom_parent;    /* [ngeoms] parent joint */
+    const int32_t *geom_shape;     /* [ngeoms] pbp_shape_type */
+    const float *geom_placement;   /* [ngeoms][12] */
+    const float *geom_params;      /* [ngeoms][4] sphere: r | box: hx hy hz | cylinder, capsule: r, half length */
+    const int32_t *geom_vert_off;  /* [ngeoms] first hull vertex (convex shapes) */
+    const int32_t *geom_vert_cnt;  /* [ngeoms] hull vertex count */
+    const float *geom_outer;       /* [ngeoms][4] enclosing sphere (cx cy cz r), geometry frame */
+    const float *geom_inner;       /* [ngeoms][4] inscribed sphere (cx cy cz r), geometry frame */
+    const float *verts;            /* [nverts][3] hull vertices, geometry frame */
+    const int32_t *pairs;          /* [npairs][2] active collision pairs (first, second) */
+    const int32_t *frame_parent;   /* [nframes] parent joint of each frame (may be NULL if nframes == 0) */
+    const float *frame_placement;  /* [nframes][12] */
+} pbp_model_desc;
+
+typedef struct pbp_engine pbp_engine;
+
+/* Work counters since creation / last reset (for bench.py: gpu_launches, items per state). */
+typedef struct {
+    int64_t kernel_launches;   /* kernels launched by this engine */
+    int64_t states;            /* configurations pushed through FK + broadphase */
+    int64_t narrowphase_items; /* (state, pair) items that reached GJK (only counted by *_host / sync calls) */
+    int64_t chunks;            /* broadphase / narrowphase chunk iterations */
+} pbp_stats;
+
+const char *pbp_last_error(void);
+int pbp_abi_version(void);
+
+/* Upload a model to `device`, allocate workspaces.  max_chunk_states <= 0 picks a default.
+ * Replaces model.createData() / collision_model.createData() (core/utils.py:39-42). */
+int pbp_engine_create(const pbp_model_desc *desc, int device, int64_t max_chunk_states, pbp_engine **out);
+void pbp_engine_destroy(pbp_engine *e);
+int pbp_engine_device(const pbp_engine *e);
+int pbp_get_stats(pbp_engine *e, pbp_stats *out, int reset);
+
+/* Forward kinematics + placement of joints / geometries / frames for N configurations.
+ * Replaces pinocchio.framesForwardKinematics + updateGeometryPlacements
+ * (core/utils.py:253,297,345,374; implicit in computeCollisions at core/utils.py:48).
+ * Any of the three outputs may be NULL.  Layouts: oMi [N][njoints][12], oMg [N][ngeoms][12],
+ * oMf [N][nframes][12]. */
+int pbp_fk(pbp_engine *e, const float *q_dev, int64_t n, float *oMi_dev, float *oMg_dev, float *oMf_dev, void *stream);
+
+/* Boolean collision (+ optional min distance / first colliding pair) for N configurations.
+ * Replaces check_collisions_at_state (core/utils.py:8-51) and, with min_dist,
+ * get_minimum_distance_at_state (core/utils.py:54-87).
+ *   hit[i]       = 1 iff some active pair has distance <= padding (padding >= 0)
+ *   min_dist[i]  = min over pairs of max(distance, 0); +inf when the model has no pairs  (nullable)
+ *   first_pair[i]= smallest pair index in collision, -1 if none                          (nullable) */
+int pbp_check_states(pbp_engine *e, const float *q_dev, int64_t n, float padding, uint8_t *hit_dev, float *min_dist_dev,
+                     int32_t *first_pair_dev, void *stream);
+int pbp_check_states_host(pbp_engine *e, const float *q_host, int64_t n, float padding, uint8_t *hit_host,
+                          float *min_dist_host, int32_t *first_pair_host);
+
+/* Edge validation: edge e = straight joint-space segment q1[e] -> q2[e], discretised on device
+ * with ceil(||dq||_2 / step) + 1 samples (both ends included) and collision-checked.
+ * Replaces has_collision_free_path (planning/utils.py:51-111) =
+ * discretize_joint_space_path (planning/utils.py:114-140) + check_collisions_along_path
+ * (core/utils.py:90-132).  hit[e] = 1 iff any sample collides (edge NOT free).
+ *   first_bad[e] = smallest colliding sample index, -1 if none (nullable; disables early-out) */
+int pbp_check_edges(pbp_engine *e, const float *q1_dev, const float *q2_dev, int64_t n_edges, double step, float padding,
+                    uint8_t *hit_dev, int32_t *first_bad_dev, void *stream);
+int pbp_check_edges_host(pbp_engine *e, const float *q1_host, const float *q2_host, int64_t n_edges, double step,
+                         float padding, uint8_t *hit_host, int32_t *first_bad_host);
+
+/* Path discretisation on device (planning/utils.py:114-140), two calls:
+ *   counts[e]  = ceil(||q2[e]-q1[e]|| / step) + 1
+ *   q_out[offsets[e] + i] = q1[e] + (i / (counts[e]-1)) * (q2[e] - q1[e]),  last sample s = 1
+ * offsets = exclusive prefix sum of counts (caller computes it, e.g. torch.cumsum). */
+int pbp_discretize_counts(pbp_engine *e, const float *q1_dev, const float *q2_dev, int64_t n_edges, double step,
+                          int32_t *counts_dev, void *stream);
+int pbp_discretize_fill(pbp_engine *e, const float *q1_dev, const float *q2_dev, int64_t n_edges,
+                        const int32_t *counts_dev, const int64_t *offsets_dev, float *q_out_dev, void *stream);
+
+/* Pre-discretised path (one group of samples): replaces check_collisions_along_path
+ * (core/utils.py:90-132) for a batch of paths given as a ragged array.
+ *   q [total][nq], path_offsets [n_paths + 1] (int64, device), hit[p] = 1 iff any sample collides. */
+int pbp_check_paths(pbp_engine *e, const float *q_dev, const int64_t *path_offsets_dev, int64_t n_paths, int64_t total,
+                    float padding, uint8_t *hit_dev, void *stream);
+
+/* Rejection sampling of collision-free configurations on device: n uniform draws in
+ * [lower + joint_padding, upper - joint_padding] per round (counter-based Philox stream
+ * keyed by `seed`), collision-checked; free ones are compacted in draw order into q_out until
+ * n_wanted are found or max_rounds rounds ran.  *n_found_host receives the count.
+ * Batched sibling of get_random_collision_free_state (core/utils.py:195-229). */
+int pbp_sample_free_states(pbp_engine *e, int64_t n_wanted, uint64_t seed, float joint_padding, float padding,
+                           int max_rounds, float *q_out_dev, int64_t *n_found_host, int64_t *n_drawn_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBP_ENGINE_H */

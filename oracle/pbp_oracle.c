@@ -1,0 +1,562 @@
+/*
+ * pbp_oracle.c -- float64 CPU restatement of the reference's collision hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (pyroboplan_b200/) may import, link or
+ * execute this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference leg use it, and only as the checker or the reported CPU baseline.
+ *
+ * What is restated, and from where
+ * --------------------------------
+ * The reference's arithmetic for this path lives in un-vendored third-party code:
+ * Pinocchio (pin == 3.7.0, /root/reference/pyproject.toml:10) and coal (transitive, unpinned).
+ * Neither is installable here, so this file restates their published algorithms and anchors
+ * on the reference's own call sites:
+ *   - pinocchio.computeCollisions(model, data, cmodel, cdata, q, stop_at_first=True)
+ *       /root/reference/src/pyroboplan/core/utils.py:48-51 and :125-130
+ *     = forward kinematics  oMi[j] = oMi[parent] * jointPlacement[j] * T_j(q_j),
+ *       geometry placement  oMg[g] = oMi[parentJoint(g)] * placement(g),
+ *       then, pair by pair in list order, coal collide(): collision <=> distance <=
+ *       security_margin, returning at the first colliding pair.
+ *   - pinocchio.computeDistances  (core/utils.py:86): min over pairs of the pair distance.
+ *   - discretize_joint_space_path  /root/reference/src/pyroboplan/planning/utils.py:114-140
+ *   - has_collision_free_path      /root/reference/src/pyroboplan/planning/utils.py:51-111
+ *   - check_collisions_along_path  /root/reference/src/pyroboplan/core/utils.py:90-132
+ * Pair distance: GJK (Gilbert-Johnson-Keerthi) on support functions, float64, run to
+ * convergence (exact for polytopes), with spheres/capsules handled as core + radius.  URDF
+ * meshes are treated as their convex hulls (see DESIGN.md "mesh semantics").  Distances of
+ * penetrating pairs are reported as 0 (coal's penetration depth is not restated).
+ *
+ * Parity pin: tests/test_oracle_golden.py checks this file against every known-answer vector
+ * the reference's tests hold for the path and verifies, independently of GJK,
+ * the separating-plane / common-point certificate this file emits for each pair result.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <stdatomic.h>
+#include <unistd.h>
+
+enum { SH_SPHERE = 0, SH_BOX = 1, SH_CYLINDER = 2, SH_CAPSULE = 3, SH_CONVEX = 4 };
+enum { JT_FIXED = 0, JT_REVOLUTE = 1, JT_PRISMATIC = 2 };
+
+typedef struct {
+    int32_t nq, njoints, ngeoms, npairs, nverts;
+    const int32_t *joint_parent;   /* [njoints] */
+    const int32_t *joint_type;     /* [njoints] */
+    const int32_t *joint_idx_q;    /* [njoints] */
+    const double *joint_placement; /* [njoints][12]  R row-major (9) then t (3) */
+    const double *joint_axis;      /* [njoints][3] unit */
+    const int32_t *geom_parent;    /* [ngeoms] parent joint */
+    const int32_t *geom_shape;     /* [ngeoms] */
+    const double *geom_placement;  /* [ngeoms][12] */
+    const double *geom_params;     /* [ngeoms][4] sphere r | box hx hy hz | cyl r hl | capsule r hl */
+    const int32_t *geom_vert_off;  /* [ngeoms] */
+    const int32_t *geom_vert_cnt;  /* [ngeoms] */
+    const double *geom_bsphere;    /* [ngeoms][4] bounding sphere cx cy cz r in geometry frame */
+    const double *verts;           /* [nverts][3] */
+    const int32_t *pairs;          /* [npairs][2] */
+} oracle_model;
+
+typedef struct {
+    int64_t pair_tests;    /* pairs that reached the narrowphase */
+    int64_t gjk_iters;     /* total GJK iterations */
+    int64_t support_calls; /* total single-shape support evaluations */
+    int64_t support_verts; /* total hull vertices scanned by support evaluations */
+    int64_t culled;        /* pairs rejected by the bounding-sphere test */
+} oracle_counters;
+
+/* ------------------------------------------------------------------ small vector helpers */
+static inline double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static inline void sub3(const double *a, const double *b, double *o) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
+static inline void cross3(const double *a, const double *b, double *o) {
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+/* T = [R(9) | t(3)] */
+static void se3_mul(const double *A, const double *B, double *C) {
+    double tmp[12];
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++)
+            tmp[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+        tmp[9 + i] = A[3 * i] * B[9] + A[3 * i + 1] * B[10] + A[3 * i + 2] * B[11] + A[9 + i];
+    }
+    memcpy(C, tmp, sizeof tmp);
+}
+static void se3_identity(double *T) { memset(T, 0, 12 * sizeof(double)); T[0] = T[4] = T[8] = 1.0; }
+
+static void joint_motion(int type, const double *ax, double q, double *T) {
+    se3_identity(T);
+    if (type == JT_REVOLUTE) {
+        double c = cos(q), s = sin(q), C = 1.0 - c, x = ax[0], y = ax[1], z = ax[2];
+        T[0] = c + x * x * C;     T[1] = x * y * C - z * s; T[2] = x * z * C + y * s;
+        T[3] = y * x * C + z * s; T[4] = c + y * y * C;     T[5] = y * z * C - x * s;
+        T[6] = z * x * C - y * s; T[7] = z * y * C + x * s; T[8] = c + z * z * C;
+    } else if (type == JT_PRISMATIC) {
+        T[9] = ax[0] * q; T[10] = ax[1] * q; T[11] = ax[2] * q;
+    }
+}
+
+/* Forward kinematics + geometry placement.  oMi [njoints][12], oMg [ngeoms][12]. */
+void oracle_fk(const oracle_model *m, const double *q, double *oMi, double *oMg) {
+    se3_identity(oMi);
+    for (int j = 1; j < m->njoints; j++) {
+        double Tj[12], tmp[12];
+        joint_motion(m->joint_type[j], m->joint_axis + 3 * j, q[m->joint_idx_q[j]], Tj);
+        se3_mul(oMi + 12 * m->joint_parent[j], m->joint_placement + 12 * j, tmp);
+        se3_mul(tmp, Tj, oMi + 12 * j);
+    }
+    for (int g = 0; g < m->ngeoms; g++)
+        se3_mul(oMi + 12 * m->geom_parent[g], m->geom_placement + 12 * g, oMg + 12 * g);
+}
+
+/* ------------------------------------------------------------------ support functions */
+typedef struct {
+    int shape;
+    const double *par;
+    const double *verts;
+    int nverts;
+    const double *T; /* world placement */
+    double radius;   /* sphere / capsule inflation handled outside GJK */
+} shape_t;
+
+static void support_local(const shape_t *s, const double *d, double *out, oracle_counters *cnt) {
+    cnt->support_calls++;
+    switch (s->shape) {
+    case SH_SPHERE:
+        out[0] = out[1] = out[2] = 0.0;
+        break;
+    case SH_CAPSULE:
+        out[0] = out[1] = 0.0;
+        out[2] = d[2] >= 0.0 ? s->par[1] : -s->par[1];
+        break;
+    case SH_BOX:
+        for (int i = 0; i < 3; i++) out[i] = d[i] >= 0.0 ? s->par[i] : -s->par[i];
+        break;
+    case SH_CYLINDER: {
+        double n = sqrt(d[0] * d[0] + d[1] * d[1]);
+        if (n > 0.0) { out[0] = s->par[0] * d[0] / n; out[1] = s->par[0] * d[1] / n; }
+        else { out[0] = out[1] = 0.0; }
+        out[2] = d[2] >= 0.0 ? s->par[1] : -s->par[1];
+        break;
+    }
+    default: {
+        int best = 0;
+        double bd = -INFINITY;
+        for (int i = 0; i < s->nverts; i++) {
+            double v = dot3(s->verts + 3 * i, d);
+            if (v > bd) { bd = v; best = i; }
+        }
+        cnt->support_verts += s->nverts;
+        memcpy(out, s->verts + 3 * best, 3 * sizeof(double));
+    }
+    }
+}
+
+static void support_world(const shape_t *s, const double *d, double *out, oracle_counters *cnt) {
+    const double *R = s->T;
+    double dl[3] = {R[0] * d[0] + R[3] * d[1] + R[6] * d[2], R[1] * d[0] + R[4] * d[1] + R[7] * d[2],
+                    R[2] * d[0] + R[5] * d[1] + R[8] * d[2]};
+    double p[3];
+    support_local(s, dl, p, cnt);
+    for (int i = 0; i < 3; i++) out[i] = R[3 * i] * p[0] + R[3 * i + 1] * p[1] + R[3 * i + 2] * p[2] + R[9 + i];
+}
+
+/* ------------------------------------------------------------------ simplex closest point */
+typedef struct {
+    double w[4][3], a[4][3], b[4][3];
+    double lam[4];
+    int n;
+} simplex_t;
+
+static void simplex_keep(simplex_t *s, const int *idx, const double *lam, int n) {
+    simplex_t t = *s;
+    for (int i = 0; i < n; i++) {
+        memcpy(s->w[i], t.w[idx[i]], sizeof s->w[i]);
+        memcpy(s->a[i], t.a[idx[i]], sizeof s->a[i]);
+        memcpy(s->b[i], t.b[idx[i]], sizeof s->b[i]);
+        s->lam[i] = lam[i];
+    }
+    s->n = n;
+}
+
+/* closest point to the origin on segment (A,B): barycentric (u,v) */
+static void closest_segment(const double *A, const double *B, double *lam, int *mask) {
+    double ab[3];
+    sub3(B, A, ab);
+    double den = dot3(ab, ab);
+    double t = den > 0.0 ? -dot3(A, ab) / den : 0.0;
+    if (t <= 0.0) { lam[0] = 1.0; lam[1] = 0.0; *mask = 1; }
+    else if (t >= 1.0) { lam[0] = 0.0; lam[1] = 1.0; *mask = 2; }
+    else { lam[0] = 1.0 - t; lam[1] = t; *mask = 3; }
+}
+
+/* closest point to the origin on triangle (A,B,C) (Voronoi-region walk); mask = used verts */
+static void closest_triangle(const double *A, const double *B, const double *C, double *lam, int *mask) {
+    double ab[3], ac[3], ap[3], bp[3], cp[3];
+    sub3(B, A, ab); sub3(C, A, ac);
+    for (int i = 0; i < 3; i++) { ap[i] = -A[i]; bp[i] = -B[i]; cp[i] = -C[i]; }
+    double d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+    if (d1 <= 0.0 && d2 <= 0.0) { lam[0] = 1; lam[1] = 0; lam[2] = 0; *mask = 1; return; }
+    double d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+    if (d3 >= 0.0 && d4 <= d3) { lam[0] = 0; lam[1] = 1; lam[2] = 0; *mask = 2; return; }
+    double vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) {
+        double v = d1 / (d1 - d3);
+        lam[0] = 1 - v; lam[1] = v; lam[2] = 0; *mask = 3; return;
+    }
+    double d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+    if (d6 >= 0.0 && d5 <= d6) { lam[0] = 0; lam[1] = 0; lam[2] = 1; *mask = 4; return; }
+    double vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) {
+        double w = d2 / (d2 - d6);
+        lam[0] = 1 - w; lam[1] = 0; lam[2] = w; *mask = 5; return;
+    }
+    double va = d3 * d6 - d5 * d4;
+    if (va <= 0.0 && (d4 - d3) >= 0.0 && (d5 - d6) >= 0.0) {
+        double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        lam[0] = 0; lam[1] = 1 - w; lam[2] = w; *mask = 6; return;
+    }
+    double den = 1.0 / (va + vb + vc);
+    lam[1] = vb * den; lam[2] = vc * den; lam[0] = 1.0 - lam[1] - lam[2]; *mask = 7;
+}
+
+/* Reduce the simplex to the face closest to the origin; v = closest point.
+ * Returns 1 when the origin is inside a tetrahedron (shapes intersect). */
+static int simplex_closest(simplex_t *s, double *v) {
+    double lam[4];
+    int idx[4], n = 0;
+    if (s->n == 1) {
+        lam[0] = 1.0; idx[0] = 0; n = 1;
+    } else if (s->n == 2) {
+        int mask; double l2[2];
+        closest_segment(s->w[0], s->w[1], l2, &mask);
+        for (int i = 0; i < 2; i++) if (mask & (1 << i)) { idx[n] = i; lam[n++] = l2[i]; }
+    } else if (s->n == 3) {
+        int mask; double l3[3];
+        closest_triangle(s->w[0], s->w[1], s->w[2], l3, &mask);
+        for (int i = 0; i < 3; i++) if (mask & (1 << i)) { idx[n] = i; lam[n++] = l3[i]; }
+    } else {
+        /* tetrahedron: test the origin against each face's outward side */
+        static const int F[4][4] = {{0, 1, 2, 3}, {0, 1, 3, 2}, {0, 2, 3, 1}, {1, 2, 3, 0}};
+        double best = INFINITY, bl[3] = {0, 0, 0};
+        int bmask = 0, bf = -1, outside_any = 0;
+        for (int f = 0; f < 4; f++) {
+            const double *A = s->w[F[f][0]], *B = s->w[F[f][1]], *C = s->w[F[f][2]], *D = s->w[F[f][3]];
+            double ab[3], ac[3], nrm[3], ad[3];
+            sub3(B, A, ab); sub3(C, A, ac); cross3(ab, ac, nrm); sub3(D, A, ad);
+            double sd = dot3(nrm, ad);      /* side of the opposite vertex */
+            double so = -dot3(nrm, A);      /* side of the origin */
+            int outside = (sd > 0.0) ? (so < 0.0) : (sd < 0.0 ? (so > 0.0) : 1);
+            if (!outside) continue;
+            outside_any = 1;
+            double l3[3]; int mask;
+            closest_triangle(A, B, C, l3, &mask);
+            double p[3];
+            for (int i = 0; i < 3; i++) p[i] = l3[0] * A[i] + l3[1] * B[i] + l3[2] * C[i];
+            double d2 = dot3(p, p);
+            if (d2 < best) { best = d2; bf = f; bmask = mask; memcpy(bl, l3, sizeof bl); }
+        }
+        if (!outside_any) {
+            /* barycentric coordinates of the origin in the tetrahedron (for the certificate) */
+            double vol[4], tot = 0.0;
+            for (int f = 0; f < 4; f++) {
+                const double *A = s->w[F[f][0]], *B = s->w[F[f][1]], *C = s->w[F[f][2]];
+                double bc[3];
+                cross3(B, C, bc);
+                vol[F[f][3]] = fabs(dot3(A, bc));
+                tot += vol[F[f][3]];
+            }
+            for (int i = 0; i < 4; i++) s->lam[i] = tot > 0.0 ? vol[i] / tot : 0.25;
+            v[0] = v[1] = v[2] = 0.0;
+            return 1;
+        }
+        for (int i = 0; i < 3; i++) if (bmask & (1 << i)) { idx[n] = F[bf][i]; lam[n++] = bl[i]; }
+    }
+    simplex_keep(s, idx, lam, n);
+    for (int k = 0; k < 3; k++) {
+        v[k] = 0.0;
+        for (int i = 0; i < s->n; i++) v[k] += s->lam[i] * s->w[i][k];
+    }
+    return 0;
+}
+
+#define ORACLE_GJK_MAX_ITERS 2000
+#define ORACLE_GJK_TOL 1e-11
+
+/* Distance between the *cores* of two shapes; returns 0 and intersect=1 when cores overlap.
+ * pa/pb: witness points on core A / core B (equal when intersecting). */
+static double gjk_core_distance(const shape_t *A, const shape_t *B, double *pa, double *pb, int *intersect,
+                                oracle_counters *cnt) {
+    simplex_t s;
+    s.n = 0;
+    double v[3] = {A->T[9] - B->T[9], A->T[10] - B->T[10], A->T[11] - B->T[11]};
+    if (dot3(v, v) == 0.0) { v[0] = 1.0; }
+    *intersect = 0;
+    for (int it = 0; it < ORACLE_GJK_MAX_ITERS; it++) {
+        cnt->gjk_iters++;
+        double d[3] = {-v[0], -v[1], -v[2]}, sa[3], sb[3], w[3];
+        support_world(A, d, sa, cnt);
+        support_world(B, v, sb, cnt);
+        sub3(sa, sb, w);
+        double vv = dot3(v, v), vw = dot3(v, w);
+        if (s.n > 0) {
+            if (vv - vw <= ORACLE_GJK_TOL * sqrt(vv)) break; /* ub - lb <= tol */
+            int dup = 0;
+            for (int i = 0; i < s.n; i++)
+                if (s.w[i][0] == w[0] && s.w[i][1] == w[1] && s.w[i][2] == w[2]) dup = 1;
+            if (dup) break;
+        }
+        memcpy(s.w[s.n], w, sizeof w); memcpy(s.a[s.n], sa, sizeof sa); memcpy(s.b[s.n], sb, sizeof sb);
+        s.n++;
+        if (simplex_closest(&s, v)) { *intersect = 1; break; }
+        if (dot3(v, v) <= 1e-28) { *intersect = 1; break; }
+    }
+    for (int k = 0; k < 3; k++) {
+        pa[k] = pb[k] = 0.0;
+        for (int i = 0; i < s.n; i++) { pa[k] += s.lam[i] * s.a[i][k]; pb[k] += s.lam[i] * s.b[i][k]; }
+    }
+    if (*intersect) return 0.0;
+    return sqrt(dot3(v, v));
+}
+
+static void make_shape(const oracle_model *m, int g, const double *oMg, shape_t *s) {
+    s->shape = m->geom_shape[g];
+    s->par = m->geom_params + 4 * g;
+    s->verts = m->verts + 3 * m->geom_vert_off[g];
+    s->nverts = m->geom_vert_cnt[g];
+    s->T = oMg + 12 * g;
+    s->radius = (s->shape == SH_SPHERE || s->shape == SH_CAPSULE) ? s->par[0] : 0.0;
+}
+
+/* Distance between geometries ga and gb (>= 0; 0 when they touch or overlap).
+ * out[0..2] witness on A, out[3..5] witness on B (world frame), out[6] = 1 if intersecting. */
+double oracle_pair_distance(const oracle_model *m, const double *oMg, int ga, int gb, double *out,
+                            oracle_counters *cnt) {
+    shape_t A, B;
+    oracle_counters local = {0};
+    if (!cnt) cnt = &local;
+    make_shape(m, ga, oMg, &A);
+    make_shape(m, gb, oMg, &B);
+    cnt->pair_tests++;
+    double pa[3], pb[3];
+    int inter;
+    double dc = gjk_core_distance(&A, &B, pa, pb, &inter, cnt);
+    double r = A.radius + B.radius;
+    double dist;
+    if (inter || dc <= r) {
+        dist = 0.0;
+        inter = 1;
+        if (dc > 0.0 && !isnan(dc)) {
+            /* cores apart but inflated shapes overlap: any point of the overlap works as witness */
+            double t = A.radius / (r > 0.0 ? r : 1.0); /* |p-pa| = dc*rA/r <= rA, |p-pb| = dc*rB/r <= rB */
+            for (int k = 0; k < 3; k++) { double c = pa[k] + (pb[k] - pa[k]) * t; pa[k] = pb[k] = c; }
+        }
+    } else {
+        dist = dc - r;
+        double n[3] = {(pb[0] - pa[0]) / dc, (pb[1] - pa[1]) / dc, (pb[2] - pa[2]) / dc};
+        for (int k = 0; k < 3; k++) { pa[k] += A.radius * n[k]; pb[k] -= B.radius * n[k]; }
+    }
+    if (out) {
+        memcpy(out, pa, 3 * sizeof(double)); memcpy(out + 3, pb, 3 * sizeof(double));
+        out[6] = inter ? 1.0 : 0.0;
+    }
+    return dist;
+}
+
+static int sphere_cull(const oracle_model *m, const double *oMg, int ga, int gb, double margin) {
+    double ca[3], cb[3];
+    const double *Ta = oMg + 12 * ga, *Tb = oMg + 12 * gb, *sa = m->geom_bsphere + 4 * ga, *sb = m->geom_bsphere + 4 * gb;
+    for (int i = 0; i < 3; i++) {
+        ca[i] = Ta[3 * i] * sa[0] + Ta[3 * i + 1] * sa[1] + Ta[3 * i + 2] * sa[2] + Ta[9 + i];
+        cb[i] = Tb[3 * i] * sb[0] + Tb[3 * i + 1] * sb[1] + Tb[3 * i + 2] * sb[2] + Tb[9 + i];
+    }
+    double d[3];
+    sub3(ca, cb, d);
+    double r = sa[3] + sb[3] + margin + 1e-9;
+    return dot3(d, d) > r * r;
+}
+
+/* One configuration.  Returns hit (0/1).  Restates computeCollisions(..., stop_at_first) +
+ * np.any(isCollision) (reference core/utils.py:48-51).  When want_all != 0 every pair is
+ * evaluated (as computeDistances does, core/utils.py:86) and *min_dist is the min over pairs.
+ * first_pair = index of the first colliding pair in list order, or -1.
+ * use_cull: skip pairs whose bounding spheres are farther apart than `padding` (cannot change
+ * the verdict; min_dist then is min over the un-culled pairs and the cull lower bounds). */
+int oracle_check_state(const oracle_model *m, const double *q, double padding, int want_all, int use_cull,
+                       double *min_dist, int32_t *first_pair, double *oMi_scratch, double *oMg_scratch,
+                       oracle_counters *cnt) {
+    oracle_fk(m, q, oMi_scratch, oMg_scratch);
+    int hit = 0;
+    double md = INFINITY;
+    int fp = -1;
+    for (int k = 0; k < m->npairs; k++) {
+        int ga = m->pairs[2 * k], gb = m->pairs[2 * k + 1];
+        if (use_cull && !want_all && sphere_cull(m, oMg_scratch, ga, gb, padding)) { cnt->culled++; continue; }
+        if (use_cull && want_all && md < INFINITY && sphere_cull(m, oMg_scratch, ga, gb, md)) { cnt->culled++; continue; }
+        double d = oracle_pair_distance(m, oMg_scratch, ga, gb, NULL, cnt);
+        if (d < md) md = d;
+        if (d <= padding) {
+            if (fp < 0) fp = k;
+            hit = 1;
+            if (!want_all) break;
+        }
+    }
+    if (min_dist) *min_dist = md;
+    if (first_pair) *first_pair = fp;
+    return hit;
+}
+
+/* ------------------------------------------------------------------ pthread parallel-for */
+typedef void (*chunk_fn)(void *ctx, int64_t begin, int64_t end, oracle_counters *cnt, int64_t *aux);
+typedef struct {
+    chunk_fn fn; void *ctx; int64_t n, chunk; atomic_llong *next;
+    oracle_counters cnt; int64_t aux;
+} worker_t;
+
+static void *worker_main(void *arg) {
+    worker_t *w = (worker_t *)arg;
+    for (;;) {
+        int64_t b = atomic_fetch_add(w->next, w->chunk);
+        if (b >= w->n) break;
+        int64_t e = b + w->chunk < w->n ? b + w->chunk : w->n;
+        w->fn(w->ctx, b, e, &w->cnt, &w->aux);
+    }
+    return NULL;
+}
+
+int oracle_num_threads(void) {
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n > 0 ? (int)n : 1;
+}
+
+static void parallel_for(int64_t n, int64_t chunk, int nthreads, chunk_fn fn, void *ctx, oracle_counters *total,
+                         int64_t *aux_total) {
+    if (nthreads <= 0) nthreads = oracle_num_threads();
+    if (nthreads > 256) nthreads = 256;
+    atomic_llong next = 0;
+    worker_t w[256];
+    pthread_t th[256];
+    for (int t = 0; t < nthreads; t++) {
+        memset(&w[t], 0, sizeof w[t]);
+        w[t].fn = fn; w[t].ctx = ctx; w[t].n = n; w[t].chunk = chunk; w[t].next = &next;
+    }
+    for (int t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, worker_main, &w[t]);
+    worker_main(&w[0]);
+    for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
+    oracle_counters sum = {0};
+    int64_t aux = 0;
+    for (int t = 0; t < nthreads; t++) {
+        sum.pair_tests += w[t].cnt.pair_tests; sum.gjk_iters += w[t].cnt.gjk_iters;
+        sum.support_calls += w[t].cnt.support_calls; sum.support_verts += w[t].cnt.support_verts;
+        sum.culled += w[t].cnt.culled; aux += w[t].aux;
+    }
+    if (total) *total = sum;
+    if (aux_total) *aux_total = aux;
+}
+
+typedef struct {
+    const oracle_model *m; const double *q; double padding; int want_all, use_cull;
+    uint8_t *hit; double *min_dist; int32_t *first_pair;
+} states_ctx;
+
+static void states_chunk(void *vctx, int64_t b, int64_t e, oracle_counters *cnt, int64_t *aux) {
+    states_ctx *c = (states_ctx *)vctx;
+    const oracle_model *m = c->m;
+    (void)aux;
+    double *oMi = malloc(sizeof(double) * 12 * m->njoints), *oMg = malloc(sizeof(double) * 12 * m->ngeoms);
+    for (int64_t i = b; i < e; i++) {
+        double md;
+        int32_t fp;
+        c->hit[i] = (uint8_t)oracle_check_state(m, c->q + i * m->nq, c->padding, c->want_all, c->use_cull, &md, &fp,
+                                                oMi, oMg, cnt);
+        if (c->min_dist) c->min_dist[i] = md;
+        if (c->first_pair) c->first_pair[i] = fp;
+    }
+    free(oMi); free(oMg);
+}
+
+/* Batch of configurations, nthreads host threads (<= 0: all online cores). */
+void oracle_check_states(const oracle_model *m, const double *q, int64_t n, double padding, int want_all,
+                         int use_cull, int nthreads, uint8_t *hit, double *min_dist, int32_t *first_pair,
+                         oracle_counters *total) {
+    states_ctx c = {m, q, padding, want_all, use_cull, hit, min_dist, first_pair};
+    parallel_for(n, 256, nthreads, states_chunk, &c, total, NULL);
+}
+
+/* Number of samples of one discretised segment: ceil(||dq|| / step) + 1
+ * (reference planning/utils.py:137). */
+int64_t oracle_segment_samples(const double *q1, const double *q2, int nq, double step) {
+    double s = 0.0;
+    for (int i = 0; i < nq; i++) { double d = q2[i] - q1[i]; s += d * d; }
+    return (int64_t)ceil(sqrt(s) / step) + 1;
+}
+
+/* Write the samples of one segment: q1 + linspace(0,1,n)[i] * (q2 - q1)
+ * (reference planning/utils.py:138-139; numpy.linspace: i * (1/(n-1)), last sample = 1.0). */
+void oracle_discretize_segment(const double *q1, const double *q2, int nq, int64_t n, double *out) {
+    double step = n > 1 ? 1.0 / (double)(n - 1) : 0.0;
+    for (int64_t i = 0; i < n; i++) {
+        double s = (n > 1 && i == n - 1) ? 1.0 : (double)i * step;
+        for (int k = 0; k < nq; k++) out[i * nq + k] = q1[k] + s * (q2[k] - q1[k]);
+    }
+}
+
+typedef struct {
+    const oracle_model *m; const double *q1, *q2; double step, padding; int use_cull;
+    uint8_t *hit; int32_t *first_bad;
+} edges_ctx;
+
+static void edges_chunk(void *vctx, int64_t b0, int64_t e0, oracle_counters *cnt, int64_t *evals) {
+    edges_ctx *c = (edges_ctx *)vctx;
+    const oracle_model *m = c->m;
+    double *oMi = malloc(sizeof(double) * 12 * m->njoints), *oMg = malloc(sizeof(double) * 12 * m->ngeoms);
+    double *qs = malloc(sizeof(double) * m->nq);
+    for (int64_t e = b0; e < e0; e++) {
+        const double *a = c->q1 + e * m->nq, *b = c->q2 + e * m->nq;
+        int h = 0;
+        int32_t fb = -1;
+        (*evals)++;
+        if (oracle_check_state(m, b, c->padding, 0, c->use_cull, NULL, NULL, oMi, oMg, cnt)) {
+            h = 1;
+            fb = -2; /* destination itself collides */
+        } else {
+            int64_t n = oracle_segment_samples(a, b, m->nq, c->step);
+            double st = n > 1 ? 1.0 / (double)(n - 1) : 0.0;
+            for (int64_t i = 0; i < n; i++) {
+                double s = (n > 1 && i == n - 1) ? 1.0 : (double)i * st;
+                for (int k = 0; k < m->nq; k++) qs[k] = a[k] + s * (b[k] - a[k]);
+                (*evals)++;
+                if (oracle_check_state(m, qs, c->padding, 0, c->use_cull, NULL, NULL, oMi, oMg, cnt)) {
+                    h = 1; fb = (int32_t)i; break;
+                }
+            }
+        }
+        c->hit[e] = (uint8_t)h;
+        if (c->first_bad) c->first_bad[e] = fb;
+    }
+    free(oMi); free(oMg); free(qs);
+}
+
+/* Edge validity as has_collision_free_path computes it (reference planning/utils.py:89-111):
+ * q2 checked first, then the discretised path sequentially, stopping at the first colliding
+ * state (core/utils.py:125-130).  hit[e] = 1 means the edge is NOT collision free.
+ * states_evaluated counts the states the sequential reference would have evaluated;
+ * first_bad[e] = index of the first colliding sample along the path (-2: q2 itself), -1 if none. */
+void oracle_check_edges(const oracle_model *m, const double *q1, const double *q2, int64_t n_edges, double step,
+                        double padding, int use_cull, int nthreads, uint8_t *hit, int32_t *first_bad,
+                        int64_t *states_evaluated, oracle_counters *total) {
+    edges_ctx c = {m, q1, q2, step, padding, use_cull, hit, first_bad};
+    parallel_for(n_edges, 16, nthreads, edges_chunk, &c, total, states_evaluated);
+}
+
+/* Pre-discretised path, as check_collisions_along_path takes it (reference core/utils.py:90-132). */
+int oracle_check_path(const oracle_model *m, const double *q_path, int64_t n, double padding, int use_cull) {
+    double *oMi = malloc(sizeof(double) * 12 * m->njoints), *oMg = malloc(sizeof(double) * 12 * m->ngeoms);
+    oracle_counters c = {0};
+    int h = 0;
+    for (int64_t i = 0; i < n && !h; i++)
+        h = oracle_check_state(m, q_path + i * m->nq, padding, 0, use_cull, NULL, NULL, oMi, oMg, &c);
+    free(oMi); free(oMg);
+    return h;
+}

@@ -1,0 +1,189 @@
+"""Drop-in for the collision hot path of ``pyroboplan.core.utils``.
+
+Same names, arity and return conventions as /root/reference/src/pyroboplan/core/utils.py; the
+arithmetic runs on the B200 through ``libpbp_engine.so`` (see ``pyroboplan_b200.engine``).
+There is no CPU path: without the CUDA library or a CUDA device these functions raise.
+"""
+
+import numpy as np
+
+from ..model import CollisionPair
+
+
+# ----------------------------------------------------------------------------------------------
+# Pair / geometry bookkeeping (integer work, host side) -- reference core/utils.py:379-475
+# ----------------------------------------------------------------------------------------------
+def get_collision_geometry_ids(model, collision_model, body):
+    """Collision geometry ids for a geometry name or a frame (link) name.
+
+    Reference: core/utils.py:379-413 (geometry name first, then frame -> ``parentFrame`` match).
+    """
+    ids = []
+    gid = collision_model.getGeometryId(body)
+    if gid < collision_model.ngeoms:
+        ids.append(gid)
+    else:
+        fid = model.getFrameId(body)
+        if fid < model.nframes:
+            for i, obj in enumerate(collision_model.geometryObjects):
+                if obj.parentFrame == fid:
+                    ids.append(i)
+    return ids
+
+
+def get_collision_pair_indices_from_bodies(model, collision_model, body_list):
+    """Indices of the active pairs touching any of the bodies. Reference: core/utils.py:416-446."""
+    ids = set()
+    for body in body_list:
+        ids.update(get_collision_geometry_ids(model, collision_model, body))
+    return [
+        k
+        for k, p in enumerate(collision_model.collisionPairs)
+        if p.first in ids or p.second in ids
+    ]
+
+
+def set_collisions(model, collision_model, body1, body2, enable):
+    """Enable/disable all pairs between two bodies. Reference: core/utils.py:449-475."""
+    for id1 in get_collision_geometry_ids(model, collision_model, body1):
+        for id2 in get_collision_geometry_ids(model, collision_model, body2):
+            pair = CollisionPair(id1, id2)
+            if enable:
+                collision_model.addCollisionPair(pair)
+            else:
+                collision_model.removeCollisionPair(pair)
+
+
+# ----------------------------------------------------------------------------------------------
+# Collision queries -- single-state signatures of the reference, executed on the GPU engine
+# ----------------------------------------------------------------------------------------------
+def _engine(model, collision_model):
+    from ..engine import get_engine
+
+    return get_engine(model, collision_model)
+
+
+def check_collisions_at_state(
+    model, collision_model, q, data=None, collision_data=None, distance_padding=0.0
+):
+    """True if ``q`` is in collision (some active pair closer than ``distance_padding``).
+
+    Reference: core/utils.py:8-51.  ``data`` / ``collision_data`` are accepted for signature
+    compatibility and ignored (the engine owns its device workspaces); the padding is a
+    per-call argument, not sticky state.  Zero active pairs -> False (``np.any([])``).
+    """
+    if len(collision_model.collisionPairs) == 0:
+        return np.bool_(False)
+    hit = _engine(model, collision_model).check_states(np.asarray(q, dtype=np.float64).reshape(1, -1), distance_padding)
+    return np.bool_(hit[0])
+
+
+def get_minimum_distance_at_state(model, collision_model, q, data=None, collision_data=None):
+    """Minimum distance over the active pairs (``np.inf`` without pairs; 0 when penetrating).
+
+    Reference: core/utils.py:54-87.
+    """
+    if len(collision_model.collisionPairs) == 0:
+        return np.inf
+    _, dist = _engine(model, collision_model).check_states(
+        np.asarray(q, dtype=np.float64).reshape(1, -1), 0.0, return_distance=True
+    )
+    return float(dist[0])
+
+
+def check_collisions_along_path(
+    model, collision_model, q_path, data=None, collision_data=None, distance_padding=0.0
+):
+    """True if any configuration of the (already discretised) path collides.
+
+    Reference: core/utils.py:90-132 (sequential with early return; same verdict).
+    """
+    if len(q_path) == 0 or len(collision_model.collisionPairs) == 0:
+        return False
+    Q = np.asarray(q_path, dtype=np.float64).reshape(len(q_path), -1)
+    hit = _engine(model, collision_model).check_paths(Q, [0, len(Q)], distance_padding)
+    return bool(hit[0])
+
+
+def configuration_distance(q_start, q_end):
+    """Euclidean joint-space distance. Reference: core/utils.py:135-151."""
+    return np.linalg.norm(q_end - q_start)
+
+
+def get_path_length(q_path):
+    """Sum of segment distances. Reference: core/utils.py:154-171."""
+    total_distance = 0.0
+    for idx in range(1, len(q_path)):
+        total_distance += configuration_distance(q_path[idx - 1], q_path[idx])
+    return total_distance
+
+
+def get_random_state(model, padding=0.0):
+    """Uniform sample in the padded joint limits, drawn from the legacy global ``np.random``
+    stream exactly as the reference does (core/utils.py:174-192), so seeded callers agree."""
+    return np.random.uniform(model.lowerPositionLimit + padding, model.upperPositionLimit - padding)
+
+
+def get_random_collision_free_state(
+    model, collision_model, joint_padding=0.0, distance_padding=0.0, max_tries=100
+):
+    """Rejection sampling, one host draw + one device check per try.
+
+    Reference: core/utils.py:195-229 (prints and returns None after ``max_tries`` failures).
+    """
+    num_tries = 0
+    while num_tries < max_tries:
+        state = get_random_state(model, padding=joint_padding)
+        if not check_collisions_at_state(model, collision_model, state, distance_padding=distance_padding):
+            return state
+        num_tries += 1
+    print(f"Could not generate collision-free state after {max_tries} tries.")
+    return None
+
+
+def check_within_limits(model, q):
+    """Reference: core/utils.py:303-319."""
+    return np.all(q >= model.lowerPositionLimit) and np.all(q <= model.upperPositionLimit)
+
+
+def extract_cartesian_pose(model, target_frame, q, data=None):
+    """Pose of a model frame at ``q`` (device FK). Reference: core/utils.py:322-346."""
+    return extract_cartesian_poses(model, target_frame, [q])[0]
+
+
+def extract_cartesian_poses(model, target_frame, q_vec, data=None):
+    """Poses of a model frame for a list of configurations. Reference: core/utils.py:349-376."""
+    from ..engine import get_engine
+    from ..model import GeometryModel, SE3
+
+    fid = model.getFrameId(target_frame)
+    if fid >= model.nframes:
+        raise ValueError(f"unknown frame {target_frame!r}")
+    holder = getattr(model, "_pbp_fk_holder", None)
+    if holder is None:
+        holder = GeometryModel()
+        model._pbp_fk_holder = holder
+    eng = get_engine(model, holder)
+    Q = np.asarray(q_vec, dtype=np.float64).reshape(len(q_vec), -1)
+    _, _, oMf = eng.fk(Q, joints=False, geoms=False, frames=True)
+    return [SE3(oMf[i, fid, :9].reshape(3, 3).astype(np.float64), oMf[i, fid, 9:].astype(np.float64)) for i in range(len(Q))]
+
+
+# ----------------------------------------------------------------------------------------------
+# Batched siblings (the point of the engine)
+# ----------------------------------------------------------------------------------------------
+def check_collisions_at_states(model, collision_model, Q, distance_padding=0.0, return_distance=False, return_pair=False):
+    """Batched ``check_collisions_at_state``: ``Q`` [N, nq] (numpy or CUDA tensor) -> bool [N]
+    (+ float32 min distance [N], + int32 first colliding pair index [N])."""
+    return _engine(model, collision_model).check_states(Q, distance_padding, return_distance, return_pair)
+
+
+def check_collisions_along_paths(model, collision_model, Q, offsets, distance_padding=0.0):
+    """Batched ``check_collisions_along_path`` over a ragged array of pre-discretised paths."""
+    return _engine(model, collision_model).check_paths(Q, offsets, distance_padding)
+
+
+def sample_collision_free_states(model, collision_model, n, seed=0, joint_padding=0.0, distance_padding=0.0, as_numpy=True):
+    """Batched ``get_random_collision_free_state``: ``n`` free states from a Philox stream keyed
+    by ``seed`` (not the global ``np.random`` stream)."""
+    return _engine(model, collision_model).sample_free_states(n, seed, joint_padding, distance_padding, as_numpy=as_numpy)

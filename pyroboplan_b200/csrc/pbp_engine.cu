@@ -1,0 +1,742 @@
+// libpbp_engine.so -- host side of the C ABI declared in include/pbp_engine.h.
+//
+// Owns the device copy of the compiled model, the per-pair item bins and the scratch used by
+// the chunked broadphase -> narrowphase pipeline.  All launches go to the caller's stream.
+#include <cub/device/device_select.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pbp_kernels.cuh"
+
+using namespace pbp;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                  \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return fail(PBP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceBuffer {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        size_t want = std::max(need, (size_t)256);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return fail(PBP_ERR_ALLOC, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        bytes = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace
+
+struct pbp_engine {
+    int device = 0;
+    int num_sms = 0;
+    int nq = 0, njoints = 0, ngeoms = 0, npairs = 0, nframes = 0, nmoving = 0, nverts_padded = 0;
+    bool small_tables = true;   // joints <= 16 and moving geoms <= 24 -> small local arrays
+    bool verts_in_smem = true;
+    DevModel dm{};
+    DeviceBuffer d_joints, d_geoms, d_pairs, d_order, d_verts, d_qlim, d_frames;
+    // pipeline workspaces
+    int64_t chunk = 0;  // states per broadphase/narrowphase round = bin capacity
+    DeviceBuffer d_bin_group, d_bin_sample, d_bin_T, d_ctrl;
+    DeviceBuffer d_counts, d_desc_group, d_desc_frac, d_desc_sample, d_scratch_i32, d_scratch_u8, d_cub, d_sel;
+    DeviceBuffer d_io_q, d_io_q2, d_io_hit, d_io_f32, d_io_i32;   // staging for the *_host entry points
+    unsigned long long *h_pinned = nullptr;  // small pinned mailbox for device -> host counters
+    size_t smem_bp = 0, smem_np = 0, smem_fk = 0;
+    int np_blocks = 0;
+    pbp_stats stats{};
+};
+
+namespace {
+
+// control block layout (uint32 words): [0, npairs) bin counts, [npairs] tile counter,
+// then two 64-bit counters (level total, emit cursor) at an 8-byte aligned offset.
+inline uint32_t *ctrl_counts(pbp_engine *e) { return e->d_ctrl.as<uint32_t>(); }
+inline uint32_t *ctrl_tile(pbp_engine *e) { return e->d_ctrl.as<uint32_t>() + e->npairs; }
+inline unsigned long long *ctrl_u64(pbp_engine *e, int i) {
+    const size_t off = (((size_t)e->npairs + 1) * 4 + 7) & ~(size_t)7;
+    return reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(e->d_ctrl.p) + off) + i;
+}
+inline size_t ctrl_bytes(const pbp_engine *e) { return ((((size_t)e->npairs + 1) * 4 + 7) & ~(size_t)7) + 32; }
+
+inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+template <int MODE>
+int launch_broadphase(pbp_engine *e, const StateSource &src, int64_t n, float padding, const Outputs &out, const Bins &bins,
+                      cudaStream_t st) {
+    const unsigned grid = grid_for(n, BP_THREADS);
+    if (e->small_tables)
+        k_broadphase<16, 24, MODE><<<grid, BP_THREADS, e->smem_bp, st>>>(e->dm, src, n, padding, out, bins);
+    else
+        k_broadphase<PBP_MAX_JOINTS, PBP_MAX_GEOMS, MODE><<<grid, BP_THREADS, e->smem_bp, st>>>(e->dm, src, n, padding, out, bins);
+    CUDA_TRY(cudaGetLastError());
+    e->stats.kernel_launches++;
+    return 0;
+}
+
+template <int MODE>
+int launch_narrowphase(pbp_engine *e, float padding, const Outputs &out, const Bins &bins, bool has_sample, cudaStream_t st) {
+    if (e->verts_in_smem)
+        k_narrowphase<MODE, true><<<e->np_blocks, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_tile(e), has_sample);
+    else
+        k_narrowphase<MODE, false><<<e->np_blocks, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_tile(e), has_sample);
+    CUDA_TRY(cudaGetLastError());
+    e->stats.kernel_launches++;
+    return 0;
+}
+
+// One broadphase + narrowphase round over n <= chunk states.
+int run_round(pbp_engine *e, int mode, const StateSource &src, int64_t n, float padding, const Outputs &out, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (e->npairs == 0) return 0;  // nothing can collide; outputs were initialised by the caller
+    Bins bins;
+    bins.group = e->d_bin_group.as<int32_t>();
+    bins.sample = e->d_bin_sample.as<int32_t>();
+    bins.T = e->d_bin_T.as<float>();
+    bins.count = ctrl_counts(e);
+    bins.cap = e->chunk;
+    CUDA_TRY(cudaMemsetAsync(e->d_ctrl.p, 0, ((size_t)e->npairs + 1) * 4, st));
+    int rc;
+    const bool has_sample = src.sample != nullptr;
+    if (mode == MODE_BOOL) {
+        if ((rc = launch_broadphase<MODE_BOOL>(e, src, n, padding, out, bins, st))) return rc;
+        if ((rc = launch_narrowphase<MODE_BOOL>(e, padding, out, bins, has_sample, st))) return rc;
+    } else if (mode == MODE_BOOL_ALL) {
+        if ((rc = launch_broadphase<MODE_BOOL_ALL>(e, src, n, padding, out, bins, st))) return rc;
+        if ((rc = launch_narrowphase<MODE_BOOL_ALL>(e, padding, out, bins, has_sample, st))) return rc;
+    } else {
+        if ((rc = launch_broadphase<MODE_DIST>(e, src, n, padding, out, bins, st))) return rc;
+        if ((rc = launch_narrowphase<MODE_DIST>(e, padding, out, bins, has_sample, st))) return rc;
+    }
+    e->stats.states += n;
+    e->stats.chunks++;
+    return 0;
+}
+
+int check_args(pbp_engine *e, const void *a, int64_t n) {
+    if (!e) return fail(PBP_ERR_ARG, "engine is NULL");
+    if (n < 0) return fail(PBP_ERR_ARG, "negative count");
+    if (n > 0 && !a) return fail(PBP_ERR_ARG, "NULL buffer");
+    if (n > (int64_t)INT32_MAX) return fail(PBP_ERR_ARG, "more than 2^31-1 states/edges per call are not supported");
+    return 0;
+}
+
+}  // namespace
+
+// ==========================================================================================
+extern "C" {
+
+const char *pbp_last_error(void) { return g_last_error.c_str(); }
+int pbp_abi_version(void) { return PBP_ABI_VERSION; }
+int pbp_engine_device(const pbp_engine *e) { return e ? e->device : -1; }
+
+int pbp_get_stats(pbp_engine *e, pbp_stats *out, int reset) {
+    if (!e || !out) return fail(PBP_ERR_ARG, "NULL argument");
+    *out = e->stats;
+    if (reset) e->stats = pbp_stats{};
+    return 0;
+}
+
+void pbp_engine_destroy(pbp_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    DeviceBuffer *bufs[] = {&e->d_joints, &e->d_geoms, &e->d_pairs, &e->d_order, &e->d_verts, &e->d_qlim, &e->d_frames,
+                            &e->d_bin_group, &e->d_bin_sample, &e->d_bin_T, &e->d_ctrl, &e->d_counts, &e->d_desc_group,
+                            &e->d_desc_frac, &e->d_desc_sample, &e->d_scratch_i32, &e->d_scratch_u8, &e->d_cub, &e->d_sel,
+                            &e->d_io_q, &e->d_io_q2, &e->d_io_hit, &e->d_io_f32, &e->d_io_i32};
+    for (DeviceBuffer *b : bufs) b->release();
+    if (e->h_pinned) cudaFreeHost(e->h_pinned);
+    delete e;
+}
+
+int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_states, pbp_engine **out) {
+    if (!d || !out) return fail(PBP_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (d->njoints < 1 || d->njoints > PBP_MAX_JOINTS) return fail(PBP_ERR_CAPACITY, "njoints %d outside [1, %d]", d->njoints, PBP_MAX_JOINTS);
+    if (d->ngeoms < 0 || d->ngeoms > PBP_MAX_GEOMS) return fail(PBP_ERR_CAPACITY, "ngeoms %d outside [0, %d]", d->ngeoms, PBP_MAX_GEOMS);
+    if (d->npairs < 0 || d->npairs > PBP_MAX_PAIRS) return fail(PBP_ERR_CAPACITY, "npairs %d outside [0, %d]", d->npairs, PBP_MAX_PAIRS);
+    if (d->nq < 1 || d->nq > PBP_MAX_NQ) return fail(PBP_ERR_CAPACITY, "nq %d outside [1, %d]", d->nq, PBP_MAX_NQ);
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(PBP_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback", cudaGetErrorString(ce));
+    if (device < 0 || device >= ndev) return fail(PBP_ERR_ARG, "device %d out of range [0, %d)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+
+    pbp_engine *e = new pbp_engine();
+    e->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    e->num_sms = prop.multiProcessorCount;
+    e->nq = d->nq; e->njoints = d->njoints; e->ngeoms = d->ngeoms; e->npairs = d->npairs; e->nframes = d->nframes;
+
+    // ---- joints
+    std::vector<DevJoint> joints(d->njoints);
+    for (int j = 0; j < d->njoints; j++) {
+        DevJoint &J = joints[j];
+        memcpy(J.P, d->joint_placement + 12 * j, sizeof J.P);
+        memcpy(J.axis, d->joint_axis + 3 * j, sizeof J.axis);
+        J.parent = d->joint_parent[j];
+        J.type = d->joint_type[j];
+        J.idx_q = d->joint_idx_q[j];
+        J.chain = (j > 0 && J.parent == j - 1) ? 1 : 0;
+        J.axis_code = 0;
+        for (int k = 0; k < 3; k++) {
+            const float a = J.axis[k], b = J.axis[(k + 1) % 3], c = J.axis[(k + 2) % 3];
+            if (fabsf(fabsf(a) - 1.0f) < 1e-7f && b == 0.0f && c == 0.0f) J.axis_code = k + 1;
+        }
+        if (j > 0 && (J.parent < 0 || J.parent >= j)) { delete e; return fail(PBP_ERR_ARG, "joint %d: parent %d not topologically ordered", j, J.parent); }
+        if (j > 0 && (J.idx_q < 0 || J.idx_q >= d->nq)) { delete e; return fail(PBP_ERR_ARG, "joint %d: idx_q %d out of range", j, J.idx_q); }
+    }
+    // ---- geometries (+ padded vertex table)
+    std::vector<DevGeom> geoms(d->ngeoms);
+    std::vector<float4> verts;
+    int nmoving = 0;
+    for (int g = 0; g < d->ngeoms; g++) {
+        DevGeom &G = geoms[g];
+        memset(&G, 0, sizeof G);
+        memcpy(G.P, d->geom_placement + 12 * g, sizeof G.P);
+        memcpy(G.par, d->geom_params + 4 * g, sizeof G.par);
+        memcpy(G.outer, d->geom_outer + 4 * g, sizeof G.outer);
+        memcpy(G.inner, d->geom_inner + 4 * g, sizeof G.inner);
+        G.parent = d->geom_parent[g];
+        G.shape = d->geom_shape[g];
+        if (G.parent < 0 || G.parent >= d->njoints) { delete e; return fail(PBP_ERR_ARG, "geometry %d: bad parent joint", g); }
+        G.identity = 1;
+        for (int i = 0; i < 12; i++) {
+            const float id = (i == 0 || i == 4 || i == 8) ? 1.f : 0.f;
+            if (G.P[i] != id) G.identity = 0;
+        }
+        G.core_radius = (G.shape == PBP_SHAPE_SPHERE || G.shape == PBP_SHAPE_CAPSULE) ? G.par[0] : 0.f;
+        if (G.parent == 0) {
+            G.slot = -1;
+            // static geometry: sphere centres are stored in world coordinates
+            for (int s = 0; s < 2; s++) {
+                float *c = s == 0 ? G.outer : G.inner;
+                float w[3];
+                for (int i = 0; i < 3; i++) w[i] = G.P[3 * i] * c[0] + G.P[3 * i + 1] * c[1] + G.P[3 * i + 2] * c[2] + G.P[9 + i];
+                c[0] = w[0]; c[1] = w[1]; c[2] = w[2];
+            }
+        } else {
+            G.slot = nmoving++;
+        }
+        if (G.shape == PBP_SHAPE_CONVEX) {
+            const int off = d->geom_vert_off[g], cnt = d->geom_vert_cnt[g];
+            if (cnt < 1 || off < 0 || off + cnt > d->nverts) { delete e; return fail(PBP_ERR_ARG, "geometry %d: bad vertex range", g); }
+            G.vert_off = (int)verts.size();
+            for (int i = 0; i < cnt; i++) verts.push_back(make_float4(d->verts[3 * (off + i)], d->verts[3 * (off + i) + 1], d->verts[3 * (off + i) + 2], 0.f));
+            while (verts.size() % 4) verts.push_back(verts.back());
+            G.vert_cnt = (int)verts.size() - G.vert_off;
+        }
+    }
+    if (verts.empty()) verts.push_back(make_float4(0, 0, 0, 0));
+    e->nmoving = nmoving;
+    e->nverts_padded = (int)verts.size();
+    e->small_tables = d->njoints <= 16 && nmoving <= 24;
+    // ---- pairs + bin order (most expensive narrowphase first, for load balance)
+    std::vector<DevPair> pairs(std::max(d->npairs, 1));
+    std::vector<int32_t> order(std::max(d->npairs, 1), 0);
+    std::vector<long> cost(std::max(d->npairs, 1), 0);
+    for (int p = 0; p < d->npairs; p++) {
+        const int a = d->pairs[2 * p], b = d->pairs[2 * p + 1];
+        if (a < 0 || b < 0 || a >= d->ngeoms || b >= d->ngeoms || a == b) { delete e; return fail(PBP_ERR_ARG, "pair %d: bad geometry ids", p); }
+        pairs[p].a = (int16_t)a; pairs[p].b = (int16_t)b; pairs[p]._pad = 0;
+        const int sa = geoms[a].shape, sb = geoms[b].shape;
+        if (sa == PBP_SHAPE_SPHERE && sb == PBP_SHAPE_SPHERE) pairs[p].kind = BP_EXACT_SPHERES;
+        else if (sa == PBP_SHAPE_BOX) pairs[p].kind = BP_BOX_A;
+        else if (sb == PBP_SHAPE_BOX) pairs[p].kind = BP_BOX_B;
+        else pairs[p].kind = BP_SPHERES;
+        cost[p] = 8 + geoms[a].vert_cnt + geoms[b].vert_cnt;
+        order[p] = p;
+    }
+    std::stable_sort(order.begin(), order.begin() + d->npairs, [&](int x, int y) { return cost[x] > cost[y]; });
+
+    auto upload = [&](DeviceBuffer &buf, const void *src, size_t bytes) -> int {
+        int rc = buf.ensure(bytes);
+        if (rc) return rc;
+        cudaError_t er = cudaMemcpy(buf.p, src, bytes, cudaMemcpyHostToDevice);
+        if (er != cudaSuccess) return fail(PBP_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(er));
+        return 0;
+    };
+    std::vector<float> qlim(2 * d->nq);
+    for (int i = 0; i < d->nq; i++) { qlim[i] = d->q_lower ? d->q_lower[i] : 0.f; qlim[d->nq + i] = d->q_upper ? d->q_upper[i] : 0.f; }
+    std::vector<float> frames(std::max(d->nframes, 1) * 13, 0.f);
+    std::vector<int32_t> fparent(std::max(d->nframes, 1), 0);
+    for (int f = 0; f < d->nframes; f++) {
+        fparent[f] = d->frame_parent[f];
+        if (fparent[f] < 0 || fparent[f] >= d->njoints) { delete e; return fail(PBP_ERR_ARG, "frame %d: bad parent joint", f); }
+    }
+    int rc = 0;
+    if ((rc = upload(e->d_joints, joints.data(), joints.size() * sizeof(DevJoint))) ||
+        (rc = upload(e->d_geoms, geoms.data(), std::max<size_t>(geoms.size(), 1) * sizeof(DevGeom))) ||
+        (rc = upload(e->d_pairs, pairs.data(), pairs.size() * sizeof(DevPair))) ||
+        (rc = upload(e->d_order, order.data(), order.size() * sizeof(int32_t))) ||
+        (rc = upload(e->d_verts, verts.data(), verts.size() * sizeof(float4))) ||
+        (rc = upload(e->d_qlim, qlim.data(), qlim.size() * sizeof(float)))) {
+        pbp_engine_destroy(e);
+        return rc;
+    }
+    {
+        // frames: [nframes] int32 parents followed (16-byte aligned) by [nframes][12] placements
+        const size_t poff = (((size_t)std::max(d->nframes, 1) * 4) + 15) & ~(size_t)15;
+        std::vector<unsigned char> blob(poff + (size_t)std::max(d->nframes, 1) * 48, 0);
+        memcpy(blob.data(), fparent.data(), (size_t)std::max(d->nframes, 1) * 4);
+        if (d->nframes > 0) memcpy(blob.data() + poff, d->frame_placement, (size_t)d->nframes * 48);
+        if ((rc = upload(e->d_frames, blob.data(), blob.size()))) { pbp_engine_destroy(e); return rc; }
+        e->dm.frame_parent = e->d_frames.as<int32_t>();
+        e->dm.frame_placement = reinterpret_cast<const float *>(reinterpret_cast<char *>(e->d_frames.p) + poff);
+    }
+    e->dm.nq = d->nq; e->dm.njoints = d->njoints; e->dm.ngeoms = d->ngeoms; e->dm.npairs = d->npairs;
+    e->dm.nverts_padded = e->nverts_padded; e->dm.nframes = d->nframes; e->dm.nmoving = nmoving;
+    e->dm.joints = e->d_joints.as<DevJoint>();
+    e->dm.geoms = e->d_geoms.as<DevGeom>();
+    e->dm.pairs = e->d_pairs.as<DevPair>();
+    e->dm.bin_order = e->d_order.as<int32_t>();
+    e->dm.verts = e->d_verts.as<float4>();
+    e->dm.q_lower = e->d_qlim.as<float>();
+    e->dm.q_upper = e->d_qlim.as<float>() + d->nq;
+
+    // ---- shared memory budgets and launch geometry
+    const size_t tables = (size_t)d->njoints * sizeof(DevJoint) + (size_t)d->ngeoms * sizeof(DevGeom) +
+                          (size_t)((d->npairs + 1) & ~1) * sizeof(DevPair);
+    e->smem_bp = tables + (size_t)BP_THREADS * d->nq * sizeof(float) + 16;
+    e->smem_fk = (size_t)d->njoints * sizeof(DevJoint) + (size_t)d->ngeoms * sizeof(DevGeom);
+    const size_t np_tables = (size_t)d->ngeoms * sizeof(DevGeom) + (size_t)((d->npairs + 1) & ~1) * sizeof(DevPair) +
+                             ((size_t)d->npairs + 1) * 4 + (size_t)std::max(d->npairs, 1) * 4 + 16;
+    const size_t vert_bytes = (size_t)e->nverts_padded * sizeof(float4);
+    e->verts_in_smem = np_tables + vert_bytes <= 96 * 1024;
+    e->smem_np = np_tables + (e->verts_in_smem ? vert_bytes : 0);
+    const size_t max_optin = prop.sharedMemPerBlockOptin;
+    if (e->smem_bp > max_optin || e->smem_np > max_optin) { pbp_engine_destroy(e); return fail(PBP_ERR_CAPACITY, "model tables exceed shared memory (%zu / %zu bytes)", e->smem_bp, e->smem_np); }
+#define SET_SMEM(kern, bytes) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
+    SET_SMEM((k_broadphase<16, 24, MODE_BOOL>), e->smem_bp);
+    SET_SMEM((k_broadphase<16, 24, MODE_BOOL_ALL>), e->smem_bp);
+    SET_SMEM((k_broadphase<16, 24, MODE_DIST>), e->smem_bp);
+    SET_SMEM((k_broadphase<PBP_MAX_JOINTS, PBP_MAX_GEOMS, MODE_BOOL>), e->smem_bp);
+    SET_SMEM((k_broadphase<PBP_MAX_JOINTS, PBP_MAX_GEOMS, MODE_BOOL_ALL>), e->smem_bp);
+    SET_SMEM((k_broadphase<PBP_MAX_JOINTS, PBP_MAX_GEOMS, MODE_DIST>), e->smem_bp);
+    SET_SMEM((k_narrowphase<MODE_BOOL, true>), e->smem_np);
+    SET_SMEM((k_narrowphase<MODE_BOOL_ALL, true>), e->smem_np);
+    SET_SMEM((k_narrowphase<MODE_DIST, true>), e->smem_np);
+    SET_SMEM((k_narrowphase<MODE_BOOL, false>), e->smem_np);
+    SET_SMEM((k_narrowphase<MODE_BOOL_ALL, false>), e->smem_np);
+    SET_SMEM((k_narrowphase<MODE_DIST, false>), e->smem_np);
+#undef SET_SMEM
+    int occ = 1;
+    if (e->verts_in_smem)
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrowphase<MODE_BOOL, true>, NP_THREADS, e->smem_np));
+    else
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrowphase<MODE_BOOL, false>, NP_THREADS, e->smem_np));
+    e->np_blocks = e->num_sms * std::max(occ, 1);
+
+    // ---- bins: one slot per (state of a chunk, pair)
+    const size_t item_bytes = 4 + 4 + 48;
+    int64_t chunk = max_chunk_states > 0 ? max_chunk_states : (int64_t)1 << 20;
+    const size_t budget = (size_t)6 << 30;
+    if (d->npairs > 0) {
+        const int64_t fit = (int64_t)(budget / (item_bytes * (size_t)d->npairs));
+        chunk = std::max<int64_t>(std::min(chunk, fit), 1024);
+    }
+    chunk = (chunk + 255) & ~(int64_t)255;
+    e->chunk = chunk;
+    const size_t slots = (size_t)std::max(d->npairs, 1) * (size_t)chunk;
+    if ((rc = e->d_bin_group.ensure(slots * 4)) || (rc = e->d_bin_sample.ensure(slots * 4)) ||
+        (rc = e->d_bin_T.ensure(slots * 48)) || (rc = e->d_ctrl.ensure(ctrl_bytes(e)))) {
+        pbp_engine_destroy(e);
+        return rc;
+    }
+    CUDA_TRY(cudaMemset(e->d_ctrl.p, 0, ctrl_bytes(e)));
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&e->h_pinned), 64));
+    *out = e;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+int pbp_fk(pbp_engine *e, const float *q_dev, int64_t n, float *oMi_dev, float *oMg_dev, float *oMf_dev, void *stream) {
+    int rc = check_args(e, q_dev, n);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaFuncSetAttribute(k_fk_output<PBP_MAX_JOINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_fk));
+    k_fk_output<PBP_MAX_JOINTS><<<grid_for(n, BP_THREADS), BP_THREADS, e->smem_fk, st>>>(e->dm, q_dev, n, oMi_dev, oMg_dev, oMf_dev);
+    CUDA_TRY(cudaGetLastError());
+    e->stats.kernel_launches++;
+    return 0;
+}
+
+int pbp_check_states(pbp_engine *e, const float *q_dev, int64_t n, float padding, uint8_t *hit_dev, float *min_dist_dev,
+                     int32_t *first_pair_dev, void *stream) {
+    int rc = check_args(e, q_dev, n);
+    if (rc) return rc;
+    if (n > 0 && !hit_dev) return fail(PBP_ERR_ARG, "hit buffer is NULL");
+    if (!(padding >= 0.0f)) return fail(PBP_ERR_ARG, "distance padding must be >= 0 (got %g)", (double)padding);
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(hit_dev, 0, (size_t)n, st));
+    if (min_dist_dev) {
+        k_fill_f32<<<grid_for(n, 256), 256, 0, st>>>(min_dist_dev, n, INFINITY);
+        e->stats.kernel_launches++;
+    }
+    if (first_pair_dev) {
+        k_fill_i32<<<grid_for(n, 256), 256, 0, st>>>(first_pair_dev, n, INT_MAX);
+        e->stats.kernel_launches++;
+    }
+    // min distance wins over first_pair for the mode; both requested -> two passes
+    const int mode = min_dist_dev ? MODE_DIST : (first_pair_dev ? MODE_BOOL_ALL : MODE_BOOL);
+    for (int64_t off = 0; off < n; off += e->chunk) {
+        const int64_t cnt = std::min(e->chunk, n - off);
+        StateSource src{};
+        src.q = q_dev + off * e->nq;
+        src.mode = 0;
+        Outputs out{};
+        out.hit = hit_dev + off;
+        out.min_dist = min_dist_dev ? min_dist_dev + off : nullptr;
+        out.first_pair = (mode == MODE_BOOL_ALL) ? first_pair_dev + off : nullptr;
+        if ((rc = run_round(e, mode, src, cnt, padding, out, st))) return rc;
+        if (min_dist_dev && first_pair_dev) {
+            // second pass for the pair index (scratch hit buffer: verdicts are already final)
+            if ((rc = e->d_scratch_u8.ensure((size_t)e->chunk))) return rc;
+            Outputs o2{};
+            o2.hit = e->d_scratch_u8.as<uint8_t>();
+            o2.first_pair = first_pair_dev + off;
+            if ((rc = run_round(e, MODE_BOOL_ALL, src, cnt, padding, o2, st))) return rc;
+        }
+    }
+    if (first_pair_dev) {
+        k_finalize_index<<<grid_for(n, 256), 256, 0, st>>>(first_pair_dev, n);
+        e->stats.kernel_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int pbp_check_paths(pbp_engine *e, const float *q_dev, const int64_t *path_offsets_dev, int64_t n_paths, int64_t total,
+                    float padding, uint8_t *hit_dev, void *stream) {
+    int rc = check_args(e, hit_dev, n_paths);
+    if (rc) return rc;
+    if ((rc = check_args(e, q_dev, total))) return rc;
+    if (!(padding >= 0.0f)) return fail(PBP_ERR_ARG, "distance padding must be >= 0");
+    if (n_paths == 0) return 0;
+    if (!path_offsets_dev) return fail(PBP_ERR_ARG, "path_offsets is NULL");
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(hit_dev, 0, (size_t)n_paths, st));
+    if (total == 0) return 0;
+    if ((rc = e->d_desc_group.ensure((size_t)total * 4))) return rc;
+    k_path_groups<<<grid_for(total, 256), 256, 0, st>>>(path_offsets_dev, n_paths, total, e->d_desc_group.as<int32_t>(), nullptr);
+    e->stats.kernel_launches++;
+    for (int64_t off = 0; off < total; off += e->chunk) {
+        const int64_t cnt = std::min(e->chunk, total - off);
+        StateSource src{};
+        src.q = q_dev + off * e->nq;
+        src.group = e->d_desc_group.as<int32_t>() + off;
+        src.mode = 0;
+        Outputs out{};
+        out.hit = hit_dev;
+        if ((rc = run_round(e, MODE_BOOL, src, cnt, padding, out, st))) return rc;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int pbp_discretize_counts(pbp_engine *e, const float *q1_dev, const float *q2_dev, int64_t n_edges, double step,
+                          int32_t *counts_dev, void *stream) {
+    int rc = check_args(e, q1_dev, n_edges);
+    if (rc) return rc;
+    if (n_edges > 0 && (!q2_dev || !counts_dev)) return fail(PBP_ERR_ARG, "NULL buffer");
+    if (!(step > 0.0)) return fail(PBP_ERR_ARG, "step must be > 0");
+    if (n_edges == 0) return 0;
+    CUDA_TRY(cudaSetDevice(e->device));
+    k_edge_counts<<<grid_for(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(q1_dev, q2_dev, n_edges, e->nq, step, counts_dev);
+    CUDA_TRY(cudaGetLastError());
+    e->stats.kernel_launches++;
+    return 0;
+}
+
+int pbp_discretize_fill(pbp_engine *e, const float *q1_dev, const float *q2_dev, int64_t n_edges, const int32_t *counts_dev,
+                        const int64_t *offsets_dev, float *q_out_dev, void *stream) {
+    int rc = check_args(e, q1_dev, n_edges);
+    if (rc) return rc;
+    if (n_edges > 0 && (!q2_dev || !counts_dev || !offsets_dev || !q_out_dev)) return fail(PBP_ERR_ARG, "NULL buffer");
+    if (n_edges == 0) return 0;
+    CUDA_TRY(cudaSetDevice(e->device));
+    k_edge_fill<<<grid_for(n_edges * 32, 256), 256, 0, (cudaStream_t)stream>>>(q1_dev, q2_dev, n_edges, e->nq, counts_dev, offsets_dev, q_out_dev);
+    CUDA_TRY(cudaGetLastError());
+    e->stats.kernel_launches++;
+    return 0;
+}
+
+int pbp_check_edges(pbp_engine *e, const float *q1_dev, const float *q2_dev, int64_t n_edges, double step, float padding,
+                    uint8_t *hit_dev, int32_t *first_bad_dev, void *stream) {
+    int rc = check_args(e, q1_dev, n_edges);
+    if (rc) return rc;
+    if (n_edges > 0 && (!q2_dev || !hit_dev)) return fail(PBP_ERR_ARG, "NULL buffer");
+    if (!(step > 0.0)) return fail(PBP_ERR_ARG, "step must be > 0");
+    if (!(padding >= 0.0f)) return fail(PBP_ERR_ARG, "distance padding must be >= 0");
+    if (n_edges == 0) return 0;
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = e->d_counts.ensure((size_t)n_edges * 4))) return rc;
+    int32_t *counts = e->d_counts.as<int32_t>();
+    k_edge_counts<<<grid_for(n_edges, 256), 256, 0, st>>>(q1_dev, q2_dev, n_edges, e->nq, step, counts);
+    e->stats.kernel_launches++;
+    CUDA_TRY(cudaMemsetAsync(hit_dev, 0, (size_t)n_edges, st));
+    if (first_bad_dev) {
+        k_fill_i32<<<grid_for(n_edges, 256), 256, 0, st>>>(first_bad_dev, n_edges, INT_MAX);
+        e->stats.kernel_launches++;
+    }
+    if (e->npairs == 0) {
+        if (first_bad_dev) {
+            k_finalize_index<<<grid_for(n_edges, 256), 256, 0, st>>>(first_bad_dev, n_edges);
+            e->stats.kernel_launches++;
+        }
+        return 0;
+    }
+
+    // Refinement levels.  With first_bad every sample is tested (one level, stride 1).
+    std::vector<LevelSpec> levels;
+    if (first_bad_dev) {
+        levels.push_back(LevelSpec{1, 0, 1});
+    } else {
+        const int top = 128;
+        levels.push_back(LevelSpec{top, 0, 1});
+        for (int s = top / 2; s >= 1; s >>= 1) levels.push_back(LevelSpec{s, 2 * s, 0});
+    }
+    const int mode = first_bad_dev ? MODE_BOOL_ALL : MODE_BOOL;
+    unsigned long long *d_total = ctrl_u64(e, 0), *d_cursor = ctrl_u64(e, 1);
+    for (const LevelSpec &lv : levels) {
+        CUDA_TRY(cudaMemsetAsync(d_total, 0, 16, st));
+        const uint8_t *dead = first_bad_dev ? nullptr : hit_dev;
+        k_level_count<<<grid_for(n_edges, 256), 256, 0, st>>>(counts, dead, n_edges, lv, d_total);
+        e->stats.kernel_launches++;
+        CUDA_TRY(cudaMemcpyAsync(e->h_pinned, d_total, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const int64_t total = (int64_t)e->h_pinned[0];
+        if (total == 0) continue;
+        if ((rc = e->d_desc_group.ensure((size_t)total * 4)) || (rc = e->d_desc_frac.ensure((size_t)total * 4))) return rc;
+        if (first_bad_dev && (rc = e->d_desc_sample.ensure((size_t)total * 4))) return rc;
+        int32_t *dg = e->d_desc_group.as<int32_t>();
+        float *df = e->d_desc_frac.as<float>();
+        int32_t *ds = first_bad_dev ? e->d_desc_sample.as<int32_t>() : nullptr;
+        k_level_emit<<<grid_for(n_edges, 256), 256, 0, st>>>(counts, dead, n_edges, lv, d_cursor, dg, df, ds);
+        e->stats.kernel_launches++;
+        for (int64_t off = 0; off < total; off += e->chunk) {
+            const int64_t cnt = std::min(e->chunk, total - off);
+            StateSource src{};
+            src.q1 = q1_dev; src.q2 = q2_dev;
+            src.group = dg + off; src.frac = df + off; src.sample = ds ? ds + off : nullptr;
+            src.mode = 1;
+            Outputs out{};
+            out.hit = hit_dev;
+            out.first_bad = first_bad_dev;
+            if ((rc = run_round(e, mode, src, cnt, padding, out, st))) return rc;
+        }
+    }
+    if (first_bad_dev) {
+        k_finalize_index<<<grid_for(n_edges, 256), 256, 0, st>>>(first_bad_dev, n_edges);
+        e->stats.kernel_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer entry points: H2D, run, D2H, synchronise
+// ------------------------------------------------------------------------------------------
+int pbp_check_states_host(pbp_engine *e, const float *q_host, int64_t n, float padding, uint8_t *hit_host,
+                          float *min_dist_host, int32_t *first_pair_host) {
+    int rc = check_args(e, q_host, n);
+    if (rc) return rc;
+    if (n > 0 && !hit_host) return fail(PBP_ERR_ARG, "hit buffer is NULL");
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(e->device));
+    if ((rc = e->d_io_q.ensure((size_t)n * e->nq * 4)) || (rc = e->d_io_hit.ensure((size_t)n))) return rc;
+    if (min_dist_host && (rc = e->d_io_f32.ensure((size_t)n * 4))) return rc;
+    if (first_pair_host && (rc = e->d_io_i32.ensure((size_t)n * 4))) return rc;
+    cudaStream_t st = 0;
+    CUDA_TRY(cudaMemcpyAsync(e->d_io_q.p, q_host, (size_t)n * e->nq * 4, cudaMemcpyHostToDevice, st));
+    rc = pbp_check_states(e, e->d_io_q.as<float>(), n, padding, e->d_io_hit.as<uint8_t>(),
+                          min_dist_host ? e->d_io_f32.as<float>() : nullptr,
+                          first_pair_host ? e->d_io_i32.as<int32_t>() : nullptr, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(hit_host, e->d_io_hit.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (min_dist_host) CUDA_TRY(cudaMemcpyAsync(min_dist_host, e->d_io_f32.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (first_pair_host) CUDA_TRY(cudaMemcpyAsync(first_pair_host, e->d_io_i32.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int pbp_check_edges_host(pbp_engine *e, const float *q1_host, const float *q2_host, int64_t n_edges, double step,
+                         float padding, uint8_t *hit_host, int32_t *first_bad_host) {
+    int rc = check_args(e, q1_host, n_edges);
+    if (rc) return rc;
+    if (n_edges > 0 && (!q2_host || !hit_host)) return fail(PBP_ERR_ARG, "NULL buffer");
+    if (n_edges == 0) return 0;
+    CUDA_TRY(cudaSetDevice(e->device));
+    const size_t qb = (size_t)n_edges * e->nq * 4;
+    if ((rc = e->d_io_q.ensure(qb)) || (rc = e->d_io_q2.ensure(qb)) || (rc = e->d_io_hit.ensure((size_t)n_edges))) return rc;
+    if (first_bad_host && (rc = e->d_io_i32.ensure((size_t)n_edges * 4))) return rc;
+    cudaStream_t st = 0;
+    CUDA_TRY(cudaMemcpyAsync(e->d_io_q.p, q1_host, qb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_io_q2.p, q2_host, qb, cudaMemcpyHostToDevice, st));
+    rc = pbp_check_edges(e, e->d_io_q.as<float>(), e->d_io_q2.as<float>(), n_edges, step, padding, e->d_io_hit.as<uint8_t>(),
+                         first_bad_host ? e->d_io_i32.as<int32_t>() : nullptr, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(hit_host, e->d_io_hit.p, (size_t)n_edges, cudaMemcpyDeviceToHost, st));
+    if (first_bad_host) CUDA_TRY(cudaMemcpyAsync(first_bad_host, e->d_io_i32.p, (size_t)n_edges * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// rejection sampling on device
+// ------------------------------------------------------------------------------------------
+namespace {
+
+// Philox4x32-10 (Salmon et al., SC'11), counter = (draw index, coordinate block), key = seed.
+__device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    uint32_t c0 = ctr.x, c1 = ctr.y, c2 = ctr.z, c3 = ctr.w, k0 = key.x, k1 = key.y;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// q[i][k] = lo_k + u * (hi_k - lo_k), u in [0,1) with 24 random bits; draw index = first_draw + i
+__global__ void k_sample_uniform(const float *lower, const float *upper, int nq, float pad, uint64_t seed, uint64_t first_draw,
+                                 int64_t n, float *q) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t draw = first_draw + (uint64_t)i;
+    for (int k0 = 0; k0 < nq; k0 += 4) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)draw, (uint32_t)(draw >> 32), (uint32_t)(k0 >> 2), 0u),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+        for (int k = k0; k < min(k0 + 4, nq); k++) {
+            const float u = (float)(rr[k - k0] >> 8) * (1.0f / 16777216.0f);
+            const float lo = lower[k] + pad, hi = upper[k] - pad;
+            q[i * nq + k] = fmaf(u, hi - lo, lo);
+        }
+    }
+}
+
+__global__ void k_invert_flags(const uint8_t *hit, int64_t n, uint8_t *free_flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) free_flag[i] = hit[i] ? 0 : 1;
+}
+
+__global__ void k_gather_rows(const float *q, const int32_t *rows, int64_t n_rows, int nq, int64_t out_first, int64_t out_cap,
+                              float *q_out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = t / nq;
+    const int k = (int)(t - r * nq);
+    if (r >= n_rows || out_first + r >= out_cap) return;
+    q_out[(out_first + r) * nq + k] = q[(int64_t)rows[r] * nq + k];
+}
+
+__global__ void k_iota_i32(int32_t *p, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int32_t)i;
+}
+
+}  // namespace
+
+extern "C" int pbp_sample_free_states(pbp_engine *e, int64_t n_wanted, uint64_t seed, float joint_padding, float padding,
+                                      int max_rounds, float *q_out_dev, int64_t *n_found_host, int64_t *n_drawn_host,
+                                      void *stream) {
+    int rc = check_args(e, q_out_dev, n_wanted);
+    if (rc) return rc;
+    if (!n_found_host) return fail(PBP_ERR_ARG, "n_found_host is NULL");
+    *n_found_host = 0;
+    if (n_drawn_host) *n_drawn_host = 0;
+    if (n_wanted == 0) return 0;
+    if (max_rounds <= 0) max_rounds = 64;
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t batch = std::min<int64_t>(std::max<int64_t>(n_wanted, 4096), e->chunk);
+    if ((rc = e->d_io_q.ensure((size_t)batch * e->nq * 4)) || (rc = e->d_io_hit.ensure((size_t)batch)) ||
+        (rc = e->d_scratch_u8.ensure((size_t)std::max(batch, e->chunk))) || (rc = e->d_scratch_i32.ensure((size_t)batch * 4)) ||
+        (rc = e->d_sel.ensure((size_t)batch * 4 + 16)))
+        return rc;
+    float *q = e->d_io_q.as<float>();
+    uint8_t *hit = e->d_io_hit.as<uint8_t>();
+    uint8_t *flag = e->d_scratch_u8.as<uint8_t>();
+    int32_t *iota = e->d_scratch_i32.as<int32_t>();
+    int32_t *sel = e->d_sel.as<int32_t>();
+    int *d_nsel = reinterpret_cast<int *>(ctrl_u64(e, 2));
+    k_iota_i32<<<grid_for(batch, 256), 256, 0, st>>>(iota, batch);
+    size_t cub_bytes = 0;
+    cub::DeviceSelect::Flagged(nullptr, cub_bytes, iota, flag, sel, d_nsel, (int)batch, st);
+    if ((rc = e->d_cub.ensure(cub_bytes))) return rc;
+    int64_t found = 0, drawn = 0;
+    for (int round = 0; round < max_rounds && found < n_wanted; round++) {
+        k_sample_uniform<<<grid_for(batch, 256), 256, 0, st>>>(e->dm.q_lower, e->dm.q_upper, e->nq, joint_padding, seed,
+                                                              (uint64_t)drawn, batch, q);
+        e->stats.kernel_launches++;
+        if ((rc = pbp_check_states(e, q, batch, padding, hit, nullptr, nullptr, st))) return rc;
+        k_invert_flags<<<grid_for(batch, 256), 256, 0, st>>>(hit, batch, flag);
+        cub::DeviceSelect::Flagged(e->d_cub.p, cub_bytes, iota, flag, sel, d_nsel, (int)batch, st);
+        e->stats.kernel_launches += 2;
+        CUDA_TRY(cudaMemcpyAsync(e->h_pinned, d_nsel, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const int64_t nsel = (int64_t)(*reinterpret_cast<int *>(e->h_pinned));
+        const int64_t take = std::min(nsel, n_wanted - found);
+        if (take > 0) {
+            k_gather_rows<<<grid_for(take * e->nq, 256), 256, 0, st>>>(q, sel, take, e->nq, found, n_wanted, q_out_dev);
+            e->stats.kernel_launches++;
+        }
+        found += take;
+        drawn += batch;
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    *n_found_host = found;
+    if (n_drawn_host) *n_drawn_host = drawn;
+    return 0;
+}

@@ -1,0 +1,252 @@
+// FP32 GJK on support functions (sphere / box / cylinder / capsule cores, convex hulls).
+//
+// One thread runs one (state, pair) item; all lanes of a warp work on the SAME pair, so the
+// hull vertex loop of the support function reads identical shared-memory addresses in every
+// lane (hardware broadcast, one wavefront per LDS.128, no bank conflicts) and never diverges.
+// Spheres and capsules are handled as core (point / segment) + radius folded into `margin`.
+#pragma once
+#include <float.h>
+
+#include "pbp_model.cuh"
+
+namespace pbp {
+
+struct ShapeRef {
+    int shape;
+    float p0, p1, p2;       // box: half sides | cylinder/capsule: p0 = radius, p1 = half length
+    const float4 *verts;    // convex: padded vertex table (shared memory or global)
+    int nverts;             // multiple of 4
+};
+
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ float3 sub3(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 cross3(float3 a, float3 b) {
+    return make_float3(fmaf(a.y, b.z, -a.z * b.y), fmaf(a.z, b.x, -a.x * b.z), fmaf(a.x, b.y, -a.y * b.x));
+}
+__device__ __forceinline__ float3 madd3(float3 a, float3 d, float t) {
+    return make_float3(fmaf(d.x, t, a.x), fmaf(d.y, t, a.y), fmaf(d.z, t, a.z));
+}
+
+// argmax_i <v_i, d> over a padded vertex table; 4 independent running maxima for ILP.
+__device__ __forceinline__ float3 support_convex(const float4 *__restrict__ v, int n, float3 d) {
+    float b0 = -FLT_MAX, b1 = -FLT_MAX, b2 = -FLT_MAX, b3 = -FLT_MAX;
+    int i0 = 0, i1 = 1, i2 = 2, i3 = 3;
+#pragma unroll 2
+    for (int i = 0; i < n; i += 4) {
+        const float4 p0 = v[i], p1 = v[i + 1], p2 = v[i + 2], p3 = v[i + 3];
+        const float d0 = fmaf(p0.x, d.x, fmaf(p0.y, d.y, p0.z * d.z));
+        const float d1 = fmaf(p1.x, d.x, fmaf(p1.y, d.y, p1.z * d.z));
+        const float d2 = fmaf(p2.x, d.x, fmaf(p2.y, d.y, p2.z * d.z));
+        const float d3 = fmaf(p3.x, d.x, fmaf(p3.y, d.y, p3.z * d.z));
+        if (d0 > b0) { b0 = d0; i0 = i; }
+        if (d1 > b1) { b1 = d1; i1 = i + 1; }
+        if (d2 > b2) { b2 = d2; i2 = i + 2; }
+        if (d3 > b3) { b3 = d3; i3 = i + 3; }
+    }
+    if (b1 > b0) { b0 = b1; i0 = i1; }
+    if (b3 > b2) { b2 = b3; i2 = i3; }
+    if (b2 > b0) { i0 = i2; }
+    const float4 p = v[i0];
+    return make_float3(p.x, p.y, p.z);
+}
+
+__device__ __forceinline__ float3 support_local(const ShapeRef &s, float3 d) {
+    switch (s.shape) {
+    case PBP_SHAPE_SPHERE:
+        return make_float3(0.f, 0.f, 0.f);
+    case PBP_SHAPE_CAPSULE:
+        return make_float3(0.f, 0.f, d.z >= 0.f ? s.p1 : -s.p1);
+    case PBP_SHAPE_BOX:
+        return make_float3(d.x >= 0.f ? s.p0 : -s.p0, d.y >= 0.f ? s.p1 : -s.p1, d.z >= 0.f ? s.p2 : -s.p2);
+    case PBP_SHAPE_CYLINDER: {
+        const float n2 = fmaf(d.x, d.x, d.y * d.y);
+        const float k = n2 > 0.f ? s.p0 * rsqrtf(n2) : 0.f;
+        return make_float3(d.x * k, d.y * k, d.z >= 0.f ? s.p1 : -s.p1);
+    }
+    default:
+        return support_convex(s.verts, s.nverts, d);
+    }
+}
+
+// ---------------------------------------------------------------- simplex sub-algorithms
+// Each returns the point of the sub-simplex closest to the origin in `v` and a bit mask of the
+// vertices that support it (bit i = i-th argument).
+
+__device__ __forceinline__ int closest_on_segment(float3 A, float3 B, float3 &v) {
+    const float3 ab = sub3(B, A);
+    const float den = dot3(ab, ab);
+    const float t = den > 0.f ? -dot3(A, ab) / den : 0.f;
+    if (t <= 0.f) { v = A; return 1; }
+    if (t >= 1.f) { v = B; return 2; }
+    v = madd3(A, ab, t);
+    return 3;
+}
+
+__device__ __forceinline__ int closest_on_triangle(float3 A, float3 B, float3 C, float3 &v) {
+    const float3 ab = sub3(B, A), ac = sub3(C, A);
+    const float d1 = -dot3(ab, A), d2 = -dot3(ac, A);
+    if (d1 <= 0.f && d2 <= 0.f) { v = A; return 1; }
+    const float d3 = -dot3(ab, B), d4 = -dot3(ac, B);
+    if (d3 >= 0.f && d4 <= d3) { v = B; return 2; }
+    const float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) {
+        const float den = d1 - d3;
+        v = madd3(A, ab, den > 0.f ? d1 / den : 0.f);
+        return 3;
+    }
+    const float d5 = -dot3(ab, C), d6 = -dot3(ac, C);
+    if (d6 >= 0.f && d5 <= d6) { v = C; return 4; }
+    const float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) {
+        const float den = d2 - d6;
+        v = madd3(A, ac, den > 0.f ? d2 / den : 0.f);
+        return 5;
+    }
+    const float va = d3 * d6 - d5 * d4;
+    if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
+        const float den = (d4 - d3) + (d5 - d6);
+        v = madd3(B, sub3(C, B), den > 0.f ? (d4 - d3) / den : 0.f);
+        return 6;
+    }
+    // interior: project the origin on the supporting plane (better conditioned in FP32 than
+    // recombining the vertices with barycentric weights)
+    const float3 n = cross3(ab, ac);
+    const float nn = dot3(n, n);
+    if (!(nn > 0.f)) {  // degenerate (collinear) triangle: best of the three edges
+        float3 v1, v2, v3;
+        const int m1 = closest_on_segment(A, B, v1);
+        const int m2 = closest_on_segment(A, C, v2);
+        const int m3 = closest_on_segment(B, C, v3);
+        const float e1 = dot3(v1, v1), e2 = dot3(v2, v2), e3 = dot3(v3, v3);
+        if (e1 <= e2 && e1 <= e3) { v = v1; return m1; }
+        if (e2 <= e3) { v = v2; return (m2 & 1) | ((m2 & 2) << 1); }
+        v = v3;
+        return m3 << 1;
+    }
+    const float k = dot3(A, n) / nn;
+    v = make_float3(n.x * k, n.y * k, n.z * k);
+    return 7;
+}
+
+// Tetrahedron (A,B,C,D).  Returns 0 when the origin is inside (or on) it.
+__device__ __forceinline__ int closest_on_tetrahedron(float3 A, float3 B, float3 C, float3 D, float3 &v) {
+    float best = FLT_MAX;
+    int bmask = 0;
+    float3 bv = make_float3(0.f, 0.f, 0.f);
+    bool any_outside = false;
+    // face f omits vertex f; remap[] lifts the 3-bit triangle mask to the 4-bit tetra mask
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+        const float3 P = f == 0 ? B : A;
+        const float3 Q = f <= 1 ? C : B;
+        const float3 R = f == 3 ? C : D;
+        const float3 O = f == 0 ? A : (f == 1 ? B : (f == 2 ? C : D));
+        const float3 n = cross3(sub3(Q, P), sub3(R, P));
+        const float sd = dot3(n, sub3(O, P));  // side of the omitted vertex
+        const float so = -dot3(n, P);          // side of the origin
+        if (so * sd > 0.f) continue;           // origin strictly on the inner side of this face
+        any_outside = true;
+        float3 tv;
+        const int m = closest_on_triangle(P, Q, R, tv);
+        const float d2 = dot3(tv, tv);
+        if (d2 < best) {
+            best = d2;
+            bv = tv;
+            // triangle vertices (P,Q,R) as tetra indices
+            const int ip = f == 0 ? 1 : 0, iq = f <= 1 ? 2 : 1, ir = f == 3 ? 2 : 3;
+            bmask = ((m & 1) << ip) | (((m >> 1) & 1) << iq) | (((m >> 2) & 1) << ir);
+        }
+    }
+    if (!any_outside) return 0;
+    v = bv;
+    return bmask;
+}
+
+struct GjkOut {
+    float dist;   // distance between the cores (0 when they overlap); in boolean mode only
+                  // meaningful as "<= margin" / "> margin"
+    int hit;      // dist <= margin
+    int iters;
+};
+
+#define PBP_GJK_MAX_ITERS 48
+#define PBP_GJK_TOL 1e-6f       // ub - lb convergence (metres)
+#define PBP_GJK_EPS_ABS2 2.5e-13f  // |v|^2 below this counts as contact (|v| < 5e-7 m)
+
+// T: placement of B in A's frame.  v0: initial search direction (centre of A - centre of B, A frame).
+// WANT_DIST = false: stop as soon as "distance > margin" or "distance <= margin" is certain.
+// WANT_DIST = true : run to convergence unless the pair is certainly farther than `bound`.
+template <bool WANT_DIST>
+__device__ __forceinline__ GjkOut gjk_run(const ShapeRef &A, const ShapeRef &B, const float *T, float3 v, float margin,
+                                          float bound) {
+    GjkOut out;
+    float vv = dot3(v, v);
+    if (!(vv > 1e-12f)) { v = make_float3(1.f, 0.f, 0.f); vv = 1.f; }
+    float3 W0 = make_float3(0, 0, 0), W1 = W0, W2 = W0, W3 = W0;
+    int n = 0;
+    const float m2 = margin * margin;
+    const float cut = WANT_DIST ? bound : margin;
+    const float cut2 = cut * cut;
+    int it = 0;
+    bool enclosed = false;
+    for (; it < PBP_GJK_MAX_ITERS; it++) {
+        // support of (A - B) in direction -v
+        const float3 sa = support_local(A, make_float3(-v.x, -v.y, -v.z));
+        const float3 db = make_float3(fmaf(T[0], v.x, fmaf(T[3], v.y, T[6] * v.z)), fmaf(T[1], v.x, fmaf(T[4], v.y, T[7] * v.z)),
+                                      fmaf(T[2], v.x, fmaf(T[5], v.y, T[8] * v.z)));
+        const float3 sl = support_local(B, db);
+        const float3 sb = se3_act(T, sl.x, sl.y, sl.z);
+        const float3 w = sub3(sa, sb);
+        const float vw = dot3(v, w);
+        // <v,w>/|v| is a lower bound of the distance for ANY direction v
+        if (vw > 0.f && vw * vw > cut2 * vv) {
+            out.dist = vw * rsqrtf(vv);
+            out.hit = 0;
+            out.iters = it + 1;
+            return out;
+        }
+        if (n > 0) {
+            if (vv - vw <= PBP_GJK_TOL * sqrtf(vv)) break;  // v is (numerically) the closest point
+            const bool dup = (w.x == W0.x && w.y == W0.y && w.z == W0.z) ||
+                             (n > 1 && w.x == W1.x && w.y == W1.y && w.z == W1.z) ||
+                             (n > 2 && w.x == W2.x && w.y == W2.y && w.z == W2.z);
+            if (dup) break;
+        }
+        // append w and solve for the closest point of the simplex
+        float3 nv;
+        int mask;
+        if (n == 0) { W0 = w; nv = w; mask = 1; }
+        else if (n == 1) { W1 = w; mask = closest_on_segment(W0, W1, nv); }
+        else if (n == 2) { W2 = w; mask = closest_on_triangle(W0, W1, W2, nv); }
+        else {
+            W3 = w;
+            mask = closest_on_tetrahedron(W0, W1, W2, W3, nv);
+            if (mask == 0) { enclosed = true; break; }
+        }
+        const float nvv = dot3(nv, nv);
+        if (nvv <= PBP_GJK_EPS_ABS2) { enclosed = true; break; }
+        if (!WANT_DIST && nvv <= m2) { v = nv; vv = nvv; break; }      // upper bound already within margin
+        if (n > 0 && nvv >= vv) break;                                 // no progress (rounding): keep previous v
+        v = nv;
+        vv = nvv;
+        // compact the kept vertices to the front (static indices only -> stays in registers)
+#pragma unroll
+        for (int pass = 0; pass < 3; pass++) {
+            if (!(mask & 1) && (mask >> 1)) { W0 = W1; W1 = W2; W2 = W3; mask >>= 1; }
+            if (!(mask & 2) && (mask >> 2)) { W1 = W2; W2 = W3; mask = (mask & 1) | ((mask >> 1) & ~1); }
+            if (!(mask & 4) && (mask >> 3)) { W2 = W3; mask = (mask & 3) | ((mask >> 1) & ~3); }
+        }
+        n = __popc(mask);
+    }
+    out.iters = it + 1;
+    if (enclosed) {
+        out.dist = 0.f;
+        out.hit = 1;
+        return out;
+    }
+    out.dist = sqrtf(vv);
+    out.hit = out.dist <= margin;
+    return out;
+}
+
+}  // namespace pbp

@@ -1,0 +1,400 @@
+"""ctypes binding of ``libpbp_engine.so`` (C ABI in ``include/pbp_engine.h``) + model flattening.
+
+``CollisionEngine`` owns one device-resident compiled model and exposes the batched
+operations of the hot path.  Inputs/outputs are either CUDA ``torch`` tensors (zero-copy, the
+call is asynchronous on torch's current stream) or host ``numpy`` arrays (the ``*_host`` entry
+points copy in, run and copy out).  PyTorch is used only for device memory and streams.
+
+There is no CPU fallback: a missing library or a missing CUDA device raises ``RuntimeError``.
+"""
+
+import ctypes
+import os
+
+import numpy as np
+
+from .model.shapes import Box, Capsule, Convex, Cylinder, Sphere
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpbp_engine.so")
+
+PBP_ABI_VERSION = 1
+
+# symbols declared in include/pbp_engine.h (tests check the library exports every one)
+EXPORTED_SYMBOLS = [
+    "pbp_last_error",
+    "pbp_abi_version",
+    "pbp_engine_create",
+    "pbp_engine_destroy",
+    "pbp_engine_device",
+    "pbp_get_stats",
+    "pbp_fk",
+    "pbp_check_states",
+    "pbp_check_states_host",
+    "pbp_check_edges",
+    "pbp_check_edges_host",
+    "pbp_discretize_counts",
+    "pbp_discretize_fill",
+    "pbp_check_paths",
+    "pbp_sample_free_states",
+]
+
+
+class _ModelDesc(ctypes.Structure):
+    _fields_ = [
+        ("nq", ctypes.c_int32),
+        ("njoints", ctypes.c_int32),
+        ("ngeoms", ctypes.c_int32),
+        ("npairs", ctypes.c_int32),
+        ("nverts", ctypes.c_int32),
+        ("nframes", ctypes.c_int32),
+        ("joint_parent", ctypes.c_void_p),
+        ("joint_type", ctypes.c_void_p),
+        ("joint_idx_q", ctypes.c_void_p),
+        ("joint_placement", ctypes.c_void_p),
+        ("joint_axis", ctypes.c_void_p),
+        ("q_lower", ctypes.c_void_p),
+        ("q_upper", ctypes.c_void_p),
+        ("geom_parent", ctypes.c_void_p),
+        ("geom_shape", ctypes.c_void_p),
+        ("geom_placement", ctypes.c_void_p),
+        ("geom_params", ctypes.c_void_p),
+        ("geom_vert_off", ctypes.c_void_p),
+        ("geom_vert_cnt", ctypes.c_void_p),
+        ("geom_outer", ctypes.c_void_p),
+        ("geom_inner", ctypes.c_void_p),
+        ("verts", ctypes.c_void_p),
+        ("pairs", ctypes.c_void_p),
+        ("frame_parent", ctypes.c_void_p),
+        ("frame_placement", ctypes.c_void_p),
+    ]
+
+
+class _Stats(ctypes.Structure):
+    _fields_ = [
+        ("kernel_launches", ctypes.c_int64),
+        ("states", ctypes.c_int64),
+        ("narrowphase_items", ctypes.c_int64),
+        ("chunks", ctypes.c_int64),
+    ]
+
+
+_lib = None
+
+
+def load_library():
+    """Load ``libpbp_engine.so``; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). pyroboplan_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i64, i32, f32, f64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_double
+    lib.pbp_last_error.restype = ctypes.c_char_p
+    lib.pbp_abi_version.restype = ctypes.c_int
+    lib.pbp_engine_create.argtypes = [ctypes.POINTER(_ModelDesc), i32, i64, ctypes.POINTER(vp)]
+    lib.pbp_engine_destroy.argtypes = [vp]
+    lib.pbp_engine_destroy.restype = None
+    lib.pbp_engine_device.argtypes = [vp]
+    lib.pbp_get_stats.argtypes = [vp, ctypes.POINTER(_Stats), i32]
+    lib.pbp_fk.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.pbp_check_states.argtypes = [vp, vp, i64, f32, vp, vp, vp, vp]
+    lib.pbp_check_states_host.argtypes = [vp, vp, i64, f32, vp, vp, vp]
+    lib.pbp_check_edges.argtypes = [vp, vp, vp, i64, f64, f32, vp, vp, vp]
+    lib.pbp_check_edges_host.argtypes = [vp, vp, vp, i64, f64, f32, vp, vp]
+    lib.pbp_discretize_counts.argtypes = [vp, vp, vp, i64, f64, vp, vp]
+    lib.pbp_discretize_fill.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
+    lib.pbp_check_paths.argtypes = [vp, vp, vp, i64, i64, f32, vp, vp]
+    lib.pbp_sample_free_states.argtypes = [vp, i64, ctypes.c_uint64, f32, f32, i32, vp, ctypes.POINTER(i64), ctypes.POINTER(i64), vp]
+    if lib.pbp_abi_version() != PBP_ABI_VERSION:
+        raise RuntimeError("libpbp_engine.so ABI version mismatch; rebuild it")
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        msg = _lib.pbp_last_error().decode("utf-8", "replace") if _lib else ""
+        raise RuntimeError(f"pbp_engine error {rc}: {msg}")
+
+
+def _se3_row(T):
+    return np.concatenate([np.asarray(T.rotation, dtype=np.float64).reshape(9), np.asarray(T.translation, dtype=np.float64)])
+
+
+def _up32(x):
+    """Smallest float32 >= x (x >= 0)."""
+    y = np.float32(x)
+    return y if float(y) >= x else np.nextafter(y, np.float32(np.inf))
+
+
+def flatten_model(model, collision_model):
+    """Host containers -> dict of contiguous float32 / int32 arrays matching ``pbp_model_desc``.
+
+    Enclosing spheres are rounded outwards and inscribed spheres inwards so the float32
+    broadphase stays conservative.
+    """
+    geoms = collision_model.geometryObjects
+    ng = len(geoms)
+    a = {
+        "joint_parent": np.array(model.parents, dtype=np.int32),
+        "joint_type": np.array([j.type for j in model.joints], dtype=np.int32),
+        "joint_idx_q": np.array([j.idx_q for j in model.joints], dtype=np.int32),
+        "joint_placement": np.array([_se3_row(p) for p in model.jointPlacements], dtype=np.float32),
+        "joint_axis": np.array([j.axis for j in model.joints], dtype=np.float32),
+        "q_lower": np.asarray(model.lowerPositionLimit, dtype=np.float32),
+        "q_upper": np.asarray(model.upperPositionLimit, dtype=np.float32),
+        "geom_parent": np.array([g.parentJoint for g in geoms], dtype=np.int32).reshape(ng),
+        "geom_shape": np.zeros(ng, dtype=np.int32),
+        "geom_placement": np.zeros((ng, 12), dtype=np.float32),
+        "geom_params": np.zeros((ng, 4), dtype=np.float32),
+        "geom_vert_off": np.zeros(ng, dtype=np.int32),
+        "geom_vert_cnt": np.zeros(ng, dtype=np.int32),
+        "geom_outer": np.zeros((ng, 4), dtype=np.float32),
+        "geom_inner": np.zeros((ng, 4), dtype=np.float32),
+    }
+    verts = []
+    nv = 0
+    for i, g in enumerate(geoms):
+        s = g.geometry
+        a["geom_placement"][i] = _se3_row(g.placement)
+        a["geom_shape"][i] = s.shape_type
+        if isinstance(s, Sphere):
+            a["geom_params"][i, 0] = s.radius
+        elif isinstance(s, Box):
+            a["geom_params"][i, :3] = s.halfSide
+        elif isinstance(s, (Cylinder, Capsule)):
+            a["geom_params"][i, :2] = [s.radius, s.halfLength]
+        elif isinstance(s, Convex):
+            pts = np.asarray(s.points, dtype=np.float32)
+            a["geom_vert_off"][i] = nv
+            a["geom_vert_cnt"][i] = len(pts)
+            verts.append(pts)
+            nv += len(pts)
+        else:
+            raise TypeError(f"unsupported collision geometry {type(s).__name__}")
+        oc, orad = s.bounding_sphere()
+        ic, irad = s.inner_sphere()
+        oc32 = np.asarray(oc, dtype=np.float32)
+        ic32 = np.asarray(ic, dtype=np.float32)
+        if isinstance(s, Convex):
+            p64 = np.asarray(s.points, dtype=np.float32).astype(np.float64)
+            orad = float(np.sqrt(((p64 - oc32.astype(np.float64)) ** 2).sum(axis=1).max()))
+        if isinstance(s, (Sphere,)):
+            o32, i32r = np.float32(s.radius), np.float32(s.radius)  # exact pair tests use the true radius
+        else:
+            o32 = _up32(orad * (1.0 + 1e-6) + 1e-7)
+            i32r = np.float32(max(irad - 2e-6 - float(np.linalg.norm(ic32.astype(np.float64) - ic)), 0.0))
+        a["geom_outer"][i] = [*oc32, o32]
+        a["geom_inner"][i] = [*ic32, i32r]
+    a["verts"] = np.concatenate(verts).astype(np.float32) if verts else np.zeros((1, 3), dtype=np.float32)
+    pairs = np.array([[p.first, p.second] for p in collision_model.collisionPairs], dtype=np.int32).reshape(-1, 2)
+    a["pairs"] = pairs if len(pairs) else np.zeros((1, 2), dtype=np.int32)
+    a["frame_parent"] = np.array([f.parentJoint for f in model.frames], dtype=np.int32)
+    a["frame_placement"] = np.array([_se3_row(f.placement) for f in model.frames], dtype=np.float32)
+    sizes = dict(nq=model.nq, njoints=model.njoints, ngeoms=ng, npairs=len(pairs), nverts=nv, nframes=len(model.frames))
+    return {k: np.ascontiguousarray(v) for k, v in a.items()}, sizes
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+class CollisionEngine:
+    """Device-resident compiled (model, collision_model) + batched hot-path operations."""
+
+    def __init__(self, model, collision_model, device=None, max_chunk_states=0):
+        self.lib = load_library()
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("pyroboplan_b200 needs a CUDA device (B200); there is no CPU fallback")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = int(torch.device("cuda", device).index if not isinstance(device, int) else device)
+        self.torch_device = torch.device("cuda", self.device)
+        arrays, sizes = flatten_model(model, collision_model)
+        self._arrays = arrays
+        self.nq, self.njoints, self.ngeoms = sizes["nq"], sizes["njoints"], sizes["ngeoms"]
+        self.npairs, self.nframes = sizes["npairs"], sizes["nframes"]
+        desc = _ModelDesc()
+        for k, v in sizes.items():
+            setattr(desc, k, v)
+        for k, v in arrays.items():
+            setattr(desc, k, v.ctypes.data)
+        handle = ctypes.c_void_p()
+        _check(self.lib.pbp_engine_create(ctypes.byref(desc), self.device, int(max_chunk_states), ctypes.byref(handle)))
+        self._h = handle
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.pbp_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return ctypes.c_void_p(_torch().cuda.current_stream(self.torch_device).cuda_stream)
+
+    def _dev_q(self, Q):
+        torch = _torch()
+        if not (isinstance(Q, torch.Tensor) and Q.is_cuda):
+            raise TypeError("expected a CUDA torch tensor")
+        if Q.device != self.torch_device:
+            raise ValueError(f"tensor on {Q.device}, engine on {self.torch_device}")
+        Q = Q.to(torch.float32).contiguous().reshape(-1, self.nq)
+        return Q
+
+    @staticmethod
+    def _host_q(Q, nq):
+        return np.ascontiguousarray(np.asarray(Q, dtype=np.float32).reshape(-1, nq))
+
+    def _is_dev(self, x):
+        torch = _torch()
+        return isinstance(x, torch.Tensor) and x.is_cuda
+
+    def stats(self, reset=False):
+        s = _Stats()
+        _check(self.lib.pbp_get_stats(self._h, ctypes.byref(s), int(reset)))
+        return {k: int(getattr(s, k)) for k, _ in s._fields_}
+
+    # ------------------------------------------------------------------ FK
+    def fk(self, Q, joints=True, geoms=True, frames=True):
+        """Placements [N, n*, 12] (R row-major, then t) for joints / geometries / frames."""
+        torch = _torch()
+        host = not self._is_dev(Q)
+        Qd = torch.as_tensor(self._host_q(Q, self.nq), device=self.torch_device) if host else self._dev_q(Q)
+        n = Qd.shape[0]
+        mk = lambda cnt, want: torch.empty((n, cnt, 12), dtype=torch.float32, device=self.torch_device) if want else None
+        oMi, oMg, oMf = mk(self.njoints, joints), mk(self.ngeoms, geoms), mk(self.nframes, frames)
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        _check(self.lib.pbp_fk(self._h, ptr(Qd), n, ptr(oMi), ptr(oMg), ptr(oMf), self._stream()))
+        if host:
+            conv = lambda t: t.cpu().numpy() if t is not None else None
+            return conv(oMi), conv(oMg), conv(oMf)
+        return oMi, oMg, oMf
+
+    # ------------------------------------------------------------------ states
+    def check_states(self, Q, padding=0.0, return_distance=False, return_pair=False):
+        """Collision verdict per configuration.
+
+        CUDA tensor in -> CUDA tensors out (bool [N], optionally float32 min distance [N] and
+        int32 first colliding pair [N]); numpy / list in -> numpy out.
+        """
+        torch = _torch()
+        if self._is_dev(Q):
+            Qd = self._dev_q(Q)
+            n = Qd.shape[0]
+            hit = torch.empty(n, dtype=torch.uint8, device=self.torch_device)
+            dist = torch.empty(n, dtype=torch.float32, device=self.torch_device) if return_distance else None
+            pair = torch.empty(n, dtype=torch.int32, device=self.torch_device) if return_pair else None
+            ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+            _check(self.lib.pbp_check_states(self._h, ptr(Qd), n, float(padding), ptr(hit), ptr(dist), ptr(pair), self._stream()))
+            res = [hit.to(torch.bool)]
+        else:
+            Qh = self._host_q(Q, self.nq)
+            n = Qh.shape[0]
+            hit = np.zeros(n, dtype=np.uint8)
+            dist = np.zeros(n, dtype=np.float32) if return_distance else None
+            pair = np.zeros(n, dtype=np.int32) if return_pair else None
+            ptr = lambda t: ctypes.c_void_p(t.ctypes.data) if t is not None else None
+            _check(self.lib.pbp_check_states_host(self._h, ptr(Qh), n, float(padding), ptr(hit), ptr(dist), ptr(pair)))
+            res = [hit.astype(bool)]
+        if return_distance:
+            res.append(dist)
+        if return_pair:
+            res.append(pair)
+        return res[0] if len(res) == 1 else tuple(res)
+
+    # ------------------------------------------------------------------ edges
+    def check_edges(self, Q1, Q2, max_step_size, padding=0.0, return_first_bad=False):
+        """hit[E] = True iff the discretised segment Q1[e] -> Q2[e] has a colliding sample."""
+        torch = _torch()
+        if self._is_dev(Q1):
+            A, B = self._dev_q(Q1), self._dev_q(Q2)
+            n = A.shape[0]
+            hit = torch.empty(n, dtype=torch.uint8, device=self.torch_device)
+            fb = torch.empty(n, dtype=torch.int32, device=self.torch_device) if return_first_bad else None
+            ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+            _check(self.lib.pbp_check_edges(self._h, ptr(A), ptr(B), n, float(max_step_size), float(padding), ptr(hit), ptr(fb), self._stream()))
+            out = hit.to(torch.bool)
+        else:
+            A, B = self._host_q(Q1, self.nq), self._host_q(Q2, self.nq)
+            n = A.shape[0]
+            hit = np.zeros(n, dtype=np.uint8)
+            fb = np.zeros(n, dtype=np.int32) if return_first_bad else None
+            ptr = lambda t: ctypes.c_void_p(t.ctypes.data) if t is not None else None
+            _check(self.lib.pbp_check_edges_host(self._h, ptr(A), ptr(B), n, float(max_step_size), float(padding), ptr(hit), ptr(fb)))
+            out = hit.astype(bool)
+        return (out, fb) if return_first_bad else out
+
+    def check_paths(self, Q, offsets, padding=0.0):
+        """Ragged batch of pre-discretised paths: samples Q[offsets[p]:offsets[p+1]] form path p."""
+        torch = _torch()
+        host = not self._is_dev(Q)
+        Qd = torch.as_tensor(self._host_q(Q, self.nq), device=self.torch_device) if host else self._dev_q(Q)
+        off = torch.as_tensor(np.asarray(offsets, dtype=np.int64) if not isinstance(offsets, torch.Tensor) else offsets,
+                              device=self.torch_device).to(torch.int64).contiguous()
+        n_paths = off.numel() - 1
+        hit = torch.empty(max(n_paths, 0), dtype=torch.uint8, device=self.torch_device)
+        if n_paths > 0:
+            _check(self.lib.pbp_check_paths(self._h, ctypes.c_void_p(Qd.data_ptr()), ctypes.c_void_p(off.data_ptr()), n_paths,
+                                            Qd.shape[0], float(padding), ctypes.c_void_p(hit.data_ptr()), self._stream()))
+        out = hit.to(torch.bool)
+        return out.cpu().numpy() if host else out
+
+    def discretize(self, Q1, Q2, max_step_size):
+        """(counts [E] int32, offsets [E+1] int64, states [sum(counts), nq]) on the input's side."""
+        torch = _torch()
+        host = not self._is_dev(Q1)
+        A = torch.as_tensor(self._host_q(Q1, self.nq), device=self.torch_device) if host else self._dev_q(Q1)
+        B = torch.as_tensor(self._host_q(Q2, self.nq), device=self.torch_device) if host else self._dev_q(Q2)
+        n = A.shape[0]
+        counts = torch.empty(n, dtype=torch.int32, device=self.torch_device)
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        _check(self.lib.pbp_discretize_counts(self._h, ptr(A), ptr(B), n, float(max_step_size), ptr(counts), self._stream()))
+        offsets = torch.zeros(n + 1, dtype=torch.int64, device=self.torch_device)
+        torch.cumsum(counts.to(torch.int64), dim=0, out=offsets[1:])
+        total = int(offsets[-1].item()) if n else 0
+        states = torch.empty((total, self.nq), dtype=torch.float32, device=self.torch_device)
+        if total:
+            _check(self.lib.pbp_discretize_fill(self._h, ptr(A), ptr(B), n, ptr(counts), ptr(offsets), ptr(states), self._stream()))
+        if host:
+            return counts.cpu().numpy(), offsets.cpu().numpy(), states.cpu().numpy()
+        return counts, offsets, states
+
+    # ------------------------------------------------------------------ sampling
+    def sample_free_states(self, n, seed=0, joint_padding=0.0, padding=0.0, max_rounds=64, as_numpy=False):
+        """Up to n collision-free configurations (uniform in the padded joint limits), in draw order."""
+        torch = _torch()
+        out = torch.empty((n, self.nq), dtype=torch.float32, device=self.torch_device)
+        found, drawn = ctypes.c_int64(0), ctypes.c_int64(0)
+        _check(self.lib.pbp_sample_free_states(self._h, n, ctypes.c_uint64(seed), float(joint_padding), float(padding),
+                                               int(max_rounds), ctypes.c_void_p(out.data_ptr()), ctypes.byref(found),
+                                               ctypes.byref(drawn), self._stream()))
+        out = out[: found.value]
+        self.last_sample_draws = drawn.value
+        return out.cpu().numpy() if as_numpy else out
+
+
+def get_engine(model, collision_model, device=None):
+    """Engine cached on the collision model; rebuilt when the model or its pair list changes."""
+    key = (id(model), getattr(model, "_revision", 0), getattr(collision_model, "_revision", 0), device)
+    cached = getattr(collision_model, "_pbp_engine_cache", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    if cached is not None:
+        cached[1].close()
+    eng = CollisionEngine(model, collision_model, device=device)
+    collision_model._pbp_engine_cache = (key, eng)
+    return eng
