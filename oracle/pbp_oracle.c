@@ -247,7 +247,8 @@ static int simplex_closest(simplex_t *s, double *v) {
             sub3(B, A, ab); sub3(C, A, ac); cross3(ab, ac, nrm); sub3(D, A, ad);
             double sd = dot3(nrm, ad);      /* side of the opposite vertex */
             double so = -dot3(nrm, A);      /* side of the origin */
-            int outside = (sd > 0.0) ? (so < 0.0) : (sd < 0.0 ? (so > 0.0) : 1);
+            int flat = sd * sd <= 1e-24 * dot3(nrm, nrm) * dot3(ad, ad); /* degenerate: no reliable inside */
+            int outside = flat ? 1 : ((sd > 0.0) ? (so <= 0.0) : (so >= 0.0));
             if (!outside) continue;
             outside_any = 1;
             double l3[3]; int mask;

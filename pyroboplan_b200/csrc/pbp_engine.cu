@@ -98,11 +98,20 @@ template <int MODE>
 int launch_broadphase(pbp_engine *e, const StateSource &src, int64_t n, float padding, const Outputs &out, const Bins &bins,
                       cudaStream_t st) {
     const unsigned grid = grid_for(n, BP_THREADS);
+    {
+        cudaError_t pending = cudaGetLastError();
+        if (pending != cudaSuccess) return fail(PBP_ERR_CUDA, "pending CUDA error before broadphase: %s", cudaGetErrorString(pending));
+    }
     if (e->small_tables)
         k_broadphase<16, 24, MODE><<<grid, BP_THREADS, e->smem_bp, st>>>(e->dm, src, n, padding, out, bins);
     else
         k_broadphase<PBP_MAX_JOINTS, PBP_MAX_GEOMS, MODE><<<grid, BP_THREADS, e->smem_bp, st>>>(e->dm, src, n, padding, out, bins);
-    CUDA_TRY(cudaGetLastError());
+    {
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess)
+            return fail(PBP_ERR_CUDA, "broadphase launch failed: %s (mode %d, n %lld, grid %u, smem %zu)", cudaGetErrorString(le),
+                        MODE, (long long)n, grid, e->smem_bp);
+    }
     e->stats.kernel_launches++;
     return 0;
 }
@@ -341,19 +350,23 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     e->smem_np = np_tables + (e->verts_in_smem ? vert_bytes : 0);
     const size_t max_optin = prop.sharedMemPerBlockOptin;
     if (e->smem_bp > max_optin || e->smem_np > max_optin) { pbp_engine_destroy(e); return fail(PBP_ERR_CAPACITY, "model tables exceed shared memory (%zu / %zu bytes)", e->smem_bp, e->smem_np); }
-#define SET_SMEM(kern, bytes) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
-    SET_SMEM((k_broadphase<16, 24, MODE_BOOL>), e->smem_bp);
-    SET_SMEM((k_broadphase<16, 24, MODE_BOOL_ALL>), e->smem_bp);
-    SET_SMEM((k_broadphase<16, 24, MODE_DIST>), e->smem_bp);
-    SET_SMEM((k_broadphase<PBP_MAX_JOINTS, PBP_MAX_GEOMS, MODE_BOOL>), e->smem_bp);
-    SET_SMEM((k_broadphase<PBP_MAX_JOINTS, PBP_MAX_GEOMS, MODE_BOOL_ALL>), e->smem_bp);
-    SET_SMEM((k_broadphase<PBP_MAX_JOINTS, PBP_MAX_GEOMS, MODE_DIST>), e->smem_bp);
-    SET_SMEM((k_narrowphase<MODE_BOOL, true>), e->smem_np);
-    SET_SMEM((k_narrowphase<MODE_BOOL_ALL, true>), e->smem_np);
-    SET_SMEM((k_narrowphase<MODE_DIST, true>), e->smem_np);
-    SET_SMEM((k_narrowphase<MODE_BOOL, false>), e->smem_np);
-    SET_SMEM((k_narrowphase<MODE_BOOL_ALL, false>), e->smem_np);
-    SET_SMEM((k_narrowphase<MODE_DIST, false>), e->smem_np);
+// The dynamic shared-memory cap is a per-function attribute shared by every engine of the
+    // process: raise it to the device's opt-in maximum once (a per-engine value would lower
+    // the cap under another engine's feet).
+#define SET_SMEM(kern) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_optin))
+    SET_SMEM((k_broadphase<16, 24, MODE_BOOL>));
+    SET_SMEM((k_broadphase<16, 24, MODE_BOOL_ALL>));
+    SET_SMEM((k_broadphase<16, 24, MODE_DIST>));
+    SET_SMEM((k_broadphase<PBP_MAX_JOINTS, PBP_MAX_GEOMS, MODE_BOOL>));
+    SET_SMEM((k_broadphase<PBP_MAX_JOINTS, PBP_MAX_GEOMS, MODE_BOOL_ALL>));
+    SET_SMEM((k_broadphase<PBP_MAX_JOINTS, PBP_MAX_GEOMS, MODE_DIST>));
+    SET_SMEM((k_narrowphase<MODE_BOOL, true>));
+    SET_SMEM((k_narrowphase<MODE_BOOL_ALL, true>));
+    SET_SMEM((k_narrowphase<MODE_DIST, true>));
+    SET_SMEM((k_narrowphase<MODE_BOOL, false>));
+    SET_SMEM((k_narrowphase<MODE_BOOL_ALL, false>));
+    SET_SMEM((k_narrowphase<MODE_DIST, false>));
+    SET_SMEM((k_fk_output<PBP_MAX_JOINTS>));
 #undef SET_SMEM
     int occ = 1;
     if (e->verts_in_smem)
@@ -391,7 +404,6 @@ int pbp_fk(pbp_engine *e, const float *q_dev, int64_t n, float *oMi_dev, float *
     if (n == 0) return 0;
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaFuncSetAttribute(k_fk_output<PBP_MAX_JOINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_fk));
     k_fk_output<PBP_MAX_JOINTS><<<grid_for(n, BP_THREADS), BP_THREADS, e->smem_fk, st>>>(e->dm, q_dev, n, oMi_dev, oMg_dev, oMf_dev);
     CUDA_TRY(cudaGetLastError());
     e->stats.kernel_launches++;
@@ -514,6 +526,7 @@ int pbp_check_edges(pbp_engine *e, const float *q1_dev, const float *q2_dev, int
     if ((rc = e->d_counts.ensure((size_t)n_edges * 4))) return rc;
     int32_t *counts = e->d_counts.as<int32_t>();
     k_edge_counts<<<grid_for(n_edges, 256), 256, 0, st>>>(q1_dev, q2_dev, n_edges, e->nq, step, counts);
+    CUDA_TRY(cudaGetLastError());
     e->stats.kernel_launches++;
     CUDA_TRY(cudaMemsetAsync(hit_dev, 0, (size_t)n_edges, st));
     if (first_bad_dev) {
@@ -543,6 +556,7 @@ int pbp_check_edges(pbp_engine *e, const float *q1_dev, const float *q2_dev, int
         CUDA_TRY(cudaMemsetAsync(d_total, 0, 16, st));
         const uint8_t *dead = first_bad_dev ? nullptr : hit_dev;
         k_level_count<<<grid_for(n_edges, 256), 256, 0, st>>>(counts, dead, n_edges, lv, d_total);
+        CUDA_TRY(cudaGetLastError());
         e->stats.kernel_launches++;
         CUDA_TRY(cudaMemcpyAsync(e->h_pinned, d_total, 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -554,6 +568,7 @@ int pbp_check_edges(pbp_engine *e, const float *q1_dev, const float *q2_dev, int
         float *df = e->d_desc_frac.as<float>();
         int32_t *ds = first_bad_dev ? e->d_desc_sample.as<int32_t>() : nullptr;
         k_level_emit<<<grid_for(n_edges, 256), 256, 0, st>>>(counts, dead, n_edges, lv, d_cursor, dg, df, ds);
+        CUDA_TRY(cudaGetLastError());
         e->stats.kernel_launches++;
         for (int64_t off = 0; off < total; off += e->chunk) {
             const int64_t cnt = std::min(e->chunk, total - off);

@@ -84,6 +84,22 @@ __device__ __forceinline__ int closest_on_segment(float3 A, float3 B, float3 &v)
 
 __device__ __forceinline__ int closest_on_triangle(float3 A, float3 B, float3 C, float3 &v) {
     const float3 ab = sub3(B, A), ac = sub3(C, A);
+    const float3 n = cross3(ab, ac);
+    const float nn = dot3(n, n);
+    // Sliver / collinear triangle (sin^2 of the apex angle below 1e-9): the Voronoi-region signs
+    // below are rounding noise in FP32, so use the best of the three edges instead.  This
+    // arises with curved supports (near-duplicate points on an arc) and in planar models.
+    if (!(nn > 1e-9f * dot3(ab, ab) * dot3(ac, ac))) {
+        float3 v1, v2, v3;
+        const int m1 = closest_on_segment(A, B, v1);
+        const int m2 = closest_on_segment(A, C, v2);
+        const int m3 = closest_on_segment(B, C, v3);
+        const float e1 = dot3(v1, v1), e2 = dot3(v2, v2), e3 = dot3(v3, v3);
+        if (e1 <= e2 && e1 <= e3) { v = v1; return m1; }
+        if (e2 <= e3) { v = v2; return (m2 & 1) | ((m2 & 2) << 1); }
+        v = v3;
+        return m3 << 1;
+    }
     const float d1 = -dot3(ab, A), d2 = -dot3(ac, A);
     if (d1 <= 0.f && d2 <= 0.f) { v = A; return 1; }
     const float d3 = -dot3(ab, B), d4 = -dot3(ac, B);
@@ -110,19 +126,6 @@ __device__ __forceinline__ int closest_on_triangle(float3 A, float3 B, float3 C,
     }
     // interior: project the origin on the supporting plane (better conditioned in FP32 than
     // recombining the vertices with barycentric weights)
-    const float3 n = cross3(ab, ac);
-    const float nn = dot3(n, n);
-    if (!(nn > 0.f)) {  // degenerate (collinear) triangle: best of the three edges
-        float3 v1, v2, v3;
-        const int m1 = closest_on_segment(A, B, v1);
-        const int m2 = closest_on_segment(A, C, v2);
-        const int m3 = closest_on_segment(B, C, v3);
-        const float e1 = dot3(v1, v1), e2 = dot3(v2, v2), e3 = dot3(v3, v3);
-        if (e1 <= e2 && e1 <= e3) { v = v1; return m1; }
-        if (e2 <= e3) { v = v2; return (m2 & 1) | ((m2 & 2) << 1); }
-        v = v3;
-        return m3 << 1;
-    }
     const float k = dot3(A, n) / nn;
     v = make_float3(n.x * k, n.y * k, n.z * k);
     return 7;
@@ -142,9 +145,12 @@ __device__ __forceinline__ int closest_on_tetrahedron(float3 A, float3 B, float3
         const float3 R = f == 3 ? C : D;
         const float3 O = f == 0 ? A : (f == 1 ? B : (f == 2 ? C : D));
         const float3 n = cross3(sub3(Q, P), sub3(R, P));
-        const float sd = dot3(n, sub3(O, P));  // side of the omitted vertex
+        const float3 op = sub3(O, P);
+        const float sd = dot3(n, op);          // side of the omitted vertex
         const float so = -dot3(n, P);          // side of the origin
-        if (so * sd > 0.f) continue;           // origin strictly on the inner side of this face
+        // a (nearly) flat tetrahedron has no reliable inside: its faces are all candidates
+        const bool flat = sd * sd <= 1e-10f * dot3(n, n) * dot3(op, op);
+        if (!flat && so * sd > 0.f) continue;  // origin strictly on the inner side of this face
         any_outside = true;
         float3 tv;
         const int m = closest_on_triangle(P, Q, R, tv);
@@ -199,6 +205,9 @@ __device__ __forceinline__ GjkOut gjk_run(const ShapeRef &A, const ShapeRef &B, 
         const float3 w = sub3(sa, sb);
         const float vw = dot3(v, w);
         // <v,w>/|v| is a lower bound of the distance for ANY direction v
+#ifdef PBP_GJK_DEBUG
+        printf("it %d n %d v (%g %g %g) |v| %.9g w (%g %g %g) vw/|v| %.9g\n", it, n, v.x, v.y, v.z, sqrtf(vv), w.x, w.y, w.z, vw / sqrtf(vv));
+#endif
         if (vw > 0.f && vw * vw > cut2 * vv) {
             out.dist = vw * rsqrtf(vv);
             out.hit = 0;
@@ -207,9 +216,10 @@ __device__ __forceinline__ GjkOut gjk_run(const ShapeRef &A, const ShapeRef &B, 
         }
         if (n > 0) {
             if (vv - vw <= PBP_GJK_TOL * sqrtf(vv)) break;  // v is (numerically) the closest point
-            const bool dup = (w.x == W0.x && w.y == W0.y && w.z == W0.z) ||
-                             (n > 1 && w.x == W1.x && w.y == W1.y && w.z == W1.z) ||
-                             (n > 2 && w.x == W2.x && w.y == W2.y && w.z == W2.z);
+            // w (numerically) already in the simplex: v cannot improve any further
+            const float near2 = 1e-10f * dot3(w, w);
+            const float3 e0 = sub3(w, W0), e1 = sub3(w, W1), e2 = sub3(w, W2);
+            const bool dup = dot3(e0, e0) <= near2 || (n > 1 && dot3(e1, e1) <= near2) || (n > 2 && dot3(e2, e2) <= near2);
             if (dup) break;
         }
         // append w and solve for the closest point of the simplex
@@ -223,7 +233,26 @@ __device__ __forceinline__ GjkOut gjk_run(const ShapeRef &A, const ShapeRef &B, 
             mask = closest_on_tetrahedron(W0, W1, W2, W3, nv);
             if (mask == 0) { enclosed = true; break; }
         }
-        const float nvv = dot3(nv, nv);
+        float nvv = dot3(nv, nv);
+        if (n >= 2 && nvv >= vv) {
+            // Backup step: sliver simplices (curved supports, near-duplicate points) can defeat the
+            // region tests in FP32; retry with the sub-simplices that contain the new vertex.
+            float3 c1, c2, c3;
+            if (n == 2) {
+                const int a1 = closest_on_segment(W0, W2, c1), a2 = closest_on_segment(W1, W2, c2);
+                const float e1 = dot3(c1, c1), e2 = dot3(c2, c2);
+                if (e1 <= e2) { nv = c1; mask = (a1 & 1) | ((a1 & 2) << 1); }
+                else { nv = c2; mask = a2 << 1; }
+            } else {
+                const int a1 = closest_on_triangle(W0, W1, W3, c1), a2 = closest_on_triangle(W0, W2, W3, c2),
+                          a3 = closest_on_triangle(W1, W2, W3, c3);
+                const float e1 = dot3(c1, c1), e2 = dot3(c2, c2), e3 = dot3(c3, c3);
+                if (e1 <= e2 && e1 <= e3) { nv = c1; mask = (a1 & 3) | ((a1 & 4) << 1); }
+                else if (e2 <= e3) { nv = c2; mask = (a2 & 1) | ((a2 & 6) << 1); }
+                else { nv = c3; mask = a3 << 1; }
+            }
+            nvv = dot3(nv, nv);
+        }
         if (nvv <= PBP_GJK_EPS_ABS2) { enclosed = true; break; }
         if (!WANT_DIST && nvv <= m2) { v = nv; vv = nvv; break; }      // upper bound already within margin
         if (n > 0 && nvv >= vv) break;                                 // no progress (rounding): keep previous v

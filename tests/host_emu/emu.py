@@ -1,0 +1,79 @@
+"""ctypes driver of the host build of the engine's FP32 GJK (test tooling, see gjk_emu.cpp)."""
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libgjk_emu.so")
+_SRC = os.path.join(_HERE, "gjk_emu.cpp")
+_HDRS = [os.path.join(_HERE, "..", "..", "pyroboplan_b200", "csrc", f) for f in ("pbp_gjk.cuh", "pbp_model.cuh")]
+_lib = None
+
+
+def cuda_include():
+    for d in ("/usr/local/cuda/include", os.path.join(os.environ.get("CUDA_HOME", ""), "include")):
+        if os.path.exists(os.path.join(d, "cuda_runtime.h")):
+            return d
+    return None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        newest = max(os.path.getmtime(p) for p in [_SRC] + _HDRS)
+        if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < newest:
+            inc = cuda_include()
+            if inc is None:
+                raise RuntimeError("CUDA headers not found")
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", f"-I{inc}", "-o", _LIB, _SRC])
+        _lib = ctypes.CDLL(_LIB)
+        vp = ctypes.c_void_p
+        _lib.emu_gjk_batch.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp,
+                                       ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_int, vp, vp, vp]
+        _lib.emu_gjk_batch.restype = None
+    return _lib
+
+
+def padded_verts(arrays, g):
+    """float4-padded vertex table of geometry g, as the engine builds it (last vertex repeated)."""
+    off, cnt = int(arrays["geom_vert_off"][g]), int(arrays["geom_vert_cnt"][g])
+    if cnt == 0:
+        return np.zeros((4, 4), dtype=np.float32)
+    v = np.zeros((cnt, 4), dtype=np.float32)
+    v[:, :3] = arrays["verts"][off : off + cnt]
+    while len(v) % 4:
+        v = np.vstack([v, v[-1:]])
+    return np.ascontiguousarray(v)
+
+
+def gjk_batch(arrays, ga, gb, T, v0, margin, want_dist=False, bound=np.inf):
+    """Run the FP32 GJK on n items of the pair (ga, gb). Returns (hit, dist, iters)."""
+    lib = load()
+    T = np.ascontiguousarray(T, dtype=np.float32).reshape(-1, 12)
+    v0 = np.ascontiguousarray(v0, dtype=np.float32).reshape(-1, 3)
+    n = len(T)
+    va, vb = padded_verts(arrays, ga), padded_verts(arrays, gb)
+    pa = np.ascontiguousarray(arrays["geom_params"][ga][:3], dtype=np.float32)
+    pb = np.ascontiguousarray(arrays["geom_params"][gb][:3], dtype=np.float32)
+    hit = np.zeros(n, dtype=np.int32)
+    dist = np.zeros(n, dtype=np.float32)
+    iters = np.zeros(n, dtype=np.int32)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    lib.emu_gjk_batch(int(arrays["geom_shape"][ga]), p(pa), p(va), len(va) if arrays["geom_vert_cnt"][ga] else 0,
+                      int(arrays["geom_shape"][gb]), p(pb), p(vb), len(vb) if arrays["geom_vert_cnt"][gb] else 0,
+                      p(T), p(v0), n, float(margin), float(bound), int(want_dist), p(hit), p(dist), p(iters))
+    return hit, dist, iters
+
+
+def relative_placements(oMg, ga, gb):
+    """T = oMg[a]^-1 * oMg[b] for a batch of placements oMg [n, ngeoms, 12] (float64 in)."""
+    Ra = oMg[:, ga, :9].reshape(-1, 3, 3)
+    ta = oMg[:, ga, 9:]
+    Rb = oMg[:, gb, :9].reshape(-1, 3, 3)
+    tb = oMg[:, gb, 9:]
+    R = np.einsum("nji,njk->nik", Ra, Rb)
+    t = np.einsum("nji,nj->ni", Ra, tb - ta)
+    return np.concatenate([R.reshape(-1, 9), t], axis=1)

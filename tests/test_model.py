@@ -1,0 +1,134 @@
+"""Host model containers vs the conventions the reference relies on."""
+
+import os
+
+import numpy as np
+import pytest
+
+from conftest import make_panda, make_two_dof
+from pyroboplan_b200.core.utils import (
+    get_collision_geometry_ids,
+    get_collision_pair_indices_from_bodies,
+    set_collisions,
+)
+from pyroboplan_b200.model import SE3, Convex, rpy_to_matrix
+
+REF_MODELS = "/root/reference/src/pyroboplan/models"
+
+
+def test_panda_dimensions():
+    model, cmodel, _ = make_panda(False, False)
+    assert model.nq == 9  # reference test/core/test_utils.py:65
+    assert model.njoints == 10
+    assert model.names[1:] == [f"panda_joint{i}" for i in range(1, 8)] + ["panda_finger_joint1", "panda_finger_joint2"]
+    np.testing.assert_allclose(model.lowerPositionLimit, [-2.9671, -1.8326, -2.9671, -3.1416, -2.9671, -0.0873, -2.9671, 0.0, 0.0])
+    np.testing.assert_allclose(model.upperPositionLimit, [2.9671, 1.8326, 2.9671, 0.0873, 2.9671, 3.8223, 2.9671, 0.04, 0.04])
+    assert cmodel.ngeoms == 11
+    assert len(cmodel.collisionPairs) == 0
+
+
+def test_geometry_names_and_ids():
+    # reference test/core/test_utils.py:215-232
+    model, cmodel, _ = make_panda(False, False)
+    assert get_collision_geometry_ids(model, cmodel, "panda_link1_0") == [cmodel.getGeometryId("panda_link1_0")]
+    assert get_collision_geometry_ids(model, cmodel, "panda_link3") == [cmodel.getGeometryId("panda_link3_0")]
+    assert get_collision_geometry_ids(model, cmodel, "panda_link1000") == []
+    assert cmodel.getGeometryId("nope") == cmodel.ngeoms
+    assert model.getFrameId("nope") == model.nframes
+
+
+def test_set_collisions_pair_ids():
+    # reference test/core/test_utils.py:234-246: geometry id == link index
+    model, cmodel, _ = make_panda(False, False)
+    set_collisions(model, cmodel, "panda_link4", "panda_link5", True)
+    assert len(cmodel.collisionPairs) == 1
+    assert cmodel.collisionPairs[0].first == 4
+    assert cmodel.collisionPairs[0].second == 5
+    set_collisions(model, cmodel, "panda_link4", "panda_link5", True)  # no duplicates
+    assert len(cmodel.collisionPairs) == 1
+    set_collisions(model, cmodel, "panda_link5", "panda_link4", False)  # unordered equality
+    assert len(cmodel.collisionPairs) == 0
+
+
+def test_panda_pair_list():
+    # 20 self pairs after the SRDF, then 54 obstacle pairs = 74
+    model, cmodel, vmodel = make_panda(True, False)
+    self_pairs = [(p.first, p.second) for p in cmodel.collisionPairs]
+    expected = [(a, b) for a in (0, 1, 2) for b in (5, 6, 7, 8, 9, 10)] + [(5, 9), (5, 10)]
+    assert self_pairs == expected
+    model, cmodel, vmodel = make_panda(True, True)
+    assert cmodel.ngeoms == 16
+    assert len(cmodel.collisionPairs) == 74
+    obstacle_pairs = [(p.first, p.second) for p in cmodel.collisionPairs[20:]]
+    names = [g.name for g in cmodel.geometryObjects]
+    assert names[11:] == ["ground_plane", "obstacle_sphere_1", "obstacle_sphere_2", "obstacle_box_1", "obstacle_box_2"]
+    # insertion order: ground, box_1, box_2, sphere_1, sphere_2, each against links 0..10; (ground, link0) removed
+    exp = [(11, l) for l in range(1, 11)]
+    for obs in (14, 15, 12, 13):
+        exp += [(obs, l) for l in range(11)]
+    assert obstacle_pairs == exp
+    idx = get_collision_pair_indices_from_bodies(model, cmodel, ["ground_plane"])
+    assert idx == list(range(20, 30))
+
+
+def test_two_dof_model():
+    model, cmodel, _ = make_two_dof(False)
+    assert model.nq == 2 and cmodel.ngeoms == 2 and len(cmodel.collisionPairs) == 0
+    model, cmodel, _ = make_two_dof(True)
+    assert [g.name for g in cmodel.geometryObjects] == ["upperarm_0", "forearm_0", "obstacle_1", "obstacle_2"]
+    assert [(p.first, p.second) for p in cmodel.collisionPairs] == [(2, 0), (2, 1), (3, 0), (3, 1)]
+    np.testing.assert_allclose(cmodel.geometryObjects[0].placement.translation, [0.5, 0, 0])
+
+
+def test_sphere_model():
+    from pyroboplan_b200.models import panda
+
+    model, cmodel, _ = panda.load_models(use_sphere_collisions=True)
+    assert cmodel.ngeoms == 17 and model.nq == 9
+
+
+def test_hand_placement_and_meshes():
+    model, cmodel, _ = make_panda(False, False)
+    hand = cmodel.geometryObjects[8]
+    assert hand.name == "panda_hand_0" and hand.parentJoint == 7
+    np.testing.assert_allclose(hand.placement.translation, [0, 0, 0.107])
+    np.testing.assert_allclose(hand.placement.rotation, rpy_to_matrix(0, 0, -0.785398163397), atol=1e-12)
+    rf = cmodel.geometryObjects[10]
+    np.testing.assert_allclose(rf.placement.rotation, rpy_to_matrix(0, 0, 3.14159265359), atol=1e-12)
+    counts = [len(g.geometry.points) for g in cmodel.geometryObjects]
+    assert counts == [102, 152, 152, 152, 152, 152, 102, 102, 102, 18, 18]
+    for g in cmodel.geometryObjects:
+        assert isinstance(g.geometry, Convex)
+        assert g.geometry.volume_ratio > 0.999  # the Panda collision meshes are convex to < 0.03 % volume
+        c, r = g.geometry.bounding_sphere()
+        assert np.all(np.linalg.norm(g.geometry.points - c, axis=1) <= r + 1e-12)
+        ci, ri = g.geometry.inner_sphere()
+        assert ri > 0 and np.all(g.geometry.planes[:, :3] @ ci + g.geometry.planes[:, 3] <= -ri + 1e-9)
+
+
+def test_se3():
+    rng = np.random.default_rng(0)
+    a = SE3(rpy_to_matrix(*rng.normal(size=3)), rng.normal(size=3))
+    b = SE3(rpy_to_matrix(*rng.normal(size=3)), rng.normal(size=3))
+    p = rng.normal(size=3)
+    np.testing.assert_allclose((a * b).act(p), a.act(b.act(p)), atol=1e-12)
+    np.testing.assert_allclose((a * a.inverse()).homogeneous, np.eye(4), atol=1e-12)
+    np.testing.assert_allclose(a.actInv(a.act(p)), p, atol=1e-12)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_MODELS), reason="reference assets only exist in the authoring container")
+def test_urdf_parser_matches_bundled_description():
+    """The URDF/SRDF/STL path and the bundled JSON descriptions give the same models."""
+    from pyroboplan_b200.model import buildModelsFromUrdf, removeCollisionPairs
+
+    model, cmodel, _ = buildModelsFromUrdf(os.path.join(REF_MODELS, "panda_description/urdf/panda.urdf"), package_dirs=REF_MODELS)
+    cmodel.addAllCollisionPairs()
+    assert len(cmodel.collisionPairs) == 54
+    removeCollisionPairs(model, cmodel, os.path.join(REF_MODELS, "panda_description/srdf/panda.srdf"))
+    ref_model, ref_cmodel, _ = make_panda(True, False)
+    assert [(p.first, p.second) for p in cmodel.collisionPairs] == [(p.first, p.second) for p in ref_cmodel.collisionPairs]
+    for g, h in zip(cmodel.geometryObjects, ref_cmodel.geometryObjects):
+        assert g.name == h.name and g.parentJoint == h.parentJoint and g.parentFrame == h.parentFrame
+        np.testing.assert_allclose(g.geometry.points, h.geometry.points, rtol=0, atol=1e-9)
+    for a, b in zip(model.jointPlacements, ref_model.jointPlacements):
+        np.testing.assert_allclose(a.homogeneous, b.homogeneous, atol=1e-15)
