@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Headline benchmark: collision-checked Panda configurations per second (BASELINE.json config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the hot path (FK + placement + boolean collision over the 74 active
+pairs) over one batch of 1 M uniformly sampled Panda configurations per GPU.  Under torchrun
+(N > 1) every rank owns its own batches (weak scaling, no data-path collective); the timed
+region is bracketed by a barrier + synchronize and the max over ranks is reported.
+
+Output: ONE JSON line on rank 0 (see DESIGN.md "Measurement" for every field).
+`--impl reference` times the CPU restatement of the reference path (oracle/, float64, all host
+threads) on a bounded sample of the same workload; Pinocchio/coal cannot be installed here.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "collision-checked configs/sec (Panda 7-DOF, 1/2/4/8 B200) vs reference CPU"
+UNIT = "configs/s"
+WORKLOAD = "config2: Panda nq=9, 16 geoms, 74 active pairs (20 self + 32 box + 22 sphere), uniform states in joint limits, padding 0"
+N_STATES = 1 << 20          # states per GPU per step (BASELINE.json config 2: 1 M random states)
+N_BATCHES = 4               # distinct input batches rotated between steps (4 x 37.7 MB > 126 MB L2)
+
+# Algorithmic FP32 work per configuration, frozen from the float64 oracle's counters on the
+# config-2 distribution (seed 0, 100 k states, cull-aware counting mode; DESIGN.md "F_alg"):
+#   FK 1.5 kflop + broadphase 74 pairs x 30 flop + 6 flop x 1598 hull vertices scanned
+#   + 150 flop x 7.57 GJK iterations  = 14.4 kflop / configuration.
+F_BP_FLOP_PER_CONFIG = 1.5e3 + 74 * 30.0          # k_broadphase: FK + 74 proxy tests
+F_NP_FLOP_PER_CONFIG = 6.0 * 1598 + 150.0 * 7.57  # k_narrowphase: support scans + simplex updates
+F_ALG_FLOP_PER_CONFIG = F_BP_FLOP_PER_CONFIG + F_NP_FLOP_PER_CONFIG  # = 14.4 kflop
+HBM_BYTES_PER_CONFIG = 9 * 4 + 1   # 9 float32 in, 1 verdict byte out
+
+
+def panda_models():
+    from pyroboplan_b200.models import panda
+
+    model, cmodel, vmodel = panda.load_models()
+    panda.add_self_collisions(model, cmodel)
+    panda.add_object_collisions(model, cmodel, vmodel)
+    return model, cmodel
+
+
+def make_batch(model, n, seed):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(model.lowerPositionLimit, model.upperPositionLimit, size=(n, model.nq)).astype(np.float32)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except (OSError, ValueError):
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                power.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(smax) if smax else None,
+            "power_w_max": max(power) if power else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def run_reference(args, rank):
+    """CPU arm: the float64 oracle (port of the reference path), all host threads, bounded sample."""
+    if rank != 0:
+        return
+    from oracle.oracle import Oracle
+
+    model, cmodel = panda_models()
+    orc = Oracle(model, cmodel)
+    threads = len(os.sched_getaffinity(0))
+    sample = int(os.environ.get("PBP_REF_SAMPLE", 200_000))
+    batches = [make_batch(model, sample, 1000 + b).astype(np.float64) for b in range(2)]
+    for w in range(max(args.warmup, 1)):
+        orc.check_states(batches[w % 2][: sample // 4], use_cull=1, nthreads=threads)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        orc.check_states(batches[k % 2], use_cull=1, nthreads=threads)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "states_per_step": sample, "note": "CPU restatement (oracle/pbp_oracle.c), not Pinocchio/coal: those are not installable here"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} states/step x {args.steps} steps of the config-2 distribution, bounding-sphere cull + first-hit exit"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--states", type=int, default=N_STATES, help="states per GPU per step")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from pyroboplan_b200.engine import CollisionEngine, measure_fp32_peak
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    model, cmodel = panda_models()
+    eng = CollisionEngine(model, cmodel, device=local_rank)
+    n = args.states
+    host_batches = [torch.from_numpy(make_batch(model, n, 7919 * rank + b)).pin_memory() for b in range(N_BATCHES)]
+    dev_batches = [b.to(dev, non_blocking=True) for b in host_batches]
+    hits = [None] * N_BATCHES
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---------------- device-resident throughput
+    for w in range(args.warmup):
+        hits[w % N_BATCHES] = eng.check_states(dev_batches[w % N_BATCHES])
+    torch.cuda.synchronize()
+    fp32_peak = measure_fp32_peak(local_rank)
+    eng.stats(reset=True)
+    eng.set_profiling(True)
+    eng.profile(reset=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for k in range(args.steps):
+        hits[k % N_BATCHES] = eng.check_states(dev_batches[k % N_BATCHES])
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    prof = eng.profile(reset=True)
+    eng.set_profiling(False)
+    stats = eng.stats(reset=True)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * n * args.steps / (ms_max * 1e-3)
+
+    # ---------------- end to end through the host-buffer C ABI (pinned inputs, H2D + D2H timed)
+    host_np = [b.numpy() for b in host_batches]
+    for w in range(2):
+        eng.check_states(host_np[w % N_BATCHES])
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        hit_host = eng.check_states(host_np[k % N_BATCHES])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * args.steps / float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (per-launch CUDA events inside the timed region)
+    peaks, peak_src = measured_peaks()
+    rounds = max(prof["rounds"], 1)
+    bp_ms, np_ms = prof["broadphase_ms"] / rounds, prof["narrowphase_ms"] / rounds
+    dominant = "k_narrowphase" if np_ms >= bp_ms else "k_broadphase"
+    states_per_launch = n * args.steps / rounds
+    kernel_ms = max(np_ms, bp_ms)
+    f_dom = F_NP_FLOP_PER_CONFIG if dominant == "k_narrowphase" else F_BP_FLOP_PER_CONFIG
+    achieved_tflops = f_dom * states_per_launch / (kernel_ms * 1e-3) / 1e12
+    step_kernel_ms = bp_ms + np_ms
+    step_tflops = F_ALG_FLOP_PER_CONFIG * states_per_launch / (step_kernel_ms * 1e-3) / 1e12
+    hbm_gbs = HBM_BYTES_PER_CONFIG * states_per_launch / (step_kernel_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": achieved_tflops / fp32_peak if fp32_peak else None, "traffic": None,
+        "kernel": dominant,
+        "kernel_avg_ms": kernel_ms,
+        "kernel_share_of_step": kernel_ms / step_kernel_ms if step_kernel_ms else None,
+        "peak_source": "FFMA microbenchmark run in this process (pbp_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
+        "note": "scalar FP32 geometry: neither HBM- nor tensor-bound (SURVEY.md 8d); bound = FP32 pipe",
+        "kernel_ms": {"k_broadphase": bp_ms, "k_narrowphase": np_ms},
+        "states_per_launch": states_per_launch,
+        "narrowphase_items_per_state": prof["narrowphase_items"] / max(n * args.steps, 1),
+        "flop_per_config": {"k_broadphase": F_BP_FLOP_PER_CONFIG, "k_narrowphase": F_NP_FLOP_PER_CONFIG},
+        "step": {"achieved": step_tflops, "frac": step_tflops / fp32_peak if fp32_peak else None, "unit": "TFLOP/s"},
+        "hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                "frac": hbm_gbs / peaks.get("hbm_gbs", 1.0), "peak_source": f"MEASURED_PEAKS.json ({peak_src})"},
+    }
+
+    # ---------------- CPU baseline + parity on a bounded sample (rank 0, N = 1 only)
+    cpu_baseline = None
+    parity = None
+    if world == 1:
+        from oracle.oracle import Oracle
+
+        orc = Oracle(model, cmodel)
+        threads = len(os.sched_getaffinity(0))
+        sample_n = min(n, int(os.environ.get("PBP_CPU_SAMPLE", 500_000)))
+        qs = host_np[(args.steps - 1) % N_BATCHES][:sample_n].astype(np.float64)
+        orc.check_states(qs[:20000], use_cull=1, nthreads=threads)
+        t0 = time.perf_counter()
+        hit_cpu, _, _, _ = orc.check_states(qs, use_cull=1, nthreads=threads)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": sample_n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"first {sample_n} states of the last timed batch, float64 oracle, bounding-sphere cull + first-hit exit"}
+        bad = np.nonzero(hit_cpu.astype(bool) != hit_host[:sample_n])[0]
+        beyond = 0
+        if len(bad):
+            # classify: verdicts may differ only where the reference min distance is within 1e-6 m
+            _, md_bad, _, _ = orc.check_states(qs[bad], want_all=True, use_cull=0, nthreads=threads)
+            beyond = int((md_bad > 1e-6).sum())
+        parity = {"checked": sample_n, "mismatches": int(len(bad)), "mismatches_beyond_1e-6m": beyond}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "states_per_gpu_per_step": n,
+                   "l2": f"inputs rotate over {N_BATCHES} batches ({N_BATCHES * n * 36 / 1e6:.0f} MB > 126 MB L2)",
+                   "parallelism": f"{world} rank(s), states sharded, no data-path collective"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 9 * 4, "d2h_bytes_per_step": n,
+                "api": "CollisionEngine.check_states(numpy) -> pbp_check_states_host (pinned host buffers)"},
+        "gpu_launches": stats["kernel_launches"],
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "parity": parity,
+        "p_collision": float(hits[(args.steps - 1) % N_BATCHES].float().mean().item()),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -99,6 +99,23 @@ void pbp_engine_destroy(pbp_engine *e);
 int pbp_engine_device(const pbp_engine *e);
 int pbp_get_stats(pbp_engine *e, pbp_stats *out, int reset);
 
+/* Optional per-kernel timing (CUDA events recorded on the caller's stream around the two hot
+ * kernels of every round) and narrowphase item counting.  Off by default; bench.py turns it
+ * on to report the dominant kernel's average launch duration for the roofline figure. */
+typedef struct {
+    double broadphase_ms;      /* sum of k_broadphase launch durations */
+    double narrowphase_ms;     /* sum of k_narrowphase launch durations */
+    int64_t rounds;            /* broadphase + narrowphase rounds timed */
+    int64_t narrowphase_items; /* (state, pair) items that reached GJK */
+} pbp_profile;
+int pbp_set_profiling(pbp_engine *e, int enabled);
+/* Synchronises the recorded events, accumulates, returns totals since the last reset. */
+int pbp_get_profile(pbp_engine *e, pbp_profile *out, int reset);
+
+/* Measured FP32 FMA throughput of the device (dependent-chain-free FFMA loop on every SM),
+ * in TFLOP/s; used as the roofline denominator of this FP32-pipe-bound path. */
+int pbp_measure_fp32_peak(int device, double *tflops_out);
+
 /* Forward kinematics + placement of joints / geometries / frames for N configurations.
  * Replaces pinocchio.framesForwardKinematics + updateGeometryPlacements
  * (core/utils.py:253,297,345,374; implicit in computeCollisions at core/utils.py:48).

@@ -50,6 +50,7 @@ class _CModel(ctypes.Structure):
         ("geom_vert_off", ctypes.c_void_p),
         ("geom_vert_cnt", ctypes.c_void_p),
         ("geom_bsphere", ctypes.c_void_p),
+        ("geom_isphere", ctypes.c_void_p),
         ("verts", ctypes.c_void_p),
         ("pairs", ctypes.c_void_p),
     ]
@@ -132,11 +133,14 @@ class Oracle:
         a["geom_vert_off"] = np.zeros(ng, dtype=np.int32)
         a["geom_vert_cnt"] = np.zeros(ng, dtype=np.int32)
         a["geom_bsphere"] = np.zeros((ng, 4), dtype=np.float64)
+        a["geom_isphere"] = np.zeros((ng, 4), dtype=np.float64)
         verts = []
         nv = 0
         for i, g in enumerate(geoms):
             s = g.geometry
             a["geom_placement"][i] = _se3_row(g.placement)
+            ic, ir = s.inner_sphere()
+            a["geom_isphere"][i] = [*np.asarray(ic, dtype=np.float64), max(ir - 1e-9, 0.0)]
             name = type(s).__name__
             if name == "Sphere":
                 a["geom_shape"][i] = SH_SPHERE
@@ -196,7 +200,11 @@ class Oracle:
 
     # ------------------------------------------------------------------ states
     def check_states(self, Q, padding=0.0, want_all=False, use_cull=True, nthreads=0):
-        """hit[N] uint8, min_dist[N] (over evaluated pairs), first_pair[N], counters."""
+        """hit[N] uint8, min_dist[N] (over evaluated pairs), first_pair[N], counters.
+
+        use_cull: False/0 = every pair through GJK in list order (the reference's loop);
+        True/1 = skip pairs whose bounding spheres are apart; 2 = work-counting mode with
+        the cull-aware proxy broadphase (same verdicts; first_pair/min_dist not comparable)."""
         Q = np.ascontiguousarray(Q, dtype=np.float64).reshape(-1, self.nq)
         n = len(Q)
         hit = np.zeros(n, dtype=np.uint8)

@@ -55,6 +55,7 @@ typedef struct {
     const int32_t *geom_vert_off;  /* [ngeoms] */
     const int32_t *geom_vert_cnt;  /* [ngeoms] */
     const double *geom_bsphere;    /* [ngeoms][4] bounding sphere cx cy cz r in geometry frame */
+    const double *geom_isphere;    /* [ngeoms][4] inscribed sphere cx cy cz r in geometry frame */
     const double *verts;           /* [nverts][3] */
     const int32_t *pairs;          /* [npairs][2] */
 } oracle_model;
@@ -378,6 +379,44 @@ static int sphere_cull(const oracle_model *m, const double *oMg, int ga, int gb,
     return dot3(d, d) > r * r;
 }
 
+static double point_box_dist(const double *T, const double *h, const double *p) {
+    /* distance from world point p to the box with placement T and half sides h */
+    double d2 = 0.0;
+    for (int i = 0; i < 3; i++) {
+        double l = T[i] * (p[0] - T[9]) + T[3 + i] * (p[1] - T[10]) + T[6 + i] * (p[2] - T[11]);
+        double e = fabs(l) - h[i];
+        if (e > 0.0) d2 += e * e;
+    }
+    return sqrt(d2);
+}
+
+static void sphere_world(const double *T, const double *s, double *c) {
+    for (int i = 0; i < 3; i++) c[i] = T[3 * i] * s[0] + T[3 * i + 1] * s[1] + T[3 * i + 2] * s[2] + T[9 + i];
+}
+
+/* Conservative proxy bounds of one pair (enclosing / inscribed spheres, exact boxes): the same
+ * broadphase idea the CUDA engine uses, in float64.  lb <= distance <= ub (ub may be < 0). */
+static void proxy_bounds(const oracle_model *m, const double *oMg, int ga, int gb, double *lb, double *ub) {
+    int box = m->geom_shape[ga] == SH_BOX ? ga : (m->geom_shape[gb] == SH_BOX ? gb : -1);
+    if (box >= 0) {
+        int ot = box == ga ? gb : ga;
+        double c[3], ic[3];
+        sphere_world(oMg + 12 * ot, m->geom_bsphere + 4 * ot, c);
+        sphere_world(oMg + 12 * ot, m->geom_isphere + 4 * ot, ic);
+        *lb = point_box_dist(oMg + 12 * box, m->geom_params + 4 * box, c) - m->geom_bsphere[4 * ot + 3];
+        *ub = point_box_dist(oMg + 12 * box, m->geom_params + 4 * box, ic) - m->geom_isphere[4 * ot + 3];
+    } else {
+        double ca[3], cb[3], ia[3], ib[3], d[3], e[3];
+        sphere_world(oMg + 12 * ga, m->geom_bsphere + 4 * ga, ca);
+        sphere_world(oMg + 12 * gb, m->geom_bsphere + 4 * gb, cb);
+        sphere_world(oMg + 12 * ga, m->geom_isphere + 4 * ga, ia);
+        sphere_world(oMg + 12 * gb, m->geom_isphere + 4 * gb, ib);
+        sub3(ca, cb, d); sub3(ia, ib, e);
+        *lb = sqrt(dot3(d, d)) - m->geom_bsphere[4 * ga + 3] - m->geom_bsphere[4 * gb + 3];
+        *ub = sqrt(dot3(e, e)) - m->geom_isphere[4 * ga + 3] - m->geom_isphere[4 * gb + 3];
+    }
+}
+
 /* One configuration.  Returns hit (0/1).  Restates computeCollisions(..., stop_at_first) +
  * np.any(isCollision) (reference core/utils.py:48-51).  When want_all != 0 every pair is
  * evaluated (as computeDistances does, core/utils.py:86) and *min_dist is the min over pairs.
@@ -391,6 +430,29 @@ int oracle_check_state(const oracle_model *m, const double *q, double padding, i
     int hit = 0;
     double md = INFINITY;
     int fp = -1;
+    if (use_cull == 2 && !want_all) {
+        /* Work-counting mode (verdict unchanged): proxy bounds first -- any certain hit decides
+         * the state without narrowphase -- then GJK only on the undecided pairs.  Used to count
+         * the algorithmic narrowphase work of a cull-aware method (F_alg). */
+        const double slack = 1e-9;
+        for (int k = 0; k < m->npairs; k++) {
+            double lb, ub;
+            proxy_bounds(m, oMg_scratch, m->pairs[2 * k], m->pairs[2 * k + 1], &lb, &ub);
+            if (ub <= padding - slack) { if (first_pair) *first_pair = k; if (min_dist) *min_dist = 0.0; return 1; }
+        }
+        for (int k = 0; k < m->npairs; k++) {
+            double lb, ub;
+            int ga = m->pairs[2 * k], gb = m->pairs[2 * k + 1];
+            proxy_bounds(m, oMg_scratch, ga, gb, &lb, &ub);
+            if (lb > padding + slack) { cnt->culled++; continue; }
+            double d = oracle_pair_distance(m, oMg_scratch, ga, gb, NULL, cnt);
+            if (d < md) md = d;
+            if (d <= padding) { hit = 1; fp = k; break; }
+        }
+        if (min_dist) *min_dist = md;
+        if (first_pair) *first_pair = fp;
+        return hit;
+    }
     for (int k = 0; k < m->npairs; k++) {
         int ga = m->pairs[2 * k], gb = m->pairs[2 * k + 1];
         if (use_cull && !want_all && sphere_cull(m, oMg_scratch, ga, gb, padding)) { cnt->culled++; continue; }

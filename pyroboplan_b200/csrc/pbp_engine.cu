@@ -78,6 +78,10 @@ struct pbp_engine {
     size_t smem_bp = 0, smem_np = 0, smem_fk = 0;
     int np_blocks = 0;
     pbp_stats stats{};
+    // optional per-kernel timing
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;   // triples: before broadphase, between, after narrowphase
+    pbp_profile prof{};
 };
 
 namespace {
@@ -140,15 +144,31 @@ int run_round(pbp_engine *e, int mode, const StateSource &src, int64_t n, float 
     CUDA_TRY(cudaMemsetAsync(e->d_ctrl.p, 0, ((size_t)e->npairs + 1) * 4, st));
     int rc;
     const bool has_sample = src.sample != nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (e->profiling) {
+        for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
+        CUDA_TRY(cudaEventRecord(ev[0], st));
+    }
+#define PROF_MID() do { if (e->profiling) CUDA_TRY(cudaEventRecord(ev[1], st)); } while (0)
     if (mode == MODE_BOOL) {
         if ((rc = launch_broadphase<MODE_BOOL>(e, src, n, padding, out, bins, st))) return rc;
+        PROF_MID();
         if ((rc = launch_narrowphase<MODE_BOOL>(e, padding, out, bins, has_sample, st))) return rc;
     } else if (mode == MODE_BOOL_ALL) {
         if ((rc = launch_broadphase<MODE_BOOL_ALL>(e, src, n, padding, out, bins, st))) return rc;
+        PROF_MID();
         if ((rc = launch_narrowphase<MODE_BOOL_ALL>(e, padding, out, bins, has_sample, st))) return rc;
     } else {
         if ((rc = launch_broadphase<MODE_DIST>(e, src, n, padding, out, bins, st))) return rc;
+        PROF_MID();
         if ((rc = launch_narrowphase<MODE_DIST>(e, padding, out, bins, has_sample, st))) return rc;
+    }
+#undef PROF_MID
+    if (e->profiling) {
+        CUDA_TRY(cudaEventRecord(ev[2], st));
+        for (int i = 0; i < 3; i++) e->prof_events.push_back(ev[i]);
+        k_sum_counts<<<1, 256, 0, st>>>(bins.count, e->npairs, ctrl_u64(e, 3));
+        e->stats.kernel_launches++;
     }
     e->stats.states += n;
     e->stats.chunks++;
@@ -179,9 +199,41 @@ int pbp_get_stats(pbp_engine *e, pbp_stats *out, int reset) {
     return 0;
 }
 
+int pbp_set_profiling(pbp_engine *e, int enabled) {
+    if (!e) return fail(PBP_ERR_ARG, "engine is NULL");
+    e->profiling = enabled != 0;
+    return 0;
+}
+
+int pbp_get_profile(pbp_engine *e, pbp_profile *out, int reset) {
+    if (!e || !out) return fail(PBP_ERR_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    for (size_t i = 0; i + 2 < e->prof_events.size(); i += 3) {
+        float a = 0.f, b = 0.f;
+        CUDA_TRY(cudaEventSynchronize(e->prof_events[i + 2]));
+        CUDA_TRY(cudaEventElapsedTime(&a, e->prof_events[i], e->prof_events[i + 1]));
+        CUDA_TRY(cudaEventElapsedTime(&b, e->prof_events[i + 1], e->prof_events[i + 2]));
+        e->prof.broadphase_ms += a;
+        e->prof.narrowphase_ms += b;
+        e->prof.rounds++;
+        for (int k = 0; k < 3; k++) cudaEventDestroy(e->prof_events[i + k]);
+    }
+    e->prof_events.clear();
+    unsigned long long items = 0;
+    CUDA_TRY(cudaMemcpy(&items, ctrl_u64(e, 3), 8, cudaMemcpyDeviceToHost));
+    e->prof.narrowphase_items = (int64_t)items;
+    *out = e->prof;
+    if (reset) {
+        e->prof = pbp_profile{};
+        CUDA_TRY(cudaMemset(ctrl_u64(e, 3), 0, 8));
+    }
+    return 0;
+}
+
 void pbp_engine_destroy(pbp_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
     DeviceBuffer *bufs[] = {&e->d_joints, &e->d_geoms, &e->d_pairs, &e->d_order, &e->d_verts, &e->d_qlim, &e->d_frames,
                             &e->d_bin_group, &e->d_bin_sample, &e->d_bin_T, &e->d_ctrl, &e->d_counts, &e->d_desc_group,
                             &e->d_desc_frac, &e->d_desc_sample, &e->d_scratch_i32, &e->d_scratch_u8, &e->d_cub, &e->d_sel,
@@ -753,5 +805,55 @@ extern "C" int pbp_sample_free_states(pbp_engine *e, int64_t n_wanted, uint64_t 
     CUDA_TRY(cudaGetLastError());
     *n_found_host = found;
     if (n_drawn_host) *n_drawn_host = drawn;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// FP32 FMA peak microbenchmark (roofline denominator of this FP32-pipe-bound path)
+// ------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters, float a, float b) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
+          x7 = x0 + 7.f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+}  // namespace
+
+extern "C" int pbp_measure_fp32_peak(int device, double *tflops_out) {
+    if (!tflops_out) return fail(PBP_ERR_ARG, "NULL argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(PBP_ERR_CUDA, "no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    float *buf = nullptr;
+    CUDA_TRY(cudaMalloc(&buf, (size_t)blocks * threads * 4));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CUDA_TRY(cudaEventRecord(e0, 0));
+        k_fma_peak<<<blocks, threads>>>(buf, iters, 0.999f, 1e-3f);
+        CUDA_TRY(cudaEventRecord(e1, 0));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    CUDA_TRY(cudaGetLastError());
+    *tflops_out = best;
     return 0;
 }

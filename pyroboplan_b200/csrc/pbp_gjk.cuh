@@ -193,7 +193,7 @@ __device__ __forceinline__ GjkOut gjk_run(const ShapeRef &A, const ShapeRef &B, 
     const float m2 = margin * margin;
     const float cut = WANT_DIST ? bound : margin;
     const float cut2 = cut * cut;
-    int it = 0;
+    int it = 0, stalls = 0;
     bool enclosed = false;
     for (; it < PBP_GJK_MAX_ITERS; it++) {
         // support of (A - B) in direction -v
@@ -241,21 +241,28 @@ __device__ __forceinline__ GjkOut gjk_run(const ShapeRef &A, const ShapeRef &B, 
             if (n == 2) {
                 const int a1 = closest_on_segment(W0, W2, c1), a2 = closest_on_segment(W1, W2, c2);
                 const float e1 = dot3(c1, c1), e2 = dot3(c2, c2);
-                if (e1 <= e2) { nv = c1; mask = (a1 & 1) | ((a1 & 2) << 1); }
-                else { nv = c2; mask = a2 << 1; }
+                if (e1 < nvv && e1 <= e2) { nv = c1; mask = (a1 & 1) | ((a1 & 2) << 1); }
+                else if (e2 < nvv) { nv = c2; mask = a2 << 1; }
             } else {
                 const int a1 = closest_on_triangle(W0, W1, W3, c1), a2 = closest_on_triangle(W0, W2, W3, c2),
                           a3 = closest_on_triangle(W1, W2, W3, c3);
                 const float e1 = dot3(c1, c1), e2 = dot3(c2, c2), e3 = dot3(c3, c3);
-                if (e1 <= e2 && e1 <= e3) { nv = c1; mask = (a1 & 3) | ((a1 & 4) << 1); }
-                else if (e2 <= e3) { nv = c2; mask = (a2 & 1) | ((a2 & 6) << 1); }
-                else { nv = c3; mask = a3 << 1; }
+                if (e1 < nvv && e1 <= e2 && e1 <= e3) { nv = c1; mask = (a1 & 3) | ((a1 & 4) << 1); }
+                else if (e2 < nvv && e2 <= e3) { nv = c2; mask = (a2 & 1) | ((a2 & 6) << 1); }
+                else if (e3 < nvv) { nv = c3; mask = a3 << 1; }
             }
             nvv = dot3(nv, nv);
         }
         if (nvv <= PBP_GJK_EPS_ABS2) { enclosed = true; break; }
         if (!WANT_DIST && nvv <= m2) { v = nv; vv = nvv; break; }      // upper bound already within margin
-        if (n > 0 && nvv >= vv) break;                                 // no progress (rounding): keep previous v
+        // |v| must decrease; a decrease below FP32 resolution (large flat faces far from the origin)
+        // is still real progress -- the direction turns and the next support finds a new vertex --
+        // so tolerate a few such steps, but stop on a genuinely worse point or when it persists.
+        if (n > 0 && nvv >= vv) {
+            if (nvv > vv * 1.00001f || ++stalls > 4) break;
+        } else {
+            stalls = 0;
+        }
         v = nv;
         vv = nvv;
         // compact the kept vertices to the front (static indices only -> stays in registers)

@@ -566,6 +566,12 @@ __global__ void k_fill_f32(float *p, int64_t n, float v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
+// total += sum(count[0..n))   (profiling: items that reached the narrowphase)
+__global__ void k_sum_counts(const uint32_t *count, int n, unsigned long long *total) {
+    unsigned long long s = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += count[i];
+    if (s) atomicAdd(total, s);
+}
 // INT_MAX (none) -> -1
 __global__ void k_finalize_index(int32_t *p, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -37,6 +37,9 @@ EXPORTED_SYMBOLS = [
     "pbp_discretize_fill",
     "pbp_check_paths",
     "pbp_sample_free_states",
+    "pbp_set_profiling",
+    "pbp_get_profile",
+    "pbp_measure_fp32_peak",
 ]
 
 
@@ -79,6 +82,15 @@ class _Stats(ctypes.Structure):
     ]
 
 
+class _Profile(ctypes.Structure):
+    _fields_ = [
+        ("broadphase_ms", ctypes.c_double),
+        ("narrowphase_ms", ctypes.c_double),
+        ("rounds", ctypes.c_int64),
+        ("narrowphase_items", ctypes.c_int64),
+    ]
+
+
 _lib = None
 
 
@@ -110,6 +122,9 @@ def load_library():
     lib.pbp_discretize_fill.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
     lib.pbp_check_paths.argtypes = [vp, vp, vp, i64, i64, f32, vp, vp]
     lib.pbp_sample_free_states.argtypes = [vp, i64, ctypes.c_uint64, f32, f32, i32, vp, ctypes.POINTER(i64), ctypes.POINTER(i64), vp]
+    lib.pbp_set_profiling.argtypes = [vp, i32]
+    lib.pbp_get_profile.argtypes = [vp, ctypes.POINTER(_Profile), i32]
+    lib.pbp_measure_fp32_peak.argtypes = [i32, ctypes.POINTER(f64)]
     if lib.pbp_abi_version() != PBP_ABI_VERSION:
         raise RuntimeError("libpbp_engine.so ABI version mismatch; rebuild it")
     _lib = lib
@@ -268,6 +283,15 @@ class CollisionEngine:
         _check(self.lib.pbp_get_stats(self._h, ctypes.byref(s), int(reset)))
         return {k: int(getattr(s, k)) for k, _ in s._fields_}
 
+    def set_profiling(self, enabled=True):
+        _check(self.lib.pbp_set_profiling(self._h, int(enabled)))
+
+    def profile(self, reset=False):
+        """Per-kernel CUDA-event timings (ms) and narrowphase item count since the last reset."""
+        p = _Profile()
+        _check(self.lib.pbp_get_profile(self._h, ctypes.byref(p), int(reset)))
+        return {k: getattr(p, k) for k, _ in p._fields_}
+
     # ------------------------------------------------------------------ FK
     def fk(self, Q, joints=True, geoms=True, frames=True):
         """Placements [N, n*, 12] (R row-major, then t) for joints / geometries / frames."""
@@ -295,12 +319,12 @@ class CollisionEngine:
         if self._is_dev(Q):
             Qd = self._dev_q(Q)
             n = Qd.shape[0]
-            hit = torch.empty(n, dtype=torch.uint8, device=self.torch_device)
+            hit = torch.empty(n, dtype=torch.bool, device=self.torch_device)  # kernels write 0/1 bytes
             dist = torch.empty(n, dtype=torch.float32, device=self.torch_device) if return_distance else None
             pair = torch.empty(n, dtype=torch.int32, device=self.torch_device) if return_pair else None
             ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
             _check(self.lib.pbp_check_states(self._h, ptr(Qd), n, float(padding), ptr(hit), ptr(dist), ptr(pair), self._stream()))
-            res = [hit.to(torch.bool)]
+            res = [hit]
         else:
             Qh = self._host_q(Q, self.nq)
             n = Qh.shape[0]
@@ -309,7 +333,7 @@ class CollisionEngine:
             pair = np.zeros(n, dtype=np.int32) if return_pair else None
             ptr = lambda t: ctypes.c_void_p(t.ctypes.data) if t is not None else None
             _check(self.lib.pbp_check_states_host(self._h, ptr(Qh), n, float(padding), ptr(hit), ptr(dist), ptr(pair)))
-            res = [hit.astype(bool)]
+            res = [hit.view(np.bool_)]
         if return_distance:
             res.append(dist)
         if return_pair:
@@ -323,11 +347,11 @@ class CollisionEngine:
         if self._is_dev(Q1):
             A, B = self._dev_q(Q1), self._dev_q(Q2)
             n = A.shape[0]
-            hit = torch.empty(n, dtype=torch.uint8, device=self.torch_device)
+            hit = torch.empty(n, dtype=torch.bool, device=self.torch_device)
             fb = torch.empty(n, dtype=torch.int32, device=self.torch_device) if return_first_bad else None
             ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
             _check(self.lib.pbp_check_edges(self._h, ptr(A), ptr(B), n, float(max_step_size), float(padding), ptr(hit), ptr(fb), self._stream()))
-            out = hit.to(torch.bool)
+            out = hit
         else:
             A, B = self._host_q(Q1, self.nq), self._host_q(Q2, self.nq)
             n = A.shape[0]
@@ -335,7 +359,7 @@ class CollisionEngine:
             fb = np.zeros(n, dtype=np.int32) if return_first_bad else None
             ptr = lambda t: ctypes.c_void_p(t.ctypes.data) if t is not None else None
             _check(self.lib.pbp_check_edges_host(self._h, ptr(A), ptr(B), n, float(max_step_size), float(padding), ptr(hit), ptr(fb)))
-            out = hit.astype(bool)
+            out = hit.view(np.bool_)
         return (out, fb) if return_first_bad else out
 
     def check_paths(self, Q, offsets, padding=0.0):
@@ -346,12 +370,11 @@ class CollisionEngine:
         off = torch.as_tensor(np.asarray(offsets, dtype=np.int64) if not isinstance(offsets, torch.Tensor) else offsets,
                               device=self.torch_device).to(torch.int64).contiguous()
         n_paths = off.numel() - 1
-        hit = torch.empty(max(n_paths, 0), dtype=torch.uint8, device=self.torch_device)
+        hit = torch.empty(max(n_paths, 0), dtype=torch.bool, device=self.torch_device)
         if n_paths > 0:
             _check(self.lib.pbp_check_paths(self._h, ctypes.c_void_p(Qd.data_ptr()), ctypes.c_void_p(off.data_ptr()), n_paths,
                                             Qd.shape[0], float(padding), ctypes.c_void_p(hit.data_ptr()), self._stream()))
-        out = hit.to(torch.bool)
-        return out.cpu().numpy() if host else out
+        return hit.cpu().numpy() if host else hit
 
     def discretize(self, Q1, Q2, max_step_size):
         """(counts [E] int32, offsets [E+1] int64, states [sum(counts), nq]) on the input's side."""
@@ -385,6 +408,14 @@ class CollisionEngine:
         out = out[: found.value]
         self.last_sample_draws = drawn.value
         return out.cpu().numpy() if as_numpy else out
+
+
+def measure_fp32_peak(device=0):
+    """Measured FP32 FMA throughput of `device` in TFLOP/s (microbenchmark inside the library)."""
+    lib = load_library()
+    out = ctypes.c_double(0.0)
+    _check(lib.pbp_measure_fp32_peak(int(device), ctypes.byref(out)))
+    return out.value
 
 
 def get_engine(model, collision_model, device=None):
