@@ -254,7 +254,7 @@ def main():
     kernel_ms = max(np_ms, bp_ms)
     f_dom = F_NP_FLOP_PER_CONFIG if dominant == "k_narrowphase" else F_BP_FLOP_PER_CONFIG
     achieved_tflops = f_dom * states_per_launch / (kernel_ms * 1e-3) / 1e12
-    step_kernel_ms = bp_ms + np_ms
+    step_kernel_ms = bp_ms + np_ms + prof["item_setup_ms"] / rounds
     step_tflops = F_ALG_FLOP_PER_CONFIG * states_per_launch / (step_kernel_ms * 1e-3) / 1e12
     hbm_gbs = HBM_BYTES_PER_CONFIG * states_per_launch / (step_kernel_ms * 1e-3) / 1e9
     roofline = {
@@ -265,7 +265,7 @@ def main():
         "kernel_share_of_step": kernel_ms / step_kernel_ms if step_kernel_ms else None,
         "peak_source": "FFMA microbenchmark run in this process (pbp_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
         "note": "scalar FP32 geometry: neither HBM- nor tensor-bound (SURVEY.md 8d); bound = FP32 pipe",
-        "kernel_ms": {"k_broadphase": bp_ms, "k_narrowphase": np_ms},
+        "kernel_ms": {"k_broadphase": bp_ms, "k_item_setup": prof["item_setup_ms"] / rounds, "k_narrowphase": np_ms},
         "states_per_launch": states_per_launch,
         "narrowphase_items_per_state": prof["narrowphase_items"] / max(n * args.steps, 1),
         "flop_per_config": {"k_broadphase": F_BP_FLOP_PER_CONFIG, "k_narrowphase": F_NP_FLOP_PER_CONFIG},

@@ -72,7 +72,7 @@ typedef struct {
     const int32_t *geom_vert_off;  /* [ngeoms] first hull vertex (convex shapes) */
     const int32_t *geom_vert_cnt;  /* [ngeoms] hull vertex count */
     const float *geom_outer;       /* [ngeoms][4] enclosing sphere (cx cy cz r), geometry frame */
-    const float *geom_inner;       /* [ngeoms][4] inscribed sphere (cx cy cz r), geometry frame */
+    const float *geom_inner;       /* [ngeoms][4] inscribed sphere, SAME centre as geom_outer (cx cy cz r) */
     const float *verts;            /* [nverts][3] hull vertices, geometry frame */
     const int32_t *pairs;          /* [npairs][2] active collision pairs (first, second) */
     const int32_t *frame_parent;   /* [nframes] parent joint of each frame (may be NULL if nframes == 0) */
@@ -104,6 +104,7 @@ int pbp_get_stats(pbp_engine *e, pbp_stats *out, int reset);
  * on to report the dominant kernel's average launch duration for the roofline figure. */
 typedef struct {
     double broadphase_ms;      /* sum of k_broadphase launch durations */
+    double item_setup_ms;      /* sum of k_item_setup launch durations */
     double narrowphase_ms;     /* sum of k_narrowphase launch durations */
     int64_t rounds;            /* broadphase + narrowphase rounds timed */
     int64_t narrowphase_items; /* (state, pair) items that reached GJK */

@@ -65,18 +65,18 @@ struct pbp_engine {
     int device = 0;
     int num_sms = 0;
     int nq = 0, njoints = 0, ngeoms = 0, npairs = 0, nframes = 0, nmoving = 0, nverts_padded = 0;
-    bool small_tables = true;   // joints <= 16 and moving geoms <= 24 -> small local arrays
+    bool bp_smem_store = true;  // per-thread broadphase store fits in shared memory
     bool verts_in_smem = true;
     DevModel dm{};
-    DeviceBuffer d_joints, d_geoms, d_pairs, d_order, d_verts, d_qlim, d_frames;
+    DeviceBuffer d_joints, d_jgeoms, d_geoms, d_bpgeoms, d_bpboxes, d_bppairs, d_paths, d_pathops, d_order, d_verts, d_qlim, d_frames;
     // pipeline workspaces
     int64_t chunk = 0;  // states per broadphase/narrowphase round = bin capacity
-    DeviceBuffer d_bin_group, d_bin_sample, d_bin_T, d_ctrl;
+    DeviceBuffer d_bin_state, d_bin_group, d_bin_sample, d_bin_T, d_ctrl;
     DeviceBuffer d_counts, d_desc_group, d_desc_frac, d_desc_sample, d_scratch_i32, d_scratch_u8, d_cub, d_sel;
     DeviceBuffer d_io_q, d_io_q2, d_io_hit, d_io_f32, d_io_i32;   // staging for the *_host entry points
     unsigned long long *h_pinned = nullptr;  // small pinned mailbox for device -> host counters
-    size_t smem_bp = 0, smem_np = 0, smem_fk = 0;
-    int np_blocks = 0;
+    size_t smem_bp = 0, smem_is = 0, smem_np = 0, smem_fk = 0;
+    int np_blocks = 0, is_blocks = 0;
     pbp_stats stats{};
     // optional per-kernel timing
     bool profiling = false;
@@ -86,87 +86,76 @@ struct pbp_engine {
 
 namespace {
 
-// control block layout (uint32 words): [0, npairs) bin counts, [npairs] tile counter,
-// then two 64-bit counters (level total, emit cursor) at an 8-byte aligned offset.
+// control block layout (uint32 words): [0, npairs) bin counts, [npairs] item-setup tile counter,
+// [npairs + 1] narrowphase tile counter, then four 64-bit counters at an 8-byte aligned offset
+// (level total, emit cursor, select count, profiled item total).
+inline size_t ctrl_words(const pbp_engine *e) { return (size_t)e->npairs + 2; }
 inline uint32_t *ctrl_counts(pbp_engine *e) { return e->d_ctrl.as<uint32_t>(); }
-inline uint32_t *ctrl_tile(pbp_engine *e) { return e->d_ctrl.as<uint32_t>() + e->npairs; }
+inline uint32_t *ctrl_tile_setup(pbp_engine *e) { return e->d_ctrl.as<uint32_t>() + e->npairs; }
+inline uint32_t *ctrl_tile_np(pbp_engine *e) { return e->d_ctrl.as<uint32_t>() + e->npairs + 1; }
 inline unsigned long long *ctrl_u64(pbp_engine *e, int i) {
-    const size_t off = (((size_t)e->npairs + 1) * 4 + 7) & ~(size_t)7;
+    const size_t off = (ctrl_words(e) * 4 + 7) & ~(size_t)7;
     return reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(e->d_ctrl.p) + off) + i;
 }
-inline size_t ctrl_bytes(const pbp_engine *e) { return ((((size_t)e->npairs + 1) * 4 + 7) & ~(size_t)7) + 32; }
+inline size_t ctrl_bytes(const pbp_engine *e) { return ((ctrl_words(e) * 4 + 7) & ~(size_t)7) + 32; }
 
 inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
+#define LAUNCH_CHECK(what)                                                                                  \
+    do {                                                                                                    \
+        cudaError_t _le = cudaGetLastError();                                                               \
+        if (_le != cudaSuccess) return fail(PBP_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(_le)); \
+        e->stats.kernel_launches++;                                                                         \
+    } while (0)
+
 template <int MODE>
-int launch_broadphase(pbp_engine *e, const StateSource &src, int64_t n, float padding, const Outputs &out, const Bins &bins,
-                      cudaStream_t st) {
+int launch_round_kernels(pbp_engine *e, const StateSource &src, int64_t n, float padding, const Outputs &out, const Bins &bins,
+                         cudaEvent_t *ev, cudaStream_t st) {
     const unsigned grid = grid_for(n, BP_THREADS);
-    {
-        cudaError_t pending = cudaGetLastError();
-        if (pending != cudaSuccess) return fail(PBP_ERR_CUDA, "pending CUDA error before broadphase: %s", cudaGetErrorString(pending));
-    }
-    if (e->small_tables)
-        k_broadphase<16, 24, MODE><<<grid, BP_THREADS, e->smem_bp, st>>>(e->dm, src, n, padding, out, bins);
+    const bool has_sample = src.sample != nullptr;
+    if (e->bp_smem_store)
+        k_broadphase<MODE, true><<<grid, BP_THREADS, e->smem_bp, st>>>(e->dm, src, n, padding, out, bins);
     else
-        k_broadphase<PBP_MAX_JOINTS, PBP_MAX_GEOMS, MODE><<<grid, BP_THREADS, e->smem_bp, st>>>(e->dm, src, n, padding, out, bins);
-    {
-        cudaError_t le = cudaGetLastError();
-        if (le != cudaSuccess)
-            return fail(PBP_ERR_CUDA, "broadphase launch failed: %s (mode %d, n %lld, grid %u, smem %zu)", cudaGetErrorString(le),
-                        MODE, (long long)n, grid, e->smem_bp);
-    }
-    e->stats.kernel_launches++;
-    return 0;
-}
-
-template <int MODE>
-int launch_narrowphase(pbp_engine *e, float padding, const Outputs &out, const Bins &bins, bool has_sample, cudaStream_t st) {
+        k_broadphase<MODE, false><<<grid, BP_THREADS, e->smem_bp, st>>>(e->dm, src, n, padding, out, bins);
+    LAUNCH_CHECK("k_broadphase");
+    if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
+    k_item_setup<MODE><<<e->is_blocks, IS_THREADS, e->smem_is, st>>>(e->dm, src, out, bins, ctrl_tile_setup(e));
+    LAUNCH_CHECK("k_item_setup");
+    if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
     if (e->verts_in_smem)
-        k_narrowphase<MODE, true><<<e->np_blocks, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_tile(e), has_sample);
+        k_narrowphase<MODE, true><<<e->np_blocks, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_tile_np(e), has_sample);
     else
-        k_narrowphase<MODE, false><<<e->np_blocks, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_tile(e), has_sample);
-    CUDA_TRY(cudaGetLastError());
-    e->stats.kernel_launches++;
+        k_narrowphase<MODE, false><<<e->np_blocks, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_tile_np(e), has_sample);
+    LAUNCH_CHECK("k_narrowphase");
     return 0;
 }
 
-// One broadphase + narrowphase round over n <= chunk states.
+// One broadphase -> item setup -> narrowphase round over n <= chunk states.
 int run_round(pbp_engine *e, int mode, const StateSource &src, int64_t n, float padding, const Outputs &out, cudaStream_t st) {
     if (n <= 0) return 0;
     if (e->npairs == 0) return 0;  // nothing can collide; outputs were initialised by the caller
     Bins bins;
+    bins.state = e->d_bin_state.as<int32_t>();
     bins.group = e->d_bin_group.as<int32_t>();
     bins.sample = e->d_bin_sample.as<int32_t>();
     bins.T = e->d_bin_T.as<float>();
     bins.count = ctrl_counts(e);
     bins.cap = e->chunk;
-    CUDA_TRY(cudaMemsetAsync(e->d_ctrl.p, 0, ((size_t)e->npairs + 1) * 4, st));
+    CUDA_TRY(cudaMemsetAsync(e->d_ctrl.p, 0, ctrl_words(e) * 4, st));
     int rc;
-    const bool has_sample = src.sample != nullptr;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (e->profiling) {
-        for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
+        for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
         CUDA_TRY(cudaEventRecord(ev[0], st));
     }
-#define PROF_MID() do { if (e->profiling) CUDA_TRY(cudaEventRecord(ev[1], st)); } while (0)
-    if (mode == MODE_BOOL) {
-        if ((rc = launch_broadphase<MODE_BOOL>(e, src, n, padding, out, bins, st))) return rc;
-        PROF_MID();
-        if ((rc = launch_narrowphase<MODE_BOOL>(e, padding, out, bins, has_sample, st))) return rc;
-    } else if (mode == MODE_BOOL_ALL) {
-        if ((rc = launch_broadphase<MODE_BOOL_ALL>(e, src, n, padding, out, bins, st))) return rc;
-        PROF_MID();
-        if ((rc = launch_narrowphase<MODE_BOOL_ALL>(e, padding, out, bins, has_sample, st))) return rc;
-    } else {
-        if ((rc = launch_broadphase<MODE_DIST>(e, src, n, padding, out, bins, st))) return rc;
-        PROF_MID();
-        if ((rc = launch_narrowphase<MODE_DIST>(e, padding, out, bins, has_sample, st))) return rc;
-    }
-#undef PROF_MID
+    cudaEvent_t *evp = e->profiling ? ev : nullptr;
+    if (mode == MODE_BOOL) rc = launch_round_kernels<MODE_BOOL>(e, src, n, padding, out, bins, evp, st);
+    else if (mode == MODE_BOOL_ALL) rc = launch_round_kernels<MODE_BOOL_ALL>(e, src, n, padding, out, bins, evp, st);
+    else rc = launch_round_kernels<MODE_DIST>(e, src, n, padding, out, bins, evp, st);
+    if (rc) return rc;
     if (e->profiling) {
-        CUDA_TRY(cudaEventRecord(ev[2], st));
-        for (int i = 0; i < 3; i++) e->prof_events.push_back(ev[i]);
+        CUDA_TRY(cudaEventRecord(ev[3], st));
+        for (int i = 0; i < 4; i++) e->prof_events.push_back(ev[i]);
         k_sum_counts<<<1, 256, 0, st>>>(bins.count, e->npairs, ctrl_u64(e, 3));
         e->stats.kernel_launches++;
     }
@@ -208,15 +197,17 @@ int pbp_set_profiling(pbp_engine *e, int enabled) {
 int pbp_get_profile(pbp_engine *e, pbp_profile *out, int reset) {
     if (!e || !out) return fail(PBP_ERR_ARG, "NULL argument");
     CUDA_TRY(cudaSetDevice(e->device));
-    for (size_t i = 0; i + 2 < e->prof_events.size(); i += 3) {
-        float a = 0.f, b = 0.f;
-        CUDA_TRY(cudaEventSynchronize(e->prof_events[i + 2]));
+    for (size_t i = 0; i + 3 < e->prof_events.size(); i += 4) {
+        float a = 0.f, b = 0.f, c = 0.f;
+        CUDA_TRY(cudaEventSynchronize(e->prof_events[i + 3]));
         CUDA_TRY(cudaEventElapsedTime(&a, e->prof_events[i], e->prof_events[i + 1]));
         CUDA_TRY(cudaEventElapsedTime(&b, e->prof_events[i + 1], e->prof_events[i + 2]));
+        CUDA_TRY(cudaEventElapsedTime(&c, e->prof_events[i + 2], e->prof_events[i + 3]));
         e->prof.broadphase_ms += a;
-        e->prof.narrowphase_ms += b;
+        e->prof.item_setup_ms += b;
+        e->prof.narrowphase_ms += c;
         e->prof.rounds++;
-        for (int k = 0; k < 3; k++) cudaEventDestroy(e->prof_events[i + k]);
+        for (int k = 0; k < 4; k++) cudaEventDestroy(e->prof_events[i + k]);
     }
     e->prof_events.clear();
     unsigned long long items = 0;
@@ -234,7 +225,8 @@ void pbp_engine_destroy(pbp_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
-    DeviceBuffer *bufs[] = {&e->d_joints, &e->d_geoms, &e->d_pairs, &e->d_order, &e->d_verts, &e->d_qlim, &e->d_frames,
+    DeviceBuffer *bufs[] = {&e->d_joints, &e->d_jgeoms, &e->d_geoms, &e->d_bpgeoms, &e->d_bpboxes, &e->d_bppairs, &e->d_paths,
+                            &e->d_pathops, &e->d_order, &e->d_verts, &e->d_qlim, &e->d_frames, &e->d_bin_state,
                             &e->d_bin_group, &e->d_bin_sample, &e->d_bin_T, &e->d_ctrl, &e->d_counts, &e->d_desc_group,
                             &e->d_desc_frac, &e->d_desc_sample, &e->d_scratch_i32, &e->d_scratch_u8, &e->d_cub, &e->d_sel,
                             &e->d_io_q, &e->d_io_q2, &e->d_io_hit, &e->d_io_f32, &e->d_io_i32};
@@ -264,85 +256,156 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     e->num_sms = prop.multiProcessorCount;
     e->nq = d->nq; e->njoints = d->njoints; e->ngeoms = d->ngeoms; e->npairs = d->npairs; e->nframes = d->nframes;
 
-    // ---- joints
+    auto bail = [&](int code) { pbp_engine_destroy(e); return code; };
+
+    // ---- joints (+ which transforms the broadphase must keep for non-adjacent children)
     std::vector<DevJoint> joints(d->njoints);
     for (int j = 0; j < d->njoints; j++) {
         DevJoint &J = joints[j];
+        memset(&J, 0, sizeof J);
         memcpy(J.P, d->joint_placement + 12 * j, sizeof J.P);
         memcpy(J.axis, d->joint_axis + 3 * j, sizeof J.axis);
         J.parent = d->joint_parent[j];
         J.type = d->joint_type[j];
         J.idx_q = d->joint_idx_q[j];
-        J.chain = (j > 0 && J.parent == j - 1) ? 1 : 0;
         J.axis_code = 0;
         for (int k = 0; k < 3; k++) {
             const float a = J.axis[k], b = J.axis[(k + 1) % 3], c = J.axis[(k + 2) % 3];
             if (fabsf(fabsf(a) - 1.0f) < 1e-7f && b == 0.0f && c == 0.0f) J.axis_code = k + 1;
         }
-        if (j > 0 && (J.parent < 0 || J.parent >= j)) { delete e; return fail(PBP_ERR_ARG, "joint %d: parent %d not topologically ordered", j, J.parent); }
-        if (j > 0 && (J.idx_q < 0 || J.idx_q >= d->nq)) { delete e; return fail(PBP_ERR_ARG, "joint %d: idx_q %d out of range", j, J.idx_q); }
+        J.parent_slot = -1;
+        J.save_slot = -1;
+        if (j > 0 && (J.parent < 0 || J.parent >= j)) return bail(fail(PBP_ERR_ARG, "joint %d: parent %d not topologically ordered", j, J.parent));
+        if (j > 0 && (J.idx_q < 0 || J.idx_q >= d->nq)) return bail(fail(PBP_ERR_ARG, "joint %d: idx_q %d out of range", j, J.idx_q));
+        if (j > 0 && J.type != PBP_JOINT_REVOLUTE && J.type != PBP_JOINT_PRISMATIC) return bail(fail(PBP_ERR_ARG, "joint %d: unsupported type %d", j, J.type));
     }
-    // ---- geometries (+ padded vertex table)
-    std::vector<DevGeom> geoms(d->ngeoms);
+    int nsave = 0;
+    for (int j = 1; j < d->njoints; j++) {
+        DevJoint &J = joints[j];
+        if (J.parent == 0) J.parent_slot = -2;
+        else if (J.parent == j - 1) J.parent_slot = -1;
+        else {
+            if (joints[J.parent].save_slot < 0) joints[J.parent].save_slot = nsave++;
+            J.parent_slot = joints[J.parent].save_slot;
+        }
+    }
+    if (nsave > BP_MAX_SAVES) return bail(fail(PBP_ERR_CAPACITY, "kinematic tree has %d branch points (max %d)", nsave, BP_MAX_SAVES));
+
+    // ---- geometries: narrowphase view, broadphase proxies, static boxes, padded vertex table
+    std::vector<DevGeom> geoms(std::max(d->ngeoms, 1));
+    std::vector<BpGeom> bpgeoms(std::max(d->ngeoms, 1));
+    std::vector<BpBox> bpboxes;
     std::vector<float4> verts;
+    std::vector<int32_t> jgeoms;
     int nmoving = 0;
     for (int g = 0; g < d->ngeoms; g++) {
         DevGeom &G = geoms[g];
+        BpGeom &B = bpgeoms[g];
         memset(&G, 0, sizeof G);
+        memset(&B, 0, sizeof B);
         memcpy(G.P, d->geom_placement + 12 * g, sizeof G.P);
         memcpy(G.par, d->geom_params + 4 * g, sizeof G.par);
-        memcpy(G.outer, d->geom_outer + 4 * g, sizeof G.outer);
-        memcpy(G.inner, d->geom_inner + 4 * g, sizeof G.inner);
+        const float *outer = d->geom_outer + 4 * g, *inner = d->geom_inner + 4 * g;
+        for (int i = 0; i < 3; i++)
+            if (fabsf(outer[i] - inner[i]) > 1e-6f) return bail(fail(PBP_ERR_ARG, "geometry %d: geom_inner must share the centre of geom_outer", g));
+        if (!(inner[3] <= outer[3])) return bail(fail(PBP_ERR_ARG, "geometry %d: inscribed radius exceeds enclosing radius", g));
+        memcpy(G.centre, outer, sizeof G.centre);
         G.parent = d->geom_parent[g];
         G.shape = d->geom_shape[g];
-        if (G.parent < 0 || G.parent >= d->njoints) { delete e; return fail(PBP_ERR_ARG, "geometry %d: bad parent joint", g); }
-        G.identity = 1;
-        for (int i = 0; i < 12; i++) {
-            const float id = (i == 0 || i == 4 || i == 8) ? 1.f : 0.f;
-            if (G.P[i] != id) G.identity = 0;
-        }
+        if (G.parent < 0 || G.parent >= d->njoints) return bail(fail(PBP_ERR_ARG, "geometry %d: bad parent joint", g));
+        if (G.shape < PBP_SHAPE_SPHERE || G.shape > PBP_SHAPE_CONVEX) return bail(fail(PBP_ERR_ARG, "geometry %d: bad shape %d", g, G.shape));
         G.core_radius = (G.shape == PBP_SHAPE_SPHERE || G.shape == PBP_SHAPE_CAPSULE) ? G.par[0] : 0.f;
-        if (G.parent == 0) {
-            G.slot = -1;
-            // static geometry: sphere centres are stored in world coordinates
-            for (int s = 0; s < 2; s++) {
-                float *c = s == 0 ? G.outer : G.inner;
-                float w[3];
-                for (int i = 0; i < 3; i++) w[i] = G.P[3 * i] * c[0] + G.P[3 * i + 1] * c[1] + G.P[3 * i + 2] * c[2] + G.P[9 + i];
-                c[0] = w[0]; c[1] = w[1]; c[2] = w[2];
-            }
-        } else {
-            G.slot = nmoving++;
+        // proxy centre in the parent-joint frame (= world frame for static geometries)
+        for (int i = 0; i < 3; i++) B.c[i] = G.P[3 * i] * outer[0] + G.P[3 * i + 1] * outer[1] + G.P[3 * i + 2] * outer[2] + G.P[9 + i];
+        B.r_out = outer[3];
+        B.r_in = inner[3];
+        B.slot = G.parent == 0 ? -1 : nmoving++;
+        B.box = -1;
+        if (G.parent == 0 && G.shape == PBP_SHAPE_BOX) {
+            BpBox bx;
+            memset(&bx, 0, sizeof bx);
+            memcpy(bx.R, G.P, sizeof bx.R);
+            memcpy(bx.t, G.P + 9, sizeof bx.t);
+            memcpy(bx.h, G.par, sizeof bx.h);
+            B.box = (int)bpboxes.size();
+            bpboxes.push_back(bx);
         }
         if (G.shape == PBP_SHAPE_CONVEX) {
             const int off = d->geom_vert_off[g], cnt = d->geom_vert_cnt[g];
-            if (cnt < 1 || off < 0 || off + cnt > d->nverts) { delete e; return fail(PBP_ERR_ARG, "geometry %d: bad vertex range", g); }
+            if (cnt < 1 || off < 0 || off + cnt > d->nverts) return bail(fail(PBP_ERR_ARG, "geometry %d: bad vertex range", g));
             G.vert_off = (int)verts.size();
             for (int i = 0; i < cnt; i++) verts.push_back(make_float4(d->verts[3 * (off + i)], d->verts[3 * (off + i) + 1], d->verts[3 * (off + i) + 2], 0.f));
             while (verts.size() % 4) verts.push_back(verts.back());
             G.vert_cnt = (int)verts.size() - G.vert_off;
         }
     }
+    // moving geometries grouped by parent joint (the broadphase places them right after that joint)
+    for (int j = 1; j < d->njoints; j++) {
+        joints[j].geom_begin = (int)jgeoms.size();
+        for (int g = 0; g < d->ngeoms; g++)
+            if (geoms[g].parent == j) jgeoms.push_back(g);
+        joints[j].geom_end = (int)jgeoms.size();
+    }
     if (verts.empty()) verts.push_back(make_float4(0, 0, 0, 0));
+    if (bpboxes.empty()) bpboxes.push_back(BpBox{});
+    if (jgeoms.empty()) jgeoms.push_back(0);
     e->nmoving = nmoving;
     e->nverts_padded = (int)verts.size();
-    e->small_tables = d->njoints <= 16 && nmoving <= 24;
-    // ---- pairs + bin order (most expensive narrowphase first, for load balance)
-    std::vector<DevPair> pairs(std::max(d->npairs, 1));
-    std::vector<int32_t> order(std::max(d->npairs, 1), 0);
-    std::vector<long> cost(std::max(d->npairs, 1), 0);
+
+    // ---- pairs: broadphase recipe, joint path for the item setup, bin order
+    const int np1 = std::max(d->npairs, 1);
+    std::vector<BpPair> bppairs(np1);
+    std::vector<PairPath> paths(np1);
+    std::vector<uint8_t> pathops;
+    std::vector<int32_t> order(np1, 0);
+    std::vector<long> cost(np1, 0);
+    auto chain_to_root = [&](int j) {  // joints from the root down to j (empty for the universe)
+        std::vector<int> c;
+        for (; j > 0; j = joints[j].parent) c.push_back(j);
+        std::reverse(c.begin(), c.end());
+        return c;
+    };
     for (int p = 0; p < d->npairs; p++) {
         const int a = d->pairs[2 * p], b = d->pairs[2 * p + 1];
-        if (a < 0 || b < 0 || a >= d->ngeoms || b >= d->ngeoms || a == b) { delete e; return fail(PBP_ERR_ARG, "pair %d: bad geometry ids", p); }
-        pairs[p].a = (int16_t)a; pairs[p].b = (int16_t)b; pairs[p]._pad = 0;
+        if (a < 0 || b < 0 || a >= d->ngeoms || b >= d->ngeoms || a == b) return bail(fail(PBP_ERR_ARG, "pair %d: bad geometry ids", p));
+        BpPair &P = bppairs[p];
+        memset(&P, 0, sizeof P);
+        P.a = (uint8_t)a;
+        P.b = (uint8_t)b;
+        P.box = -1;
         const int sa = geoms[a].shape, sb = geoms[b].shape;
-        if (sa == PBP_SHAPE_SPHERE && sb == PBP_SHAPE_SPHERE) pairs[p].kind = BP_EXACT_SPHERES;
-        else if (sa == PBP_SHAPE_BOX) pairs[p].kind = BP_BOX_A;
-        else if (sb == PBP_SHAPE_BOX) pairs[p].kind = BP_BOX_B;
-        else pairs[p].kind = BP_SPHERES;
+        if (sa == PBP_SHAPE_SPHERE && sb == PBP_SHAPE_SPHERE) {
+            P.kind = BP_EXACT_SPHERES;
+            P.r_out = P.r_in = geoms[a].par[0] + geoms[b].par[0];
+        } else if (bpgeoms[a].box >= 0) {
+            P.kind = BP_BOX_A;
+            P.box = bpgeoms[a].box;
+            P.r_out = bpgeoms[b].r_out;
+            P.r_in = bpgeoms[b].r_in;
+        } else if (bpgeoms[b].box >= 0) {
+            P.kind = BP_BOX_B;
+            P.box = bpgeoms[b].box;
+            P.r_out = bpgeoms[a].r_out;
+            P.r_in = bpgeoms[a].r_in;
+        } else {
+            P.kind = BP_SPHERES;
+            P.r_out = bpgeoms[a].r_out + bpgeoms[b].r_out;
+            P.r_in = bpgeoms[a].r_in + bpgeoms[b].r_in;
+        }
+        const std::vector<int> ca = chain_to_root(geoms[a].parent), cb = chain_to_root(geoms[b].parent);
+        size_t common = 0;
+        while (common < ca.size() && common < cb.size() && ca[common] == cb[common]) common++;
+        paths[p].off = (int32_t)pathops.size();
+        paths[p].n_trunk = (uint8_t)common;
+        paths[p].n_a = (uint8_t)(ca.size() - common);
+        paths[p].n_b = (uint8_t)(cb.size() - common);
+        for (size_t i = 0; i < ca.size(); i++) pathops.push_back((uint8_t)ca[i]);
+        for (size_t i = common; i < cb.size(); i++) pathops.push_back((uint8_t)cb[i]);
         cost[p] = 8 + geoms[a].vert_cnt + geoms[b].vert_cnt;
         order[p] = p;
     }
+    if (pathops.empty()) pathops.push_back(0);
+    while (pathops.size() % 4) pathops.push_back(0);
     std::stable_sort(order.begin(), order.begin() + d->npairs, [&](int x, int y) { return cost[x] > cost[y]; });
 
     auto upload = [&](DeviceBuffer &buf, const void *src, size_t bytes) -> int {
@@ -354,71 +417,86 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     };
     std::vector<float> qlim(2 * d->nq);
     for (int i = 0; i < d->nq; i++) { qlim[i] = d->q_lower ? d->q_lower[i] : 0.f; qlim[d->nq + i] = d->q_upper ? d->q_upper[i] : 0.f; }
-    std::vector<float> frames(std::max(d->nframes, 1) * 13, 0.f);
     std::vector<int32_t> fparent(std::max(d->nframes, 1), 0);
     for (int f = 0; f < d->nframes; f++) {
         fparent[f] = d->frame_parent[f];
-        if (fparent[f] < 0 || fparent[f] >= d->njoints) { delete e; return fail(PBP_ERR_ARG, "frame %d: bad parent joint", f); }
+        if (fparent[f] < 0 || fparent[f] >= d->njoints) return bail(fail(PBP_ERR_ARG, "frame %d: bad parent joint", f));
     }
     int rc = 0;
     if ((rc = upload(e->d_joints, joints.data(), joints.size() * sizeof(DevJoint))) ||
-        (rc = upload(e->d_geoms, geoms.data(), std::max<size_t>(geoms.size(), 1) * sizeof(DevGeom))) ||
-        (rc = upload(e->d_pairs, pairs.data(), pairs.size() * sizeof(DevPair))) ||
+        (rc = upload(e->d_jgeoms, jgeoms.data(), jgeoms.size() * 4)) ||
+        (rc = upload(e->d_geoms, geoms.data(), geoms.size() * sizeof(DevGeom))) ||
+        (rc = upload(e->d_bpgeoms, bpgeoms.data(), bpgeoms.size() * sizeof(BpGeom))) ||
+        (rc = upload(e->d_bpboxes, bpboxes.data(), bpboxes.size() * sizeof(BpBox))) ||
+        (rc = upload(e->d_bppairs, bppairs.data(), bppairs.size() * sizeof(BpPair))) ||
+        (rc = upload(e->d_paths, paths.data(), paths.size() * sizeof(PairPath))) ||
+        (rc = upload(e->d_pathops, pathops.data(), pathops.size())) ||
         (rc = upload(e->d_order, order.data(), order.size() * sizeof(int32_t))) ||
         (rc = upload(e->d_verts, verts.data(), verts.size() * sizeof(float4))) ||
-        (rc = upload(e->d_qlim, qlim.data(), qlim.size() * sizeof(float)))) {
-        pbp_engine_destroy(e);
-        return rc;
-    }
+        (rc = upload(e->d_qlim, qlim.data(), qlim.size() * sizeof(float))))
+        return bail(rc);
     {
         // frames: [nframes] int32 parents followed (16-byte aligned) by [nframes][12] placements
         const size_t poff = (((size_t)std::max(d->nframes, 1) * 4) + 15) & ~(size_t)15;
         std::vector<unsigned char> blob(poff + (size_t)std::max(d->nframes, 1) * 48, 0);
         memcpy(blob.data(), fparent.data(), (size_t)std::max(d->nframes, 1) * 4);
         if (d->nframes > 0) memcpy(blob.data() + poff, d->frame_placement, (size_t)d->nframes * 48);
-        if ((rc = upload(e->d_frames, blob.data(), blob.size()))) { pbp_engine_destroy(e); return rc; }
+        if ((rc = upload(e->d_frames, blob.data(), blob.size()))) return bail(rc);
         e->dm.frame_parent = e->d_frames.as<int32_t>();
         e->dm.frame_placement = reinterpret_cast<const float *>(reinterpret_cast<char *>(e->d_frames.p) + poff);
     }
     e->dm.nq = d->nq; e->dm.njoints = d->njoints; e->dm.ngeoms = d->ngeoms; e->dm.npairs = d->npairs;
-    e->dm.nverts_padded = e->nverts_padded; e->dm.nframes = d->nframes; e->dm.nmoving = nmoving;
+    e->dm.nverts_padded = e->nverts_padded; e->dm.nframes = d->nframes; e->dm.nmoving = nmoving; e->dm.nsave = nsave;
+    e->dm.nboxes = (int)bpboxes.size();
     e->dm.joints = e->d_joints.as<DevJoint>();
+    e->dm.joint_geoms = e->d_jgeoms.as<int32_t>();
     e->dm.geoms = e->d_geoms.as<DevGeom>();
-    e->dm.pairs = e->d_pairs.as<DevPair>();
+    e->dm.bpgeoms = e->d_bpgeoms.as<BpGeom>();
+    e->dm.bpboxes = e->d_bpboxes.as<BpBox>();
+    e->dm.bppairs = e->d_bppairs.as<BpPair>();
+    e->dm.paths = e->d_paths.as<PairPath>();
+    e->dm.path_ops = e->d_pathops.as<uint8_t>();
     e->dm.bin_order = e->d_order.as<int32_t>();
     e->dm.verts = e->d_verts.as<float4>();
     e->dm.q_lower = e->d_qlim.as<float>();
     e->dm.q_upper = e->d_qlim.as<float>() + d->nq;
 
     // ---- shared memory budgets and launch geometry
-    const size_t tables = (size_t)d->njoints * sizeof(DevJoint) + (size_t)d->ngeoms * sizeof(DevGeom) +
-                          (size_t)((d->npairs + 1) & ~1) * sizeof(DevPair);
-    e->smem_bp = tables + (size_t)BP_THREADS * d->nq * sizeof(float) + 16;
-    e->smem_fk = (size_t)d->njoints * sizeof(DevJoint) + (size_t)d->ngeoms * sizeof(DevGeom);
-    const size_t np_tables = (size_t)d->ngeoms * sizeof(DevGeom) + (size_t)((d->npairs + 1) & ~1) * sizeof(DevPair) +
-                             ((size_t)d->npairs + 1) * 4 + (size_t)std::max(d->npairs, 1) * 4 + 16;
-    const size_t vert_bytes = (size_t)e->nverts_padded * sizeof(float4);
+    const size_t max_optin = prop.sharedMemPerBlockOptin;
+    const size_t bp_tables = bp_table_bytes(d->njoints, nmoving, d->ngeoms, e->dm.nboxes, d->npairs, d->nq);
+    const size_t bp_store = (size_t)(nmoving * 3 + nsave * 12) * BP_THREADS * 4;
+    e->bp_smem_store = bp_tables + bp_store <= 100 * 1024 && nmoving <= BP_MAX_LOCAL_CENTRES;
+    e->smem_bp = bp_tables + (e->bp_smem_store ? bp_store : 0) + 16;
+    e->smem_fk = align16((size_t)d->njoints * sizeof(DevJoint)) + align16((size_t)np1 * 0 + (size_t)std::max(d->ngeoms, 1) * sizeof(DevGeom));
+    const size_t tile_tables = align16(((size_t)d->npairs + 1) * 4) + align16((size_t)np1 * 4);
+    e->smem_is = align16((size_t)d->njoints * sizeof(DevJoint)) + align16((size_t)std::max(d->ngeoms, 1) * sizeof(DevGeom)) +
+                 align16((size_t)np1 * sizeof(BpPair)) + align16((size_t)np1 * sizeof(PairPath)) + tile_tables + 16;
+    const size_t np_tables = align16((size_t)std::max(d->ngeoms, 1) * sizeof(DevGeom)) + align16((size_t)np1 * sizeof(BpPair)) + tile_tables + 16;
+    const size_t vert_bytes = align16((size_t)e->nverts_padded * sizeof(float4));
     e->verts_in_smem = np_tables + vert_bytes <= 96 * 1024;
     e->smem_np = np_tables + (e->verts_in_smem ? vert_bytes : 0);
-    const size_t max_optin = prop.sharedMemPerBlockOptin;
-    if (e->smem_bp > max_optin || e->smem_np > max_optin) { pbp_engine_destroy(e); return fail(PBP_ERR_CAPACITY, "model tables exceed shared memory (%zu / %zu bytes)", e->smem_bp, e->smem_np); }
-// The dynamic shared-memory cap is a per-function attribute shared by every engine of the
+    if (e->smem_bp > max_optin || e->smem_np > max_optin || e->smem_is > max_optin)
+        return bail(fail(PBP_ERR_CAPACITY, "model tables exceed shared memory (%zu / %zu / %zu bytes)", e->smem_bp, e->smem_is, e->smem_np));
+    // The dynamic shared-memory cap is a per-function attribute shared by every engine of the
     // process: raise it to the device's opt-in maximum once (a per-engine value would lower
     // the cap under another engine's feet).
 #define SET_SMEM(kern) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_optin))
-    SET_SMEM((k_broadphase<16, 24, MODE_BOOL>));
-    SET_SMEM((k_broadphase<16, 24, MODE_BOOL_ALL>));
-    SET_SMEM((k_broadphase<16, 24, MODE_DIST>));
-    SET_SMEM((k_broadphase<PBP_MAX_JOINTS, PBP_MAX_GEOMS, MODE_BOOL>));
-    SET_SMEM((k_broadphase<PBP_MAX_JOINTS, PBP_MAX_GEOMS, MODE_BOOL_ALL>));
-    SET_SMEM((k_broadphase<PBP_MAX_JOINTS, PBP_MAX_GEOMS, MODE_DIST>));
+    SET_SMEM((k_broadphase<MODE_BOOL, true>));
+    SET_SMEM((k_broadphase<MODE_BOOL_ALL, true>));
+    SET_SMEM((k_broadphase<MODE_DIST, true>));
+    SET_SMEM((k_broadphase<MODE_BOOL, false>));
+    SET_SMEM((k_broadphase<MODE_BOOL_ALL, false>));
+    SET_SMEM((k_broadphase<MODE_DIST, false>));
+    SET_SMEM((k_item_setup<MODE_BOOL>));
+    SET_SMEM((k_item_setup<MODE_BOOL_ALL>));
+    SET_SMEM((k_item_setup<MODE_DIST>));
     SET_SMEM((k_narrowphase<MODE_BOOL, true>));
     SET_SMEM((k_narrowphase<MODE_BOOL_ALL, true>));
     SET_SMEM((k_narrowphase<MODE_DIST, true>));
     SET_SMEM((k_narrowphase<MODE_BOOL, false>));
     SET_SMEM((k_narrowphase<MODE_BOOL_ALL, false>));
     SET_SMEM((k_narrowphase<MODE_DIST, false>));
-    SET_SMEM((k_fk_output<PBP_MAX_JOINTS>));
+    SET_SMEM(k_fk_output);
 #undef SET_SMEM
     int occ = 1;
     if (e->verts_in_smem)
@@ -426,9 +504,11 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     else
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrowphase<MODE_BOOL, false>, NP_THREADS, e->smem_np));
     e->np_blocks = e->num_sms * std::max(occ, 1);
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_item_setup<MODE_BOOL>, IS_THREADS, e->smem_is));
+    e->is_blocks = e->num_sms * std::max(occ, 1);
 
     // ---- bins: one slot per (state of a chunk, pair)
-    const size_t item_bytes = 4 + 4 + 48;
+    const size_t item_bytes = 4 + 4 + 4 + 48;
     int64_t chunk = max_chunk_states > 0 ? max_chunk_states : (int64_t)1 << 20;
     const size_t budget = (size_t)6 << 30;
     if (d->npairs > 0) {
@@ -437,12 +517,10 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     }
     chunk = (chunk + 255) & ~(int64_t)255;
     e->chunk = chunk;
-    const size_t slots = (size_t)std::max(d->npairs, 1) * (size_t)chunk;
-    if ((rc = e->d_bin_group.ensure(slots * 4)) || (rc = e->d_bin_sample.ensure(slots * 4)) ||
-        (rc = e->d_bin_T.ensure(slots * 48)) || (rc = e->d_ctrl.ensure(ctrl_bytes(e)))) {
-        pbp_engine_destroy(e);
-        return rc;
-    }
+    const size_t slots = (size_t)np1 * (size_t)chunk;
+    if ((rc = e->d_bin_state.ensure(slots * 4)) || (rc = e->d_bin_group.ensure(slots * 4)) || (rc = e->d_bin_sample.ensure(slots * 4)) ||
+        (rc = e->d_bin_T.ensure(slots * 48)) || (rc = e->d_ctrl.ensure(ctrl_bytes(e))))
+        return bail(rc);
     CUDA_TRY(cudaMemset(e->d_ctrl.p, 0, ctrl_bytes(e)));
     CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&e->h_pinned), 64));
     *out = e;
@@ -456,7 +534,7 @@ int pbp_fk(pbp_engine *e, const float *q_dev, int64_t n, float *oMi_dev, float *
     if (n == 0) return 0;
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
-    k_fk_output<PBP_MAX_JOINTS><<<grid_for(n, BP_THREADS), BP_THREADS, e->smem_fk, st>>>(e->dm, q_dev, n, oMi_dev, oMg_dev, oMf_dev);
+    k_fk_output<<<grid_for(n, 128), 128, e->smem_fk, st>>>(e->dm, q_dev, n, oMi_dev, oMg_dev, oMf_dev);
     CUDA_TRY(cudaGetLastError());
     e->stats.kernel_launches++;
     return 0;

@@ -179,73 +179,84 @@ struct GjkOut {
 #define PBP_GJK_TOL 1e-6f       // ub - lb convergence (metres)
 #define PBP_GJK_EPS_ABS2 2.5e-13f  // |v|^2 below this counts as contact (|v| < 5e-7 m)
 
-// T: placement of B in A's frame.  v0: initial search direction (centre of A - centre of B, A frame).
-// WANT_DIST = false: stop as soon as "distance > margin" or "distance <= margin" is certain.
+// Per-item GJK state: lives in registers of the owning lane between iterations, so a warp can
+// run "one iteration for every active lane" and refill finished lanes with new items.
+struct GjkState {
+    float3 v;            // current closest point of the simplex (search direction is -v)
+    float vv;            // |v|^2
+    float3 W0, W1, W2;   // simplex vertices (Minkowski-difference points), n of them valid
+    int n, it, stalls;
+};
+
+__device__ __forceinline__ void gjk_init(GjkState &s, float3 v0) {
+    s.v = v0;
+    s.vv = dot3(v0, v0);
+    if (!(s.vv > 1e-12f)) { s.v = make_float3(1.f, 0.f, 0.f); s.vv = 1.f; }
+    s.W0 = s.W1 = s.W2 = make_float3(0.f, 0.f, 0.f);
+    s.n = 0; s.it = 0; s.stalls = 0;
+}
+
+// One GJK iteration.  T: placement of B in A's frame.  Returns true when the item is finished
+// (out is then valid).
+// WANT_DIST = false: finish as soon as "distance > margin" or "distance <= margin" is certain.
 // WANT_DIST = true : run to convergence unless the pair is certainly farther than `bound`.
 template <bool WANT_DIST>
-__device__ __forceinline__ GjkOut gjk_run(const ShapeRef &A, const ShapeRef &B, const float *T, float3 v, float margin,
-                                          float bound) {
-    GjkOut out;
-    float vv = dot3(v, v);
-    if (!(vv > 1e-12f)) { v = make_float3(1.f, 0.f, 0.f); vv = 1.f; }
-    float3 W0 = make_float3(0, 0, 0), W1 = W0, W2 = W0, W3 = W0;
-    int n = 0;
-    const float m2 = margin * margin;
+__device__ __forceinline__ bool gjk_step(const ShapeRef &A, const ShapeRef &B, const float *T, GjkState &s, float margin,
+                                         float bound, GjkOut &out) {
+    const float3 v = s.v;
+    const float vv = s.vv;
+    const int n = s.n;
     const float cut = WANT_DIST ? bound : margin;
-    const float cut2 = cut * cut;
-    int it = 0, stalls = 0;
-    bool enclosed = false;
-    for (; it < PBP_GJK_MAX_ITERS; it++) {
-        // support of (A - B) in direction -v
-        const float3 sa = support_local(A, make_float3(-v.x, -v.y, -v.z));
-        const float3 db = make_float3(fmaf(T[0], v.x, fmaf(T[3], v.y, T[6] * v.z)), fmaf(T[1], v.x, fmaf(T[4], v.y, T[7] * v.z)),
-                                      fmaf(T[2], v.x, fmaf(T[5], v.y, T[8] * v.z)));
-        const float3 sl = support_local(B, db);
-        const float3 sb = se3_act(T, sl.x, sl.y, sl.z);
-        const float3 w = sub3(sa, sb);
-        const float vw = dot3(v, w);
-        // <v,w>/|v| is a lower bound of the distance for ANY direction v
+    // support of (A - B) in direction -v
+    const float3 sa = support_local(A, make_float3(-v.x, -v.y, -v.z));
+    const float3 db = make_float3(fmaf(T[0], v.x, fmaf(T[3], v.y, T[6] * v.z)), fmaf(T[1], v.x, fmaf(T[4], v.y, T[7] * v.z)),
+                                  fmaf(T[2], v.x, fmaf(T[5], v.y, T[8] * v.z)));
+    const float3 sl = support_local(B, db);
+    const float3 sb = se3_act(T, sl.x, sl.y, sl.z);
+    const float3 w = sub3(sa, sb);
+    const float vw = dot3(v, w);
 #ifdef PBP_GJK_DEBUG
-        printf("it %d n %d v (%g %g %g) |v| %.9g w (%g %g %g) vw/|v| %.9g\n", it, n, v.x, v.y, v.z, sqrtf(vv), w.x, w.y, w.z, vw / sqrtf(vv));
+    printf("it %d n %d v (%g %g %g) |v| %.9g w (%g %g %g) vw/|v| %.9g\n", s.it, n, v.x, v.y, v.z, sqrtf(vv), w.x, w.y, w.z, vw / sqrtf(vv));
 #endif
-        if (vw > 0.f && vw * vw > cut2 * vv) {
-            out.dist = vw * rsqrtf(vv);
-            out.hit = 0;
-            out.iters = it + 1;
-            return out;
-        }
-        if (n > 0) {
-            if (vv - vw <= PBP_GJK_TOL * sqrtf(vv)) break;  // v is (numerically) the closest point
-            // w (numerically) already in the simplex: v cannot improve any further
-            const float near2 = 1e-10f * dot3(w, w);
-            const float3 e0 = sub3(w, W0), e1 = sub3(w, W1), e2 = sub3(w, W2);
-            const bool dup = dot3(e0, e0) <= near2 || (n > 1 && dot3(e1, e1) <= near2) || (n > 2 && dot3(e2, e2) <= near2);
-            if (dup) break;
-        }
+    out.iters = ++s.it;
+    // <v,w>/|v| is a lower bound of the distance for ANY direction v
+    if (vw > 0.f && vw * vw > cut * cut * vv) {
+        out.dist = vw * rsqrtf(vv);
+        out.hit = 0;
+        return true;
+    }
+    bool done = false, enclosed = false;
+    if (n > 0) {
+        if (vv - vw <= PBP_GJK_TOL * sqrtf(vv)) done = true;  // v is (numerically) the closest point
+        // w (numerically) already in the simplex: v cannot improve any further
+        const float near2 = 1e-10f * dot3(w, w);
+        const float3 e0 = sub3(w, s.W0), e1 = sub3(w, s.W1), e2 = sub3(w, s.W2);
+        if (dot3(e0, e0) <= near2 || (n > 1 && dot3(e1, e1) <= near2) || (n > 2 && dot3(e2, e2) <= near2)) done = true;
+    }
+    if (!done) {
         // append w and solve for the closest point of the simplex
-        float3 nv;
+        float3 nv, W3 = w;
         int mask;
-        if (n == 0) { W0 = w; nv = w; mask = 1; }
-        else if (n == 1) { W1 = w; mask = closest_on_segment(W0, W1, nv); }
-        else if (n == 2) { W2 = w; mask = closest_on_triangle(W0, W1, W2, nv); }
+        if (n == 0) { s.W0 = w; nv = w; mask = 1; }
+        else if (n == 1) { s.W1 = w; mask = closest_on_segment(s.W0, s.W1, nv); }
+        else if (n == 2) { s.W2 = w; mask = closest_on_triangle(s.W0, s.W1, s.W2, nv); }
         else {
-            W3 = w;
-            mask = closest_on_tetrahedron(W0, W1, W2, W3, nv);
-            if (mask == 0) { enclosed = true; break; }
+            mask = closest_on_tetrahedron(s.W0, s.W1, s.W2, W3, nv);
+            if (mask == 0) { enclosed = true; nv = make_float3(0.f, 0.f, 0.f); }
         }
         float nvv = dot3(nv, nv);
-        if (n >= 2 && nvv >= vv) {
+        if (!enclosed && n >= 2 && nvv >= vv) {
             // Backup step: sliver simplices (curved supports, near-duplicate points) can defeat the
             // region tests in FP32; retry with the sub-simplices that contain the new vertex.
             float3 c1, c2, c3;
             if (n == 2) {
-                const int a1 = closest_on_segment(W0, W2, c1), a2 = closest_on_segment(W1, W2, c2);
+                const int a1 = closest_on_segment(s.W0, s.W2, c1), a2 = closest_on_segment(s.W1, s.W2, c2);
                 const float e1 = dot3(c1, c1), e2 = dot3(c2, c2);
                 if (e1 < nvv && e1 <= e2) { nv = c1; mask = (a1 & 1) | ((a1 & 2) << 1); }
                 else if (e2 < nvv) { nv = c2; mask = a2 << 1; }
             } else {
-                const int a1 = closest_on_triangle(W0, W1, W3, c1), a2 = closest_on_triangle(W0, W2, W3, c2),
-                          a3 = closest_on_triangle(W1, W2, W3, c3);
+                const int a1 = closest_on_triangle(s.W0, s.W1, W3, c1), a2 = closest_on_triangle(s.W0, s.W2, W3, c2),
+                          a3 = closest_on_triangle(s.W1, s.W2, W3, c3);
                 const float e1 = dot3(c1, c1), e2 = dot3(c2, c2), e3 = dot3(c3, c3);
                 if (e1 < nvv && e1 <= e2 && e1 <= e3) { nv = c1; mask = (a1 & 3) | ((a1 & 4) << 1); }
                 else if (e2 < nvv && e2 <= e3) { nv = c2; mask = (a2 & 1) | ((a2 & 6) << 1); }
@@ -253,35 +264,56 @@ __device__ __forceinline__ GjkOut gjk_run(const ShapeRef &A, const ShapeRef &B, 
             }
             nvv = dot3(nv, nv);
         }
-        if (nvv <= PBP_GJK_EPS_ABS2) { enclosed = true; break; }
-        if (!WANT_DIST && nvv <= m2) { v = nv; vv = nvv; break; }      // upper bound already within margin
+        if (enclosed || nvv <= PBP_GJK_EPS_ABS2) {
+            out.dist = 0.f;
+            out.hit = 1;
+            return true;
+        }
+        if (!WANT_DIST && nvv <= margin * margin) {  // upper bound already within margin
+            out.dist = sqrtf(nvv);
+            out.hit = 1;
+            return true;
+        }
         // |v| must decrease; a decrease below FP32 resolution (large flat faces far from the origin)
         // is still real progress -- the direction turns and the next support finds a new vertex --
         // so tolerate a few such steps, but stop on a genuinely worse point or when it persists.
         if (n > 0 && nvv >= vv) {
-            if (nvv > vv * 1.00001f || ++stalls > 4) break;
+            if (nvv > vv * 1.00001f || ++s.stalls > 4) done = true;
         } else {
-            stalls = 0;
+            s.stalls = 0;
         }
-        v = nv;
-        vv = nvv;
-        // compact the kept vertices to the front (static indices only -> stays in registers)
+        if (!done) {
+            s.v = nv;
+            s.vv = nvv;
+            // compact the kept vertices to the front (static indices only -> stays in registers)
 #pragma unroll
-        for (int pass = 0; pass < 3; pass++) {
-            if (!(mask & 1) && (mask >> 1)) { W0 = W1; W1 = W2; W2 = W3; mask >>= 1; }
-            if (!(mask & 2) && (mask >> 2)) { W1 = W2; W2 = W3; mask = (mask & 1) | ((mask >> 1) & ~1); }
-            if (!(mask & 4) && (mask >> 3)) { W2 = W3; mask = (mask & 3) | ((mask >> 1) & ~3); }
+            for (int pass = 0; pass < 3; pass++) {
+                if (!(mask & 1) && (mask >> 1)) { s.W0 = s.W1; s.W1 = s.W2; s.W2 = W3; mask >>= 1; }
+                if (!(mask & 2) && (mask >> 2)) { s.W1 = s.W2; s.W2 = W3; mask = (mask & 1) | ((mask >> 1) & ~1); }
+                if (!(mask & 4) && (mask >> 3)) { s.W2 = W3; mask = (mask & 3) | ((mask >> 1) & ~3); }
+            }
+            s.n = __popc(mask);
+            if (s.it >= PBP_GJK_MAX_ITERS) done = true;
         }
-        n = __popc(mask);
     }
-    out.iters = it + 1;
-    if (enclosed) {
-        out.dist = 0.f;
-        out.hit = 1;
-        return out;
+    if (done) {
+        out.dist = sqrtf(s.vv);
+        out.hit = out.dist <= margin;
+        return true;
     }
-    out.dist = sqrtf(vv);
-    out.hit = out.dist <= margin;
+    return false;
+}
+
+// Whole item in one call (host build used by the CPU tests; the device narrowphase drives
+// gjk_step itself so that finished lanes can be refilled).
+template <bool WANT_DIST>
+__device__ __forceinline__ GjkOut gjk_run(const ShapeRef &A, const ShapeRef &B, const float *T, float3 v0, float margin,
+                                          float bound) {
+    GjkState s;
+    GjkOut out;
+    gjk_init(s, v0);
+    while (!gjk_step<WANT_DIST>(A, B, T, s, margin, bound, out)) {
+    }
     return out;
 }
 

@@ -1,14 +1,18 @@
-// Kernels of the collision-validation engine (sm_100a).
+// Kernels of the collision-validation engine (sm_100a, scalar FP32).
 //
-//   k_broadphase   one thread per state: FK of the joint tree with SE(3) products in registers,
-//                  world centres of each geometry's enclosing / inscribed sphere, then a
-//                  conservative test per active pair: certainly free / certainly colliding /
-//                  undecided.  Undecided (state, pair) items are appended -- with the relative
-//                  placement of the two geometries -- to that pair's bin (warp-aggregated
-//                  atomics, coalesced SoA writes).
-//   k_narrowphase  persistent blocks; hull vertices + shape tables staged once per block in
-//                  shared memory; each warp pulls 32-item tiles of ONE pair and runs FP32 GJK.
-//   k_edge_*       path discretisation on device (counts, explicit fill, sample descriptors).
+//   k_broadphase   one thread per state.  FK of the joint tree with the running SE(3) product in
+//                  registers; only the world centre of each moving geometry's proxy sphere (3
+//                  floats) is kept, thread-interleaved in shared memory.  Every active pair is then
+//                  classified from squared distances (no sqrt): certainly free / certainly
+//                  colliding / undecided.  Undecided (state, pair) items are appended to the
+//                  pair's bin (one warp-aggregated atomic per pair, coalesced stores).
+//   k_item_setup   one thread per item, pair-major tiles: recomputes the FK chain of just the two
+//                  geometries of the item's pair (uniform control flow inside a warp, everything in
+//                  registers) and stores the relative placement T = oMg[a]^-1 oMg[b].
+//   k_narrowphase  persistent blocks, hull vertices staged once per block in shared memory; each
+//                  warp streams the items of ONE pair through FP32 GJK, one iteration per trip for
+//                  all active lanes, refilling finished lanes from the pair's bin.
+//   k_edge_* / k_level_*   path discretisation on device (counts, explicit fill, level descriptors).
 //   k_fk_output    FK only, writes joint / geometry / frame placements.
 #pragma once
 #include <limits.h>
@@ -17,8 +21,12 @@
 
 namespace pbp {
 
-constexpr int BP_THREADS = 256;
+constexpr int BP_THREADS = 128;
 constexpr int NP_THREADS = 256;
+constexpr int IS_THREADS = 256;
+constexpr int TILE_ITEMS = 128;    // items of one pair handed to a warp per tile fetch
+constexpr int BP_MAX_LOCAL_CENTRES = PBP_MAX_GEOMS;
+constexpr int BP_MAX_SAVES = 16;
 constexpr float BP_SLACK = 2e-5f;  // broadphase decisions keep this margin (metres) for FP32 rounding
 
 // Where the states of a launch come from.
@@ -33,9 +41,10 @@ struct StateSource {
 
 // Per-pair bins of undecided items (SoA; bin p occupies [p*cap, (p+1)*cap)).
 struct Bins {
-    int32_t *group;      // [npairs*cap]
-    int32_t *sample;     // [npairs*cap] (only written when the source carries sample ids)
-    float *T;            // [12][npairs*cap]
+    int32_t *state;      // [npairs*cap] written by the broadphase: state index inside the round
+    int32_t *group;      // [npairs*cap] written by the item setup: output group, -1 = dropped
+    int32_t *sample;     // [npairs*cap] (only when the source carries sample ids)
+    float *T;            // [12][npairs*cap] relative placement of b in a's frame
     uint32_t *count;     // [npairs]
     int64_t cap;
 };
@@ -48,14 +57,9 @@ struct Outputs {
 };
 
 enum { MODE_BOOL = 0, MODE_BOOL_ALL = 1, MODE_DIST = 2 };
-// MODE_BOOL      verdict only; a state stops at its first certain hit, dead groups are skipped
+// MODE_BOOL      verdict only; a state stops at its first certain hit, decided groups are skipped
 // MODE_BOOL_ALL  verdict + first_pair / first_bad: every pair of every state is resolved
 // MODE_DIST      verdict + min distance: pairs are resolved unless certainly farther than the bound
-
-__device__ __forceinline__ float point_box_distance(float3 p, float hx, float hy, float hz) {
-    const float dx = fmaxf(fabsf(p.x) - hx, 0.f), dy = fmaxf(fabsf(p.y) - hy, 0.f), dz = fmaxf(fabsf(p.z) - hz, 0.f);
-    return sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-}
 
 __device__ __forceinline__ void stage_words(void *dst, const void *src, int bytes) {
     const int n = bytes >> 2;
@@ -63,6 +67,8 @@ __device__ __forceinline__ void stage_words(void *dst, const void *src, int byte
     const uint32_t *s = reinterpret_cast<const uint32_t *>(src);
     for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
 }
+
+__host__ __device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // Load this block's states into shared memory: sq[local_state * nq + k].
 __device__ __forceinline__ void load_states(const StateSource &src, int nq, int64_t block_first, int count, float *sq) {
@@ -92,23 +98,38 @@ __device__ __forceinline__ void load_states(const StateSource &src, int nq, int6
     }
 }
 
+// Shared-memory footprint of the broadphase tables (everything but the per-thread store).
+__host__ __device__ inline size_t bp_table_bytes(int njoints, int nmoving, int ngeoms, int nboxes, int npairs, int nq) {
+    return align16((size_t)njoints * sizeof(DevJoint)) + align16((size_t)(nmoving > 0 ? nmoving : 1) * 4) +
+           align16((size_t)(ngeoms > 0 ? ngeoms : 1) * sizeof(BpGeom)) + align16((size_t)(nboxes > 0 ? nboxes : 1) * sizeof(BpBox)) +
+           align16((size_t)(npairs > 0 ? npairs : 1) * sizeof(BpPair)) + align16((size_t)BP_THREADS * nq * 4);
+}
+
 // ------------------------------------------------------------------------------------------
 // FK + broadphase
 // ------------------------------------------------------------------------------------------
-template <int MAXJ, int MAXM, int MODE>
+// SMEM_STORE: per-thread proxy centres / saved branch transforms live thread-interleaved in shared
+// memory (no local memory at all); otherwise (very large models) in local arrays.
+template <int MODE, bool SMEM_STORE>
 __global__ void __launch_bounds__(BP_THREADS)
 k_broadphase(DevModel M, StateSource src, int64_t n_states, float padding, Outputs out, Bins bins) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    DevJoint *sj = reinterpret_cast<DevJoint *>(smem_raw);
-    DevGeom *sg = reinterpret_cast<DevGeom *>(sj + M.njoints);
-    DevPair *sp = reinterpret_cast<DevPair *>(sg + M.ngeoms);
-    float *sq = reinterpret_cast<float *>(sp + ((M.npairs + 1) & ~1));
+    unsigned char *ptr = smem_raw;
+    DevJoint *sj = reinterpret_cast<DevJoint *>(ptr);   ptr += align16((size_t)M.njoints * sizeof(DevJoint));
+    int32_t *sjg = reinterpret_cast<int32_t *>(ptr);     ptr += align16((size_t)max(M.nmoving, 1) * 4);
+    BpGeom *sg = reinterpret_cast<BpGeom *>(ptr);        ptr += align16((size_t)max(M.ngeoms, 1) * sizeof(BpGeom));
+    BpBox *sb = reinterpret_cast<BpBox *>(ptr);          ptr += align16((size_t)max(M.nboxes, 1) * sizeof(BpBox));
+    BpPair *sp = reinterpret_cast<BpPair *>(ptr);        ptr += align16((size_t)max(M.npairs, 1) * sizeof(BpPair));
+    float *sq = reinterpret_cast<float *>(ptr);          ptr += align16((size_t)BP_THREADS * M.nq * 4);
+    float *sstore = reinterpret_cast<float *>(ptr);      // [(nmoving*3 + nsave*12)][BP_THREADS]
 
     const int64_t block_first = (int64_t)blockIdx.x * BP_THREADS;
     const int count = (int)min((int64_t)BP_THREADS, n_states - block_first);
     stage_words(sj, M.joints, M.njoints * (int)sizeof(DevJoint));
-    stage_words(sg, M.geoms, M.ngeoms * (int)sizeof(DevGeom));
-    stage_words(sp, M.pairs, M.npairs * (int)sizeof(DevPair));
+    stage_words(sjg, M.joint_geoms, M.nmoving * 4);
+    stage_words(sg, M.bpgeoms, M.ngeoms * (int)sizeof(BpGeom));
+    stage_words(sb, M.bpboxes, M.nboxes * (int)sizeof(BpBox));
+    stage_words(sp, M.bppairs, M.npairs * (int)sizeof(BpPair));
     load_states(src, M.nq, block_first, count, sq);
     __syncthreads();
 
@@ -116,106 +137,80 @@ k_broadphase(DevModel M, StateSource src, int64_t n_states, float padding, Outpu
     const int64_t state = block_first + tid;
     const bool valid = tid < count;
     const int32_t group = valid ? (src.group ? src.group[state] : (int32_t)state) : 0;
-    const int32_t sample = (valid && src.sample) ? src.sample[state] : 0;
     bool alive = valid;
     if (MODE == MODE_BOOL && src.group && valid && out.hit[group]) alive = false;  // group already decided
 
-    // ---- forward kinematics: oMi kept in local memory for random parent access, the running
-    //      transform of a serial chain stays in registers
-    float oMi[MAXJ][12];
-    float cw[MAXM][3], iw[MAXM][3];
-    float cur[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) { cur[i] = (i == 0 || i == 4 || i == 8) ? 1.f : 0.f; oMi[0][i] = cur[i]; }
-    const float *myq = sq + tid * M.nq;
+    float lstore[SMEM_STORE ? 1 : (BP_MAX_LOCAL_CENTRES * 3 + BP_MAX_SAVES * 12)];
+    auto store = [&](int idx) -> float & {
+        if (SMEM_STORE) return sstore[idx * BP_THREADS + tid];
+        return lstore[SMEM_STORE ? 0 : idx];
+    };
+    const int save_base = M.nmoving * 3;
+
+    // ---- forward kinematics: running product in registers
     if (__any_sync(0xffffffffu, alive)) {
+        float cur[12];
+        se3_identity(cur);
+        const float *myq = sq + tid * M.nq;
         for (int j = 1; j < M.njoints; j++) {
             const DevJoint &J = sj[j];
             float par[12];
-            if (J.chain) {
+            if (J.parent_slot == -1) {
 #pragma unroll
                 for (int i = 0; i < 12; i++) par[i] = cur[i];
+            } else if (J.parent_slot == -2) {
+                se3_identity(par);
             } else {
 #pragma unroll
-                for (int i = 0; i < 12; i++) par[i] = oMi[J.parent][i];
+                for (int i = 0; i < 12; i++) par[i] = store(save_base + J.parent_slot * 12 + i);
             }
             const float qj = valid ? myq[J.idx_q] : 0.f;
             joint_transform(J, par, qj, cur);
+            if (J.save_slot >= 0) {
 #pragma unroll
-            for (int i = 0; i < 12; i++) oMi[j][i] = cur[i];
-        }
-        // world centres of the moving geometries' spheres
-        for (int g = 0; g < M.ngeoms; g++) {
-            const DevGeom &G = sg[g];
-            if (G.slot < 0) continue;
-            float T[12];
-            if (G.identity) {
-#pragma unroll
-                for (int i = 0; i < 12; i++) T[i] = oMi[G.parent][i];
-            } else {
-                float P[12];
-#pragma unroll
-                for (int i = 0; i < 12; i++) P[i] = oMi[G.parent][i];
-                se3_mul(P, G.P, T);
+                for (int i = 0; i < 12; i++) store(save_base + J.save_slot * 12 + i) = cur[i];
             }
-            const float3 c = se3_act(T, G.outer[0], G.outer[1], G.outer[2]);
-            const float3 ic = se3_act(T, G.inner[0], G.inner[1], G.inner[2]);
-            cw[G.slot][0] = c.x; cw[G.slot][1] = c.y; cw[G.slot][2] = c.z;
-            iw[G.slot][0] = ic.x; iw[G.slot][1] = ic.y; iw[G.slot][2] = ic.z;
+            for (int gi = J.geom_begin; gi < J.geom_end; gi++) {
+                const BpGeom &G = sg[sjg[gi]];
+                const float3 c = se3_act(cur, G.c[0], G.c[1], G.c[2]);
+                store(G.slot * 3 + 0) = c.x;
+                store(G.slot * 3 + 1) = c.y;
+                store(G.slot * 3 + 2) = c.z;
+            }
         }
     }
 
-    auto outer_centre = [&](const DevGeom &G) {
-        return G.slot < 0 ? make_float3(G.outer[0], G.outer[1], G.outer[2]) : make_float3(cw[G.slot][0], cw[G.slot][1], cw[G.slot][2]);
+    auto centre = [&](int g) {
+        const BpGeom &G = sg[g];
+        if (G.slot < 0) return make_float3(G.c[0], G.c[1], G.c[2]);
+        return make_float3(store(G.slot * 3 + 0), store(G.slot * 3 + 1), store(G.slot * 3 + 2));
     };
-    auto inner_centre = [&](const DevGeom &G) {
-        return G.slot < 0 ? make_float3(G.inner[0], G.inner[1], G.inner[2]) : make_float3(iw[G.slot][0], iw[G.slot][1], iw[G.slot][2]);
-    };
-    auto world_placement = [&](const DevGeom &G, float *T) {
-        if (G.slot < 0) {
-#pragma unroll
-            for (int i = 0; i < 12; i++) T[i] = G.P[i];
-        } else if (G.identity) {
-#pragma unroll
-            for (int i = 0; i < 12; i++) T[i] = oMi[G.parent][i];
-        } else {
-            float P[12];
-#pragma unroll
-            for (int i = 0; i < 12; i++) P[i] = oMi[G.parent][i];
-            se3_mul(P, G.P, T);
-        }
-    };
-    // lower / upper bound of the distance of one pair from the sphere (and box) proxies
-    auto pair_bounds = [&](const DevPair &pr, const DevGeom &GA, const DevGeom &GB, float &lb, float &ub) {
+    // squared distance between the proxies of one pair (centre-centre, or centre-to-box)
+    auto proxy_dist2 = [&](const BpPair &pr) {
         if (pr.kind == BP_BOX_A || pr.kind == BP_BOX_B) {
-            const DevGeom &BX = pr.kind == BP_BOX_A ? GA : GB;
-            const DevGeom &OT = pr.kind == BP_BOX_A ? GB : GA;
-            float T[12];
-            world_placement(BX, T);
-            const float3 pc = se3_act_inv(T, outer_centre(OT));
-            const float3 pi = se3_act_inv(T, inner_centre(OT));
-            lb = point_box_distance(pc, BX.par[0], BX.par[1], BX.par[2]) - OT.outer[3];
-            ub = point_box_distance(pi, BX.par[0], BX.par[1], BX.par[2]) - OT.inner[3];
-        } else {
-            const float3 d = sub3(outer_centre(GA), outer_centre(GB));
-            const float3 e = sub3(inner_centre(GA), inner_centre(GB));
-            lb = sqrtf(dot3(d, d)) - GA.outer[3] - GB.outer[3];
-            ub = sqrtf(dot3(e, e)) - GA.inner[3] - GB.inner[3];
+            const BpBox &bx = sb[pr.box];
+            const float3 c = centre(pr.kind == BP_BOX_A ? pr.b : pr.a);
+            const float dx = c.x - bx.t[0], dy = c.y - bx.t[1], dz = c.z - bx.t[2];
+            const float lx = fmaf(bx.R[0], dx, fmaf(bx.R[3], dy, bx.R[6] * dz));
+            const float ly = fmaf(bx.R[1], dx, fmaf(bx.R[4], dy, bx.R[7] * dz));
+            const float lz = fmaf(bx.R[2], dx, fmaf(bx.R[5], dy, bx.R[8] * dz));
+            const float ex = fmaxf(fabsf(lx) - bx.h[0], 0.f), ey = fmaxf(fabsf(ly) - bx.h[1], 0.f), ez = fmaxf(fabsf(lz) - bx.h[2], 0.f);
+            return fmaf(ex, ex, fmaf(ey, ey, ez * ez));
         }
+        const float3 d = sub3(centre(pr.a), centre(pr.b));
+        return dot3(d, d);
     };
 
     float bound = INFINITY;     // MODE_DIST: certain upper bound of this state's min distance
     int first_pair = INT_MAX;   // MODE_BOOL_ALL
     bool state_hit = false;
 
-    if (MODE == MODE_DIST) {
+    if (MODE == MODE_DIST && alive) {
         // pass 1: the smallest certain upper bound over all pairs
         for (int p = 0; p < M.npairs; p++) {
-            const DevPair pr = sp[p];
-            float lb, ub;
-            pair_bounds(pr, sg[pr.a], sg[pr.b], lb, ub);
+            const BpPair pr = sp[p];
             const float slack = pr.kind == BP_EXACT_SPHERES ? 0.f : BP_SLACK;
-            bound = fminf(bound, fmaxf(ub + slack, 0.f));
+            bound = fminf(bound, fmaxf(sqrtf(proxy_dist2(pr)) - pr.r_in + slack, 0.f));
         }
     }
 
@@ -223,46 +218,36 @@ k_broadphase(DevModel M, StateSource src, int64_t n_states, float padding, Outpu
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int p = 0; p < M.npairs; p++) {
         if (MODE == MODE_BOOL && !__any_sync(0xffffffffu, alive)) break;
-        const DevPair pr = sp[p];
-        const DevGeom &GA = sg[pr.a];
-        const DevGeom &GB = sg[pr.b];
+        const BpPair pr = sp[p];
         bool undecided = false;
         if (alive) {
-            float lb, ub;
-            pair_bounds(pr, GA, GB, lb, ub);
+            const float d2 = proxy_dist2(pr);
             const bool exact = pr.kind == BP_EXACT_SPHERES;
             const float slack = exact ? 0.f : BP_SLACK;
-            const bool sure = ub <= padding - slack;
+            const float rs = pr.r_in + padding - slack;         // |proxy distance| <= rs  ->  certainly colliding
+            const bool sure = rs >= 0.f && d2 <= rs * rs;
             if (sure) {
                 state_hit = true;
                 if (MODE == MODE_BOOL) alive = false;
                 if (MODE == MODE_BOOL_ALL) first_pair = min(first_pair, p);
             }
             if (MODE == MODE_DIST) {
-                if (exact) bound = fminf(bound, fmaxf(lb, 0.f));  // lb == ub == exact distance
+                const float lb = sqrtf(d2) - pr.r_out;
+                if (exact) bound = fminf(bound, fmaxf(lb, 0.f));  // the proxies are the shapes
                 undecided = !exact && (lb - slack <= bound);
             } else {
-                const bool free_ = exact ? !sure : (lb > padding + slack);
+                const float rf = pr.r_out + padding + slack;    // proxy distance > rf  ->  certainly free
+                const bool free_ = exact ? !sure : (d2 > rf * rf);
                 undecided = !sure && !free_;
             }
         }
         const unsigned um = __ballot_sync(0xffffffffu, undecided);
         if (um) {
+            const int leader = __ffs(um) - 1;
             uint32_t base = 0;
-            if (lane == (unsigned)(__ffs(um) - 1)) base = atomicAdd(bins.count + p, (uint32_t)__popc(um));
-            base = __shfl_sync(0xffffffffu, base, __ffs(um) - 1);
-            if (undecided) {
-                float TA[12], TB[12], R[12];
-                world_placement(GA, TA);
-                world_placement(GB, TB);
-                se3_inv_mul(TA, TB, R);
-                const int64_t slot = (int64_t)p * bins.cap + base + __popc(um & lt_mask);
-                const int64_t stride = (int64_t)M.npairs * bins.cap;
-                bins.group[slot] = group;
-                if (src.sample) bins.sample[slot] = sample;
-#pragma unroll
-                for (int k = 0; k < 12; k++) bins.T[k * stride + slot] = R[k];
-            }
+            if ((int)lane == leader) base = atomicAdd(bins.count + p, (uint32_t)__popc(um));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (undecided) bins.state[(int64_t)p * bins.cap + base + __popc(um & lt_mask)] = (int32_t)state;
         }
     }
 
@@ -273,7 +258,7 @@ k_broadphase(DevModel M, StateSource src, int64_t n_states, float padding, Outpu
             if (state_hit) {
                 out.hit[group] = 1;
                 if (out.first_pair) atomicMin(out.first_pair + state, first_pair);
-                if (out.first_bad) atomicMin(out.first_bad + group, sample);
+                if (out.first_bad) atomicMin(out.first_bad + group, src.sample ? src.sample[state] : 0);
             }
         } else {
             if (state_hit) out.hit[group] = 1;
@@ -284,107 +269,221 @@ k_broadphase(DevModel M, StateSource src, int64_t n_states, float padding, Outpu
 }
 
 // ------------------------------------------------------------------------------------------
-// Narrowphase (GJK), persistent, pair-major tiles
+// Tile scheduling shared by the item setup and the narrowphase: tiles of TILE_ITEMS items of one
+// pair, bins visited in `order` (most expensive pairs first).  prefix[k] = tiles before bin k.
 // ------------------------------------------------------------------------------------------
-template <int MODE, bool VERTS_IN_SMEM>
-__global__ void __launch_bounds__(NP_THREADS)
-k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *tile_counter, bool has_sample) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *sv = reinterpret_cast<float4 *>(smem_raw);
-    DevGeom *sg = reinterpret_cast<DevGeom *>(sv + (VERTS_IN_SMEM ? M.nverts_padded : 0));
-    DevPair *sp = reinterpret_cast<DevPair *>(sg + M.ngeoms);
-    uint32_t *prefix = reinterpret_cast<uint32_t *>(sp + ((M.npairs + 1) & ~1));  // [npairs + 1] tiles before bin k
-    int32_t *order = reinterpret_cast<int32_t *>(prefix + M.npairs + 1);
-
-    if (VERTS_IN_SMEM) stage_words(sv, M.verts, M.nverts_padded * (int)sizeof(float4));
-    stage_words(sg, M.geoms, M.ngeoms * (int)sizeof(DevGeom));
-    stage_words(sp, M.pairs, M.npairs * (int)sizeof(DevPair));
-    stage_words(order, M.bin_order, M.npairs * (int)sizeof(int32_t));
-    __syncthreads();
+__device__ __forceinline__ void compute_tile_prefix(const uint32_t *count, const int32_t *order, int npairs, uint32_t *prefix) {
     if (threadIdx.x < 32) {
-        // warp scan of tiles per bin, in bin order
         uint32_t run = 0;
-        for (int k0 = 0; k0 < M.npairs; k0 += 32) {
+        for (int k0 = 0; k0 < npairs; k0 += 32) {
             const int k = k0 + threadIdx.x;
-            uint32_t t = k < M.npairs ? (bins.count[order[k]] + 31u) >> 5 : 0u;
+            const uint32_t t = k < npairs ? (count[order[k]] + TILE_ITEMS - 1) / TILE_ITEMS : 0u;
             uint32_t inc = t;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
                 if ((int)threadIdx.x >= o) inc += y;
             }
-            if (k < M.npairs) prefix[k] = run + inc - t;
+            if (k < npairs) prefix[k] = run + inc - t;
             run += __shfl_sync(0xffffffffu, inc, 31);
         }
-        if (threadIdx.x == 0) prefix[M.npairs] = run;
+        if (threadIdx.x == 0) prefix[npairs] = run;
     }
+}
+
+// Fetch the next tile for this warp.  Returns false when the work is exhausted.
+__device__ __forceinline__ bool next_tile(uint32_t *tile_counter, const uint32_t *prefix, const int32_t *order, int npairs,
+                                          const uint32_t *count, int &pair, uint32_t &begin, uint32_t &end) {
+    uint32_t tile = 0;
+    if ((threadIdx.x & 31) == 0) tile = atomicAdd(tile_counter, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= prefix[npairs]) return false;
+    int lo = 0, hi = npairs;  // last k with prefix[k] <= tile
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= tile) lo = mid; else hi = mid;
+    }
+    pair = order[lo];
+    begin = (tile - prefix[lo]) * TILE_ITEMS;
+    end = min(begin + TILE_ITEMS, count[pair]);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// Item setup: T = oMg[a]^-1 * oMg[b] for every undecided (state, pair) item
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(IS_THREADS)
+k_item_setup(DevModel M, StateSource src, Outputs out, Bins bins, uint32_t *tile_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char *ptr = smem_raw;
+    DevJoint *sj = reinterpret_cast<DevJoint *>(ptr);    ptr += align16((size_t)M.njoints * sizeof(DevJoint));
+    DevGeom *sg = reinterpret_cast<DevGeom *>(ptr);      ptr += align16((size_t)max(M.ngeoms, 1) * sizeof(DevGeom));
+    BpPair *sp = reinterpret_cast<BpPair *>(ptr);        ptr += align16((size_t)max(M.npairs, 1) * sizeof(BpPair));
+    PairPath *spath = reinterpret_cast<PairPath *>(ptr); ptr += align16((size_t)max(M.npairs, 1) * sizeof(PairPath));
+    uint32_t *prefix = reinterpret_cast<uint32_t *>(ptr); ptr += align16(((size_t)M.npairs + 1) * 4);
+    int32_t *order = reinterpret_cast<int32_t *>(ptr);   ptr += align16((size_t)max(M.npairs, 1) * 4);
+
+    stage_words(sj, M.joints, M.njoints * (int)sizeof(DevJoint));
+    stage_words(sg, M.geoms, M.ngeoms * (int)sizeof(DevGeom));
+    stage_words(sp, M.bppairs, M.npairs * (int)sizeof(BpPair));
+    stage_words(spath, M.paths, M.npairs * (int)sizeof(PairPath));
+    stage_words(order, M.bin_order, M.npairs * 4);
     __syncthreads();
-    const uint32_t total_tiles = prefix[M.npairs];
+    compute_tile_prefix(bins.count, order, M.npairs, prefix);
+    __syncthreads();
+
     const unsigned lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)M.npairs * bins.cap;
+    int p;
+    uint32_t begin, end;
+    while (next_tile(tile_counter, prefix, order, M.npairs, bins.count, p, begin, end)) {
+        const PairPath path = spath[p];
+        const uint8_t *ops = M.path_ops + path.off;   // tiny, L1/L2 resident, warp-uniform addresses
+        const DevGeom &GA = sg[sp[p].a];
+        const DevGeom &GB = sg[sp[p].b];
+        for (uint32_t idx = begin + lane; idx < end; idx += 32) {
+            const int64_t slot = (int64_t)p * bins.cap + idx;
+            const int32_t state = bins.state[slot];
+            const int32_t group = src.group ? src.group[state] : state;
+            if (MODE == MODE_BOOL && out.hit[group]) {  // the broadphase already decided this group
+                bins.group[slot] = -1;
+                continue;
+            }
+            bins.group[slot] = group;
+            if (src.sample) bins.sample[slot] = src.sample[state];
+            // joint value of this state
+            auto qval = [&](int k) {
+                if (src.mode == 0) return __ldg(src.q + (int64_t)state * M.nq + k);
+                const float f = src.frac[state];
+                const float qa = __ldg(src.q1 + (int64_t)group * M.nq + k), qb = __ldg(src.q2 + (int64_t)group * M.nq + k);
+                return fmaf(f, qb - qa, qa);
+            };
+            float cur[12], lca[12], TA[12], nxt[12];
+            se3_identity(cur);
+            int o = 0;
+            for (int i = 0; i < path.n_trunk; i++, o++) {
+                const DevJoint &J = sj[ops[o]];
+                joint_transform(J, cur, qval(J.idx_q), nxt);
+#pragma unroll
+                for (int k = 0; k < 12; k++) cur[k] = nxt[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 12; k++) lca[k] = cur[k];
+            for (int i = 0; i < path.n_a; i++, o++) {
+                const DevJoint &J = sj[ops[o]];
+                joint_transform(J, cur, qval(J.idx_q), nxt);
+#pragma unroll
+                for (int k = 0; k < 12; k++) cur[k] = nxt[k];
+            }
+            se3_mul(cur, GA.P, TA);   // oMg[a]
+#pragma unroll
+            for (int k = 0; k < 12; k++) cur[k] = lca[k];
+            for (int i = 0; i < path.n_b; i++, o++) {
+                const DevJoint &J = sj[ops[o]];
+                joint_transform(J, cur, qval(J.idx_q), nxt);
+#pragma unroll
+                for (int k = 0; k < 12; k++) cur[k] = nxt[k];
+            }
+            float TB[12], R[12];
+            se3_mul(cur, GB.P, TB);   // oMg[b]
+            se3_inv_mul(TA, TB, R);
+#pragma unroll
+            for (int k = 0; k < 12; k++) bins.T[k * stride + slot] = R[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Narrowphase (GJK), persistent, pair-major, lane refill
+// ------------------------------------------------------------------------------------------
+template <int MODE, bool VERTS_IN_SMEM>
+__global__ void __launch_bounds__(NP_THREADS)
+k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *tile_counter, bool has_sample) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char *ptr = smem_raw;
+    float4 *sv = reinterpret_cast<float4 *>(ptr);        ptr += VERTS_IN_SMEM ? align16((size_t)M.nverts_padded * sizeof(float4)) : 0;
+    DevGeom *sg = reinterpret_cast<DevGeom *>(ptr);      ptr += align16((size_t)max(M.ngeoms, 1) * sizeof(DevGeom));
+    BpPair *sp = reinterpret_cast<BpPair *>(ptr);        ptr += align16((size_t)max(M.npairs, 1) * sizeof(BpPair));
+    uint32_t *prefix = reinterpret_cast<uint32_t *>(ptr); ptr += align16(((size_t)M.npairs + 1) * 4);
+    int32_t *order = reinterpret_cast<int32_t *>(ptr);   ptr += align16((size_t)max(M.npairs, 1) * 4);
+
+    if (VERTS_IN_SMEM) stage_words(sv, M.verts, M.nverts_padded * (int)sizeof(float4));
+    stage_words(sg, M.geoms, M.ngeoms * (int)sizeof(DevGeom));
+    stage_words(sp, M.bppairs, M.npairs * (int)sizeof(BpPair));
+    stage_words(order, M.bin_order, M.npairs * 4);
+    __syncthreads();
+    compute_tile_prefix(bins.count, order, M.npairs, prefix);
+    __syncthreads();
+
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const float4 *verts = VERTS_IN_SMEM ? sv : M.verts;
     const int64_t stride = (int64_t)M.npairs * bins.cap;
 
-    for (;;) {
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(tile_counter, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= total_tiles) break;
-        // bin = last k with prefix[k] <= tile
-        int lo = 0, hi = M.npairs;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (prefix[mid] <= tile) lo = mid; else hi = mid;
-        }
-        const int p = order[lo];
-        const uint32_t idx = ((tile - prefix[lo]) << 5) + lane;
-        if (idx >= bins.count[p]) continue;
-        const int64_t slot = (int64_t)p * bins.cap + idx;
-        const int32_t group = bins.group[slot];
-        if (MODE == MODE_BOOL && out.hit[group]) continue;  // another item / the broadphase already decided it
-        float T[12];
-#pragma unroll
-        for (int k = 0; k < 12; k++) T[k] = bins.T[k * stride + slot];
-
-        const DevPair pr = sp[p];
-        const DevGeom &GA = sg[pr.a];
-        const DevGeom &GB = sg[pr.b];
+    int p;
+    uint32_t begin, end;
+    while (next_tile(tile_counter, prefix, order, M.npairs, bins.count, p, begin, end)) {
+        const DevGeom &GA = sg[sp[p].a];
+        const DevGeom &GB = sg[sp[p].b];
         ShapeRef A, B;
         A.shape = GA.shape; A.p0 = GA.par[0]; A.p1 = GA.par[1]; A.p2 = GA.par[2];
         A.verts = verts + GA.vert_off; A.nverts = GA.vert_cnt;
         B.shape = GB.shape; B.p0 = GB.par[0]; B.p1 = GB.par[1]; B.p2 = GB.par[2];
         B.verts = verts + GB.vert_off; B.nverts = GB.vert_cnt;
-        // initial direction: centre(A) - centre(B) in A's frame (geometry-frame sphere centres)
-        const DevGeom *ga_glob = M.geoms + pr.a, *gb_glob = M.geoms + pr.b;
-        (void)ga_glob; (void)gb_glob;
         const float radii = GA.core_radius + GB.core_radius;
-        float3 ca, cb;
-        {
-            // moving geometries keep geometry-frame centres in `outer`; static ones hold world
-            // centres there, so recover the geometry-frame centre through the placement
-            if (GA.slot < 0) ca = se3_act_inv(GA.P, make_float3(GA.outer[0], GA.outer[1], GA.outer[2]));
-            else ca = make_float3(GA.outer[0], GA.outer[1], GA.outer[2]);
-            float3 cbl;
-            if (GB.slot < 0) cbl = se3_act_inv(GB.P, make_float3(GB.outer[0], GB.outer[1], GB.outer[2]));
-            else cbl = make_float3(GB.outer[0], GB.outer[1], GB.outer[2]);
-            cb = se3_act(T, cbl.x, cbl.y, cbl.z);
-        }
-        const float3 v0 = sub3(ca, cb);
+        const float margin = padding + radii;
+        const int64_t bin_base = (int64_t)p * bins.cap;
 
-        if (MODE == MODE_DIST) {
-            const float cur = out.min_dist[group];  // group == state in this mode
-            const GjkOut r = gjk_run<true>(A, B, T, v0, padding + radii, cur + radii);
-            const float d = fmaxf(r.dist - radii, 0.f);
-            if (r.hit) out.hit[group] = 1;
-            atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(d));
-        } else {
-            const GjkOut r = gjk_run<false>(A, B, T, v0, padding + radii, 0.f);
-            if (r.hit) {
-                if (MODE == MODE_BOOL) {
-                    out.hit[group] = 1;
-                } else {
-                    // MODE_BOOL_ALL: `group` holds the state index unless the source has groups
-                    if (out.first_pair) { atomicMin(out.first_pair + group, p); out.hit[group] = 1; }
-                    if (out.first_bad) { atomicMin(out.first_bad + group, has_sample ? bins.sample[slot] : 0); out.hit[group] = 1; }
+        // lane-resident item
+        bool active = false;
+        GjkState s;
+        float T[12];
+        int32_t group = 0;
+        uint32_t my_idx = 0;
+        float bound = 0.f;
+        uint32_t cursor = begin;
+        for (;;) {
+            // ---- refill finished lanes with the next items of this tile
+            const unsigned need = __ballot_sync(0xffffffffu, !active);
+            if (need && cursor < end) {
+                const uint32_t idx = cursor + __popc(need & lt_mask);
+                if (!active && idx < end) {
+                    const int32_t g = bins.group[bin_base + idx];
+                    if (g >= 0 && !(MODE == MODE_BOOL && out.hit[g])) {
+#pragma unroll
+                        for (int k = 0; k < 12; k++) T[k] = bins.T[k * stride + bin_base + idx];
+                        const float3 cb = se3_act(T, GB.centre[0], GB.centre[1], GB.centre[2]);
+                        gjk_init(s, make_float3(GA.centre[0] - cb.x, GA.centre[1] - cb.y, GA.centre[2] - cb.z));
+                        group = g;
+                        my_idx = idx;
+                        if (MODE == MODE_DIST) bound = out.min_dist[g] + radii;  // group == state in this mode
+                        active = true;
+                    }
+                }
+                cursor += __popc(need);
+            }
+            if (!__any_sync(0xffffffffu, active)) {
+                if (cursor >= end) break;
+                continue;
+            }
+            // ---- one GJK iteration for every active lane
+            if (active) {
+                GjkOut r;
+                const bool done = (MODE == MODE_DIST) ? gjk_step<true>(A, B, T, s, margin, bound, r)
+                                                      : gjk_step<false>(A, B, T, s, margin, 0.f, r);
+                if (done) {
+                    active = false;
+                    if (MODE == MODE_DIST) {
+                        if (r.hit) out.hit[group] = 1;
+                        atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(fmaxf(r.dist - radii, 0.f)));
+                    } else if (r.hit) {
+                        out.hit[group] = 1;
+                        if (MODE == MODE_BOOL_ALL) {
+                            if (out.first_pair) atomicMin(out.first_pair + group, p);
+                            if (out.first_bad) atomicMin(out.first_bad + group, has_sample ? bins.sample[bin_base + my_idx] : 0);
+                        }
+                    }
                 }
             }
         }
@@ -509,20 +608,18 @@ __global__ void k_path_groups(const int64_t *offsets, int64_t n_paths, int64_t t
 // ------------------------------------------------------------------------------------------
 // FK output
 // ------------------------------------------------------------------------------------------
-template <int MAXJ>
-__global__ void __launch_bounds__(BP_THREADS)
+__global__ void __launch_bounds__(128)
 k_fk_output(DevModel M, const float *q, int64_t n_states, float *oMi_out, float *oMg_out, float *oMf_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevJoint *sj = reinterpret_cast<DevJoint *>(smem_raw);
-    DevGeom *sg = reinterpret_cast<DevGeom *>(sj + M.njoints);
+    DevGeom *sg = reinterpret_cast<DevGeom *>(smem_raw + align16((size_t)M.njoints * sizeof(DevJoint)));
     stage_words(sj, M.joints, M.njoints * (int)sizeof(DevJoint));
     stage_words(sg, M.geoms, M.ngeoms * (int)sizeof(DevGeom));
     __syncthreads();
-    const int64_t s = (int64_t)blockIdx.x * BP_THREADS + threadIdx.x;
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_states) return;
-    float oMi[MAXJ][12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) oMi[0][i] = (i == 0 || i == 4 || i == 8) ? 1.f : 0.f;
+    float oMi[PBP_MAX_JOINTS][12];
+    se3_identity(oMi[0]);
     for (int j = 1; j < M.njoints; j++) {
         const DevJoint &J = sj[j];
         float par[12], cur[12];

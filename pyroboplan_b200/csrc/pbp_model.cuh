@@ -8,56 +8,83 @@
 namespace pbp {
 
 // SE(3) as 12 floats: rotation row-major r[0..8], translation r[9..11].
-struct Se3 {
-    float r[12];
-};
 
-struct DevJoint {    // 80 B
-    float P[12];     // placement in parent joint frame
+struct DevJoint {       // 96 B
+    float P[12];        // placement in parent joint frame
     float axis[3];
     int32_t parent;
     int32_t type;
     int32_t idx_q;
-    int32_t chain;   // 1 if parent == index - 1 (previous transform can stay in registers)
-    int32_t axis_code;  // 0 generic axis, 1/2/3 = +-x/y/z aligned (sign folded into axis_sign)
+    int32_t axis_code;  // 0 generic axis, 1/2/3 = +-x/y/z aligned (sign in axis[])
+    int32_t parent_slot;  // broadphase: -1 parent is the previous joint (running product), -2 universe, >= 0 saved slot
+    int32_t save_slot;    // broadphase: >= 0 -> keep this joint's transform in that slot (it has a non-adjacent child)
+    int32_t geom_begin, geom_end;  // range in DevModel::joint_geoms of the moving geometries attached to this joint
+    int32_t _pad;
 };
 
-struct DevGeom {     // 128 B
-    float P[12];     // placement in parent joint frame (world placement if parent == 0)
-    float par[4];    // shape parameters
-    float outer[4];  // enclosing sphere (geometry frame)
-    float inner[4];  // inscribed sphere (geometry frame)
+struct DevGeom {        // 96 B -- narrowphase / item-setup view of a geometry
+    float P[12];        // placement in parent joint frame (world placement if parent == 0)
+    float par[4];       // shape parameters
+    float centre[3];    // proxy-sphere centre in the geometry frame (initial GJK direction)
+    float core_radius;  // sphere / capsule inflation applied outside GJK
     int32_t parent;
     int32_t shape;
     int32_t vert_off;   // offset into the padded float4 vertex table
     int32_t vert_cnt;   // padded to a multiple of 4 (last vertex repeated)
-    int32_t slot;       // index into the per-thread moving-geometry table, -1 if static
-    int32_t identity;   // placement is the identity
-    float core_radius;  // sphere / capsule inflation applied outside GJK
+};
+
+struct BpGeom {         // 32 B -- broadphase view: one proxy centre, two radii
+    float c[3];         // centre: parent-JOINT frame for moving geometries, world frame for static ones
+    float r_out;        // enclosing radius
+    float r_in;         // inscribed radius (same centre)
+    int32_t slot;       // per-thread centre slot, -1 if static
+    int32_t box;        // index into the static-box table, -1 if this is not a static box
     int32_t _pad;
 };
 
-struct DevPair {     // 8 B
-    int16_t a, b;    // geometry ids (first, second)
-    int16_t kind;    // broadphase recipe, see BP_* below
-    int16_t _pad;
+struct BpBox {          // 64 B -- static box: world placement + half sides
+    float R[9];
+    float t[3];
+    float h[3];
+    float _pad;
+};
+
+struct BpPair {         // 16 B
+    uint8_t a, b;       // geometry ids (first, second)
+    uint8_t kind;       // BP_*
+    uint8_t _pad;
+    float r_out;        // BP_SPHERES: r_out(a) + r_out(b) | BP_BOX_*: r_out of the non-box geometry
+    float r_in;         // same for the inscribed radii
+    int32_t box;        // BP_BOX_*: static-box table index
 };
 
 // Broadphase recipes (warp-uniform per pair).
-enum : int16_t {
-    BP_SPHERES = 0,  // enclosing spheres for "free", inscribed spheres for "hit"
-    BP_BOX_A = 1,    // a is a box: point-to-box distance in a's frame against b's spheres
-    BP_BOX_B = 2,    // b is a box
-    BP_EXACT_SPHERES = 3,  // both shapes are spheres: broadphase decides exactly
+enum : uint8_t {
+    BP_SPHERES = 0,        // enclosing spheres for "free", inscribed spheres for "hit"
+    BP_BOX_A = 1,          // a is a static box: exact point-to-box distance against b's spheres
+    BP_BOX_B = 2,          // b is a static box
+    BP_EXACT_SPHERES = 3,  // both shapes are spheres: the proxies are the shapes, decided exactly
+};
+
+// Joint path of a pair for the item-setup FK: trunk (root .. lowest common ancestor), then the
+// branch to a's joint, then the branch to b's joint.  Ops are joint indices.
+struct PairPath {       // 8 B
+    int32_t off;        // into DevModel::path_ops
+    uint8_t n_trunk, n_a, n_b, _pad;
 };
 
 struct DevModel {
-    int32_t nq, njoints, ngeoms, npairs, nverts_padded, nframes, nmoving, _pad;
+    int32_t nq, njoints, ngeoms, npairs, nverts_padded, nframes, nmoving, nsave, nboxes, _pad;
     const DevJoint *joints;
+    const int32_t *joint_geoms;  // moving geometry ids grouped by parent joint
     const DevGeom *geoms;
-    const DevPair *pairs;
-    const int32_t *bin_order;   // [npairs] pair indices sorted by decreasing narrowphase cost
-    const float4 *verts;        // padded hull vertices
+    const BpGeom *bpgeoms;
+    const BpBox *bpboxes;
+    const BpPair *bppairs;
+    const PairPath *paths;
+    const uint8_t *path_ops;
+    const int32_t *bin_order;    // [npairs] pair indices sorted by decreasing narrowphase cost
+    const float4 *verts;         // padded hull vertices
     const float *q_lower, *q_upper;
     const int32_t *frame_parent;
     const float *frame_placement;
@@ -100,6 +127,11 @@ __device__ __forceinline__ float3 se3_act_inv(const float *T, float3 p) {
     const float dx = p.x - T[9], dy = p.y - T[10], dz = p.z - T[11];
     return make_float3(fmaf(T[0], dx, fmaf(T[3], dy, T[6] * dz)), fmaf(T[1], dx, fmaf(T[4], dy, T[7] * dz)),
                        fmaf(T[2], dx, fmaf(T[5], dy, T[8] * dz)));
+}
+
+__device__ __forceinline__ void se3_identity(float *T) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) T[i] = (i == 0 || i == 4 || i == 8) ? 1.f : 0.f;
 }
 
 // out = A * R where R rotates columns U and W (Rx: 1,2  Ry: 0,2 with the opposite sign  Rz: 0,1).

@@ -85,6 +85,7 @@ class _Stats(ctypes.Structure):
 class _Profile(ctypes.Structure):
     _fields_ = [
         ("broadphase_ms", ctypes.c_double),
+        ("item_setup_ms", ctypes.c_double),
         ("narrowphase_ms", ctypes.c_double),
         ("rounds", ctypes.c_int64),
         ("narrowphase_items", ctypes.c_int64),
@@ -150,8 +151,8 @@ def _up32(x):
 def flatten_model(model, collision_model):
     """Host containers -> dict of contiguous float32 / int32 arrays matching ``pbp_model_desc``.
 
-    Enclosing spheres are rounded outwards and inscribed spheres inwards so the float32
-    broadphase stays conservative.
+    ``geom_outer`` / ``geom_inner`` share one centre per geometry (the enclosing sphere's); radii
+    are rounded outwards / inwards so the float32 broadphase stays conservative.
     """
     geoms = collision_model.geometryObjects
     ng = len(geoms)
@@ -192,20 +193,29 @@ def flatten_model(model, collision_model):
             nv += len(pts)
         else:
             raise TypeError(f"unsupported collision geometry {type(s).__name__}")
+        # One proxy centre per geometry, two radii: the enclosing radius (rounded outwards) and the
+        # radius of the largest ball around the SAME centre that stays inside the shape (rounded
+        # inwards), so the float32 broadphase stays conservative.
         oc, orad = s.bounding_sphere()
-        ic, irad = s.inner_sphere()
         oc32 = np.asarray(oc, dtype=np.float32)
-        ic32 = np.asarray(ic, dtype=np.float32)
+        c64 = oc32.astype(np.float64)
         if isinstance(s, Convex):
             p64 = np.asarray(s.points, dtype=np.float32).astype(np.float64)
-            orad = float(np.sqrt(((p64 - oc32.astype(np.float64)) ** 2).sum(axis=1).max()))
-        if isinstance(s, (Sphere,)):
+            orad = float(np.sqrt(((p64 - c64) ** 2).sum(axis=1).max()))
+            irad = float((-(s.planes[:, :3] @ c64 + s.planes[:, 3])).min())
+        elif isinstance(s, Box):
+            irad = float(np.min(s.halfSide))
+        elif isinstance(s, Cylinder):
+            irad = min(s.radius, s.halfLength)
+        else:  # Sphere, Capsule
+            irad = s.radius
+        if isinstance(s, Sphere):
             o32, i32r = np.float32(s.radius), np.float32(s.radius)  # exact pair tests use the true radius
         else:
             o32 = _up32(orad * (1.0 + 1e-6) + 1e-7)
-            i32r = np.float32(max(irad - 2e-6 - float(np.linalg.norm(ic32.astype(np.float64) - ic)), 0.0))
+            i32r = np.float32(max(irad - 2e-6, 0.0))
         a["geom_outer"][i] = [*oc32, o32]
-        a["geom_inner"][i] = [*ic32, i32r]
+        a["geom_inner"][i] = [*oc32, i32r]
     a["verts"] = np.concatenate(verts).astype(np.float32) if verts else np.zeros((1, 3), dtype=np.float32)
     pairs = np.array([[p.first, p.second] for p in collision_model.collisionPairs], dtype=np.int32).reshape(-1, 2)
     a["pairs"] = pairs if len(pairs) else np.zeros((1, 2), dtype=np.int32)
