@@ -80,7 +80,8 @@ struct pbp_engine {
     pbp_stats stats{};
     // optional per-kernel timing
     bool profiling = false;
-    std::vector<cudaEvent_t> prof_events;   // triples: before broadphase, between, after narrowphase
+    std::vector<cudaEvent_t> prof_events;   // four per round: before broadphase / item setup / narrowphase, after
+    std::vector<cudaEvent_t> prof_pool;     // recycled events
     pbp_profile prof{};
 };
 
@@ -145,7 +146,10 @@ int run_round(pbp_engine *e, int mode, const StateSource &src, int64_t n, float 
     int rc;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (e->profiling) {
-        for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
+        for (int i = 0; i < 4; i++) {
+            if (!e->prof_pool.empty()) { ev[i] = e->prof_pool.back(); e->prof_pool.pop_back(); }
+            else CUDA_TRY(cudaEventCreate(&ev[i]));
+        }
         CUDA_TRY(cudaEventRecord(ev[0], st));
     }
     cudaEvent_t *evp = e->profiling ? ev : nullptr;
@@ -207,7 +211,7 @@ int pbp_get_profile(pbp_engine *e, pbp_profile *out, int reset) {
         e->prof.item_setup_ms += b;
         e->prof.narrowphase_ms += c;
         e->prof.rounds++;
-        for (int k = 0; k < 4; k++) cudaEventDestroy(e->prof_events[i + k]);
+        for (int k = 0; k < 4; k++) e->prof_pool.push_back(e->prof_events[i + k]);
     }
     e->prof_events.clear();
     unsigned long long items = 0;
@@ -225,6 +229,7 @@ void pbp_engine_destroy(pbp_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->prof_pool) cudaEventDestroy(ev);
     DeviceBuffer *bufs[] = {&e->d_joints, &e->d_jgeoms, &e->d_geoms, &e->d_bpgeoms, &e->d_bpboxes, &e->d_bppairs, &e->d_paths,
                             &e->d_pathops, &e->d_order, &e->d_verts, &e->d_qlim, &e->d_frames, &e->d_bin_state,
                             &e->d_bin_group, &e->d_bin_sample, &e->d_bin_T, &e->d_ctrl, &e->d_counts, &e->d_desc_group,

@@ -102,7 +102,8 @@ __device__ __forceinline__ void load_states(const StateSource &src, int nq, int6
 __host__ __device__ inline size_t bp_table_bytes(int njoints, int nmoving, int ngeoms, int nboxes, int npairs, int nq) {
     return align16((size_t)njoints * sizeof(DevJoint)) + align16((size_t)(nmoving > 0 ? nmoving : 1) * 4) +
            align16((size_t)(ngeoms > 0 ? ngeoms : 1) * sizeof(BpGeom)) + align16((size_t)(nboxes > 0 ? nboxes : 1) * sizeof(BpBox)) +
-           align16((size_t)(npairs > 0 ? npairs : 1) * sizeof(BpPair)) + align16((size_t)BP_THREADS * nq * 4);
+           align16((size_t)(npairs > 0 ? npairs : 1) * sizeof(BpPair)) + align16((size_t)BP_THREADS * nq * 4) +
+           align16((size_t)((npairs + 31) >> 5) * BP_THREADS * 4 + 16) + align16((size_t)(BP_THREADS / 32) * (npairs > 0 ? npairs : 1) * 4);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -121,6 +122,8 @@ k_broadphase(DevModel M, StateSource src, int64_t n_states, float padding, Outpu
     BpBox *sb = reinterpret_cast<BpBox *>(ptr);          ptr += align16((size_t)max(M.nboxes, 1) * sizeof(BpBox));
     BpPair *sp = reinterpret_cast<BpPair *>(ptr);        ptr += align16((size_t)max(M.npairs, 1) * sizeof(BpPair));
     float *sq = reinterpret_cast<float *>(ptr);          ptr += align16((size_t)BP_THREADS * M.nq * 4);
+    uint32_t *sbits = reinterpret_cast<uint32_t *>(ptr); ptr += align16((size_t)((M.npairs + 31) >> 5) * BP_THREADS * 4 + 16);
+    uint32_t *swcount = reinterpret_cast<uint32_t *>(ptr); ptr += align16((size_t)(BP_THREADS / 32) * max(M.npairs, 1) * 4);
     float *sstore = reinterpret_cast<float *>(ptr);      // [(nmoving*3 + nsave*12)][BP_THREADS]
 
     const int64_t block_first = (int64_t)blockIdx.x * BP_THREADS;
@@ -131,6 +134,7 @@ k_broadphase(DevModel M, StateSource src, int64_t n_states, float padding, Outpu
     stage_words(sb, M.bpboxes, M.nboxes * (int)sizeof(BpBox));
     stage_words(sp, M.bppairs, M.npairs * (int)sizeof(BpPair));
     load_states(src, M.nq, block_first, count, sq);
+    for (int i = threadIdx.x; i < (BP_THREADS / 32) * M.npairs; i += BP_THREADS) swcount[i] = 0;
     __syncthreads();
 
     const int tid = threadIdx.x;
@@ -214,40 +218,89 @@ k_broadphase(DevModel M, StateSource src, int64_t n_states, float padding, Outpu
         }
     }
 
+    // ---- pass 1: classify every pair; remember the undecided ones as per-thread bit words and
+    //      per-warp counts in shared memory (no global atomics on the critical path)
     const unsigned lane = tid & 31;
+    const unsigned warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    for (int p = 0; p < M.npairs; p++) {
-        if (MODE == MODE_BOOL && !__any_sync(0xffffffffu, alive)) break;
-        const BpPair pr = sp[p];
-        bool undecided = false;
-        if (alive) {
-            const float d2 = proxy_dist2(pr);
-            const bool exact = pr.kind == BP_EXACT_SPHERES;
-            const float slack = exact ? 0.f : BP_SLACK;
-            const float rs = pr.r_in + padding - slack;         // |proxy distance| <= rs  ->  certainly colliding
-            const bool sure = rs >= 0.f && d2 <= rs * rs;
-            if (sure) {
-                state_hit = true;
-                if (MODE == MODE_BOOL) alive = false;
-                if (MODE == MODE_BOOL_ALL) first_pair = min(first_pair, p);
-            }
-            if (MODE == MODE_DIST) {
-                const float lb = sqrtf(d2) - pr.r_out;
-                if (exact) bound = fminf(bound, fmaxf(lb, 0.f));  // the proxies are the shapes
-                undecided = !exact && (lb - slack <= bound);
-            } else {
-                const float rf = pr.r_out + padding + slack;    // proxy distance > rf  ->  certainly free
-                const bool free_ = exact ? !sure : (d2 > rf * rf);
-                undecided = !sure && !free_;
+    const int nwords = (M.npairs + 31) >> 5;
+    for (int w = 0; w < nwords; w++) {
+        uint32_t bits = 0;
+        if (!(MODE == MODE_BOOL && !__any_sync(0xffffffffu, alive))) {
+            const int pend = min(M.npairs, (w + 1) << 5);
+            for (int p = w << 5; p < pend; p++) {
+                const BpPair pr = sp[p];
+                bool undecided = false;
+                if (alive) {
+                    const float d2 = proxy_dist2(pr);
+                    const bool exact = pr.kind == BP_EXACT_SPHERES;
+                    const float slack = exact ? 0.f : BP_SLACK;
+                    const float rs = pr.r_in + padding - slack;         // |proxy distance| <= rs  ->  certainly colliding
+                    const bool sure = rs >= 0.f && d2 <= rs * rs;
+                    if (sure) {
+                        state_hit = true;
+                        if (MODE == MODE_BOOL) alive = false;
+                        if (MODE == MODE_BOOL_ALL) first_pair = min(first_pair, p);
+                    }
+                    if (MODE == MODE_DIST) {
+                        const float lb = sqrtf(d2) - pr.r_out;
+                        if (exact) bound = fminf(bound, fmaxf(lb, 0.f));  // the proxies are the shapes
+                        undecided = !exact && (lb - slack <= bound);
+                    } else {
+                        const float rf = pr.r_out + padding + slack;    // proxy distance > rf  ->  certainly free
+                        const bool free_ = exact ? !sure : (d2 > rf * rf);
+                        undecided = !sure && !free_;
+                    }
+                }
+                const unsigned um = __ballot_sync(0xffffffffu, undecided);
+                if (um && lane == 0) swcount[warp * M.npairs + p] = __popc(um);
+                bits |= (undecided ? 1u : 0u) << (p & 31);
             }
         }
-        const unsigned um = __ballot_sync(0xffffffffu, undecided);
-        if (um) {
-            const int leader = __ffs(um) - 1;
-            uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(bins.count + p, (uint32_t)__popc(um));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (undecided) bins.state[(int64_t)p * bins.cap + base + __popc(um & lt_mask)] = (int32_t)state;
+        // a state decided "colliding" needs none of its items (boolean mode)
+        sbits[w * BP_THREADS + tid] = bits;
+    }
+    __syncwarp();
+    if (MODE == MODE_BOOL && state_hit) {
+        // drop this thread's items: clear its bits and take them out of the warp counts
+        for (int w = 0; w < nwords; w++) {
+            uint32_t bits = sbits[w * BP_THREADS + tid];
+            sbits[w * BP_THREADS + tid] = 0;
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                atomicSub(&swcount[warp * M.npairs + (w << 5) + b], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- one global reservation per (block, pair), issued by different threads in parallel
+    for (int p = tid; p < M.npairs; p += BP_THREADS) {
+        uint32_t total = 0;
+        for (int wv = 0; wv < BP_THREADS / 32; wv++) total += swcount[wv * M.npairs + p];
+        uint32_t base = total ? atomicAdd(bins.count + p, total) : 0u;
+        for (int wv = 0; wv < BP_THREADS / 32; wv++) {
+            const uint32_t c = swcount[wv * M.npairs + p];
+            swcount[wv * M.npairs + p] = base;   // becomes the warp's base slot
+            base += c;
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: write the items (coalesced per warp and pair)
+    for (int w = 0; w < nwords; w++) {
+        const uint32_t bits = sbits[w * BP_THREADS + tid];
+        unsigned anyw = __ballot_sync(0xffffffffu, bits != 0);
+        if (!anyw) continue;
+        uint32_t warp_bits = bits;   // union over the warp: which pairs of this word have items
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) warp_bits |= __shfl_xor_sync(0xffffffffu, warp_bits, o);
+        while (warp_bits) {
+            const int b = __ffs(warp_bits) - 1;
+            warp_bits &= warp_bits - 1;
+            const int p = (w << 5) + b;
+            const bool mine = (bits >> b) & 1u;
+            const unsigned um = __ballot_sync(0xffffffffu, mine);
+            if (mine) bins.state[(int64_t)p * bins.cap + swcount[warp * M.npairs + p] + __popc(um & lt_mask)] = (int32_t)state;
         }
     }
 
@@ -423,7 +476,8 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *tile_
 
     int p;
     uint32_t begin, end;
-    while (next_tile(tile_counter, prefix, order, M.npairs, bins.count, p, begin, end)) {
+    bool have = next_tile(tile_counter, prefix, order, M.npairs, bins.count, p, begin, end);
+    while (have) {
         const DevGeom &GA = sg[sp[p].a];
         const DevGeom &GB = sg[sp[p].b];
         ShapeRef A, B;
@@ -443,9 +497,22 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *tile_
         uint32_t my_idx = 0;
         float bound = 0.f;
         uint32_t cursor = begin;
+        // next tile, fetched as soon as this one runs dry: if it belongs to the same pair the warp
+        // keeps streaming (no drain); otherwise the lanes drain and the warp switches pair
+        bool fetched = false, more = true;
+        int next_p = -1;
+        uint32_t next_begin = 0, next_end = 0;
         for (;;) {
-            // ---- refill finished lanes with the next items of this tile
             const unsigned need = __ballot_sync(0xffffffffu, !active);
+            if (need && cursor >= end && !fetched) {
+                more = next_tile(tile_counter, prefix, order, M.npairs, bins.count, next_p, next_begin, next_end);
+                fetched = true;
+                if (more && next_p == p) {
+                    begin = next_begin; end = next_end; cursor = next_begin;
+                    fetched = false;
+                }
+            }
+            // ---- refill finished lanes with the next items of this pair
             if (need && cursor < end) {
                 const uint32_t idx = cursor + __popc(need & lt_mask);
                 if (!active && idx < end) {
@@ -464,7 +531,7 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *tile_
                 cursor += __popc(need);
             }
             if (!__any_sync(0xffffffffu, active)) {
-                if (cursor >= end) break;
+                if (cursor >= end && fetched) break;
                 continue;
             }
             // ---- one GJK iteration for every active lane
@@ -487,6 +554,8 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *tile_
                 }
             }
         }
+        have = more;
+        p = next_p; begin = next_begin; end = next_end;
     }
 }
 
