@@ -13,6 +13,9 @@
 #include <vector>
 
 #include "pbp_kernels.cuh"
+#include "pbp_supmap.h"
+
+static_assert(pbp::SUPMAP_KD == pbp::SUPMAP_K, "support map resolution mismatch");
 
 using namespace pbp;
 
@@ -68,7 +71,7 @@ struct pbp_engine {
     bool bp_smem_store = true;  // per-thread broadphase store fits in shared memory
     bool verts_in_smem = true;
     DevModel dm{};
-    DeviceBuffer d_joints, d_jgeoms, d_geoms, d_bpgeoms, d_bpboxes, d_bppairs, d_paths, d_pathops, d_order, d_verts, d_qlim, d_frames;
+    DeviceBuffer d_joints, d_jgeoms, d_geoms, d_bpgeoms, d_bpboxes, d_bppairs, d_paths, d_pathops, d_order, d_verts, d_supcells, d_suplists, d_qlim, d_frames;
     // pipeline workspaces
     int64_t chunk = 0;  // states per broadphase/narrowphase round = bin capacity
     DeviceBuffer d_bin_state, d_bin_group, d_bin_sample, d_bin_T, d_ctrl;
@@ -88,12 +91,12 @@ struct pbp_engine {
 namespace {
 
 // control block layout (uint32 words): [0, npairs) bin counts, [npairs] item-setup tile counter,
-// [npairs + 1] narrowphase tile counter, then four 64-bit counters at an 8-byte aligned offset
+// [npairs + 1] narrowphase chunk cursor, then four 64-bit counters at an 8-byte aligned offset
 // (level total, emit cursor, select count, profiled item total).
 inline size_t ctrl_words(const pbp_engine *e) { return (size_t)e->npairs + 2; }
 inline uint32_t *ctrl_counts(pbp_engine *e) { return e->d_ctrl.as<uint32_t>(); }
 inline uint32_t *ctrl_tile_setup(pbp_engine *e) { return e->d_ctrl.as<uint32_t>() + e->npairs; }
-inline uint32_t *ctrl_tile_np(pbp_engine *e) { return e->d_ctrl.as<uint32_t>() + e->npairs + 1; }
+inline uint32_t *ctrl_chunk_np(pbp_engine *e) { return e->d_ctrl.as<uint32_t>() + e->npairs + 1; }
 inline unsigned long long *ctrl_u64(pbp_engine *e, int i) {
     const size_t off = (ctrl_words(e) * 4 + 7) & ~(size_t)7;
     return reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(e->d_ctrl.p) + off) + i;
@@ -124,9 +127,9 @@ int launch_round_kernels(pbp_engine *e, const StateSource &src, int64_t n, float
     LAUNCH_CHECK("k_item_setup");
     if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
     if (e->verts_in_smem)
-        k_narrowphase<MODE, true><<<e->np_blocks, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_tile_np(e), has_sample);
+        k_narrowphase<MODE, true><<<e->np_blocks, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
     else
-        k_narrowphase<MODE, false><<<e->np_blocks, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_tile_np(e), has_sample);
+        k_narrowphase<MODE, false><<<e->np_blocks, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
     LAUNCH_CHECK("k_narrowphase");
     return 0;
 }
@@ -231,7 +234,7 @@ void pbp_engine_destroy(pbp_engine *e) {
     for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->prof_pool) cudaEventDestroy(ev);
     DeviceBuffer *bufs[] = {&e->d_joints, &e->d_jgeoms, &e->d_geoms, &e->d_bpgeoms, &e->d_bpboxes, &e->d_bppairs, &e->d_paths,
-                            &e->d_pathops, &e->d_order, &e->d_verts, &e->d_qlim, &e->d_frames, &e->d_bin_state,
+                            &e->d_pathops, &e->d_order, &e->d_verts, &e->d_supcells, &e->d_suplists, &e->d_qlim, &e->d_frames, &e->d_bin_state,
                             &e->d_bin_group, &e->d_bin_sample, &e->d_bin_T, &e->d_ctrl, &e->d_counts, &e->d_desc_group,
                             &e->d_desc_frac, &e->d_desc_sample, &e->d_scratch_i32, &e->d_scratch_u8, &e->d_cub, &e->d_sel,
                             &e->d_io_q, &e->d_io_q2, &e->d_io_hit, &e->d_io_f32, &e->d_io_i32};
@@ -301,6 +304,7 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     std::vector<BpGeom> bpgeoms(std::max(d->ngeoms, 1));
     std::vector<BpBox> bpboxes;
     std::vector<float4> verts;
+    std::vector<uint16_t> sup_cells, sup_lists;
     std::vector<int32_t> jgeoms;
     int nmoving = 0;
     for (int g = 0; g < d->ngeoms; g++) {
@@ -308,6 +312,8 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
         BpGeom &B = bpgeoms[g];
         memset(&G, 0, sizeof G);
         memset(&B, 0, sizeof B);
+        G.map_off = -1;
+        G.list_off = 0;
         memcpy(G.P, d->geom_placement + 12 * g, sizeof G.P);
         memcpy(G.par, d->geom_params + 4 * g, sizeof G.par);
         const float *outer = d->geom_outer + 4 * g, *inner = d->geom_inner + 4 * g;
@@ -342,8 +348,28 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
             for (int i = 0; i < cnt; i++) verts.push_back(make_float4(d->verts[3 * (off + i)], d->verts[3 * (off + i) + 1], d->verts[3 * (off + i) + 2], 0.f));
             while (verts.size() % 4) verts.push_back(verts.back());
             G.vert_cnt = (int)verts.size() - G.vert_off;
+            // exact support map of this hull (shared by geometries with identical vertex data)
+            int same = -1;
+            for (int h = 0; h < g && same < 0; h++)
+                if (geoms[h].shape == PBP_SHAPE_CONVEX && d->geom_vert_cnt[h] == cnt &&
+                    memcmp(d->verts + 3 * d->geom_vert_off[h], d->verts + 3 * off, (size_t)cnt * 12) == 0)
+                    same = h;
+            if (same >= 0) {
+                G.map_off = geoms[same].map_off;
+                G.list_off = geoms[same].list_off;
+            } else if (cnt <= 65535) {
+                const SupMap sm = build_support_map(d->verts + 3 * off, cnt);
+                if (sm.list.size() <= 65535) {
+                    G.map_off = (int)sup_cells.size();
+                    G.list_off = (int)sup_lists.size();
+                    sup_cells.insert(sup_cells.end(), sm.cell_off.begin(), sm.cell_off.end());
+                    sup_lists.insert(sup_lists.end(), sm.list.begin(), sm.list.end());
+                }
+            }
         }
     }
+    while (sup_cells.empty() || sup_cells.size() % 8) sup_cells.push_back(0);
+    while (sup_lists.empty() || sup_lists.size() % 8) sup_lists.push_back(0);
     // moving geometries grouped by parent joint (the broadphase places them right after that joint)
     for (int j = 1; j < d->njoints; j++) {
         joints[j].geom_begin = (int)jgeoms.size();
@@ -438,6 +464,8 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
         (rc = upload(e->d_pathops, pathops.data(), pathops.size())) ||
         (rc = upload(e->d_order, order.data(), order.size() * sizeof(int32_t))) ||
         (rc = upload(e->d_verts, verts.data(), verts.size() * sizeof(float4))) ||
+        (rc = upload(e->d_supcells, sup_cells.data(), sup_cells.size() * 2)) ||
+        (rc = upload(e->d_suplists, sup_lists.data(), sup_lists.size() * 2)) ||
         (rc = upload(e->d_qlim, qlim.data(), qlim.size() * sizeof(float))))
         return bail(rc);
     {
@@ -463,6 +491,10 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     e->dm.path_ops = e->d_pathops.as<uint8_t>();
     e->dm.bin_order = e->d_order.as<int32_t>();
     e->dm.verts = e->d_verts.as<float4>();
+    e->dm.sup_cells = e->d_supcells.as<uint16_t>();
+    e->dm.sup_lists = e->d_suplists.as<uint16_t>();
+    e->dm.n_sup_cells = (int)sup_cells.size();
+    e->dm.n_sup_lists = (int)sup_lists.size();
     e->dm.q_lower = e->d_qlim.as<float>();
     e->dm.q_upper = e->d_qlim.as<float>() + d->nq;
 
@@ -477,7 +509,7 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     e->smem_is = align16((size_t)d->njoints * sizeof(DevJoint)) + align16((size_t)std::max(d->ngeoms, 1) * sizeof(DevGeom)) +
                  align16((size_t)np1 * sizeof(BpPair)) + align16((size_t)np1 * sizeof(PairPath)) + tile_tables + 16;
     const size_t np_tables = align16((size_t)std::max(d->ngeoms, 1) * sizeof(DevGeom)) + align16((size_t)np1 * sizeof(BpPair)) + tile_tables + 16;
-    const size_t vert_bytes = align16((size_t)e->nverts_padded * sizeof(float4));
+    const size_t vert_bytes = align16((size_t)e->nverts_padded * sizeof(float4)) + align16(sup_cells.size() * 2) + align16(sup_lists.size() * 2);
     e->verts_in_smem = np_tables + vert_bytes <= 96 * 1024;
     e->smem_np = np_tables + (e->verts_in_smem ? vert_bytes : 0);
     if (e->smem_bp > max_optin || e->smem_np > max_optin || e->smem_is > max_optin)

@@ -16,7 +16,11 @@ struct ShapeRef {
     float p0, p1, p2;       // box: half sides | cylinder/capsule: p0 = radius, p1 = half length
     const float4 *verts;    // convex: padded vertex table (shared memory or global)
     int nverts;             // multiple of 4
+    const uint16_t *cell_off;  // convex: support map (pbp_supmap.h), NULL -> scan every vertex
+    const uint16_t *cell_list;
 };
+
+constexpr int SUPMAP_KD = 8;  // must equal SUPMAP_K of pbp_supmap.h
 
 __device__ __forceinline__ float dot3(float3 a, float3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
 __device__ __forceinline__ float3 sub3(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
@@ -50,6 +54,39 @@ __device__ __forceinline__ float3 support_convex(const float4 *__restrict__ v, i
     return make_float3(p.x, p.y, p.z);
 }
 
+// Exact support through the hull's support map: the cell of the direction (cube-face chart) lists
+// every vertex that can be the maximiser for a direction in that cell (~3 instead of ~150).
+__device__ __forceinline__ float3 support_convex_map(const ShapeRef &s, float3 d) {
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int a;
+    float da, db, dc;
+    if (ax >= ay && ax >= az) { a = 0; da = d.x; db = d.y; dc = d.z; }
+    else if (ay >= az) { a = 1; da = d.y; db = d.z; dc = d.x; }
+    else { a = 2; da = d.z; db = d.x; dc = d.y; }
+    const float inv = 1.0f / fabsf(da);
+    const int iu = min(SUPMAP_KD - 1, max(0, (int)((db * inv + 1.0f) * (0.5f * SUPMAP_KD))));
+    const int iw = min(SUPMAP_KD - 1, max(0, (int)((dc * inv + 1.0f) * (0.5f * SUPMAP_KD))));
+    const int cell = (2 * a + (da < 0.f ? 1 : 0)) * (SUPMAP_KD * SUPMAP_KD) + iu * SUPMAP_KD + iw;
+    const int off = s.cell_off[cell], end = s.cell_off[cell + 1];
+    float best = -FLT_MAX;
+    float4 bp = make_float4(0.f, 0.f, 0.f, 0.f);
+    // four candidates per trip: the index loads, then the vertex loads, are independent of each
+    // other, so their shared-memory latencies overlap (lists are padded by 4 entries at the end)
+    for (int j = off; j < end; j += 4) {
+        const int i0 = s.cell_list[j], i1 = s.cell_list[j + 1], i2 = s.cell_list[j + 2], i3 = s.cell_list[j + 3];
+        const float4 p0 = s.verts[i0], p1 = s.verts[i1], p2 = s.verts[i2], p3 = s.verts[i3];
+        const float d0 = fmaf(p0.x, d.x, fmaf(p0.y, d.y, p0.z * d.z));
+        const float d1 = j + 1 < end ? fmaf(p1.x, d.x, fmaf(p1.y, d.y, p1.z * d.z)) : -FLT_MAX;
+        const float d2 = j + 2 < end ? fmaf(p2.x, d.x, fmaf(p2.y, d.y, p2.z * d.z)) : -FLT_MAX;
+        const float d3 = j + 3 < end ? fmaf(p3.x, d.x, fmaf(p3.y, d.y, p3.z * d.z)) : -FLT_MAX;
+        if (d0 > best) { best = d0; bp = p0; }
+        if (d1 > best) { best = d1; bp = p1; }
+        if (d2 > best) { best = d2; bp = p2; }
+        if (d3 > best) { best = d3; bp = p3; }
+    }
+    return make_float3(bp.x, bp.y, bp.z);
+}
+
 __device__ __forceinline__ float3 support_local(const ShapeRef &s, float3 d) {
     switch (s.shape) {
     case PBP_SHAPE_SPHERE:
@@ -64,7 +101,7 @@ __device__ __forceinline__ float3 support_local(const ShapeRef &s, float3 d) {
         return make_float3(d.x * k, d.y * k, d.z >= 0.f ? s.p1 : -s.p1);
     }
     default:
-        return support_convex(s.verts, s.nverts, d);
+        return s.cell_off ? support_convex_map(s, d) : support_convex(s.verts, s.nverts, d);
     }
 }
 
@@ -239,10 +276,45 @@ __device__ __forceinline__ bool gjk_step(const ShapeRef &A, const ShapeRef &B, c
         int mask;
         if (n == 0) { s.W0 = w; nv = w; mask = 1; }
         else if (n == 1) { s.W1 = w; mask = closest_on_segment(s.W0, s.W1, nv); }
-        else if (n == 2) { s.W2 = w; mask = closest_on_triangle(s.W0, s.W1, s.W2, nv); }
         else {
-            mask = closest_on_tetrahedron(s.W0, s.W1, s.W2, W3, nv);
-            if (mask == 0) { enclosed = true; nv = make_float3(0.f, 0.f, 0.f); }
+            // Triangle (n == 2) and tetrahedron (n == 3) share one code path so that the lanes of a
+            // warp, which sit at different simplex sizes, stay converged: the tetrahedron visits its
+            // four faces (face f omits vertex f), the triangle only "face 3" = (W0, W1, W2).
+            if (n == 2) s.W2 = w;
+            float best = FLT_MAX;
+            int bmask = 0;
+            float3 bv = make_float3(0.f, 0.f, 0.f);
+            bool any_outside = false;
+#pragma unroll
+            for (int f = 0; f < 4; f++) {
+                if (n == 2 && f != 3) continue;
+                const float3 P = f == 0 ? s.W1 : s.W0;
+                const float3 Q = f <= 1 ? s.W2 : s.W1;
+                const float3 R = f == 3 ? s.W2 : W3;
+                if (n == 3) {
+                    const float3 O = f == 0 ? s.W0 : (f == 1 ? s.W1 : (f == 2 ? s.W2 : W3));
+                    const float3 nf = cross3(sub3(Q, P), sub3(R, P));
+                    const float3 op = sub3(O, P);
+                    const float sd = dot3(nf, op);          // side of the omitted vertex
+                    const float so = -dot3(nf, P);          // side of the origin
+                    // a (nearly) flat tetrahedron has no reliable inside: its faces are all candidates
+                    const bool flat = sd * sd <= 1e-10f * dot3(nf, nf) * dot3(op, op);
+                    if (!flat && so * sd > 0.f) continue;   // origin strictly on the inner side of this face
+                }
+                any_outside = true;
+                float3 tv;
+                const int m = closest_on_triangle(P, Q, R, tv);
+                const float d2 = dot3(tv, tv);
+                if (d2 < best) {
+                    best = d2;
+                    bv = tv;
+                    const int ip = f == 0 ? 1 : 0, iq = f <= 1 ? 2 : 1, ir = f == 3 ? 2 : 3;
+                    bmask = ((m & 1) << ip) | (((m >> 1) & 1) << iq) | (((m >> 2) & 1) << ir);
+                }
+            }
+            if (!any_outside) { enclosed = true; bv = make_float3(0.f, 0.f, 0.f); }
+            nv = bv;
+            mask = bmask;
         }
         float nvv = dot3(nv, nv);
         if (!enclosed && n >= 2 && nvv >= vv) {
@@ -285,13 +357,12 @@ __device__ __forceinline__ bool gjk_step(const ShapeRef &A, const ShapeRef &B, c
         if (!done) {
             s.v = nv;
             s.vv = nvv;
-            // compact the kept vertices to the front (static indices only -> stays in registers)
-#pragma unroll
-            for (int pass = 0; pass < 3; pass++) {
-                if (!(mask & 1) && (mask >> 1)) { s.W0 = s.W1; s.W1 = s.W2; s.W2 = W3; mask >>= 1; }
-                if (!(mask & 2) && (mask >> 2)) { s.W1 = s.W2; s.W2 = W3; mask = (mask & 1) | ((mask >> 1) & ~1); }
-                if (!(mask & 4) && (mask >> 3)) { s.W2 = W3; mask = (mask & 3) | ((mask >> 1) & ~3); }
-            }
+            // compact the kept vertices to the front, branch-free (select chains on static registers)
+            const int m1 = mask & (mask - 1), m2 = m1 & (m1 - 1);
+            const int i0 = __ffs(mask) - 1, i1 = __ffs(m1) - 1, i2 = __ffs(m2) - 1;
+            auto pick = [&](int i) { return i == 0 ? s.W0 : (i == 1 ? s.W1 : (i == 2 ? s.W2 : W3)); };
+            const float3 n0 = pick(i0), n1 = pick(i1), n2 = pick(i2);
+            s.W0 = n0; s.W1 = n1; s.W2 = n2;
             s.n = __popc(mask);
             if (s.it >= PBP_GJK_MAX_ITERS) done = true;
         }

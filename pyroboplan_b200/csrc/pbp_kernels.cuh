@@ -448,114 +448,144 @@ k_item_setup(DevModel M, StateSource src, Outputs out, Bins bins, uint32_t *tile
 }
 
 // ------------------------------------------------------------------------------------------
-// Narrowphase (GJK), persistent, pair-major, lane refill
+// Narrowphase (GJK): persistent warps, one item per lane, lanes refilled as they finish
 // ------------------------------------------------------------------------------------------
-template <int MODE, bool VERTS_IN_SMEM>
-__global__ void __launch_bounds__(NP_THREADS)
-k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *tile_counter, bool has_sample) {
+// The items of all bins, concatenated in bin order, form one global sequence; warps claim chunks
+// of NP_CHUNK consecutive items from an atomic cursor and keep every lane busy: each trip of the
+// loop runs ONE GJK iteration for every active lane, and lanes whose item finished take the next
+// item of the chunk.  A lane carries its own pair (neighbouring items almost always share it, so
+// shape tables are read at the same shared-memory addresses), which means a warp never has to
+// drain when it crosses from one bin into the next.
+constexpr int NP_CHUNK = 128;
+
+template <int MODE, bool TABLES_IN_SMEM>
+__global__ void __launch_bounds__(NP_THREADS, 2)
+k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk_cursor, bool has_sample) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *ptr = smem_raw;
-    float4 *sv = reinterpret_cast<float4 *>(ptr);        ptr += VERTS_IN_SMEM ? align16((size_t)M.nverts_padded * sizeof(float4)) : 0;
+    float4 *sv = reinterpret_cast<float4 *>(ptr);        ptr += TABLES_IN_SMEM ? align16((size_t)M.nverts_padded * sizeof(float4)) : 0;
+    uint16_t *scell = reinterpret_cast<uint16_t *>(ptr); ptr += TABLES_IN_SMEM ? align16((size_t)M.n_sup_cells * 2) : 0;
+    uint16_t *slist = reinterpret_cast<uint16_t *>(ptr); ptr += TABLES_IN_SMEM ? align16((size_t)M.n_sup_lists * 2) : 0;
     DevGeom *sg = reinterpret_cast<DevGeom *>(ptr);      ptr += align16((size_t)max(M.ngeoms, 1) * sizeof(DevGeom));
     BpPair *sp = reinterpret_cast<BpPair *>(ptr);        ptr += align16((size_t)max(M.npairs, 1) * sizeof(BpPair));
-    uint32_t *prefix = reinterpret_cast<uint32_t *>(ptr); ptr += align16(((size_t)M.npairs + 1) * 4);
+    uint32_t *prefix = reinterpret_cast<uint32_t *>(ptr); ptr += align16(((size_t)M.npairs + 1) * 4);   // items before bin k
     int32_t *order = reinterpret_cast<int32_t *>(ptr);   ptr += align16((size_t)max(M.npairs, 1) * 4);
 
-    if (VERTS_IN_SMEM) stage_words(sv, M.verts, M.nverts_padded * (int)sizeof(float4));
+    if (TABLES_IN_SMEM) {
+        stage_words(sv, M.verts, M.nverts_padded * (int)sizeof(float4));
+        stage_words(scell, M.sup_cells, M.n_sup_cells * 2);
+        stage_words(slist, M.sup_lists, M.n_sup_lists * 2);
+    }
     stage_words(sg, M.geoms, M.ngeoms * (int)sizeof(DevGeom));
     stage_words(sp, M.bppairs, M.npairs * (int)sizeof(BpPair));
     stage_words(order, M.bin_order, M.npairs * 4);
     __syncthreads();
-    compute_tile_prefix(bins.count, order, M.npairs, prefix);
+    if (threadIdx.x < 32) {   // exclusive scan of the bin counts, in bin order
+        uint32_t run = 0;
+        for (int k0 = 0; k0 < M.npairs; k0 += 32) {
+            const int k = k0 + threadIdx.x;
+            const uint32_t t = k < M.npairs ? bins.count[order[k]] : 0u;
+            uint32_t inc = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)threadIdx.x >= o) inc += y;
+            }
+            if (k < M.npairs) prefix[k] = run + inc - t;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (threadIdx.x == 0) prefix[M.npairs] = run;
+    }
     __syncthreads();
 
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const float4 *verts = VERTS_IN_SMEM ? sv : M.verts;
+    const float4 *verts = TABLES_IN_SMEM ? sv : M.verts;
+    const uint16_t *cells = TABLES_IN_SMEM ? scell : M.sup_cells;
+    const uint16_t *lists = TABLES_IN_SMEM ? slist : M.sup_lists;
     const int64_t stride = (int64_t)M.npairs * bins.cap;
+    const uint32_t total = prefix[M.npairs];
 
-    int p;
-    uint32_t begin, end;
-    bool have = next_tile(tile_counter, prefix, order, M.npairs, bins.count, p, begin, end);
-    while (have) {
-        const DevGeom &GA = sg[sp[p].a];
-        const DevGeom &GB = sg[sp[p].b];
-        ShapeRef A, B;
-        A.shape = GA.shape; A.p0 = GA.par[0]; A.p1 = GA.par[1]; A.p2 = GA.par[2];
-        A.verts = verts + GA.vert_off; A.nverts = GA.vert_cnt;
-        B.shape = GB.shape; B.p0 = GB.par[0]; B.p1 = GB.par[1]; B.p2 = GB.par[2];
-        B.verts = verts + GB.vert_off; B.nverts = GB.vert_cnt;
-        const float radii = GA.core_radius + GB.core_radius;
-        const float margin = padding + radii;
-        const int64_t bin_base = (int64_t)p * bins.cap;
-
-        // lane-resident item
-        bool active = false;
-        GjkState s;
-        float T[12];
-        int32_t group = 0;
-        uint32_t my_idx = 0;
-        float bound = 0.f;
-        uint32_t cursor = begin;
-        // next tile, fetched as soon as this one runs dry: if it belongs to the same pair the warp
-        // keeps streaming (no drain); otherwise the lanes drain and the warp switches pair
-        bool fetched = false, more = true;
-        int next_p = -1;
-        uint32_t next_begin = 0, next_end = 0;
-        for (;;) {
-            const unsigned need = __ballot_sync(0xffffffffu, !active);
-            if (need && cursor >= end && !fetched) {
-                more = next_tile(tile_counter, prefix, order, M.npairs, bins.count, next_p, next_begin, next_end);
-                fetched = true;
-                if (more && next_p == p) {
-                    begin = next_begin; end = next_end; cursor = next_begin;
-                    fetched = false;
+    // lane-resident item
+    bool active = false;
+    GjkState s;
+    float T[12];
+    int32_t group = 0;
+    int p = 0;               // this lane's pair
+    int64_t slot = 0;        // this lane's bin slot
+    float bound = 0.f;
+    // chunk claimed by the warp
+    uint32_t cursor = 0, chunk_end = 0;
+    bool more = true;
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, !active);
+        if (need && cursor >= chunk_end && more) {
+            uint32_t c = 0;
+            if (lane == 0) c = atomicAdd(chunk_cursor, (uint32_t)NP_CHUNK);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c >= total) more = false;
+            else { cursor = c; chunk_end = min(c + NP_CHUNK, total); }
+        }
+        // ---- refill finished lanes with the next items of the chunk
+        if (need && cursor < chunk_end) {
+            const uint32_t gi = cursor + __popc(need & lt_mask);
+            if (!active && gi < chunk_end) {
+                int lo = 0, hi = M.npairs;  // last bin k with prefix[k] <= gi
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (prefix[mid] <= gi) lo = mid; else hi = mid;
                 }
-            }
-            // ---- refill finished lanes with the next items of this pair
-            if (need && cursor < end) {
-                const uint32_t idx = cursor + __popc(need & lt_mask);
-                if (!active && idx < end) {
-                    const int32_t g = bins.group[bin_base + idx];
-                    if (g >= 0 && !(MODE == MODE_BOOL && out.hit[g])) {
+                p = order[lo];
+                slot = (int64_t)p * bins.cap + (gi - prefix[lo]);
+                const int32_t g = bins.group[slot];
+                if (g >= 0 && !(MODE == MODE_BOOL && out.hit[g])) {
 #pragma unroll
-                        for (int k = 0; k < 12; k++) T[k] = bins.T[k * stride + bin_base + idx];
-                        const float3 cb = se3_act(T, GB.centre[0], GB.centre[1], GB.centre[2]);
-                        gjk_init(s, make_float3(GA.centre[0] - cb.x, GA.centre[1] - cb.y, GA.centre[2] - cb.z));
-                        group = g;
-                        my_idx = idx;
-                        if (MODE == MODE_DIST) bound = out.min_dist[g] + radii;  // group == state in this mode
-                        active = true;
-                    }
+                    for (int k = 0; k < 12; k++) T[k] = bins.T[k * stride + slot];
+                    const DevGeom &GA = sg[sp[p].a];
+                    const DevGeom &GB = sg[sp[p].b];
+                    const float3 cb = se3_act(T, GB.centre[0], GB.centre[1], GB.centre[2]);
+                    gjk_init(s, make_float3(GA.centre[0] - cb.x, GA.centre[1] - cb.y, GA.centre[2] - cb.z));
+                    group = g;
+                    if (MODE == MODE_DIST) bound = out.min_dist[g] + GA.core_radius + GB.core_radius;  // group == state here
+                    active = true;
                 }
-                cursor += __popc(need);
             }
-            if (!__any_sync(0xffffffffu, active)) {
-                if (cursor >= end && fetched) break;
-                continue;
-            }
-            // ---- one GJK iteration for every active lane
-            if (active) {
-                GjkOut r;
-                const bool done = (MODE == MODE_DIST) ? gjk_step<true>(A, B, T, s, margin, bound, r)
-                                                      : gjk_step<false>(A, B, T, s, margin, 0.f, r);
-                if (done) {
-                    active = false;
-                    if (MODE == MODE_DIST) {
-                        if (r.hit) out.hit[group] = 1;
-                        atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(fmaxf(r.dist - radii, 0.f)));
-                    } else if (r.hit) {
-                        out.hit[group] = 1;
-                        if (MODE == MODE_BOOL_ALL) {
-                            if (out.first_pair) atomicMin(out.first_pair + group, p);
-                            if (out.first_bad) atomicMin(out.first_bad + group, has_sample ? bins.sample[bin_base + my_idx] : 0);
-                        }
+            cursor += __popc(need);
+        }
+        if (!__any_sync(0xffffffffu, active)) {
+            if (!more && cursor >= chunk_end) break;
+            continue;
+        }
+        // ---- one GJK iteration for every active lane
+        if (active) {
+            const DevGeom &GA = sg[sp[p].a];
+            const DevGeom &GB = sg[sp[p].b];
+            ShapeRef A, B;
+            A.shape = GA.shape; A.p0 = GA.par[0]; A.p1 = GA.par[1]; A.p2 = GA.par[2];
+            A.verts = verts + GA.vert_off; A.nverts = GA.vert_cnt;
+            A.cell_off = GA.map_off >= 0 ? cells + GA.map_off : nullptr; A.cell_list = lists + GA.list_off;
+            B.shape = GB.shape; B.p0 = GB.par[0]; B.p1 = GB.par[1]; B.p2 = GB.par[2];
+            B.verts = verts + GB.vert_off; B.nverts = GB.vert_cnt;
+            B.cell_off = GB.map_off >= 0 ? cells + GB.map_off : nullptr; B.cell_list = lists + GB.list_off;
+            const float radii = GA.core_radius + GB.core_radius;
+            const float margin = padding + radii;
+            GjkOut r;
+            const bool done = (MODE == MODE_DIST) ? gjk_step<true>(A, B, T, s, margin, bound, r)
+                                                  : gjk_step<false>(A, B, T, s, margin, 0.f, r);
+            if (done) {
+                active = false;
+                if (MODE == MODE_DIST) {
+                    if (r.hit) out.hit[group] = 1;
+                    atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(fmaxf(r.dist - radii, 0.f)));
+                } else if (r.hit) {
+                    out.hit[group] = 1;
+                    if (MODE == MODE_BOOL_ALL) {
+                        if (out.first_pair) atomicMin(out.first_pair + group, p);
+                        if (out.first_bad) atomicMin(out.first_bad + group, has_sample ? bins.sample[slot] : 0);
                     }
                 }
             }
         }
-        have = more;
-        p = next_p; begin = next_begin; end = next_end;
     }
 }
 

@@ -22,7 +22,7 @@ struct DevJoint {       // 96 B
     int32_t _pad;
 };
 
-struct DevGeom {        // 96 B -- narrowphase / item-setup view of a geometry
+struct DevGeom {        // 112 B -- narrowphase / item-setup view of a geometry
     float P[12];        // placement in parent joint frame (world placement if parent == 0)
     float par[4];       // shape parameters
     float centre[3];    // proxy-sphere centre in the geometry frame (initial GJK direction)
@@ -31,6 +31,9 @@ struct DevGeom {        // 96 B -- narrowphase / item-setup view of a geometry
     int32_t shape;
     int32_t vert_off;   // offset into the padded float4 vertex table
     int32_t vert_cnt;   // padded to a multiple of 4 (last vertex repeated)
+    int32_t map_off;    // convex: offset of this hull's support-map cell table (uint16 units), -1 if none
+    int32_t list_off;   // convex: offset of this hull's candidate lists (uint16 units)
+    int32_t _pad[2];
 };
 
 struct BpGeom {         // 32 B -- broadphase view: one proxy centre, two radii
@@ -85,6 +88,9 @@ struct DevModel {
     const uint8_t *path_ops;
     const int32_t *bin_order;    // [npairs] pair indices sorted by decreasing narrowphase cost
     const float4 *verts;         // padded hull vertices
+    const uint16_t *sup_cells;   // support maps: per hull SUPMAP_CELLS + 1 offsets
+    const uint16_t *sup_lists;   // support maps: candidate vertex indices
+    int32_t n_sup_cells, n_sup_lists;   // uint16 entries (padded to a multiple of 8)
     const float *q_lower, *q_upper;
     const int32_t *frame_parent;
     const float *frame_placement;

@@ -9,7 +9,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libgjk_emu.so")
 _SRC = os.path.join(_HERE, "gjk_emu.cpp")
-_HDRS = [os.path.join(_HERE, "..", "..", "pyroboplan_b200", "csrc", f) for f in ("pbp_gjk.cuh", "pbp_model.cuh")]
+_HDRS = [os.path.join(_HERE, "..", "..", "pyroboplan_b200", "csrc", f) for f in ("pbp_gjk.cuh", "pbp_model.cuh", "pbp_supmap.h")]
 _lib = None
 
 
@@ -32,8 +32,10 @@ def load():
         _lib = ctypes.CDLL(_LIB)
         vp = ctypes.c_void_p
         _lib.emu_gjk_batch.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp,
-                                       ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_int, vp, vp, vp]
+                                       ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, vp, vp, vp]
         _lib.emu_gjk_batch.restype = None
+        _lib.emu_supmap_check.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int64, vp]
+        _lib.emu_supmap_check.restype = None
     return _lib
 
 
@@ -49,7 +51,17 @@ def padded_verts(arrays, g):
     return np.ascontiguousarray(v)
 
 
-def gjk_batch(arrays, ga, gb, T, v0, margin, want_dist=False, bound=np.inf):
+def supmap_check(arrays, g, dirs):
+    """(list entries, max candidates per cell, #directions where the map disagrees with a full scan)."""
+    lib = load()
+    v = padded_verts(arrays, g)
+    dirs = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
+    out = np.zeros(3, dtype=np.int64)
+    lib.emu_supmap_check(ctypes.c_void_p(v.ctypes.data), len(v), ctypes.c_void_p(dirs.ctypes.data), len(dirs), ctypes.c_void_p(out.ctypes.data))
+    return tuple(int(x) for x in out)
+
+
+def gjk_batch(arrays, ga, gb, T, v0, margin, want_dist=False, bound=np.inf, use_maps=True):
     """Run the FP32 GJK on n items of the pair (ga, gb). Returns (hit, dist, iters)."""
     lib = load()
     T = np.ascontiguousarray(T, dtype=np.float32).reshape(-1, 12)
@@ -64,7 +76,7 @@ def gjk_batch(arrays, ga, gb, T, v0, margin, want_dist=False, bound=np.inf):
     p = lambda a: ctypes.c_void_p(a.ctypes.data)
     lib.emu_gjk_batch(int(arrays["geom_shape"][ga]), p(pa), p(va), len(va) if arrays["geom_vert_cnt"][ga] else 0,
                       int(arrays["geom_shape"][gb]), p(pb), p(vb), len(vb) if arrays["geom_vert_cnt"][gb] else 0,
-                      p(T), p(v0), n, float(margin), float(bound), int(want_dist), p(hit), p(dist), p(iters))
+                      p(T), p(v0), n, float(margin), float(bound), int(want_dist), int(use_maps), p(hit), p(dist), p(iters))
     return hit, dist, iters
 
 
