@@ -9,6 +9,10 @@
 
 #include "pbp_model.cuh"
 
+#if !defined(__CUDACC__) && !defined(__noinline__)
+#define __noinline__ __attribute__((noinline))   // host build of this header (tests/host_emu)
+#endif
+
 namespace pbp {
 
 struct ShapeRef {
@@ -32,7 +36,7 @@ __device__ __forceinline__ float3 madd3(float3 a, float3 d, float t) {
 }
 
 // argmax_i <v_i, d> over a padded vertex table; 4 independent running maxima for ILP.
-__device__ __forceinline__ float3 support_convex(const float4 *__restrict__ v, int n, float3 d) {
+__device__ __noinline__ float3 support_convex(const float4 *__restrict__ v, int n, float3 d) {
     float b0 = -FLT_MAX, b1 = -FLT_MAX, b2 = -FLT_MAX, b3 = -FLT_MAX;
     int i0 = 0, i1 = 1, i2 = 2, i3 = 3;
 #pragma unroll 2
@@ -119,7 +123,9 @@ __device__ __forceinline__ int closest_on_segment(float3 A, float3 B, float3 &v)
     return 3;
 }
 
-__device__ __forceinline__ int closest_on_triangle(float3 A, float3 B, float3 C, float3 &v) {
+// Deliberately NOT inlined: it is called from several places of the simplex phase, and one copy
+// keeps the narrowphase kernel inside the instruction cache.
+__device__ __forceinline__ int closest_on_triangle_impl(float3 A, float3 B, float3 C, float3 &v) {
     const float3 ab = sub3(B, A), ac = sub3(C, A);
     const float3 n = cross3(ab, ac);
     const float nn = dot3(n, n);
@@ -166,6 +172,18 @@ __device__ __forceinline__ int closest_on_triangle(float3 A, float3 B, float3 C,
     const float k = dot3(A, n) / nn;
     v = make_float3(n.x * k, n.y * k, n.z * k);
     return 7;
+}
+
+// Out-of-line entry point (one copy in the kernel): closest point in xyz, vertex mask in w.
+__device__ __noinline__ float4 closest_on_triangle_packed(float3 A, float3 B, float3 C) {
+    float3 v;
+    const int m = closest_on_triangle_impl(A, B, C, v);
+    return make_float4(v.x, v.y, v.z, __int_as_float(m));
+}
+__device__ __forceinline__ int closest_on_triangle(float3 A, float3 B, float3 C, float3 &v) {
+    const float4 r = closest_on_triangle_packed(A, B, C);
+    v = make_float3(r.x, r.y, r.z);
+    return __float_as_int(r.w);
 }
 
 // Tetrahedron (A,B,C,D).  Returns 0 when the origin is inside (or on) it.
@@ -216,12 +234,14 @@ struct GjkOut {
 #define PBP_GJK_TOL 1e-6f       // ub - lb convergence (metres)
 #define PBP_GJK_EPS_ABS2 2.5e-13f  // |v|^2 below this counts as contact (|v| < 5e-7 m)
 
-// Per-item GJK state: lives in registers of the owning lane between iterations, so a warp can
-// run "one iteration for every active lane" and refill finished lanes with new items.
+// Per-item GJK state: lives in registers of the owning lane between phases, so a warp can run
+// "the support phase for every lane that needs one" / "the simplex phase for every lane that
+// needs one" and refill finished lanes with new items.
 struct GjkState {
     float3 v;            // current closest point of the simplex (search direction is -v)
     float vv;            // |v|^2
     float3 W0, W1, W2;   // simplex vertices (Minkowski-difference points), n of them valid
+    float3 w;            // newest support point, handed from the support phase to the simplex phase
     int n, it, stalls;
 };
 
@@ -229,26 +249,36 @@ __device__ __forceinline__ void gjk_init(GjkState &s, float3 v0) {
     s.v = v0;
     s.vv = dot3(v0, v0);
     if (!(s.vv > 1e-12f)) { s.v = make_float3(1.f, 0.f, 0.f); s.vv = 1.f; }
-    s.W0 = s.W1 = s.W2 = make_float3(0.f, 0.f, 0.f);
+    s.W0 = s.W1 = s.W2 = s.w = make_float3(0.f, 0.f, 0.f);
     s.n = 0; s.it = 0; s.stalls = 0;
 }
 
-// One GJK iteration.  T: placement of B in A's frame.  Returns true when the item is finished
-// (out is then valid).
+// Support phase of one GJK iteration: new support point of A - B in direction -v, then the
+// termination tests that only need it.  T: placement of B in A's frame.  Returns true when the
+// item is finished (out is then valid); otherwise s.w holds the point for the simplex phase.
 // WANT_DIST = false: finish as soon as "distance > margin" or "distance <= margin" is certain.
 // WANT_DIST = true : run to convergence unless the pair is certainly farther than `bound`.
 template <bool WANT_DIST>
-__device__ __forceinline__ bool gjk_step(const ShapeRef &A, const ShapeRef &B, const float *T, GjkState &s, float margin,
-                                         float bound, GjkOut &out) {
+__device__ __forceinline__ bool gjk_support_phase(const ShapeRef &A, const ShapeRef &B, const float *T, GjkState &s, float margin,
+                                                  float bound, GjkOut &out) {
     const float3 v = s.v;
     const float vv = s.vv;
     const int n = s.n;
     const float cut = WANT_DIST ? bound : margin;
-    // support of (A - B) in direction -v
-    const float3 sa = support_local(A, make_float3(-v.x, -v.y, -v.z));
     const float3 db = make_float3(fmaf(T[0], v.x, fmaf(T[3], v.y, T[6] * v.z)), fmaf(T[1], v.x, fmaf(T[4], v.y, T[7] * v.z)),
                                   fmaf(T[2], v.x, fmaf(T[5], v.y, T[8] * v.z)));
-    const float3 sl = support_local(B, db);
+    // one copy of the support code serves both shapes (instruction-cache footprint)
+    float3 sa = make_float3(0.f, 0.f, 0.f), sl = sa;
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+        ShapeRef S;
+        S.shape = side ? B.shape : A.shape;
+        S.p0 = side ? B.p0 : A.p0; S.p1 = side ? B.p1 : A.p1; S.p2 = side ? B.p2 : A.p2;
+        S.verts = side ? B.verts : A.verts; S.nverts = side ? B.nverts : A.nverts;
+        S.cell_off = side ? B.cell_off : A.cell_off; S.cell_list = side ? B.cell_list : A.cell_list;
+        const float3 r = support_local(S, side ? db : make_float3(-v.x, -v.y, -v.z));
+        if (side) sl = r; else sa = r;
+    }
     const float3 sb = se3_act(T, sl.x, sl.y, sl.z);
     const float3 w = sub3(sa, sb);
     const float vw = dot3(v, w);
@@ -262,15 +292,32 @@ __device__ __forceinline__ bool gjk_step(const ShapeRef &A, const ShapeRef &B, c
         out.hit = 0;
         return true;
     }
-    bool done = false, enclosed = false;
     if (n > 0) {
-        if (vv - vw <= PBP_GJK_TOL * sqrtf(vv)) done = true;  // v is (numerically) the closest point
+        bool done = vv - vw <= PBP_GJK_TOL * sqrtf(vv);   // v is (numerically) the closest point
         // w (numerically) already in the simplex: v cannot improve any further
         const float near2 = 1e-10f * dot3(w, w);
         const float3 e0 = sub3(w, s.W0), e1 = sub3(w, s.W1), e2 = sub3(w, s.W2);
         if (dot3(e0, e0) <= near2 || (n > 1 && dot3(e1, e1) <= near2) || (n > 2 && dot3(e2, e2) <= near2)) done = true;
+        if (done) {
+            out.dist = sqrtf(vv);
+            out.hit = out.dist <= margin;
+            return true;
+        }
     }
-    if (!done) {
+    s.w = w;
+    return false;
+}
+
+// Simplex phase: append s.w, find the point of the simplex closest to the origin, reduce the
+// simplex to the face that supports it.  Returns true when the item is finished.
+template <bool WANT_DIST>
+__device__ __forceinline__ bool gjk_simplex_phase(GjkState &s, float margin, GjkOut &out) {
+    const float3 w = s.w;
+    const float vv = s.vv;
+    const int n = s.n;
+    out.iters = s.it;
+    bool done = false, enclosed = false;
+    {
         // append w and solve for the closest point of the simplex
         float3 nv, W3 = w;
         int mask;
@@ -285,9 +332,8 @@ __device__ __forceinline__ bool gjk_step(const ShapeRef &A, const ShapeRef &B, c
             int bmask = 0;
             float3 bv = make_float3(0.f, 0.f, 0.f);
             bool any_outside = false;
-#pragma unroll
-            for (int f = 0; f < 4; f++) {
-                if (n == 2 && f != 3) continue;
+#pragma unroll 1
+            for (int f = (n == 2 ? 3 : 0); f < 4; f++) {
                 const float3 P = f == 0 ? s.W1 : s.W0;
                 const float3 Q = f <= 1 ? s.W2 : s.W1;
                 const float3 R = f == 3 ? s.W2 : W3;
@@ -320,19 +366,28 @@ __device__ __forceinline__ bool gjk_step(const ShapeRef &A, const ShapeRef &B, c
         if (!enclosed && n >= 2 && nvv >= vv) {
             // Backup step: sliver simplices (curved supports, near-duplicate points) can defeat the
             // region tests in FP32; retry with the sub-simplices that contain the new vertex.
-            float3 c1, c2, c3;
             if (n == 2) {
+                float3 c1, c2;
                 const int a1 = closest_on_segment(s.W0, s.W2, c1), a2 = closest_on_segment(s.W1, s.W2, c2);
                 const float e1 = dot3(c1, c1), e2 = dot3(c2, c2);
                 if (e1 < nvv && e1 <= e2) { nv = c1; mask = (a1 & 1) | ((a1 & 2) << 1); }
                 else if (e2 < nvv) { nv = c2; mask = a2 << 1; }
             } else {
-                const int a1 = closest_on_triangle(s.W0, s.W1, W3, c1), a2 = closest_on_triangle(s.W0, s.W2, W3, c2),
-                          a3 = closest_on_triangle(s.W1, s.W2, W3, c3);
-                const float e1 = dot3(c1, c1), e2 = dot3(c2, c2), e3 = dot3(c3, c3);
-                if (e1 < nvv && e1 <= e2 && e1 <= e3) { nv = c1; mask = (a1 & 3) | ((a1 & 4) << 1); }
-                else if (e2 < nvv && e2 <= e3) { nv = c2; mask = (a2 & 1) | ((a2 & 6) << 1); }
-                else if (e3 < nvv) { nv = c3; mask = a3 << 1; }
+                // the three faces that contain the new vertex W3: (W0,W1,W3), (W0,W2,W3), (W1,W2,W3)
+#pragma unroll 1
+                for (int f = 0; f < 3; f++) {
+                    const float3 P = f == 2 ? s.W1 : s.W0;
+                    const float3 Q = f == 0 ? s.W1 : s.W2;
+                    float3 c;
+                    const int a = closest_on_triangle(P, Q, W3, c);
+                    const float e = dot3(c, c);
+                    if (e < nvv) {
+                        nvv = e;
+                        nv = c;
+                        const int ip = f == 2 ? 1 : 0, iq = f == 0 ? 1 : 2;
+                        mask = ((a & 1) << ip) | (((a >> 1) & 1) << iq) | (((a >> 2) & 1) << 3);
+                    }
+                }
             }
             nvv = dot3(nv, nv);
         }
@@ -373,6 +428,14 @@ __device__ __forceinline__ bool gjk_step(const ShapeRef &A, const ShapeRef &B, c
         return true;
     }
     return false;
+}
+
+// One full GJK iteration (support phase, then simplex phase).
+template <bool WANT_DIST>
+__device__ __forceinline__ bool gjk_step(const ShapeRef &A, const ShapeRef &B, const float *T, GjkState &s, float margin,
+                                         float bound, GjkOut &out) {
+    if (gjk_support_phase<WANT_DIST>(A, B, T, s, margin, bound, out)) return true;
+    return gjk_simplex_phase<WANT_DIST>(s, margin, out);
 }
 
 // Whole item in one call (host build used by the CPU tests; the device narrowphase drives

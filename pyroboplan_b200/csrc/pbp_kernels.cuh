@@ -457,6 +457,7 @@ k_item_setup(DevModel M, StateSource src, Outputs out, Bins bins, uint32_t *tile
 // shape tables are read at the same shared-memory addresses), which means a warp never has to
 // drain when it crosses from one bin into the next.
 constexpr int NP_CHUNK = 128;
+constexpr int NP_SIMPLEX_QUORUM = 12;   // lanes waiting for a simplex phase that make it worth a trip
 
 template <int MODE, bool TABLES_IN_SMEM>
 __global__ void __launch_bounds__(NP_THREADS, 2)
@@ -506,8 +507,8 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
     const int64_t stride = (int64_t)M.npairs * bins.cap;
     const uint32_t total = prefix[M.npairs];
 
-    // lane-resident item
-    bool active = false;
+    // lane-resident item; phase: 0 = empty, 1 = needs a support phase, 2 = needs a simplex phase
+    int phase = 0;
     GjkState s;
     float T[12];
     int32_t group = 0;
@@ -518,7 +519,7 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
     uint32_t cursor = 0, chunk_end = 0;
     bool more = true;
     for (;;) {
-        const unsigned need = __ballot_sync(0xffffffffu, !active);
+        const unsigned need = __ballot_sync(0xffffffffu, phase == 0);
         if (need && cursor >= chunk_end && more) {
             uint32_t c = 0;
             if (lane == 0) c = atomicAdd(chunk_cursor, (uint32_t)NP_CHUNK);
@@ -529,7 +530,7 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
         // ---- refill finished lanes with the next items of the chunk
         if (need && cursor < chunk_end) {
             const uint32_t gi = cursor + __popc(need & lt_mask);
-            if (!active && gi < chunk_end) {
+            if (phase == 0 && gi < chunk_end) {
                 int lo = 0, hi = M.npairs;  // last bin k with prefix[k] <= gi
                 while (hi - lo > 1) {
                     const int mid = (lo + hi) >> 1;
@@ -547,17 +548,32 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
                     gjk_init(s, make_float3(GA.centre[0] - cb.x, GA.centre[1] - cb.y, GA.centre[2] - cb.z));
                     group = g;
                     if (MODE == MODE_DIST) bound = out.min_dist[g] + GA.core_radius + GB.core_radius;  // group == state here
-                    active = true;
+                    phase = 1;
                 }
             }
             cursor += __popc(need);
         }
-        if (!__any_sync(0xffffffffu, active)) {
+        // ---- run the phase most lanes are waiting for (most items end right after their first
+        //      support phase, so the simplex phase is only worth a trip once enough lanes queue up)
+        const int n_sup = __popc(__ballot_sync(0xffffffffu, phase == 1));
+        const int n_smp = __popc(__ballot_sync(0xffffffffu, phase == 2));
+        if (n_sup == 0 && n_smp == 0) {
             if (!more && cursor >= chunk_end) break;
             continue;
         }
-        // ---- one GJK iteration for every active lane
-        if (active) {
+        const bool refillable = more || cursor < chunk_end;
+        const bool run_simplex = n_smp > 0 && (n_sup == 0 || n_smp >= NP_SIMPLEX_QUORUM || (!refillable && n_smp >= n_sup));
+        bool finished = false;
+        GjkOut r;
+        float radii = 0.f;
+        if (run_simplex) {
+            if (phase == 2) {
+                const float margin = padding + sg[sp[p].a].core_radius + sg[sp[p].b].core_radius;
+                radii = margin - padding;
+                finished = (MODE == MODE_DIST) ? gjk_simplex_phase<true>(s, margin, r) : gjk_simplex_phase<false>(s, margin, r);
+                phase = finished ? 0 : 1;
+            }
+        } else if (phase == 1) {
             const DevGeom &GA = sg[sp[p].a];
             const DevGeom &GB = sg[sp[p].b];
             ShapeRef A, B;
@@ -567,22 +583,21 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
             B.shape = GB.shape; B.p0 = GB.par[0]; B.p1 = GB.par[1]; B.p2 = GB.par[2];
             B.verts = verts + GB.vert_off; B.nverts = GB.vert_cnt;
             B.cell_off = GB.map_off >= 0 ? cells + GB.map_off : nullptr; B.cell_list = lists + GB.list_off;
-            const float radii = GA.core_radius + GB.core_radius;
+            radii = GA.core_radius + GB.core_radius;
             const float margin = padding + radii;
-            GjkOut r;
-            const bool done = (MODE == MODE_DIST) ? gjk_step<true>(A, B, T, s, margin, bound, r)
-                                                  : gjk_step<false>(A, B, T, s, margin, 0.f, r);
-            if (done) {
-                active = false;
-                if (MODE == MODE_DIST) {
-                    if (r.hit) out.hit[group] = 1;
-                    atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(fmaxf(r.dist - radii, 0.f)));
-                } else if (r.hit) {
-                    out.hit[group] = 1;
-                    if (MODE == MODE_BOOL_ALL) {
-                        if (out.first_pair) atomicMin(out.first_pair + group, p);
-                        if (out.first_bad) atomicMin(out.first_bad + group, has_sample ? bins.sample[slot] : 0);
-                    }
+            finished = (MODE == MODE_DIST) ? gjk_support_phase<true>(A, B, T, s, margin, bound, r)
+                                           : gjk_support_phase<false>(A, B, T, s, margin, 0.f, r);
+            phase = finished ? 0 : 2;
+        }
+        if (finished) {
+            if (MODE == MODE_DIST) {
+                if (r.hit) out.hit[group] = 1;
+                atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(fmaxf(r.dist - radii, 0.f)));
+            } else if (r.hit) {
+                out.hit[group] = 1;
+                if (MODE == MODE_BOOL_ALL) {
+                    if (out.first_pair) atomicMin(out.first_pair + group, p);
+                    if (out.first_bad) atomicMin(out.first_bad + group, has_sample ? bins.sample[slot] : 0);
                 }
             }
         }

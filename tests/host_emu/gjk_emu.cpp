@@ -12,6 +12,8 @@
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline int __popc(int x) { return __builtin_popcount((unsigned)x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline float __int_as_float(int i) { float f; __builtin_memcpy(&f, &i, 4); return f; }
+static inline int __float_as_int(float f) { int i; __builtin_memcpy(&i, &f, 4); return i; }
 using std::max;
 using std::min;
 
