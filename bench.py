@@ -180,6 +180,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     model, cmodel = panda_models()
@@ -195,7 +197,9 @@ def main():
             dist.barrier()
 
     # ---------------- device-resident throughput
-    for w in range(args.warmup):
+    # W untimed warm-up steps (at least one per input batch, so no batch is touched for the
+    # first time inside the timed region)
+    for w in range(max(args.warmup, N_BATCHES + 1)):
         hits[w % N_BATCHES] = eng.check_states(dev_batches[w % N_BATCHES])
     torch.cuda.synchronize()
     fp32_peak = measure_fp32_peak(local_rank)
@@ -239,6 +243,14 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n * args.steps / float(t.item())
+    # pinned H2D bandwidth of this box, for context (the e2e path moves 36 B per state over PCIe)
+    h2d0, h2d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h2d0.record()
+    for b in range(N_BATCHES):
+        dev_batches[b].copy_(host_batches[b], non_blocking=True)
+    h2d1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = N_BATCHES * n * 36 / (h2d0.elapsed_time(h2d1) * 1e-3) / 1e9
 
     if rank != 0:
         if world > 1:
@@ -306,7 +318,8 @@ def main():
                    "l2": f"inputs rotate over {N_BATCHES} batches ({N_BATCHES * n * 36 / 1e6:.0f} MB > 126 MB L2)",
                    "parallelism": f"{world} rank(s), states sharded, no data-path collective"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 9 * 4, "d2h_bytes_per_step": n,
-                "api": "CollisionEngine.check_states(numpy) -> pbp_check_states_host (pinned host buffers)"},
+                "api": "CollisionEngine.check_states(numpy) -> pbp_check_states_host (pinned host buffers, copies overlapped with kernels)",
+                "pinned_h2d_gbs_measured": h2d_gbs, "pcie_bound_value": h2d_gbs * 1e9 / 36.0 * world},
         "gpu_launches": stats["kernel_launches"],
         "clocks": clocks,
         "roofline": roofline,

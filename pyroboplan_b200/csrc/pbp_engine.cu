@@ -71,13 +71,15 @@ struct pbp_engine {
     bool bp_smem_store = true;  // per-thread broadphase store fits in shared memory
     bool verts_in_smem = true;
     DevModel dm{};
-    DeviceBuffer d_joints, d_jgeoms, d_geoms, d_bpgeoms, d_bpboxes, d_bppairs, d_paths, d_pathops, d_order, d_verts, d_supcells, d_suplists, d_qlim, d_frames;
+    DeviceBuffer d_joints, d_jgeoms, d_geoms, d_bpgeoms, d_bpboxes, d_bppairs, d_groups, d_pairorig, d_paths, d_pathops, d_order, d_verts, d_supcells, d_suplists, d_qlim, d_frames;
     // pipeline workspaces
     int64_t chunk = 0;  // states per broadphase/narrowphase round = bin capacity
     DeviceBuffer d_bin_state, d_bin_group, d_bin_sample, d_bin_T, d_ctrl;
     DeviceBuffer d_counts, d_desc_group, d_desc_frac, d_desc_sample, d_scratch_i32, d_scratch_u8, d_cub, d_sel;
     DeviceBuffer d_io_q, d_io_q2, d_io_hit, d_io_f32, d_io_i32;   // staging for the *_host entry points
     unsigned long long *h_pinned = nullptr;  // small pinned mailbox for device -> host counters
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;   // *_host entry points: copy / compute pipeline
+    std::vector<cudaEvent_t> io_events;
     size_t smem_bp = 0, smem_is = 0, smem_np = 0, smem_fk = 0;
     int np_blocks = 0, is_blocks = 0;
     pbp_stats stats{};
@@ -233,13 +235,16 @@ void pbp_engine_destroy(pbp_engine *e) {
     cudaSetDevice(e->device);
     for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->prof_pool) cudaEventDestroy(ev);
-    DeviceBuffer *bufs[] = {&e->d_joints, &e->d_jgeoms, &e->d_geoms, &e->d_bpgeoms, &e->d_bpboxes, &e->d_bppairs, &e->d_paths,
+    DeviceBuffer *bufs[] = {&e->d_joints, &e->d_jgeoms, &e->d_geoms, &e->d_bpgeoms, &e->d_bpboxes, &e->d_bppairs, &e->d_groups, &e->d_pairorig, &e->d_paths,
                             &e->d_pathops, &e->d_order, &e->d_verts, &e->d_supcells, &e->d_suplists, &e->d_qlim, &e->d_frames, &e->d_bin_state,
                             &e->d_bin_group, &e->d_bin_sample, &e->d_bin_T, &e->d_ctrl, &e->d_counts, &e->d_desc_group,
                             &e->d_desc_frac, &e->d_desc_sample, &e->d_scratch_i32, &e->d_scratch_u8, &e->d_cub, &e->d_sel,
                             &e->d_io_q, &e->d_io_q2, &e->d_io_hit, &e->d_io_f32, &e->d_io_i32};
     for (DeviceBuffer *b : bufs) b->release();
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
+    for (cudaEvent_t ev : e->io_events) cudaEventDestroy(ev);
+    if (e->s_copy) cudaStreamDestroy(e->s_copy);
+    if (e->s_comp) cudaStreamDestroy(e->s_comp);
     delete e;
 }
 
@@ -383,9 +388,30 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     e->nmoving = nmoving;
     e->nverts_padded = (int)verts.size();
 
-    // ---- pairs: broadphase recipe, joint path for the item setup, bin order
+    // ---- pairs: internal order (moving-moving first, then one contiguous group per static
+    //      geometry), broadphase recipe, joint path for the item setup, bin order
     const int np1 = std::max(d->npairs, 1);
+    struct PairKey { int cls, sidx, orig; };
+    std::vector<PairKey> keys(d->npairs);
+    for (int p = 0; p < d->npairs; p++) {
+        const int a = d->pairs[2 * p], b = d->pairs[2 * p + 1];
+        if (a < 0 || b < 0 || a >= d->ngeoms || b >= d->ngeoms || a == b) return bail(fail(PBP_ERR_ARG, "pair %d: bad geometry ids", p));
+        const bool sa = bpgeoms[a].slot < 0, sb = bpgeoms[b].slot < 0;
+        PairKey k{GRP_GENERIC, 0, p};
+        if (!sa && !sb) k = PairKey{GRP_MOVING, 0, p};
+        else if (sa != sb) {
+            const int st = sa ? a : b;
+            if (bpgeoms[st].box >= 0) k = PairKey{GRP_STATIC_BOX, bpgeoms[st].box, p};
+            else k = PairKey{GRP_STATIC_POINT, st, p};
+        }
+        keys[p] = k;
+    }
+    std::stable_sort(keys.begin(), keys.end(), [](const PairKey &x, const PairKey &y) {
+        return x.cls != y.cls ? x.cls < y.cls : x.sidx < y.sidx;
+    });
     std::vector<BpPair> bppairs(np1);
+    std::vector<BpGroup> groups;
+    std::vector<int32_t> pair_orig(np1, 0);
     std::vector<PairPath> paths(np1);
     std::vector<uint8_t> pathops;
     std::vector<int32_t> order(np1, 0);
@@ -397,25 +423,28 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
         return c;
     };
     for (int p = 0; p < d->npairs; p++) {
-        const int a = d->pairs[2 * p], b = d->pairs[2 * p + 1];
-        if (a < 0 || b < 0 || a >= d->ngeoms || b >= d->ngeoms || a == b) return bail(fail(PBP_ERR_ARG, "pair %d: bad geometry ids", p));
+        const PairKey &key = keys[p];
+        const int a = d->pairs[2 * key.orig], b = d->pairs[2 * key.orig + 1];
+        pair_orig[p] = key.orig;
+        if (groups.empty() || groups.back().cls != key.cls || (key.cls != GRP_MOVING && key.cls != GRP_GENERIC && groups.back().sidx != key.sidx))
+            groups.push_back(BpGroup{key.cls, key.sidx, p, p});
+        groups.back().end = p + 1;
         BpPair &P = bppairs[p];
         memset(&P, 0, sizeof P);
         P.a = (uint8_t)a;
         P.b = (uint8_t)b;
-        P.box = -1;
-        const int sa = geoms[a].shape, sb = geoms[b].shape;
-        if (sa == PBP_SHAPE_SPHERE && sb == PBP_SHAPE_SPHERE) {
+        P.slot_a = (int16_t)bpgeoms[a].slot;
+        P.slot_b = (int16_t)bpgeoms[b].slot;
+        const int sha = geoms[a].shape, shb = geoms[b].shape;
+        if (sha == PBP_SHAPE_SPHERE && shb == PBP_SHAPE_SPHERE) {
             P.kind = BP_EXACT_SPHERES;
             P.r_out = P.r_in = geoms[a].par[0] + geoms[b].par[0];
         } else if (bpgeoms[a].box >= 0) {
             P.kind = BP_BOX_A;
-            P.box = bpgeoms[a].box;
             P.r_out = bpgeoms[b].r_out;
             P.r_in = bpgeoms[b].r_in;
         } else if (bpgeoms[b].box >= 0) {
             P.kind = BP_BOX_B;
-            P.box = bpgeoms[b].box;
             P.r_out = bpgeoms[a].r_out;
             P.r_in = bpgeoms[a].r_in;
         } else {
@@ -435,6 +464,7 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
         cost[p] = 8 + geoms[a].vert_cnt + geoms[b].vert_cnt;
         order[p] = p;
     }
+    if (groups.empty()) groups.push_back(BpGroup{GRP_GENERIC, 0, 0, 0});
     if (pathops.empty()) pathops.push_back(0);
     while (pathops.size() % 4) pathops.push_back(0);
     std::stable_sort(order.begin(), order.begin() + d->npairs, [&](int x, int y) { return cost[x] > cost[y]; });
@@ -460,6 +490,8 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
         (rc = upload(e->d_bpgeoms, bpgeoms.data(), bpgeoms.size() * sizeof(BpGeom))) ||
         (rc = upload(e->d_bpboxes, bpboxes.data(), bpboxes.size() * sizeof(BpBox))) ||
         (rc = upload(e->d_bppairs, bppairs.data(), bppairs.size() * sizeof(BpPair))) ||
+        (rc = upload(e->d_groups, groups.data(), groups.size() * sizeof(BpGroup))) ||
+        (rc = upload(e->d_pairorig, pair_orig.data(), pair_orig.size() * 4)) ||
         (rc = upload(e->d_paths, paths.data(), paths.size() * sizeof(PairPath))) ||
         (rc = upload(e->d_pathops, pathops.data(), pathops.size())) ||
         (rc = upload(e->d_order, order.data(), order.size() * sizeof(int32_t))) ||
@@ -487,6 +519,9 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     e->dm.bpgeoms = e->d_bpgeoms.as<BpGeom>();
     e->dm.bpboxes = e->d_bpboxes.as<BpBox>();
     e->dm.bppairs = e->d_bppairs.as<BpPair>();
+    e->dm.groups = e->d_groups.as<BpGroup>();
+    e->dm.pair_orig = e->d_pairorig.as<int32_t>();
+    e->dm.ngroups = (int)groups.size();
     e->dm.paths = e->d_paths.as<PairPath>();
     e->dm.path_ops = e->d_pathops.as<uint8_t>();
     e->dm.bin_order = e->d_order.as<int32_t>();
@@ -500,7 +535,7 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
 
     // ---- shared memory budgets and launch geometry
     const size_t max_optin = prop.sharedMemPerBlockOptin;
-    const size_t bp_tables = bp_table_bytes(d->njoints, nmoving, d->ngeoms, e->dm.nboxes, d->npairs, d->nq);
+    const size_t bp_tables = bp_table_bytes(d->njoints, nmoving, d->ngeoms, e->dm.nboxes, d->npairs, (int)groups.size(), d->nq);
     const size_t bp_store = (size_t)(nmoving * 3 + nsave * 12) * BP_THREADS * 4;
     e->bp_smem_store = bp_tables + bp_store <= 100 * 1024 && nmoving <= BP_MAX_LOCAL_CENTRES;
     e->smem_bp = bp_tables + (e->bp_smem_store ? bp_store : 0) + 16;
@@ -560,6 +595,8 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
         return bail(rc);
     CUDA_TRY(cudaMemset(e->d_ctrl.p, 0, ctrl_bytes(e)));
     CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&e->h_pinned), 64));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
     *out = e;
     return 0;
 }
@@ -760,6 +797,10 @@ int pbp_check_edges(pbp_engine *e, const float *q1_dev, const float *q2_dev, int
 // ------------------------------------------------------------------------------------------
 // host-buffer entry points: H2D, run, D2H, synchronise
 // ------------------------------------------------------------------------------------------
+// Host buffers in, host buffers out.  The batch is cut into slices; every slice's H2D copy is
+// queued on a copy stream up front and its FK/broadphase/narrowphase rounds + result D2H follow on
+// a compute stream as soon as that slice has landed, so PCIe transfers overlap the kernels
+// (with pinned host memory; pageable memory still works, just without overlap).
 int pbp_check_states_host(pbp_engine *e, const float *q_host, int64_t n, float padding, uint8_t *hit_host,
                           float *min_dist_host, int32_t *first_pair_host) {
     int rc = check_args(e, q_host, n);
@@ -770,16 +811,31 @@ int pbp_check_states_host(pbp_engine *e, const float *q_host, int64_t n, float p
     if ((rc = e->d_io_q.ensure((size_t)n * e->nq * 4)) || (rc = e->d_io_hit.ensure((size_t)n))) return rc;
     if (min_dist_host && (rc = e->d_io_f32.ensure((size_t)n * 4))) return rc;
     if (first_pair_host && (rc = e->d_io_i32.ensure((size_t)n * 4))) return rc;
-    cudaStream_t st = 0;
-    CUDA_TRY(cudaMemcpyAsync(e->d_io_q.p, q_host, (size_t)n * e->nq * 4, cudaMemcpyHostToDevice, st));
-    rc = pbp_check_states(e, e->d_io_q.as<float>(), n, padding, e->d_io_hit.as<uint8_t>(),
-                          min_dist_host ? e->d_io_f32.as<float>() : nullptr,
-                          first_pair_host ? e->d_io_i32.as<int32_t>() : nullptr, st);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(hit_host, e->d_io_hit.p, (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (min_dist_host) CUDA_TRY(cudaMemcpyAsync(min_dist_host, e->d_io_f32.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    if (first_pair_host) CUDA_TRY(cudaMemcpyAsync(first_pair_host, e->d_io_i32.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    const int64_t slice = 1 << 18;
+    const int64_t n_slices = (n + slice - 1) / slice;
+    while ((int64_t)e->io_events.size() < n_slices) {
+        cudaEvent_t ev;
+        CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        e->io_events.push_back(ev);
+    }
+    float *dq = e->d_io_q.as<float>();
+    for (int64_t k = 0; k < n_slices; k++) {
+        const int64_t off = k * slice, cnt = std::min(slice, n - off);
+        CUDA_TRY(cudaMemcpyAsync(dq + off * e->nq, q_host + off * e->nq, (size_t)cnt * e->nq * 4, cudaMemcpyHostToDevice, e->s_copy));
+        CUDA_TRY(cudaEventRecord(e->io_events[k], e->s_copy));
+    }
+    for (int64_t k = 0; k < n_slices; k++) {
+        const int64_t off = k * slice, cnt = std::min(slice, n - off);
+        CUDA_TRY(cudaStreamWaitEvent(e->s_comp, e->io_events[k], 0));
+        uint8_t *dh = e->d_io_hit.as<uint8_t>() + off;
+        float *dd = min_dist_host ? e->d_io_f32.as<float>() + off : nullptr;
+        int32_t *dp = first_pair_host ? e->d_io_i32.as<int32_t>() + off : nullptr;
+        if ((rc = pbp_check_states(e, dq + off * e->nq, cnt, padding, dh, dd, dp, e->s_comp))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(hit_host + off, dh, (size_t)cnt, cudaMemcpyDeviceToHost, e->s_comp));
+        if (dd) CUDA_TRY(cudaMemcpyAsync(min_dist_host + off, dd, (size_t)cnt * 4, cudaMemcpyDeviceToHost, e->s_comp));
+        if (dp) CUDA_TRY(cudaMemcpyAsync(first_pair_host + off, dp, (size_t)cnt * 4, cudaMemcpyDeviceToHost, e->s_comp));
+    }
+    CUDA_TRY(cudaStreamSynchronize(e->s_comp));
     return 0;
 }
 
@@ -793,7 +849,7 @@ int pbp_check_edges_host(pbp_engine *e, const float *q1_host, const float *q2_ho
     const size_t qb = (size_t)n_edges * e->nq * 4;
     if ((rc = e->d_io_q.ensure(qb)) || (rc = e->d_io_q2.ensure(qb)) || (rc = e->d_io_hit.ensure((size_t)n_edges))) return rc;
     if (first_bad_host && (rc = e->d_io_i32.ensure((size_t)n_edges * 4))) return rc;
-    cudaStream_t st = 0;
+    cudaStream_t st = e->s_comp;
     CUDA_TRY(cudaMemcpyAsync(e->d_io_q.p, q1_host, qb, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->d_io_q2.p, q2_host, qb, cudaMemcpyHostToDevice, st));
     rc = pbp_check_edges(e, e->d_io_q.as<float>(), e->d_io_q2.as<float>(), n_edges, step, padding, e->d_io_hit.as<uint8_t>(),

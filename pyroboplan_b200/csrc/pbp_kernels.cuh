@@ -99,11 +99,13 @@ __device__ __forceinline__ void load_states(const StateSource &src, int nq, int6
 }
 
 // Shared-memory footprint of the broadphase tables (everything but the per-thread store).
-__host__ __device__ inline size_t bp_table_bytes(int njoints, int nmoving, int ngeoms, int nboxes, int npairs, int nq) {
+__host__ __device__ inline size_t bp_table_bytes(int njoints, int nmoving, int ngeoms, int nboxes, int npairs, int ngroups, int nq) {
+    const size_t np1 = npairs > 0 ? npairs : 1;
     return align16((size_t)njoints * sizeof(DevJoint)) + align16((size_t)(nmoving > 0 ? nmoving : 1) * 4) +
            align16((size_t)(ngeoms > 0 ? ngeoms : 1) * sizeof(BpGeom)) + align16((size_t)(nboxes > 0 ? nboxes : 1) * sizeof(BpBox)) +
-           align16((size_t)(npairs > 0 ? npairs : 1) * sizeof(BpPair)) + align16((size_t)BP_THREADS * nq * 4) +
-           align16((size_t)((npairs + 31) >> 5) * BP_THREADS * 4 + 16) + align16((size_t)(BP_THREADS / 32) * (npairs > 0 ? npairs : 1) * 4);
+           align16(np1 * sizeof(BpPair)) + align16((size_t)(ngroups > 0 ? ngroups : 1) * sizeof(BpGroup)) + align16(np1 * sizeof(float2)) +
+           align16((size_t)BP_THREADS * nq * 4) + align16((size_t)((npairs + 31) >> 5) * BP_THREADS * 4 + 16) +
+           align16((size_t)(BP_THREADS / 32) * np1 * 4);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -121,6 +123,8 @@ k_broadphase(DevModel M, StateSource src, int64_t n_states, float padding, Outpu
     BpGeom *sg = reinterpret_cast<BpGeom *>(ptr);        ptr += align16((size_t)max(M.ngeoms, 1) * sizeof(BpGeom));
     BpBox *sb = reinterpret_cast<BpBox *>(ptr);          ptr += align16((size_t)max(M.nboxes, 1) * sizeof(BpBox));
     BpPair *sp = reinterpret_cast<BpPair *>(ptr);        ptr += align16((size_t)max(M.npairs, 1) * sizeof(BpPair));
+    BpGroup *sgrp = reinterpret_cast<BpGroup *>(ptr);    ptr += align16((size_t)max(M.ngroups, 1) * sizeof(BpGroup));
+    float2 *sthr = reinterpret_cast<float2 *>(ptr);      ptr += align16((size_t)max(M.npairs, 1) * sizeof(float2));
     float *sq = reinterpret_cast<float *>(ptr);          ptr += align16((size_t)BP_THREADS * M.nq * 4);
     uint32_t *sbits = reinterpret_cast<uint32_t *>(ptr); ptr += align16((size_t)((M.npairs + 31) >> 5) * BP_THREADS * 4 + 16);
     uint32_t *swcount = reinterpret_cast<uint32_t *>(ptr); ptr += align16((size_t)(BP_THREADS / 32) * max(M.npairs, 1) * 4);
@@ -133,8 +137,19 @@ k_broadphase(DevModel M, StateSource src, int64_t n_states, float padding, Outpu
     stage_words(sg, M.bpgeoms, M.ngeoms * (int)sizeof(BpGeom));
     stage_words(sb, M.bpboxes, M.nboxes * (int)sizeof(BpBox));
     stage_words(sp, M.bppairs, M.npairs * (int)sizeof(BpPair));
+    stage_words(sgrp, M.groups, M.ngroups * (int)sizeof(BpGroup));
     load_states(src, M.nq, block_first, count, sq);
     for (int i = threadIdx.x; i < (BP_THREADS / 32) * M.npairs; i += BP_THREADS) swcount[i] = 0;
+    // squared decision thresholds of every pair for this call's padding:
+    //   d2 > x -> certainly free,  d2 <= y -> certainly colliding  (y < 0: never)
+    for (int p = threadIdx.x; p < M.npairs; p += BP_THREADS) {
+        const BpPair pr = M.bppairs[p];
+        const bool exact = pr.kind == BP_EXACT_SPHERES;
+        const float slack = exact ? 0.f : BP_SLACK;
+        const float rf = pr.r_out + padding + slack, rs = pr.r_in + padding - slack;
+        const float y = rs >= 0.f ? rs * rs : -1.f;
+        sthr[p] = make_float2(exact ? y : rf * rf, y);
+    }
     __syncthreads();
 
     const int tid = threadIdx.x;
@@ -184,93 +199,117 @@ k_broadphase(DevModel M, StateSource src, int64_t n_states, float padding, Outpu
         }
     }
 
-    auto centre = [&](int g) {
-        const BpGeom &G = sg[g];
-        if (G.slot < 0) return make_float3(G.c[0], G.c[1], G.c[2]);
-        return make_float3(store(G.slot * 3 + 0), store(G.slot * 3 + 1), store(G.slot * 3 + 2));
+    auto moving_centre = [&](int slot) { return make_float3(store(slot * 3 + 0), store(slot * 3 + 1), store(slot * 3 + 2)); };
+    auto any_centre = [&](int g, int slot) {
+        return slot >= 0 ? moving_centre(slot) : make_float3(sg[g].c[0], sg[g].c[1], sg[g].c[2]);
     };
-    // squared distance between the proxies of one pair (centre-centre, or centre-to-box)
-    auto proxy_dist2 = [&](const BpPair &pr) {
-        if (pr.kind == BP_BOX_A || pr.kind == BP_BOX_B) {
-            const BpBox &bx = sb[pr.box];
-            const float3 c = centre(pr.kind == BP_BOX_A ? pr.b : pr.a);
-            const float dx = c.x - bx.t[0], dy = c.y - bx.t[1], dz = c.z - bx.t[2];
-            const float lx = fmaf(bx.R[0], dx, fmaf(bx.R[3], dy, bx.R[6] * dz));
-            const float ly = fmaf(bx.R[1], dx, fmaf(bx.R[4], dy, bx.R[7] * dz));
-            const float lz = fmaf(bx.R[2], dx, fmaf(bx.R[5], dy, bx.R[8] * dz));
-            const float ex = fmaxf(fabsf(lx) - bx.h[0], 0.f), ey = fmaxf(fabsf(ly) - bx.h[1], 0.f), ez = fmaxf(fabsf(lz) - bx.h[2], 0.f);
-            return fmaf(ex, ex, fmaf(ey, ey, ez * ez));
-        }
-        const float3 d = sub3(centre(pr.a), centre(pr.b));
+    auto box_dist2 = [&](const BpBox &bx, float3 c) {
+        const float dx = c.x - bx.t[0], dy = c.y - bx.t[1], dz = c.z - bx.t[2];
+        const float lx = fmaf(bx.R[0], dx, fmaf(bx.R[3], dy, bx.R[6] * dz));
+        const float ly = fmaf(bx.R[1], dx, fmaf(bx.R[4], dy, bx.R[7] * dz));
+        const float lz = fmaf(bx.R[2], dx, fmaf(bx.R[5], dy, bx.R[8] * dz));
+        const float ex = fmaxf(fabsf(lx) - bx.h[0], 0.f), ey = fmaxf(fabsf(ly) - bx.h[1], 0.f), ez = fmaxf(fabsf(lz) - bx.h[2], 0.f);
+        return fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+    };
+    // proxy distance of any pair, without the per-group hoisting (MODE_DIST pass 1, generic groups)
+    auto generic_dist2 = [&](const BpPair &pr) {
+        if (pr.kind == BP_BOX_A) return box_dist2(sb[sg[pr.a].box], any_centre(pr.b, pr.slot_b));
+        if (pr.kind == BP_BOX_B) return box_dist2(sb[sg[pr.b].box], any_centre(pr.a, pr.slot_a));
+        const float3 d = sub3(any_centre(pr.a, pr.slot_a), any_centre(pr.b, pr.slot_b));
         return dot3(d, d);
     };
 
     float bound = INFINITY;     // MODE_DIST: certain upper bound of this state's min distance
-    int first_pair = INT_MAX;   // MODE_BOOL_ALL
+    int first_pair = INT_MAX;   // MODE_BOOL_ALL (caller's pair numbering)
     bool state_hit = false;
 
     if (MODE == MODE_DIST && alive) {
-        // pass 1: the smallest certain upper bound over all pairs
+        // pass 0: the smallest certain upper bound over all pairs
         for (int p = 0; p < M.npairs; p++) {
             const BpPair pr = sp[p];
             const float slack = pr.kind == BP_EXACT_SPHERES ? 0.f : BP_SLACK;
-            bound = fminf(bound, fmaxf(sqrtf(proxy_dist2(pr)) - pr.r_in + slack, 0.f));
+            bound = fminf(bound, fmaxf(sqrtf(generic_dist2(pr)) - pr.r_in + slack, 0.f));
         }
     }
 
-    // ---- pass 1: classify every pair; remember the undecided ones as per-thread bit words and
-    //      per-warp counts in shared memory (no global atomics on the critical path)
+    // ---- pass 1: classify every pair, group by group; undecided pairs become bits of per-thread
+    //      words kept in shared memory (no atomics on the critical path)
     const unsigned lane = tid & 31;
     const unsigned warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int nwords = (M.npairs + 31) >> 5;
-    for (int w = 0; w < nwords; w++) {
-        uint32_t bits = 0;
-        if (!(MODE == MODE_BOOL && !__any_sync(0xffffffffu, alive))) {
-            const int pend = min(M.npairs, (w + 1) << 5);
-            for (int p = w << 5; p < pend; p++) {
+    uint32_t bits = 0;
+    auto classify = [&](int p, float d2) {
+        bool undecided = false;
+        if (alive) {
+            const float2 thr = sthr[p];
+            const bool sure = d2 <= thr.y;
+            if (sure) {
+                state_hit = true;
+                if (MODE == MODE_BOOL) alive = false;
+                if (MODE == MODE_BOOL_ALL) first_pair = min(first_pair, M.pair_orig[p]);
+            }
+            if (MODE == MODE_DIST) {
                 const BpPair pr = sp[p];
-                bool undecided = false;
-                if (alive) {
-                    const float d2 = proxy_dist2(pr);
-                    const bool exact = pr.kind == BP_EXACT_SPHERES;
-                    const float slack = exact ? 0.f : BP_SLACK;
-                    const float rs = pr.r_in + padding - slack;         // |proxy distance| <= rs  ->  certainly colliding
-                    const bool sure = rs >= 0.f && d2 <= rs * rs;
-                    if (sure) {
-                        state_hit = true;
-                        if (MODE == MODE_BOOL) alive = false;
-                        if (MODE == MODE_BOOL_ALL) first_pair = min(first_pair, p);
-                    }
-                    if (MODE == MODE_DIST) {
-                        const float lb = sqrtf(d2) - pr.r_out;
-                        if (exact) bound = fminf(bound, fmaxf(lb, 0.f));  // the proxies are the shapes
-                        undecided = !exact && (lb - slack <= bound);
-                    } else {
-                        const float rf = pr.r_out + padding + slack;    // proxy distance > rf  ->  certainly free
-                        const bool free_ = exact ? !sure : (d2 > rf * rf);
-                        undecided = !sure && !free_;
-                    }
-                }
-                const unsigned um = __ballot_sync(0xffffffffu, undecided);
-                if (um && lane == 0) swcount[warp * M.npairs + p] = __popc(um);
-                bits |= (undecided ? 1u : 0u) << (p & 31);
+                const bool exact = pr.kind == BP_EXACT_SPHERES;
+                const float lb = sqrtf(d2) - pr.r_out;
+                if (exact) bound = fminf(bound, fmaxf(lb, 0.f));  // the proxies are the shapes
+                undecided = !exact && (lb - BP_SLACK <= bound);
+            } else {
+                undecided = !sure && !(d2 > thr.x);
             }
         }
-        // a state decided "colliding" needs none of its items (boolean mode)
-        sbits[w * BP_THREADS + tid] = bits;
-    }
-    __syncwarp();
-    if (MODE == MODE_BOOL && state_hit) {
-        // drop this thread's items: clear its bits and take them out of the warp counts
-        for (int w = 0; w < nwords; w++) {
-            uint32_t bits = sbits[w * BP_THREADS + tid];
-            sbits[w * BP_THREADS + tid] = 0;
-            while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                atomicSub(&swcount[warp * M.npairs + (w << 5) + b], 1u);
+        bits |= (undecided ? 1u : 0u) << (p & 31);
+        if ((p & 31) == 31 || p == M.npairs - 1) {   // word complete (uniform branch)
+            sbits[(p >> 5) * BP_THREADS + tid] = bits;
+            bits = 0;
+        }
+    };
+    for (int gi = 0; gi < M.ngroups; gi++) {
+        const BpGroup grp = sgrp[gi];
+        if (MODE == MODE_BOOL && !__any_sync(0xffffffffu, alive)) {
+            // nobody needs the remaining pairs: their words are zero
+            for (int p = grp.begin; p < grp.end; p++) classify(p, 0.f);
+            continue;
+        }
+        if (grp.cls == GRP_MOVING) {
+            for (int p = grp.begin; p < grp.end; p++) {
+                const BpPair pr = sp[p];
+                const float3 d = sub3(moving_centre(pr.slot_a), moving_centre(pr.slot_b));
+                classify(p, dot3(d, d));
             }
+        } else if (grp.cls == GRP_STATIC_POINT) {
+            const float3 c0 = make_float3(sg[grp.sidx].c[0], sg[grp.sidx].c[1], sg[grp.sidx].c[2]);
+            for (int p = grp.begin; p < grp.end; p++) {
+                const BpPair pr = sp[p];
+                const float3 d = sub3(moving_centre(pr.slot_a >= 0 ? pr.slot_a : pr.slot_b), c0);
+                classify(p, dot3(d, d));
+            }
+        } else if (grp.cls == GRP_STATIC_BOX) {
+            const BpBox &bx = sb[grp.sidx];
+            for (int p = grp.begin; p < grp.end; p++) {
+                const BpPair pr = sp[p];
+                classify(p, box_dist2(bx, moving_centre(pr.slot_a >= 0 ? pr.slot_a : pr.slot_b)));
+            }
+        } else {
+            for (int p = grp.begin; p < grp.end; p++) classify(p, generic_dist2(sp[p]));
+        }
+    }
+    // ---- per-warp item counts of every pair that has items in this warp
+    if (MODE == MODE_BOOL && state_hit) {
+        // a state decided "colliding" needs none of its items
+        for (int w = 0; w < nwords; w++) sbits[w * BP_THREADS + tid] = 0;
+    }
+    for (int w = 0; w < nwords; w++) {
+        const uint32_t mybits = sbits[w * BP_THREADS + tid];
+        uint32_t warp_bits = mybits;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) warp_bits |= __shfl_xor_sync(0xffffffffu, warp_bits, o);
+        while (warp_bits) {
+            const int b = __ffs(warp_bits) - 1;
+            warp_bits &= warp_bits - 1;
+            const unsigned um = __ballot_sync(0xffffffffu, (mybits >> b) & 1u);
+            if (lane == 0) swcount[warp * M.npairs + (w << 5) + b] = __popc(um);
         }
     }
     __syncthreads();
@@ -596,7 +635,7 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
             } else if (r.hit) {
                 out.hit[group] = 1;
                 if (MODE == MODE_BOOL_ALL) {
-                    if (out.first_pair) atomicMin(out.first_pair + group, p);
+                    if (out.first_pair) atomicMin(out.first_pair + group, M.pair_orig[p]);
                     if (out.first_bad) atomicMin(out.first_bad + group, has_sample ? bins.sample[slot] : 0);
                 }
             }

@@ -52,13 +52,16 @@ struct BpBox {          // 64 B -- static box: world placement + half sides
     float _pad;
 };
 
+// Pairs are renumbered internally (DevModel::pair_orig maps back to the caller's index): first the
+// pairs between two moving geometries, then the pairs against each static geometry as one
+// contiguous group per static geometry, so the broadphase loads an obstacle once per group.
 struct BpPair {         // 16 B
-    uint8_t a, b;       // geometry ids (first, second)
-    uint8_t kind;       // BP_*
+    int16_t slot_a, slot_b;  // per-thread centre slots of a / b, -1 if static
+    uint8_t a, b;            // geometry ids (first, second)
+    uint8_t kind;            // BP_*
     uint8_t _pad;
-    float r_out;        // BP_SPHERES: r_out(a) + r_out(b) | BP_BOX_*: r_out of the non-box geometry
-    float r_in;         // same for the inscribed radii
-    int32_t box;        // BP_BOX_*: static-box table index
+    float r_out;             // BP_SPHERES: r_out(a) + r_out(b) | BP_BOX_*: r_out of the non-box geometry
+    float r_in;              // same for the inscribed radii
 };
 
 // Broadphase recipes (warp-uniform per pair).
@@ -69,6 +72,19 @@ enum : uint8_t {
     BP_EXACT_SPHERES = 3,  // both shapes are spheres: the proxies are the shapes, decided exactly
 };
 
+// A run of consecutive (internal) pairs that share how their proxy distance is computed.
+enum : int32_t {
+    GRP_MOVING = 0,        // both geometries move: centre - centre
+    GRP_STATIC_POINT = 1,  // one static sphere-proxy (centre loaded once) vs moving geometries
+    GRP_STATIC_BOX = 2,    // one static box (placement loaded once) vs moving geometries
+    GRP_GENERIC = 3,       // anything else (static vs static, ...)
+};
+struct BpGroup {        // 16 B
+    int32_t cls;        // GRP_*
+    int32_t sidx;       // GRP_STATIC_POINT: static geometry id | GRP_STATIC_BOX: static-box table index
+    int32_t begin, end; // internal pair range
+};
+
 // Joint path of a pair for the item-setup FK: trunk (root .. lowest common ancestor), then the
 // branch to a's joint, then the branch to b's joint.  Ops are joint indices.
 struct PairPath {       // 8 B
@@ -77,13 +93,15 @@ struct PairPath {       // 8 B
 };
 
 struct DevModel {
-    int32_t nq, njoints, ngeoms, npairs, nverts_padded, nframes, nmoving, nsave, nboxes, _pad;
+    int32_t nq, njoints, ngeoms, npairs, nverts_padded, nframes, nmoving, nsave, nboxes, ngroups;
     const DevJoint *joints;
     const int32_t *joint_geoms;  // moving geometry ids grouped by parent joint
     const DevGeom *geoms;
     const BpGeom *bpgeoms;
     const BpBox *bpboxes;
     const BpPair *bppairs;
+    const BpGroup *groups;
+    const int32_t *pair_orig;    // [npairs] internal pair index -> caller's pair index
     const PairPath *paths;
     const uint8_t *path_ops;
     const int32_t *bin_order;    // [npairs] pair indices sorted by decreasing narrowphase cost

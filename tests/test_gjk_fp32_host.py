@@ -97,3 +97,37 @@ def test_fp32_gjk_near_contact_band():
     bad = hit.astype(bool) != hit_ref
     # penetrating side: clearance is reported as 0 by the oracle, so measure the band in q instead
     assert np.all(np.abs(qs[bad, 0] - lo) < 2e-6), (qs[bad, 0] - lo)
+
+
+def test_support_maps_are_exact():
+    """The per-hull support maps (pbp_supmap.h) return the same support VALUE as a scan of every
+    vertex, for random directions and for directions on cell boundaries / coordinate axes."""
+    model, cmodel, _ = make_panda()
+    arrays, _ = flatten_model(model, cmodel)
+    rng = np.random.default_rng(7)
+    d = rng.normal(size=(60000, 3)).astype(np.float32)
+    d[:2000] = np.round(d[:2000])                      # axis / face-diagonal directions
+    d[2000:4000, 0] = np.abs(d[2000:4000, 1])          # |u| == 1 chart boundaries
+    k = rng.integers(-4, 5, size=(2000, 2)).astype(np.float32) / 4.0
+    d[4000:6000] = np.stack([np.ones(2000, dtype=np.float32), k[:, 0], k[:, 1]], axis=1)  # exact cell edges
+    d = d[np.abs(d).sum(axis=1) > 0]
+    for g in (0, 1, 5, 8, 9):
+        entries, max_per_cell, mismatches = emu.supmap_check(arrays, g, d)
+        assert mismatches == 0
+        assert entries / 384 < 4.0 and max_per_cell <= 24   # ~3 candidates per cell instead of 100-150 vertices
+
+
+def test_support_maps_do_not_change_gjk_results():
+    model, cmodel, _ = make_panda()
+    arrays, _ = flatten_model(model, cmodel)
+    orc = Oracle(model, cmodel)
+    q = uniform_states(model, 150, 23).astype(np.float64)
+    oMg = np.array([orc.fk(x)[1] for x in q])
+    for a, b in ((1, 5), (0, 8), (14, 3), (12, 6), (5, 10)):
+        T = emu.relative_placements(oMg, a, b)
+        v0 = -T[:, 9:]
+        radii = sum(float(arrays["geom_params"][g][0]) for g in (a, b) if arrays["geom_shape"][g] in (0, 3))
+        h1, d1, _ = emu.gjk_batch(arrays, a, b, T, v0, radii, True, use_maps=True)
+        h0, d0, _ = emu.gjk_batch(arrays, a, b, T, v0, radii, True, use_maps=False)
+        assert (h1 == h0).all()
+        np.testing.assert_allclose(d1, d0, atol=2e-6)
