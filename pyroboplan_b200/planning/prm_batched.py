@@ -1,0 +1,81 @@
+"""Batched PRM roadmap construction (BASELINE.json config 4).
+
+The reference grows a roadmap node by node (`PRMPlanner.construct_roadmap` /
+`connect_node`, /root/reference/src/pyroboplan/planning/prm.py:115-205): rejection-sample a free
+configuration, take its `k` nearest *earlier* nodes within `radius`
+(`Graph.get_nearest_neighbors`, planning/graph.py:271-301, sorted by distance) and keep the
+edges whose straight segment is collision free (`has_collision_free_path(node.q, new_node.q, ...)`).
+
+Every one of those steps is independent across nodes once the node set is fixed, so here they are
+batched: (1) free nodes from the device sampler, (2) k nearest predecessors by brute-force L2 on
+the GPU (dense `torch.cdist` + `topk`, library code: the k-NN is not the hot path of this
+repository), (3) ALL candidate edges validated in one `check_edges` call -- block-sharded across
+ranks, with one NCCL all-gather assembling the validity mask on every rank.
+"""
+
+import numpy as np
+
+from ..distributed import validate_edges_sharded
+from ..engine import get_engine
+
+
+def nearest_predecessors(nodes, k, radius=np.inf, block=4096):
+    """For node i: its k nearest nodes j < i with distance <= radius, sorted by distance.
+
+    nodes: CUDA float32 tensor [N, nq].  Returns (idx [N, k] int64 with -1 padding, dist [N, k]).
+    Mirrors the reference's incremental semantics: a node only sees the nodes added before it.
+    """
+    import torch
+
+    n = nodes.shape[0]
+    idx = torch.full((n, k), -1, dtype=torch.int64, device=nodes.device)
+    dist = torch.full((n, k), float("inf"), dtype=torch.float32, device=nodes.device)
+    cols = torch.arange(n, device=nodes.device)
+    for r0 in range(0, n, block):
+        r1 = min(r0 + block, n)
+        d = torch.cdist(nodes[r0:r1], nodes[:r1])  # only predecessors can matter
+        rows = torch.arange(r0, r1, device=nodes.device)
+        d = torch.where((cols[:r1][None, :] < rows[:, None]) & (d <= radius), d, torch.full_like(d, float("inf")))
+        kk = min(k, r1)
+        dv, di = torch.topk(d, kk, dim=1, largest=False, sorted=True)
+        di = torch.where(torch.isinf(dv), torch.full_like(di, -1), di)
+        idx[r0:r1, :kk] = di
+        dist[r0:r1, :kk] = dv
+    return idx, dist
+
+
+def construct_roadmap_batched(model, collision_model, n_nodes, k=10, radius=np.inf, max_step_size=0.05,
+                              distance_padding=0.0, seed=0, nodes=None, group=None):
+    """Builds a PRM roadmap with batched sampling, k-NN and edge validation.
+
+    Returns a dict with
+      nodes       float32 [N, nq]   collision-free configurations (device tensor)
+      candidates  int64   [M, 2]    (neighbour j, node i) with j < i, in the reference's visiting order
+      valid       bool    [M]       True where the segment nodes[j] -> nodes[i] is collision free
+      edges       int64   [E, 2]    candidates[valid]
+      lengths     float32 [M]       joint-space edge lengths
+    Under torch.distributed every rank validates its block of the candidates and receives the
+    full mask (one all-gather); without it the single process does everything.
+    """
+    import torch
+
+    eng = get_engine(model, collision_model)
+    if nodes is None:
+        nodes = eng.sample_free_states(n_nodes, seed=seed, padding=distance_padding)
+        if nodes.shape[0] < n_nodes:
+            raise RuntimeError(f"sampler found only {nodes.shape[0]} of {n_nodes} free states")
+    else:
+        nodes = torch.as_tensor(np.asarray(nodes, dtype=np.float32) if not isinstance(nodes, torch.Tensor) else nodes,
+                                device=eng.torch_device).to(torch.float32).contiguous()
+    idx, dist = nearest_predecessors(nodes, k, radius)
+    node_ids = torch.arange(nodes.shape[0], device=nodes.device)[:, None].expand_as(idx)
+    keep = idx >= 0
+    cand = torch.stack([idx[keep], node_ids[keep]], dim=1)  # row-major: node by node, nearest first
+    lengths = dist[keep]
+    q1 = nodes[cand[:, 0]].contiguous()
+    q2 = nodes[cand[:, 1]].contiguous()
+    if len(collision_model.collisionPairs) == 0:
+        valid = torch.ones(cand.shape[0], dtype=torch.bool, device=nodes.device)
+    else:
+        valid = validate_edges_sharded(eng.check_edges, q1, q2, max_step_size, distance_padding, group=group)
+    return {"nodes": nodes, "candidates": cand, "valid": valid, "edges": cand[valid], "lengths": lengths}
