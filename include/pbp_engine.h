@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PBP_ABI_VERSION 1
+#define PBP_ABI_VERSION 2
 
 typedef enum {
     PBP_OK = 0,
@@ -77,6 +77,13 @@ typedef struct {
     const int32_t *pairs;          /* [npairs][2] active collision pairs (first, second) */
     const int32_t *frame_parent;   /* [nframes] parent joint of each frame (may be NULL if nframes == 0) */
     const float *frame_placement;  /* [nframes][12] */
+    /* float64 copies of the kinematic tables for the FP64 differential-IK kernel (each may be
+     * NULL: the float32 table above is widened instead) */
+    const double *joint_placement_f64; /* [njoints][12] */
+    const double *joint_axis_f64;      /* [njoints][3] */
+    const double *frame_placement_f64; /* [nframes][12] */
+    const double *q_lower_f64;         /* [nq] */
+    const double *q_upper_f64;         /* [nq] */
 } pbp_model_desc;
 
 typedef struct pbp_engine pbp_engine;
@@ -168,6 +175,32 @@ int pbp_check_paths(pbp_engine *e, const float *q_dev, const int64_t *path_offse
  * Batched sibling of get_random_collision_free_state (core/utils.py:195-229). */
 int pbp_sample_free_states(pbp_engine *e, int64_t n_wanted, uint64_t seed, float joint_padding, float padding,
                            int max_rounds, float *q_out_dev, int64_t *n_found_host, int64_t *n_drawn_host, void *stream);
+
+/* One try of damped-least-squares differential IK for N targets (thread per target, FP64 end to
+ * end -- unlike the collision entry points the states here are DOUBLES, because an iterate that
+ * crosses a singularity amplifies input rounding by up to 1/damping^2).
+ * Restates the inner loop of DifferentialIk.solve (src/pyroboplan/ik/differential_ik.py:208-298):
+ * up to max_iters iterations of  FK -> error = -log6(target^-1 * frame pose) -> converged? ->
+ * LOCAL frame Jacobian -> (J W J^T + damping^2 I) y = error -> q += alpha W J^T y.
+ *   frame_id      index into the model's frames (pbp_model_desc.frame_*)
+ *   targets_dev   [N][12] desired frame placements (float64)
+ *   q_dev         [N][nq] float64, in: initial states, out: final states (every coordinate wrapped
+ *                 to [-pi, pi) when converged, differential_ik.py:221)
+ *   active_mask   bit k set = joint coordinate k may move (ignore_joint_indices cleared)
+ *   w_diag_host   [nq] diagonal of W = inverse joint weights (NULL = identity)
+ *   e0_dev        [N] in/out initial error norm of each solve (0 = not captured yet; it is kept
+ *                 across retries, as the reference does, :200,264-265)
+ *   status_dev    [N] bit 0: pose error within tolerance, bit 1: within joint limits (after wrapping)
+ *   iters_dev     [N] iterations used (nullable)
+ * The collision gate and the random restarts stay with the caller (pbp_check_states,
+ * pbp_sample_free_states), exactly where the reference has them (:223-230, :306-311). */
+typedef struct {
+    int32_t max_iters;
+    double max_translation_error, max_rotation_error, damping, min_step_size, max_step_size;
+} pbp_ik_options;
+int pbp_ik_iterate(pbp_engine *e, int32_t frame_id, const double *targets_dev, double *q_dev, int64_t n, const pbp_ik_options *opt,
+                   uint64_t active_mask, const double *w_diag_host, double *e0_dev, int32_t *status_dev, int32_t *iters_dev,
+                   void *stream);
 
 #ifdef __cplusplus
 }

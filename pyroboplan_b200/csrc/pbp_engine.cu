@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "pbp_kernels.cuh"
+#include "pbp_ik.cuh"
 #include "pbp_supmap.h"
 
 static_assert(pbp::SUPMAP_KD == pbp::SUPMAP_K, "support map resolution mismatch");
@@ -80,6 +81,12 @@ struct pbp_engine {
     unsigned long long *h_pinned = nullptr;  // small pinned mailbox for device -> host counters
     cudaStream_t s_copy = nullptr, s_comp = nullptr;   // *_host entry points: copy / compute pipeline
     std::vector<cudaEvent_t> io_events;
+    // float64 host copies of the kinematic tables for the IK kernel + the last uploaded chain
+    std::vector<int32_t> h_joint_parent, h_joint_type, h_joint_idx_q, h_frame_parent;
+    std::vector<double> h_joint_placement, h_joint_axis, h_frame_placement, h_q_lower, h_q_upper;
+    DeviceBuffer d_ik_tables;
+    pbp::IkTables ik_cached{}, ik_build{};
+    bool ik_cached_valid = false;
     size_t smem_bp = 0, smem_is = 0, smem_np = 0, smem_fk = 0;
     int np_blocks = 0, is_blocks = 0;
     pbp_stats stats{};
@@ -239,7 +246,7 @@ void pbp_engine_destroy(pbp_engine *e) {
                             &e->d_pathops, &e->d_order, &e->d_verts, &e->d_supcells, &e->d_suplists, &e->d_qlim, &e->d_frames, &e->d_bin_state,
                             &e->d_bin_group, &e->d_bin_sample, &e->d_bin_T, &e->d_ctrl, &e->d_counts, &e->d_desc_group,
                             &e->d_desc_frac, &e->d_desc_sample, &e->d_scratch_i32, &e->d_scratch_u8, &e->d_cub, &e->d_sel,
-                            &e->d_io_q, &e->d_io_q2, &e->d_io_hit, &e->d_io_f32, &e->d_io_i32};
+                            &e->d_io_q, &e->d_io_q2, &e->d_io_hit, &e->d_io_f32, &e->d_io_i32, &e->d_ik_tables};
     for (DeviceBuffer *b : bufs) b->release();
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     for (cudaEvent_t ev : e->io_events) cudaEventDestroy(ev);
@@ -268,6 +275,23 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     e->num_sms = prop.multiProcessorCount;
     e->nq = d->nq; e->njoints = d->njoints; e->ngeoms = d->ngeoms; e->npairs = d->npairs; e->nframes = d->nframes;
+    {
+        auto widen = [](std::vector<double> &dst, const double *f64, const float *f32, size_t cnt) {
+            dst.resize(cnt);
+            for (size_t k = 0; k < cnt; k++) dst[k] = f64 ? f64[k] : (double)f32[k];
+        };
+        e->h_joint_parent.assign(d->joint_parent, d->joint_parent + d->njoints);
+        e->h_joint_type.assign(d->joint_type, d->joint_type + d->njoints);
+        e->h_joint_idx_q.assign(d->joint_idx_q, d->joint_idx_q + d->njoints);
+        widen(e->h_joint_placement, d->joint_placement_f64, d->joint_placement, 12 * (size_t)d->njoints);
+        widen(e->h_joint_axis, d->joint_axis_f64, d->joint_axis, 3 * (size_t)d->njoints);
+        widen(e->h_q_lower, d->q_lower_f64, d->q_lower, (size_t)d->nq);
+        widen(e->h_q_upper, d->q_upper_f64, d->q_upper, (size_t)d->nq);
+        if (d->nframes > 0) {
+            e->h_frame_parent.assign(d->frame_parent, d->frame_parent + d->nframes);
+            widen(e->h_frame_placement, d->frame_placement_f64, d->frame_placement, 12 * (size_t)d->nframes);
+        }
+    }
 
     auto bail = [&](int code) { pbp_engine_destroy(e); return code; };
 
@@ -1026,5 +1050,90 @@ extern "C" int pbp_measure_fp32_peak(int device, double *tflops_out) {
     cudaFree(buf);
     CUDA_TRY(cudaGetLastError());
     *tflops_out = best;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// differential IK (one try for N targets)
+// ------------------------------------------------------------------------------------------
+extern "C" int pbp_ik_iterate(pbp_engine *e, int32_t frame_id, const double *targets_dev, double *q_dev, int64_t n,
+                              const pbp_ik_options *opt, uint64_t active_mask, const double *w_diag_host, double *e0_dev,
+                              int32_t *status_dev, int32_t *iters_dev, void *stream) {
+    int rc = check_args(e, q_dev, n);
+    if (rc) return rc;
+    if (n > 0 && (!targets_dev || !e0_dev || !status_dev || !opt)) return fail(PBP_ERR_ARG, "NULL buffer");
+    if (frame_id < 0 || frame_id >= e->nframes) return fail(PBP_ERR_ARG, "frame %d out of range [0, %d)", frame_id, e->nframes);
+    if (opt->max_iters < 0) return fail(PBP_ERR_ARG, "max_iters must be >= 0");
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // chain root -> frame, as float64 tables
+    std::vector<int> path;
+    for (int j = e->h_frame_parent[frame_id]; j > 0; j = e->h_joint_parent[j])
+        if (e->h_joint_type[j] != PBP_JOINT_FIXED) path.push_back(j);
+    std::reverse(path.begin(), path.end());
+    if ((int)path.size() > IK_MAX_PATH) return fail(PBP_ERR_CAPACITY, "frame chain longer than %d joints", IK_MAX_PATH);
+    IkTables &tab = e->ik_build;
+    memset(&tab, 0, sizeof(tab));
+    // fixed joints between two moving ones fold into the next moving joint's placement
+    {
+        std::vector<int> full;
+        for (int j = e->h_frame_parent[frame_id]; j > 0; j = e->h_joint_parent[j]) full.push_back(j);
+        std::reverse(full.begin(), full.end());
+        double acc[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+        int k = 0;
+        auto mul = [](const double *A, const double *B, double *C) {
+            for (int i = 0; i < 3; i++) {
+                for (int c = 0; c < 3; c++) C[3 * i + c] = A[3 * i] * B[c] + A[3 * i + 1] * B[3 + c] + A[3 * i + 2] * B[6 + c];
+                C[9 + i] = A[3 * i] * B[9] + A[3 * i + 1] * B[10] + A[3 * i + 2] * B[11] + A[9 + i];
+            }
+        };
+        for (int j : full) {
+            double tmp[12];
+            mul(acc, e->h_joint_placement.data() + 12 * (size_t)j, tmp);
+            if (e->h_joint_type[j] == PBP_JOINT_FIXED) {
+                memcpy(acc, tmp, sizeof(acc));
+                continue;
+            }
+            IkJoint &J = tab.joint[k++];
+            memcpy(J.P, tmp, sizeof(tmp));
+            for (int a = 0; a < 3; a++) J.axis[a] = e->h_joint_axis[3 * (size_t)j + a];
+            J.type = e->h_joint_type[j];
+            J.idx_q = e->h_joint_idx_q[j];
+            const bool active = J.idx_q < 64 && ((active_mask >> J.idx_q) & 1ull);
+            J.w = active ? (w_diag_host ? w_diag_host[J.idx_q] : 1.0) : 0.0;
+            const double ident[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+            memcpy(acc, ident, sizeof(acc));
+        }
+        double fr[12];
+        mul(acc, e->h_frame_placement.data() + 12 * (size_t)frame_id, fr);
+        memcpy(tab.frame, fr, sizeof(fr));
+        tab.npath = k;
+    }
+    tab.nq = e->nq;
+    for (int k = 0; k < e->nq; k++) { tab.q_lower[k] = e->h_q_lower[k]; tab.q_upper[k] = e->h_q_upper[k]; }
+    if ((rc = e->d_ik_tables.ensure(sizeof(IkTables)))) return rc;
+    if (!e->ik_cached_valid || memcmp(&tab, &e->ik_cached, sizeof(IkTables)) != 0) {
+        // rare (new frame / weights): a synchronous upload, ordered after earlier work on `st`
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemcpy(e->d_ik_tables.p, &tab, sizeof(IkTables), cudaMemcpyHostToDevice));
+        memcpy(&e->ik_cached, &tab, sizeof(IkTables));
+        e->ik_cached_valid = true;
+    }
+    IkOptions o;
+    o.max_iters = opt->max_iters;
+    o.tol_translation = opt->max_translation_error;
+    o.tol_rotation = opt->max_rotation_error;
+    o.damping = opt->damping;
+    o.min_step = opt->min_step_size;
+    o.max_step = opt->max_step_size;
+    const IkTables *dt = e->d_ik_tables.as<IkTables>();
+    if (tab.npath <= 8)
+        k_ik_iterate<8><<<grid_for(n, 128), 128, 0, st>>>(dt, targets_dev, q_dev, n, o, e0_dev, status_dev, iters_dev);
+    else if (tab.npath <= 16)
+        k_ik_iterate<16><<<grid_for(n, 128), 128, 0, st>>>(dt, targets_dev, q_dev, n, o, e0_dev, status_dev, iters_dev);
+    else
+        k_ik_iterate<IK_MAX_PATH><<<grid_for(n, 128), 128, 0, st>>>(dt, targets_dev, q_dev, n, o, e0_dev, status_dev, iters_dev);
+    LAUNCH_CHECK("k_ik_iterate");
     return 0;
 }

@@ -18,7 +18,7 @@ from .model.shapes import Box, Capsule, Convex, Cylinder, Sphere
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpbp_engine.so")
 
-PBP_ABI_VERSION = 1
+PBP_ABI_VERSION = 2
 
 # symbols declared in include/pbp_engine.h (tests check the library exports every one)
 EXPORTED_SYMBOLS = [
@@ -40,6 +40,7 @@ EXPORTED_SYMBOLS = [
     "pbp_set_profiling",
     "pbp_get_profile",
     "pbp_measure_fp32_peak",
+    "pbp_ik_iterate",
 ]
 
 
@@ -70,6 +71,11 @@ class _ModelDesc(ctypes.Structure):
         ("pairs", ctypes.c_void_p),
         ("frame_parent", ctypes.c_void_p),
         ("frame_placement", ctypes.c_void_p),
+        ("joint_placement_f64", ctypes.c_void_p),
+        ("joint_axis_f64", ctypes.c_void_p),
+        ("frame_placement_f64", ctypes.c_void_p),
+        ("q_lower_f64", ctypes.c_void_p),
+        ("q_upper_f64", ctypes.c_void_p),
     ]
 
 
@@ -79,6 +85,17 @@ class _Stats(ctypes.Structure):
         ("states", ctypes.c_int64),
         ("narrowphase_items", ctypes.c_int64),
         ("chunks", ctypes.c_int64),
+    ]
+
+
+class _IkOptions(ctypes.Structure):
+    _fields_ = [
+        ("max_iters", ctypes.c_int32),
+        ("max_translation_error", ctypes.c_double),
+        ("max_rotation_error", ctypes.c_double),
+        ("damping", ctypes.c_double),
+        ("min_step_size", ctypes.c_double),
+        ("max_step_size", ctypes.c_double),
     ]
 
 
@@ -126,6 +143,7 @@ def load_library():
     lib.pbp_set_profiling.argtypes = [vp, i32]
     lib.pbp_get_profile.argtypes = [vp, ctypes.POINTER(_Profile), i32]
     lib.pbp_measure_fp32_peak.argtypes = [i32, ctypes.POINTER(f64)]
+    lib.pbp_ik_iterate.argtypes = [vp, i32, vp, vp, i64, ctypes.POINTER(_IkOptions), ctypes.c_uint64, vp, vp, vp, vp, vp]
     if lib.pbp_abi_version() != PBP_ABI_VERSION:
         raise RuntimeError("libpbp_engine.so ABI version mismatch; rebuild it")
     _lib = lib
@@ -221,6 +239,12 @@ def flatten_model(model, collision_model):
     a["pairs"] = pairs if len(pairs) else np.zeros((1, 2), dtype=np.int32)
     a["frame_parent"] = np.array([f.parentJoint for f in model.frames], dtype=np.int32)
     a["frame_placement"] = np.array([_se3_row(f.placement) for f in model.frames], dtype=np.float32)
+    # float64 kinematic tables for the FP64 differential-IK kernel
+    a["joint_placement_f64"] = np.array([_se3_row(p) for p in model.jointPlacements], dtype=np.float64)
+    a["joint_axis_f64"] = np.array([j.axis for j in model.joints], dtype=np.float64)
+    a["frame_placement_f64"] = np.array([_se3_row(f.placement) for f in model.frames], dtype=np.float64)
+    a["q_lower_f64"] = np.asarray(model.lowerPositionLimit, dtype=np.float64)
+    a["q_upper_f64"] = np.asarray(model.upperPositionLimit, dtype=np.float64)
     sizes = dict(nq=model.nq, njoints=model.njoints, ngeoms=ng, npairs=len(pairs), nverts=nv, nframes=len(model.frames))
     return {k: np.ascontiguousarray(v) for k, v in a.items()}, sizes
 
@@ -405,6 +429,34 @@ class CollisionEngine:
         if host:
             return counts.cpu().numpy(), offsets.cpu().numpy(), states.cpu().numpy()
         return counts, offsets, states
+
+    # ------------------------------------------------------------------ differential IK
+    def ik_iterate(self, frame_id, targets, Q, e0=None, max_iters=200, max_translation_error=1e-3, max_rotation_error=1e-3,
+                   damping=1e-3, min_step_size=0.1, max_step_size=0.5, active_mask=None, joint_weights=None):
+        """One try of batched DLS differential IK (device tensors; see pbp_ik_iterate in the header).
+
+        targets [N, 12] (R row-major, then t), Q [N, nq] initial states; both are used as float64.  Returns
+        (Q_out [N, nq], status [N] int32 (bit 0 converged, bit 1 within limits), iters [N], e0 [N]).
+        """
+        torch = _torch()
+        f64 = torch.float64
+        Qd = torch.as_tensor(Q, device=self.torch_device).to(f64).reshape(-1, self.nq).contiguous().clone()
+        n = Qd.shape[0]
+        Td = torch.as_tensor(targets, device=self.torch_device).to(f64).contiguous().reshape(n, 12)
+        e0 = torch.zeros(n, dtype=f64, device=self.torch_device) if e0 is None else e0.to(f64).contiguous().clone()
+        status = torch.zeros(n, dtype=torch.int32, device=self.torch_device)
+        iters = torch.zeros(n, dtype=torch.int32, device=self.torch_device)
+        opt = _IkOptions(int(max_iters), float(max_translation_error), float(max_rotation_error), float(damping),
+                         float(min_step_size), float(max_step_size))
+        mask = (1 << self.nq) - 1 if active_mask is None else int(active_mask)
+        w = None
+        if joint_weights is not None:
+            w = np.ascontiguousarray(joint_weights, dtype=np.float64).reshape(self.nq)
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        _check(self.lib.pbp_ik_iterate(self._h, int(frame_id), ptr(Td), ptr(Qd), n, ctypes.byref(opt), ctypes.c_uint64(mask),
+                                       ctypes.c_void_p(w.ctypes.data) if w is not None else None, ptr(e0), ptr(status), ptr(iters),
+                                       self._stream()))
+        return Qd, status, iters, e0
 
     # ------------------------------------------------------------------ sampling
     def sample_free_states(self, n, seed=0, joint_padding=0.0, padding=0.0, max_rounds=64, as_numpy=False):
