@@ -17,7 +17,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -58,59 +57,82 @@ def make_batch(model, n, seed):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clock, power and throttle reasons through NVML (a poll every ~2 ms from a thread;
+    `nvidia-smi -lms` cannot start, let alone sample, inside a timed region of a few milliseconds).
+    Samples carry a timestamp; `stop(t0, t1)` reports those taken inside [t0, t1]."""
 
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {  # nvmlClocksEventReasons bits (nvml.h)
+        0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+    }
 
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
-        self.rows = []
-        self.proc = None
+        self.samples = []   # (t, sm_mhz, power_w, reasons bitmask)
+        self.running = False
+        self.handle = None
+        self.sm_max = None
+        try:
+            import pynvml
+
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = gpu_index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[gpu_index])
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            elif vis and vis.split(",")[gpu_index].strip().startswith("GPU-"):
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(vis.split(",")[gpu_index].strip())
+            else:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:  # no NVML: report that, never fail the bench
+            self.error = repr(exc)
+            self.handle = None
+
+    def _poll(self):
+        nv = self.nv
+        while self.running:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                power = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                self.samples.append((time.perf_counter(), float(sm), power, int(reasons)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu_index)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except (OSError, ValueError):
-            self.proc = None
+        if self.handle is None:
+            return
+        self.running = True
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 9:
-                continue
-            try:
-                sm.append(float(r[1]))
-                smax.append(float(r[2]))
-                power.append(float(r[3]))
-            except ValueError:
-                continue
-            for name, val in zip(names, r[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+    def stop(self, t0, t1):
+        if self.handle is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"NVML unavailable: {getattr(self, 'error', '')}"]}
+        self.running = False
+        self.thread.join(timeout=1.0)
+        inside = [x for x in self.samples if t0 <= x[0] <= t1]
+        window = "timed region"
+        if not inside:  # a timed region shorter than one poll: fall back to the whole loaded window
+            inside, window = self.samples, "warm-up + timed region (timed region shorter than one NVML poll)"
+        bits = 0
+        for x in inside:
+            bits |= x[3]
         return {
-            "sm_mhz": statistics.median(sm) if sm else None,
-            "sm_max_mhz": max(smax) if smax else None,
-            "power_w_max": max(power) if power else None,
-            "samples": len(sm),
-            "reasons": sorted(reasons),
+            "sm_mhz": statistics.median(x[1] for x in inside) if inside else None,
+            "sm_min_mhz": min(x[1] for x in inside) if inside else None,
+            "sm_max_mhz": self.sm_max,
+            "power_w_max": max(x[2] for x in inside) if inside else None,
+            "samples": len(inside),
+            "window": window,
+            "reasons": sorted(name for bit, name in self.REASONS.items() if bits & bit),
         }
 
 
@@ -156,8 +178,8 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--states", type=int, default=N_STATES, help="states per GPU per step")
     args = ap.parse_args()
@@ -199,6 +221,8 @@ def main():
     # ---------------- device-resident throughput
     # W untimed warm-up steps (at least one per input batch, so no batch is touched for the
     # first time inside the timed region)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for w in range(max(args.warmup, N_BATCHES + 1)):
         hits[w % N_BATCHES] = eng.check_states(dev_batches[w % N_BATCHES])
     torch.cuda.synchronize()
@@ -206,18 +230,18 @@ def main():
     eng.stats(reset=True)
     eng.set_profiling(True)
     eng.profile(reset=True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     torch.cuda.synchronize()
+    t_region0 = time.perf_counter()
     ev0.record()
     for k in range(args.steps):
         hits[k % N_BATCHES] = eng.check_states(dev_batches[k % N_BATCHES])
     ev1.record()
     torch.cuda.synchronize()
+    t_region1 = time.perf_counter()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_region0, t_region1)
     ms = ev0.elapsed_time(ev1)
     prof = eng.profile(reset=True)
     eng.set_profiling(False)

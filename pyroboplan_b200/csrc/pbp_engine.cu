@@ -65,6 +65,29 @@ struct DeviceBuffer {
 
 }  // namespace
 
+struct PinnedBuffer {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMallocHost(&p, need);
+        if (e != cudaSuccess) return fail(PBP_ERR_ALLOC, "cudaMallocHost(%zu) failed: %s", need, cudaGetErrorString(e));
+        bytes = need;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+};
+
+// true when `ptr` is page-locked host memory known to CUDA (async copies really are async)
+static bool is_pinned_host(const void *ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 struct pbp_engine {
     int device = 0;
     int num_sms = 0;
@@ -81,6 +104,14 @@ struct pbp_engine {
     unsigned long long *h_pinned = nullptr;  // small pinned mailbox for device -> host counters
     cudaStream_t s_copy = nullptr, s_comp = nullptr;   // *_host entry points: copy / compute pipeline
     std::vector<cudaEvent_t> io_events;
+    PinnedBuffer h_io_hit, h_io_f32, h_io_i32;   // staging for results bound for pageable caller memory
+    int64_t host_slice = 1 << 18;                // states per slice of the *_host copy/compute pipeline
+    // Two workspaces (halves of every bin + one control block each) let the *_host pipeline run
+    // consecutive slices on two streams: the latency-bound tail of one slice's narrowphase
+    // overlaps the next slice's broadphase.  ws selects the workspace run_round uses.
+    int ws = 0;
+    bool ws_split = false;
+    cudaStream_t s_comp2 = nullptr;
     // float64 host copies of the kinematic tables for the IK kernel + the last uploaded chain
     std::vector<int32_t> h_joint_parent, h_joint_type, h_joint_idx_q, h_frame_parent;
     std::vector<double> h_joint_placement, h_joint_axis, h_frame_placement, h_q_lower, h_q_upper;
@@ -103,14 +134,20 @@ namespace {
 // [npairs + 1] narrowphase chunk cursor, then four 64-bit counters at an 8-byte aligned offset
 // (level total, emit cursor, select count, profiled item total).
 inline size_t ctrl_words(const pbp_engine *e) { return (size_t)e->npairs + 2; }
-inline uint32_t *ctrl_counts(pbp_engine *e) { return e->d_ctrl.as<uint32_t>(); }
-inline uint32_t *ctrl_tile_setup(pbp_engine *e) { return e->d_ctrl.as<uint32_t>() + e->npairs; }
-inline uint32_t *ctrl_chunk_np(pbp_engine *e) { return e->d_ctrl.as<uint32_t>() + e->npairs + 1; }
+// There are two such blocks (workspaces 0 / 1, see pbp_engine::ws); the 64-bit counters live in block 0.
+inline size_t ctrl_bytes(const pbp_engine *e) { return ((ctrl_words(e) * 4 + 7) & ~(size_t)7) + 32; }
+inline uint32_t *ctrl_base(pbp_engine *e) {
+    return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(e->d_ctrl.p) + (size_t)e->ws * ctrl_bytes(e));
+}
+inline uint32_t *ctrl_counts(pbp_engine *e) { return ctrl_base(e); }
+inline uint32_t *ctrl_tile_setup(pbp_engine *e) { return ctrl_base(e) + e->npairs; }
+inline uint32_t *ctrl_chunk_np(pbp_engine *e) { return ctrl_base(e) + e->npairs + 1; }
 inline unsigned long long *ctrl_u64(pbp_engine *e, int i) {
     const size_t off = (ctrl_words(e) * 4 + 7) & ~(size_t)7;
     return reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(e->d_ctrl.p) + off) + i;
 }
-inline size_t ctrl_bytes(const pbp_engine *e) { return ((ctrl_words(e) * 4 + 7) & ~(size_t)7) + 32; }
+// states one broadphase -> narrowphase round may take (half the bins each when two workspaces alternate)
+inline int64_t round_cap(const pbp_engine *e) { return e->ws_split ? e->chunk / 2 : e->chunk; }
 
 inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
@@ -148,13 +185,15 @@ int run_round(pbp_engine *e, int mode, const StateSource &src, int64_t n, float 
     if (n <= 0) return 0;
     if (e->npairs == 0) return 0;  // nothing can collide; outputs were initialised by the caller
     Bins bins;
-    bins.state = e->d_bin_state.as<int32_t>();
-    bins.group = e->d_bin_group.as<int32_t>();
-    bins.sample = e->d_bin_sample.as<int32_t>();
-    bins.T = e->d_bin_T.as<float>();
+    if (n > round_cap(e)) return fail(PBP_ERR_ARG, "internal: round of %lld states exceeds the bin capacity", (long long)n);
+    const int64_t ws_off = e->ws_split ? (int64_t)e->ws * (e->chunk / 2) : 0;   // this workspace's half of every bin
+    bins.state = e->d_bin_state.as<int32_t>() + ws_off;
+    bins.group = e->d_bin_group.as<int32_t>() + ws_off;
+    bins.sample = e->d_bin_sample.as<int32_t>() + ws_off;
+    bins.T = e->d_bin_T.as<float>() + ws_off;
     bins.count = ctrl_counts(e);
     bins.cap = e->chunk;
-    CUDA_TRY(cudaMemsetAsync(e->d_ctrl.p, 0, ctrl_words(e) * 4, st));
+    CUDA_TRY(cudaMemsetAsync(ctrl_base(e), 0, ctrl_words(e) * 4, st));
     int rc;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (e->profiling) {
@@ -249,9 +288,11 @@ void pbp_engine_destroy(pbp_engine *e) {
                             &e->d_io_q, &e->d_io_q2, &e->d_io_hit, &e->d_io_f32, &e->d_io_i32, &e->d_ik_tables};
     for (DeviceBuffer *b : bufs) b->release();
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
+    e->h_io_hit.release(); e->h_io_f32.release(); e->h_io_i32.release();
     for (cudaEvent_t ev : e->io_events) cudaEventDestroy(ev);
     if (e->s_copy) cudaStreamDestroy(e->s_copy);
     if (e->s_comp) cudaStreamDestroy(e->s_comp);
+    if (e->s_comp2) cudaStreamDestroy(e->s_comp2);
     delete e;
 }
 
@@ -615,12 +656,17 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     e->chunk = chunk;
     const size_t slots = (size_t)np1 * (size_t)chunk;
     if ((rc = e->d_bin_state.ensure(slots * 4)) || (rc = e->d_bin_group.ensure(slots * 4)) || (rc = e->d_bin_sample.ensure(slots * 4)) ||
-        (rc = e->d_bin_T.ensure(slots * 48)) || (rc = e->d_ctrl.ensure(ctrl_bytes(e))))
+        (rc = e->d_bin_T.ensure(slots * 48)) || (rc = e->d_ctrl.ensure(2 * ctrl_bytes(e))))
         return bail(rc);
-    CUDA_TRY(cudaMemset(e->d_ctrl.p, 0, ctrl_bytes(e)));
+    CUDA_TRY(cudaMemset(e->d_ctrl.p, 0, 2 * ctrl_bytes(e)));
     CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&e->h_pinned), 64));
+    if (const char *hs = getenv("PBP_HOST_SLICE")) {
+        const long long v = atoll(hs);
+        if (v >= 1024) e->host_slice = v;
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_comp2, cudaStreamNonBlocking));
     *out = e;
     return 0;
 }
@@ -658,8 +704,8 @@ int pbp_check_states(pbp_engine *e, const float *q_dev, int64_t n, float padding
     }
     // min distance wins over first_pair for the mode; both requested -> two passes
     const int mode = min_dist_dev ? MODE_DIST : (first_pair_dev ? MODE_BOOL_ALL : MODE_BOOL);
-    for (int64_t off = 0; off < n; off += e->chunk) {
-        const int64_t cnt = std::min(e->chunk, n - off);
+    for (int64_t off = 0; off < n; off += round_cap(e)) {
+        const int64_t cnt = std::min(round_cap(e), n - off);
         StateSource src{};
         src.q = q_dev + off * e->nq;
         src.mode = 0;
@@ -835,7 +881,17 @@ int pbp_check_states_host(pbp_engine *e, const float *q_host, int64_t n, float p
     if ((rc = e->d_io_q.ensure((size_t)n * e->nq * 4)) || (rc = e->d_io_hit.ensure((size_t)n))) return rc;
     if (min_dist_host && (rc = e->d_io_f32.ensure((size_t)n * 4))) return rc;
     if (first_pair_host && (rc = e->d_io_i32.ensure((size_t)n * 4))) return rc;
-    const int64_t slice = 1 << 18;
+    // Results bound for pageable memory are staged in the engine's pinned buffers: a device ->
+    // pageable cudaMemcpyAsync blocks the host thread and would stall the launch pipeline.
+    uint8_t *hh = hit_host;
+    float *hd = min_dist_host;
+    int32_t *hp = first_pair_host;
+    if (!is_pinned_host(hit_host)) { if ((rc = e->h_io_hit.ensure((size_t)n))) return rc; hh = (uint8_t *)e->h_io_hit.p; }
+    if (min_dist_host && !is_pinned_host(min_dist_host)) { if ((rc = e->h_io_f32.ensure((size_t)n * 4))) return rc; hd = (float *)e->h_io_f32.p; }
+    if (first_pair_host && !is_pinned_host(first_pair_host)) { if ((rc = e->h_io_i32.ensure((size_t)n * 4))) return rc; hp = (int32_t *)e->h_io_i32.p; }
+    // Slices small enough that the compute of the last one (all that is left once the final H2D
+    // copy lands) is short, large enough to fill the 148 SMs for a few waves.
+    const int64_t slice = e->host_slice;
     const int64_t n_slices = (n + slice - 1) / slice;
     while ((int64_t)e->io_events.size() < n_slices) {
         cudaEvent_t ev;
@@ -848,18 +904,31 @@ int pbp_check_states_host(pbp_engine *e, const float *q_host, int64_t n, float p
         CUDA_TRY(cudaMemcpyAsync(dq + off * e->nq, q_host + off * e->nq, (size_t)cnt * e->nq * 4, cudaMemcpyHostToDevice, e->s_copy));
         CUDA_TRY(cudaEventRecord(e->io_events[k], e->s_copy));
     }
+    // consecutive slices alternate between the two workspaces / compute streams (not when both
+    // the distance and the pair index are wanted: that second pass shares one scratch buffer)
+    struct SplitGuard {
+        pbp_engine *e;
+        ~SplitGuard() { e->ws_split = false; e->ws = 0; }
+    } guard{e};
+    e->ws_split = n_slices > 1 && slice <= e->chunk / 2 && !(min_dist_host && first_pair_host);
     for (int64_t k = 0; k < n_slices; k++) {
         const int64_t off = k * slice, cnt = std::min(slice, n - off);
-        CUDA_TRY(cudaStreamWaitEvent(e->s_comp, e->io_events[k], 0));
+        e->ws = e->ws_split ? (int)(k & 1) : 0;
+        cudaStream_t sc = e->ws ? e->s_comp2 : e->s_comp;
+        CUDA_TRY(cudaStreamWaitEvent(sc, e->io_events[k], 0));
         uint8_t *dh = e->d_io_hit.as<uint8_t>() + off;
         float *dd = min_dist_host ? e->d_io_f32.as<float>() + off : nullptr;
         int32_t *dp = first_pair_host ? e->d_io_i32.as<int32_t>() + off : nullptr;
-        if ((rc = pbp_check_states(e, dq + off * e->nq, cnt, padding, dh, dd, dp, e->s_comp))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(hit_host + off, dh, (size_t)cnt, cudaMemcpyDeviceToHost, e->s_comp));
-        if (dd) CUDA_TRY(cudaMemcpyAsync(min_dist_host + off, dd, (size_t)cnt * 4, cudaMemcpyDeviceToHost, e->s_comp));
-        if (dp) CUDA_TRY(cudaMemcpyAsync(first_pair_host + off, dp, (size_t)cnt * 4, cudaMemcpyDeviceToHost, e->s_comp));
+        if ((rc = pbp_check_states(e, dq + off * e->nq, cnt, padding, dh, dd, dp, sc))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(hh + off, dh, (size_t)cnt, cudaMemcpyDeviceToHost, sc));
+        if (dd) CUDA_TRY(cudaMemcpyAsync(hd + off, dd, (size_t)cnt * 4, cudaMemcpyDeviceToHost, sc));
+        if (dp) CUDA_TRY(cudaMemcpyAsync(hp + off, dp, (size_t)cnt * 4, cudaMemcpyDeviceToHost, sc));
     }
     CUDA_TRY(cudaStreamSynchronize(e->s_comp));
+    if (e->ws_split) CUDA_TRY(cudaStreamSynchronize(e->s_comp2));
+    if (hh != hit_host) memcpy(hit_host, hh, (size_t)n);
+    if (min_dist_host && hd != min_dist_host) memcpy(min_dist_host, hd, (size_t)n * 4);
+    if (first_pair_host && hp != first_pair_host) memcpy(first_pair_host, hp, (size_t)n * 4);
     return 0;
 }
 

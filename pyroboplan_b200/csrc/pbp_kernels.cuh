@@ -560,11 +560,20 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
     for (;;) {
         const unsigned need = __ballot_sync(0xffffffffu, phase == 0);
         if (need && cursor >= chunk_end && more) {
-            uint32_t c = 0;
-            if (lane == 0) c = atomicAdd(chunk_cursor, (uint32_t)NP_CHUNK);
+            // guided self-scheduling: NP_CHUNK items while plenty are left, down to one warp-load
+            // near the end, so the last chunk of a launch (and every chunk of a small launch) is
+            // short -- a 128-item chunk is ~100 us of serial GJK trips for one warp
+            uint32_t c = 0, sz = 0;
+            if (lane == 0) {
+                const uint32_t seen = *reinterpret_cast<volatile uint32_t *>(chunk_cursor);
+                const uint32_t left = seen < total ? total - seen : 0u;
+                sz = min((uint32_t)NP_CHUNK, max(32u, left / (2u * gridDim.x * (NP_THREADS / 32))));
+                c = atomicAdd(chunk_cursor, sz);
+            }
             c = __shfl_sync(0xffffffffu, c, 0);
+            sz = __shfl_sync(0xffffffffu, sz, 0);
             if (c >= total) more = false;
-            else { cursor = c; chunk_end = min(c + NP_CHUNK, total); }
+            else { cursor = c; chunk_end = min(c + sz, total); }
         }
         // ---- refill finished lanes with the next items of the chunk
         if (need && cursor < chunk_end) {
