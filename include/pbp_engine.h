@@ -176,6 +176,19 @@ int pbp_check_paths(pbp_engine *e, const float *q_dev, const int64_t *path_offse
 int pbp_sample_free_states(pbp_engine *e, int64_t n_wanted, uint64_t seed, float joint_padding, float padding,
                            int max_rounds, float *q_out_dev, int64_t *n_found_host, int64_t *n_drawn_host, void *stream);
 
+/* k nearest neighbours in joint space of every node among the other nodes, for batched PRM
+ * construction.  Replaces one Graph.get_nearest_neighbors call per node
+ * (src/pyroboplan/planning/graph.py:271-301, called from PRMPlanner.connect_node,
+ * src/pyroboplan/planning/prm.py:186-190): neighbours with distance <= radius, sorted by distance
+ * (ties keep index order), first k; the node itself is never returned.
+ *   nodes_dev          [n][nq] float32
+ *   predecessors_only  != 0: node i only sees nodes j < i (the reference's incremental roadmap)
+ *   idx_dev            [n][k] int32, -1 where fewer than k neighbours qualify
+ *   dist_dev           [n][k] float32 distances (inf where idx is -1)
+ * Distances accumulate in FP64.  k <= 64. */
+int pbp_knn(pbp_engine *e, const float *nodes_dev, int64_t n, int32_t k, double radius, int32_t predecessors_only,
+            int32_t *idx_dev, float *dist_dev, void *stream);
+
 /* One try of damped-least-squares differential IK for N targets (thread per target, FP64 end to
  * end -- unlike the collision entry points the states here are DOUBLES, because an iterate that
  * crosses a singularity amplifies input rounding by up to 1/damping^2).

@@ -14,6 +14,7 @@
 
 #include "pbp_kernels.cuh"
 #include "pbp_ik.cuh"
+#include "pbp_knn.cuh"
 #include "pbp_supmap.h"
 
 static_assert(pbp::SUPMAP_KD == pbp::SUPMAP_K, "support map resolution mismatch");
@@ -1204,5 +1205,39 @@ extern "C" int pbp_ik_iterate(pbp_engine *e, int32_t frame_id, const double *tar
     else
         k_ik_iterate<IK_MAX_PATH><<<grid_for(n, 128), 128, 0, st>>>(dt, targets_dev, q_dev, n, o, e0_dev, status_dev, iters_dev);
     LAUNCH_CHECK("k_ik_iterate");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// k nearest neighbours (batched PRM construction)
+// ------------------------------------------------------------------------------------------
+extern "C" int pbp_knn(pbp_engine *e, const float *nodes_dev, int64_t n, int32_t k, double radius, int32_t predecessors_only,
+                       int32_t *idx_dev, float *dist_dev, void *stream) {
+    int rc = check_args(e, nodes_dev, n);
+    if (rc) return rc;
+    if (n > 0 && (!idx_dev || !dist_dev)) return fail(PBP_ERR_ARG, "NULL buffer");
+    if (k < 1 || k > KNN_MAX_K) return fail(PBP_ERR_ARG, "k must be in [1, %d]", KNN_MAX_K);
+    if (e->nq > KNN_MAX_NQ) return fail(PBP_ERR_CAPACITY, "nq > %d", KNN_MAX_NQ);
+    if (!(radius >= 0.0)) return fail(PBP_ERR_ARG, "radius must be >= 0");
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = knn_smem_bytes(e->nq, k);
+    const double r2 = std::isinf(radius) ? INFINITY : radius * radius;
+    const unsigned grid = grid_for(n, KNN_THREADS);
+#define KNN_LAUNCH(NQ)                                                                                                   \
+    do {                                                                                                                 \
+        CUDA_TRY(cudaFuncSetAttribute(k_knn<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+        k_knn<NQ><<<grid, KNN_THREADS, smem, st>>>(nodes_dev, n, e->nq, k, r2, predecessors_only, idx_dev, dist_dev);     \
+    } while (0)
+    switch (e->nq) {
+    case 2: KNN_LAUNCH(2); break;
+    case 6: KNN_LAUNCH(6); break;
+    case 7: KNN_LAUNCH(7); break;
+    case 9: KNN_LAUNCH(9); break;
+    default: KNN_LAUNCH(0); break;
+    }
+#undef KNN_LAUNCH
+    LAUNCH_CHECK("k_knn");
     return 0;
 }

@@ -1,0 +1,94 @@
+// Brute-force k nearest neighbours in joint space for batched PRM construction.
+//
+// Restates Graph.get_nearest_neighbors (/root/reference/src/pyroboplan/planning/graph.py:271-301)
+// as used by PRMPlanner.connect_node (planning/prm.py:186-187): all nodes with
+// configuration_distance(q_i, q_j) <= radius, sorted by distance (stable: ties keep index order),
+// first k.  "Predecessor" mode mirrors the reference's incremental construction, where node i only
+// sees the nodes inserted before it (j < i).
+//
+// One thread per query node; candidates stream through shared memory in tiles, so every node is
+// read from HBM once per block of KNN_THREADS queries (N = 20 k, nq = 9: 720 KB, L2 resident).
+// Distances accumulate in FP64 (the nodes are float32, hence exact in FP64; the reference orders
+// float64 norms) -- 20 k x 20 k x 9 DFMA is ~3.6 GFLOP, noise for the chip.  The k best live in a
+// thread-interleaved shared-memory array kept sorted by insertion; almost every candidate fails
+// the first comparison against the current k-th best.
+#pragma once
+#include <stdint.h>
+
+namespace pbp {
+
+constexpr int KNN_THREADS = 128;
+constexpr int KNN_TILE = 128;
+constexpr int KNN_MAX_K = 64;
+constexpr int KNN_MAX_NQ = 64;
+
+inline size_t knn_smem_bytes(int nq, int k) {
+    return (size_t)KNN_TILE * nq * 4 + (size_t)k * KNN_THREADS * (8 + 4) + 16;
+}
+
+// NQ > 0: query coordinates in registers; NQ == 0: any nq <= KNN_MAX_NQ (query re-read from shared memory)
+template <int NQ>
+__global__ void __launch_bounds__(KNN_THREADS)
+k_knn(const float *__restrict__ nodes, int64_t n, int nq_dyn, int k, double radius2, int predecessors_only,
+      int32_t *__restrict__ idx_out, float *__restrict__ dist_out) {
+    extern __shared__ __align__(16) unsigned char knn_smem[];
+    const int nq = NQ > 0 ? NQ : nq_dyn;
+    double *sd = reinterpret_cast<double *>(knn_smem);                                   // [k][KNN_THREADS]
+    int32_t *si = reinterpret_cast<int32_t *>(knn_smem + (size_t)k * KNN_THREADS * 8);     // [k][KNN_THREADS]
+    float *tile = reinterpret_cast<float *>(knn_smem + (size_t)k * KNN_THREADS * 12);      // [KNN_TILE][nq]
+    const int tid = threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.x * KNN_THREADS;
+    const int64_t i = i0 + tid;
+    const bool live = i < n;
+    float qi[NQ > 0 ? NQ : 1];
+    if (NQ > 0 && live) {
+#pragma unroll
+        for (int c = 0; c < NQ; c++) qi[c] = nodes[i * NQ + c];
+    }
+    for (int s = 0; s < k; s++) { sd[s * KNN_THREADS + tid] = INFINITY; si[s * KNN_THREADS + tid] = -1; }
+    double worst = INFINITY;   // k-th best so far (radius2 until k are found is handled by the radius test)
+    const int64_t j_end = predecessors_only ? min(n, i0 + KNN_THREADS) : n;
+    for (int64_t j0 = 0; j0 < j_end; j0 += KNN_TILE) {
+        const int cnt = (int)min((int64_t)KNN_TILE, j_end - j0);
+        __syncthreads();
+        for (int t = tid; t < cnt * nq; t += KNN_THREADS) tile[t] = nodes[j0 * nq + t];
+        __syncthreads();
+        if (!live) continue;
+        const int lim = predecessors_only ? (int)min((int64_t)cnt, i - j0) : cnt;   // j < i only
+        for (int jj = 0; jj < lim; jj++) {
+            const int64_t j = j0 + jj;
+            if (j == i) continue;
+            double d2 = 0.0;
+            if (NQ > 0) {
+#pragma unroll
+                for (int c = 0; c < NQ; c++) {
+                    const double d = (double)qi[c] - (double)tile[jj * NQ + c];
+                    d2 = fma(d, d, d2);
+                }
+            } else {
+                for (int c = 0; c < nq; c++) {
+                    const double d = (double)nodes[i * nq + c] - (double)tile[jj * nq + c];
+                    d2 = fma(d, d, d2);
+                }
+            }
+            if (!(d2 <= radius2) || !(d2 < worst)) continue;
+            // insert, keeping the list sorted (strict <: an equal distance stays behind earlier indices)
+            int s = k - 1;
+            while (s > 0 && sd[(s - 1) * KNN_THREADS + tid] > d2) {
+                sd[s * KNN_THREADS + tid] = sd[(s - 1) * KNN_THREADS + tid];
+                si[s * KNN_THREADS + tid] = si[(s - 1) * KNN_THREADS + tid];
+                s--;
+            }
+            sd[s * KNN_THREADS + tid] = d2;
+            si[s * KNN_THREADS + tid] = (int32_t)j;
+            worst = sd[(k - 1) * KNN_THREADS + tid];
+        }
+    }
+    if (!live) return;
+    for (int s = 0; s < k; s++) {
+        idx_out[i * k + s] = si[s * KNN_THREADS + tid];
+        dist_out[i * k + s] = si[s * KNN_THREADS + tid] >= 0 ? (float)sqrt(sd[s * KNN_THREADS + tid]) : INFINITY;
+    }
+}
+
+}  // namespace pbp

@@ -41,6 +41,7 @@ EXPORTED_SYMBOLS = [
     "pbp_get_profile",
     "pbp_measure_fp32_peak",
     "pbp_ik_iterate",
+    "pbp_knn",
 ]
 
 
@@ -144,6 +145,7 @@ def load_library():
     lib.pbp_get_profile.argtypes = [vp, ctypes.POINTER(_Profile), i32]
     lib.pbp_measure_fp32_peak.argtypes = [i32, ctypes.POINTER(f64)]
     lib.pbp_ik_iterate.argtypes = [vp, i32, vp, vp, i64, ctypes.POINTER(_IkOptions), ctypes.c_uint64, vp, vp, vp, vp, vp]
+    lib.pbp_knn.argtypes = [vp, vp, i64, i32, f64, i32, vp, vp, vp]
     if lib.pbp_abi_version() != PBP_ABI_VERSION:
         raise RuntimeError("libpbp_engine.so ABI version mismatch; rebuild it")
     _lib = lib
@@ -457,6 +459,19 @@ class CollisionEngine:
                                        ctypes.c_void_p(w.ctypes.data) if w is not None else None, ptr(e0), ptr(status), ptr(iters),
                                        self._stream()))
         return Qd, status, iters, e0
+
+    # ------------------------------------------------------------------ k nearest neighbours
+    def knn(self, nodes, k, radius=np.inf, predecessors_only=False):
+        """k nearest nodes of every node (CUDA tensor [N, nq]) -> (idx [N, k] int32, -1 padded; dist [N, k] float32)."""
+        torch = _torch()
+        Nd = self._dev_q(nodes)
+        n = Nd.shape[0]
+        idx = torch.empty((n, int(k)), dtype=torch.int32, device=self.torch_device)
+        dist = torch.empty((n, int(k)), dtype=torch.float32, device=self.torch_device)
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        _check(self.lib.pbp_knn(self._h, ptr(Nd), n, int(k), float(radius), int(bool(predecessors_only)), ptr(idx), ptr(dist),
+                                self._stream()))
+        return idx, dist
 
     # ------------------------------------------------------------------ sampling
     def sample_free_states(self, n, seed=0, joint_padding=0.0, padding=0.0, max_rounds=64, as_numpy=False):

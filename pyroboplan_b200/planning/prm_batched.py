@@ -8,8 +8,8 @@ edges whose straight segment is collision free (`has_collision_free_path(node.q,
 
 Every one of those steps is independent across nodes once the node set is fixed, so here they are
 batched: (1) free nodes from the device sampler, (2) k nearest predecessors by brute-force L2 on
-the GPU (dense `torch.cdist` + `topk`, library code: the k-NN is not the hot path of this
-repository), (3) ALL candidate edges validated in one `check_edges` call -- block-sharded across
+the GPU (`pbp_knn`, a hand-written tiled kernel with FP64 distance accumulation so the neighbour
+order equals the reference's), (3) ALL candidate edges validated in one `check_edges` call -- block-sharded across
 ranks, with one NCCL all-gather assembling the validity mask on every rank.
 """
 
@@ -19,7 +19,7 @@ from ..distributed import validate_edges_sharded
 from ..engine import get_engine
 
 
-def nearest_predecessors(nodes, k, radius=np.inf, block=4096):
+def nearest_predecessors(nodes, k, radius=np.inf, engine=None, predecessors_only=True):
     """For node i: its k nearest nodes j < i with distance <= radius, sorted by distance.
 
     nodes: CUDA float32 tensor [N, nq].  Returns (idx [N, k] int64 with -1 padding, dist [N, k]).
@@ -27,20 +27,16 @@ def nearest_predecessors(nodes, k, radius=np.inf, block=4096):
     """
     import torch
 
-    n = nodes.shape[0]
-    idx = torch.full((n, k), -1, dtype=torch.int64, device=nodes.device)
-    dist = torch.full((n, k), float("inf"), dtype=torch.float32, device=nodes.device)
-    cols = torch.arange(n, device=nodes.device)
-    for r0 in range(0, n, block):
-        r1 = min(r0 + block, n)
-        d = torch.cdist(nodes[r0:r1], nodes[:r1])  # only predecessors can matter
-        rows = torch.arange(r0, r1, device=nodes.device)
-        d = torch.where((cols[:r1][None, :] < rows[:, None]) & (d <= radius), d, torch.full_like(d, float("inf")))
-        kk = min(k, r1)
-        dv, di = torch.topk(d, kk, dim=1, largest=False, sorted=True)
-        di = torch.where(torch.isinf(dv), torch.full_like(di, -1), di)
-        idx[r0:r1, :kk] = di
-        dist[r0:r1, :kk] = dv
+    if engine is None:
+        raise ValueError("nearest_predecessors needs the CollisionEngine that owns the device (engine=...)")
+    idx = torch.full((nodes.shape[0], k), -1, dtype=torch.int64, device=nodes.device)
+    dist = torch.full((nodes.shape[0], k), float("inf"), dtype=torch.float32, device=nodes.device)
+    for k0 in range(0, k, 64):   # the kernel keeps at most 64 neighbours per pass; more is not a PRM use case
+        if k0 > 0:
+            raise ValueError("k > 64 is not supported")
+        i32, d = engine.knn(nodes, min(k, 64), radius, predecessors_only=predecessors_only)
+        idx[:, : i32.shape[1]] = i32.to(torch.int64)
+        dist[:, : d.shape[1]] = d
     return idx, dist
 
 
@@ -67,7 +63,7 @@ def construct_roadmap_batched(model, collision_model, n_nodes, k=10, radius=np.i
     else:
         nodes = torch.as_tensor(np.asarray(nodes, dtype=np.float32) if not isinstance(nodes, torch.Tensor) else nodes,
                                 device=eng.torch_device).to(torch.float32).contiguous()
-    idx, dist = nearest_predecessors(nodes, k, radius)
+    idx, dist = nearest_predecessors(nodes, k, radius, engine=eng)
     node_ids = torch.arange(nodes.shape[0], device=nodes.device)[:, None].expand_as(idx)
     keep = idx >= 0
     cand = torch.stack([idx[keep], node_ids[keep]], dim=1)  # row-major: node by node, nearest first
