@@ -176,6 +176,26 @@ int pbp_check_paths(pbp_engine *e, const float *q_dev, const int64_t *path_offse
 int pbp_sample_free_states(pbp_engine *e, int64_t n_wanted, uint64_t seed, float joint_padding, float padding,
                            int max_rounds, float *q_out_dev, int64_t *n_found_host, int64_t *n_drawn_host, void *stream);
 
+/* Distance, witness points and normal of EVERY active pair for N configurations (FP32 GJK with
+ * witness tracking, thread per (pair, state)).  Replaces pinocchio.computeDistances as the
+ * reference reads its results -- distanceResults[k].min_distance, getNearestPoint1/2(), normal
+ * (src/pyroboplan/core/utils.py:505-516; src/pyroboplan/ik/nullspace_components.py:124-131).
+ * Outputs are PAIR-MAJOR in the caller's pair order: dist_dev[k*N + i]; p1/p2/normal_dev
+ * [(k*N + i)*3 ..] in the world frame (each of the three may be NULL).
+ *   cutoff   pairs certainly farther apart than this return a lower bound of their distance
+ *            (> cutoff) and zero witness data; INFINITY = exact distances everywhere
+ * Overlapping pairs report distance 0 and zero witness data (no penetration depth / EPA). */
+int pbp_compute_distances(pbp_engine *e, const float *q_dev, int64_t n, float cutoff, float *dist_dev, float *p1_dev,
+                          float *p2_dev, float *normal_dev, void *stream);
+
+/* Collision-avoidance null-space term for N configurations:
+ *   component[i] = gain * sum_{pairs k with dist <= dist_padding} -(normal_k dist_k - dist_padding) @ (Jcoll2 - Jcoll1)
+ * Replaces collision_avoidance_nullspace_component (src/pyroboplan/ik/nullspace_components.py:82-142)
+ * including calculate_collision_vector_and_jacobians (src/pyroboplan/core/utils.py:478-538).
+ *   component_dev  [N][nq] float32 */
+int pbp_collision_nullspace(pbp_engine *e, const float *q_dev, int64_t n, float dist_padding, float gain,
+                            float *component_dev, void *stream);
+
 /* k nearest neighbours in joint space of every node among the other nodes, for batched PRM
  * construction.  Replaces one Graph.get_nearest_neighbors call per node
  * (src/pyroboplan/planning/graph.py:271-301, called from PRMPlanner.connect_node,
@@ -201,6 +221,10 @@ int pbp_knn(pbp_engine *e, const float *nodes_dev, int64_t n, int32_t k, double 
  *                 to [-pi, pi) when converged, differential_ik.py:221)
  *   active_mask   bit k set = joint coordinate k may move (ignore_joint_indices cleared)
  *   w_diag_host   [nq] diagonal of W = inverse joint weights (NULL = identity)
+ *   nullspace_dev [N][nq] float64 null-space term, constant for the iterations of this call
+ *                 (NULL = none): the step becomes alpha (W J^T solve(jjt, error - J ns) + ns) on the
+ *                 active coordinates (:274-283).  Terms that depend on q (joint limits, collision
+ *                 avoidance) are refreshed by calling with max_iters = 1 once per iteration.
  *   e0_dev        [N] in/out initial error norm of each solve (0 = not captured yet; it is kept
  *                 across retries, as the reference does, :200,264-265)
  *   status_dev    [N] bit 0: pose error within tolerance, bit 1: within joint limits (after wrapping)
@@ -212,8 +236,8 @@ typedef struct {
     double max_translation_error, max_rotation_error, damping, min_step_size, max_step_size;
 } pbp_ik_options;
 int pbp_ik_iterate(pbp_engine *e, int32_t frame_id, const double *targets_dev, double *q_dev, int64_t n, const pbp_ik_options *opt,
-                   uint64_t active_mask, const double *w_diag_host, double *e0_dev, int32_t *status_dev, int32_t *iters_dev,
-                   void *stream);
+                   uint64_t active_mask, const double *w_diag_host, const double *nullspace_dev, double *e0_dev,
+                   int32_t *status_dev, int32_t *iters_dev, void *stream);
 
 #ifdef __cplusplus
 }

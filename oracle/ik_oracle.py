@@ -98,8 +98,9 @@ def log6(M):
 
 
 def ik_try(model, frame_id, target, q0, e0=None, max_iters=200, max_translation_error=1e-3, max_rotation_error=1e-3,
-           damping=1e-3, min_step_size=0.1, max_step_size=0.5, active=None, joint_weights=None):
-    """One try (inner while loop of the reference).  target: 4x4.  Returns (q, converged, within_limits, iters, e0)."""
+           damping=1e-3, min_step_size=0.1, max_step_size=0.5, active=None, joint_weights=None, nullspace_components=()):
+    """One try (inner while loop of the reference).  target: 4x4.  Returns (q, converged, within_limits, iters, e0).
+    nullspace_components: callables ``comp(model, q)`` as in the reference (:274-283)."""
     q = np.array(q0, dtype=np.float64)
     active = list(range(model.nq)) if active is None else list(active)
     W = np.eye(len(active)) if joint_weights is None else np.linalg.inv(np.diag(np.asarray(joint_weights, dtype=np.float64)))
@@ -119,7 +120,11 @@ def ik_try(model, frame_id, target, q0, e0=None, max_iters=200, max_translation_
         if not e0:
             e0 = error_norm
         alpha = min_step_size + (1.0 - error_norm / e0) * (max_step_size - min_step_size)
-        q_step = alpha * W @ J.T @ np.linalg.solve(jjt, error)
+        if not nullspace_components:
+            q_step = alpha * W @ J.T @ np.linalg.solve(jjt, error)
+        else:
+            ns = sum(comp(model, q)[active] for comp in nullspace_components)
+            q_step = alpha * (W @ J.T @ np.linalg.solve(jjt, error - J @ ns) + ns)
         for dq, idx in zip(q_step, active):
             q[idx] += dq
         n_iters += 1
@@ -127,3 +132,52 @@ def ik_try(model, frame_id, target, q0, e0=None, max_iters=200, max_translation_
             break
     within = bool(np.all(q >= model.lowerPositionLimit) and np.all(q <= model.upperPositionLimit)) if converged else False
     return q, converged, within, n_iters, e0
+
+
+# ------------------------------------------------------------------------------------------------
+# collision-avoidance null-space term (reference ik/nullspace_components.py:82-142 with
+# core/utils.py:478-538), float64, from the C oracle's per-pair distances and witness points
+# ------------------------------------------------------------------------------------------------
+def point_jacobian(model, joint_T, parent_joint, point):
+    """3 x nv Jacobian of the linear velocity of a world point rigidly attached to `parent_joint`
+    (= [I, -skew(r)] @ LOCAL_WORLD_ALIGNED frame Jacobian of the reference)."""
+    J = np.zeros((3, model.nv))
+    j = parent_joint
+    while j > 0:
+        T = joint_T[j]
+        z = T[:3, :3] @ model.joints[j].axis
+        J[:, model.joints[j].idx_v] = np.cross(z, point - T[:3, 3]) if model.joints[j].type == 1 else z
+        j = model.parents[j]
+    return J
+
+
+def all_joint_poses(model, q):
+    T = {0: np.eye(4)}
+    for j in range(1, model.njoints):
+        T[j] = T[model.parents[j]] @ model.jointPlacements[j].homogeneous @ _joint_motion(model.joints[j], q[model.joints[j].idx_q])
+    return T
+
+
+def collision_vector_and_jacobians(model, collision_model, orc, pair_idx, q):
+    """(normal * distance, Jcoll1, Jcoll2, distance, intersecting) for one pair."""
+    cp = collision_model.collisionPairs[pair_idx]
+    d, pa, pb, inter = orc.pair_distance(q, cp.first, cp.second)
+    joint_T = all_joint_poses(model, q)
+    J1 = point_jacobian(model, joint_T, collision_model.geometryObjects[cp.first].parentJoint, pa)
+    J2 = point_jacobian(model, joint_T, collision_model.geometryObjects[cp.second].parentJoint, pb)
+    normal = (pb - pa) / d if (d > 0 and not inter) else np.zeros(3)
+    return normal * d, J1, J2, d, inter
+
+
+def collision_avoidance_component(model, collision_model, orc, q, dist_padding=0.05, gain=1.0):
+    """Returns (component [nv], any pair overlapping?).  Overlapping pairs contribute with distance 0
+    and a zero normal, as the engine does (no penetration depth)."""
+    comp = np.zeros(model.nv)
+    any_overlap = False
+    for k in range(len(collision_model.collisionPairs)):
+        vec, J1, J2, d, inter = collision_vector_and_jacobians(model, collision_model, orc, k, q)
+        any_overlap |= inter
+        if d > dist_padding:
+            continue
+        comp -= (vec - dist_padding) @ (J2 - J1)
+    return gain * comp, any_overlap

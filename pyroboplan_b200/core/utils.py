@@ -169,6 +169,35 @@ def extract_cartesian_poses(model, target_frame, q_vec, data=None):
     return [SE3(oMf[i, fid, :9].reshape(3, 3).astype(np.float64), oMf[i, fid, 9:].astype(np.float64)) for i in range(len(Q))]
 
 
+def calculate_collision_vector_and_jacobians(model, collision_model, data, collision_data, pair_idx, q):
+    """Collision vector (normal * distance, object 1 -> object 2) and the 3 x nv Jacobians of the two
+    witness points of pair ``pair_idx`` at ``q``.
+
+    Reference: core/utils.py:478-538.  The reference reads ``collision_data.distanceResults`` that a
+    previous ``computeDistances`` left behind; here ``data`` / ``collision_data`` are ignored and the
+    pair's distance and witness points are computed on the device for ``q``.  The Jacobians --
+    ``[I, -skew(r)] @ J_frame(LOCAL_WORLD_ALIGNED)``, i.e. column k = z_k x (p - o_k) for a revolute
+    joint on the chain of the geometry's parent joint and z_k for a prismatic one -- are small
+    host arithmetic on the device FK.  Overlapping pairs have distance 0 (no penetration depth).
+    """
+    eng = _engine(model, collision_model)
+    q = np.asarray(q, dtype=np.float64).reshape(1, -1)
+    dist, p1, p2, normal = eng.compute_distances(q)
+    oMi, _, _ = eng.fk(q, joints=True, geoms=False, frames=False)
+    cp = collision_model.collisionPairs[pair_idx]
+    jacs = []
+    for gid, point in ((cp.first, p1[0, pair_idx]), (cp.second, p2[0, pair_idx])):
+        J = np.zeros((3, model.nv))
+        j = collision_model.geometryObjects[gid].parentJoint
+        while j > 0:
+            R, o = oMi[0, j, :9].reshape(3, 3).astype(np.float64), oMi[0, j, 9:].astype(np.float64)
+            z = R @ np.asarray(model.joints[j].axis, dtype=np.float64)
+            J[:, model.joints[j].idx_v] = np.cross(z, point.astype(np.float64) - o) if model.joints[j].type == 1 else z
+            j = model.parents[j]
+        jacs.append(J)
+    return normal[0, pair_idx].astype(np.float64) * float(dist[0, pair_idx]), jacs[0], jacs[1]
+
+
 # ----------------------------------------------------------------------------------------------
 # Batched siblings (the point of the engine)
 # ----------------------------------------------------------------------------------------------
@@ -187,3 +216,8 @@ def sample_collision_free_states(model, collision_model, n, seed=0, joint_paddin
     """Batched ``get_random_collision_free_state``: ``n`` free states from a Philox stream keyed
     by ``seed`` (not the global ``np.random`` stream)."""
     return _engine(model, collision_model).sample_free_states(n, seed, joint_padding, distance_padding, as_numpy=as_numpy)
+
+
+def compute_distances_at_states(model, collision_model, Q, cutoff=np.inf):
+    """Batched ``pinocchio.computeDistances``: (dist [N, npairs], p1, p2, normal [N, npairs, 3])."""
+    return _engine(model, collision_model).compute_distances(Q, cutoff)

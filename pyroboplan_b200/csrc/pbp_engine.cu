@@ -15,6 +15,7 @@
 #include "pbp_kernels.cuh"
 #include "pbp_ik.cuh"
 #include "pbp_knn.cuh"
+#include "pbp_witness.cuh"
 #include "pbp_supmap.h"
 
 static_assert(pbp::SUPMAP_KD == pbp::SUPMAP_K, "support map resolution mismatch");
@@ -117,6 +118,7 @@ struct pbp_engine {
     std::vector<int32_t> h_joint_parent, h_joint_type, h_joint_idx_q, h_frame_parent;
     std::vector<double> h_joint_placement, h_joint_axis, h_frame_placement, h_q_lower, h_q_upper;
     DeviceBuffer d_ik_tables;
+    DeviceBuffer d_ws_oMi, d_ws_oMg, d_ws_dist, d_ws_p1, d_ws_p2, d_ws_nrm, d_pairs_orig;   // distance / witness scratch
     pbp::IkTables ik_cached{}, ik_build{};
     bool ik_cached_valid = false;
     size_t smem_bp = 0, smem_is = 0, smem_np = 0, smem_fk = 0;
@@ -286,7 +288,8 @@ void pbp_engine_destroy(pbp_engine *e) {
                             &e->d_pathops, &e->d_order, &e->d_verts, &e->d_supcells, &e->d_suplists, &e->d_qlim, &e->d_frames, &e->d_bin_state,
                             &e->d_bin_group, &e->d_bin_sample, &e->d_bin_T, &e->d_ctrl, &e->d_counts, &e->d_desc_group,
                             &e->d_desc_frac, &e->d_desc_sample, &e->d_scratch_i32, &e->d_scratch_u8, &e->d_cub, &e->d_sel,
-                            &e->d_io_q, &e->d_io_q2, &e->d_io_hit, &e->d_io_f32, &e->d_io_i32, &e->d_ik_tables};
+                            &e->d_io_q, &e->d_io_q2, &e->d_io_hit, &e->d_io_f32, &e->d_io_i32, &e->d_ik_tables, &e->d_ws_oMi, &e->d_ws_oMg, &e->d_ws_dist,
+                            &e->d_ws_p1, &e->d_ws_p2, &e->d_ws_nrm, &e->d_pairs_orig};
     for (DeviceBuffer *b : bufs) b->release();
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     e->h_io_hit.release(); e->h_io_f32.release(); e->h_io_i32.release();
@@ -564,7 +567,8 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
         (rc = upload(e->d_verts, verts.data(), verts.size() * sizeof(float4))) ||
         (rc = upload(e->d_supcells, sup_cells.data(), sup_cells.size() * 2)) ||
         (rc = upload(e->d_suplists, sup_lists.data(), sup_lists.size() * 2)) ||
-        (rc = upload(e->d_qlim, qlim.data(), qlim.size() * sizeof(float))))
+        (rc = upload(e->d_qlim, qlim.data(), qlim.size() * sizeof(float))) ||
+        (rc = upload(e->d_pairs_orig, d->pairs, std::max<size_t>((size_t)d->npairs, 1) * 8)))
         return bail(rc);
     {
         // frames: [nframes] int32 parents followed (16-byte aligned) by [nframes][12] placements
@@ -1127,8 +1131,8 @@ extern "C" int pbp_measure_fp32_peak(int device, double *tflops_out) {
 // differential IK (one try for N targets)
 // ------------------------------------------------------------------------------------------
 extern "C" int pbp_ik_iterate(pbp_engine *e, int32_t frame_id, const double *targets_dev, double *q_dev, int64_t n,
-                              const pbp_ik_options *opt, uint64_t active_mask, const double *w_diag_host, double *e0_dev,
-                              int32_t *status_dev, int32_t *iters_dev, void *stream) {
+                              const pbp_ik_options *opt, uint64_t active_mask, const double *w_diag_host,
+                              const double *nullspace_dev, double *e0_dev, int32_t *status_dev, int32_t *iters_dev, void *stream) {
     int rc = check_args(e, q_dev, n);
     if (rc) return rc;
     if (n > 0 && (!targets_dev || !e0_dev || !status_dev || !opt)) return fail(PBP_ERR_ARG, "NULL buffer");
@@ -1172,6 +1176,7 @@ extern "C" int pbp_ik_iterate(pbp_engine *e, int32_t frame_id, const double *tar
             J.idx_q = e->h_joint_idx_q[j];
             const bool active = J.idx_q < 64 && ((active_mask >> J.idx_q) & 1ull);
             J.w = active ? (w_diag_host ? w_diag_host[J.idx_q] : 1.0) : 0.0;
+            if (J.idx_q < 64) tab.path_mask |= 1ull << J.idx_q;
             const double ident[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
             memcpy(acc, ident, sizeof(acc));
         }
@@ -1181,6 +1186,7 @@ extern "C" int pbp_ik_iterate(pbp_engine *e, int32_t frame_id, const double *tar
         tab.npath = k;
     }
     tab.nq = e->nq;
+    tab.active_mask = active_mask;
     for (int k = 0; k < e->nq; k++) { tab.q_lower[k] = e->h_q_lower[k]; tab.q_upper[k] = e->h_q_upper[k]; }
     if ((rc = e->d_ik_tables.ensure(sizeof(IkTables)))) return rc;
     if (!e->ik_cached_valid || memcmp(&tab, &e->ik_cached, sizeof(IkTables)) != 0) {
@@ -1199,11 +1205,11 @@ extern "C" int pbp_ik_iterate(pbp_engine *e, int32_t frame_id, const double *tar
     o.max_step = opt->max_step_size;
     const IkTables *dt = e->d_ik_tables.as<IkTables>();
     if (tab.npath <= 8)
-        k_ik_iterate<8><<<grid_for(n, 128), 128, 0, st>>>(dt, targets_dev, q_dev, n, o, e0_dev, status_dev, iters_dev);
+        k_ik_iterate<8><<<grid_for(n, 128), 128, 0, st>>>(dt, targets_dev, q_dev, n, o, nullspace_dev, e0_dev, status_dev, iters_dev);
     else if (tab.npath <= 16)
-        k_ik_iterate<16><<<grid_for(n, 128), 128, 0, st>>>(dt, targets_dev, q_dev, n, o, e0_dev, status_dev, iters_dev);
+        k_ik_iterate<16><<<grid_for(n, 128), 128, 0, st>>>(dt, targets_dev, q_dev, n, o, nullspace_dev, e0_dev, status_dev, iters_dev);
     else
-        k_ik_iterate<IK_MAX_PATH><<<grid_for(n, 128), 128, 0, st>>>(dt, targets_dev, q_dev, n, o, e0_dev, status_dev, iters_dev);
+        k_ik_iterate<IK_MAX_PATH><<<grid_for(n, 128), 128, 0, st>>>(dt, targets_dev, q_dev, n, o, nullspace_dev, e0_dev, status_dev, iters_dev);
     LAUNCH_CHECK("k_ik_iterate");
     return 0;
 }
@@ -1239,5 +1245,62 @@ extern "C" int pbp_knn(pbp_engine *e, const float *nodes_dev, int64_t n, int32_t
     }
 #undef KNN_LAUNCH
     LAUNCH_CHECK("k_knn");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-pair distances with witness points; collision-avoidance null-space term
+// ------------------------------------------------------------------------------------------
+namespace {
+int launch_distances(pbp_engine *e, const float *q_dev, int64_t n, float cutoff, float *oMi, float *oMg, float *dist, float *p1,
+                     float *p2, float *nrm, cudaStream_t st) {
+    k_fk_output<<<grid_for(n, 128), 128, e->smem_fk, st>>>(e->dm, q_dev, n, oMi, oMg, nullptr);
+    LAUNCH_CHECK("k_fk_output");
+    const int64_t items = n * e->npairs;
+    k_pair_distances<<<grid_for(items, 128), 128, 0, st>>>(e->dm, oMg, n, cutoff, dist, p1, p2, nrm);
+    LAUNCH_CHECK("k_pair_distances");
+    return 0;
+}
+}  // namespace
+
+extern "C" int pbp_compute_distances(pbp_engine *e, const float *q_dev, int64_t n, float cutoff, float *dist_dev, float *p1_dev,
+                                     float *p2_dev, float *normal_dev, void *stream) {
+    int rc = check_args(e, q_dev, n);
+    if (rc) return rc;
+    if (n > 0 && !dist_dev) return fail(PBP_ERR_ARG, "dist buffer is NULL");
+    if (!(cutoff >= 0.0f)) return fail(PBP_ERR_ARG, "cutoff must be >= 0");
+    if (n == 0 || e->npairs == 0) return 0;
+    if (n * (int64_t)e->npairs > (int64_t)INT32_MAX * 64) return fail(PBP_ERR_ARG, "too many (state, pair) items");
+    CUDA_TRY(cudaSetDevice(e->device));
+    if ((rc = e->d_ws_oMg.ensure((size_t)n * e->ngeoms * 48))) return rc;
+    return launch_distances(e, q_dev, n, cutoff, nullptr, e->d_ws_oMg.as<float>(), dist_dev, p1_dev, p2_dev, normal_dev,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int pbp_collision_nullspace(pbp_engine *e, const float *q_dev, int64_t n, float dist_padding, float gain,
+                                       float *component_dev, void *stream) {
+    int rc = check_args(e, q_dev, n);
+    if (rc) return rc;
+    if (n > 0 && !component_dev) return fail(PBP_ERR_ARG, "component buffer is NULL");
+    if (!(dist_padding >= 0.0f)) return fail(PBP_ERR_ARG, "dist_padding must be >= 0");
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (e->npairs == 0) {
+        CUDA_TRY(cudaMemsetAsync(component_dev, 0, (size_t)n * e->nq * 4, st));
+        return 0;
+    }
+    const size_t items = (size_t)n * e->npairs;
+    if ((rc = e->d_ws_oMi.ensure((size_t)n * e->njoints * 48)) || (rc = e->d_ws_oMg.ensure((size_t)n * e->ngeoms * 48)) ||
+        (rc = e->d_ws_dist.ensure(items * 4)) || (rc = e->d_ws_p1.ensure(items * 12)) || (rc = e->d_ws_p2.ensure(items * 12)) ||
+        (rc = e->d_ws_nrm.ensure(items * 12)))
+        return rc;
+    if ((rc = launch_distances(e, q_dev, n, dist_padding, e->d_ws_oMi.as<float>(), e->d_ws_oMg.as<float>(), e->d_ws_dist.as<float>(),
+                               e->d_ws_p1.as<float>(), e->d_ws_p2.as<float>(), e->d_ws_nrm.as<float>(), st)))
+        return rc;
+    k_collision_nullspace<<<grid_for(n, 128), 128, 0, st>>>(e->dm, e->d_pairs_orig.as<int32_t>(), e->d_ws_oMi.as<float>(),
+                                                           e->d_ws_dist.as<float>(), e->d_ws_p1.as<float>(), e->d_ws_p2.as<float>(),
+                                                           e->d_ws_nrm.as<float>(), n, dist_padding, gain, component_dev);
+    LAUNCH_CHECK("k_collision_nullspace");
     return 0;
 }

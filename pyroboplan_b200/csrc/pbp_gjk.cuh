@@ -228,6 +228,7 @@ struct GjkOut {
                   // meaningful as "<= margin" / "> margin"
     int hit;      // dist <= margin
     int iters;
+    int far;      // finished through the separating-plane bound: dist is a LOWER bound beyond the cut
 };
 
 #define PBP_GJK_MAX_ITERS 48
@@ -243,6 +244,9 @@ struct GjkState {
     float3 W0, W1, W2;   // simplex vertices (Minkowski-difference points), n of them valid
     float3 w;            // newest support point, handed from the support phase to the simplex phase
     int n, it, stalls;
+    // TRACK only (witness points): the support points of shape A behind W0..W2 and behind w, in
+    // A's frame.  Kernels that never ask for witness points never touch these (dead registers).
+    float3 A0, A1, A2, a;
 };
 
 __device__ __forceinline__ void gjk_init(GjkState &s, float3 v0) {
@@ -250,6 +254,7 @@ __device__ __forceinline__ void gjk_init(GjkState &s, float3 v0) {
     s.vv = dot3(v0, v0);
     if (!(s.vv > 1e-12f)) { s.v = make_float3(1.f, 0.f, 0.f); s.vv = 1.f; }
     s.W0 = s.W1 = s.W2 = s.w = make_float3(0.f, 0.f, 0.f);
+    s.A0 = s.A1 = s.A2 = s.a = make_float3(0.f, 0.f, 0.f);
     s.n = 0; s.it = 0; s.stalls = 0;
 }
 
@@ -258,7 +263,7 @@ __device__ __forceinline__ void gjk_init(GjkState &s, float3 v0) {
 // item is finished (out is then valid); otherwise s.w holds the point for the simplex phase.
 // WANT_DIST = false: finish as soon as "distance > margin" or "distance <= margin" is certain.
 // WANT_DIST = true : run to convergence unless the pair is certainly farther than `bound`.
-template <bool WANT_DIST>
+template <bool WANT_DIST, bool TRACK = false>
 __device__ __forceinline__ bool gjk_support_phase(const ShapeRef &A, const ShapeRef &B, const float *T, GjkState &s, float margin,
                                                   float bound, GjkOut &out) {
     const float3 v = s.v;
@@ -286,10 +291,12 @@ __device__ __forceinline__ bool gjk_support_phase(const ShapeRef &A, const Shape
     printf("it %d n %d v (%g %g %g) |v| %.9g w (%g %g %g) vw/|v| %.9g\n", s.it, n, v.x, v.y, v.z, sqrtf(vv), w.x, w.y, w.z, vw / sqrtf(vv));
 #endif
     out.iters = ++s.it;
+    out.far = 0;
     // <v,w>/|v| is a lower bound of the distance for ANY direction v
     if (vw > 0.f && vw * vw > cut * cut * vv) {
         out.dist = vw * rsqrtf(vv);
         out.hit = 0;
+        out.far = 1;
         return true;
     }
     if (n > 0) {
@@ -305,22 +312,29 @@ __device__ __forceinline__ bool gjk_support_phase(const ShapeRef &A, const Shape
         }
     }
     s.w = w;
+    if (TRACK) s.a = sa;
     return false;
 }
 
 // Simplex phase: append s.w, find the point of the simplex closest to the origin, reduce the
 // simplex to the face that supports it.  Returns true when the item is finished.
-template <bool WANT_DIST>
+template <bool WANT_DIST, bool TRACK = false>
 __device__ __forceinline__ bool gjk_simplex_phase(GjkState &s, float margin, GjkOut &out) {
     const float3 w = s.w;
     const float vv = s.vv;
     const int n = s.n;
     out.iters = s.it;
+    out.far = 0;
     bool done = false, enclosed = false;
     {
         // append w and solve for the closest point of the simplex
         float3 nv, W3 = w;
         int mask;
+        if (TRACK) {
+            if (n == 0) s.A0 = s.a;
+            else if (n == 1) s.A1 = s.a;
+            else if (n == 2) s.A2 = s.a;
+        }
         if (n == 0) { s.W0 = w; nv = w; mask = 1; }
         else if (n == 1) { s.W1 = w; mask = closest_on_segment(s.W0, s.W1, nv); }
         else {
@@ -418,6 +432,11 @@ __device__ __forceinline__ bool gjk_simplex_phase(GjkState &s, float margin, Gjk
             auto pick = [&](int i) { return i == 0 ? s.W0 : (i == 1 ? s.W1 : (i == 2 ? s.W2 : W3)); };
             const float3 n0 = pick(i0), n1 = pick(i1), n2 = pick(i2);
             s.W0 = n0; s.W1 = n1; s.W2 = n2;
+            if (TRACK) {
+                auto pick_a = [&](int i) { return i == 0 ? s.A0 : (i == 1 ? s.A1 : (i == 2 ? s.A2 : s.a)); };
+                const float3 a0 = pick_a(i0), a1 = pick_a(i1), a2 = pick_a(i2);
+                s.A0 = a0; s.A1 = a1; s.A2 = a2;
+            }
             s.n = __popc(mask);
             if (s.it >= PBP_GJK_MAX_ITERS) done = true;
         }
@@ -431,11 +450,47 @@ __device__ __forceinline__ bool gjk_simplex_phase(GjkState &s, float margin, Gjk
 }
 
 // One full GJK iteration (support phase, then simplex phase).
-template <bool WANT_DIST>
+template <bool WANT_DIST, bool TRACK = false>
 __device__ __forceinline__ bool gjk_step(const ShapeRef &A, const ShapeRef &B, const float *T, GjkState &s, float margin,
                                          float bound, GjkOut &out) {
-    if (gjk_support_phase<WANT_DIST>(A, B, T, s, margin, bound, out)) return true;
-    return gjk_simplex_phase<WANT_DIST>(s, margin, out);
+    if (gjk_support_phase<WANT_DIST, TRACK>(A, B, T, s, margin, bound, out)) return true;
+    return gjk_simplex_phase<WANT_DIST, TRACK>(s, margin, out);
+}
+
+// Witness points on the cores (A's frame) of a TRACKed, finished, non-overlapping item:
+// pa = sum(lambda_i A_i) and pb = sum(lambda_i (A_i - W_i)), the same convex combination of the
+// support points of A and of B whose Minkowski image sum(lambda_i W_i) is the closest point s.v.
+// Both are convex combinations of points OF their shapes (so they lie in them whatever the
+// residual error of v); the barycentric weights are recomputed from W and v.
+__device__ __forceinline__ void gjk_witness(const GjkState &s, float3 &pa, float3 &pb) {
+    float l1 = 0.f, l2 = 0.f;   // weights of vertex 1 and 2 (vertex 0 gets the rest)
+    if (s.n == 2) {
+        const float3 e = sub3(s.W1, s.W0);
+        const float den = dot3(e, e);
+        l1 = den > 0.f ? dot3(sub3(s.v, s.W0), e) / den : 0.f;
+        l1 = fminf(fmaxf(l1, 0.f), 1.f);
+    } else if (s.n >= 3) {
+        // triangle: v = W0 + l1 e1 + l2 e2 (least squares in the plane)
+        const float3 e1 = sub3(s.W1, s.W0), e2 = sub3(s.W2, s.W0), r = sub3(s.v, s.W0);
+        const float a11 = dot3(e1, e1), a12 = dot3(e1, e2), a22 = dot3(e2, e2);
+        const float b1 = dot3(r, e1), b2 = dot3(r, e2);
+        const float det = a11 * a22 - a12 * a12;
+        if (det > 1e-12f * a11 * a22) {
+            l1 = (b1 * a22 - b2 * a12) / det;
+            l2 = (b2 * a11 - b1 * a12) / det;
+        } else if (a11 >= a22 && a11 > 0.f) {   // degenerate (collinear) triangle: use its longer edge
+            l1 = b1 / a11;
+        } else if (a22 > 0.f) {
+            l2 = b2 / a22;
+        }
+        l1 = fminf(fmaxf(l1, 0.f), 1.f);
+        l2 = fminf(fmaxf(l2, 0.f), 1.f - l1);
+    }
+    pa = s.A0;
+    float3 m = s.W0;   // Minkowski image of the combination
+    if (s.n >= 2) { pa = madd3(pa, sub3(s.A1, s.A0), l1); m = madd3(m, sub3(s.W1, s.W0), l1); }
+    if (s.n >= 3) { pa = madd3(pa, sub3(s.A2, s.A0), l2); m = madd3(m, sub3(s.W2, s.W0), l2); }
+    pb = sub3(pa, m);
 }
 
 // Whole item in one call (host build used by the CPU tests; the device narrowphase drives

@@ -37,6 +37,8 @@ struct IkTables {
     IkJoint joint[IK_MAX_PATH];
     double frame[12];                         // placement of the frame in its parent joint
     double q_lower[PBP_MAX_NQ], q_upper[PBP_MAX_NQ];
+    unsigned long long active_mask;           // coordinates that may move
+    unsigned long long path_mask;             // coordinates of the joints on the chain
     int32_t npath, nq;
 };
 
@@ -100,7 +102,8 @@ __device__ __forceinline__ void d_neg_log6(const double *E, double *e) {
 template <int MAXP>
 __global__ void __launch_bounds__(128)
 k_ik_iterate(const IkTables *__restrict__ tables, const double *__restrict__ targets, double *__restrict__ q_io, int64_t n,
-             IkOptions opt, double *__restrict__ e0_io, int32_t *__restrict__ status, int32_t *__restrict__ iters_out) {
+             IkOptions opt, const double *__restrict__ nullspace, double *__restrict__ e0_io, int32_t *__restrict__ status,
+             int32_t *__restrict__ iters_out) {
     __shared__ IkTables T;
     {
         const int words = (int)(sizeof(IkTables) / 8);
@@ -177,6 +180,16 @@ k_ik_iterate(const IkTables *__restrict__ tables, const double *__restrict__ tar
             st = 1;
             break;
         }
+        // null-space term (reference :274-283): the right-hand side becomes e - J ns
+        if (nullspace) {
+#pragma unroll
+            for (int k = 0; k < MAXP; k++) {
+                if (k >= npath || !(T.joint[k].w > 0.0)) continue;
+                const double nsk = nullspace[i * nq + T.joint[k].idx_q];
+#pragma unroll
+                for (int r = 0; r < 6; r++) e[r] -= J[k][r] * nsk;
+            }
+        }
         // A = J W J^T + damping^2 I (lower triangle), Cholesky, solve A y = e
         double A[6][6];
 #pragma unroll
@@ -214,7 +227,7 @@ k_ik_iterate(const IkTables *__restrict__ tables, const double *__restrict__ tar
             for (int m = r + 1; m < 6; m++) sacc -= A[m][r] * y[m];
             y[r] = sacc / A[r][r];
         }
-        const double en = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3] + e[4] * e[4] + e[5] * e[5]);
+        const double en = sqrt(et * et + er * er);   // norm of the pose error itself (before the null-space shift)
         if (!(e0 > 0.0)) e0 = en;
         const double alpha = opt.min_step + (1.0 - en / e0) * (opt.max_step - opt.min_step);
         bool bad = false;
@@ -224,8 +237,17 @@ k_ik_iterate(const IkTables *__restrict__ tables, const double *__restrict__ tar
             double dq = 0.0;
 #pragma unroll
             for (int r = 0; r < 6; r++) dq += J[k][r] * y[r];
-            qp[k] += alpha * T.joint[k].w * dq;
+            double step = T.joint[k].w * dq;
+            if (nullspace && T.joint[k].w > 0.0) step += nullspace[i * nq + T.joint[k].idx_q];
+            qp[k] += alpha * step;
             if (isinf(qp[k])) bad = true;
+        }
+        if (nullspace) {   // active coordinates off the chain have zero Jacobian columns: only the null-space term moves them
+            for (int k = 0; k < nq; k++)
+                if (((T.active_mask >> k) & 1ull) && !((T.path_mask >> k) & 1ull)) {
+                    q[k] += alpha * nullspace[i * nq + k];
+                    if (isinf(q[k])) bad = true;
+                }
         }
         if (bad) { it++; break; }
     }

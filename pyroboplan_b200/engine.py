@@ -42,6 +42,8 @@ EXPORTED_SYMBOLS = [
     "pbp_measure_fp32_peak",
     "pbp_ik_iterate",
     "pbp_knn",
+    "pbp_compute_distances",
+    "pbp_collision_nullspace",
 ]
 
 
@@ -144,8 +146,10 @@ def load_library():
     lib.pbp_set_profiling.argtypes = [vp, i32]
     lib.pbp_get_profile.argtypes = [vp, ctypes.POINTER(_Profile), i32]
     lib.pbp_measure_fp32_peak.argtypes = [i32, ctypes.POINTER(f64)]
-    lib.pbp_ik_iterate.argtypes = [vp, i32, vp, vp, i64, ctypes.POINTER(_IkOptions), ctypes.c_uint64, vp, vp, vp, vp, vp]
+    lib.pbp_ik_iterate.argtypes = [vp, i32, vp, vp, i64, ctypes.POINTER(_IkOptions), ctypes.c_uint64, vp, vp, vp, vp, vp, vp]
     lib.pbp_knn.argtypes = [vp, vp, i64, i32, f64, i32, vp, vp, vp]
+    lib.pbp_compute_distances.argtypes = [vp, vp, i64, f32, vp, vp, vp, vp, vp]
+    lib.pbp_collision_nullspace.argtypes = [vp, vp, i64, f32, f32, vp, vp]
     if lib.pbp_abi_version() != PBP_ABI_VERSION:
         raise RuntimeError("libpbp_engine.so ABI version mismatch; rebuild it")
     _lib = lib
@@ -434,11 +438,12 @@ class CollisionEngine:
 
     # ------------------------------------------------------------------ differential IK
     def ik_iterate(self, frame_id, targets, Q, e0=None, max_iters=200, max_translation_error=1e-3, max_rotation_error=1e-3,
-                   damping=1e-3, min_step_size=0.1, max_step_size=0.5, active_mask=None, joint_weights=None):
+                   damping=1e-3, min_step_size=0.1, max_step_size=0.5, active_mask=None, joint_weights=None, nullspace=None):
         """One try of batched DLS differential IK (device tensors; see pbp_ik_iterate in the header).
 
         targets [N, 12] (R row-major, then t), Q [N, nq] initial states; both are used as float64.  Returns
         (Q_out [N, nq], status [N] int32 (bit 0 converged, bit 1 within limits), iters [N], e0 [N]).
+        ``nullspace`` [N, nq]: null-space term held constant over the iterations of this call.
         """
         torch = _torch()
         f64 = torch.float64
@@ -454,11 +459,47 @@ class CollisionEngine:
         w = None
         if joint_weights is not None:
             w = np.ascontiguousarray(joint_weights, dtype=np.float64).reshape(self.nq)
-        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        ns = None
+        if nullspace is not None:
+            ns = torch.as_tensor(nullspace, device=self.torch_device).to(f64).reshape(n, self.nq).contiguous()
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
         _check(self.lib.pbp_ik_iterate(self._h, int(frame_id), ptr(Td), ptr(Qd), n, ctypes.byref(opt), ctypes.c_uint64(mask),
-                                       ctypes.c_void_p(w.ctypes.data) if w is not None else None, ptr(e0), ptr(status), ptr(iters),
-                                       self._stream()))
+                                       ctypes.c_void_p(w.ctypes.data) if w is not None else None, ptr(ns), ptr(e0), ptr(status),
+                                       ptr(iters), self._stream()))
         return Qd, status, iters, e0
+
+    # ------------------------------------------------------------------ per-pair distances / avoidance
+    def compute_distances(self, Q, cutoff=np.inf, witness=True):
+        """Distance (+ witness points and normal) of every active pair for every state.
+
+        CUDA tensor in -> CUDA tensors out, numpy in -> numpy out:
+        dist [N, npairs]; with ``witness`` also p1, p2, normal [N, npairs, 3] (world frame; zero for
+        overlapping pairs and for pairs farther than ``cutoff``, whose dist is a lower bound).
+        The device layout is pair-major; the returned arrays are transposed views."""
+        torch = _torch()
+        host = not self._is_dev(Q)
+        Qd = torch.as_tensor(self._host_q(Q, self.nq), device=self.torch_device) if host else self._dev_q(Q)
+        n, P = Qd.shape[0], self.npairs
+        dist = torch.empty((P, n), dtype=torch.float32, device=self.torch_device)
+        outs = [torch.empty((P, n, 3), dtype=torch.float32, device=self.torch_device) for _ in range(3)] if witness else [None] * 3
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        if P > 0:
+            _check(self.lib.pbp_compute_distances(self._h, ptr(Qd), n, float(min(cutoff, 3.0e38)) if np.isfinite(cutoff) else float("inf"),
+                                                  ptr(dist), ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), self._stream()))
+        res = [dist.transpose(0, 1)] + ([o.transpose(0, 1) for o in outs] if witness else [])
+        if host:
+            res = [r.cpu().numpy() for r in res]
+        return res[0] if not witness else tuple(res)
+
+    def collision_nullspace(self, Q, dist_padding=0.05, gain=1.0):
+        """Batched collision-avoidance null-space term [N, nq] (float32); see pbp_collision_nullspace."""
+        torch = _torch()
+        host = not self._is_dev(Q)
+        Qd = torch.as_tensor(self._host_q(Q, self.nq), device=self.torch_device) if host else self._dev_q(Q)
+        out = torch.empty((Qd.shape[0], self.nq), dtype=torch.float32, device=self.torch_device)
+        _check(self.lib.pbp_collision_nullspace(self._h, ctypes.c_void_p(Qd.data_ptr()), Qd.shape[0], float(dist_padding), float(gain),
+                                                ctypes.c_void_p(out.data_ptr()), self._stream()))
+        return out.cpu().numpy() if host else out
 
     # ------------------------------------------------------------------ k nearest neighbours
     def knn(self, nodes, k, radius=np.inf, predecessors_only=False):

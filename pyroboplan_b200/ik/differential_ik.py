@@ -6,7 +6,9 @@ restarts drawn from the global ``np.random`` stream) but runs a whole try -- up 
 damped-least-squares iterations -- in one device call.  ``solve_batch`` does the same for N targets
 at once (BASELINE.json config 5): every try is one kernel launch over the still-unsolved targets,
 the collision gate is one batched ``check_states`` and restarts come from the device sampler.
-Null-space components are host Python callables in the reference and are not supported here.
+Null-space components (host callables ``lambda model, q: ...`` as in the reference; batched
+callables ``lambda model, Q: ...`` on CUDA tensors for ``solve_batch``) are re-evaluated every
+iteration, so with them a try runs one device call per iteration instead of one per try.
 """
 
 import numpy as np
@@ -81,18 +83,40 @@ class DifferentialIk:
             mask |= 1 << i
         return mask, w_diag
 
-    def _try(self, eng, frame_id, targets, Q, e0, mask, w_diag):
+    def _try(self, eng, frame_id, targets, Q, e0, mask, w_diag, nullspace_fn=None):
+        """One try: up to max_iters iterations.  nullspace_fn(Q [M, nq] float64 tensor) -> [M, nq]."""
+        import torch
+
         o = self.options
-        return eng.ik_iterate(frame_id, targets, Q, e0, o.max_iters, o.max_translation_error, o.max_rotation_error,
-                              o.damping, o.min_step_size, o.max_step_size, mask, w_diag)
+        if nullspace_fn is None:
+            return eng.ik_iterate(frame_id, targets, Q, e0, o.max_iters, o.max_translation_error, o.max_rotation_error,
+                                  o.damping, o.min_step_size, o.max_step_size, mask, w_diag)
+        # the null-space term depends on q: one single-iteration launch per iteration over the
+        # targets that have not converged yet (the reference's loop, :208-298, iteration by iteration)
+        Q = torch.as_tensor(Q, device=eng.torch_device).to(torch.float64).reshape(-1, eng.nq).clone()
+        n = Q.shape[0]
+        e0 = torch.zeros(n, dtype=torch.float64, device=eng.torch_device) if e0 is None else e0.to(torch.float64).clone()
+        status = torch.zeros(n, dtype=torch.int32, device=eng.torch_device)
+        iters = torch.zeros(n, dtype=torch.int32, device=eng.torch_device)
+        live = torch.arange(n, device=eng.torch_device)
+        for _ in range(o.max_iters):
+            if live.numel() == 0:
+                break
+            Ql = Q[live]
+            ns = nullspace_fn(Ql)
+            Qo, st, it, e0l = eng.ik_iterate(frame_id, targets[live], Ql, e0[live], 1, o.max_translation_error, o.max_rotation_error,
+                                             o.damping, o.min_step_size, o.max_step_size, mask, w_diag, nullspace=ns)
+            Q[live], status[live], e0[live] = Qo, st, e0l
+            iters[live] += it
+            finite = torch.isfinite(Qo).all(dim=1)
+            live = live[((st & 1) == 0) & finite]
+        return Q, status, iters, e0
 
     # ------------------------------------------------------------------ single target (reference API)
     def solve(self, target_frame, target_tform, init_state=None, nullspace_components=[], verbose=False):
         """Solves one IK query; returns the joint configuration or None (reference :134-320)."""
         import torch
 
-        if nullspace_components:
-            raise NotImplementedError("null-space components are host callables in the reference; not supported on device")
         np.random.seed(self.options.rng_seed)
         frame_id = self.model.getFrameId(target_frame)
         if frame_id >= self.model.nframes:
@@ -105,9 +129,15 @@ class DifferentialIk:
         q_cur = np.array(init_state, dtype=np.float64)
         e0 = None
         n_tries = 0
+        ns_fn = None
+        if nullspace_components:
+            def ns_fn(Qt):   # host callables of the reference's form, summed (:274-279)
+                qh = Qt[0].cpu().numpy()
+                return torch.as_tensor(sum(np.asarray(comp(self.model, qh), dtype=np.float64) for comp in nullspace_components),
+                                       device=Qt.device).reshape(1, -1)
         while n_tries <= self.options.max_retries:
             Q = torch.as_tensor(q_cur, dtype=torch.float64, device=eng.torch_device).reshape(1, -1)
-            Qo, status, _, e0 = self._try(eng, frame_id, target, Q, e0, mask, w_diag)
+            Qo, status, _, e0 = self._try(eng, frame_id, target, Q, e0, mask, w_diag, ns_fn)
             st = int(status[0].item())
             q_cur = Qo[0].cpu().numpy()
             if st & 1:
@@ -133,8 +163,11 @@ class DifferentialIk:
         return None
 
     # ------------------------------------------------------------------ batched
-    def solve_batch(self, target_frame, target_tforms, init_states=None, seed=0):
+    def solve_batch(self, target_frame, target_tforms, init_states=None, seed=0, nullspace_components=[]):
         """Solves N IK queries at once.
+
+        nullspace_components: batched callables ``lambda model, Q: tensor [M, nq]`` on CUDA tensors
+        (see ``pyroboplan_b200.ik.nullspace_components.*_batch``), summed and re-evaluated every iteration.
 
         target_tforms: [N, 12] tensor/array (R row-major, then t) or a list of SE3-like objects.
         Returns (Q [N, nq] float64 device tensor, solved [N] bool device tensor, tries [N] int32).
@@ -174,7 +207,8 @@ class DifferentialIk:
         for n_tries in range(self.options.max_retries + 1):
             if pending.numel() == 0:
                 break
-            Qo, status, _, e0p = self._try(eng, frame_id, T[pending], Q[pending], e0[pending], mask, w_diag)
+            ns_fn = (lambda Qt: sum(comp(self.model, Qt) for comp in nullspace_components)) if nullspace_components else None
+            Qo, status, _, e0p = self._try(eng, frame_id, T[pending], Q[pending], e0[pending], mask, w_diag, ns_fn)
             e0[pending] = e0p
             ok = (status & 3) == 3
             if has_pairs and ok.any():

@@ -9,7 +9,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libgjk_emu.so")
 _SRC = os.path.join(_HERE, "gjk_emu.cpp")
-_HDRS = [os.path.join(_HERE, "..", "..", "pyroboplan_b200", "csrc", f) for f in ("pbp_gjk.cuh", "pbp_model.cuh", "pbp_supmap.h")]
+_HDRS = [os.path.join(_HERE, "..", "..", "pyroboplan_b200", "csrc", f) for f in ("pbp_gjk.cuh", "pbp_model.cuh", "pbp_supmap.h", "pbp_witness.cuh")]
 _lib = None
 
 
@@ -34,6 +34,9 @@ def load():
         _lib.emu_gjk_batch.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp,
                                        ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, vp, vp, vp]
         _lib.emu_gjk_batch.restype = None
+        _lib.emu_gjk_witness_batch.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp,
+                                               ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_float, vp]
+        _lib.emu_gjk_witness_batch.restype = None
         _lib.emu_supmap_check.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int64, vp]
         _lib.emu_supmap_check.restype = None
     return _lib
@@ -89,3 +92,24 @@ def relative_placements(oMg, ga, gb):
     R = np.einsum("nji,njk->nik", Ra, Rb)
     t = np.einsum("nji,nj->ni", Ra, tb - ta)
     return np.concatenate([R.reshape(-1, 9), t], axis=1)
+
+
+def gjk_witness_batch(arrays, ga, gb, T, v0, cutoff=np.inf):
+    """FP32 GJK with witness tracking on n items of the pair (ga, gb).
+
+    Returns dict(dist, hit, far, pa, pb, n): witness points / normal in geometry ga's frame."""
+    lib = load()
+    T = np.ascontiguousarray(T, dtype=np.float32).reshape(-1, 12)
+    v0 = np.ascontiguousarray(v0, dtype=np.float32).reshape(-1, 3)
+    n = len(T)
+    va, vb = padded_verts(arrays, ga), padded_verts(arrays, gb)
+    pa = np.ascontiguousarray(arrays["geom_params"][ga][:3], dtype=np.float32)
+    pb = np.ascontiguousarray(arrays["geom_params"][gb][:3], dtype=np.float32)
+    ra = float(arrays["geom_params"][ga][0]) if arrays["geom_shape"][ga] in (0, 3) else 0.0
+    rb = float(arrays["geom_params"][gb][0]) if arrays["geom_shape"][gb] in (0, 3) else 0.0
+    out = np.zeros((n, 12), dtype=np.float32)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    lib.emu_gjk_witness_batch(int(arrays["geom_shape"][ga]), p(pa), p(va), len(va) if arrays["geom_vert_cnt"][ga] else 0,
+                              int(arrays["geom_shape"][gb]), p(pb), p(vb), len(vb) if arrays["geom_vert_cnt"][gb] else 0,
+                              p(T), p(v0), n, ra, rb, float(cutoff), p(out))
+    return dict(dist=out[:, 0], hit=out[:, 1].astype(bool), far=out[:, 2].astype(bool), pa=out[:, 3:6], pb=out[:, 6:9], n=out[:, 9:12])

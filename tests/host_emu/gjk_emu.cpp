@@ -19,6 +19,7 @@ using std::min;
 
 #include "../../pyroboplan_b200/csrc/pbp_gjk.cuh"
 #include "../../pyroboplan_b200/csrc/pbp_supmap.h"
+#include "../../pyroboplan_b200/csrc/pbp_witness.cuh"
 
 static_assert(pbp::SUPMAP_KD == pbp::SUPMAP_K, "support map resolution mismatch");
 
@@ -48,6 +49,33 @@ void emu_gjk_batch(int shapeA, const float *parA, const float *vertsA, int nA, i
         hit[i] = r.hit;
         dist[i] = r.dist;
         iters[i] = r.iters;
+    }
+}
+
+// witness variant: out [n][11] = dist, hit, far, pa(3), pb(3), n(3)... packed as 12 floats (last unused)
+void emu_gjk_witness_batch(int shapeA, const float *parA, const float *vertsA, int nA, int shapeB, const float *parB,
+                           const float *vertsB, int nB, const float *T, const float *v0, int64_t n, float ra, float rb,
+                           float cutoff, float *out) {
+    pbp::ShapeRef A, B;
+    A.shape = shapeA; A.p0 = parA[0]; A.p1 = parA[1]; A.p2 = parA[2];
+    A.verts = reinterpret_cast<const float4 *>(vertsA); A.nverts = nA; A.cell_off = nullptr; A.cell_list = nullptr;
+    B.shape = shapeB; B.p0 = parB[0]; B.p1 = parB[1]; B.p2 = parB[2];
+    B.verts = reinterpret_cast<const float4 *>(vertsB); B.nverts = nB; B.cell_off = nullptr; B.cell_list = nullptr;
+    pbp::SupMap ma, mb;
+    auto make_map = [](const float *v4, int nv, pbp::SupMap &m) {
+        std::vector<float> xyz(3 * nv);
+        for (int i = 0; i < nv; i++) { xyz[3 * i] = v4[4 * i]; xyz[3 * i + 1] = v4[4 * i + 1]; xyz[3 * i + 2] = v4[4 * i + 2]; }
+        m = pbp::build_support_map(xyz.data(), nv);
+    };
+    if (shapeA == PBP_SHAPE_CONVEX) { make_map(vertsA, nA, ma); A.cell_off = ma.cell_off.data(); A.cell_list = ma.list.data(); }
+    if (shapeB == PBP_SHAPE_CONVEX) { make_map(vertsB, nB, mb); B.cell_off = mb.cell_off.data(); B.cell_list = mb.list.data(); }
+    for (int64_t i = 0; i < n; i++) {
+        const float3 v = make_float3(v0[3 * i], v0[3 * i + 1], v0[3 * i + 2]);
+        const pbp::WitnessOut w = pbp::gjk_run_witness(A, B, T + 12 * i, v, ra, rb, cutoff);
+        float *o = out + 12 * i;
+        o[0] = w.dist; o[1] = (float)w.hit; o[2] = (float)w.far;
+        o[3] = w.pa.x; o[4] = w.pa.y; o[5] = w.pa.z; o[6] = w.pb.x; o[7] = w.pb.y; o[8] = w.pb.z;
+        o[9] = w.n.x; o[10] = w.n.y; o[11] = w.n.z;
     }
 }
 
