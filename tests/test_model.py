@@ -132,3 +132,21 @@ def test_urdf_parser_matches_bundled_description():
         np.testing.assert_allclose(g.geometry.points, h.geometry.points, rtol=0, atol=1e-9)
     for a, b in zip(model.jointPlacements, ref_model.jointPlacements):
         np.testing.assert_allclose(a.homogeneous, b.homogeneous, atol=1e-15)
+
+
+def test_marble_and_sphere_panda_models():
+    """Reference models/marble.py:28-78 (10 box-marble pairs, the ground plate is not paired) and
+    models/panda.py:13-27 with use_sphere_collisions (panda_spheres.urdf: 17 link spheres)."""
+    from pyroboplan_b200.models import marble, panda
+
+    m, c, v = marble.load_models()
+    assert m.nq == 2 and [g.name for g in c.geometryObjects] == ["body_0"]
+    marble.add_object_collisions(m, c, v)
+    assert len(c.geometryObjects) == 12 and len(c.collisionPairs) == 10
+    body = c.getGeometryId("body_0")
+    assert all(p.second == body and c.geometryObjects[p.first].name.startswith("box") for p in c.collisionPairs)
+    np.testing.assert_array_equal(m.lowerPositionLimit, [0.0, 0.0])
+    np.testing.assert_array_equal(m.upperPositionLimit, [2.0, 1.0])
+    m, c, v = panda.load_models(use_sphere_collisions=True)
+    assert m.nq == 9 and len(c.geometryObjects) == 17
+    assert all(type(g.geometry).__name__ == "Sphere" for g in c.geometryObjects)

@@ -7,7 +7,7 @@ Run in the authoring container (needs /root/reference):
 
 Reads URDF + SRDF + collision STLs under
 /root/reference/src/pyroboplan/models/{panda_description,two_dof_description} and writes
-``pyroboplan_b200/models/assets/{panda,panda_spheres,two_dof}.json``: link/joint tables, the
+``pyroboplan_b200/models/assets/{panda,panda_spheres,two_dof,marble}.json``: link/joint tables, the
 unique vertices of every collision mesh (all ten Panda meshes are exactly convex: volume
 ratio 1.000, every vertex on the hull -- recorded per mesh), and the SRDF disabled pairs.
 The JSON is what travels to the GPU box; /root/reference does not exist there.
@@ -49,3 +49,4 @@ if __name__ == "__main__":
     emit("panda", "panda_description/urdf/panda.urdf", "panda_description/srdf/panda.srdf")
     emit("panda_spheres", "panda_description/urdf/panda_spheres.urdf", "panda_description/srdf/panda.srdf")
     emit("two_dof", "two_dof_description/two_dof.urdf")
+    emit("marble", "marble_description/marble.urdf")
