@@ -16,6 +16,7 @@
 #include "pbp_ik.cuh"
 #include "pbp_knn.cuh"
 #include "pbp_witness.cuh"
+#include "pbp_jit.h"
 #include "pbp_supmap.h"
 
 static_assert(pbp::SUPMAP_KD == pbp::SUPMAP_K, "support map resolution mismatch");
@@ -111,6 +112,13 @@ struct pbp_engine {
     // Two workspaces (halves of every bin + one control block each) let the *_host pipeline run
     // consecutive slices on two streams: the latency-bound tail of one slice's narrowphase
     // overlaps the next slice's broadphase.  ws selects the workspace run_round uses.
+    // model-specialised broadphase (pbp_jit.h): module + function through the driver API
+    CUmodule spec_module = nullptr;
+    CUfunction spec_bp = nullptr;
+    pbp::jit::SpecArgs spec_args{};
+    float spec_thr_padding = -1.f;
+    std::vector<float> spec_r_out, spec_r_in;      // per internal pair, for the per-call thresholds
+    std::vector<uint8_t> spec_exact;
     int ws = 0;
     bool ws_split = false;
     cudaStream_t s_comp2 = nullptr;
@@ -134,9 +142,10 @@ struct pbp_engine {
 namespace {
 
 // control block layout (uint32 words): [0, npairs) bin counts, [npairs] item-setup tile counter,
-// [npairs + 1] narrowphase chunk cursor, then four 64-bit counters at an 8-byte aligned offset
+// [npairs + 1] narrowphase chunk cursor, [npairs + 2, 2 npairs + 2) narrowphase bin counts (items the
+// item setup kept), then four 64-bit counters at an 8-byte aligned offset
 // (level total, emit cursor, select count, profiled item total).
-inline size_t ctrl_words(const pbp_engine *e) { return (size_t)e->npairs + 2; }
+inline size_t ctrl_words(const pbp_engine *e) { return 2 * (size_t)e->npairs + 2; }
 // There are two such blocks (workspaces 0 / 1, see pbp_engine::ws); the 64-bit counters live in block 0.
 inline size_t ctrl_bytes(const pbp_engine *e) { return ((ctrl_words(e) * 4 + 7) & ~(size_t)7) + 32; }
 inline uint32_t *ctrl_base(pbp_engine *e) {
@@ -145,6 +154,7 @@ inline uint32_t *ctrl_base(pbp_engine *e) {
 inline uint32_t *ctrl_counts(pbp_engine *e) { return ctrl_base(e); }
 inline uint32_t *ctrl_tile_setup(pbp_engine *e) { return ctrl_base(e) + e->npairs; }
 inline uint32_t *ctrl_chunk_np(pbp_engine *e) { return ctrl_base(e) + e->npairs + 1; }
+inline uint32_t *ctrl_counts_np(pbp_engine *e) { return ctrl_base(e) + e->npairs + 2; }
 inline unsigned long long *ctrl_u64(pbp_engine *e, int i) {
     const size_t off = (ctrl_words(e) * 4 + 7) & ~(size_t)7;
     return reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(e->d_ctrl.p) + off) + i;
@@ -153,6 +163,31 @@ inline unsigned long long *ctrl_u64(pbp_engine *e, int i) {
 inline int64_t round_cap(const pbp_engine *e) { return e->ws_split ? e->chunk / 2 : e->chunk; }
 
 inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// Driver API entry points obtained through the runtime (no link-time dependency on libcuda, so the
+// library still loads on a machine without a driver).
+struct DriverApi {
+    CUresult (*moduleLoadData)(CUmodule *, const void *) = nullptr;
+    CUresult (*moduleUnload)(CUmodule) = nullptr;
+    CUresult (*moduleGetFunction)(CUfunction *, CUmodule, const char *) = nullptr;
+    CUresult (*launchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **) = nullptr;
+    bool ok = false;
+};
+inline const DriverApi &driver_api() {
+    static DriverApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        cudaDriverEntryPointQueryResult qr;
+        auto get = [&](const char *name, void **fn) {
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess && *fn;
+        };
+        api.ok = get("cuModuleLoadData", (void **)&api.moduleLoadData) && get("cuModuleUnload", (void **)&api.moduleUnload) &&
+                 get("cuModuleGetFunction", (void **)&api.moduleGetFunction) && get("cuLaunchKernel", (void **)&api.launchKernel);
+        cudaGetLastError();
+    }
+    return api;
+}
 
 #define LAUNCH_CHECK(what)                                                                                  \
     do {                                                                                                    \
@@ -166,13 +201,34 @@ int launch_round_kernels(pbp_engine *e, const StateSource &src, int64_t n, float
                          cudaEvent_t *ev, cudaStream_t st) {
     const unsigned grid = grid_for(n, BP_THREADS);
     const bool has_sample = src.sample != nullptr;
-    if (e->bp_smem_store)
+    if (MODE == MODE_BOOL && e->spec_bp) {
+        // model-specialised broadphase: the thresholds of this call's padding ride in the kernel parameter
+        static_assert(pbp::jit::SPEC_THREADS == BP_THREADS, "block size mismatch");
+        pbp::jit::SpecArgs &a = e->spec_args;
+        a.q = src.q; a.q1 = src.q1; a.q2 = src.q2; a.group = src.group; a.frac = src.frac; a.mode = src.mode; a._pad = 0;
+        a.n_states = n; a.hit = out.hit; a.bin_state = bins.state; a.bin_count = bins.count; a.cap = bins.cap;
+        if (padding != e->spec_thr_padding) {
+            for (int p = 0; p < e->npairs; p++) {   // same float arithmetic as the generic kernel's prologue
+                const bool exact = e->spec_exact[p] != 0;
+                const float slack = exact ? 0.f : BP_SLACK;
+                const float rf = e->spec_r_out[p] + padding + slack, rs = e->spec_r_in[p] + padding - slack;
+                const float y = rs >= 0.f ? rs * rs : -1.f;
+                a.thr[p][0] = exact ? y : rf * rf;
+                a.thr[p][1] = y;
+            }
+            e->spec_thr_padding = padding;
+        }
+        void *params[] = {&a};
+        const CUresult cr = driver_api().launchKernel(e->spec_bp, grid, 1, 1, BP_THREADS, 1, 1, 0, (CUstream)st, params, nullptr);
+        if (cr != CUDA_SUCCESS) return fail(PBP_ERR_CUDA, "specialised broadphase launch failed (CUresult %d)", (int)cr);
+        e->stats.kernel_launches++;
+    } else if (e->bp_smem_store)
         k_broadphase<MODE, true><<<grid, BP_THREADS, e->smem_bp, st>>>(e->dm, src, n, padding, out, bins);
     else
         k_broadphase<MODE, false><<<grid, BP_THREADS, e->smem_bp, st>>>(e->dm, src, n, padding, out, bins);
     LAUNCH_CHECK("k_broadphase");
     if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
-    k_item_setup<MODE><<<e->is_blocks, IS_THREADS, e->smem_is, st>>>(e->dm, src, out, bins, ctrl_tile_setup(e));
+    k_item_setup<MODE><<<e->is_blocks, IS_THREADS, e->smem_is, st>>>(e->dm, src, padding, out, bins, ctrl_tile_setup(e));
     LAUNCH_CHECK("k_item_setup");
     if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
     if (e->verts_in_smem)
@@ -195,6 +251,7 @@ int run_round(pbp_engine *e, int mode, const StateSource &src, int64_t n, float 
     bins.sample = e->d_bin_sample.as<int32_t>() + ws_off;
     bins.T = e->d_bin_T.as<float>() + ws_off;
     bins.count = ctrl_counts(e);
+    bins.count_np = ctrl_counts_np(e);
     bins.cap = e->chunk;
     CUDA_TRY(cudaMemsetAsync(ctrl_base(e), 0, ctrl_words(e) * 4, st));
     int rc;
@@ -214,7 +271,7 @@ int run_round(pbp_engine *e, int mode, const StateSource &src, int64_t n, float 
     if (e->profiling) {
         CUDA_TRY(cudaEventRecord(ev[3], st));
         for (int i = 0; i < 4; i++) e->prof_events.push_back(ev[i]);
-        k_sum_counts<<<1, 256, 0, st>>>(bins.count, e->npairs, ctrl_u64(e, 3));
+        k_sum_counts<<<1, 256, 0, st>>>(bins.count_np, e->npairs, ctrl_u64(e, 3));
         e->stats.kernel_launches++;
     }
     e->stats.states += n;
@@ -231,6 +288,246 @@ int check_args(pbp_engine *e, const void *a, int64_t n) {
 }
 
 }  // namespace
+
+// Host-side compilation of a model description into the kernels' tables (no CUDA calls).
+struct HostTables {
+    std::vector<DevJoint> joints;
+    std::vector<DevGeom> geoms;
+    std::vector<BpGeom> bpgeoms;
+    std::vector<BpBox> bpboxes;
+    std::vector<float4> verts;
+    std::vector<uint16_t> sup_cells, sup_lists;
+    std::vector<int32_t> jgeoms;
+    std::vector<BpPair> bppairs;
+    std::vector<BpGroup> groups;
+    std::vector<int32_t> pair_orig;
+    std::vector<PairPath> paths;
+    std::vector<uint8_t> pathops;
+    std::vector<int32_t> order;
+    int nmoving = 0, nsave = 0;
+};
+
+static int build_host_tables(const pbp_model_desc *d, HostTables &H) {
+    // ---- joints (+ which transforms the broadphase must keep for non-adjacent children)
+    H.joints.assign(d->njoints, DevJoint{});
+    auto &joints = H.joints;
+    for (int j = 0; j < d->njoints; j++) {
+        DevJoint &J = joints[j];
+        memset(&J, 0, sizeof J);
+        memcpy(J.P, d->joint_placement + 12 * j, sizeof J.P);
+        memcpy(J.axis, d->joint_axis + 3 * j, sizeof J.axis);
+        J.parent = d->joint_parent[j];
+        J.type = d->joint_type[j];
+        J.idx_q = d->joint_idx_q[j];
+        J.axis_code = 0;
+        for (int k = 0; k < 3; k++) {
+            const float a = J.axis[k], b = J.axis[(k + 1) % 3], c = J.axis[(k + 2) % 3];
+            if (fabsf(fabsf(a) - 1.0f) < 1e-7f && b == 0.0f && c == 0.0f) J.axis_code = k + 1;
+        }
+        J.parent_slot = -1;
+        J.save_slot = -1;
+        if (j > 0 && (J.parent < 0 || J.parent >= j)) return (fail(PBP_ERR_ARG, "joint %d: parent %d not topologically ordered", j, J.parent));
+        if (j > 0 && (J.idx_q < 0 || J.idx_q >= d->nq)) return (fail(PBP_ERR_ARG, "joint %d: idx_q %d out of range", j, J.idx_q));
+        if (j > 0 && J.type != PBP_JOINT_REVOLUTE && J.type != PBP_JOINT_PRISMATIC) return (fail(PBP_ERR_ARG, "joint %d: unsupported type %d", j, J.type));
+    }
+    int nsave = 0;
+    for (int j = 1; j < d->njoints; j++) {
+        DevJoint &J = joints[j];
+        if (J.parent == 0) J.parent_slot = -2;
+        else if (J.parent == j - 1) J.parent_slot = -1;
+        else {
+            if (joints[J.parent].save_slot < 0) joints[J.parent].save_slot = nsave++;
+            J.parent_slot = joints[J.parent].save_slot;
+        }
+    }
+    if (nsave > BP_MAX_SAVES) return (fail(PBP_ERR_CAPACITY, "kinematic tree has %d branch points (max %d)", nsave, BP_MAX_SAVES));
+
+    // ---- geometries: narrowphase view, broadphase proxies, static boxes, padded vertex table
+    H.geoms.assign(std::max(d->ngeoms, 1), DevGeom{});
+    auto &geoms = H.geoms;
+    H.bpgeoms.assign(std::max(d->ngeoms, 1), BpGeom{});
+    auto &bpgeoms = H.bpgeoms;
+    auto &bpboxes = H.bpboxes;
+    auto &verts = H.verts;
+    auto &sup_cells = H.sup_cells;
+    auto &sup_lists = H.sup_lists;
+    auto &jgeoms = H.jgeoms;
+    int nmoving = 0;
+    for (int g = 0; g < d->ngeoms; g++) {
+        DevGeom &G = geoms[g];
+        BpGeom &B = bpgeoms[g];
+        memset(&G, 0, sizeof G);
+        memset(&B, 0, sizeof B);
+        G.map_off = -1;
+        G.list_off = 0;
+        memcpy(G.P, d->geom_placement + 12 * g, sizeof G.P);
+        memcpy(G.par, d->geom_params + 4 * g, sizeof G.par);
+        const float *outer = d->geom_outer + 4 * g, *inner = d->geom_inner + 4 * g;
+        for (int i = 0; i < 3; i++)
+            if (fabsf(outer[i] - inner[i]) > 1e-6f) return (fail(PBP_ERR_ARG, "geometry %d: geom_inner must share the centre of geom_outer", g));
+        if (!(inner[3] <= outer[3])) return (fail(PBP_ERR_ARG, "geometry %d: inscribed radius exceeds enclosing radius", g));
+        memcpy(G.centre, outer, sizeof G.centre);
+        G.parent = d->geom_parent[g];
+        G.shape = d->geom_shape[g];
+        if (G.parent < 0 || G.parent >= d->njoints) return (fail(PBP_ERR_ARG, "geometry %d: bad parent joint", g));
+        if (G.shape < PBP_SHAPE_SPHERE || G.shape > PBP_SHAPE_CONVEX) return (fail(PBP_ERR_ARG, "geometry %d: bad shape %d", g, G.shape));
+        G.core_radius = (G.shape == PBP_SHAPE_SPHERE || G.shape == PBP_SHAPE_CAPSULE) ? G.par[0] : 0.f;
+        // proxy centre in the parent-joint frame (= world frame for static geometries)
+        for (int i = 0; i < 3; i++) B.c[i] = G.P[3 * i] * outer[0] + G.P[3 * i + 1] * outer[1] + G.P[3 * i + 2] * outer[2] + G.P[9 + i];
+        B.r_out = outer[3];
+        B.r_in = inner[3];
+        B.slot = G.parent == 0 ? -1 : nmoving++;
+        B.box = -1;
+        if (G.parent == 0 && G.shape == PBP_SHAPE_BOX) {
+            BpBox bx;
+            memset(&bx, 0, sizeof bx);
+            memcpy(bx.R, G.P, sizeof bx.R);
+            memcpy(bx.t, G.P + 9, sizeof bx.t);
+            memcpy(bx.h, G.par, sizeof bx.h);
+            B.box = (int)bpboxes.size();
+            bpboxes.push_back(bx);
+        }
+        if (G.shape == PBP_SHAPE_CONVEX) {
+            const int off = d->geom_vert_off[g], cnt = d->geom_vert_cnt[g];
+            if (cnt < 1 || off < 0 || off + cnt > d->nverts) return (fail(PBP_ERR_ARG, "geometry %d: bad vertex range", g));
+            G.vert_off = (int)verts.size();
+            for (int i = 0; i < cnt; i++) verts.push_back(make_float4(d->verts[3 * (off + i)], d->verts[3 * (off + i) + 1], d->verts[3 * (off + i) + 2], 0.f));
+            while (verts.size() % 4) verts.push_back(verts.back());
+            G.vert_cnt = (int)verts.size() - G.vert_off;
+            // exact support map of this hull (shared by geometries with identical vertex data)
+            int same = -1;
+            for (int h = 0; h < g && same < 0; h++)
+                if (geoms[h].shape == PBP_SHAPE_CONVEX && d->geom_vert_cnt[h] == cnt &&
+                    memcmp(d->verts + 3 * d->geom_vert_off[h], d->verts + 3 * off, (size_t)cnt * 12) == 0)
+                    same = h;
+            if (same >= 0) {
+                G.map_off = geoms[same].map_off;
+                G.list_off = geoms[same].list_off;
+            } else if (cnt <= 65535) {
+                const SupMap sm = build_support_map(d->verts + 3 * off, cnt);
+                if (sm.list.size() <= 65535) {
+                    G.map_off = (int)sup_cells.size();
+                    G.list_off = (int)sup_lists.size();
+                    sup_cells.insert(sup_cells.end(), sm.cell_off.begin(), sm.cell_off.end());
+                    sup_lists.insert(sup_lists.end(), sm.list.begin(), sm.list.end());
+                }
+            }
+        }
+    }
+    while (sup_cells.empty() || sup_cells.size() % 8) sup_cells.push_back(0);
+    while (sup_lists.empty() || sup_lists.size() % 8) sup_lists.push_back(0);
+    // moving geometries grouped by parent joint (the broadphase places them right after that joint)
+    for (int j = 1; j < d->njoints; j++) {
+        joints[j].geom_begin = (int)jgeoms.size();
+        for (int g = 0; g < d->ngeoms; g++)
+            if (geoms[g].parent == j) jgeoms.push_back(g);
+        joints[j].geom_end = (int)jgeoms.size();
+    }
+    if (verts.empty()) verts.push_back(make_float4(0, 0, 0, 0));
+    if (bpboxes.empty()) bpboxes.push_back(BpBox{});
+    if (jgeoms.empty()) jgeoms.push_back(0);
+    H.nmoving = nmoving;
+    H.nsave = nsave;
+
+    // ---- pairs: internal order (moving-moving first, then one contiguous group per static
+    //      geometry), broadphase recipe, joint path for the item setup, bin order
+    const int np1 = std::max(d->npairs, 1);
+    struct PairKey { int cls, sidx, orig; };
+    std::vector<PairKey> keys(d->npairs);
+    for (int p = 0; p < d->npairs; p++) {
+        const int a = d->pairs[2 * p], b = d->pairs[2 * p + 1];
+        if (a < 0 || b < 0 || a >= d->ngeoms || b >= d->ngeoms || a == b) return (fail(PBP_ERR_ARG, "pair %d: bad geometry ids", p));
+        const bool sa = bpgeoms[a].slot < 0, sb = bpgeoms[b].slot < 0;
+        PairKey k{GRP_GENERIC, 0, p};
+        if (!sa && !sb) k = PairKey{GRP_MOVING, 0, p};
+        else if (sa != sb) {
+            const int st = sa ? a : b;
+            if (bpgeoms[st].box >= 0) k = PairKey{GRP_STATIC_BOX, bpgeoms[st].box, p};
+            else k = PairKey{GRP_STATIC_POINT, st, p};
+        }
+        keys[p] = k;
+    }
+    std::stable_sort(keys.begin(), keys.end(), [](const PairKey &x, const PairKey &y) {
+        return x.cls != y.cls ? x.cls < y.cls : x.sidx < y.sidx;
+    });
+    H.bppairs.assign(np1, BpPair{});
+    auto &bppairs = H.bppairs;
+    auto &groups = H.groups;
+    H.pair_orig.assign(np1, 0);
+    auto &pair_orig = H.pair_orig;
+    H.paths.assign(np1, PairPath{});
+    auto &paths = H.paths;
+    auto &pathops = H.pathops;
+    H.order.assign(np1, 0);
+    auto &order = H.order;
+    std::vector<long> cost(np1, 0);
+    auto chain_to_root = [&](int j) {  // joints from the root down to j (empty for the universe)
+        std::vector<int> c;
+        for (; j > 0; j = joints[j].parent) c.push_back(j);
+        std::reverse(c.begin(), c.end());
+        return c;
+    };
+    for (int p = 0; p < d->npairs; p++) {
+        const PairKey &key = keys[p];
+        const int a = d->pairs[2 * key.orig], b = d->pairs[2 * key.orig + 1];
+        pair_orig[p] = key.orig;
+        if (groups.empty() || groups.back().cls != key.cls || (key.cls != GRP_MOVING && key.cls != GRP_GENERIC && groups.back().sidx != key.sidx))
+            groups.push_back(BpGroup{key.cls, key.sidx, p, p});
+        groups.back().end = p + 1;
+        BpPair &P = bppairs[p];
+        memset(&P, 0, sizeof P);
+        P.a = (uint8_t)a;
+        P.b = (uint8_t)b;
+        P.slot_a = (int16_t)bpgeoms[a].slot;
+        P.slot_b = (int16_t)bpgeoms[b].slot;
+        const int sha = geoms[a].shape, shb = geoms[b].shape;
+        if (sha == PBP_SHAPE_SPHERE && shb == PBP_SHAPE_SPHERE) {
+            P.kind = BP_EXACT_SPHERES;
+            P.r_out = P.r_in = geoms[a].par[0] + geoms[b].par[0];
+        } else if (bpgeoms[a].box >= 0) {
+            P.kind = BP_BOX_A;
+            P.r_out = bpgeoms[b].r_out;
+            P.r_in = bpgeoms[b].r_in;
+        } else if (bpgeoms[b].box >= 0) {
+            P.kind = BP_BOX_B;
+            P.r_out = bpgeoms[a].r_out;
+            P.r_in = bpgeoms[a].r_in;
+        } else {
+            P.kind = BP_SPHERES;
+            P.r_out = bpgeoms[a].r_out + bpgeoms[b].r_out;
+            P.r_in = bpgeoms[a].r_in + bpgeoms[b].r_in;
+        }
+        const std::vector<int> ca = chain_to_root(geoms[a].parent), cb = chain_to_root(geoms[b].parent);
+        size_t common = 0;
+        while (common < ca.size() && common < cb.size() && ca[common] == cb[common]) common++;
+        paths[p].off = (int32_t)pathops.size();
+        paths[p].n_trunk = (uint8_t)common;
+        paths[p].n_a = (uint8_t)(ca.size() - common);
+        paths[p].n_b = (uint8_t)(cb.size() - common);
+        for (size_t i = 0; i < ca.size(); i++) pathops.push_back((uint8_t)ca[i]);
+        for (size_t i = common; i < cb.size(); i++) pathops.push_back((uint8_t)cb[i]);
+        cost[p] = 8 + geoms[a].vert_cnt + geoms[b].vert_cnt;
+        order[p] = p;
+    }
+    if (groups.empty()) groups.push_back(BpGroup{GRP_GENERIC, 0, 0, 0});
+    if (pathops.empty()) pathops.push_back(0);
+    while (pathops.size() % 4) pathops.push_back(0);
+    std::stable_sort(order.begin(), order.begin() + d->npairs, [&](int x, int y) { return cost[x] > cost[y]; });
+
+    return 0;
+}
+
+// CUDA source of the model-specialised broadphase (empty string when the model does not qualify).
+static std::string specialised_broadphase_source(const pbp_model_desc *d, const HostTables &H) {
+    if (d->npairs < 1 || d->npairs > pbp::jit::SPEC_MAX_PAIRS || d->njoints > 48 || d->ngeoms > 96) return std::string();
+    std::vector<int32_t> gparent(std::max(d->ngeoms, 1), 0);
+    for (int g = 0; g < d->ngeoms; g++) gparent[g] = H.geoms[g].parent;
+    pbp::jit::Input in;
+    in.nq = d->nq; in.njoints = d->njoints; in.ngeoms = d->ngeoms; in.npairs = d->npairs;
+    in.joints = H.joints.data(); in.bpgeoms = H.bpgeoms.data(); in.geom_parent = gparent.data();
+    in.bpboxes = H.bpboxes.data(); in.bppairs = H.bppairs.data(); in.groups = H.groups.data(); in.ngroups = (int)H.groups.size();
+    return pbp::jit::generate_broadphase(in);
+}
 
 // ==========================================================================================
 extern "C" {
@@ -293,6 +590,7 @@ void pbp_engine_destroy(pbp_engine *e) {
     for (DeviceBuffer *b : bufs) b->release();
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     e->h_io_hit.release(); e->h_io_f32.release(); e->h_io_i32.release();
+    if (e->spec_module && driver_api().ok) driver_api().moduleUnload(e->spec_module);
     for (cudaEvent_t ev : e->io_events) cudaEventDestroy(ev);
     if (e->s_copy) cudaStreamDestroy(e->s_copy);
     if (e->s_comp) cudaStreamDestroy(e->s_comp);
@@ -340,203 +638,18 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
 
     auto bail = [&](int code) { pbp_engine_destroy(e); return code; };
 
-    // ---- joints (+ which transforms the broadphase must keep for non-adjacent children)
-    std::vector<DevJoint> joints(d->njoints);
-    for (int j = 0; j < d->njoints; j++) {
-        DevJoint &J = joints[j];
-        memset(&J, 0, sizeof J);
-        memcpy(J.P, d->joint_placement + 12 * j, sizeof J.P);
-        memcpy(J.axis, d->joint_axis + 3 * j, sizeof J.axis);
-        J.parent = d->joint_parent[j];
-        J.type = d->joint_type[j];
-        J.idx_q = d->joint_idx_q[j];
-        J.axis_code = 0;
-        for (int k = 0; k < 3; k++) {
-            const float a = J.axis[k], b = J.axis[(k + 1) % 3], c = J.axis[(k + 2) % 3];
-            if (fabsf(fabsf(a) - 1.0f) < 1e-7f && b == 0.0f && c == 0.0f) J.axis_code = k + 1;
-        }
-        J.parent_slot = -1;
-        J.save_slot = -1;
-        if (j > 0 && (J.parent < 0 || J.parent >= j)) return bail(fail(PBP_ERR_ARG, "joint %d: parent %d not topologically ordered", j, J.parent));
-        if (j > 0 && (J.idx_q < 0 || J.idx_q >= d->nq)) return bail(fail(PBP_ERR_ARG, "joint %d: idx_q %d out of range", j, J.idx_q));
-        if (j > 0 && J.type != PBP_JOINT_REVOLUTE && J.type != PBP_JOINT_PRISMATIC) return bail(fail(PBP_ERR_ARG, "joint %d: unsupported type %d", j, J.type));
+    HostTables H;
+    {
+        const int hrc = build_host_tables(d, H);
+        if (hrc) return bail(hrc);
     }
-    int nsave = 0;
-    for (int j = 1; j < d->njoints; j++) {
-        DevJoint &J = joints[j];
-        if (J.parent == 0) J.parent_slot = -2;
-        else if (J.parent == j - 1) J.parent_slot = -1;
-        else {
-            if (joints[J.parent].save_slot < 0) joints[J.parent].save_slot = nsave++;
-            J.parent_slot = joints[J.parent].save_slot;
-        }
-    }
-    if (nsave > BP_MAX_SAVES) return bail(fail(PBP_ERR_CAPACITY, "kinematic tree has %d branch points (max %d)", nsave, BP_MAX_SAVES));
-
-    // ---- geometries: narrowphase view, broadphase proxies, static boxes, padded vertex table
-    std::vector<DevGeom> geoms(std::max(d->ngeoms, 1));
-    std::vector<BpGeom> bpgeoms(std::max(d->ngeoms, 1));
-    std::vector<BpBox> bpboxes;
-    std::vector<float4> verts;
-    std::vector<uint16_t> sup_cells, sup_lists;
-    std::vector<int32_t> jgeoms;
-    int nmoving = 0;
-    for (int g = 0; g < d->ngeoms; g++) {
-        DevGeom &G = geoms[g];
-        BpGeom &B = bpgeoms[g];
-        memset(&G, 0, sizeof G);
-        memset(&B, 0, sizeof B);
-        G.map_off = -1;
-        G.list_off = 0;
-        memcpy(G.P, d->geom_placement + 12 * g, sizeof G.P);
-        memcpy(G.par, d->geom_params + 4 * g, sizeof G.par);
-        const float *outer = d->geom_outer + 4 * g, *inner = d->geom_inner + 4 * g;
-        for (int i = 0; i < 3; i++)
-            if (fabsf(outer[i] - inner[i]) > 1e-6f) return bail(fail(PBP_ERR_ARG, "geometry %d: geom_inner must share the centre of geom_outer", g));
-        if (!(inner[3] <= outer[3])) return bail(fail(PBP_ERR_ARG, "geometry %d: inscribed radius exceeds enclosing radius", g));
-        memcpy(G.centre, outer, sizeof G.centre);
-        G.parent = d->geom_parent[g];
-        G.shape = d->geom_shape[g];
-        if (G.parent < 0 || G.parent >= d->njoints) return bail(fail(PBP_ERR_ARG, "geometry %d: bad parent joint", g));
-        if (G.shape < PBP_SHAPE_SPHERE || G.shape > PBP_SHAPE_CONVEX) return bail(fail(PBP_ERR_ARG, "geometry %d: bad shape %d", g, G.shape));
-        G.core_radius = (G.shape == PBP_SHAPE_SPHERE || G.shape == PBP_SHAPE_CAPSULE) ? G.par[0] : 0.f;
-        // proxy centre in the parent-joint frame (= world frame for static geometries)
-        for (int i = 0; i < 3; i++) B.c[i] = G.P[3 * i] * outer[0] + G.P[3 * i + 1] * outer[1] + G.P[3 * i + 2] * outer[2] + G.P[9 + i];
-        B.r_out = outer[3];
-        B.r_in = inner[3];
-        B.slot = G.parent == 0 ? -1 : nmoving++;
-        B.box = -1;
-        if (G.parent == 0 && G.shape == PBP_SHAPE_BOX) {
-            BpBox bx;
-            memset(&bx, 0, sizeof bx);
-            memcpy(bx.R, G.P, sizeof bx.R);
-            memcpy(bx.t, G.P + 9, sizeof bx.t);
-            memcpy(bx.h, G.par, sizeof bx.h);
-            B.box = (int)bpboxes.size();
-            bpboxes.push_back(bx);
-        }
-        if (G.shape == PBP_SHAPE_CONVEX) {
-            const int off = d->geom_vert_off[g], cnt = d->geom_vert_cnt[g];
-            if (cnt < 1 || off < 0 || off + cnt > d->nverts) return bail(fail(PBP_ERR_ARG, "geometry %d: bad vertex range", g));
-            G.vert_off = (int)verts.size();
-            for (int i = 0; i < cnt; i++) verts.push_back(make_float4(d->verts[3 * (off + i)], d->verts[3 * (off + i) + 1], d->verts[3 * (off + i) + 2], 0.f));
-            while (verts.size() % 4) verts.push_back(verts.back());
-            G.vert_cnt = (int)verts.size() - G.vert_off;
-            // exact support map of this hull (shared by geometries with identical vertex data)
-            int same = -1;
-            for (int h = 0; h < g && same < 0; h++)
-                if (geoms[h].shape == PBP_SHAPE_CONVEX && d->geom_vert_cnt[h] == cnt &&
-                    memcmp(d->verts + 3 * d->geom_vert_off[h], d->verts + 3 * off, (size_t)cnt * 12) == 0)
-                    same = h;
-            if (same >= 0) {
-                G.map_off = geoms[same].map_off;
-                G.list_off = geoms[same].list_off;
-            } else if (cnt <= 65535) {
-                const SupMap sm = build_support_map(d->verts + 3 * off, cnt);
-                if (sm.list.size() <= 65535) {
-                    G.map_off = (int)sup_cells.size();
-                    G.list_off = (int)sup_lists.size();
-                    sup_cells.insert(sup_cells.end(), sm.cell_off.begin(), sm.cell_off.end());
-                    sup_lists.insert(sup_lists.end(), sm.list.begin(), sm.list.end());
-                }
-            }
-        }
-    }
-    while (sup_cells.empty() || sup_cells.size() % 8) sup_cells.push_back(0);
-    while (sup_lists.empty() || sup_lists.size() % 8) sup_lists.push_back(0);
-    // moving geometries grouped by parent joint (the broadphase places them right after that joint)
-    for (int j = 1; j < d->njoints; j++) {
-        joints[j].geom_begin = (int)jgeoms.size();
-        for (int g = 0; g < d->ngeoms; g++)
-            if (geoms[g].parent == j) jgeoms.push_back(g);
-        joints[j].geom_end = (int)jgeoms.size();
-    }
-    if (verts.empty()) verts.push_back(make_float4(0, 0, 0, 0));
-    if (bpboxes.empty()) bpboxes.push_back(BpBox{});
-    if (jgeoms.empty()) jgeoms.push_back(0);
+    auto &joints = H.joints; auto &geoms = H.geoms; auto &bpgeoms = H.bpgeoms; auto &bpboxes = H.bpboxes; auto &verts = H.verts;
+    auto &sup_cells = H.sup_cells; auto &sup_lists = H.sup_lists; auto &jgeoms = H.jgeoms; auto &bppairs = H.bppairs;
+    auto &groups = H.groups; auto &pair_orig = H.pair_orig; auto &paths = H.paths; auto &pathops = H.pathops; auto &order = H.order;
+    const int nmoving = H.nmoving, nsave = H.nsave;
+    const int np1 = std::max(d->npairs, 1);
     e->nmoving = nmoving;
     e->nverts_padded = (int)verts.size();
-
-    // ---- pairs: internal order (moving-moving first, then one contiguous group per static
-    //      geometry), broadphase recipe, joint path for the item setup, bin order
-    const int np1 = std::max(d->npairs, 1);
-    struct PairKey { int cls, sidx, orig; };
-    std::vector<PairKey> keys(d->npairs);
-    for (int p = 0; p < d->npairs; p++) {
-        const int a = d->pairs[2 * p], b = d->pairs[2 * p + 1];
-        if (a < 0 || b < 0 || a >= d->ngeoms || b >= d->ngeoms || a == b) return bail(fail(PBP_ERR_ARG, "pair %d: bad geometry ids", p));
-        const bool sa = bpgeoms[a].slot < 0, sb = bpgeoms[b].slot < 0;
-        PairKey k{GRP_GENERIC, 0, p};
-        if (!sa && !sb) k = PairKey{GRP_MOVING, 0, p};
-        else if (sa != sb) {
-            const int st = sa ? a : b;
-            if (bpgeoms[st].box >= 0) k = PairKey{GRP_STATIC_BOX, bpgeoms[st].box, p};
-            else k = PairKey{GRP_STATIC_POINT, st, p};
-        }
-        keys[p] = k;
-    }
-    std::stable_sort(keys.begin(), keys.end(), [](const PairKey &x, const PairKey &y) {
-        return x.cls != y.cls ? x.cls < y.cls : x.sidx < y.sidx;
-    });
-    std::vector<BpPair> bppairs(np1);
-    std::vector<BpGroup> groups;
-    std::vector<int32_t> pair_orig(np1, 0);
-    std::vector<PairPath> paths(np1);
-    std::vector<uint8_t> pathops;
-    std::vector<int32_t> order(np1, 0);
-    std::vector<long> cost(np1, 0);
-    auto chain_to_root = [&](int j) {  // joints from the root down to j (empty for the universe)
-        std::vector<int> c;
-        for (; j > 0; j = joints[j].parent) c.push_back(j);
-        std::reverse(c.begin(), c.end());
-        return c;
-    };
-    for (int p = 0; p < d->npairs; p++) {
-        const PairKey &key = keys[p];
-        const int a = d->pairs[2 * key.orig], b = d->pairs[2 * key.orig + 1];
-        pair_orig[p] = key.orig;
-        if (groups.empty() || groups.back().cls != key.cls || (key.cls != GRP_MOVING && key.cls != GRP_GENERIC && groups.back().sidx != key.sidx))
-            groups.push_back(BpGroup{key.cls, key.sidx, p, p});
-        groups.back().end = p + 1;
-        BpPair &P = bppairs[p];
-        memset(&P, 0, sizeof P);
-        P.a = (uint8_t)a;
-        P.b = (uint8_t)b;
-        P.slot_a = (int16_t)bpgeoms[a].slot;
-        P.slot_b = (int16_t)bpgeoms[b].slot;
-        const int sha = geoms[a].shape, shb = geoms[b].shape;
-        if (sha == PBP_SHAPE_SPHERE && shb == PBP_SHAPE_SPHERE) {
-            P.kind = BP_EXACT_SPHERES;
-            P.r_out = P.r_in = geoms[a].par[0] + geoms[b].par[0];
-        } else if (bpgeoms[a].box >= 0) {
-            P.kind = BP_BOX_A;
-            P.r_out = bpgeoms[b].r_out;
-            P.r_in = bpgeoms[b].r_in;
-        } else if (bpgeoms[b].box >= 0) {
-            P.kind = BP_BOX_B;
-            P.r_out = bpgeoms[a].r_out;
-            P.r_in = bpgeoms[a].r_in;
-        } else {
-            P.kind = BP_SPHERES;
-            P.r_out = bpgeoms[a].r_out + bpgeoms[b].r_out;
-            P.r_in = bpgeoms[a].r_in + bpgeoms[b].r_in;
-        }
-        const std::vector<int> ca = chain_to_root(geoms[a].parent), cb = chain_to_root(geoms[b].parent);
-        size_t common = 0;
-        while (common < ca.size() && common < cb.size() && ca[common] == cb[common]) common++;
-        paths[p].off = (int32_t)pathops.size();
-        paths[p].n_trunk = (uint8_t)common;
-        paths[p].n_a = (uint8_t)(ca.size() - common);
-        paths[p].n_b = (uint8_t)(cb.size() - common);
-        for (size_t i = 0; i < ca.size(); i++) pathops.push_back((uint8_t)ca[i]);
-        for (size_t i = common; i < cb.size(); i++) pathops.push_back((uint8_t)cb[i]);
-        cost[p] = 8 + geoms[a].vert_cnt + geoms[b].vert_cnt;
-        order[p] = p;
-    }
-    if (groups.empty()) groups.push_back(BpGroup{GRP_GENERIC, 0, 0, 0});
-    if (pathops.empty()) pathops.push_back(0);
-    while (pathops.size() % 4) pathops.push_back(0);
-    std::stable_sort(order.begin(), order.begin() + d->npairs, [&](int x, int y) { return cost[x] > cost[y]; });
 
     auto upload = [&](DeviceBuffer &buf, const void *src, size_t bytes) -> int {
         int rc = buf.ensure(bytes);
@@ -648,6 +761,28 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     e->np_blocks = e->num_sms * std::max(occ, 1);
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_item_setup<MODE_BOOL>, IS_THREADS, e->smem_is));
     e->is_blocks = e->num_sms * std::max(occ, 1);
+
+    // ---- model-specialised broadphase (optional: any failure leaves the generic kernel in charge)
+    if (!getenv("PBP_NO_JIT") && driver_api().ok) {
+        const std::string src_text = specialised_broadphase_source(d, H);
+        if (!src_text.empty()) {
+            std::vector<char> cubin;
+            std::string log;
+            if (pbp::jit::compile(src_text, prop.major, prop.minor, cubin, log) == 0 &&
+                driver_api().moduleLoadData(&e->spec_module, cubin.data()) == CUDA_SUCCESS &&
+                driver_api().moduleGetFunction(&e->spec_bp, e->spec_module, "k_bp_spec") == CUDA_SUCCESS) {
+                e->spec_r_out.resize(np1); e->spec_r_in.resize(np1); e->spec_exact.resize(np1);
+                for (int p = 0; p < d->npairs; p++) {
+                    e->spec_r_out[p] = bppairs[p].r_out;
+                    e->spec_r_in[p] = bppairs[p].r_in;
+                    e->spec_exact[p] = bppairs[p].kind == BP_EXACT_SPHERES;
+                }
+            } else {
+                e->spec_bp = nullptr;
+                if (getenv("PBP_JIT_VERBOSE")) fprintf(stderr, "pbp: specialised broadphase unavailable: %s\n", log.c_str());
+            }
+        }
+    }
 
     // ---- bins: one slot per (state of a chunk, pair)
     const size_t item_bytes = 4 + 4 + 4 + 48;
@@ -1302,5 +1437,39 @@ extern "C" int pbp_collision_nullspace(pbp_engine *e, const float *q_dev, int64_
                                                            e->d_ws_dist.as<float>(), e->d_ws_p1.as<float>(), e->d_ws_p2.as<float>(),
                                                            e->d_ws_nrm.as<float>(), n, dist_padding, gain, component_dev);
     LAUNCH_CHECK("k_collision_nullspace");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// JIT introspection (tests, tooling): generated source / offline NVRTC build, no device needed
+// ------------------------------------------------------------------------------------------
+extern "C" int pbp_jit_broadphase_source(const pbp_model_desc *d, char *buf, size_t cap, size_t *needed) {
+    if (!d || !needed) return fail(PBP_ERR_ARG, "NULL argument");
+    HostTables H;
+    int rc = build_host_tables(d, H);
+    if (rc) return rc;
+    const std::string src_text = specialised_broadphase_source(d, H);
+    *needed = src_text.size() + 1;
+    if (buf && cap >= *needed) memcpy(buf, src_text.c_str(), *needed);
+    return 0;
+}
+
+extern "C" int pbp_jit_compile_check(const pbp_model_desc *d, int cc_major, int cc_minor, size_t *cubin_bytes, char *log_buf, size_t log_cap) {
+    if (!d || !cubin_bytes) return fail(PBP_ERR_ARG, "NULL argument");
+    HostTables H;
+    int rc = build_host_tables(d, H);
+    if (rc) return rc;
+    const std::string src_text = specialised_broadphase_source(d, H);
+    if (src_text.empty()) return fail(PBP_ERR_CAPACITY, "model does not qualify for the specialised broadphase");
+    std::vector<char> cubin;
+    std::string log;
+    const int crc = pbp::jit::compile(src_text, cc_major, cc_minor, cubin, log);
+    if (log_buf && log_cap) { strncpy(log_buf, log.c_str(), log_cap - 1); log_buf[log_cap - 1] = 0; }
+    if (crc) return fail(PBP_ERR_CUDA, "NVRTC failed: %s", log.c_str());
+    *cubin_bytes = cubin.size();
+    if (const char *dump = getenv("PBP_JIT_DUMP_CUBIN")) {
+        FILE *f = fopen(dump, "wb");
+        if (f) { fwrite(cubin.data(), 1, cubin.size(), f); fclose(f); }
+    }
     return 0;
 }

@@ -45,7 +45,8 @@ struct Bins {
     int32_t *group;      // [npairs*cap] written by the item setup: output group, -1 = dropped
     int32_t *sample;     // [npairs*cap] (only when the source carries sample ids)
     float *T;            // [12][npairs*cap] relative placement of b in a's frame
-    uint32_t *count;     // [npairs]
+    uint32_t *count;     // [npairs] items appended by the broadphase
+    uint32_t *count_np;  // [npairs] items the item setup kept for the narrowphase (compacted to the bin's front)
     int64_t cap;
 };
 
@@ -406,7 +407,7 @@ __device__ __forceinline__ bool next_tile(uint32_t *tile_counter, const uint32_t
 // ------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(IS_THREADS)
-k_item_setup(DevModel M, StateSource src, Outputs out, Bins bins, uint32_t *tile_counter) {
+k_item_setup(DevModel M, StateSource src, float padding, Outputs out, Bins bins, uint32_t *tile_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *ptr = smem_raw;
     DevJoint *sj = reinterpret_cast<DevJoint *>(ptr);    ptr += align16((size_t)M.njoints * sizeof(DevJoint));
@@ -426,6 +427,7 @@ k_item_setup(DevModel M, StateSource src, Outputs out, Bins bins, uint32_t *tile
     __syncthreads();
 
     const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t stride = (int64_t)M.npairs * bins.cap;
     int p;
     uint32_t begin, end;
@@ -434,54 +436,89 @@ k_item_setup(DevModel M, StateSource src, Outputs out, Bins bins, uint32_t *tile
         const uint8_t *ops = M.path_ops + path.off;   // tiny, L1/L2 resident, warp-uniform addresses
         const DevGeom &GA = sg[sp[p].a];
         const DevGeom &GB = sg[sp[p].b];
-        for (uint32_t idx = begin + lane; idx < end; idx += 32) {
-            const int64_t slot = (int64_t)p * bins.cap + idx;
-            const int32_t state = bins.state[slot];
-            const int32_t group = src.group ? src.group[state] : state;
-            if (MODE == MODE_BOOL && out.hit[group]) {  // the broadphase already decided this group
-                bins.group[slot] = -1;
-                continue;
+        // shapes of the pair (hull tables read through L1: warp-uniform base addresses)
+        ShapeRef A, B;
+        A.shape = GA.shape; A.p0 = GA.par[0]; A.p1 = GA.par[1]; A.p2 = GA.par[2];
+        A.verts = M.verts + GA.vert_off; A.nverts = GA.vert_cnt;
+        A.cell_off = GA.map_off >= 0 ? M.sup_cells + GA.map_off : nullptr; A.cell_list = M.sup_lists + GA.list_off;
+        B.shape = GB.shape; B.p0 = GB.par[0]; B.p1 = GB.par[1]; B.p2 = GB.par[2];
+        B.verts = M.verts + GB.vert_off; B.nverts = GB.vert_cnt;
+        B.cell_off = GB.map_off >= 0 ? M.sup_cells + GB.map_off : nullptr; B.cell_list = M.sup_lists + GB.list_off;
+        const float radii = GA.core_radius + GB.core_radius;
+        for (uint32_t base = begin; base < end; base += 32) {
+            const uint32_t idx = base + lane;
+            bool keep = idx < end;
+            int32_t state = 0, group = 0;
+            float R[12];
+            if (keep) {
+                state = bins.state[(int64_t)p * bins.cap + idx];
+                group = src.group ? src.group[state] : state;
+                if (MODE == MODE_BOOL && out.hit[group]) keep = false;   // the broadphase already decided this group
             }
-            bins.group[slot] = group;
-            if (src.sample) bins.sample[slot] = src.sample[state];
-            // joint value of this state
-            auto qval = [&](int k) {
-                if (src.mode == 0) return __ldg(src.q + (int64_t)state * M.nq + k);
-                const float f = src.frac[state];
-                const float qa = __ldg(src.q1 + (int64_t)group * M.nq + k), qb = __ldg(src.q2 + (int64_t)group * M.nq + k);
-                return fmaf(f, qb - qa, qa);
-            };
-            float cur[12], lca[12], TA[12], nxt[12];
-            se3_identity(cur);
-            int o = 0;
-            for (int i = 0; i < path.n_trunk; i++, o++) {
-                const DevJoint &J = sj[ops[o]];
-                joint_transform(J, cur, qval(J.idx_q), nxt);
+            if (keep) {
+                // joint value of this state
+                auto qval = [&](int k) {
+                    if (src.mode == 0) return __ldg(src.q + (int64_t)state * M.nq + k);
+                    const float f = src.frac[state];
+                    const float qa = __ldg(src.q1 + (int64_t)group * M.nq + k), qb = __ldg(src.q2 + (int64_t)group * M.nq + k);
+                    return fmaf(f, qb - qa, qa);
+                };
+                float cur[12], lca[12], TA[12], nxt[12];
+                se3_identity(cur);
+                int o = 0;
+                for (int i = 0; i < path.n_trunk; i++, o++) {
+                    const DevJoint &J = sj[ops[o]];
+                    joint_transform(J, cur, qval(J.idx_q), nxt);
 #pragma unroll
-                for (int k = 0; k < 12; k++) cur[k] = nxt[k];
+                    for (int k = 0; k < 12; k++) cur[k] = nxt[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 12; k++) lca[k] = cur[k];
+                for (int i = 0; i < path.n_a; i++, o++) {
+                    const DevJoint &J = sj[ops[o]];
+                    joint_transform(J, cur, qval(J.idx_q), nxt);
+#pragma unroll
+                    for (int k = 0; k < 12; k++) cur[k] = nxt[k];
+                }
+                se3_mul(cur, GA.P, TA);   // oMg[a]
+#pragma unroll
+                for (int k = 0; k < 12; k++) cur[k] = lca[k];
+                for (int i = 0; i < path.n_b; i++, o++) {
+                    const DevJoint &J = sj[ops[o]];
+                    joint_transform(J, cur, qval(J.idx_q), nxt);
+#pragma unroll
+                    for (int k = 0; k < 12; k++) cur[k] = nxt[k];
+                }
+                float TB[12];
+                se3_mul(cur, GB.P, TB);   // oMg[b]
+                se3_inv_mul(TA, TB, R);
+                // First GJK iteration, here where every lane of the warp is busy with the same pair:
+                // about two thirds of the items are already separated along the line between the
+                // proxy centres and never reach the (divergent) narrowphase.  Same arithmetic as the
+                // narrowphase's own first trip, so the decision is the one it would have taken.
+                const float3 cb = se3_act(R, GB.centre[0], GB.centre[1], GB.centre[2]);
+                GjkState gs;
+                GjkOut go;
+                gjk_init(gs, make_float3(GA.centre[0] - cb.x, GA.centre[1] - cb.y, GA.centre[2] - cb.z));
+                const float margin = padding + radii;
+                const float bound = MODE == MODE_DIST ? out.min_dist[group] + radii : 0.f;
+                const bool finished = (MODE == MODE_DIST) ? gjk_support_phase<true>(A, B, R, gs, margin, bound, go)
+                                                          : gjk_support_phase<false>(A, B, R, gs, margin, 0.f, go);
+                if (finished) keep = false;   // at n == 0 the only exit is "certainly farther than the cut"
             }
+            // compact the survivors to the front of the bin (warp-aggregated slot reservation)
+            const unsigned km = __ballot_sync(0xffffffffu, keep);
+            if (km == 0u) continue;
+            uint32_t first = 0;
+            if (lane == 0) first = atomicAdd(bins.count_np + p, (uint32_t)__popc(km));
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if (keep) {
+                const int64_t slot = (int64_t)p * bins.cap + first + __popc(km & lt_mask);
+                bins.group[slot] = group;
+                if (src.sample) bins.sample[slot] = src.sample[state];
 #pragma unroll
-            for (int k = 0; k < 12; k++) lca[k] = cur[k];
-            for (int i = 0; i < path.n_a; i++, o++) {
-                const DevJoint &J = sj[ops[o]];
-                joint_transform(J, cur, qval(J.idx_q), nxt);
-#pragma unroll
-                for (int k = 0; k < 12; k++) cur[k] = nxt[k];
+                for (int k = 0; k < 12; k++) bins.T[k * stride + slot] = R[k];
             }
-            se3_mul(cur, GA.P, TA);   // oMg[a]
-#pragma unroll
-            for (int k = 0; k < 12; k++) cur[k] = lca[k];
-            for (int i = 0; i < path.n_b; i++, o++) {
-                const DevJoint &J = sj[ops[o]];
-                joint_transform(J, cur, qval(J.idx_q), nxt);
-#pragma unroll
-                for (int k = 0; k < 12; k++) cur[k] = nxt[k];
-            }
-            float TB[12], R[12];
-            se3_mul(cur, GB.P, TB);   // oMg[b]
-            se3_inv_mul(TA, TB, R);
-#pragma unroll
-            for (int k = 0; k < 12; k++) bins.T[k * stride + slot] = R[k];
         }
     }
 }
@@ -524,7 +561,7 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
         uint32_t run = 0;
         for (int k0 = 0; k0 < M.npairs; k0 += 32) {
             const int k = k0 + threadIdx.x;
-            const uint32_t t = k < M.npairs ? bins.count[order[k]] : 0u;
+            const uint32_t t = k < M.npairs ? bins.count_np[order[k]] : 0u;
             uint32_t inc = t;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
