@@ -129,8 +129,9 @@ struct pbp_engine {
     DeviceBuffer d_ws_oMi, d_ws_oMg, d_ws_dist, d_ws_p1, d_ws_p2, d_ws_nrm, d_pairs_orig;   // distance / witness scratch
     pbp::IkTables ik_cached{}, ik_build{};
     bool ik_cached_valid = false;
-    size_t smem_bp = 0, smem_is = 0, smem_np = 0, smem_fk = 0;
-    int np_blocks = 0, is_blocks = 0;
+    size_t smem_bp = 0, smem_is = 0, smem_np = 0, smem_fk = 0, smem_np_pool = 0;
+    int np_blocks = 0, is_blocks = 0, np_pool_blocks = 0;
+    bool np_pool = false;    // block-cooperative narrowphase (k_narrowphase_pool)
     pbp_stats stats{};
     // optional per-kernel timing
     bool profiling = false;
@@ -231,7 +232,9 @@ int launch_round_kernels(pbp_engine *e, const StateSource &src, int64_t n, float
     k_item_setup<MODE><<<e->is_blocks, IS_THREADS, e->smem_is, st>>>(e->dm, src, padding, out, bins, ctrl_tile_setup(e));
     LAUNCH_CHECK("k_item_setup");
     if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
-    if (e->verts_in_smem)
+    if (e->np_pool)
+        k_narrowphase_pool<MODE><<<e->np_pool_blocks, NP_THREADS, e->smem_np_pool, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
+    else if (e->verts_in_smem)
         k_narrowphase<MODE, true><<<e->np_blocks, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
     else
         k_narrowphase<MODE, false><<<e->np_blocks, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
@@ -753,6 +756,20 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     SET_SMEM((k_narrowphase<MODE_DIST, false>));
     SET_SMEM(k_fk_output);
 #undef SET_SMEM
+    // (this kernel also has a few static __shared__ words: leave room for them under the opt-in cap)
+#define SET_SMEM_POOL(kern) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_optin - 1024))
+    SET_SMEM_POOL((k_narrowphase_pool<MODE_BOOL>));
+    SET_SMEM_POOL((k_narrowphase_pool<MODE_BOOL_ALL>));
+    SET_SMEM_POOL((k_narrowphase_pool<MODE_DIST>));
+#undef SET_SMEM_POOL
+    e->smem_np_pool = np_tables + vert_bytes + (size_t)PF_WORDS * POOL * 4 + (size_t)POOL * 12 + POOL + (size_t)POOL * 4 +
+                      3 * (NP_THREADS / 32) * 4 + 64;
+    e->np_pool = e->verts_in_smem && e->smem_np_pool <= max_optin - 1024 && getenv("PBP_NP_POOL") && atoi(getenv("PBP_NP_POOL")) != 0;
+    if (e->np_pool) {
+        int occ_pool = 1;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pool, k_narrowphase_pool<MODE_BOOL>, NP_THREADS, e->smem_np_pool));
+        e->np_pool_blocks = e->num_sms * std::max(occ_pool, 1);
+    }
     int occ = 1;
     if (e->verts_in_smem)
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrowphase<MODE_BOOL, true>, NP_THREADS, e->smem_np));

@@ -21,6 +21,12 @@
 
 namespace pbp {
 
+#ifndef PBP_IS_MIN_BLOCKS
+#define PBP_IS_MIN_BLOCKS 3   // minimum resident blocks the item setup is compiled for (80 registers; measured 121 -> 102 us)
+#endif
+#ifndef PBP_NP_MIN_BLOCKS
+#define PBP_NP_MIN_BLOCKS 2
+#endif
 constexpr int BP_THREADS = 128;
 constexpr int NP_THREADS = 256;
 constexpr int IS_THREADS = 256;
@@ -406,7 +412,7 @@ __device__ __forceinline__ bool next_tile(uint32_t *tile_counter, const uint32_t
 // Item setup: T = oMg[a]^-1 * oMg[b] for every undecided (state, pair) item
 // ------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(IS_THREADS)
+__global__ void __launch_bounds__(IS_THREADS, PBP_IS_MIN_BLOCKS)
 k_item_setup(DevModel M, StateSource src, float padding, Outputs out, Bins bins, uint32_t *tile_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *ptr = smem_raw;
@@ -533,10 +539,13 @@ k_item_setup(DevModel M, StateSource src, float padding, Outputs out, Bins bins,
 // shape tables are read at the same shared-memory addresses), which means a warp never has to
 // drain when it crosses from one bin into the next.
 constexpr int NP_CHUNK = 128;
-constexpr int NP_SIMPLEX_QUORUM = 12;   // lanes waiting for a simplex phase that make it worth a trip
+#ifndef PBP_NP_QUORUM
+#define PBP_NP_QUORUM 12
+#endif
+constexpr int NP_SIMPLEX_QUORUM = PBP_NP_QUORUM;   // lanes waiting for a simplex phase that make it worth a trip
 
 template <int MODE, bool TABLES_IN_SMEM>
-__global__ void __launch_bounds__(NP_THREADS, 2)
+__global__ void __launch_bounds__(NP_THREADS, PBP_NP_MIN_BLOCKS)
 k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk_cursor, bool has_sample) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *ptr = smem_raw;
@@ -686,6 +695,233 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
                 }
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Narrowphase, block-cooperative variant: a pool of NP_THREADS items in shared memory, re-sorted
+// by phase every round
+// ------------------------------------------------------------------------------------------
+// In k_narrowphase a lane owns its item from start to finish, so a warp always holds a mix of
+// lanes that need a support phase, lanes that need a simplex phase and lanes being refilled: on
+// average 13 of 32 lanes are active (ncu smsp__thread_inst_executed_per_inst_executed).  Here the
+// per-item GJK state lives in shared memory instead of registers, and every round the block
+// partitions its pool into "needs support" and "needs simplex" lists and hands list entries to
+// threads in order -- warps are (nearly) full and run ONE phase type.  The price is a
+// load/store of the 17-word state plus the 12-word placement around each phase and three
+// barriers per round.
+constexpr int POOL = NP_THREADS;          // items resident per block
+enum { PF_V = 0, PF_VV = 3, PF_W0 = 4, PF_W1 = 7, PF_W2 = 10, PF_W = 13, PF_T = 16, PF_BOUND = 28, PF_WORDS = 29 };
+
+template <int MODE>
+__global__ void __launch_bounds__(NP_THREADS, 2)
+k_narrowphase_pool(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk_cursor, bool has_sample) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char *ptr = smem_raw;
+    float4 *sv = reinterpret_cast<float4 *>(ptr);        ptr += align16((size_t)M.nverts_padded * sizeof(float4));
+    uint16_t *scell = reinterpret_cast<uint16_t *>(ptr); ptr += align16((size_t)M.n_sup_cells * 2);
+    uint16_t *slist = reinterpret_cast<uint16_t *>(ptr); ptr += align16((size_t)M.n_sup_lists * 2);
+    DevGeom *sg = reinterpret_cast<DevGeom *>(ptr);      ptr += align16((size_t)max(M.ngeoms, 1) * sizeof(DevGeom));
+    BpPair *sp = reinterpret_cast<BpPair *>(ptr);        ptr += align16((size_t)max(M.npairs, 1) * sizeof(BpPair));
+    uint32_t *prefix = reinterpret_cast<uint32_t *>(ptr); ptr += align16(((size_t)M.npairs + 1) * 4);   // items before bin k
+    int32_t *order = reinterpret_cast<int32_t *>(ptr);   ptr += align16((size_t)max(M.npairs, 1) * 4);
+    float *pf = reinterpret_cast<float *>(ptr);          ptr += (size_t)PF_WORDS * POOL * 4;     // [PF_WORDS][POOL]
+    int32_t *pgroup = reinterpret_cast<int32_t *>(ptr);  ptr += (size_t)POOL * 4;
+    int32_t *pslot = reinterpret_cast<int32_t *>(ptr);   ptr += (size_t)POOL * 4;                // bin slot (low 32 bits suffice per pair: idx in bin)
+    int32_t *pmeta = reinterpret_cast<int32_t *>(ptr);   ptr += (size_t)POOL * 4;                // pair | n << 16 | stalls << 20 | it << 24
+    uint8_t *pphase = reinterpret_cast<uint8_t *>(ptr);  ptr += (size_t)POOL;                    // 0 free, 1 support, 2 simplex
+    uint16_t *lsup = reinterpret_cast<uint16_t *>(ptr);  ptr += (size_t)POOL * 2;
+    uint16_t *lsmp = reinterpret_cast<uint16_t *>(ptr);  ptr += (size_t)POOL * 2;
+    uint32_t *wcnt = reinterpret_cast<uint32_t *>(ptr);  ptr += 3 * (NP_THREADS / 32) * 4 + 16;  // per-warp counts: free, support, simplex
+    __shared__ uint32_t s_base, s_take, s_nsup, s_nsmp;
+    __shared__ int s_more;
+
+    stage_words(sv, M.verts, M.nverts_padded * (int)sizeof(float4));
+    stage_words(scell, M.sup_cells, M.n_sup_cells * 2);
+    stage_words(slist, M.sup_lists, M.n_sup_lists * 2);
+    stage_words(sg, M.geoms, M.ngeoms * (int)sizeof(DevGeom));
+    stage_words(sp, M.bppairs, M.npairs * (int)sizeof(BpPair));
+    stage_words(order, M.bin_order, M.npairs * 4);
+    pphase[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_more = 1;
+    __syncthreads();
+    if (threadIdx.x < 32) {   // exclusive scan of the bin counts, in bin order
+        uint32_t run = 0;
+        for (int k0 = 0; k0 < M.npairs; k0 += 32) {
+            const int k = k0 + threadIdx.x;
+            const uint32_t t = k < M.npairs ? bins.count_np[order[k]] : 0u;
+            uint32_t inc = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)threadIdx.x >= o) inc += y;
+            }
+            if (k < M.npairs) prefix[k] = run + inc - t;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (threadIdx.x == 0) prefix[M.npairs] = run;
+    }
+    __syncthreads();
+
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int64_t stride = (int64_t)M.npairs * bins.cap;
+    const uint32_t total = prefix[M.npairs];
+    constexpr int NW = NP_THREADS / 32;
+
+    for (;;) {
+        // ---- (a) count free slots, claim that many items from the global cursor
+        const bool is_free = pphase[tid] == 0;
+        const unsigned fm = __ballot_sync(0xffffffffu, is_free);
+        if (lane == 0) wcnt[warp] = __popc(fm);
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t nfree = 0;
+            for (int w = 0; w < NW; w++) nfree += wcnt[w];
+            uint32_t base = 0, take = 0;
+            if (s_more && nfree >= (uint32_t)(POOL / 4)) {    // refill in chunks: one atomic per >= POOL/4 items
+                // guided: near the end of the launch blocks take smaller bites so that they finish together
+                const uint32_t seen = *reinterpret_cast<volatile uint32_t *>(chunk_cursor);
+                const uint32_t left = seen < total ? total - seen : 0u;
+                const uint32_t want = min(nfree, max(32u, left / (2u * gridDim.x)));
+                base = atomicAdd(chunk_cursor, want);
+                if (base >= total) s_more = 0;
+                else take = min(want, total - base);
+                if (base + want >= total) s_more = 0;
+            }
+            s_base = base;
+            s_take = take;
+        }
+        __syncthreads();
+        // ---- (b) free slots pick up their item: rank among the free slots of the block
+        if (is_free && s_take > 0) {
+            uint32_t rank = __popc(fm & lt_mask);
+            for (unsigned w = 0; w < warp; w++) rank += wcnt[w];
+            if (rank < s_take) {
+                const uint32_t gi = s_base + rank;
+                int lo = 0, hi = M.npairs;  // last bin k with prefix[k] <= gi
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (prefix[mid] <= gi) lo = mid; else hi = mid;
+                }
+                const int p = order[lo];
+                const uint32_t idx = gi - prefix[lo];
+                const int64_t slot = (int64_t)p * bins.cap + idx;
+                const int32_t g = bins.group[slot];
+                if (g >= 0 && !(MODE == MODE_BOOL && out.hit[g])) {
+                    float T[12];
+#pragma unroll
+                    for (int k = 0; k < 12; k++) T[k] = bins.T[k * stride + slot];
+                    const DevGeom &GA = sg[sp[p].a];
+                    const DevGeom &GB = sg[sp[p].b];
+                    const float3 cb = se3_act(T, GB.centre[0], GB.centre[1], GB.centre[2]);
+                    GjkState s;
+                    gjk_init(s, make_float3(GA.centre[0] - cb.x, GA.centre[1] - cb.y, GA.centre[2] - cb.z));
+                    pf[(PF_V + 0) * POOL + tid] = s.v.x; pf[(PF_V + 1) * POOL + tid] = s.v.y; pf[(PF_V + 2) * POOL + tid] = s.v.z;
+                    pf[PF_VV * POOL + tid] = s.vv;
+#pragma unroll
+                    for (int k = 0; k < 12; k++) pf[(PF_T + k) * POOL + tid] = T[k];
+                    if (MODE == MODE_DIST) pf[PF_BOUND * POOL + tid] = out.min_dist[g] + GA.core_radius + GB.core_radius;
+                    pgroup[tid] = g;
+                    pslot[tid] = (int32_t)idx;
+                    pmeta[tid] = p;            // n = 0, stalls = 0, it = 0
+                    pphase[tid] = 1;
+                }
+            }
+        }
+        // ---- (c) phase lists
+        const int ph = pphase[tid];
+        const unsigned ms = __ballot_sync(0xffffffffu, ph == 1), mq = __ballot_sync(0xffffffffu, ph == 2);
+        if (lane == 0) { wcnt[NW + warp] = __popc(ms); wcnt[2 * NW + warp] = __popc(mq); }
+        __syncthreads();
+        {
+            uint32_t bs = 0, bq = 0, ts = 0, tq = 0;
+            for (int w = 0; w < NW; w++) {
+                const uint32_t a = wcnt[NW + w], b = wcnt[2 * NW + w];
+                if (w < (int)warp) { bs += a; bq += b; }
+                ts += a; tq += b;
+            }
+            if (ph == 1) lsup[bs + __popc(ms & lt_mask)] = (uint16_t)tid;
+            if (ph == 2) lsmp[bq + __popc(mq & lt_mask)] = (uint16_t)tid;
+            if (tid == 0) { s_nsup = ts; s_nsmp = tq; }
+        }
+        __syncthreads();
+        const uint32_t nsup = s_nsup, nsmp = s_nsmp;
+        if (nsup == 0 && nsmp == 0) {
+            if (!s_more) break;
+            continue;    // pool empty but the cursor has more (only when a claimed chunk was all dropped)
+        }
+        // ---- (d) work: support items first, simplex items from the next warp boundary
+        const uint32_t sup_pad = (nsup + 31u) & ~31u;
+        for (uint32_t wi = tid; wi < sup_pad + nsmp; wi += NP_THREADS) {
+            const bool do_sup = wi < nsup;
+            const bool do_smp = wi >= sup_pad;
+            if (!do_sup && !do_smp) continue;
+            const int it = do_sup ? lsup[wi] : lsmp[wi - sup_pad];
+            const int meta = pmeta[it];
+            const int p = meta & 0xffff;
+            GjkState s;
+            s.v = make_float3(pf[(PF_V + 0) * POOL + it], pf[(PF_V + 1) * POOL + it], pf[(PF_V + 2) * POOL + it]);
+            s.vv = pf[PF_VV * POOL + it];
+            s.W0 = make_float3(pf[(PF_W0 + 0) * POOL + it], pf[(PF_W0 + 1) * POOL + it], pf[(PF_W0 + 2) * POOL + it]);
+            s.W1 = make_float3(pf[(PF_W1 + 0) * POOL + it], pf[(PF_W1 + 1) * POOL + it], pf[(PF_W1 + 2) * POOL + it]);
+            s.W2 = make_float3(pf[(PF_W2 + 0) * POOL + it], pf[(PF_W2 + 1) * POOL + it], pf[(PF_W2 + 2) * POOL + it]);
+            s.n = (meta >> 16) & 0xf; s.stalls = (meta >> 20) & 0xf; s.it = (meta >> 24) & 0xff;
+            const DevGeom &GA = sg[sp[p].a];
+            const DevGeom &GB = sg[sp[p].b];
+            const float radii = GA.core_radius + GB.core_radius;
+            const float margin = padding + radii;
+            bool finished;
+            GjkOut r;
+            if (do_sup) {
+                float T[12];
+#pragma unroll
+                for (int k = 0; k < 12; k++) T[k] = pf[(PF_T + k) * POOL + it];
+                ShapeRef A, B;
+                A.shape = GA.shape; A.p0 = GA.par[0]; A.p1 = GA.par[1]; A.p2 = GA.par[2];
+                A.verts = sv + GA.vert_off; A.nverts = GA.vert_cnt;
+                A.cell_off = GA.map_off >= 0 ? scell + GA.map_off : nullptr; A.cell_list = slist + GA.list_off;
+                B.shape = GB.shape; B.p0 = GB.par[0]; B.p1 = GB.par[1]; B.p2 = GB.par[2];
+                B.verts = sv + GB.vert_off; B.nverts = GB.vert_cnt;
+                B.cell_off = GB.map_off >= 0 ? scell + GB.map_off : nullptr; B.cell_list = slist + GB.list_off;
+                const float bound = MODE == MODE_DIST ? pf[PF_BOUND * POOL + it] : 0.f;
+                finished = (MODE == MODE_DIST) ? gjk_support_phase<true>(A, B, T, s, margin, bound, r)
+                                               : gjk_support_phase<false>(A, B, T, s, margin, 0.f, r);
+                if (!finished) {
+                    pf[(PF_W + 0) * POOL + it] = s.w.x; pf[(PF_W + 1) * POOL + it] = s.w.y; pf[(PF_W + 2) * POOL + it] = s.w.z;
+                    pphase[it] = 2;
+                }
+            } else {
+                s.w = make_float3(pf[(PF_W + 0) * POOL + it], pf[(PF_W + 1) * POOL + it], pf[(PF_W + 2) * POOL + it]);
+                finished = (MODE == MODE_DIST) ? gjk_simplex_phase<true>(s, margin, r) : gjk_simplex_phase<false>(s, margin, r);
+                if (!finished) {
+                    pf[(PF_V + 0) * POOL + it] = s.v.x; pf[(PF_V + 1) * POOL + it] = s.v.y; pf[(PF_V + 2) * POOL + it] = s.v.z;
+                    pf[PF_VV * POOL + it] = s.vv;
+                    pf[(PF_W0 + 0) * POOL + it] = s.W0.x; pf[(PF_W0 + 1) * POOL + it] = s.W0.y; pf[(PF_W0 + 2) * POOL + it] = s.W0.z;
+                    pf[(PF_W1 + 0) * POOL + it] = s.W1.x; pf[(PF_W1 + 1) * POOL + it] = s.W1.y; pf[(PF_W1 + 2) * POOL + it] = s.W1.z;
+                    pf[(PF_W2 + 0) * POOL + it] = s.W2.x; pf[(PF_W2 + 1) * POOL + it] = s.W2.y; pf[(PF_W2 + 2) * POOL + it] = s.W2.z;
+                    pphase[it] = 1;
+                }
+            }
+            if (!finished) {
+                pmeta[it] = p | (s.n << 16) | (min(s.stalls, 15) << 20) | (min(s.it, 255) << 24);
+            } else {
+                pphase[it] = 0;
+                const int32_t group = pgroup[it];
+                if (MODE == MODE_DIST) {
+                    if (r.hit) out.hit[group] = 1;
+                    atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(fmaxf(r.dist - radii, 0.f)));
+                } else if (r.hit) {
+                    out.hit[group] = 1;
+                    if (MODE == MODE_BOOL_ALL) {
+                        if (out.first_pair) atomicMin(out.first_pair + group, M.pair_orig[p]);
+                        if (out.first_bad) atomicMin(out.first_bad + group, has_sample ? bins.sample[(int64_t)p * bins.cap + pslot[it]] : 0);
+                    }
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 

@@ -120,12 +120,13 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    lib_path = os.environ.get("PBP_ENGINE_LIB", LIB_PATH)   # developer override: A/B builds of the same ABI
+    if not os.path.exists(lib_path):
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). pyroboplan_b200 has no CPU fallback."
         )
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(lib_path)
     vp, i64, i32, f32, f64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_double
     lib.pbp_last_error.restype = ctypes.c_char_p
     lib.pbp_abi_version.restype = ctypes.c_int
