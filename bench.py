@@ -39,7 +39,23 @@ N_BATCHES = 4               # distinct input batches rotated between steps (4 x 
 F_BP_FLOP_PER_CONFIG = 1.5e3 + 74 * 30.0          # k_broadphase: FK + 74 proxy tests
 F_NP_FLOP_PER_CONFIG = 6.0 * 1598 + 150.0 * 7.57  # k_narrowphase: support scans + simplex updates
 F_ALG_FLOP_PER_CONFIG = F_BP_FLOP_PER_CONFIG + F_NP_FLOP_PER_CONFIG  # = 14.4 kflop
+# The GJK work is split over two kernels: k_item_setup runs the first iteration of every item
+# (1.28 items/state of the 2.8 iterations/state the device runs in total = 45 %), k_narrowphase
+# the rest; the item setup's FK recomputation is redundant work, not algorithmic flops.
+F_KERNEL = {"k_broadphase": F_BP_FLOP_PER_CONFIG, "k_item_setup": 0.45 * F_NP_FLOP_PER_CONFIG, "k_narrowphase": 0.55 * F_NP_FLOP_PER_CONFIG}
 HBM_BYTES_PER_CONFIG = 9 * 4 + 1   # 9 float32 in, 1 verdict byte out
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) and pipe utilisation of
+# the three kernels of a 1 Mi-state round, from the committed `ncu --set full` capture
+# profiles/r01_v4_ncu_summary.txt (cold-cache, serialised launches of this same command):
+NCU = {
+    "source": "profiles/r01_v4_ncu_summary.txt",
+    "k_broadphase": {"traffic_bytes": 37.81e6 + 0.01e6, "fma_pipe_pct": 28.0, "alu_pipe_pct": 64.8, "issue_active_pct": 75.9,
+                     "threads_per_inst": 28.7, "duration_us": 124.4},
+    "k_item_setup": {"traffic_bytes": 41.72e6 + 2.74e6, "fma_pipe_pct": 27.7, "alu_pipe_pct": 36.8, "issue_active_pct": 60.0,
+                     "threads_per_inst": 28.8, "duration_us": 107.7},
+    "k_narrowphase": {"traffic_bytes": 28.37e6 + 0.13e6, "fma_pipe_pct": 22.0, "alu_pipe_pct": 38.2, "issue_active_pct": 54.6,
+                      "threads_per_inst": 13.2, "duration_us": 204.7},
+}
 
 
 def panda_models():
@@ -288,23 +304,28 @@ def main():
     dominant = "k_narrowphase" if np_ms >= bp_ms else "k_broadphase"
     states_per_launch = n * args.steps / rounds
     kernel_ms = max(np_ms, bp_ms)
-    f_dom = F_NP_FLOP_PER_CONFIG if dominant == "k_narrowphase" else F_BP_FLOP_PER_CONFIG
+    f_dom = F_KERNEL[dominant]
     achieved_tflops = f_dom * states_per_launch / (kernel_ms * 1e-3) / 1e12
     step_kernel_ms = bp_ms + np_ms + prof["item_setup_ms"] / rounds
     step_tflops = F_ALG_FLOP_PER_CONFIG * states_per_launch / (step_kernel_ms * 1e-3) / 1e12
     hbm_gbs = HBM_BYTES_PER_CONFIG * states_per_launch / (step_kernel_ms * 1e-3) / 1e9
     roofline = {
         "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-        "frac": achieved_tflops / fp32_peak if fp32_peak else None, "traffic": None,
+        "frac": achieved_tflops / fp32_peak if fp32_peak else None,
+        "traffic": NCU[dominant]["traffic_bytes"] * (states_per_launch / float(1 << 20)),
+        "traffic_source": f"{NCU['source']} (per 1 Mi-state launch, scaled to this launch size)",
         "kernel": dominant,
         "kernel_avg_ms": kernel_ms,
         "kernel_share_of_step": kernel_ms / step_kernel_ms if step_kernel_ms else None,
         "peak_source": "FFMA microbenchmark run in this process (pbp_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
-        "note": "scalar FP32 geometry: neither HBM- nor tensor-bound (SURVEY.md 8d); bound = FP32 pipe",
+        "note": "scalar FP32 geometry: neither HBM- nor tensor-bound (SURVEY.md 8d); bound = FP32 pipe. `achieved` counts the "
+                "ALGORITHMIC flops frozen from the oracle's counters (full hull scans, DESIGN.md 5); the kernels execute fewer "
+                "(exact support maps scan ~3 of ~150 vertices), so the executed-instruction view is in `ncu`",
+        "ncu": NCU,
         "kernel_ms": {"k_broadphase": bp_ms, "k_item_setup": prof["item_setup_ms"] / rounds, "k_narrowphase": np_ms},
         "states_per_launch": states_per_launch,
         "narrowphase_items_per_state": prof["narrowphase_items"] / max(n * args.steps, 1),
-        "flop_per_config": {"k_broadphase": F_BP_FLOP_PER_CONFIG, "k_narrowphase": F_NP_FLOP_PER_CONFIG},
+        "flop_per_config": F_KERNEL,
         "step": {"achieved": step_tflops, "frac": step_tflops / fp32_peak if fp32_peak else None, "unit": "TFLOP/s"},
         "hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                 "frac": hbm_gbs / peaks.get("hbm_gbs", 1.0), "peak_source": f"MEASURED_PEAKS.json ({peak_src})"},
