@@ -944,8 +944,10 @@ int pbp_discretize_fill(pbp_engine *e, const float *q1_dev, const float *q2_dev,
     return 0;
 }
 
-int pbp_check_edges(pbp_engine *e, const float *q1_dev, const float *q2_dev, int64_t n_edges, double step, float padding,
-                    uint8_t *hit_dev, int32_t *first_bad_dev, void *stream) {
+// known_total >= 0: the caller already knows the number of samples of all edges together (host
+// entry point with few edges): the single-level path then needs no device -> host round trip.
+static int check_edges_core(pbp_engine *e, const float *q1_dev, const float *q2_dev, int64_t n_edges, double step, float padding,
+                            uint8_t *hit_dev, int32_t *first_bad_dev, void *stream, int64_t known_total) {
     int rc = check_args(e, q1_dev, n_edges);
     if (rc) return rc;
     if (n_edges > 0 && (!q2_dev || !hit_dev)) return fail(PBP_ERR_ARG, "NULL buffer");
@@ -972,10 +974,15 @@ int pbp_check_edges(pbp_engine *e, const float *q1_dev, const float *q2_dev, int
         return 0;
     }
 
-    // Refinement levels.  With first_bad every sample is tested (one level, stride 1).
+    // Refinement levels.  With first_bad every sample is tested (one level, stride 1).  Every level
+    // costs a device -> host round trip (the sample total sizes the next launch), so small batches --
+    // the single-edge calls of a sequential planner -- use one level, medium ones two.
     std::vector<LevelSpec> levels;
-    if (first_bad_dev) {
+    if (first_bad_dev || n_edges <= 512) {
         levels.push_back(LevelSpec{1, 0, 1});
+    } else if (n_edges <= 16384) {
+        levels.push_back(LevelSpec{16, 0, 1});
+        levels.push_back(LevelSpec{1, 16, 0});
     } else {
         const int top = 128;
         levels.push_back(LevelSpec{top, 0, 1});
@@ -985,19 +992,32 @@ int pbp_check_edges(pbp_engine *e, const float *q1_dev, const float *q2_dev, int
     unsigned long long *d_total = ctrl_u64(e, 0), *d_cursor = ctrl_u64(e, 1);
     for (const LevelSpec &lv : levels) {
         CUDA_TRY(cudaMemsetAsync(d_total, 0, 16, st));
-        const uint8_t *dead = first_bad_dev ? nullptr : hit_dev;
-        k_level_count<<<grid_for(n_edges, 256), 256, 0, st>>>(counts, dead, n_edges, lv, d_total);
-        CUDA_TRY(cudaGetLastError());
-        e->stats.kernel_launches++;
-        CUDA_TRY(cudaMemcpyAsync(e->h_pinned, d_total, 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        const int64_t total = (int64_t)e->h_pinned[0];
+        const uint8_t *dead = (first_bad_dev || levels.size() == 1) ? nullptr : hit_dev;
+        int64_t total;
+        if (known_total >= 0 && levels.size() == 1) {
+            total = known_total;
+        } else {
+            k_level_count<<<grid_for(n_edges, 256), 256, 0, st>>>(counts, dead, n_edges, lv, d_total);
+            CUDA_TRY(cudaGetLastError());
+            e->stats.kernel_launches++;
+            CUDA_TRY(cudaMemcpyAsync(e->h_pinned, d_total, 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            total = (int64_t)e->h_pinned[0];
+        }
         if (total == 0) continue;
-        if ((rc = e->d_desc_group.ensure((size_t)total * 4)) || (rc = e->d_desc_frac.ensure((size_t)total * 4))) return rc;
-        if (first_bad_dev && (rc = e->d_desc_sample.ensure((size_t)total * 4))) return rc;
+        const size_t slack = known_total >= 0 ? (size_t)n_edges : 0;   // host-computed total: belt and braces
+        if ((rc = e->d_desc_group.ensure((total + slack) * 4)) || (rc = e->d_desc_frac.ensure((total + slack) * 4))) return rc;
+        if (first_bad_dev && (rc = e->d_desc_sample.ensure((total + slack) * 4))) return rc;
         int32_t *dg = e->d_desc_group.as<int32_t>();
         float *df = e->d_desc_frac.as<float>();
         int32_t *ds = first_bad_dev ? e->d_desc_sample.as<int32_t>() : nullptr;
+        if (known_total >= 0) {
+            // every descriptor slot holds a valid sample (edge 0, fraction 0) even if the device's
+            // counts disagreed with the host's; the caller compares the emit cursor afterwards
+            CUDA_TRY(cudaMemsetAsync(dg, 0, (total + slack) * 4, st));
+            CUDA_TRY(cudaMemsetAsync(df, 0, (total + slack) * 4, st));
+            if (ds) CUDA_TRY(cudaMemsetAsync(ds, 0, (total + slack) * 4, st));
+        }
         k_level_emit<<<grid_for(n_edges, 256), 256, 0, st>>>(counts, dead, n_edges, lv, d_cursor, dg, df, ds);
         CUDA_TRY(cudaGetLastError());
         e->stats.kernel_launches++;
@@ -1019,6 +1039,11 @@ int pbp_check_edges(pbp_engine *e, const float *q1_dev, const float *q2_dev, int
     }
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+int pbp_check_edges(pbp_engine *e, const float *q1_dev, const float *q2_dev, int64_t n_edges, double step, float padding,
+                    uint8_t *hit_dev, int32_t *first_bad_dev, void *stream) {
+    return check_edges_core(e, q1_dev, q2_dev, n_edges, step, padding, hit_dev, first_bad_dev, stream, -1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1102,12 +1127,37 @@ int pbp_check_edges_host(pbp_engine *e, const float *q1_host, const float *q2_ho
     cudaStream_t st = e->s_comp;
     CUDA_TRY(cudaMemcpyAsync(e->d_io_q.p, q1_host, qb, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->d_io_q2.p, q2_host, qb, cudaMemcpyHostToDevice, st));
-    rc = pbp_check_edges(e, e->d_io_q.as<float>(), e->d_io_q2.as<float>(), n_edges, step, padding, e->d_io_hit.as<uint8_t>(),
-                         first_bad_host ? e->d_io_i32.as<int32_t>() : nullptr, st);
+    // few edges: the sample counts are cheap to compute here (the same FP64 expression as
+    // k_edge_counts), which spares the single-level path its only device -> host round trip
+    int64_t known_total = -1;
+    if (n_edges <= 512 && step > 0.0) {
+        known_total = 0;
+        for (int64_t i = 0; i < n_edges; i++) {
+            double acc = 0.0;
+            for (int k = 0; k < e->nq; k++) {
+                const double dlt = (double)q2_host[i * e->nq + k] - (double)q1_host[i * e->nq + k];
+                acc += dlt * dlt;
+            }
+            known_total += (int64_t)((int32_t)ceil(sqrt(acc) / step) + 1);
+        }
+    }
+    rc = check_edges_core(e, e->d_io_q.as<float>(), e->d_io_q2.as<float>(), n_edges, step, padding, e->d_io_hit.as<uint8_t>(),
+                          first_bad_host ? e->d_io_i32.as<int32_t>() : nullptr, st, known_total);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(hit_host, e->d_io_hit.p, (size_t)n_edges, cudaMemcpyDeviceToHost, st));
     if (first_bad_host) CUDA_TRY(cudaMemcpyAsync(first_bad_host, e->d_io_i32.p, (size_t)n_edges * 4, cudaMemcpyDeviceToHost, st));
+    if (known_total > 0 && e->npairs > 0) CUDA_TRY(cudaMemcpyAsync(e->h_pinned, ctrl_u64(e, 1), 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (known_total > 0 && e->npairs > 0 && (int64_t)e->h_pinned[0] != known_total) {
+        // host and device sample counts disagree (never observed: both are the same IEEE FP64
+        // expression): redo the batch on the path that asks the device
+        rc = check_edges_core(e, e->d_io_q.as<float>(), e->d_io_q2.as<float>(), n_edges, step, padding, e->d_io_hit.as<uint8_t>(),
+                              first_bad_host ? e->d_io_i32.as<int32_t>() : nullptr, st, -1);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(hit_host, e->d_io_hit.p, (size_t)n_edges, cudaMemcpyDeviceToHost, st));
+        if (first_bad_host) CUDA_TRY(cudaMemcpyAsync(first_bad_host, e->d_io_i32.p, (size_t)n_edges * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
     return 0;
 }
 

@@ -289,3 +289,23 @@ def test_full_size_config3_edges(panda_engine, panda_full, panda_oracle, torch_c
     assert len(bad) <= 2, bad[:10]
     counts, offsets, _ = panda_engine.discretize(q1[:2000], q2[:2000], 0.05)
     assert 100 < counts.mean() < 115   # SURVEY.md 8d probe: ~107.5 samples per random edge
+
+
+@pytest.mark.parametrize("n_edges", [1, 7, 300, 600, 5000, 20000])
+def test_edge_batch_sizes_pick_different_level_schedules(panda_engine, panda_oracle, panda_full, n_edges):
+    """One level (<= 512 edges; host path without any device -> host round trip), two levels
+    (<= 16384) and the full 128..1 hierarchy give the same verdicts as the oracle's in-order walk."""
+    import torch
+
+    model = panda_full[0]
+    a = uniform_states(model, n_edges, 300 + n_edges)
+    b = uniform_states(model, n_edges, 900 + n_edges)
+    b[: n_edges // 2] = a[: n_edges // 2] + np.float32(0.08) * (b[: n_edges // 2] - a[: n_edges // 2])
+    ref, _, _, _ = panda_oracle.check_edges(a.astype(np.float64), b.astype(np.float64), 0.05)
+    got_host = panda_engine.check_edges(a, b, 0.05)
+    got_dev = panda_engine.check_edges(torch.as_tensor(a, device="cuda:0"), torch.as_tensor(b, device="cuda:0"), 0.05).cpu().numpy()
+    assert (got_host == ref.astype(bool)).all()
+    assert (got_dev == ref.astype(bool)).all()
+    # zero-length edges (one sample each)
+    z = panda_engine.check_edges(a[:3], a[:3], 0.05)
+    assert (z == panda_oracle.check_states(a[:3].astype(np.float64))[0].astype(bool)).all()
