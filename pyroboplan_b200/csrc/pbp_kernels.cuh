@@ -24,6 +24,12 @@ namespace pbp {
 #ifndef PBP_IS_MIN_BLOCKS
 #define PBP_IS_MIN_BLOCKS 3   // minimum resident blocks the item setup is compiled for (80 registers; measured 121 -> 102 us)
 #endif
+#ifndef PBP_NP_REFILL_MIN
+#define PBP_NP_REFILL_MIN 8   // measured on config 2: 173.7 us (1) / 172.9 (4) / 170.0 (8) / 170.7 (12) / 171.0 (16)
+#endif
+#ifndef PBP_NP_LOCKSTEP
+#define PBP_NP_LOCKSTEP 1
+#endif
 #ifndef PBP_NP_MIN_BLOCKS
 #define PBP_NP_MIN_BLOCKS 2
 #endif
@@ -604,7 +610,10 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
     uint32_t cursor = 0, chunk_end = 0;
     bool more = true;
     for (;;) {
-        const unsigned need = __ballot_sync(0xffffffffu, phase == 0);
+        unsigned need = __ballot_sync(0xffffffffu, phase == 0);
+        // batch the refills: the refill path (bin search, 12 strided loads, GJK init) runs with only
+        // the free lanes active, so it is taken once enough lanes are free (or nothing else is left)
+        if (need != 0xffffffffu && __popc(need) < PBP_NP_REFILL_MIN) need = 0u;
         if (need && cursor >= chunk_end && more) {
             // guided self-scheduling: NP_CHUNK items while plenty are left, down to one warp-load
             // near the end, so the last chunk of a launch (and every chunk of a small launch) is
@@ -647,27 +656,25 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
             }
             cursor += __popc(need);
         }
-        // ---- run the phase most lanes are waiting for (most items end right after their first
-        //      support phase, so the simplex phase is only worth a trip once enough lanes queue up)
-        const int n_sup = __popc(__ballot_sync(0xffffffffu, phase == 1));
-        const int n_smp = __popc(__ballot_sync(0xffffffffu, phase == 2));
-        if (n_sup == 0 && n_smp == 0) {
-            if (!more && cursor >= chunk_end) break;
-            continue;
-        }
-        const bool refillable = more || cursor < chunk_end;
-        const bool run_simplex = n_smp > 0 && (n_sup == 0 || n_smp >= NP_SIMPLEX_QUORUM || (!refillable && n_smp >= n_sup));
-        bool finished = false;
-        GjkOut r;
-        float radii = 0.f;
-        if (run_simplex) {
-            if (phase == 2) {
-                const float margin = padding + sg[sp[p].a].core_radius + sg[sp[p].b].core_radius;
-                radii = margin - padding;
-                finished = (MODE == MODE_DIST) ? gjk_simplex_phase<true>(s, margin, r) : gjk_simplex_phase<false>(s, margin, r);
-                phase = finished ? 0 : 1;
+        // ---- one GJK iteration for every live lane: the support phase, then -- for the lanes it did
+        //      not finish -- the simplex phase.  Since the item setup removed the items that end
+        //      after one support call, the items here all run several iterations, and keeping the
+        //      lanes in lock-step (every live lane is at "support" at the top of a trip) wastes only
+        //      the simplex slot of a lane's last trip.  (PBP_NP_LOCKSTEP=0 restores the older
+        //      policy: per trip, run only the phase most lanes are waiting for.)
+        auto publish = [&](const GjkOut &r, float radii) {
+            if (MODE == MODE_DIST) {
+                if (r.hit) out.hit[group] = 1;
+                atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(fmaxf(r.dist - radii, 0.f)));
+            } else if (r.hit) {
+                out.hit[group] = 1;
+                if (MODE == MODE_BOOL_ALL) {
+                    if (out.first_pair) atomicMin(out.first_pair + group, M.pair_orig[p]);
+                    if (out.first_bad) atomicMin(out.first_bad + group, has_sample ? bins.sample[slot] : 0);
+                }
             }
-        } else if (phase == 1) {
+        };
+        auto support = [&](GjkOut &r, float &radii) {
             const DevGeom &GA = sg[sp[p].a];
             const DevGeom &GB = sg[sp[p].b];
             ShapeRef A, B;
@@ -679,22 +686,48 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
             B.cell_off = GB.map_off >= 0 ? cells + GB.map_off : nullptr; B.cell_list = lists + GB.list_off;
             radii = GA.core_radius + GB.core_radius;
             const float margin = padding + radii;
-            finished = (MODE == MODE_DIST) ? gjk_support_phase<true>(A, B, T, s, margin, bound, r)
-                                           : gjk_support_phase<false>(A, B, T, s, margin, 0.f, r);
+            return (MODE == MODE_DIST) ? gjk_support_phase<true>(A, B, T, s, margin, bound, r)
+                                       : gjk_support_phase<false>(A, B, T, s, margin, 0.f, r);
+        };
+        auto simplex = [&](GjkOut &r, float &radii) {
+            const float margin = padding + sg[sp[p].a].core_radius + sg[sp[p].b].core_radius;
+            radii = margin - padding;
+            return (MODE == MODE_DIST) ? gjk_simplex_phase<true>(s, margin, r) : gjk_simplex_phase<false>(s, margin, r);
+        };
+        const int n_sup = __popc(__ballot_sync(0xffffffffu, phase == 1));
+        const int n_smp = __popc(__ballot_sync(0xffffffffu, phase == 2));
+        if (n_sup == 0 && n_smp == 0) {
+            if (!more && cursor >= chunk_end) break;
+            continue;
+        }
+        GjkOut r;
+        float radii = 0.f;
+#if PBP_NP_LOCKSTEP
+        if (phase == 1) {
+            const bool finished = support(r, radii);
+            phase = finished ? 0 : 2;
+            if (finished) publish(r, radii);
+        }
+        if (phase == 2) {
+            const bool finished = simplex(r, radii);
+            phase = finished ? 0 : 1;
+            if (finished) publish(r, radii);
+        }
+#else
+        const bool refillable = more || cursor < chunk_end;
+        const bool run_simplex = n_smp > 0 && (n_sup == 0 || n_smp >= NP_SIMPLEX_QUORUM || (!refillable && n_smp >= n_sup));
+        bool finished = false;
+        if (run_simplex) {
+            if (phase == 2) {
+                finished = simplex(r, radii);
+                phase = finished ? 0 : 1;
+            }
+        } else if (phase == 1) {
+            finished = support(r, radii);
             phase = finished ? 0 : 2;
         }
-        if (finished) {
-            if (MODE == MODE_DIST) {
-                if (r.hit) out.hit[group] = 1;
-                atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(fmaxf(r.dist - radii, 0.f)));
-            } else if (r.hit) {
-                out.hit[group] = 1;
-                if (MODE == MODE_BOOL_ALL) {
-                    if (out.first_pair) atomicMin(out.first_pair + group, M.pair_orig[p]);
-                    if (out.first_bad) atomicMin(out.first_bad + group, has_sample ? bins.sample[slot] : 0);
-                }
-            }
-        }
+        if (finished) publish(r, radii);
+#endif
     }
 }
 
