@@ -239,6 +239,16 @@ int pbp_ik_iterate(pbp_engine *e, int32_t frame_id, const double *targets_dev, d
                    uint64_t active_mask, const double *w_diag_host, const double *nullspace_dev, double *e0_dev,
                    int32_t *status_dev, int32_t *iters_dev, void *stream);
 
+/* Introspection of the model-specialised broadphase (pyroboplan_b200/csrc/pbp_jit.h): boolean
+ * queries run a kernel whose CUDA source is generated from the model (joint chain as straight-line
+ * code, pair tests unrolled) and built with NVRTC when the engine is created.  These two entry
+ * points need no CUDA device; they exist for tests and tooling (tools/jit_dump.py).
+ *   pbp_jit_broadphase_source  writes the generated source (NUL terminated) when cap >= *needed;
+ *                              *needed = 1 (empty string) when the model does not qualify
+ *   pbp_jit_compile_check      NVRTC build for sm_<major><minor>a; *cubin_bytes = size of the result */
+int pbp_jit_broadphase_source(const pbp_model_desc *desc, char *buf, size_t cap, size_t *needed);
+int pbp_jit_compile_check(const pbp_model_desc *desc, int cc_major, int cc_minor, size_t *cubin_bytes, char *log_buf, size_t log_cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,8 @@ EXPORTED_SYMBOLS = [
     "pbp_knn",
     "pbp_compute_distances",
     "pbp_collision_nullspace",
+    "pbp_jit_broadphase_source",
+    "pbp_jit_compile_check",
 ]
 
 

@@ -63,6 +63,12 @@ def test_argument_validation_without_device():
     assert lib.pbp_get_stats(None, None, 0) == -1
     assert lib.pbp_check_states(None, None, 1, ctypes.c_float(0.0), None, None, None, None) == -1
     assert b"NULL" in lib.pbp_last_error()
+    # the entry points added for the IK / distance / k-NN rows validate before touching the device too
+    assert lib.pbp_knn(None, None, 4, 3, ctypes.c_double(1.0), 0, None, None, None) == -1
+    assert lib.pbp_compute_distances(None, None, 4, ctypes.c_float(0.0), None, None, None, None, None) == -1
+    assert lib.pbp_collision_nullspace(None, None, 4, ctypes.c_float(0.05), ctypes.c_float(1.0), None, None) == -1
+    assert lib.pbp_ik_iterate(None, 0, None, None, 4, None, ctypes.c_uint64(0), None, None, None, None, None, None) == -1
+    assert lib.pbp_jit_broadphase_source(None, None, 0, None) == -1
 
 
 def test_flatten_model_is_conservative():
