@@ -731,7 +731,7 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
                  align16((size_t)np1 * sizeof(BpPair)) + align16((size_t)np1 * sizeof(PairPath)) + tile_tables + 16;
     const size_t np_tables = align16((size_t)std::max(d->ngeoms, 1) * sizeof(DevGeom)) + align16((size_t)np1 * sizeof(BpPair)) + tile_tables + 16;
     const size_t vert_bytes = align16((size_t)e->nverts_padded * sizeof(float4)) + align16(sup_cells.size() * 2) + align16(sup_lists.size() * 2);
-    e->verts_in_smem = np_tables + vert_bytes <= 96 * 1024;
+    e->verts_in_smem = np_tables + vert_bytes <= 110 * 1024;   // two narrowphase blocks per SM must fit in 227 KB
     e->smem_np = np_tables + (e->verts_in_smem ? vert_bytes : 0);
     if (e->smem_bp > max_optin || e->smem_np > max_optin || e->smem_is > max_optin)
         return bail(fail(PBP_ERR_CAPACITY, "model tables exceed shared memory (%zu / %zu / %zu bytes)", e->smem_bp, e->smem_is, e->smem_np));

@@ -24,7 +24,10 @@ struct ShapeRef {
     const uint16_t *cell_list;
 };
 
-constexpr int SUPMAP_KD = 8;  // must equal SUPMAP_K of pbp_supmap.h
+#ifndef PBP_SUPMAP_K
+#define PBP_SUPMAP_K 16
+#endif
+constexpr int SUPMAP_KD = PBP_SUPMAP_K;  // must equal SUPMAP_K of pbp_supmap.h
 
 __device__ __forceinline__ float dot3(float3 a, float3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
 __device__ __forceinline__ float3 sub3(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
