@@ -7,8 +7,8 @@
 // the program: the joint chain is straight-line code with the placements as literals (zeros and
 // ones fold away), the proxy centres of the moving geometries stay in registers, every pair test
 // is unrolled with its geometry ids resolved at generation time, and the per-call thresholds sit
-// in the kernel parameter (constant bank) -- ~14 instructions per pair.  The item-append epilogue
-// is the generic kernel's, verbatim.  Only the boolean mode (the planning hot path: states and
+// in the kernel parameter (constant bank) -- ~14 instructions per pair.  The item append works on
+// each thread's own items with shared-memory atomics.  Only the boolean mode (the planning hot path: states and
 // edge samples) is specialised; distance / first-pair modes and models that do not fit use the
 // generic kernel.  Set PBP_NO_JIT=1 to disable.
 #pragma once
@@ -162,7 +162,7 @@ inline std::string generate_broadphase(const Input &in) {
     s += "#define NQ " + std::to_string(NQ) + "\n#define NP " + std::to_string(NP) + "\n#define NW " + std::to_string(NW) +
          "\n#define BT " + std::to_string(SPEC_THREADS) + "\n";
     s += "extern \"C\" __global__ void __launch_bounds__(BT) k_bp_spec(const SpecArgs A) {\n";
-    s += "    __shared__ __align__(16) float sq[BT * NQ];\n    __shared__ uint32_t sbits[NW * BT];\n    __shared__ uint32_t swcount[(BT / 32) * NP];\n";
+    s += "    __shared__ __align__(16) float sq[BT * NQ];\n    __shared__ uint32_t scnt[NP];\n    __shared__ uint32_t sbase[NP];\n";
     s += "    const int tid = threadIdx.x;\n    const int64_t block_first = (int64_t)blockIdx.x * BT;\n";
     s += "    const int count = (int)min((int64_t)BT, A.n_states - block_first);\n";
     // state load (as load_states of the generic kernel)
@@ -179,7 +179,7 @@ inline std::string generate_broadphase(const Input &in) {
          "        const float *a = A.q1 + gg * NQ, *b = A.q2 + gg * NQ;\n"
          "        for (int k = 0; k < NQ; k++) { const float qa = __ldg(a + k), qb = __ldg(b + k); sq[tid * NQ + k] = fmaf(f, qb - qa, qa); }\n"
          "    }\n";
-    s += "    for (int i = tid; i < (BT / 32) * NP; i += BT) swcount[i] = 0;\n    __syncthreads();\n";
+    s += "    for (int i = tid; i < NP; i += BT) scnt[i] = 0u;\n    __syncthreads();\n";
     s += "    const int64_t state = block_first + tid;\n    const bool valid = tid < count;\n";
     s += "    const int32_t group = valid ? (A.group ? A.group[state] : (int32_t)state) : 0;\n";
     s += "    bool alive = valid;\n    if (A.group && valid && A.hit[group]) alive = false;\n    bool state_hit = false;\n";
@@ -302,56 +302,28 @@ inline std::string generate_broadphase(const Input &in) {
     }
     s += g.out;
     s += "    }\n";
-    // ---- a state decided "colliding" needs none of its items; publish the words
-    for (int w = 0; w < NW; w++) s += "    sbits[" + std::to_string(w) + " * BT + tid] = state_hit ? 0u : w" + std::to_string(w) + ";\n";
-    // ---- epilogue: the generic kernel's item append (per-warp counts, one reservation per block and pair, coalesced writes)
-    s += R"(
-    const unsigned lane = tid & 31;
-    const unsigned warp = tid >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    for (int w = 0; w < NW; w++) {
-        const uint32_t mybits = sbits[w * BT + tid];
-        uint32_t warp_bits = mybits;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) warp_bits |= __shfl_xor_sync(0xffffffffu, warp_bits, o);
-        while (warp_bits) {
-            const int b = __ffs(warp_bits) - 1;
-            warp_bits &= warp_bits - 1;
-            const unsigned um = __ballot_sync(0xffffffffu, (mybits >> b) & 1u);
-            if (lane == 0) swcount[warp * NP + (w << 5) + b] = __popc(um);
-        }
-    }
-    __syncthreads();
-    for (int p = tid; p < NP; p += BT) {
-        uint32_t total = 0;
-        for (int wv = 0; wv < BT / 32; wv++) total += swcount[wv * NP + p];
-        uint32_t base = total ? atomicAdd(A.bin_count + p, total) : 0u;
-        for (int wv = 0; wv < BT / 32; wv++) {
-            const uint32_t c = swcount[wv * NP + p];
-            swcount[wv * NP + p] = base;
-            base += c;
-        }
-    }
-    __syncthreads();
-    for (int w = 0; w < NW; w++) {
-        const uint32_t bits = sbits[w * BT + tid];
-        const unsigned anyw = __ballot_sync(0xffffffffu, bits != 0);
-        if (!anyw) continue;
-        uint32_t warp_bits = bits;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) warp_bits |= __shfl_xor_sync(0xffffffffu, warp_bits, o);
-        while (warp_bits) {
-            const int b = __ffs(warp_bits) - 1;
-            warp_bits &= warp_bits - 1;
-            const int p = (w << 5) + b;
-            const bool mine = (bits >> b) & 1u;
-            const unsigned um = __ballot_sync(0xffffffffu, mine);
-            if (mine) A.bin_state[(int64_t)p * A.cap + swcount[warp * NP + p] + __popc(um & lt_mask)] = (int32_t)state;
-        }
-    }
-    if (valid && state_hit) A.hit[group] = 1;
-}
-)";
+    // ---- epilogue: append the undecided items to their pairs' bins.  Every thread holds its items
+    //      as bits of w0..; two passes over its OWN bits with shared-memory atomics: count per pair,
+    //      one global reservation per (block, pair), then rank + store.  (The generic kernel's
+    //      warp-ballot version walks every pair present in the warp twice, ~800 instructions per
+    //      warp; here a thread pays only for its ~1.3 items.)
+    s += "    if (state_hit) {";
+    for (int w = 0; w < NW; w++) s += " w" + std::to_string(w) + " = 0u;";
+    s += " }\n";
+    for (int w = 0; w < NW; w++)
+        s += "    { uint32_t b = w" + std::to_string(w) + "; while (b) { const int k = __ffs(b) - 1; b &= b - 1; atomicAdd(&scnt[" +
+             std::to_string(32 * w) + " + k], 1u); } }\n";
+    s += "    __syncthreads();\n"
+         "    for (int p = tid; p < NP; p += BT) {\n"
+         "        const uint32_t c = scnt[p];\n"
+         "        sbase[p] = c ? atomicAdd(A.bin_count + p, c) : 0u;\n"
+         "        scnt[p] = 0u;\n"
+         "    }\n"
+         "    __syncthreads();\n";
+    for (int w = 0; w < NW; w++)
+        s += "    { uint32_t b = w" + std::to_string(w) + "; while (b) { const int k = __ffs(b) - 1; b &= b - 1; const int p = " +
+             std::to_string(32 * w) + " + k; const uint32_t r = atomicAdd(&scnt[p], 1u); A.bin_state[(int64_t)p * A.cap + sbase[p] + r] = (int32_t)state; } }\n";
+    s += "    if (valid && state_hit) A.hit[group] = 1;\n}\n";
     return s;
 }
 
