@@ -247,9 +247,6 @@ k_broadphase(DevModel M, StateSource src, int64_t n_states, float padding, Outpu
 
     // ---- pass 1: classify every pair, group by group; undecided pairs become bits of per-thread
     //      words kept in shared memory (no atomics on the critical path)
-    const unsigned lane = tid & 31;
-    const unsigned warp = tid >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const int nwords = (M.npairs + 31) >> 5;
     uint32_t bits = 0;
     auto classify = [&](int p, float d2) {
@@ -308,51 +305,37 @@ k_broadphase(DevModel M, StateSource src, int64_t n_states, float padding, Outpu
             for (int p = grp.begin; p < grp.end; p++) classify(p, generic_dist2(sp[p]));
         }
     }
-    // ---- per-warp item counts of every pair that has items in this warp
+    // ---- append the undecided items to their pairs' bins: every thread walks its OWN bits twice
+    //      with shared-memory atomics -- count per pair, one global reservation per (block, pair),
+    //      then rank + store -- so a thread pays only for its ~1.3 items
+    uint32_t *scnt = swcount, *sbase = swcount + M.npairs;
     if (MODE == MODE_BOOL && state_hit) {
         // a state decided "colliding" needs none of its items
         for (int w = 0; w < nwords; w++) sbits[w * BP_THREADS + tid] = 0;
     }
     for (int w = 0; w < nwords; w++) {
-        const uint32_t mybits = sbits[w * BP_THREADS + tid];
-        uint32_t warp_bits = mybits;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) warp_bits |= __shfl_xor_sync(0xffffffffu, warp_bits, o);
-        while (warp_bits) {
-            const int b = __ffs(warp_bits) - 1;
-            warp_bits &= warp_bits - 1;
-            const unsigned um = __ballot_sync(0xffffffffu, (mybits >> b) & 1u);
-            if (lane == 0) swcount[warp * M.npairs + (w << 5) + b] = __popc(um);
+        uint32_t b = sbits[w * BP_THREADS + tid];
+        while (b) {
+            const int k = __ffs(b) - 1;
+            b &= b - 1;
+            atomicAdd(&scnt[(w << 5) + k], 1u);
         }
     }
     __syncthreads();
-    // ---- one global reservation per (block, pair), issued by different threads in parallel
     for (int p = tid; p < M.npairs; p += BP_THREADS) {
-        uint32_t total = 0;
-        for (int wv = 0; wv < BP_THREADS / 32; wv++) total += swcount[wv * M.npairs + p];
-        uint32_t base = total ? atomicAdd(bins.count + p, total) : 0u;
-        for (int wv = 0; wv < BP_THREADS / 32; wv++) {
-            const uint32_t c = swcount[wv * M.npairs + p];
-            swcount[wv * M.npairs + p] = base;   // becomes the warp's base slot
-            base += c;
-        }
+        const uint32_t c = scnt[p];
+        sbase[p] = c ? atomicAdd(bins.count + p, c) : 0u;
+        scnt[p] = 0u;
     }
     __syncthreads();
-    // ---- pass 2: write the items (coalesced per warp and pair)
     for (int w = 0; w < nwords; w++) {
-        const uint32_t bits = sbits[w * BP_THREADS + tid];
-        unsigned anyw = __ballot_sync(0xffffffffu, bits != 0);
-        if (!anyw) continue;
-        uint32_t warp_bits = bits;   // union over the warp: which pairs of this word have items
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) warp_bits |= __shfl_xor_sync(0xffffffffu, warp_bits, o);
-        while (warp_bits) {
-            const int b = __ffs(warp_bits) - 1;
-            warp_bits &= warp_bits - 1;
-            const int p = (w << 5) + b;
-            const bool mine = (bits >> b) & 1u;
-            const unsigned um = __ballot_sync(0xffffffffu, mine);
-            if (mine) bins.state[(int64_t)p * bins.cap + swcount[warp * M.npairs + p] + __popc(um & lt_mask)] = (int32_t)state;
+        uint32_t b = sbits[w * BP_THREADS + tid];
+        while (b) {
+            const int k = __ffs(b) - 1;
+            b &= b - 1;
+            const int p = (w << 5) + k;
+            const uint32_t r = atomicAdd(&scnt[p], 1u);
+            bins.state[(int64_t)p * bins.cap + sbase[p] + r] = (int32_t)state;
         }
     }
 
