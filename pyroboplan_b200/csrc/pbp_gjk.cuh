@@ -261,6 +261,30 @@ __device__ __forceinline__ void gjk_init(GjkState &s, float3 v0) {
     s.n = 0; s.it = 0; s.stalls = 0;
 }
 
+// Initial search direction v0 (a point of A minus a point of B, in A's frame; T = placement of B in
+// A's frame).  The line between the proxy centres in general; against a BOX, the point of the box
+// closest to the other shape's centre: a flat box (the ground plate) is badly served by the centre
+// line, while the closest-point direction is the box's own separating axis -- measured on config 2,
+// the first iteration then separates 55 % instead of 15 % of the undecided box items.
+__device__ __forceinline__ float3 gjk_start_direction(const DevGeom &GA, const DevGeom &GB, const float *T) {
+    const float3 ca = make_float3(GA.centre[0], GA.centre[1], GA.centre[2]);
+    const float3 cb = se3_act(T, GB.centre[0], GB.centre[1], GB.centre[2]);
+    float3 v = sub3(ca, cb);
+    if (GA.shape == PBP_SHAPE_BOX) {
+        const float3 cl = make_float3(fminf(fmaxf(cb.x, -GA.par[0]), GA.par[0]), fminf(fmaxf(cb.y, -GA.par[1]), GA.par[1]),
+                                      fminf(fmaxf(cb.z, -GA.par[2]), GA.par[2]));
+        const float3 d = sub3(cl, cb);
+        if (dot3(d, d) > 1e-12f) v = d;            // centre of B outside the box
+    } else if (GB.shape == PBP_SHAPE_BOX) {
+        const float3 l = se3_act_inv(T, ca);       // centre of A in the box frame
+        const float3 cl = make_float3(fminf(fmaxf(l.x, -GB.par[0]), GB.par[0]), fminf(fmaxf(l.y, -GB.par[1]), GB.par[1]),
+                                      fminf(fmaxf(l.z, -GB.par[2]), GB.par[2]));
+        const float3 d = sub3(ca, se3_act(T, cl.x, cl.y, cl.z));
+        if (dot3(d, d) > 1e-12f) v = d;
+    }
+    return v;
+}
+
 // Support phase of one GJK iteration: new support point of A - B in direction -v, then the
 // termination tests that only need it.  T: placement of B in A's frame.  Returns true when the
 // item is finished (out is then valid); otherwise s.w holds the point for the simplex phase.

@@ -491,10 +491,9 @@ k_item_setup(DevModel M, StateSource src, float padding, Outputs out, Bins bins,
                 // about two thirds of the items are already separated along the line between the
                 // proxy centres and never reach the (divergent) narrowphase.  Same arithmetic as the
                 // narrowphase's own first trip, so the decision is the one it would have taken.
-                const float3 cb = se3_act(R, GB.centre[0], GB.centre[1], GB.centre[2]);
                 GjkState gs;
                 GjkOut go;
-                gjk_init(gs, make_float3(GA.centre[0] - cb.x, GA.centre[1] - cb.y, GA.centre[2] - cb.z));
+                gjk_init(gs, gjk_start_direction(GA, GB, R));
                 const float margin = padding + radii;
                 const float bound = MODE == MODE_DIST ? out.min_dist[group] + radii : 0.f;
                 const bool finished = (MODE == MODE_DIST) ? gjk_support_phase<true>(A, B, R, gs, margin, bound, go)
@@ -630,8 +629,7 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
                     for (int k = 0; k < 12; k++) T[k] = bins.T[k * stride + slot];
                     const DevGeom &GA = sg[sp[p].a];
                     const DevGeom &GB = sg[sp[p].b];
-                    const float3 cb = se3_act(T, GB.centre[0], GB.centre[1], GB.centre[2]);
-                    gjk_init(s, make_float3(GA.centre[0] - cb.x, GA.centre[1] - cb.y, GA.centre[2] - cb.z));
+                    gjk_init(s, gjk_start_direction(GA, GB, T));
                     group = g;
                     if (MODE == MODE_DIST) bound = out.min_dist[g] + GA.core_radius + GB.core_radius;  // group == state here
                     phase = 1;
@@ -831,9 +829,8 @@ k_narrowphase_pool(DevModel M, float padding, Outputs out, Bins bins, uint32_t *
                     for (int k = 0; k < 12; k++) T[k] = bins.T[k * stride + slot];
                     const DevGeom &GA = sg[sp[p].a];
                     const DevGeom &GB = sg[sp[p].b];
-                    const float3 cb = se3_act(T, GB.centre[0], GB.centre[1], GB.centre[2]);
                     GjkState s;
-                    gjk_init(s, make_float3(GA.centre[0] - cb.x, GA.centre[1] - cb.y, GA.centre[2] - cb.z));
+                    gjk_init(s, gjk_start_direction(GA, GB, T));
                     pf[(PF_V + 0) * POOL + tid] = s.v.x; pf[(PF_V + 1) * POOL + tid] = s.v.y; pf[(PF_V + 2) * POOL + tid] = s.v.z;
                     pf[PF_VV * POOL + tid] = s.vv;
 #pragma unroll

@@ -96,8 +96,7 @@ k_pair_distances(DevModel M, const float *__restrict__ oMg, int64_t n, float cut
 #pragma unroll
     for (int k = 0; k < 12; k++) { Ta[k] = oMg[(i * M.ngeoms + pr.a) * 12 + k]; Tb[k] = oMg[(i * M.ngeoms + pr.b) * 12 + k]; }
     se3_inv_mul(Ta, Tb, T);
-    const float3 cb = se3_act(T, GB.centre[0], GB.centre[1], GB.centre[2]);
-    const float3 v0 = make_float3(GA.centre[0] - cb.x, GA.centre[1] - cb.y, GA.centre[2] - cb.z);
+    const float3 v0 = gjk_start_direction(GA, GB, T);
     const WitnessOut w = gjk_run_witness(shape_ref(M, GA), shape_ref(M, GB), T, v0, GA.core_radius, GB.core_radius, cutoff);
     const int64_t o = (int64_t)M.pair_orig[p] * n + i;
     dist[o] = w.dist;
