@@ -46,15 +46,15 @@ F_KERNEL = {"k_broadphase": F_BP_FLOP_PER_CONFIG, "k_item_setup": 0.45 * F_NP_FL
 HBM_BYTES_PER_CONFIG = 9 * 4 + 1   # 9 float32 in, 1 verdict byte out
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) and pipe utilisation of
 # the three kernels of a 1 Mi-state round, from the committed `ncu --set full` capture
-# profiles/r01_v4_ncu_summary.txt (cold-cache, serialised launches of this same command):
+# profiles/r01_v5_ncu_summary.txt (cold-cache, serialised launches of this same command):
 NCU = {
-    "source": "profiles/r01_v4_ncu_summary.txt",
-    "k_broadphase": {"traffic_bytes": 37.81e6 + 0.01e6, "fma_pipe_pct": 28.0, "alu_pipe_pct": 64.8, "issue_active_pct": 75.9,
-                     "threads_per_inst": 28.7, "duration_us": 124.4},
-    "k_item_setup": {"traffic_bytes": 41.72e6 + 2.74e6, "fma_pipe_pct": 27.7, "alu_pipe_pct": 36.8, "issue_active_pct": 60.0,
-                     "threads_per_inst": 28.8, "duration_us": 107.7},
-    "k_narrowphase": {"traffic_bytes": 28.37e6 + 0.13e6, "fma_pipe_pct": 22.0, "alu_pipe_pct": 38.2, "issue_active_pct": 54.6,
-                      "threads_per_inst": 13.2, "duration_us": 204.7},
+    "source": "profiles/r01_v5_ncu_summary.txt",
+    "k_broadphase": {"traffic_bytes": 37.81e6 + 0.01e6, "fma_pipe_pct": 32.5, "alu_pipe_pct": 65.4, "issue_active_pct": 76.0,
+                     "threads_per_inst": 27.7, "duration_us": 95.0},
+    "k_item_setup": {"traffic_bytes": 41.71e6 + 1.45e6, "fma_pipe_pct": 27.2, "alu_pipe_pct": 34.2, "issue_active_pct": 58.6,
+                     "threads_per_inst": 29.8, "duration_us": 104.9},
+    "k_narrowphase": {"traffic_bytes": 23.56e6 + 0.23e6, "fma_pipe_pct": 20.3, "alu_pipe_pct": 34.0, "issue_active_pct": 50.0,
+                      "threads_per_inst": 14.3, "duration_us": 158.3},
 }
 
 
