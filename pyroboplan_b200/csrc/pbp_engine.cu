@@ -229,15 +229,20 @@ int launch_round_kernels(pbp_engine *e, const StateSource &src, int64_t n, float
         k_broadphase<MODE, false><<<grid, BP_THREADS, e->smem_bp, st>>>(e->dm, src, n, padding, out, bins);
     LAUNCH_CHECK("k_broadphase");
     if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
-    k_item_setup<MODE><<<e->is_blocks, IS_THREADS, e->smem_is, st>>>(e->dm, src, padding, out, bins, ctrl_tile_setup(e));
+    // persistent kernels: never more blocks than the round can possibly feed (at most one item per
+    // state and pair) -- a single-state call then stages the tables in a handful of blocks, not 444
+    const int64_t max_items = n * (int64_t)e->npairs;
+    const unsigned is_grid = (unsigned)std::min<int64_t>(e->is_blocks, std::max<int64_t>(1, (max_items + IS_THREADS - 1) / IS_THREADS));
+    const unsigned np_grid = (unsigned)std::min<int64_t>(e->np_blocks, std::max<int64_t>(1, (max_items + NP_THREADS - 1) / NP_THREADS));
+    k_item_setup<MODE><<<is_grid, IS_THREADS, e->smem_is, st>>>(e->dm, src, padding, out, bins, ctrl_tile_setup(e));
     LAUNCH_CHECK("k_item_setup");
     if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
     if (e->np_pool)
         k_narrowphase_pool<MODE><<<e->np_pool_blocks, NP_THREADS, e->smem_np_pool, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
     else if (e->verts_in_smem)
-        k_narrowphase<MODE, true><<<e->np_blocks, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
+        k_narrowphase<MODE, true><<<np_grid, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
     else
-        k_narrowphase<MODE, false><<<e->np_blocks, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
+        k_narrowphase<MODE, false><<<np_grid, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
     LAUNCH_CHECK("k_narrowphase");
     return 0;
 }
