@@ -145,10 +145,10 @@ namespace {
 // control block layout (uint32 words): [0, npairs) bin counts, [npairs] item-setup tile counter,
 // [npairs + 1] narrowphase chunk cursor, [npairs + 2, 2 npairs + 2) narrowphase bin counts (items the
 // item setup kept), then four 64-bit counters at an 8-byte aligned offset
-// (level total, emit cursor, select count, profiled item total).
+// (level total, emit cursor, select count, profiled item total, IK work cursor).
 inline size_t ctrl_words(const pbp_engine *e) { return 2 * (size_t)e->npairs + 2; }
 // There are two such blocks (workspaces 0 / 1, see pbp_engine::ws); the 64-bit counters live in block 0.
-inline size_t ctrl_bytes(const pbp_engine *e) { return ((ctrl_words(e) * 4 + 7) & ~(size_t)7) + 32; }
+inline size_t ctrl_bytes(const pbp_engine *e) { return ((ctrl_words(e) * 4 + 7) & ~(size_t)7) + 64; }   // 8 x 64-bit counters
 inline uint32_t *ctrl_base(pbp_engine *e) {
     return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(e->d_ctrl.p) + (size_t)e->ws * ctrl_bytes(e));
 }
@@ -1411,12 +1411,20 @@ extern "C" int pbp_ik_iterate(pbp_engine *e, int32_t frame_id, const double *tar
     o.min_step = opt->min_step_size;
     o.max_step = opt->max_step_size;
     const IkTables *dt = e->d_ik_tables.as<IkTables>();
-    if (tab.npath <= 8)
-        k_ik_iterate<8><<<grid_for(n, 128), 128, 0, st>>>(dt, targets_dev, q_dev, n, o, nullspace_dev, e0_dev, status_dev, iters_dev);
-    else if (tab.npath <= 16)
-        k_ik_iterate<16><<<grid_for(n, 128), 128, 0, st>>>(dt, targets_dev, q_dev, n, o, nullspace_dev, e0_dev, status_dev, iters_dev);
-    else
-        k_ik_iterate<IK_MAX_PATH><<<grid_for(n, 128), 128, 0, st>>>(dt, targets_dev, q_dev, n, o, nullspace_dev, e0_dev, status_dev, iters_dev);
+    unsigned long long *cursor = ctrl_u64(e, 4);
+    CUDA_TRY(cudaMemsetAsync(cursor, 0, 8, st));
+    // persistent lanes (targets are pulled from the cursor): exactly the blocks that are resident at once
+    auto launch = [&](auto kern) -> int {
+        int occ = 1;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, 0));
+        const unsigned grid = (unsigned)std::min<int64_t>((n + 127) / 128, (int64_t)e->num_sms * std::max(occ, 1));
+        kern<<<grid, 128, 0, st>>>(dt, targets_dev, q_dev, n, o, nullspace_dev, e0_dev, status_dev, iters_dev, cursor);
+        return 0;
+    };
+    if (tab.npath <= 8) rc = launch(k_ik_iterate<8>);
+    else if (tab.npath <= 16) rc = launch(k_ik_iterate<16>);
+    else rc = launch(k_ik_iterate<IK_MAX_PATH>);
+    if (rc) return rc;
     LAUNCH_CHECK("k_ik_iterate");
     return 0;
 }

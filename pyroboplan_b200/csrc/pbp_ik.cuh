@@ -103,7 +103,7 @@ template <int MAXP>
 __global__ void __launch_bounds__(128)
 k_ik_iterate(const IkTables *__restrict__ tables, const double *__restrict__ targets, double *__restrict__ q_io, int64_t n,
              IkOptions opt, const double *__restrict__ nullspace, double *__restrict__ e0_io, int32_t *__restrict__ status,
-             int32_t *__restrict__ iters_out) {
+             int32_t *__restrict__ iters_out, unsigned long long *__restrict__ work_cursor) {
     __shared__ IkTables T;
     {
         const int words = (int)(sizeof(IkTables) / 8);
@@ -112,19 +112,46 @@ k_ik_iterate(const IkTables *__restrict__ tables, const double *__restrict__ tar
         for (int k = threadIdx.x; k < words; k += blockDim.x) dst[k] = src[k];
     }
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    // Persistent lanes: a lane runs ONE iteration per trip for its current target and takes the next
+    // target from a global cursor when that one is finished.  Targets need anything from 0 to
+    // max_iters iterations (mean ~25, and ~1 % never converge): with a fixed thread <-> target mapping
+    // every warp would run as long as its slowest lane.
     const int npath = T.npath, nq = T.nq;
-    double *q = q_io + i * nq;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int64_t i = -1;
+    bool have = false, more = true;
+    double *q = q_io;
     double qp[MAXP], J[MAXP][6];
-#pragma unroll
-    for (int k = 0; k < MAXP; k++) qp[k] = k < npath ? q[T.joint[k].idx_q] : 0.0;
     double Tt[12];
-#pragma unroll
-    for (int k = 0; k < 12; k++) Tt[k] = targets[i * 12 + k];
-    double e0 = e0_io[i];
+    double e0 = 0.0;
     int st = 0, it = 0;
-    for (; it < opt.max_iters; it++) {
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, !have);
+        if (need && more) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(work_cursor, (unsigned long long)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + __popc(need) >= (unsigned long long)n) more = false;
+            if (!have) {
+                i = (int64_t)base + __popc(need & lt_mask);
+                if (i < n) {
+                    q = q_io + i * nq;
+#pragma unroll
+                    for (int k = 0; k < MAXP; k++) qp[k] = k < npath ? q[T.joint[k].idx_q] : 0.0;
+#pragma unroll
+                    for (int k = 0; k < 12; k++) Tt[k] = targets[i * 12 + k];
+                    e0 = e0_io[i];
+                    st = 0;
+                    it = 0;
+                    have = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        if (!have) continue;
+        bool done = it >= opt.max_iters;
+        if (!done) {
         double X[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) X[k] = T.frame[k];
@@ -178,8 +205,9 @@ k_ik_iterate(const IkTables *__restrict__ tables, const double *__restrict__ tar
         const double et = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]), er = sqrt(e[3] * e[3] + e[4] * e[4] + e[5] * e[5]);
         if (et < opt.tol_translation && er < opt.tol_rotation) {
             st = 1;
-            break;
+            done = true;
         }
+        if (!done) {
         // null-space term (reference :274-283): the right-hand side becomes e - J ns
         if (nullspace) {
 #pragma unroll
@@ -249,26 +277,32 @@ k_ik_iterate(const IkTables *__restrict__ tables, const double *__restrict__ tar
                     if (isinf(q[k])) bad = true;
                 }
         }
-        if (bad) { it++; break; }
-    }
+        it++;
+        if (bad) done = true;
+        }   // step
+        }   // iteration
+        if (!done) continue;
+        // ---- this target is finished: write back, free the lane
 #pragma unroll
-    for (int k = 0; k < MAXP; k++)
-        if (k < npath) q[T.joint[k].idx_q] = qp[k];
-    if (st & 1) {
-        // wrap EVERY coordinate to [-pi, pi) as the reference does before its limit check (:221-222)
-        const double PI = 3.14159265358979323846;
-        bool within = true;
-        for (int k = 0; k < nq; k++) {
-            double v = q[k] + PI;
-            v = v - (2.0 * PI) * floor(v / (2.0 * PI)) - PI;   // Python's % for a positive modulus
-            q[k] = v;
-            if (v < T.q_lower[k] || v > T.q_upper[k]) within = false;
+        for (int k = 0; k < MAXP; k++)
+            if (k < npath) q[T.joint[k].idx_q] = qp[k];
+        if (st & 1) {
+            // wrap EVERY coordinate to [-pi, pi) as the reference does before its limit check (:221-222)
+            const double PI = 3.14159265358979323846;
+            bool within = true;
+            for (int k = 0; k < nq; k++) {
+                double v = q[k] + PI;
+                v = v - (2.0 * PI) * floor(v / (2.0 * PI)) - PI;   // Python's % for a positive modulus
+                q[k] = v;
+                if (v < T.q_lower[k] || v > T.q_upper[k]) within = false;
+            }
+            if (within) st |= 2;
         }
-        if (within) st |= 2;
+        e0_io[i] = e0;
+        status[i] = st;
+        if (iters_out) iters_out[i] = it;
+        have = false;
     }
-    e0_io[i] = e0;
-    status[i] = st;
-    if (iters_out) iters_out[i] = it;
 }
 
 }  // namespace pbp
