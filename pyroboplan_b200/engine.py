@@ -371,9 +371,12 @@ class CollisionEngine:
         else:
             Qh = self._host_q(Q, self.nq)
             n = Qh.shape[0]
-            hit = np.zeros(n, dtype=np.uint8)
-            dist = np.zeros(n, dtype=np.float32) if return_distance else None
-            pair = np.zeros(n, dtype=np.int32) if return_pair else None
+            # large results land in page-locked memory (torch's caching pinned allocator): the
+            # device -> host copies go straight there instead of through the engine's staging buffer
+            big = n >= 65536
+            hit = torch.empty(n, dtype=torch.uint8, pin_memory=True).numpy() if big else np.zeros(n, dtype=np.uint8)
+            dist = (torch.empty(n, dtype=torch.float32, pin_memory=True).numpy() if big else np.zeros(n, dtype=np.float32)) if return_distance else None
+            pair = (torch.empty(n, dtype=torch.int32, pin_memory=True).numpy() if big else np.zeros(n, dtype=np.int32)) if return_pair else None
             ptr = lambda t: ctypes.c_void_p(t.ctypes.data) if t is not None else None
             _check(self.lib.pbp_check_states_host(self._h, ptr(Qh), n, float(padding), ptr(hit), ptr(dist), ptr(pair)))
             res = [hit.view(np.bool_)]
