@@ -184,11 +184,12 @@ int pbp_sample_free_states(pbp_engine *e, int64_t n_wanted, uint64_t seed, float
  * witness tracking, thread per (pair, state)).  Replaces pinocchio.computeDistances as the
  * reference reads its results -- distanceResults[k].min_distance, getNearestPoint1/2(), normal
  * (src/pyroboplan/core/utils.py:505-516; src/pyroboplan/ik/nullspace_components.py:124-131).
- * Outputs are PAIR-MAJOR in the caller's pair order: dist_dev[k*N + i]; p1/p2/normal_dev
+ * Outputs are PAIR-MAJOR in the caller's pair order: dist_dev[k*N + i] (signed); p1/p2/normal_dev
  * [(k*N + i)*3 ..] in the world frame (each of the three may be NULL).
  *   cutoff   pairs certainly farther apart than this return a lower bound of their distance
  *            (> cutoff) and zero witness data; INFINITY = exact distances everywhere
- * Overlapping pairs report distance 0 and zero witness data (no penetration depth / EPA). */
+ * Overlapping pairs report coal's convention: a NEGATIVE distance (the penetration depth, FP32
+ * Expanding Polytope Algorithm), the deepest points and the normal; p2 - p1 = normal * distance. */
 int pbp_compute_distances(pbp_engine *e, const float *q_dev, int64_t n, float cutoff, float *dist_dev, float *p1_dev,
                           float *p2_dev, float *normal_dev, void *stream);
 

@@ -159,25 +159,24 @@ def all_joint_poses(model, q):
 
 
 def collision_vector_and_jacobians(model, collision_model, orc, pair_idx, q):
-    """(normal * distance, Jcoll1, Jcoll2, distance, intersecting) for one pair."""
+    """(normal * signed distance, Jcoll1, Jcoll2, signed distance, exact) for one pair -- coal's
+    convention: negative distance = penetration depth, normal from geometry 1 to geometry 2."""
     cp = collision_model.collisionPairs[pair_idx]
-    d, pa, pb, inter = orc.pair_distance(q, cp.first, cp.second)
+    d, pa, pb, normal, exact = orc.pair_signed_distance(q, cp.first, cp.second)
     joint_T = all_joint_poses(model, q)
     J1 = point_jacobian(model, joint_T, collision_model.geometryObjects[cp.first].parentJoint, pa)
     J2 = point_jacobian(model, joint_T, collision_model.geometryObjects[cp.second].parentJoint, pb)
-    normal = (pb - pa) / d if (d > 0 and not inter) else np.zeros(3)
-    return normal * d, J1, J2, d, inter
+    return normal * d, J1, J2, d, exact
 
 
 def collision_avoidance_component(model, collision_model, orc, q, dist_padding=0.05, gain=1.0):
-    """Returns (component [nv], any pair overlapping?).  Overlapping pairs contribute with distance 0
-    and a zero normal, as the engine does (no penetration depth)."""
+    """Returns (component [nv], every contributing pair exact?)."""
     comp = np.zeros(model.nv)
-    any_overlap = False
+    all_exact = True
     for k in range(len(collision_model.collisionPairs)):
-        vec, J1, J2, d, inter = collision_vector_and_jacobians(model, collision_model, orc, k, q)
-        any_overlap |= inter
+        vec, J1, J2, d, exact = collision_vector_and_jacobians(model, collision_model, orc, k, q)
         if d > dist_padding:
             continue
+        all_exact &= exact
         comp -= (vec - dist_padding) @ (J2 - J1)
-    return gain * comp, any_overlap
+    return gain * comp, all_exact

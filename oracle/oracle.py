@@ -82,6 +82,8 @@ def _load():
         lib.oracle_fk.restype = None
         lib.oracle_pair_distance.argtypes = [P(_CModel), ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         lib.oracle_pair_distance.restype = ctypes.c_double
+        lib.oracle_pair_signed_distance.argtypes = [P(_CModel), ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        lib.oracle_pair_signed_distance.restype = ctypes.c_double
         lib.oracle_check_states.argtypes = [
             P(_CModel), ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, P(Counters),
@@ -197,6 +199,17 @@ class Oracle:
         out = np.zeros(7)
         d = self.lib.oracle_pair_distance(ctypes.byref(self._cm), _ptr(oMg), int(ga), int(gb), _ptr(out), None)
         return d, out[:3].copy(), out[3:6].copy(), bool(out[6])
+
+    def pair_signed_distance(self, q, ga, gb):
+        """coal's convention: (signed distance -- negative = penetration depth --, nearest/deepest point
+        on a [3], on b [3], unit normal a -> b [3], exact flag) for geometries ga, gb at q."""
+        _, oMg = self.fk(q)
+        return self.pair_signed_distance_placed(oMg, ga, gb)
+
+    def pair_signed_distance_placed(self, oMg, ga, gb):
+        out = np.zeros(10)
+        d = self.lib.oracle_pair_signed_distance(ctypes.byref(self._cm), _ptr(np.ascontiguousarray(oMg)), int(ga), int(gb), _ptr(out), None)
+        return d, out[:3].copy(), out[3:6].copy(), out[6:9].copy(), bool(out[9])
 
     # ------------------------------------------------------------------ states
     def check_states(self, Q, padding=0.0, want_all=False, use_cull=True, nthreads=0):

@@ -79,16 +79,21 @@ def check_collisions_at_state(
 
 
 def get_minimum_distance_at_state(model, collision_model, q, data=None, collision_data=None):
-    """Minimum distance over the active pairs (``np.inf`` without pairs; 0 when penetrating).
+    """Minimum distance over the active pairs (``np.inf`` without pairs); negative when penetrating
+    (the penetration depth, coal's convention).
 
-    Reference: core/utils.py:54-87.
+    Reference: core/utils.py:54-87.  The batched hot path clamps distances at 0; a state it reports
+    as touching / penetrating is re-evaluated pair by pair with the witness kernel, whose EPA gives
+    the signed value.
     """
     if len(collision_model.collisionPairs) == 0:
         return np.inf
-    _, dist = _engine(model, collision_model).check_states(
-        np.asarray(q, dtype=np.float64).reshape(1, -1), 0.0, return_distance=True
-    )
-    return float(dist[0])
+    eng = _engine(model, collision_model)
+    q = np.asarray(q, dtype=np.float64).reshape(1, -1)
+    _, dist = eng.check_states(q, 0.0, return_distance=True)
+    if float(dist[0]) > 0.0:
+        return float(dist[0])
+    return float(eng.compute_distances(q, witness=False)[0].min())
 
 
 def check_collisions_along_path(
@@ -178,7 +183,7 @@ def calculate_collision_vector_and_jacobians(model, collision_model, data, colli
     pair's distance and witness points are computed on the device for ``q``.  The Jacobians --
     ``[I, -skew(r)] @ J_frame(LOCAL_WORLD_ALIGNED)``, i.e. column k = z_k x (p - o_k) for a revolute
     joint on the chain of the geometry's parent joint and z_k for a prismatic one -- are small
-    host arithmetic on the device FK.  Overlapping pairs have distance 0 (no penetration depth).
+    host arithmetic on the device FK.  Overlapping pairs have a negative distance (penetration depth).
     """
     eng = _engine(model, collision_model)
     q = np.asarray(q, dtype=np.float64).reshape(1, -1)

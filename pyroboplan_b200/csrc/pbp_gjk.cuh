@@ -232,6 +232,7 @@ struct GjkOut {
     int hit;      // dist <= margin
     int iters;
     int far;      // finished through the separating-plane bound: dist is a LOWER bound beyond the cut
+    int enclosed; // the tetrahedron (W0, W1, W2, w) contains the origin: the cores overlap
 };
 
 #define PBP_GJK_MAX_ITERS 48
@@ -319,6 +320,7 @@ __device__ __forceinline__ bool gjk_support_phase(const ShapeRef &A, const Shape
 #endif
     out.iters = ++s.it;
     out.far = 0;
+    out.enclosed = 0;
     // <v,w>/|v| is a lower bound of the distance for ANY direction v
     if (vw > 0.f && vw * vw > cut * cut * vv) {
         out.dist = vw * rsqrtf(vv);
@@ -352,6 +354,7 @@ __device__ __forceinline__ bool gjk_simplex_phase(GjkState &s, float margin, Gjk
     const int n = s.n;
     out.iters = s.it;
     out.far = 0;
+    out.enclosed = 0;
     bool done = false, enclosed = false;
     {
         // append w and solve for the closest point of the simplex
@@ -435,6 +438,7 @@ __device__ __forceinline__ bool gjk_simplex_phase(GjkState &s, float margin, Gjk
         if (enclosed || nvv <= PBP_GJK_EPS_ABS2) {
             out.dist = 0.f;
             out.hit = 1;
+            out.enclosed = enclosed ? 1 : 0;
             return true;
         }
         if (!WANT_DIST && nvv <= margin * margin) {  // upper bound already within margin

@@ -479,8 +479,9 @@ class CollisionEngine:
         """Distance (+ witness points and normal) of every active pair for every state.
 
         CUDA tensor in -> CUDA tensors out, numpy in -> numpy out:
-        dist [N, npairs]; with ``witness`` also p1, p2, normal [N, npairs, 3] (world frame; zero for
-        overlapping pairs and for pairs farther than ``cutoff``, whose dist is a lower bound).
+        signed dist [N, npairs] (negative = penetration depth); with ``witness`` also p1, p2, normal
+        [N, npairs, 3] (world frame, normal from geometry 1 to 2, p2 - p1 = normal * dist; zero for pairs
+        farther than ``cutoff``, whose dist is a lower bound).
         The device layout is pair-major; the returned arrays are transposed views."""
         torch = _torch()
         host = not self._is_dev(Q)

@@ -5,7 +5,7 @@ term on the GPU against the float64 oracle and the re
 import numpy as np
 import pytest
 
-from conftest import make_panda, uniform_states
+from conftest import make_panda, uniform_states  # noqa: F401
 from oracle import ik_oracle as ik
 from test_oracle_golden import _contains
 
@@ -21,13 +21,22 @@ def test_distances_and_witness_points(panda_full, panda_oracle):
     dist, p1, p2, nrm = eng.compute_distances(q)
     assert dist.shape == (300, 74) and p1.shape == (300, 74, 3)
     geoms = cmodel.geometryObjects
-    checked = 0
+    checked = penetrating = 0
     for i in range(0, 300, 7):
         _, oMg = panda_oracle.fk(q[i].astype(np.float64))
         for k, cp in enumerate(cmodel.collisionPairs):
             d_ref, pa, pb, inter = panda_oracle.pair_distance(q[i].astype(np.float64), cp.first, cp.second)
-            if inter or dist[i, k] == 0.0:
-                assert d_ref < 1e-5 and dist[i, k] < 1e-5
+            if inter or dist[i, k] <= 0.0:
+                # overlapping: negative distance = penetration depth (coal's convention), FP32 EPA vs the oracle's
+                ds, pas, pbs, ns, exact = panda_oracle.pair_signed_distance(q[i].astype(np.float64), cp.first, cp.second)
+                if exact and abs(ds) > 1e-5:
+                    assert abs(dist[i, k] - ds) < 3e-5, (i, k, dist[i, k], ds)
+                    np.testing.assert_allclose(p2[i, k].astype(np.float64) - p1[i, k], nrm[i, k].astype(np.float64) * dist[i, k], atol=1e-5)
+                    if abs(ds) > 1e-3:
+                        assert nrm[i, k] @ ns > 1.0 - 1e-3
+                    penetrating += 1
+                else:
+                    assert abs(dist[i, k]) < 3e-5 or not exact
                 continue
             assert abs(dist[i, k] - d_ref) < 1e-5          # north_star: distances within 1e-5 m
             a, b = p1[i, k].astype(np.float64), p2[i, k].astype(np.float64)
@@ -36,10 +45,10 @@ def test_distances_and_witness_points(panda_full, panda_oracle):
             if d_ref > 1e-3:
                 np.testing.assert_allclose(nrm[i, k], (pb - pa) / d_ref, atol=2e-3 + 2e-5 / d_ref)
             checked += 1
-    assert checked > 2000
-    # the minimum over the pairs is what check_states(return_distance=True) reports
+    assert checked > 2000 and penetrating > 20
+    # the minimum over the pairs, clamped at 0, is what check_states(return_distance=True) reports
     _, md = eng.check_states(q, return_distance=True)
-    np.testing.assert_allclose(dist.min(axis=1), md, atol=2e-6)
+    np.testing.assert_allclose(np.maximum(dist.min(axis=1), 0.0), md, atol=2e-6)
     # a cutoff only replaces far pairs by lower bounds
     dc = eng.compute_distances(q, cutoff=0.05, witness=False)
     near = dist <= 0.05
@@ -55,15 +64,15 @@ def test_collision_vector_and_jacobians(panda_full, panda_oracle):
     n = 0
     for qi in q:
         for k in range(0, 74, 5):
-            vec_ref, J1_ref, J2_ref, d, inter = ik.collision_vector_and_jacobians(model, cmodel, panda_oracle, k, qi.astype(np.float32).astype(np.float64))
-            if inter or d < 1e-3:
+            vec_ref, J1_ref, J2_ref, d, exact = ik.collision_vector_and_jacobians(model, cmodel, panda_oracle, k, qi.astype(np.float32).astype(np.float64))
+            if not exact or abs(d) < 1e-3:
                 continue
             vec, J1, J2 = calculate_collision_vector_and_jacobians(model, cmodel, None, None, k, qi)
             assert J1.shape == (3, 9) and J2.shape == (3, 9)
             # witness points of parallel faces are not unique: compare what the avoidance term uses,
             # the distance vector and the Jacobians projected on it
-            np.testing.assert_allclose(vec, vec_ref, atol=3e-3 * d + 2e-5)
-            np.testing.assert_allclose(vec_ref @ (J2 - J1), vec_ref @ (J2_ref - J1_ref), atol=5e-3 * d + 1e-5)
+            np.testing.assert_allclose(vec, vec_ref, atol=3e-3 * abs(d) + 2e-5)
+            np.testing.assert_allclose(vec_ref @ (J2 - J1), vec_ref @ (J2_ref - J1_ref), atol=5e-3 * abs(d) + 1e-5)
             n += 1
     assert n > 40
 
@@ -78,13 +87,13 @@ def test_collision_avoidance_component(panda_full, panda_oracle):
     assert comp.shape == (400, 9)
     compared = nonzero = 0
     for i in range(400):
-        ref, overlap = ik.collision_avoidance_component(model, cmodel, panda_oracle, q[i].astype(np.float64), 0.05, 1.0)
-        if overlap:
-            continue    # penetration depth is not modelled (distance 0): covered by the engine's own convention below
+        ref, exact = ik.collision_avoidance_component(model, cmodel, panda_oracle, q[i].astype(np.float64), 0.05, 1.0)
+        if not exact:
+            continue    # a pair touching in a way the oracle's polytope expansion cannot start from
         np.testing.assert_allclose(comp[i], ref, atol=2e-4 + 2e-3 * np.abs(ref).max())
         compared += 1
         nonzero += int(np.abs(ref).max() > 0)
-    assert compared > 100 and nonzero > 20
+    assert compared > 300 and nonzero > 100
 
 
 def test_reference_nullspace_component_tests():
@@ -153,3 +162,21 @@ def test_ik_with_nullspace_components(panda_full, panda_oracle):
         step = np.abs(q_ref - init[i]).max()
         np.testing.assert_allclose(Q1[i], q_ref, atol=1e-9 * max(1.0, step / 1e-3))
         assert np.abs(Q1[i, 7:] - init[i, 7:]).max() > 0 or np.abs(ns_h[i, 7:]).max() == 0   # fingers move by the null-space term only
+
+
+def test_minimum_distance_is_signed(panda_self):
+    """get_minimum_distance_at_state returns coal's signed value: negative (the penetration depth) at the
+    reference's own colliding state (/root/reference/test/core/test_utils.py:129-158), positive at its free states."""
+    from conftest import COLLISION_STATE, FREE_STATE_1, FREE_STATE_2
+    from oracle.oracle import Oracle
+    from pyroboplan_b200.core.utils import get_minimum_distance_at_state
+
+    model, cmodel, _ = panda_self
+    orc = Oracle(model, cmodel)
+    for q in (COLLISION_STATE, FREE_STATE_1, FREE_STATE_2):
+        q32 = q.astype(np.float32).astype(np.float64)
+        ref = min(orc.pair_signed_distance(q32, p.first, p.second)[0] for p in cmodel.collisionPairs)
+        got = get_minimum_distance_at_state(model, cmodel, q)
+        assert got == pytest.approx(ref, abs=3e-5)
+    assert get_minimum_distance_at_state(model, cmodel, COLLISION_STATE) < -1e-3
+    assert get_minimum_distance_at_state(model, cmodel, FREE_STATE_1) == pytest.approx(0.1024, abs=2e-4)   # the survey's independent probe

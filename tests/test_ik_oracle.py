@@ -63,8 +63,8 @@ def test_reference_collision_avoidance_known_answers():
     model, cmodel, _ = make_panda(objects=False)
     orc = Oracle(model, cmodel)
     q_mid = 0.5 * (model.lowerPositionLimit + model.upperPositionLimit)
-    comp, overlap = ik.collision_avoidance_component(model, cmodel, orc, q_mid)
-    assert comp.shape == (9,) and np.all(comp == 0.0) and not overlap
+    comp, exact = ik.collision_avoidance_component(model, cmodel, orc, q_mid)
+    assert comp.shape == (9,) and np.all(comp == 0.0) and exact
     q = np.array([1.98103111, 0.27084068, -1.60819541, -3.07282607, -0.56607161, 2.2466373, 2.80244523, 0.01154539, 0.00453211])
     comp, _ = ik.collision_avoidance_component(model, cmodel, orc, q, dist_padding=0.05, gain=1.0)
     assert not np.all(comp == 0.0)

@@ -199,3 +199,41 @@ def test_edge_semantics(panda_full, panda_oracle):
             assert fb[e] == int(np.argmax(per_state))
         else:
             assert fb[e] == -1
+
+
+@pytest.mark.parametrize("which", ["panda", "two_dof"])
+def test_penetration_depth_certificates(which):
+    """The oracle's EPA (negative distances, coal's convention) is PROVED without EPA or GJK:
+    the support function of A - B along the reported normal equals the depth (so translating B by
+    depth * normal makes the shapes touch), no sampled direction gives a smaller value (the depth is
+    the minimum translation), the deepest points lie in their shapes and differ by normal * distance,
+    and separated pairs agree with the unsigned distance."""
+    model, cmodel, _ = make_panda() if which == "panda" else make_two_dof()
+    orc = Oracle(model, cmodel)
+    geoms = cmodel.geometryObjects
+    rng = np.random.default_rng(9)
+    q = uniform_states(model, 150 if which == "panda" else 1500, 77).astype(np.float64)
+    dirs = rng.normal(size=(400, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    penetrating = 0
+    for qi in q:
+        _, oMg = orc.fk(qi)
+        for p in cmodel.collisionPairs:
+            a, b = p.first, p.second
+            d0, _, _, inter = orc.pair_distance(qi, a, b)
+            d, pa, pb, n, exact = orc.pair_signed_distance(qi, a, b)
+            if not inter:
+                assert d == pytest.approx(d0, abs=1e-12) and d > 0
+                continue
+            if not exact:
+                continue
+            penetrating += 1
+            assert d <= 0.0 and np.linalg.norm(n) == pytest.approx(1.0, abs=1e-9)
+            tol = 1e-7 if which == "panda" else 2e-6       # the 2-DOF cylinder is curved: EPA converges asymptotically
+            width = _support_extent(geoms[a], oMg[a], n) + _support_extent(geoms[b], oMg[b], -n)
+            assert width == pytest.approx(-d, abs=tol)                     # depth along the normal
+            others = [_support_extent(geoms[a], oMg[a], u) + _support_extent(geoms[b], oMg[b], -u) for u in dirs[:60]]
+            assert min(others) >= -d - tol                                   # and no direction does better
+            assert _contains(geoms[a], oMg[a], pa, 1e-6) and _contains(geoms[b], oMg[b], pb, 1e-6)
+            np.testing.assert_allclose(pb - pa, n * d, atol=1e-6)            # p2 - p1 = normal * signed distance
+    assert penetrating > 30
