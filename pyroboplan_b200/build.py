@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-Xcompiler",
     "-fPIC",
     "-shared",
-    "-lnvrtc",  # model-specialised broadphase is compiled at engine creation (pbp_jit.h)
+    "-ldl",  # NVRTC (model-specialised broadphase, pbp_jit.h) and nothing else is dlopen'ed at run time
 ]
 
 

@@ -13,6 +13,7 @@
 // generic kernel.  Set PBP_NO_JIT=1 to disable.
 #pragma once
 #include <cuda.h>
+#include <dlfcn.h>
 #include <nvrtc.h>
 
 #include <cmath>
@@ -328,28 +329,61 @@ inline std::string generate_broadphase(const Input &in) {
 }
 
 // ---- NVRTC: source -> cubin for sm_XYa, cached per process by source text
+// NVRTC is loaded at run time (dlopen): the engine library has no link-time dependency on it, and a
+// machine without it simply keeps the generic kernel.
+struct NvrtcApi {
+    nvrtcResult (*createProgram)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+    nvrtcResult (*compileProgram)(nvrtcProgram, int, const char *const *) = nullptr;
+    nvrtcResult (*getProgramLogSize)(nvrtcProgram, size_t *) = nullptr;
+    nvrtcResult (*getProgramLog)(nvrtcProgram, char *) = nullptr;
+    nvrtcResult (*getCUBINSize)(nvrtcProgram, size_t *) = nullptr;
+    nvrtcResult (*getCUBIN)(nvrtcProgram, char *) = nullptr;
+    nvrtcResult (*destroyProgram)(nvrtcProgram *) = nullptr;
+    bool ok = false;
+};
+inline const NvrtcApi &nvrtc_api() {
+    static NvrtcApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *h = nullptr;
+        for (const char *name : {"libnvrtc.so.12", "libnvrtc.so", "libnvrtc.so.13"})
+            if ((h = dlopen(name, RTLD_NOW | RTLD_LOCAL))) break;
+        if (h) {
+            auto get = [&](const char *sym, void **fn) { *fn = dlsym(h, sym); return *fn != nullptr; };
+            api.ok = get("nvrtcCreateProgram", (void **)&api.createProgram) && get("nvrtcCompileProgram", (void **)&api.compileProgram) &&
+                     get("nvrtcGetProgramLogSize", (void **)&api.getProgramLogSize) && get("nvrtcGetProgramLog", (void **)&api.getProgramLog) &&
+                     get("nvrtcGetCUBINSize", (void **)&api.getCUBINSize) && get("nvrtcGetCUBIN", (void **)&api.getCUBIN) &&
+                     get("nvrtcDestroyProgram", (void **)&api.destroyProgram);
+        }
+    }
+    return api;
+}
+
 inline int compile(const std::string &src, int cc_major, int cc_minor, std::vector<char> &cubin, std::string &log) {
     static std::mutex mu;
     static std::map<std::string, std::vector<char>> cache;
     std::lock_guard<std::mutex> lock(mu);
+    const NvrtcApi &rt = nvrtc_api();
+    if (!rt.ok) { log = "NVRTC (libnvrtc.so) is not available"; return -1; }
     char arch[64];
     snprintf(arch, sizeof arch, "--gpu-architecture=sm_%d%d%s", cc_major, cc_minor, cc_major >= 9 ? "a" : "");
     const std::string key = std::string(arch) + "\n" + src;
     auto it = cache.find(key);
     if (it != cache.end()) { cubin = it->second; return 0; }
     nvrtcProgram prog;
-    if (nvrtcCreateProgram(&prog, src.c_str(), "pbp_bp_spec.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { log = "nvrtcCreateProgram failed"; return -1; }
+    if (rt.createProgram(&prog, src.c_str(), "pbp_bp_spec.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { log = "nvrtcCreateProgram failed"; return -1; }
     const char *opts[] = {arch, "--fmad=false", "-lineinfo", "--std=c++17"};
-    const nvrtcResult rc = nvrtcCompileProgram(prog, 4, opts);
+    const nvrtcResult rc = rt.compileProgram(prog, 4, opts);
     size_t ls = 0;
-    nvrtcGetProgramLogSize(prog, &ls);
-    if (ls > 1) { log.resize(ls); nvrtcGetProgramLog(prog, &log[0]); }
-    if (rc != NVRTC_SUCCESS) { nvrtcDestroyProgram(&prog); return -1; }
+    rt.getProgramLogSize(prog, &ls);
+    if (ls > 1) { log.resize(ls); rt.getProgramLog(prog, &log[0]); }
+    if (rc != NVRTC_SUCCESS) { rt.destroyProgram(&prog); return -1; }
     size_t cs = 0;
-    if (nvrtcGetCUBINSize(prog, &cs) != NVRTC_SUCCESS || cs == 0) { nvrtcDestroyProgram(&prog); log += " (no cubin)"; return -1; }
+    if (rt.getCUBINSize(prog, &cs) != NVRTC_SUCCESS || cs == 0) { rt.destroyProgram(&prog); log += " (no cubin)"; return -1; }
     cubin.resize(cs);
-    nvrtcGetCUBIN(prog, cubin.data());
-    nvrtcDestroyProgram(&prog);
+    rt.getCUBIN(prog, cubin.data());
+    rt.destroyProgram(&prog);
     cache[key] = cubin;
     return 0;
 }
