@@ -36,7 +36,10 @@ namespace pbp {
 constexpr int BP_THREADS = 128;
 constexpr int NP_THREADS = 256;
 constexpr int IS_THREADS = 256;
-constexpr int TILE_ITEMS = 128;    // items of one pair handed to a warp per tile fetch
+#ifndef PBP_TILE_ITEMS
+#define PBP_TILE_ITEMS 64    // measured: 128 -> 99.7 us, 64 -> 98.5 us (1 Mi states), 41.4 -> 38.6 us (256 Ki); 32 and 256 are worse
+#endif
+constexpr int TILE_ITEMS = PBP_TILE_ITEMS;    // items of one pair handed to a warp per tile fetch
 constexpr int BP_MAX_LOCAL_CENTRES = PBP_MAX_GEOMS;
 constexpr int BP_MAX_SAVES = 16;
 constexpr float BP_SLACK = 2e-5f;  // broadphase decisions keep this margin (metres) for FP32 rounding
@@ -526,7 +529,10 @@ k_item_setup(DevModel M, StateSource src, float padding, Outputs out, Bins bins,
 // item of the chunk.  A lane carries its own pair (neighbouring items almost always share it, so
 // shape tables are read at the same shared-memory addresses), which means a warp never has to
 // drain when it crosses from one bin into the next.
-constexpr int NP_CHUNK = 128;
+#ifndef PBP_NP_CHUNK
+#define PBP_NP_CHUNK 128
+#endif
+constexpr int NP_CHUNK = PBP_NP_CHUNK;
 #ifndef PBP_NP_QUORUM
 #define PBP_NP_QUORUM 12
 #endif
