@@ -1,14 +1,14 @@
 #!/bin/bash
-# One gpurun call: smoke, bench (ours + reference arm), ncu launch list, ncu full capture of the two hot kernels.
+# Regenerates every measured artefact of a round in ONE gpurun call (copy the results into profiles/):
+#   gpurun --timeout 1800 -- 'bash tools/gpu_round1.sh'
+# smoke, GPU test suite, bench (ours + reference arm), per-config timings, single-query latency,
+# ncu launch list + full capture of one round's three kernels.
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; echo "rc=$?" >> gpurun_out/bench_ours.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
-export PBP_CPU_SAMPLE=20000
-python bench.py --steps 2 --warmup 3 > gpurun_out/plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_list.log 2>&1
-python bench.py --steps 2 --warmup 3 > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_narrowphase -s 3 -c 2 -o gpurun_out/prof_narrowphase python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_np.log 2>&1
-python bench.py --steps 2 --warmup 3 > gpurun_out/plain3.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_broadphase -s 3 -c 2 -o gpurun_out/prof_broadphase python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_bp.log 2>&1
-ls -la gpurun_out
+python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; tail -1 gpurun_out/pytest_gpu.log
+python bench.py > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; echo "rc=$?" >> gpurun_out/bench_ours.err
+python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+python tools/gpu_configs_bench.py > gpurun_out/configs_bench.json 2>&1
+python tools/gpu_latency.py > gpurun_out/latency.log 2>&1
+bash tools/gpu_ncu.sh
+ls -la gpurun_out | tail -20
