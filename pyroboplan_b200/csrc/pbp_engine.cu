@@ -1445,7 +1445,7 @@ extern "C" int pbp_knn(pbp_engine *e, const float *nodes_dev, int64_t n, int32_t
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = knn_smem_bytes(e->nq, k);
     const double r2 = std::isinf(radius) ? INFINITY : radius * radius;
-    const unsigned grid = grid_for(n, KNN_THREADS);
+    const unsigned grid = grid_for(n, KNN_QUERIES);
 #define KNN_LAUNCH(NQ)                                                                                                   \
     do {                                                                                                                 \
         CUDA_TRY(cudaFuncSetAttribute(k_knn<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \

@@ -6,18 +6,22 @@
 // first k.  "Predecessor" mode mirrors the reference's incremental construction, where node i only
 // sees the nodes inserted before it (j < i).
 //
-// One thread per query node; candidates stream through shared memory in tiles, so every node is
-// read from HBM once per block of KNN_THREADS queries (N = 20 k, nq = 9: 720 KB, L2 resident).
-// Distances accumulate in FP64 (the nodes are float32, hence exact in FP64; the reference orders
-// float64 norms) -- 20 k x 20 k x 9 DFMA is ~3.6 GFLOP, noise for the chip.  The k best live in a
-// thread-interleaved shared-memory array kept sorted by insertion; almost every candidate fails
-// the first comparison against the current k-th best.
+// KNN_SPLIT threads share one query node: candidates stream through shared memory in tiles and
+// thread s of a query takes candidates s, s + KNN_SPLIT, ... of every tile, keeping its own sorted
+// top-k in thread-interleaved shared memory (almost every candidate fails the first comparison
+// against the current k-th best); the KNN_SPLIT lists are merged at the end, ties resolved by
+// index.  (One thread per query left a 20 k-node roadmap with ~1 block per SM: 4.2 ms; splitting
+// gives the SMs 8x the threads.)  Distances accumulate in FP64: the nodes are float32, hence exact
+// in FP64, and the reference orders float64 norms -- 20 k x 20 k x 9 DFMA is ~3.6 GFLOP, noise for
+// the chip.
 #pragma once
 #include <stdint.h>
 
 namespace pbp {
 
 constexpr int KNN_THREADS = 128;
+constexpr int KNN_SPLIT = 8;                          // threads per query
+constexpr int KNN_QUERIES = KNN_THREADS / KNN_SPLIT;  // queries per block
 constexpr int KNN_TILE = 128;
 constexpr int KNN_MAX_K = 64;
 constexpr int KNN_MAX_NQ = 64;
@@ -26,7 +30,7 @@ inline size_t knn_smem_bytes(int nq, int k) {
     return (size_t)KNN_TILE * nq * 4 + (size_t)k * KNN_THREADS * (8 + 4) + 16;
 }
 
-// NQ > 0: query coordinates in registers; NQ == 0: any nq <= KNN_MAX_NQ (query re-read from shared memory)
+// NQ > 0: query coordinates in registers; NQ == 0: any nq <= KNN_MAX_NQ (query re-read from global memory)
 template <int NQ>
 __global__ void __launch_bounds__(KNN_THREADS)
 k_knn(const float *__restrict__ nodes, int64_t n, int nq_dyn, int k, double radius2, int predecessors_only,
@@ -37,8 +41,9 @@ k_knn(const float *__restrict__ nodes, int64_t n, int nq_dyn, int k, double radi
     int32_t *si = reinterpret_cast<int32_t *>(knn_smem + (size_t)k * KNN_THREADS * 8);     // [k][KNN_THREADS]
     float *tile = reinterpret_cast<float *>(knn_smem + (size_t)k * KNN_THREADS * 12);      // [KNN_TILE][nq]
     const int tid = threadIdx.x;
-    const int64_t i0 = (int64_t)blockIdx.x * KNN_THREADS;
-    const int64_t i = i0 + tid;
+    const int sub = tid % KNN_SPLIT;                      // which slice of every tile this thread scans
+    const int64_t i0 = (int64_t)blockIdx.x * KNN_QUERIES;
+    const int64_t i = i0 + tid / KNN_SPLIT;
     const bool live = i < n;
     float qi[NQ > 0 ? NQ : 1];
     if (NQ > 0 && live) {
@@ -46,8 +51,8 @@ k_knn(const float *__restrict__ nodes, int64_t n, int nq_dyn, int k, double radi
         for (int c = 0; c < NQ; c++) qi[c] = nodes[i * NQ + c];
     }
     for (int s = 0; s < k; s++) { sd[s * KNN_THREADS + tid] = INFINITY; si[s * KNN_THREADS + tid] = -1; }
-    double worst = INFINITY;   // k-th best so far (radius2 until k are found is handled by the radius test)
-    const int64_t j_end = predecessors_only ? min(n, i0 + KNN_THREADS) : n;
+    double worst = INFINITY;   // this thread's k-th best so far
+    const int64_t j_end = predecessors_only ? min(n, i0 + KNN_QUERIES) : n;
     for (int64_t j0 = 0; j0 < j_end; j0 += KNN_TILE) {
         const int cnt = (int)min((int64_t)KNN_TILE, j_end - j0);
         __syncthreads();
@@ -55,7 +60,7 @@ k_knn(const float *__restrict__ nodes, int64_t n, int nq_dyn, int k, double radi
         __syncthreads();
         if (!live) continue;
         const int lim = predecessors_only ? (int)min((int64_t)cnt, i - j0) : cnt;   // j < i only
-        for (int jj = 0; jj < lim; jj++) {
+        for (int jj = sub; jj < lim; jj += KNN_SPLIT) {
             const int64_t j = j0 + jj;
             if (j == i) continue;
             double d2 = 0.0;
@@ -84,10 +89,30 @@ k_knn(const float *__restrict__ nodes, int64_t n, int nq_dyn, int k, double radi
             worst = sd[(k - 1) * KNN_THREADS + tid];
         }
     }
-    if (!live) return;
+    __syncthreads();
+    if (!live || sub != 0) return;
+    // merge the KNN_SPLIT sorted lists of this query: smallest (distance, index) first
+    int head[KNN_SPLIT];
+#pragma unroll
+    for (int t = 0; t < KNN_SPLIT; t++) head[t] = 0;
     for (int s = 0; s < k; s++) {
-        idx_out[i * k + s] = si[s * KNN_THREADS + tid];
-        dist_out[i * k + s] = si[s * KNN_THREADS + tid] >= 0 ? (float)sqrt(sd[s * KNN_THREADS + tid]) : INFINITY;
+        double bd = INFINITY;
+        int32_t bi = -1;
+        int bt = -1;
+#pragma unroll
+        for (int t = 0; t < KNN_SPLIT; t++) {
+            if (head[t] >= k) continue;
+            const double d = sd[head[t] * KNN_THREADS + tid + t];
+            const int32_t ix = si[head[t] * KNN_THREADS + tid + t];
+            if (ix >= 0 && (d < bd || (d == bd && ix < bi))) { bd = d; bi = ix; bt = t; }
+        }
+        if (bt >= 0) {
+#pragma unroll
+            for (int t = 0; t < KNN_SPLIT; t++)
+                if (t == bt) head[t]++;
+        }
+        idx_out[i * k + s] = bi;
+        dist_out[i * k + s] = bi >= 0 ? (float)sqrt(bd) : INFINITY;
     }
 }
 
