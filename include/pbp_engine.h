@@ -148,8 +148,8 @@ int pbp_check_states_host(pbp_engine *e, const float *q_host, int64_t n, float p
  * discretize_joint_space_path (planning/utils.py:114-140) + check_collisions_along_path
  * (core/utils.py:90-132).  hit[e] = 1 iff any sample collides (edge NOT free).
  *   first_bad[e] = smallest colliding sample index, -1 if none (nullable; disables early-out)
- * Samples are tested coarse to fine (every 128th, 64th, ... sample; edges already known to collide
- * are dropped between levels); batches of <= 16384 edges use two levels, <= 512 edges one, because
+ * Samples are tested coarse to fine (every 32nd sample, then every 4th, then the rest; edges already
+ * known to collide are dropped between levels); batches of <= 16384 edges use two levels, <= 512 one, because
  * every level costs a device -> host round trip.  This entry point therefore SYNCHRONISES `stream`
  * internally; the _host variant needs no intermediate round trip for <= 512 edges. */
 int pbp_check_edges(pbp_engine *e, const float *q1_dev, const float *q2_dev, int64_t n_edges, double step, float padding,
