@@ -4,8 +4,10 @@
 ``solve`` keeps the reference's control flow (tries, wrap, limit check, collision gate, random
 restarts drawn from the global ``np.random`` stream) but runs a whole try -- up to ``max_iters``
 damped-least-squares iterations -- in one device call.  ``solve_batch`` does the same for N targets
-at once (BASELINE.json config 5): every try is one kernel launch over the still-unsolved targets,
-the collision gate is one batched ``check_states`` and restarts come from the device sampler.
+at once (BASELINE.json config 5): the first try is one kernel launch over all targets, then ALL
+random restarts of every still-unsolved target run in one more launch (the earliest successful
+restart wins, as in the reference's sequential loop); the collision gate is one batched
+``check_states`` and restarts come from the device sampler.
 Null-space components (host callables ``lambda model, q: ...`` as in the reference; batched
 callables ``lambda model, Q: ...`` on CUDA tensors for ``solve_batch``) are re-evaluated every
 iteration, so with them a try runs one device call per iteration instead of one per try.
@@ -203,22 +205,42 @@ class DifferentialIk:
         e0 = torch.zeros(n, dtype=torch.float64, device=dev)
         solved = torch.zeros(n, dtype=torch.bool, device=dev)
         tries = torch.zeros(n, dtype=torch.int32, device=dev)
-        pending = torch.arange(n, device=dev)
-        for n_tries in range(self.options.max_retries + 1):
-            if pending.numel() == 0:
-                break
-            ns_fn = (lambda Qt: sum(comp(self.model, Qt) for comp in nullspace_components)) if nullspace_components else None
-            Qo, status, _, e0p = self._try(eng, frame_id, T[pending], Q[pending], e0[pending], mask, w_diag, ns_fn)
-            e0[pending] = e0p
+        ns_fn = (lambda Qt: sum(comp(self.model, Qt) for comp in nullspace_components)) if nullspace_components else None
+
+        def attempt(idx, Qin):
+            """One try for the targets idx from the states Qin -> (Q_out, accepted, e0_out)."""
+            Qo, status, _, e0p = self._try(eng, frame_id, T[idx], Qin, e0[idx], mask, w_diag, ns_fn)
             ok = (status & 3) == 3
             if has_pairs and ok.any():
                 hit = eng.check_states(Qo[ok].to(torch.float32))
                 ok_idx = torch.nonzero(ok).flatten()
                 ok[ok_idx[hit]] = False
-            Q[pending] = Qo
-            solved[pending[ok]] = True
-            tries[pending] += 1
-            pending = pending[~ok]
-            if pending.numel() and n_tries < self.options.max_retries:
-                Q[pending] = random_states(pending.numel(), n_tries + 1)
+            return Qo, ok, e0p
+
+        # first try: every target from its initial state
+        everyone = torch.arange(n, device=dev)
+        Qo, ok, e0p = attempt(everyone, Q)
+        e0[:] = e0p            # the initial error norm is captured once per solve and kept across retries (:200,264-265)
+        Q[:] = Qo
+        solved[ok] = True
+        tries[:] = 1
+        pending = everyone[~ok]
+        R = int(self.options.max_retries)
+        if pending.numel() and R > 0:
+            # The retries of a target are independent random restarts, and the reference returns the
+            # FIRST one that succeeds.  A try is latency-bound (up to max_iters dependent iterations,
+            # ~3 ms on the device however few targets are left), so all R restarts of every pending
+            # target run in ONE launch and the earliest successful one is kept: same outcome as the
+            # sequential loop for the same restart draws, one launch latency instead of R.
+            P = pending.numel()
+            restarts = random_states(P * R, 1).reshape(P, R, -1)
+            idx = pending.repeat_interleave(R)
+            Qr, okr, _ = attempt(idx, restarts.reshape(P * R, -1))
+            okr = okr.reshape(P, R)
+            any_ok = okr.any(dim=1)
+            first = torch.argmax(okr.to(torch.int8), dim=1)              # earliest successful restart
+            chosen = torch.where(any_ok, first, torch.full_like(first, R - 1))   # none: report the last try's state
+            Q[pending] = Qr.reshape(P, R, -1)[torch.arange(P, device=dev), chosen]
+            solved[pending] = any_ok
+            tries[pending] = (1 + torch.where(any_ok, first + 1, torch.full_like(first, R))).to(torch.int32)
         return Q, solved, tries
