@@ -119,6 +119,8 @@ struct pbp_engine {
     float spec_thr_padding = -1.f;
     std::vector<float> spec_r_out, spec_r_in;      // per internal pair, for the per-call thresholds
     std::vector<uint8_t> spec_exact;
+    int64_t small_items = 400000;   // (pair, state) items up to which boolean queries use the fused k_small_check (measured crossover with the pipeline: ~8 k Panda states = 600 k items)
+    PinnedBuffer h_desc;            // host-built sample descriptors of small edge batches
     int ws = 0;
     bool ws_split = false;
     cudaStream_t s_comp2 = nullptr;
@@ -599,6 +601,7 @@ void pbp_engine_destroy(pbp_engine *e) {
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     e->h_io_hit.release(); e->h_io_f32.release(); e->h_io_i32.release();
     if (e->spec_module && driver_api().ok) driver_api().moduleUnload(e->spec_module);
+    e->h_desc.release();
     for (cudaEvent_t ev : e->io_events) cudaEventDestroy(ev);
     if (e->s_copy) cudaStreamDestroy(e->s_copy);
     if (e->s_comp) cudaStreamDestroy(e->s_comp);
@@ -822,6 +825,7 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
         return bail(rc);
     CUDA_TRY(cudaMemset(e->d_ctrl.p, 0, 2 * ctrl_bytes(e)));
     CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&e->h_pinned), 64));
+    if (const char *sm = getenv("PBP_SMALL_ITEMS")) e->small_items = atoll(sm);
     if (const char *hs = getenv("PBP_HOST_SLICE")) {
         const long long v = atoll(hs);
         if (v >= 1024) e->host_slice = v;
@@ -866,6 +870,18 @@ int pbp_check_states(pbp_engine *e, const float *q_dev, int64_t n, float padding
     }
     // min distance wins over first_pair for the mode; both requested -> two passes
     const int mode = min_dist_dev ? MODE_DIST : (first_pair_dev ? MODE_BOOL_ALL : MODE_BOOL);
+    if (mode == MODE_BOOL && e->npairs > 0 && n * (int64_t)e->npairs <= e->small_items) {
+        // small batch: FK + proxies + GJK fused in one launch
+        StateSource src{};
+        src.q = q_dev;
+        src.mode = 0;
+        Outputs out{};
+        out.hit = hit_dev;
+        k_small_check<<<grid_for(n * e->npairs, SMALL_THREADS), SMALL_THREADS, 0, st>>>(e->dm, src, n, padding, out);
+        LAUNCH_CHECK("k_small_check");
+        e->stats.states += n;
+        return 0;
+    }
     for (int64_t off = 0; off < n; off += round_cap(e)) {
         const int64_t cnt = std::min(round_cap(e), n - off);
         StateSource src{};
@@ -952,8 +968,44 @@ int pbp_discretize_fill(pbp_engine *e, const float *q1_dev, const float *q2_dev,
 // known_total >= 0: the caller already knows the number of samples of all edges together (host
 // entry point with few edges): the single-level path then needs no device -> host round trip.
 static int check_edges_core(pbp_engine *e, const float *q1_dev, const float *q2_dev, int64_t n_edges, double step, float padding,
-                            uint8_t *hit_dev, int32_t *first_bad_dev, void *stream, int64_t known_total) {
+                            uint8_t *hit_dev, int32_t *first_bad_dev, void *stream, int64_t known_total,
+                            const int32_t *host_counts = nullptr) {
     int rc = check_args(e, q1_dev, n_edges);
+    if (host_counts && known_total >= 0 && !first_bad_dev && e->npairs > 0 && n_edges > 0 && q2_dev && hit_dev && step > 0.0 &&
+        padding >= 0.0f && known_total * (int64_t)e->npairs <= e->small_items) {
+        // few samples in total: descriptors (edge, fraction) built here, one fused launch
+        // (no count / emit kernels, no refinement levels, no device -> host round trip)
+        if (rc) return rc;
+        CUDA_TRY(cudaSetDevice(e->device));
+        cudaStream_t st = (cudaStream_t)stream;
+        CUDA_TRY(cudaMemsetAsync(hit_dev, 0, (size_t)n_edges, st));
+        if (known_total == 0) return 0;
+        const size_t tot = (size_t)known_total;
+        if ((rc = e->h_desc.ensure(tot * 8)) || (rc = e->d_desc_group.ensure(tot * 4)) || (rc = e->d_desc_frac.ensure(tot * 4))) return rc;
+        int32_t *hg = (int32_t *)e->h_desc.p;
+        float *hf = (float *)((char *)e->h_desc.p + tot * 4);
+        size_t o = 0;
+        for (int64_t ed = 0; ed < n_edges; ed++) {
+            const int nn = host_counts[ed];
+            const float inv = nn > 1 ? 1.0f / (float)(nn - 1) : 0.f;       // the same expression as k_level_emit
+            for (int i = 0; i < nn; i++, o++) {
+                hg[o] = (int32_t)ed;
+                hf[o] = (i == nn - 1 && nn > 1) ? 1.0f : (float)i * inv;
+            }
+        }
+        CUDA_TRY(cudaMemcpyAsync(e->d_desc_group.p, hg, tot * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(e->d_desc_frac.p, hf, tot * 4, cudaMemcpyHostToDevice, st));
+        StateSource src{};
+        src.q1 = q1_dev; src.q2 = q2_dev;
+        src.group = e->d_desc_group.as<int32_t>(); src.frac = e->d_desc_frac.as<float>();
+        src.mode = 1;
+        Outputs out{};
+        out.hit = hit_dev;
+        k_small_check<<<grid_for((int64_t)tot * e->npairs, SMALL_THREADS), SMALL_THREADS, 0, st>>>(e->dm, src, (int64_t)tot, padding, out);
+        LAUNCH_CHECK("k_small_check");
+        e->stats.states += (int64_t)tot;
+        return 0;
+    }
     if (rc) return rc;
     if (n_edges > 0 && (!q2_dev || !hit_dev)) return fail(PBP_ERR_ARG, "NULL buffer");
     if (!(step > 0.0)) return fail(PBP_ERR_ARG, "step must be > 0");
@@ -1150,25 +1202,29 @@ int pbp_check_edges_host(pbp_engine *e, const float *q1_host, const float *q2_ho
     // few edges: the sample counts are cheap to compute here (the same FP64 expression as
     // k_edge_counts), which spares the single-level path its only device -> host round trip
     int64_t known_total = -1;
+    std::vector<int32_t> hcounts;
     if (n_edges <= 512 && step > 0.0) {
         known_total = 0;
+        hcounts.resize((size_t)n_edges);
         for (int64_t i = 0; i < n_edges; i++) {
             double acc = 0.0;
             for (int k = 0; k < e->nq; k++) {
                 const double dlt = (double)q2_host[i * e->nq + k] - (double)q1_host[i * e->nq + k];
                 acc += dlt * dlt;
             }
-            known_total += (int64_t)((int32_t)ceil(sqrt(acc) / step) + 1);
+            hcounts[(size_t)i] = (int32_t)ceil(sqrt(acc) / step) + 1;
+            known_total += hcounts[(size_t)i];
         }
     }
+    const bool fused = known_total >= 0 && !first_bad_host && e->npairs > 0 && known_total * (int64_t)e->npairs <= e->small_items;
     rc = check_edges_core(e, e->d_io_q.as<float>(), e->d_io_q2.as<float>(), n_edges, step, padding, e->d_io_hit.as<uint8_t>(),
-                          first_bad_host ? e->d_io_i32.as<int32_t>() : nullptr, st, known_total);
+                          first_bad_host ? e->d_io_i32.as<int32_t>() : nullptr, st, known_total, hcounts.empty() ? nullptr : hcounts.data());
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(hit_host, e->d_io_hit.p, (size_t)n_edges, cudaMemcpyDeviceToHost, st));
     if (first_bad_host) CUDA_TRY(cudaMemcpyAsync(first_bad_host, e->d_io_i32.p, (size_t)n_edges * 4, cudaMemcpyDeviceToHost, st));
-    if (known_total > 0 && e->npairs > 0) CUDA_TRY(cudaMemcpyAsync(e->h_pinned, ctrl_u64(e, 1), 8, cudaMemcpyDeviceToHost, st));
+    if (known_total > 0 && e->npairs > 0 && !fused) CUDA_TRY(cudaMemcpyAsync(e->h_pinned, ctrl_u64(e, 1), 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    if (known_total > 0 && e->npairs > 0 && (int64_t)e->h_pinned[0] != known_total) {
+    if (known_total > 0 && e->npairs > 0 && !fused && (int64_t)e->h_pinned[0] != known_total) {
         // host and device sample counts disagree (never observed: both are the same IEEE FP64
         // expression): redo the batch on the path that asks the device
         rc = check_edges_core(e, e->d_io_q.as<float>(), e->d_io_q2.as<float>(), n_edges, step, padding, e->d_io_hit.as<uint8_t>(),

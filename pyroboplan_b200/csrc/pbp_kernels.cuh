@@ -945,6 +945,97 @@ k_narrowphase_pool(DevModel M, float padding, Outputs out, Bins bins, uint32_t *
 }
 
 // ------------------------------------------------------------------------------------------
+// Small batches: one fused kernel, one thread per (pair, state)
+// ------------------------------------------------------------------------------------------
+// The three-kernel pipeline is built for throughput; a single state or a single edge (the calls of a
+// sequential RRT loop) pays three latency-bound launches plus their memsets.  For at most a few
+// ten thousand (pair, state) items this kernel does everything in one launch: FK of the pair's two
+// geometries along its joint path, the broadphase's proxy classification (same thresholds), and --
+// only where that is undecided -- the whole GJK.  Boolean verdicts only.
+constexpr int SMALL_THREADS = 128;
+
+__global__ void __launch_bounds__(SMALL_THREADS)
+k_small_check(DevModel M, StateSource src, int64_t n_states, float padding, Outputs out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_states * M.npairs) return;
+    const int p = (int)(t / n_states);                  // pair-major: the lanes of a warp share the pair
+    const int64_t state = t - (int64_t)p * n_states;
+    const int32_t group = src.group ? src.group[state] : (int32_t)state;
+    if (out.hit[group]) return;                         // already decided by another item of this launch
+    const BpPair pr = M.bppairs[p];
+    const DevGeom &GA = M.geoms[pr.a];
+    const DevGeom &GB = M.geoms[pr.b];
+    auto qval = [&](int k) {
+        if (src.mode == 0) return __ldg(src.q + state * M.nq + k);
+        const float f = src.frac[state];
+        const float qa = __ldg(src.q1 + (int64_t)group * M.nq + k), qb = __ldg(src.q2 + (int64_t)group * M.nq + k);
+        return fmaf(f, qb - qa, qa);
+    };
+    // ---- relative placement of b in a's frame (as k_item_setup)
+    const PairPath path = M.paths[p];
+    const uint8_t *ops = M.path_ops + path.off;
+    float cur[12], lca[12], TA[12], TB[12], nxt[12], R[12];
+    se3_identity(cur);
+    int o = 0;
+    for (int i = 0; i < path.n_trunk; i++, o++) {
+        const DevJoint &J = M.joints[ops[o]];
+        joint_transform(J, cur, qval(J.idx_q), nxt);
+#pragma unroll
+        for (int k = 0; k < 12; k++) cur[k] = nxt[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 12; k++) lca[k] = cur[k];
+    for (int i = 0; i < path.n_a; i++, o++) {
+        const DevJoint &J = M.joints[ops[o]];
+        joint_transform(J, cur, qval(J.idx_q), nxt);
+#pragma unroll
+        for (int k = 0; k < 12; k++) cur[k] = nxt[k];
+    }
+    se3_mul(cur, GA.P, TA);
+#pragma unroll
+    for (int k = 0; k < 12; k++) cur[k] = lca[k];
+    for (int i = 0; i < path.n_b; i++, o++) {
+        const DevJoint &J = M.joints[ops[o]];
+        joint_transform(J, cur, qval(J.idx_q), nxt);
+#pragma unroll
+        for (int k = 0; k < 12; k++) cur[k] = nxt[k];
+    }
+    se3_mul(cur, GB.P, TB);
+    se3_inv_mul(TA, TB, R);
+    // ---- proxy classification with the broadphase's thresholds, in a's frame
+    const float3 ca = make_float3(GA.centre[0], GA.centre[1], GA.centre[2]);
+    const float3 cb = se3_act(R, GB.centre[0], GB.centre[1], GB.centre[2]);
+    float d2;
+    if (pr.kind == BP_BOX_A) {
+        const float ex = fmaxf(fabsf(cb.x) - GA.par[0], 0.f), ey = fmaxf(fabsf(cb.y) - GA.par[1], 0.f), ez = fmaxf(fabsf(cb.z) - GA.par[2], 0.f);
+        d2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+    } else if (pr.kind == BP_BOX_B) {
+        const float3 l = se3_act_inv(R, ca);
+        const float ex = fmaxf(fabsf(l.x) - GB.par[0], 0.f), ey = fmaxf(fabsf(l.y) - GB.par[1], 0.f), ez = fmaxf(fabsf(l.z) - GB.par[2], 0.f);
+        d2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+    } else {
+        const float3 d = sub3(ca, cb);
+        d2 = dot3(d, d);
+    }
+    const bool exact = pr.kind == BP_EXACT_SPHERES;
+    const float slack = exact ? 0.f : BP_SLACK;
+    const float rf = pr.r_out + padding + slack, rs = pr.r_in + padding - slack;
+    if (rs >= 0.f && d2 <= rs * rs) { out.hit[group] = 1; return; }     // certainly colliding
+    if (exact || d2 > rf * rf) return;                                   // certainly free (or decided exactly)
+    // ---- undecided: the whole GJK
+    ShapeRef A, B;
+    A.shape = GA.shape; A.p0 = GA.par[0]; A.p1 = GA.par[1]; A.p2 = GA.par[2];
+    A.verts = M.verts + GA.vert_off; A.nverts = GA.vert_cnt;
+    A.cell_off = GA.map_off >= 0 ? M.sup_cells + GA.map_off : nullptr; A.cell_list = M.sup_lists + GA.list_off;
+    B.shape = GB.shape; B.p0 = GB.par[0]; B.p1 = GB.par[1]; B.p2 = GB.par[2];
+    B.verts = M.verts + GB.vert_off; B.nverts = GB.vert_cnt;
+    B.cell_off = GB.map_off >= 0 ? M.sup_cells + GB.map_off : nullptr; B.cell_list = M.sup_lists + GB.list_off;
+    const float margin = padding + GA.core_radius + GB.core_radius;
+    const GjkOut r = gjk_run<false>(A, B, R, gjk_start_direction(GA, GB, R), margin, 0.f);
+    if (r.hit) out.hit[group] = 1;
+}
+
+// ------------------------------------------------------------------------------------------
 // Path discretisation (reference planning/utils.py:114-140)
 // ------------------------------------------------------------------------------------------
 // counts[e] = ceil(||q2 - q1||_2 / step) + 1, evaluated in FP64 so the sample count matches the
