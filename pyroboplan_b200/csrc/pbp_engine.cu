@@ -924,6 +924,18 @@ int pbp_check_paths(pbp_engine *e, const float *q_dev, const int64_t *path_offse
     if ((rc = e->d_desc_group.ensure((size_t)total * 4))) return rc;
     k_path_groups<<<grid_for(total, 256), 256, 0, st>>>(path_offsets_dev, n_paths, total, e->d_desc_group.as<int32_t>(), nullptr);
     e->stats.kernel_launches++;
+    if (e->npairs > 0 && total * (int64_t)e->npairs <= e->small_items) {   // few samples: the fused latency kernel
+        StateSource src{};
+        src.q = q_dev;
+        src.group = e->d_desc_group.as<int32_t>();
+        src.mode = 0;
+        Outputs out{};
+        out.hit = hit_dev;
+        k_small_check<<<grid_for(total * e->npairs, SMALL_THREADS), SMALL_THREADS, 0, st>>>(e->dm, src, total, padding, out);
+        LAUNCH_CHECK("k_small_check");
+        e->stats.states += total;
+        return 0;
+    }
     for (int64_t off = 0; off < total; off += e->chunk) {
         const int64_t cnt = std::min(e->chunk, total - off);
         StateSource src{};
