@@ -46,9 +46,9 @@ F_KERNEL = {"k_broadphase": F_BP_FLOP_PER_CONFIG, "k_item_setup": 0.45 * F_NP_FL
 HBM_BYTES_PER_CONFIG = 9 * 4 + 1   # 9 float32 in, 1 verdict byte out
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) and pipe utilisation of
 # the three kernels of a 1 Mi-state round, from the committed `ncu --set full` capture
-# profiles/r01_v5_ncu_summary.txt (cold-cache, serialised launches of this same command):
+# profiles/r01_v6_ncu_summary.txt (cold-cache, serialised launches of this same command):
 NCU = {
-    "source": "profiles/r01_v5_ncu_summary.txt",
+    "source": "profiles/r01_v6_ncu_summary.txt",
     "k_broadphase": {"traffic_bytes": 37.81e6 + 0.01e6, "fma_pipe_pct": 32.5, "alu_pipe_pct": 65.4, "issue_active_pct": 76.0,
                      "threads_per_inst": 27.7, "duration_us": 95.0},
     "k_item_setup": {"traffic_bytes": 41.71e6 + 1.45e6, "fma_pipe_pct": 27.2, "alu_pipe_pct": 34.2, "issue_active_pct": 58.6,
