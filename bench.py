@@ -49,12 +49,12 @@ HBM_BYTES_PER_CONFIG = 9 * 4 + 1   # 9 float32 in, 1 verdict byte out
 # profiles/r01_v6_ncu_summary.txt (cold-cache, serialised launches of this same command):
 NCU = {
     "source": "profiles/r01_v6_ncu_summary.txt",
-    "k_broadphase": {"traffic_bytes": 37.81e6 + 0.01e6, "fma_pipe_pct": 32.5, "alu_pipe_pct": 65.4, "issue_active_pct": 76.0,
+    "k_broadphase": {"traffic_bytes": 37.80e6 + 0.02e6, "fma_pipe_pct": 32.5, "alu_pipe_pct": 65.6, "issue_active_pct": 76.0,
                      "threads_per_inst": 27.7, "duration_us": 95.0},
-    "k_item_setup": {"traffic_bytes": 41.71e6 + 1.45e6, "fma_pipe_pct": 27.2, "alu_pipe_pct": 34.2, "issue_active_pct": 58.6,
-                     "threads_per_inst": 29.8, "duration_us": 104.9},
-    "k_narrowphase": {"traffic_bytes": 23.56e6 + 0.23e6, "fma_pipe_pct": 20.3, "alu_pipe_pct": 34.0, "issue_active_pct": 50.0,
-                      "threads_per_inst": 14.3, "duration_us": 158.3},
+    "k_item_setup": {"traffic_bytes": 41.75e6 + 1.63e6, "fma_pipe_pct": 27.0, "alu_pipe_pct": 35.1, "issue_active_pct": 59.6,
+                     "threads_per_inst": 29.8, "duration_us": 105.4},
+    "k_narrowphase": {"traffic_bytes": 23.56e6 + 0.06e6, "fma_pipe_pct": 20.3, "alu_pipe_pct": 34.0, "issue_active_pct": 50.2,
+                      "threads_per_inst": 14.3, "duration_us": 152.0},
 }
 
 
