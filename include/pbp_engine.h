@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PBP_ABI_VERSION 2
+#define PBP_ABI_VERSION 3
 
 typedef enum {
     PBP_OK = 0,
@@ -84,6 +84,10 @@ typedef struct {
     const double *frame_placement_f64; /* [nframes][12] */
     const double *q_lower_f64;         /* [nq] */
     const double *q_upper_f64;         /* [nq] */
+    /* optional (may be NULL): an enclosing capsule per geometry, geometry frame -- p0 (3), p1 (3),
+     * radius, flag (!= 0: use it).  A second "certainly free" proxy of the broadphase for elongated
+     * shapes; it must contain the whole shape. */
+    const float *geom_capsule;         /* [ngeoms][8] */
 } pbp_model_desc;
 
 typedef struct pbp_engine pbp_engine;

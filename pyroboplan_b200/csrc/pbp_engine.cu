@@ -118,6 +118,7 @@ struct pbp_engine {
     pbp::jit::SpecArgs spec_args{};
     float spec_thr_padding = -1.f;
     std::vector<float> spec_r_out, spec_r_in;      // per internal pair, for the per-call thresholds
+    std::vector<float> spec_r_cap;                 // capsule-based "free" radius sum of the pair (< 0: none)
     std::vector<uint8_t> spec_exact;
     int64_t small_items = 400000;   // (pair, state) items up to which boolean queries use the fused k_small_check (measured crossover with the pipeline: ~8 k Panda states = 600 k items)
     PinnedBuffer h_desc;            // host-built sample descriptors of small edge batches
@@ -218,6 +219,8 @@ int launch_round_kernels(pbp_engine *e, const StateSource &src, int64_t n, float
                 const float y = rs >= 0.f ? rs * rs : -1.f;
                 a.thr[p][0] = exact ? y : rf * rf;
                 a.thr[p][1] = y;
+                const float rc = e->spec_r_cap[p] + padding + BP_SLACK;
+                a.thr[p][2] = e->spec_r_cap[p] >= 0.f ? rc * rc : INFINITY;
             }
             e->spec_thr_padding = padding;
         }
@@ -386,6 +389,15 @@ static int build_host_tables(const pbp_model_desc *d, HostTables &H) {
         for (int i = 0; i < 3; i++) B.c[i] = G.P[3 * i] * outer[0] + G.P[3 * i + 1] * outer[1] + G.P[3 * i + 2] * outer[2] + G.P[9 + i];
         B.r_out = outer[3];
         B.r_in = inner[3];
+        if (d->geom_capsule && d->geom_capsule[8 * g + 7] != 0.f) {
+            const float *cp = d->geom_capsule + 8 * g;
+            B.has_cap = 1;
+            B.cap_r = cp[6];
+            for (int i = 0; i < 3; i++) {
+                B.cap0[i] = G.P[3 * i] * cp[0] + G.P[3 * i + 1] * cp[1] + G.P[3 * i + 2] * cp[2] + G.P[9 + i];
+                B.cap1[i] = G.P[3 * i] * cp[3] + G.P[3 * i + 1] * cp[4] + G.P[3 * i + 2] * cp[5] + G.P[9 + i];
+            }
+        }
         B.slot = G.parent == 0 ? -1 : nmoving++;
         B.box = -1;
         if (G.parent == 0 && G.shape == PBP_SHAPE_BOX) {
@@ -796,11 +808,22 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
             if (pbp::jit::compile(src_text, prop.major, prop.minor, cubin, log) == 0 &&
                 driver_api().moduleLoadData(&e->spec_module, cubin.data()) == CUDA_SUCCESS &&
                 driver_api().moduleGetFunction(&e->spec_bp, e->spec_module, "k_bp_spec") == CUDA_SUCCESS) {
-                e->spec_r_out.resize(np1); e->spec_r_in.resize(np1); e->spec_exact.resize(np1);
+                e->spec_r_out.resize(np1); e->spec_r_in.resize(np1); e->spec_exact.resize(np1); e->spec_r_cap.assign(np1, -1.f);
                 for (int p = 0; p < d->npairs; p++) {
                     e->spec_r_out[p] = bppairs[p].r_out;
                     e->spec_r_in[p] = bppairs[p].r_in;
                     e->spec_exact[p] = bppairs[p].kind == BP_EXACT_SPHERES;
+                    if (bppairs[p].kind == BP_SPHERES) {   // must mirror the generator's choice (pbp_jit.h)
+                        const BpGeom &ga = bpgeoms[bppairs[p].a], &gb = bpgeoms[bppairs[p].b];
+                        auto usable = [](const BpGeom &g) {
+                            const float du[3] = {g.cap1[0] - g.cap0[0], g.cap1[1] - g.cap0[1], g.cap1[2] - g.cap0[2]};
+                            return g.has_cap && (du[0] * du[0] + du[1] * du[1] + du[2] * du[2]) > 0.f;
+                        };
+                        const bool ca = usable(ga), cb = usable(gb);
+                        if (ca && cb) e->spec_r_cap[p] = ga.cap_r + gb.cap_r;
+                        else if (ca) e->spec_r_cap[p] = ga.cap_r + gb.r_out;
+                        else if (cb) e->spec_r_cap[p] = gb.cap_r + ga.r_out;
+                    }
                 }
             } else {
                 e->spec_bp = nullptr;

@@ -30,7 +30,7 @@ namespace pbp {
 namespace jit {
 
 constexpr int SPEC_THREADS = 128;
-constexpr int SPEC_MAX_PAIRS = 384;   // thresholds travel in the kernel parameter (4 KB limit)
+constexpr int SPEC_MAX_PAIRS = 300;   // thresholds travel in the kernel parameter (4 KB limit)
 
 // Kernel parameter of the generated kernel (mirrored textually in the generated source).
 struct SpecArgs {
@@ -44,9 +44,9 @@ struct SpecArgs {
     int32_t *bin_state;
     uint32_t *bin_count;
     long long cap;
-    float thr[SPEC_MAX_PAIRS][2];   // only the first npairs entries are passed (size computed per model)
+    float thr[SPEC_MAX_PAIRS][3];   // free / hit / capsule-free squared thresholds; only the first npairs entries are passed
 };
-inline size_t spec_args_bytes(int npairs) { return offsetof(SpecArgs, thr) + (size_t)npairs * 8; }
+inline size_t spec_args_bytes(int npairs) { return offsetof(SpecArgs, thr) + (size_t)npairs * 12; }
 
 // ---- tiny expression helper: a scalar that is either a literal or a named variable
 struct Ex {
@@ -159,9 +159,27 @@ inline std::string generate_broadphase(const Input &in) {
     s += "typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t;\n";
     s += "struct SpecArgs { const float *q, *q1, *q2; const int32_t *group; const float *frac; int32_t mode; int32_t _pad;\n"
          "  long long n_states; unsigned char *hit; int32_t *bin_state; uint32_t *bin_count; long long cap; float thr[" +
-         std::to_string(NP) + "][2]; };\n";
+         std::to_string(NP) + "][3]; };\n";
     s += "#define NQ " + std::to_string(NQ) + "\n#define NP " + std::to_string(NP) + "\n#define NW " + std::to_string(NW) +
          "\n#define BT " + std::to_string(SPEC_THREADS) + "\n";
+    // squared distance point <-> segment (p0, u = p1 - p0, 1 / |u|^2) and segment <-> segment (Ericson, Real-Time Collision Detection 5.1.9)
+    s += "__device__ __forceinline__ float pt_seg2(float cx, float cy, float cz, float px, float py, float pz, float ux, float uy, float uz, float inv_uu) {\n"
+         "    const float dx = cx - px, dy = cy - py, dz = cz - pz;\n"
+         "    const float t = fminf(fmaxf(fmaf(dx, ux, fmaf(dy, uy, dz * uz)) * inv_uu, 0.f), 1.f);\n"
+         "    const float wx = fmaf(-t, ux, dx), wy = fmaf(-t, uy, dy), wz = fmaf(-t, uz, dz);\n"
+         "    return fmaf(wx, wx, fmaf(wy, wy, wz * wz));\n}\n";
+    s += "__device__ __forceinline__ float seg_seg2(float px, float py, float pz, float d1x, float d1y, float d1z, float a,\n"
+         "                                          float qx, float qy, float qz, float d2x, float d2y, float d2z, float e) {\n"
+         "    const float rx = px - qx, ry = py - qy, rz = pz - qz;\n"
+         "    const float f = fmaf(d2x, rx, fmaf(d2y, ry, d2z * rz)), c = fmaf(d1x, rx, fmaf(d1y, ry, d1z * rz));\n"
+         "    const float b = fmaf(d1x, d2x, fmaf(d1y, d2y, d1z * d2z));\n"
+         "    const float den = a * e - b * b;\n"
+         "    float sN = den > 1e-12f * a * e ? fminf(fmaxf((b * f - c * e) / den, 0.f), 1.f) : 0.f;\n"
+         "    float tN = (b * sN + f) / e;\n"
+         "    if (tN < 0.f) { tN = 0.f; sN = fminf(fmaxf(-c / a, 0.f), 1.f); }\n"
+         "    else if (tN > 1.f) { tN = 1.f; sN = fminf(fmaxf((b - c) / a, 0.f), 1.f); }\n"
+         "    const float wx = fmaf(sN, d1x, rx) - tN * d2x, wy = fmaf(sN, d1y, ry) - tN * d2y, wz = fmaf(sN, d1z, rz) - tN * d2z;\n"
+         "    return fmaf(wx, wx, fmaf(wy, wy, wz * wz));\n}\n";
     s += "extern \"C\" __global__ void __launch_bounds__(BT) k_bp_spec(const SpecArgs A) {\n";
     s += "    __shared__ __align__(16) float sq[BT * NQ];\n    __shared__ uint32_t scnt[NP];\n    __shared__ uint32_t sbase[NP];\n";
     s += "    const int tid = threadIdx.x;\n    const int64_t block_first = (int64_t)blockIdx.x * BT;\n";
@@ -258,6 +276,32 @@ inline std::string generate_broadphase(const Input &in) {
             cz[gi] = act_lit(g, n + "z", P, 2, B.c);
         }
     }
+    // ---- enclosing capsules (second "certainly free" proxy of elongated shapes): end points, direction
+    std::vector<Ex> k0x(in.ngeoms), k0y(in.ngeoms), k0z(in.ngeoms), kux(in.ngeoms), kuy(in.ngeoms), kuz(in.ngeoms);
+    std::vector<float> kuu(in.ngeoms, 0.f);
+    for (int gi = 0; gi < in.ngeoms; gi++) {
+        const BpGeom &B = in.bpgeoms[gi];
+        if (!B.has_cap) continue;
+        bool used = false;
+        for (int p = 0; p < in.npairs && !used; p++)
+            used = in.bppairs[p].kind == BP_SPHERES && (in.bppairs[p].a == gi || in.bppairs[p].b == gi);
+        if (!used) continue;
+        const float du[3] = {B.cap1[0] - B.cap0[0], B.cap1[1] - B.cap0[1], B.cap1[2] - B.cap0[2]};
+        kuu[gi] = du[0] * du[0] + du[1] * du[1] + du[2] * du[2];
+        const std::string n = "k" + std::to_string(gi);
+        if (in.geom_parent[gi] == 0) {
+            k0x[gi] = Ex::L(B.cap0[0]); k0y[gi] = Ex::L(B.cap0[1]); k0z[gi] = Ex::L(B.cap0[2]);
+            kux[gi] = Ex::L(du[0]); kuy[gi] = Ex::L(du[1]); kuz[gi] = Ex::L(du[2]);
+        } else {
+            const Xf &P = X[in.geom_parent[gi]];
+            k0x[gi] = act_lit(g, n + "x", P, 0, B.cap0); k0y[gi] = act_lit(g, n + "y", P, 1, B.cap0); k0z[gi] = act_lit(g, n + "z", P, 2, B.cap0);
+            // direction: rotation only
+            const Ex zero = Ex::L(0.f);
+            kux[gi] = g.dot(n + "ux", {P.m[0], P.m[1], P.m[2]}, {Ex::L(du[0]), Ex::L(du[1]), Ex::L(du[2])}, &zero);
+            kuy[gi] = g.dot(n + "uy", {P.m[3], P.m[4], P.m[5]}, {Ex::L(du[0]), Ex::L(du[1]), Ex::L(du[2])}, &zero);
+            kuz[gi] = g.dot(n + "uz", {P.m[6], P.m[7], P.m[8]}, {Ex::L(du[0]), Ex::L(du[1]), Ex::L(du[2])}, &zero);
+        }
+    }
     // ---- pair tests, group by group (a warp whose lanes are all decided skips the rest)
     auto diff = [&](const std::string &name, const Ex &a, const Ex &b) {
         const Ex one = Ex::L(1.f), neg = Ex::L(-1.f);
@@ -294,7 +338,24 @@ inline std::string generate_broadphase(const Input &in) {
             const std::string P = std::to_string(p);
             g.line("const float d2v = " + d2.str() + ";");
             g.line("const bool sure = alive && d2v <= A.thr[" + P + "][1];");
-            g.line("const bool und = alive && !sure && !(d2v > A.thr[" + P + "][0]);");
+            std::string cap_free;
+            if (pr.kind == BP_SPHERES) {
+                const bool ca = in.bpgeoms[pr.a].has_cap && kuu[pr.a] > 0.f, cb2 = in.bpgeoms[pr.b].has_cap && kuu[pr.b] > 0.f;
+                auto f = [](float x) { return Ex::L(x).str(); };
+                if (ca && cb2) {
+                    g.line("const float dk = seg_seg2(" + k0x[pr.a].str() + ", " + k0y[pr.a].str() + ", " + k0z[pr.a].str() + ", " + kux[pr.a].str() + ", " +
+                           kuy[pr.a].str() + ", " + kuz[pr.a].str() + ", " + f(kuu[pr.a]) + ", " + k0x[pr.b].str() + ", " + k0y[pr.b].str() + ", " +
+                           k0z[pr.b].str() + ", " + kux[pr.b].str() + ", " + kuy[pr.b].str() + ", " + kuz[pr.b].str() + ", " + f(kuu[pr.b]) + ");");
+                    cap_free = " && !(dk > A.thr[" + P + "][2])";
+                } else if (ca || cb2) {
+                    const int gc = ca ? pr.a : pr.b, go = ca ? pr.b : pr.a;
+                    g.line("const float dk = pt_seg2(" + cx[go].str() + ", " + cy[go].str() + ", " + cz[go].str() + ", " + k0x[gc].str() + ", " +
+                           k0y[gc].str() + ", " + k0z[gc].str() + ", " + kux[gc].str() + ", " + kuy[gc].str() + ", " + kuz[gc].str() + ", " +
+                           f(1.0f / kuu[gc]) + ");");
+                    cap_free = " && !(dk > A.thr[" + P + "][2])";
+                }
+            }
+            g.line("const bool und = alive && !sure && !(d2v > A.thr[" + P + "][0])" + cap_free + ";");
             g.line("if (sure) { state_hit = true; alive = false; }");
             g.line("w" + std::to_string(p >> 5) + " |= und ? " + std::to_string(1u << (p & 31)) + "u : 0u;");
             g.line("}");

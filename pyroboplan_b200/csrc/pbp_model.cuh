@@ -36,13 +36,17 @@ struct DevGeom {        // 112 B -- narrowphase / item-setup view of a geometry
     int32_t _pad[2];
 };
 
-struct BpGeom {         // 32 B -- broadphase view: one proxy centre, two radii
+struct BpGeom {         // 64 B -- broadphase view: one proxy centre, two radii (+ optional enclosing capsule)
     float c[3];         // centre: parent-JOINT frame for moving geometries, world frame for static ones
     float r_out;        // enclosing radius
     float r_in;         // inscribed radius (same centre)
     int32_t slot;       // per-thread centre slot, -1 if static
     int32_t box;        // index into the static-box table, -1 if this is not a static box
-    int32_t _pad;
+    int32_t has_cap;    // != 0: cap0 / cap1 / cap_r describe a capsule that contains the shape
+    float cap0[3];      // capsule segment end points, same frame as c
+    float cap_r;
+    float cap1[3];
+    float _pad;
 };
 
 struct BpBox {          // 64 B -- static box: world placement + half sides

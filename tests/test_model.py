@@ -150,3 +150,27 @@ def test_marble_and_sphere_panda_models():
     m, c, v = panda.load_models(use_sphere_collisions=True)
     assert m.nq == 9 and len(c.geometryObjects) == 17
     assert all(type(g.geometry).__name__ == "Sphere" for g in c.geometryObjects)
+
+
+def test_enclosing_capsules_contain_their_hulls():
+    """The broadphase's capsule proxies (engine.enclosing_capsule) must contain every hull vertex, in
+    the float32 numbers the device sees; only clearly elongated links get one."""
+    from pyroboplan_b200.engine import flatten_model
+
+    model, cmodel, _ = make_panda()
+    arrays, _ = flatten_model(model, cmodel)
+    flagged = []
+    for g, obj in enumerate(cmodel.geometryObjects):
+        cap = arrays["geom_capsule"][g].astype(np.float64)
+        if type(obj.geometry).__name__ != "Convex":
+            assert not cap.any()
+            continue
+        pts = np.asarray(obj.geometry.points, dtype=np.float32).astype(np.float64)
+        p0, p1, r = cap[:3], cap[3:6], cap[6]
+        u = p1 - p0
+        s = np.clip(((pts - p0) @ u) / max(u @ u, 1e-30), 0.0, 1.0)
+        assert (np.linalg.norm(pts - (p0 + np.outer(s, u)), axis=1) <= r).all()
+        if cap[7]:
+            flagged.append(obj.name)
+            assert r < 0.55 * arrays["geom_outer"][g][3]
+    assert flagged == ["panda_link5_0", "panda_hand_0"]
