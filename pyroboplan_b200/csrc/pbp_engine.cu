@@ -389,6 +389,14 @@ static int build_host_tables(const pbp_model_desc *d, HostTables &H) {
         for (int i = 0; i < 3; i++) B.c[i] = G.P[3 * i] * outer[0] + G.P[3 * i + 1] * outer[1] + G.P[3 * i + 2] * outer[2] + G.P[9 + i];
         B.r_out = outer[3];
         B.r_in = inner[3];
+        if (d->geom_capsule) {   // the capsule's segment doubles as the shape's "long axis" for the GJK start direction
+            const float *cp = d->geom_capsule + 8 * g;
+            const float du[3] = {cp[3] - cp[0], cp[4] - cp[1], cp[5] - cp[2]};
+            if (cp[6] > 0.f && du[0] * du[0] + du[1] * du[1] + du[2] * du[2] > 1e-10f) {
+                G.has_axis = 1;
+                for (int i = 0; i < 3; i++) { G.axis0[i] = cp[i]; G.axis1[i] = cp[3 + i]; }
+            }
+        }
         if (d->geom_capsule && d->geom_capsule[8 * g + 7] != 0.f) {
             const float *cp = d->geom_capsule + 8 * g;
             B.has_cap = 1;

@@ -22,7 +22,7 @@ struct DevJoint {       // 96 B
     int32_t _pad;
 };
 
-struct DevGeom {        // 112 B -- narrowphase / item-setup view of a geometry
+struct DevGeom {        // 144 B -- narrowphase / item-setup view of a geometry
     float P[12];        // placement in parent joint frame (world placement if parent == 0)
     float par[4];       // shape parameters
     float centre[3];    // proxy-sphere centre in the geometry frame (initial GJK direction)
@@ -33,7 +33,12 @@ struct DevGeom {        // 112 B -- narrowphase / item-setup view of a geometry
     int32_t vert_cnt;   // padded to a multiple of 4 (last vertex repeated)
     int32_t map_off;    // convex: offset of this hull's support-map cell table (uint16 units), -1 if none
     int32_t list_off;   // convex: offset of this hull's candidate lists (uint16 units)
-    int32_t _pad[2];
+    int32_t has_axis;   // != 0: axis0 / axis1 is the segment of the shape's enclosing capsule (geometry frame)
+    int32_t _pad;
+    float axis0[3];     // used for the GJK start direction of elongated shapes
+    float _pad2;
+    float axis1[3];
+    float _pad3;
 };
 
 struct BpGeom {         // 64 B -- broadphase view: one proxy centre, two radii (+ optional enclosing capsule)
