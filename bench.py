@@ -40,21 +40,21 @@ F_BP_FLOP_PER_CONFIG = 1.5e3 + 74 * 30.0          # k_broadphase: FK + 74 proxy 
 F_NP_FLOP_PER_CONFIG = 6.0 * 1598 + 150.0 * 7.57  # k_narrowphase: support scans + simplex updates
 F_ALG_FLOP_PER_CONFIG = F_BP_FLOP_PER_CONFIG + F_NP_FLOP_PER_CONFIG  # = 14.4 kflop
 # The GJK work is split over two kernels: k_item_setup runs the first iteration of every item
-# (1.28 items/state of the 2.8 iterations/state the device runs in total = 45 %), k_narrowphase
-# the rest; the item setup's FK recomputation is redundant work, not algorithmic flops.
+# (about 45 % of the iterations the device runs in total), k_narrowphase the rest; the item
+# setup's FK recomputation is redundant work, not algorithmic flops.
 F_KERNEL = {"k_broadphase": F_BP_FLOP_PER_CONFIG, "k_item_setup": 0.45 * F_NP_FLOP_PER_CONFIG, "k_narrowphase": 0.55 * F_NP_FLOP_PER_CONFIG}
 HBM_BYTES_PER_CONFIG = 9 * 4 + 1   # 9 float32 in, 1 verdict byte out
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) and pipe utilisation of
 # the three kernels of a 1 Mi-state round, from the committed `ncu --set full` capture
-# profiles/r01_v6_ncu_summary.txt (cold-cache, serialised launches of this same command):
+# profiles/r01_v7_ncu_summary.txt (cold-cache, serialised launches of this same command):
 NCU = {
-    "source": "profiles/r01_v6_ncu_summary.txt",
-    "k_broadphase": {"traffic_bytes": 37.80e6 + 0.02e6, "fma_pipe_pct": 32.5, "alu_pipe_pct": 65.6, "issue_active_pct": 76.0,
-                     "threads_per_inst": 27.7, "duration_us": 95.0},
-    "k_item_setup": {"traffic_bytes": 41.75e6 + 1.63e6, "fma_pipe_pct": 27.0, "alu_pipe_pct": 35.1, "issue_active_pct": 59.6,
-                     "threads_per_inst": 29.8, "duration_us": 105.4},
-    "k_narrowphase": {"traffic_bytes": 23.56e6 + 0.06e6, "fma_pipe_pct": 20.3, "alu_pipe_pct": 34.0, "issue_active_pct": 50.2,
-                      "threads_per_inst": 14.3, "duration_us": 152.0},
+    "source": "profiles/r01_v7_ncu_summary.txt",
+    "k_broadphase": {"traffic_bytes": 37.81e6 + 0.01e6, "fma_pipe_pct": 34.5, "alu_pipe_pct": 62.4, "issue_active_pct": 76.3,
+                     "threads_per_inst": 28.4, "duration_us": 103.6},
+    "k_item_setup": {"traffic_bytes": 35.34e6 + 0.24e6, "fma_pipe_pct": 26.1, "alu_pipe_pct": 32.8, "issue_active_pct": 57.2,
+                     "threads_per_inst": 29.7, "duration_us": 75.8},
+    "k_narrowphase": {"traffic_bytes": 16.45e6 + 0.08e6, "fma_pipe_pct": 18.0, "alu_pipe_pct": 32.3, "issue_active_pct": 46.8,
+                      "threads_per_inst": 14.4, "duration_us": 125.5},
 }
 
 
