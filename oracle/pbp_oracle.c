@@ -296,6 +296,7 @@ static double gjk_core_distance(const shape_t *A, const shape_t *B, double *pa, 
     double v[3] = {A->T[9] - B->T[9], A->T[10] - B->T[10], A->T[11] - B->T[11]};
     if (dot3(v, v) == 0.0) { v[0] = 1.0; }
     *intersect = 0;
+    double best_lb = 0.0;
     for (int it = 0; it < ORACLE_GJK_MAX_ITERS; it++) {
         cnt->gjk_iters++;
         double d[3] = {-v[0], -v[1], -v[2]}, sa[3], sb[3], w[3];
@@ -310,10 +311,20 @@ static double gjk_core_distance(const shape_t *A, const shape_t *B, double *pa, 
                 if (s.w[i][0] == w[0] && s.w[i][1] == w[1] && s.w[i][2] == w[2]) dup = 1;
             if (dup) break;
         }
+        /* <v,w>/|v| is a lower bound of the distance for ANY v: once it is positive the shapes are
+         * certainly apart.  Curved supports (cylinders) produce sliver tetrahedra near convergence
+         * whose inside test is rounding noise; a claimed enclosure that contradicts the bound is
+         * discarded and the previous (converged to within ub - lb) closest point is kept. */
+        if (vw > 0.0 && vw / sqrt(vv) > best_lb) best_lb = vw / sqrt(vv);
+        simplex_t prev = s;
+        double v_prev[3] = {v[0], v[1], v[2]};
         memcpy(s.w[s.n], w, sizeof w); memcpy(s.a[s.n], sa, sizeof sa); memcpy(s.b[s.n], sb, sizeof sb);
         s.n++;
-        if (simplex_closest(&s, v)) { *intersect = 1; break; }
+        const int enclosed = simplex_closest(&s, v);
+        if ((enclosed || dot3(v, v) <= 1e-28) && best_lb > 1e-9) { s = prev; memcpy(v, v_prev, sizeof v_prev); break; }
+        if (enclosed) { *intersect = 1; break; }
         if (dot3(v, v) <= 1e-28) { *intersect = 1; break; }
+        if (dot3(v, v) > vv && s.n > 1 && best_lb > 1e-9 && vv - best_lb * sqrt(vv) < 1e-9 * (1.0 + vv)) { s = prev; memcpy(v, v_prev, sizeof v_prev); break; }
     }
     for (int k = 0; k < 3; k++) {
         pa[k] = pb[k] = 0.0;
@@ -750,6 +761,7 @@ static double gjk_core_distance_simplex(const shape_t *A, const shape_t *B, doub
     double v[3] = {A->T[9] - B->T[9], A->T[10] - B->T[10], A->T[11] - B->T[11]};
     if (dot3(v, v) == 0.0) { v[0] = 1.0; }
     *intersect = 0;
+    double best_lb = 0.0;
     for (int it = 0; it < ORACLE_GJK_MAX_ITERS; it++) {
         cnt->gjk_iters++;
         double d[3] = {-v[0], -v[1], -v[2]}, sa[3], sb[3], w[3];
@@ -764,10 +776,15 @@ static double gjk_core_distance_simplex(const shape_t *A, const shape_t *B, doub
                 if (s.w[i][0] == w[0] && s.w[i][1] == w[1] && s.w[i][2] == w[2]) dup = 1;
             if (dup) break;
         }
+        if (vw > 0.0 && vw / sqrt(vv) > best_lb) best_lb = vw / sqrt(vv);   /* see gjk_core_distance */
+        simplex_t prev = s;
+        double v_prev[3] = {v[0], v[1], v[2]};
         memcpy(s.w[s.n], w, sizeof w); memcpy(s.a[s.n], sa, sizeof sa); memcpy(s.b[s.n], sb, sizeof sb);
         s.n++;
         simplex_t before = s;
-        if (simplex_closest(&s, v)) { *intersect = 1; s = before; break; }   /* keep the enclosing tetrahedron */
+        const int enclosed = simplex_closest(&s, v);
+        if ((enclosed || dot3(v, v) <= 1e-28) && best_lb > 1e-9) { s = prev; memcpy(v, v_prev, sizeof v_prev); break; }
+        if (enclosed) { *intersect = 1; s = before; break; }   /* keep the enclosing tetrahedron */
         if (dot3(v, v) <= 1e-28) { *intersect = 1; break; }
     }
     for (int k = 0; k < 3; k++) {

@@ -237,3 +237,26 @@ def test_penetration_depth_certificates(which):
             assert _contains(geoms[a], oMg[a], pa, 1e-6) and _contains(geoms[b], oMg[b], pb, 1e-6)
             np.testing.assert_allclose(pb - pa, n * d, atol=1e-6)            # p2 - p1 = normal * signed distance
     assert penetrating > 30
+
+
+def test_curved_pairs_are_stable_under_tiny_perturbations():
+    """Regression: cylinder-cylinder GJK produces sliver tetrahedra near convergence whose inside test
+    is rounding noise; the oracle once reported a pair 4.3 cm apart as intersecting for one state and
+    not for the same state perturbed by 1e-8 (found by tests/test_gpu_random_models.py).  A claimed
+    enclosure that contradicts a positive separating-plane bound is now discarded."""
+    from test_gpu_random_models import random_model
+
+    model, cm = random_model(3)
+    orc = Oracle(model, cm)
+    q = np.array([-0.08408726, 0.8007079, 0.00525507, -1.2401325, -0.89210567, -0.01261778, 1.05439098])
+    d0 = orc.pair_distance(q, 3, 5)[0]
+    assert d0 == pytest.approx(0.0431242, abs=1e-6)
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        d = orc.pair_distance(q + rng.normal(scale=1e-8, size=q.shape), 3, 5)[0]
+        assert d == pytest.approx(d0, abs=1e-6)
+    # and broadly: distances of curved pairs vary continuously along a fine path
+    qs = q + np.linspace(0.0, 1e-3, 400)[:, None] * rng.normal(size=q.shape)
+    for a, b in [(p.first, p.second) for p in cm.collisionPairs][:40]:
+        ds = np.array([orc.pair_distance(x, a, b)[0] for x in qs])
+        assert np.abs(np.diff(ds)).max() < 1e-4
