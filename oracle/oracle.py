@@ -101,6 +101,13 @@ def _load():
         lib.oracle_discretize_segment.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p]
         lib.oracle_discretize_segment.restype = None
         lib.oracle_num_threads.restype = ctypes.c_int
+        lib.oracle_soup_pair_distance.argtypes = [P(_CModel), ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                                  ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int]
+        lib.oracle_soup_pair_distance.restype = ctypes.c_double
+        lib.oracle_soup_check_states.argtypes = [P(_CModel), ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                 P(ctypes.c_int64)]
+        lib.oracle_soup_check_states.restype = None
         _lib = lib
     return _lib
 
@@ -265,6 +272,41 @@ class Oracle:
 
     def num_threads(self):
         return int(self.lib.oracle_num_threads())
+
+    # ------------------------------------------------------------------ triangle-soup semantics (study)
+    def set_mesh_triangles(self, collision_model):
+        """Triangle tables for the surface semantics of Pinocchio's BVHModel meshes: geometries that carry
+        ``mesh_vertices`` / ``mesh_triangles`` (URDF meshes) become soups, everything else stays a solid."""
+        tris, off, cnt = [], [], []
+        for g in collision_model.geometryObjects:
+            t = getattr(g.geometry, "mesh_triangles", None)
+            off.append(sum(len(x) for x in tris))
+            if t is None:
+                cnt.append(0)
+                continue
+            v = np.asarray(g.geometry.mesh_vertices, dtype=np.float64)
+            tris.append(v[np.asarray(t)].reshape(-1, 9))
+            cnt.append(len(t))
+        self._tris = np.ascontiguousarray(np.concatenate(tris) if tris else np.zeros((0, 9)))
+        self._tri_off = np.asarray(off, dtype=np.int32)
+        self._tri_cnt = np.asarray(cnt, dtype=np.int32)
+
+    def soup_pair_distance(self, oMg, ga, gb, stop_at=-1.0, brute=False):
+        ta = self._tris[self._tri_off[ga]: self._tri_off[ga] + self._tri_cnt[ga]]
+        tb = self._tris[self._tri_off[gb]: self._tri_off[gb] + self._tri_cnt[gb]]
+        ta, tb = np.ascontiguousarray(ta), np.ascontiguousarray(tb)
+        return float(self.lib.oracle_soup_pair_distance(ctypes.byref(self._cm), _ptr(np.ascontiguousarray(oMg)), int(ga), int(gb),
+                                                        _ptr(ta), len(ta), _ptr(tb), len(tb), float(stop_at), int(brute)))
+
+    def soup_check_states(self, Q, padding=0.0, nthreads=0):
+        """(hull_hit[N], soup_hit[N], pairs per state that hit by hull but not by surface, #triangle tests run)."""
+        Q = np.ascontiguousarray(Q, dtype=np.float64).reshape(-1, self.nq)
+        n = len(Q)
+        hh, sh, fl = np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.int32)
+        tests = ctypes.c_int64(0)
+        self.lib.oracle_soup_check_states(ctypes.byref(self._cm), _ptr(Q), n, float(padding), _ptr(self._tris), _ptr(self._tri_off),
+                                          _ptr(self._tri_cnt), int(nthreads), _ptr(hh), _ptr(sh), _ptr(fl), ctypes.byref(tests))
+        return hh, sh, fl, int(tests.value)
 
 
 def discretize_joint_space_path(q_path, max_angle_distance):

@@ -668,18 +668,67 @@ static int epa_make_face(epa_face_t *f, int i0, int i1, int i2, double (*W)[3]) 
 }
 
 /* depth >= 0 of the cores' overlap; n = unit normal from A to B; pa/pb deepest points on the cores.
- * Returns 0 when the simplex handed over does not enclose the origin (touching configurations). */
+ * Returns 0 when no polytope around the origin can be started from the simplex handed over (a single
+ * point: the cores touch in a vertex). */
 static int epa_core(const shape_t *A, const shape_t *B, const simplex_t *s, double *depth, double *n_out, double *pa, double *pb,
                     oracle_counters *cnt) {
     static __thread double W[EPA_MAXV][3], Av[EPA_MAXV][3];
     static __thread epa_face_t F[EPA_MAXF];
     static __thread int edges[3 * EPA_MAXF][2];
-    if (s->n != 4) return 0;
-    int nv = 4, nf = 0;
-    for (int i = 0; i < 4; i++) { memcpy(W[i], s->w[i], sizeof W[i]); memcpy(Av[i], s->a[i], sizeof Av[i]); }
-    static const int tet[4][3] = {{0, 1, 2}, {0, 1, 3}, {0, 2, 3}, {1, 2, 3}};
-    /* the GJK orientation test uses the opposite vertex; here the origin: it is inside */
-    for (int f = 0; f < 4; f++) epa_make_face(&F[nf++], tet[f][0], tet[f][1], tet[f][2], W);
+    int nv = 0, nf = 0;
+    if (s->n < 2 || s->n > 4) return 0;
+    for (int i = 0; i < s->n; i++) { memcpy(W[i], s->w[i], sizeof W[i]); memcpy(Av[i], s->a[i], sizeof Av[i]); }
+    nv = s->n;
+    if (s->n == 4) {
+        static const int tet[4][3] = {{0, 1, 2}, {0, 1, 3}, {0, 2, 3}, {1, 2, 3}};
+        /* the GJK orientation test uses the opposite vertex; here the origin: it is inside */
+        for (int f = 0; f < 4; f++) epa_make_face(&F[nf++], tet[f][0], tet[f][1], tet[f][2], W);
+    } else {
+        /* GJK stopped on a triangle / segment THROUGH the origin (it does whenever the support
+         * points stay in one plane by symmetry, e.g. a sphere centre inside a cylinder: every
+         * direction lies in the axial plane through the centre).  That is an overlap, not a
+         * touching contact: close the simplex into a bipyramid with extra support points -- two
+         * apexes along +- the triangle normal, or a ring of three around the segment. */
+        double dirs[3][3];
+        int nd = 0;
+        if (s->n == 3) {
+            double e1[3], e2[3], nn[3];
+            sub3(W[1], W[0], e1); sub3(W[2], W[0], e2); cross3(e1, e2, nn);
+            const double len = sqrt(dot3(nn, nn));
+            if (!(len > 1e-150)) return 0;
+            for (int k = 0; k < 3; k++) { dirs[0][k] = nn[k] / len; dirs[1][k] = -nn[k] / len; }
+            nd = 2;
+        } else {
+            double u[3], e[3] = {0, 0, 0}, d1[3], d2[3];
+            sub3(W[1], W[0], u);
+            if (!(dot3(u, u) > 1e-300)) return 0;
+            const double ax = fabs(u[0]), ay = fabs(u[1]), az = fabs(u[2]);
+            e[(ax <= ay && ax <= az) ? 0 : (ay <= az ? 1 : 2)] = 1.0;
+            cross3(u, e, d1); cross3(u, d1, d2);
+            const double l1 = sqrt(dot3(d1, d1)), l2 = sqrt(dot3(d2, d2));
+            for (int k = 0; k < 3; k++) {
+                d1[k] /= l1; d2[k] /= l2;
+                dirs[0][k] = d1[k];
+                dirs[1][k] = -0.5 * d1[k] + 0.86602540378443865 * d2[k];
+                dirs[2][k] = -0.5 * d1[k] - 0.86602540378443865 * d2[k];
+            }
+            nd = 3;
+        }
+        for (int j = 0; j < nd; j++) {
+            double md[3] = {-dirs[j][0], -dirs[j][1], -dirs[j][2]}, sa[3], sb[3];
+            support_world(A, dirs[j], sa, cnt);
+            support_world(B, md, sb, cnt);
+            sub3(sa, sb, W[nv]); memcpy(Av[nv], sa, sizeof sa);
+            nv++;
+        }
+        if (s->n == 3) {
+            static const int bip[6][3] = {{0, 1, 3}, {1, 2, 3}, {2, 0, 3}, {0, 1, 4}, {1, 2, 4}, {2, 0, 4}};
+            for (int f = 0; f < 6; f++) epa_make_face(&F[nf++], bip[f][0], bip[f][1], bip[f][2], W);
+        } else {
+            static const int bip[6][3] = {{2, 3, 0}, {3, 4, 0}, {4, 2, 0}, {2, 3, 1}, {3, 4, 1}, {4, 2, 1}};
+            for (int f = 0; f < 6; f++) epa_make_face(&F[nf++], bip[f][0], bip[f][1], bip[f][2], W);
+        }
+    }
     int best = -1;
     for (int iter = 0; iter < 4 * EPA_MAXV; iter++) {
         best = -1;
@@ -820,7 +869,7 @@ double oracle_pair_signed_distance(const oracle_model *m, const double *oMg, int
     } else {
         double depth = 0.0;
         if (epa_core(&A, &B, &s, &depth, n, pa, pb, cnt)) dist = -depth - r;
-        else { dist = -r; ok = r > 0.0 ? 1 : 0; }   /* cores touch: without radii the depth is 0 */
+        else { dist = -r; ok = (s.n == 1 && r > 0.0) ? 1 : 0; }   /* cores touch in a vertex: the depth is that of the radii */
         if (!ok || (dist == -r && depth == 0.0 && dot3(n, n) == 0.0)) {
             double len = sqrt(dot3(v, v));
             if (len > 0.0) for (int k = 0; k < 3; k++) n[k] = -v[k] / len;
@@ -832,4 +881,235 @@ double oracle_pair_signed_distance(const oracle_model *m, const double *oMg, int
         out[9] = ok ? 1.0 : 0.0;
     }
     return dist;
+}
+
+/* ------------------------------------------------------------------ triangle-soup semantics (study)
+ * Pinocchio loads a URDF <mesh> as a coal BVHModel: the SURFACE triangles, not the solid and not
+ * its convex hull (Appendix A.5 of SURVEY.md; the call sites are
+ * /root/reference/src/pyroboplan/models/panda.py:27 -> pinocchio.buildModelsFromUrdf).  Two meshes
+ * collide when two of their triangles are within the security margin; a primitive collides with a
+ * mesh when it is within the margin of one triangle.  The engine works on convex hulls; for the
+ * Panda meshes the hull and the surface differ only by sub-millimetre dents.  The
+ * functions below evaluate the surface semantics exactly (float64, brute force over triangles with
+ * bounding-box rejection) so that the difference can be COUNTED on the benchmark inputs. */
+static inline double clamp01(double x) { return x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x); }
+
+/* squared distance between segments p1q1 and p2q2 (Ericson, Real-Time Collision Detection 5.1.9) */
+static double seg_seg_dist2(const double *p1, const double *q1, const double *p2, const double *q2) {
+    double d1[3], d2[3], r[3];
+    sub3(q1, p1, d1); sub3(q2, p2, d2); sub3(p1, p2, r);
+    const double a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r);
+    double s, t;
+    if (a <= 0.0 && e <= 0.0) return dot3(r, r);
+    if (a <= 0.0) { s = 0.0; t = clamp01(f / e); }
+    else {
+        const double c = dot3(d1, r);
+        if (e <= 0.0) { t = 0.0; s = clamp01(-c / a); }
+        else {
+            const double b = dot3(d1, d2), den = a * e - b * b;
+            s = den > 0.0 ? clamp01((b * f - c * e) / den) : 0.0;
+            t = (b * s + f) / e;
+            if (t < 0.0) { t = 0.0; s = clamp01(-c / a); }
+            else if (t > 1.0) { t = 1.0; s = clamp01((b - c) / a); }
+        }
+    }
+    double d[3];
+    for (int k = 0; k < 3; k++) d[k] = (p1[k] + s * d1[k]) - (p2[k] + t * d2[k]);
+    return dot3(d, d);
+}
+
+/* squared distance from point p to triangle abc (Ericson 5.1.5, Voronoi regions) */
+static double point_tri_dist2(const double *p, const double *a, const double *b, const double *c) {
+    double ab[3], ac[3], ap[3], bp[3], cp[3], q[3];
+    sub3(b, a, ab); sub3(c, a, ac); sub3(p, a, ap);
+    const double d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+    if (d1 <= 0.0 && d2 <= 0.0) return dot3(ap, ap);
+    sub3(p, b, bp);
+    const double d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+    if (d3 >= 0.0 && d4 <= d3) return dot3(bp, bp);
+    const double vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) {
+        const double v = d1 / (d1 - d3);
+        for (int k = 0; k < 3; k++) q[k] = ap[k] - v * ab[k];
+        return dot3(q, q);
+    }
+    sub3(p, c, cp);
+    const double d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+    if (d6 >= 0.0 && d5 <= d6) return dot3(cp, cp);
+    const double vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) {
+        const double w = d2 / (d2 - d6);
+        for (int k = 0; k < 3; k++) q[k] = ap[k] - w * ac[k];
+        return dot3(q, q);
+    }
+    const double va = d3 * d6 - d5 * d4;
+    if (va <= 0.0 && (d4 - d3) >= 0.0 && (d5 - d6) >= 0.0) {
+        const double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        for (int k = 0; k < 3; k++) q[k] = bp[k] - w * (c[k] - b[k]);
+        return dot3(q, q);
+    }
+    const double den = 1.0 / (va + vb + vc), v = vb * den, w = vc * den;
+    for (int k = 0; k < 3; k++) q[k] = ap[k] - v * ab[k] - w * ac[k];
+    return dot3(q, q);
+}
+
+/* does the segment pq cross the triangle abc (closed sets, non-coplanar case; the coplanar case is
+ * caught by the edge-edge distances, which are then 0) */
+static int seg_crosses_tri(const double *p, const double *q, const double *a, const double *b, const double *c) {
+    double ab[3], ac[3], n[3], ap[3], aq[3];
+    sub3(b, a, ab); sub3(c, a, ac); cross3(ab, ac, n);
+    sub3(p, a, ap); sub3(q, a, aq);
+    const double sp = dot3(n, ap), sq = dot3(n, aq);
+    if ((sp > 0.0 && sq > 0.0) || (sp < 0.0 && sq < 0.0) || sp == sq) return 0;
+    const double t = sp / (sp - sq);
+    double x[3], ax[3];
+    for (int k = 0; k < 3; k++) x[k] = p[k] + t * (q[k] - p[k]);
+    sub3(x, a, ax);
+    const double d00 = dot3(ab, ab), d01 = dot3(ab, ac), d11 = dot3(ac, ac), d20 = dot3(ax, ab), d21 = dot3(ax, ac);
+    const double den = d00 * d11 - d01 * d01;
+    if (!(den > 0.0)) return 0;
+    const double v = (d11 * d20 - d01 * d21) / den, w = (d00 * d21 - d01 * d20) / den;
+    return v >= 0.0 && w >= 0.0 && v + w <= 1.0;
+}
+
+/* exact distance between two triangles (0 when they intersect); A = a[0..8], B = b[0..8] */
+static double tri_tri_dist2(const double *a, const double *b) {
+    for (int i = 0; i < 3; i++) {
+        if (seg_crosses_tri(a + 3 * i, a + 3 * ((i + 1) % 3), b, b + 3, b + 6)) return 0.0;
+        if (seg_crosses_tri(b + 3 * i, b + 3 * ((i + 1) % 3), a, a + 3, a + 6)) return 0.0;
+    }
+    double best = INFINITY;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            const double d = seg_seg_dist2(a + 3 * i, a + 3 * ((i + 1) % 3), b + 3 * j, b + 3 * ((j + 1) % 3));
+            if (d < best) best = d;
+        }
+    for (int i = 0; i < 3; i++) {
+        double d = point_tri_dist2(a + 3 * i, b, b + 3, b + 6);
+        if (d < best) best = d;
+        d = point_tri_dist2(b + 3 * i, a, a + 3, a + 6);
+        if (d < best) best = d;
+    }
+    return best;
+}
+
+static void tri_to_world(const double *T, const double *tri, double *out, double *lo, double *hi) {
+    for (int k = 0; k < 3; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+    for (int v = 0; v < 3; v++)
+        for (int k = 0; k < 3; k++) {
+            const double x = T[3 * k] * tri[3 * v] + T[3 * k + 1] * tri[3 * v + 1] + T[3 * k + 2] * tri[3 * v + 2] + T[9 + k];
+            out[3 * v + k] = x;
+            if (x < lo[k]) lo[k] = x;
+            if (x > hi[k]) hi[k] = x;
+        }
+}
+
+/* Distance between the SURFACES of geometries ga and gb, where a geometry with ntri > 0 is its
+ * triangle soup (tri: [ntri][9] vertex coordinates in the geometry frame) and a geometry with
+ * ntri == 0 is the solid primitive of the model.  Stops as soon as a distance <= stop_at is found
+ * and returns it (pass a negative stop_at for the exact minimum).  brute != 0 disables the
+ * bounding-box rejection (used by the tests to validate it). */
+double oracle_soup_pair_distance(const oracle_model *m, const double *oMg, int ga, int gb, const double *triA, int ntA,
+                                 const double *triB, int ntB, double stop_at, int brute) {
+    oracle_counters cnt = {0};
+    double best = INFINITY;
+    if (ntA > 0 && ntB > 0) {
+        double *WB = malloc((size_t)ntB * 15 * sizeof(double));
+        for (int j = 0; j < ntB; j++) tri_to_world(oMg + 12 * gb, triB + 9 * j, WB + 15 * j, WB + 15 * j + 9, WB + 15 * j + 12);
+        double blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int j = 0; j < ntB; j++)
+            for (int k = 0; k < 3; k++) {
+                if (WB[15 * j + 9 + k] < blo[k]) blo[k] = WB[15 * j + 9 + k];
+                if (WB[15 * j + 12 + k] > bhi[k]) bhi[k] = WB[15 * j + 12 + k];
+            }
+        for (int i = 0; i < ntA && !(best <= stop_at); i++) {
+            double wa[9], lo[3], hi[3];
+            tri_to_world(oMg + 12 * ga, triA + 9 * i, wa, lo, hi);
+            if (!brute) {   /* against B's whole box first */
+                double g2 = 0.0;
+                for (int k = 0; k < 3; k++) { const double g = fmax(fmax(lo[k] - bhi[k], blo[k] - hi[k]), 0.0); g2 += g * g; }
+                if (g2 >= best * best) continue;
+            }
+            for (int j = 0; j < ntB; j++) {
+                const double *wb = WB + 15 * j;
+                if (!brute) {
+                    double g2 = 0.0;
+                    for (int k = 0; k < 3; k++) { const double g = fmax(fmax(lo[k] - wb[12 + k], wb[9 + k] - hi[k]), 0.0); g2 += g * g; }
+                    if (g2 >= best * best) continue;
+                }
+                const double d2 = tri_tri_dist2(wa, wb);
+                if (d2 < best * best) best = sqrt(d2);
+                if (best <= stop_at) break;
+            }
+        }
+        free(WB);
+        return best;
+    }
+    if (ntA == 0 && ntB == 0) return oracle_pair_distance(m, oMg, ga, gb, NULL, NULL);
+    /* primitive (solid) against a soup: GJK between the primitive's core and each triangle */
+    const int gp = ntA == 0 ? ga : gb, gs = ntA == 0 ? gb : ga;
+    const double *tri = ntA == 0 ? triB : triA;
+    const int nt = ntA == 0 ? ntB : ntA;
+    shape_t P, Tr;
+    make_shape(m, gp, oMg, &P);
+    Tr.shape = SH_CONVEX; Tr.par = NULL; Tr.nverts = 3; Tr.T = oMg + 12 * gs; Tr.radius = 0.0;
+    for (int i = 0; i < nt && !(best <= stop_at); i++) {
+        Tr.verts = tri + 9 * i;
+        double pa[3], pb[3];
+        int inter;
+        double d = gjk_core_distance(&P, &Tr, pa, pb, &inter, &cnt);
+        d = inter ? 0.0 : fmax(d - P.radius, 0.0);
+        if (d < best) best = d;
+    }
+    return best;
+}
+
+/* Batch: per state the hull verdict (the engine's semantics: any active pair with hull distance <=
+ * padding) and the surface verdict (any active pair with surface distance <= padding).  A surface
+ * lies inside its hull, so only pairs that hit by hull need the triangle test.  min_hull_hit[i] =
+ * number of pairs of state i that hit by hull but not by surface.  tris: all triangles [..][9] in
+ * their geometry frames; tri_off / tri_cnt per geometry (cnt 0 = primitive). */
+typedef struct {
+    const oracle_model *m; const double *q; double padding;
+    const double *tris; const int32_t *tri_off, *tri_cnt;
+    uint8_t *hull_hit, *soup_hit; int32_t *flipped_pairs;
+} soup_ctx;
+
+static void soup_chunk(void *vctx, int64_t b, int64_t e, oracle_counters *cnt, int64_t *aux) {
+    soup_ctx *c = (soup_ctx *)vctx;
+    const oracle_model *m = c->m;
+    double *oMi = malloc(sizeof(double) * 12 * m->njoints), *oMg = malloc(sizeof(double) * 12 * m->ngeoms);
+    for (int64_t i = b; i < e; i++) {
+        oracle_fk(m, c->q + i * m->nq, oMi, oMg);
+        int hh = 0, sh = 0, flipped = 0;
+        for (int p = 0; p < m->npairs; p++) {
+            const int ga = m->pairs[2 * p], gb = m->pairs[2 * p + 1];
+            double ca[3], cb[3];
+            for (int k = 0; k < 3; k++) {
+                const double *Ta = oMg + 12 * ga, *Tb = oMg + 12 * gb, *sa = m->geom_bsphere + 4 * ga, *sb = m->geom_bsphere + 4 * gb;
+                ca[k] = Ta[3 * k] * sa[0] + Ta[3 * k + 1] * sa[1] + Ta[3 * k + 2] * sa[2] + Ta[9 + k];
+                cb[k] = Tb[3 * k] * sb[0] + Tb[3 * k + 1] * sb[1] + Tb[3 * k + 2] * sb[2] + Tb[9 + k];
+            }
+            double dcen[3];
+            sub3(ca, cb, dcen);
+            const double rr = m->geom_bsphere[4 * ga + 3] + m->geom_bsphere[4 * gb + 3] + c->padding;
+            if (dot3(dcen, dcen) > rr * rr) continue;
+            if (oracle_pair_distance(m, oMg, ga, gb, NULL, cnt) > c->padding) continue;
+            hh = 1;
+            const double ds = oracle_soup_pair_distance(m, oMg, ga, gb, c->tris + 9 * (int64_t)c->tri_off[ga], c->tri_cnt[ga],
+                                                        c->tris + 9 * (int64_t)c->tri_off[gb], c->tri_cnt[gb], c->padding, 0);
+            (*aux)++;
+            if (ds <= c->padding) sh = 1; else flipped++;
+        }
+        c->hull_hit[i] = (uint8_t)hh; c->soup_hit[i] = (uint8_t)sh;
+        if (c->flipped_pairs) c->flipped_pairs[i] = flipped;
+    }
+    free(oMi); free(oMg);
+}
+
+void oracle_soup_check_states(const oracle_model *m, const double *q, int64_t n, double padding, const double *tris,
+                              const int32_t *tri_off, const int32_t *tri_cnt, int nthreads, uint8_t *hull_hit, uint8_t *soup_hit,
+                              int32_t *flipped_pairs, int64_t *soup_tests) {
+    soup_ctx c = {m, q, padding, tris, tri_off, tri_cnt, hull_hit, soup_hit, flipped_pairs};
+    parallel_for(n, 64, nthreads, soup_chunk, &c, NULL, soup_tests);
 }

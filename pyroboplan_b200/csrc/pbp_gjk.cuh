@@ -529,21 +529,60 @@ __device__ __forceinline__ void gjk_witness(const GjkState &s, float3 &pa, float
         l1 = den > 0.f ? dot3(sub3(s.v, s.W0), e) / den : 0.f;
         l1 = fminf(fmaxf(l1, 0.f), 1.f);
     } else if (s.n >= 3) {
-        // triangle: v = W0 + l1 e1 + l2 e2 (least squares in the plane)
-        const float3 e1 = sub3(s.W1, s.W0), e2 = sub3(s.W2, s.W0), r = sub3(s.v, s.W0);
-        const float a11 = dot3(e1, e1), a12 = dot3(e1, e2), a22 = dot3(e2, e2);
-        const float b1 = dot3(r, e1), b2 = dot3(r, e2);
-        const float det = a11 * a22 - a12 * a12;
-        if (det > 1e-12f * a11 * a22) {
-            l1 = (b1 * a22 - b2 * a12) / det;
-            l2 = (b2 * a11 - b1 * a12) / det;
-        } else if (a11 >= a22 && a11 > 0.f) {   // degenerate (collinear) triangle: use its longer edge
-            l1 = b1 / a11;
-        } else if (a22 > 0.f) {
-            l2 = b2 / a22;
+        // triangle: v = sum(lam_i W_i), least squares in the plane, solved from the corner with the
+        // widest angle-sine.  GJK on curved supports ends on needle triangles (two rim points of a
+        // cylinder 0.4 mm apart, the third 35 cm away): from the needle's tip the Gram determinant
+        // a11 a22 - a12^2 cancels to a few FP32 digits (weights wrong by 10 %, witnesses by
+        // centimetres), from an end of the short edge it is well conditioned.
+        const float3 Wc[3] = {s.W0, s.W1, s.W2};
+        float lam[3] = {1.f, 0.f, 0.f};
+        float best_rel = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float3 f1 = sub3(Wc[(c + 1) % 3], Wc[c]), f2 = sub3(Wc[(c + 2) % 3], Wc[c]), rc = sub3(s.v, Wc[c]);
+            const float c11 = dot3(f1, f1), c12 = dot3(f1, f2), c22 = dot3(f2, f2);
+            const float dc = c11 * c22 - c12 * c12;
+            const float rel = c11 * c22 > 0.f ? dc / (c11 * c22) : 0.f;
+            if (rel > best_rel) {
+                best_rel = rel;
+                const float g1 = dot3(rc, f1), g2 = dot3(rc, f2);
+                const float u = (g1 * c22 - g2 * c12) / dc, w = (g2 * c11 - g1 * c12) / dc;
+                lam[(c + 1) % 3] = u; lam[(c + 2) % 3] = w; lam[c] = 1.f - u - w;
+            }
         }
-        l1 = fminf(fmaxf(l1, 0.f), 1.f);
-        l2 = fminf(fmaxf(l2, 0.f), 1.f - l1);
+        const float3 e1 = sub3(s.W1, s.W0), e2 = sub3(s.W2, s.W0), r = sub3(s.v, s.W0);
+        const float a11 = dot3(e1, e1), a22 = dot3(e2, e2);
+        const float b1 = dot3(r, e1), b2 = dot3(r, e2);
+        bool ok = false;
+        if (best_rel > 1e-6f) {
+            l1 = lam[1]; l2 = lam[2];
+            ok = l1 >= -1e-4f && l2 >= -1e-4f && l1 + l2 <= 1.0001f;
+            l1 = fminf(fmaxf(l1, 0.f), 1.f);
+            l2 = fminf(fmaxf(l2, 0.f), 1.f - l1);
+        }
+        if (!ok) {
+            // Sliver triangle (curved supports: two rim points of a cylinder next to each other) or
+            // weights that needed clamping: v lies on one of the edges to working precision -- take
+            // the edge whose closest point reproduces v best, so that sum(l_i W_i) = v holds and the
+            // two witnesses stay |v| apart.
+            const float3 e3 = sub3(s.W2, s.W1);
+            const float a33 = dot3(e3, e3);
+            const float t1 = a11 > 0.f ? fminf(fmaxf(b1 / a11, 0.f), 1.f) : 0.f;                      // edge 0-1
+            const float t2 = a22 > 0.f ? fminf(fmaxf(b2 / a22, 0.f), 1.f) : 0.f;                      // edge 0-2
+            const float t3 = a33 > 0.f ? fminf(fmaxf(dot3(sub3(s.v, s.W1), e3) / a33, 0.f), 1.f) : 0.f; // edge 1-2
+            const float3 r1 = sub3(r, make_float3(e1.x * t1, e1.y * t1, e1.z * t1));
+            const float3 r2 = sub3(r, make_float3(e2.x * t2, e2.y * t2, e2.z * t2));
+            const float3 r3 = sub3(sub3(s.v, s.W1), make_float3(e3.x * t3, e3.y * t3, e3.z * t3));
+            const float q1 = dot3(r1, r1), q2 = dot3(r2, r2), q3 = dot3(r3, r3);
+            float q0 = FLT_MAX;
+            if (best_rel > 1e-6f) {
+                const float3 r0 = sub3(r, make_float3(e1.x * l1 + e2.x * l2, e1.y * l1 + e2.y * l2, e1.z * l1 + e2.z * l2));
+                q0 = dot3(r0, r0);
+            }
+            if (q1 <= q0 && q1 <= q2 && q1 <= q3) { l1 = t1; l2 = 0.f; }
+            else if (q2 <= q0 && q2 <= q3) { l1 = 0.f; l2 = t2; }
+            else if (q3 <= q0) { l1 = 1.f - t3; l2 = t3; }
+        }
     }
     pa = s.A0;
     float3 m = s.W0;   // Minkowski image of the combination

@@ -174,8 +174,11 @@ __device__ __noinline__ bool epa_run(const ShapeRef &A, const ShapeRef &B, const
     depth = f.d;
     n = make_float3(f.nx, f.ny, f.nz);
     pa = madd3(madd3(Av[f.v0], sub3(Av[f.v1], Av[f.v0]), bu), sub3(Av[f.v2], Av[f.v0]), bw);
-    const float3 m = madd3(madd3(W[f.v0], sub3(W[f.v1], W[f.v0]), bu), sub3(W[f.v2], W[f.v0]), bw);
-    pb = sub3(pa, m);
+    // the witness on B is the one on A moved by the penetration vector n * depth.  (The barycentric
+    // point of the face equals n * depth on a convex polytope; on curved supports the 40-vertex
+    // polytope has sliver faces, the projection of the origin can fall outside the closest one and
+    // the clamped weights would break p2 - p1 = n * distance, which the callers rely on.)
+    pb = make_float3(pa.x - n.x * depth, pa.y - n.y * depth, pa.z - n.z * depth);
     return true;
 }
 

@@ -100,3 +100,64 @@ def test_random_model_matches_oracle(seed):
     ref, _, _, _ = orc.check_edges(a.astype(np.float64), b.astype(np.float64), 0.05)
     assert (eng.check_edges(a, b, 0.05) == ref.astype(bool)).all()
     eng.close()
+
+
+@pytest.mark.parametrize("seed", [21, 22, 23, 24])
+def test_random_model_signed_distances_and_witnesses(seed):
+    """Per-pair signed distances (EPA for overlaps), witness points and normals on random models."""
+    from oracle.oracle import Oracle
+    from pyroboplan_b200.engine import CollisionEngine
+
+    model, cm = random_model(seed)
+    eng = CollisionEngine(model, cm, device=0)
+    orc = Oracle(model, cm)
+    rng = np.random.default_rng(200 + seed)
+    q = rng.uniform(model.lowerPositionLimit, model.upperPositionLimit, size=(150, model.nq)).astype(np.float32)
+    dist, p1, p2, nrm = eng.compute_distances(q)
+    curved = [type(g.geometry).__name__ in ("Cylinder",) for g in cm.geometryObjects]
+    checked = deep = 0
+    for i in range(len(q)):
+        _, oMg = orc.fk(q[i].astype(np.float64))
+        for k, cp in enumerate(cm.collisionPairs):
+            ds, pa, pb, n, exact = orc.pair_signed_distance_placed(oMg, cp.first, cp.second)
+            if not exact:
+                continue
+            tol = 2e-3 if (curved[cp.first] or curved[cp.second]) and ds < 0 else 3e-5   # 40-vertex EPA polytope on curved supports
+            assert abs(dist[i, k] - ds) < tol, (seed, i, k, dist[i, k], ds)
+            if abs(ds) > 1e-4:
+                np.testing.assert_allclose(p2[i, k].astype(np.float64) - p1[i, k], nrm[i, k].astype(np.float64) * dist[i, k], atol=2e-5)
+            checked += 1
+            deep += int(ds < -1e-4)
+    assert checked > 1000 and deep > 5
+    eng.close()
+
+
+@pytest.mark.parametrize("seed", [31, 32, 33])
+def test_random_tree_ik_iteration(seed):
+    """One damped-least-squares iteration on random trees (generic axes, prismatic joints, branches)."""
+    import torch
+
+    from oracle import ik_oracle as ik
+    from pyroboplan_b200.engine import CollisionEngine
+    from pyroboplan_b200.model import Frame, FRAME_OP, SE3
+
+    model, cm = random_model(seed)
+    rng = np.random.default_rng(300 + seed)
+    fid = model.addFrame(Frame("tool", model.njoints - 1, SE3(random_rotation(rng), rng.uniform(-0.1, 0.1, size=3)), FRAME_OP))
+    eng = CollisionEngine(model, cm, device=0)
+    n = 100
+    goal = rng.uniform(model.lowerPositionLimit, model.upperPositionLimit, size=(n, model.nq))
+    init = rng.uniform(model.lowerPositionLimit, model.upperPositionLimit, size=(n, model.nq))
+    targets = np.array([np.concatenate([T[:3, :3].reshape(9), T[:3, 3]]) for T in (ik.frame_pose(model, fid, g)[0] for g in goal)])
+    Q1, status, iters, e0 = eng.ik_iterate(fid, torch.as_tensor(targets, device="cuda:0"), torch.as_tensor(init, device="cuda:0"), max_iters=1)
+    Q1 = Q1.cpu().numpy()
+    for i in range(n):
+        T = np.eye(4)
+        T[:3, :3] = targets[i, :9].reshape(3, 3)
+        T[:3, 3] = targets[i, 9:]
+        q_ref, conv, _, it, _ = ik.ik_try(model, fid, T, init[i], max_iters=1)
+        if conv:
+            continue
+        step = np.abs(q_ref - init[i]).max()
+        np.testing.assert_allclose(Q1[i], q_ref, atol=1e-9 * max(1.0, step / 1e-3))
+    eng.close()

@@ -260,3 +260,36 @@ def test_curved_pairs_are_stable_under_tiny_perturbations():
     for a, b in [(p.first, p.second) for p in cm.collisionPairs][:40]:
         ds = np.array([orc.pair_distance(x, a, b)[0] for x in qs])
         assert np.abs(np.diff(ds)).max() < 1e-4
+
+
+def test_penetration_depth_from_a_planar_gjk_simplex():
+    """Regression: a sphere centre inside a cylinder keeps every GJK direction in the axial plane through
+    the centre, so GJK ends on a TRIANGLE through the origin, not on a tetrahedron.  The oracle once
+    read that as touching cores (depth = sphere radius only; found by tests/test_gpu_random_models.py,
+    where the device's bipyramid start was right).  The analytic depth of a point inside a cylinder is
+    min(R - rho, h/2 - |z|); the sphere radius adds to it."""
+    from test_gpu_random_models import random_model
+
+    model, cm = random_model(22)
+    orc = Oracle(model, cm)
+    geoms = cm.geometryObjects
+    pairs = [(p.first, p.second) for p in cm.collisionPairs
+             if {type(geoms[p.first].geometry).__name__, type(geoms[p.second].geometry).__name__} == {"Sphere", "Cylinder"}]
+    rng = np.random.default_rng(222)
+    q = rng.uniform(model.lowerPositionLimit, model.upperPositionLimit, size=(300, model.nq))
+    placements = [orc.fk(x)[1] for x in q]
+    inside = 0
+    for pair in pairs:
+        a, b = pair if type(geoms[pair[0]].geometry).__name__ == "Sphere" else pair[::-1]
+        r, R, hl = geoms[a].geometry.radius, geoms[b].geometry.radius, geoms[b].geometry.halfLength
+        for oMg in placements:
+            Rb, tb = oMg[b][:9].reshape(3, 3), oMg[b][9:]
+            c = Rb.T @ (oMg[a][9:] - tb)            # sphere centre in the cylinder's frame
+            rho = np.hypot(c[0], c[1])
+            if rho >= R or abs(c[2]) >= hl:
+                continue
+            ds, _, _, _, exact = orc.pair_signed_distance_placed(oMg, *pair)
+            assert exact
+            assert ds == pytest.approx(-(min(R - rho, hl - abs(c[2])) + r), abs=1e-4)   # 320-vertex polytope on a curved support
+            inside += 1
+    assert inside > 20
