@@ -88,6 +88,23 @@ typedef struct {
      * radius, flag (!= 0: use it).  A second "certainly free" proxy of the broadphase for elongated
      * shapes; it must contain the whole shape. */
     const float *geom_capsule;         /* [ngeoms][8] */
+    /* optional (all NULL / 0: every geometry is a solid): SURFACE semantics of triangle meshes.
+     * Pinocchio loads a URDF <mesh> as a coal BVHModel -- the surface triangles, not the solid
+     * (pinocchio.buildModelsFromUrdf, src/pyroboplan/models/panda.py:27) -- so a shape that lies
+     * wholly inside a mesh without touching its surface does NOT collide with it in the reference
+     * (1 in 1000 uniform Panda states: a finger inside link 0 / 1 / 2 / 5 while the hand - link pair
+     * is disabled by the SRDF).  For such pairs a hull overlap only counts when neither shape is
+     * enclosed by the other's surface; the enclosure test needs the hull's face planes.
+     *   planes            n.x <= off inside, unit normals, geometry frame
+     *   geom_surface_tol  how far the mesh surface lies below its hull (dents), metres
+     *   pair_enclose      bit 0: `second` could lie wholly inside `first`, and `first` is a surface;
+     *                     bit 1: `first` could lie wholly inside `second`, and `second` is a surface */
+    const float *planes;               /* [nplanes][4] nx ny nz off */
+    const int32_t *geom_plane_off;     /* [ngeoms] first plane of the geometry's hull */
+    const int32_t *geom_plane_cnt;     /* [ngeoms] number of planes (0: none given) */
+    const float *geom_surface_tol;     /* [ngeoms] */
+    const uint8_t *pair_enclose;       /* [npairs] */
+    int32_t nplanes;
 } pbp_model_desc;
 
 typedef struct pbp_engine pbp_engine;

@@ -53,6 +53,9 @@ class _CModel(ctypes.Structure):
         ("geom_isphere", ctypes.c_void_p),
         ("verts", ctypes.c_void_p),
         ("pairs", ctypes.c_void_p),
+        ("tris", ctypes.c_void_p),
+        ("tri_off", ctypes.c_void_p),
+        ("tri_cnt", ctypes.c_void_p),
     ]
 
 
@@ -123,7 +126,10 @@ def _ptr(a):
 class Oracle:
     """Float64 CPU evaluation of the hot path for one (model, collision_model)."""
 
-    def __init__(self, model, collision_model):
+    def __init__(self, model, collision_model, mesh_semantics="surface"):
+        """mesh_semantics: "surface" -- geometries that carry the triangles of a mesh file are surfaces,
+        as Pinocchio's BVHModel meshes are in the reference (verdicts and min distances then come from
+        exact triangle tests wherever the hulls are within the padding); "hull" -- convex solids."""
         self.lib = _load()
         self.nq = model.nq
         nj = model.njoints
@@ -190,6 +196,10 @@ class Oracle:
         for k, v in self._arrays.items():
             setattr(cm, k, v.ctypes.data)
         self._cm = cm
+        self.set_mesh_triangles(collision_model)
+        self.mesh_semantics = mesh_semantics if self._tri_cnt.any() else "hull"
+        if self.mesh_semantics == "surface":
+            cm.tris, cm.tri_off, cm.tri_cnt = self._tris.ctypes.data, self._tri_off.ctypes.data, self._tri_cnt.ctypes.data
 
     # ------------------------------------------------------------------ FK
     def fk(self, q):
@@ -205,6 +215,11 @@ class Oracle:
         _, oMg = self.fk(q)
         out = np.zeros(7)
         d = self.lib.oracle_pair_distance(ctypes.byref(self._cm), _ptr(oMg), int(ga), int(gb), _ptr(out), None)
+        return d, out[:3].copy(), out[3:6].copy(), bool(out[6])
+
+    def pair_distance_placed(self, oMg, ga, gb):
+        out = np.zeros(7)
+        d = self.lib.oracle_pair_distance(ctypes.byref(self._cm), _ptr(np.ascontiguousarray(oMg)), int(ga), int(gb), _ptr(out), None)
         return d, out[:3].copy(), out[3:6].copy(), bool(out[6])
 
     def pair_signed_distance(self, q, ga, gb):

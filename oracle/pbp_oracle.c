@@ -59,6 +59,11 @@ typedef struct {
     const double *geom_isphere;    /* [ngeoms][4] inscribed sphere cx cy cz r in geometry frame */
     const double *verts;           /* [nverts][3] */
     const int32_t *pairs;          /* [npairs][2] */
+    /* optional (NULL: every geometry is a solid): surface triangles of the mesh geometries, the
+     * reference's semantics for URDF meshes (see "triangle-soup semantics" at the end of the file) */
+    const double *tris;            /* [ntris][9] vertex coordinates, geometry frame */
+    const int32_t *tri_off;        /* [ngeoms] */
+    const int32_t *tri_cnt;        /* [ngeoms] 0 = solid primitive / solid hull */
 } oracle_model;
 
 typedef struct {
@@ -435,6 +440,22 @@ static void proxy_bounds(const oracle_model *m, const double *oMg, int ga, int g
  * first_pair = index of the first colliding pair in list order, or -1.
  * use_cull: skip pairs whose bounding spheres are farther apart than `padding` (cannot change
  * the verdict; min_dist then is min over the un-culled pairs and the cull lower bounds). */
+double oracle_soup_pair_distance(const oracle_model *m, const double *oMg, int ga, int gb, const double *triA, int ntA,
+                                 const double *triB, int ntB, double stop_at, int mode);
+
+/* Distance of a pair under the model's semantics.  Solids: the hull / primitive distance.  With
+ * surface triangles: a surface lies inside its hull, so the hull distance is a lower bound and only
+ * a pair whose hulls are within `padding` needs the triangle test; its result (stopped at the first
+ * triangle pair within padding) replaces the hull distance. */
+static double pair_distance_semantics(const oracle_model *m, const double *oMg, int ga, int gb, double padding, int want_exact,
+                                      oracle_counters *cnt) {
+    double d = oracle_pair_distance(m, oMg, ga, gb, NULL, cnt);
+    if (d <= padding && m->tris && (m->tri_cnt[ga] > 0 || m->tri_cnt[gb] > 0))
+        d = oracle_soup_pair_distance(m, oMg, ga, gb, m->tris + 9 * (int64_t)m->tri_off[ga], m->tri_cnt[ga],
+                                      m->tris + 9 * (int64_t)m->tri_off[gb], m->tri_cnt[gb], padding, want_exact ? 0 : 2);
+    return d;
+}
+
 int oracle_check_state(const oracle_model *m, const double *q, double padding, int want_all, int use_cull,
                        double *min_dist, int32_t *first_pair, double *oMi_scratch, double *oMg_scratch,
                        oracle_counters *cnt) {
@@ -450,6 +471,7 @@ int oracle_check_state(const oracle_model *m, const double *q, double padding, i
         for (int k = 0; k < m->npairs; k++) {
             double lb, ub;
             proxy_bounds(m, oMg_scratch, m->pairs[2 * k], m->pairs[2 * k + 1], &lb, &ub);
+            if (m->tris && (m->tri_cnt[m->pairs[2 * k]] > 0 || m->tri_cnt[m->pairs[2 * k + 1]] > 0)) continue;   /* overlapping inscribed spheres do not prove a SURFACE contact */
             if (ub <= padding - slack) { if (first_pair) *first_pair = k; if (min_dist) *min_dist = 0.0; return 1; }
         }
         for (int k = 0; k < m->npairs; k++) {
@@ -457,7 +479,7 @@ int oracle_check_state(const oracle_model *m, const double *q, double padding, i
             int ga = m->pairs[2 * k], gb = m->pairs[2 * k + 1];
             proxy_bounds(m, oMg_scratch, ga, gb, &lb, &ub);
             if (lb > padding + slack) { cnt->culled++; continue; }
-            double d = oracle_pair_distance(m, oMg_scratch, ga, gb, NULL, cnt);
+            double d = pair_distance_semantics(m, oMg_scratch, ga, gb, padding, 0, cnt);
             if (d < md) md = d;
             if (d <= padding) { hit = 1; fp = k; break; }
         }
@@ -469,7 +491,7 @@ int oracle_check_state(const oracle_model *m, const double *q, double padding, i
         int ga = m->pairs[2 * k], gb = m->pairs[2 * k + 1];
         if (use_cull && !want_all && sphere_cull(m, oMg_scratch, ga, gb, padding)) { cnt->culled++; continue; }
         if (use_cull && want_all && md < INFINITY && sphere_cull(m, oMg_scratch, ga, gb, md)) { cnt->culled++; continue; }
-        double d = oracle_pair_distance(m, oMg_scratch, ga, gb, NULL, cnt);
+        double d = pair_distance_semantics(m, oMg_scratch, ga, gb, padding, min_dist != NULL, cnt);
         if (d < md) md = d;
         if (d <= padding) {
             if (fp < 0) fp = k;
@@ -1006,13 +1028,17 @@ static void tri_to_world(const double *T, const double *tri, double *out, double
 
 /* Distance between the SURFACES of geometries ga and gb, where a geometry with ntri > 0 is its
  * triangle soup (tri: [ntri][9] vertex coordinates in the geometry frame) and a geometry with
- * ntri == 0 is the solid primitive of the model.  Stops as soon as a distance <= stop_at is found
- * and returns it (pass a negative stop_at for the exact minimum).  brute != 0 disables the
- * bounding-box rejection (used by the tests to validate it). */
+ * ntri == 0 is the solid primitive of the model.  Stops as soon as a distance <= stop_at (or 0) is
+ * found and returns it.  mode 0: exact minimum otherwise, with bounding-box rejection; mode 1: the
+ * same by brute force (the tests validate mode 0 with it); mode 2: verdict only -- triangles
+ * farther than stop_at from the other mesh's box are never visited, and when nothing is within
+ * stop_at the value returned is merely some number > stop_at. */
 double oracle_soup_pair_distance(const oracle_model *m, const double *oMg, int ga, int gb, const double *triA, int ntA,
-                                 const double *triB, int ntB, double stop_at, int brute) {
+                                 const double *triB, int ntB, double stop_at, int mode) {
     oracle_counters cnt = {0};
     double best = INFINITY;
+    const int brute = mode == 1;
+    if (stop_at < 0.0) stop_at = 0.0;
     if (ntA > 0 && ntB > 0) {
         double *WB = malloc((size_t)ntB * 15 * sizeof(double));
         for (int j = 0; j < ntB; j++) tri_to_world(oMg + 12 * gb, triB + 9 * j, WB + 15 * j, WB + 15 * j + 9, WB + 15 * j + 12);
@@ -1022,20 +1048,57 @@ double oracle_soup_pair_distance(const oracle_model *m, const double *oMg, int g
                 if (WB[15 * j + 9 + k] < blo[k]) blo[k] = WB[15 * j + 9 + k];
                 if (WB[15 * j + 12 + k] > bhi[k]) bhi[k] = WB[15 * j + 12 + k];
             }
+        /* the triangle pairs that can matter lie in the overlap of the two bounding boxes (grown by
+         * the distance that is still interesting): keep only B's triangles that reach A's box */
+        int nB = ntB;
+        if (!brute) {
+            double alo[3] = {INFINITY, INFINITY, INFINITY}, ahi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int i = 0; i < ntA; i++) {
+                double wa[9], lo[3], hi[3];
+                tri_to_world(oMg + 12 * ga, triA + 9 * i, wa, lo, hi);
+                for (int k = 0; k < 3; k++) { if (lo[k] < alo[k]) alo[k] = lo[k]; if (hi[k] > ahi[k]) ahi[k] = hi[k]; }
+            }
+            /* an upper bound of the surface distance: the boxes' diameter sum is crude but finite */
+            const double reach = stop_at > 0.0 ? stop_at : 0.0;
+            int any_overlap = 1;
+            for (int k = 0; k < 3; k++) if (alo[k] - bhi[k] > reach || blo[k] - ahi[k] > reach) any_overlap = 0;
+            if (!any_overlap && mode == 2) { free(WB); return INFINITY; }
+            if (any_overlap && mode == 2) {
+                /* verdict mode: only triangles within `reach` of the other box can produce a hit; if
+                 * none does, the exact distance is still wanted by the caller only as "> stop_at" */
+                nB = 0;
+                for (int j = 0; j < ntB; j++) {
+                    const double *wb = WB + 15 * j;
+                    int keep = 1;
+                    for (int k = 0; k < 3; k++) if (wb[9 + k] - ahi[k] > reach || alo[k] - wb[12 + k] > reach) keep = 0;
+                    if (keep) { if (nB != j) memcpy(WB + 15 * nB, wb, 15 * sizeof(double)); nB++; }
+                }
+                if (nB == 0) { free(WB); return INFINITY; }
+                for (int k = 0; k < 3; k++) { blo[k] = INFINITY; bhi[k] = -INFINITY; }
+                for (int j = 0; j < nB; j++)
+                    for (int k = 0; k < 3; k++) {
+                        if (WB[15 * j + 9 + k] < blo[k]) blo[k] = WB[15 * j + 9 + k];
+                        if (WB[15 * j + 12 + k] > bhi[k]) bhi[k] = WB[15 * j + 12 + k];
+                    }
+                best = INFINITY;
+            }
+        }
+        const int verdict_only = mode == 2;
+        const double reach2 = stop_at > 0.0 ? stop_at * stop_at : 0.0;
         for (int i = 0; i < ntA && !(best <= stop_at); i++) {
             double wa[9], lo[3], hi[3];
             tri_to_world(oMg + 12 * ga, triA + 9 * i, wa, lo, hi);
             if (!brute) {   /* against B's whole box first */
                 double g2 = 0.0;
                 for (int k = 0; k < 3; k++) { const double g = fmax(fmax(lo[k] - bhi[k], blo[k] - hi[k]), 0.0); g2 += g * g; }
-                if (g2 >= best * best) continue;
+                if (g2 >= best * best || (verdict_only && g2 > reach2)) continue;
             }
-            for (int j = 0; j < ntB; j++) {
+            for (int j = 0; j < nB; j++) {
                 const double *wb = WB + 15 * j;
                 if (!brute) {
                     double g2 = 0.0;
                     for (int k = 0; k < 3; k++) { const double g = fmax(fmax(lo[k] - wb[12 + k], wb[9 + k] - hi[k]), 0.0); g2 += g * g; }
-                    if (g2 >= best * best) continue;
+                    if (g2 >= best * best || (verdict_only && g2 > reach2)) continue;
                 }
                 const double d2 = tri_tri_dist2(wa, wb);
                 if (d2 < best * best) best = sqrt(d2);
@@ -1053,8 +1116,21 @@ double oracle_soup_pair_distance(const oracle_model *m, const double *oMg, int g
     shape_t P, Tr;
     make_shape(m, gp, oMg, &P);
     Tr.shape = SH_CONVEX; Tr.par = NULL; Tr.nverts = 3; Tr.T = oMg + 12 * gs; Tr.radius = 0.0;
+    double pc[3];
+    {
+        const double *Tp = oMg + 12 * gp, *bs = m->geom_bsphere + 4 * gp;
+        for (int k = 0; k < 3; k++) pc[k] = Tp[3 * k] * bs[0] + Tp[3 * k + 1] * bs[1] + Tp[3 * k + 2] * bs[2] + Tp[9 + k];
+    }
+    const double pr = m->geom_bsphere[4 * gp + 3];
     for (int i = 0; i < nt && !(best <= stop_at); i++) {
         Tr.verts = tri + 9 * i;
+        if (mode != 1) {   /* the triangle's box against the primitive's bounding sphere */
+            double wt[9], lo[3], hi[3], g2 = 0.0;
+            tri_to_world(oMg + 12 * gs, tri + 9 * i, wt, lo, hi);
+            for (int k = 0; k < 3; k++) { const double g = fmax(fmax(lo[k] - pc[k], pc[k] - hi[k]), 0.0); g2 += g * g; }
+            const double lb = sqrt(g2) - pr;
+            if (lb >= best || (mode == 2 && lb > stop_at)) continue;
+        }
         double pa[3], pb[3];
         int inter;
         double d = gjk_core_distance(&P, &Tr, pa, pb, &inter, &cnt);
@@ -1097,7 +1173,7 @@ static void soup_chunk(void *vctx, int64_t b, int64_t e, oracle_counters *cnt, i
             if (oracle_pair_distance(m, oMg, ga, gb, NULL, cnt) > c->padding) continue;
             hh = 1;
             const double ds = oracle_soup_pair_distance(m, oMg, ga, gb, c->tris + 9 * (int64_t)c->tri_off[ga], c->tri_cnt[ga],
-                                                        c->tris + 9 * (int64_t)c->tri_off[gb], c->tri_cnt[gb], c->padding, 0);
+                                                        c->tris + 9 * (int64_t)c->tri_off[gb], c->tri_cnt[gb], c->padding, 2);
             (*aux)++;
             if (ds <= c->padding) sh = 1; else flipped++;
         }

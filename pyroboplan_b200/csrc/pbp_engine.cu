@@ -98,7 +98,8 @@ struct pbp_engine {
     bool bp_smem_store = true;  // per-thread broadphase store fits in shared memory
     bool verts_in_smem = true;
     DevModel dm{};
-    DeviceBuffer d_joints, d_jgeoms, d_geoms, d_bpgeoms, d_bpboxes, d_bppairs, d_groups, d_pairorig, d_paths, d_pathops, d_order, d_verts, d_supcells, d_suplists, d_qlim, d_frames;
+    DeviceBuffer d_joints, d_jgeoms, d_geoms, d_bpgeoms, d_bpboxes, d_bppairs, d_groups, d_pairorig, d_paths, d_pathops, d_order, d_verts, d_supcells, d_suplists, d_qlim, d_frames, d_planes, d_plane_idx, d_surf_tol, d_pair_enclose;
+    bool surface = false;   // some pair carries an enclosure flag (surface semantics of mesh geometries)
     // pipeline workspaces
     int64_t chunk = 0;  // states per broadphase/narrowphase round = bin capacity
     DeviceBuffer d_bin_state, d_bin_group, d_bin_sample, d_bin_T, d_ctrl;
@@ -249,6 +250,12 @@ int launch_round_kernels(pbp_engine *e, const StateSource &src, int64_t n, float
     else
         k_narrowphase<MODE, false><<<np_grid, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
     LAUNCH_CHECK("k_narrowphase");
+    if (e->surface) {
+        // hull hits of pairs with an enclosure flag were parked by the narrowphase: decide them
+        const unsigned sr_grid = (unsigned)std::min<int64_t>(8 * (int64_t)e->num_sms, std::max<int64_t>(1, (max_items + 31) / 32 / (SR_THREADS / 32)));
+        k_surface_refine<MODE><<<sr_grid, SR_THREADS, 0, st>>>(e->dm, padding, out, bins, has_sample);
+        LAUNCH_CHECK("k_surface_refine");
+    }
     return 0;
 }
 
@@ -527,6 +534,9 @@ static int build_host_tables(const pbp_model_desc *d, HostTables &H) {
             P.r_out = bpgeoms[a].r_out + bpgeoms[b].r_out;
             P.r_in = bpgeoms[a].r_in + bpgeoms[b].r_in;
         }
+        // surface semantics: a pair where one shape could be enclosed by the other's surface is never
+        // "certainly colliding" by its inscribed spheres (the enclosed placement is the free one)
+        if (d->pair_enclose && d->pair_enclose[key.orig] && P.kind != BP_EXACT_SPHERES) P.r_in = -1e30f;
         const std::vector<int> ca = chain_to_root(geoms[a].parent), cb = chain_to_root(geoms[b].parent);
         size_t common = 0;
         while (common < ca.size() && common < cb.size() && ca[common] == cb[common]) common++;
@@ -616,7 +626,7 @@ void pbp_engine_destroy(pbp_engine *e) {
                             &e->d_bin_group, &e->d_bin_sample, &e->d_bin_T, &e->d_ctrl, &e->d_counts, &e->d_desc_group,
                             &e->d_desc_frac, &e->d_desc_sample, &e->d_scratch_i32, &e->d_scratch_u8, &e->d_cub, &e->d_sel,
                             &e->d_io_q, &e->d_io_q2, &e->d_io_hit, &e->d_io_f32, &e->d_io_i32, &e->d_ik_tables, &e->d_ws_oMi, &e->d_ws_oMg, &e->d_ws_dist,
-                            &e->d_ws_p1, &e->d_ws_p2, &e->d_ws_nrm, &e->d_pairs_orig};
+                            &e->d_ws_p1, &e->d_ws_p2, &e->d_ws_nrm, &e->d_pairs_orig, &e->d_planes, &e->d_plane_idx, &e->d_surf_tol, &e->d_pair_enclose};
     for (DeviceBuffer *b : bufs) b->release();
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     e->h_io_hit.release(); e->h_io_f32.release(); e->h_io_i32.release();
@@ -744,6 +754,40 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     e->dm.sup_lists = e->d_suplists.as<uint16_t>();
     e->dm.n_sup_cells = (int)sup_cells.size();
     e->dm.n_sup_lists = (int)sup_lists.size();
+    {
+        // surface semantics tables (optional): planes as float4, per-geometry (offset, count), dent
+        // depth, enclosure flags in INTERNAL pair order
+        std::vector<float> pl(4, 0.f), tol(std::max(d->ngeoms, 1), 0.f);
+        std::vector<int32_t> pidx(2 * (size_t)std::max(d->ngeoms, 1), 0);
+        std::vector<uint8_t> flags(np1, 0);
+        const bool have = d->planes && d->geom_plane_off && d->geom_plane_cnt && d->pair_enclose && d->nplanes > 0;
+        if (have) {
+            pl.assign(d->planes, d->planes + 4 * (size_t)d->nplanes);
+            for (int g = 0; g < d->ngeoms; g++) {
+                pidx[2 * g] = d->geom_plane_off[g];
+                pidx[2 * g + 1] = d->geom_plane_cnt[g];
+                if (pidx[2 * g] < 0 || pidx[2 * g + 1] < 0 || pidx[2 * g] + pidx[2 * g + 1] > d->nplanes)
+                    return bail(fail(PBP_ERR_ARG, "geometry %d: plane range outside [0, %d)", g, d->nplanes));
+                if (d->geom_surface_tol) tol[g] = d->geom_surface_tol[g];
+            }
+            for (int p = 0; p < d->npairs; p++) {
+                const uint8_t f = d->pair_enclose[pair_orig[p]] & 3;
+                const int a = bppairs[p].a, b = bppairs[p].b;
+                if (((f & 1) && pidx[2 * a + 1] == 0) || ((f & 2) && pidx[2 * b + 1] == 0))
+                    return bail(fail(PBP_ERR_ARG, "pair %d: enclosure flag on a geometry without hull planes", pair_orig[p]));
+                flags[p] = f;
+                if (f) e->surface = true;
+            }
+        }
+        if ((rc = upload(e->d_planes, pl.data(), pl.size() * 4)) || (rc = upload(e->d_plane_idx, pidx.data(), pidx.size() * 4)) ||
+            (rc = upload(e->d_surf_tol, tol.data(), tol.size() * 4)) || (rc = upload(e->d_pair_enclose, flags.data(), flags.size())))
+            return bail(rc);
+        e->dm.planes = e->d_planes.as<float4>();
+        e->dm.plane_idx = e->d_plane_idx.as<int2>();
+        e->dm.surface_tol = e->d_surf_tol.as<float>();
+        e->dm.pair_enclose = e->d_pair_enclose.as<uint8_t>();
+        e->dm.surface = e->surface ? 1 : 0;
+    }
     e->dm.q_lower = e->d_qlim.as<float>();
     e->dm.q_upper = e->d_qlim.as<float>() + d->nq;
 
@@ -792,7 +836,7 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
 #undef SET_SMEM_POOL
     e->smem_np_pool = np_tables + vert_bytes + (size_t)PF_WORDS * POOL * 4 + (size_t)POOL * 12 + POOL + (size_t)POOL * 4 +
                       3 * (NP_THREADS / 32) * 4 + 64;
-    e->np_pool = e->verts_in_smem && e->smem_np_pool <= max_optin - 1024 && getenv("PBP_NP_POOL") && atoi(getenv("PBP_NP_POOL")) != 0;
+    e->np_pool = e->verts_in_smem && e->smem_np_pool <= max_optin - 1024 && getenv("PBP_NP_POOL") && atoi(getenv("PBP_NP_POOL")) != 0 && !e->surface;
     if (e->np_pool) {
         int occ_pool = 1;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pool, k_narrowphase_pool<MODE_BOOL>, NP_THREADS, e->smem_np_pool));

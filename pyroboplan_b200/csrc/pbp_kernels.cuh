@@ -73,6 +73,8 @@ struct Outputs {
 };
 
 enum { MODE_BOOL = 0, MODE_BOOL_ALL = 1, MODE_DIST = 2 };
+// bit set in Bins::group by the narrowphase on a hull hit that k_surface_refine has to decide
+constexpr int32_t SR_PARKED = 0x40000000;
 // MODE_BOOL      verdict only; a state stops at its first certain hit, decided groups are skipped
 // MODE_BOOL_ALL  verdict + first_pair / first_bad: every pair of every state is resolved
 // MODE_DIST      verdict + min distance: pairs are resolved unless certainly farther than the bound
@@ -401,6 +403,58 @@ __device__ __forceinline__ bool next_tile(uint32_t *tile_counter, const uint32_t
 }
 
 // ------------------------------------------------------------------------------------------
+// Surface semantics: can this hull hit be an enclosure at all?
+// ------------------------------------------------------------------------------------------
+// A shape wholly inside a mesh SURFACE does not collide with it (k_surface_refine below).  Most hull
+// hits of a flagged pair are ordinary partial overlaps, and one direction d in which the would-be
+// inner shape reaches at least as far as the would-be outer one, h_inner(d) + padding >= h_outer(d),
+// proves that.  Tried, per flagged role: the line between the proxy centres (the inner shape pokes
+// out on the side its centre is displaced to) and both directions of the inner shape's long axis
+// (a finger half inside a link pokes out with one end).  Two support evaluations per direction, on
+// the lane that found the hit; only the items no direction settles are parked for the plane test.
+__device__ __forceinline__ float support_value(const ShapeRef &S, float3 d, float radius, float len) {
+    const float3 sl = support_local(S, d);
+    return dot3(d, sl) + radius * len;
+}
+__device__ __forceinline__ float support_value_placed(const ShapeRef &S, const float *T, float3 d, float radius, float len) {
+    const float3 dl = make_float3(fmaf(T[0], d.x, fmaf(T[3], d.y, T[6] * d.z)), fmaf(T[1], d.x, fmaf(T[4], d.y, T[7] * d.z)),
+                                  fmaf(T[2], d.x, fmaf(T[5], d.y, T[8] * d.z)));
+    const float3 sl = support_local(S, dl);
+    return dot3(d, se3_act(T, sl.x, sl.y, sl.z)) + radius * len;
+}
+__device__ __noinline__ bool may_be_enclosed(int fl, const DevGeom &GA, const DevGeom &GB, const ShapeRef &A, const ShapeRef &B, const float *T,
+                                             float padding) {
+    const float3 ca = make_float3(GA.centre[0], GA.centre[1], GA.centre[2]);
+    const float3 cb = se3_act(T, GB.centre[0], GB.centre[1], GB.centre[2]);
+    float3 d = sub3(cb, ca);
+    if (!(dot3(d, d) > 1e-12f)) d = make_float3(1.f, 0.f, 0.f);
+    if (fl & 1) {   // b inside a's surface?
+        const float3 p0 = se3_act(T, GB.axis0[0], GB.axis0[1], GB.axis0[2]), p1 = se3_act(T, GB.axis1[0], GB.axis1[1], GB.axis1[2]);
+        const float3 u = sub3(p1, p0);
+        bool out = false;
+#pragma unroll 1
+        for (int k = 0; k < (GB.has_axis ? 3 : 1) && !out; k++) {
+            const float3 dir = k == 0 ? d : (k == 1 ? u : make_float3(-u.x, -u.y, -u.z));
+            const float len = sqrtf(dot3(dir, dir));
+            out = support_value_placed(B, T, dir, GB.core_radius, len) + padding * len >= support_value(A, dir, GA.core_radius, len);
+        }
+        if (!out) return true;
+    }
+    if (fl & 2) {   // a inside b's surface?
+        const float3 u = make_float3(GA.axis1[0] - GA.axis0[0], GA.axis1[1] - GA.axis0[1], GA.axis1[2] - GA.axis0[2]);
+        bool out = false;
+#pragma unroll 1
+        for (int k = 0; k < (GA.has_axis ? 3 : 1) && !out; k++) {
+            const float3 dir = k == 0 ? make_float3(-d.x, -d.y, -d.z) : (k == 1 ? u : make_float3(-u.x, -u.y, -u.z));
+            const float len = sqrtf(dot3(dir, dir));
+            out = support_value(A, dir, GA.core_radius, len) + padding * len >= support_value_placed(B, T, dir, GB.core_radius, len);
+        }
+        if (!out) return true;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------
 // Item setup: T = oMg[a]^-1 * oMg[b] for every undecided (state, pair) item
 // ------------------------------------------------------------------------------------------
 template <int MODE>
@@ -650,6 +704,13 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
         //      the simplex slot of a lane's last trip.  (PBP_NP_LOCKSTEP=0 restores the older
         //      policy: per trip, run only the phase most lanes are waiting for.)
         auto publish = [&](const GjkOut &r, float radii) {
+            if (r.hit && M.surface && M.pair_enclose[p]) {
+                // surface semantics: one shape of this pair could be enclosed by the other's surface,
+                // which is the free placement -- k_surface_refine decides the parked item (all its
+                // lanes busy with such items, instead of one lane of this warp)
+                bins.group[slot] = group | SR_PARKED;
+                return;
+            }
             if (MODE == MODE_DIST) {
                 if (r.hit) out.hit[group] = 1;
                 atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(fmaxf(r.dist - radii, 0.f)));
@@ -945,6 +1006,147 @@ k_narrowphase_pool(DevModel M, float padding, Outputs out, Bins bins, uint32_t *
 }
 
 // ------------------------------------------------------------------------------------------
+// Surface semantics of mesh geometries: enclosure test for parked hull hits
+// ------------------------------------------------------------------------------------------
+// The reference's meshes are SURFACES (coal BVHModel): a shape that lies wholly inside a mesh without
+// reaching its surface does not collide with it.  For a convex hull A = {x : n_f.x <= w_f} and a
+// convex shape B, the gap of B to A's boundary is  min_f (w_f - h_B(n_f))  (h_B: support function);
+// B is enclosed with clearance beyond `padding` when that gap exceeds padding.  (The mesh surface lies
+// up to DevModel::surface_tol below its hull where a quad is triangulated along its valley; an
+// enclosed shape closer than that to a dented face is the residual difference to the reference,
+// a few states in a million -- tools/soup_study.py, tools/gpu_surface_check.py.)  The faces are split over `nlanes` cooperating lanes; the caller
+// reduces with a warp maximum when nlanes > 1.
+//   T: placement of `inner` in the frame of the geometry `g_outer`; returns max_f (h_inner(n_f) - w_f).
+__device__ __forceinline__ float enclosure_excess(const DevModel &M, int g_outer, const ShapeRef &inner, float inner_radius, const float *T,
+                                                  float padding, int lane, int nlanes) {
+    const int2 pi = M.plane_idx[g_outer];
+    float worst = -FLT_MAX;
+    for (int f0 = 0; f0 < pi.y; f0 += nlanes) {
+        const int f = f0 + lane;
+        if (f < pi.y) {
+            const float4 pl = __ldg(M.planes + pi.x + f);
+            const float3 dl = make_float3(fmaf(T[0], pl.x, fmaf(T[3], pl.y, T[6] * pl.z)), fmaf(T[1], pl.x, fmaf(T[4], pl.y, T[7] * pl.z)),
+                                          fmaf(T[2], pl.x, fmaf(T[5], pl.y, T[8] * pl.z)));
+            const float3 sl = support_local(inner, dl);
+            const float3 sw = se3_act(T, sl.x, sl.y, sl.z);
+            worst = fmaxf(worst, fmaf(pl.x, sw.x, fmaf(pl.y, sw.y, pl.z * sw.z)) + inner_radius - pl.w);
+        }
+        // one face the inner shape reaches (to within padding) settles it: not enclosed.  Nearly all
+        // parked items end here after the first batch of faces.
+        const bool out = worst >= -padding;
+        if (nlanes > 1 ? __any_sync(0xffffffffu, out) : out) return FLT_MAX;
+    }
+    return worst;
+}
+
+// flags bit 0: b could lie inside a's surface; bit 1: a inside b's.  T: placement of b in a's frame.
+// gap_out (optional): the clearance of the enclosed shape to the enclosing hull.
+__device__ __forceinline__ bool surface_enclosed(const DevModel &M, int flags, int ga, int gb, const ShapeRef &A, const ShapeRef &B, float ra,
+                                                 float rb, const float *T, float padding, int lane, int nlanes, float *gap_out = nullptr) {
+    if (flags & 1) {
+        float ex = enclosure_excess(M, ga, B, rb, T, padding, lane, nlanes);
+        if (nlanes > 1) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ex = fmaxf(ex, __shfl_xor_sync(0xffffffffu, ex, o));
+        }
+        if (-ex > padding) { if (gap_out) *gap_out = -ex; return true; }
+    }
+    if (flags & 2) {
+        float Ti[12];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            Ti[3 * i + 0] = T[i]; Ti[3 * i + 1] = T[3 + i]; Ti[3 * i + 2] = T[6 + i];
+            Ti[9 + i] = -(T[i] * T[9] + T[3 + i] * T[10] + T[6 + i] * T[11]);
+        }
+        float ex = enclosure_excess(M, gb, A, ra, Ti, padding, lane, nlanes);
+        if (nlanes > 1) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ex = fmaxf(ex, __shfl_xor_sync(0xffffffffu, ex, o));
+        }
+        if (-ex > padding) { if (gap_out) *gap_out = -ex; return true; }
+    }
+    return false;
+}
+
+// Parked items (the narrowphase marked bins.group with SR_PARKED instead of publishing the hull hit)
+// are about 0.1 per Panda state; 1 in 100 of them is a real enclosure.  The bins of the flagged pairs
+// are cut into chunks of 32 items, the chunks dealt round-robin to the warps.  Pass 1, one item per
+// lane: may_be_enclosed() -- a direction in which the would-be inner shape pokes out publishes the
+// hit.  Pass 2, one item per warp: the face planes of the enclosing hull split over the 32 lanes.
+constexpr int SR_THREADS = 128;
+
+template <int MODE>
+__global__ void __launch_bounds__(SR_THREADS)
+k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, bool has_sample) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * SR_THREADS + threadIdx.x) >> 5, nwarps = gridDim.x * (SR_THREADS / 32);
+    const int64_t stride = (int64_t)M.npairs * bins.cap;
+    auto commit = [&](int p, int32_t group, int64_t slot, bool enclosed, float gap) {
+        if (MODE == MODE_DIST) {
+            if (!enclosed) out.hit[group] = 1;
+            atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(enclosed ? gap : 0.f));
+        } else if (!enclosed) {
+            out.hit[group] = 1;
+            if (MODE == MODE_BOOL_ALL) {
+                if (out.first_pair) atomicMin(out.first_pair + group, M.pair_orig[p]);
+                if (out.first_bad) atomicMin(out.first_bad + group, has_sample ? bins.sample[slot] : 0);
+            }
+        }
+    };
+    for (uint32_t c = warp;; c += nwarps) {
+        // chunk c of the concatenated flagged bins
+        int p = -1;
+        uint32_t local = 0, acc = 0;
+        for (int k = 0; k < M.npairs; k++) {
+            if (!M.pair_enclose[k]) continue;
+            const uint32_t nch = (bins.count_np[k] + 31u) >> 5;
+            if (c < acc + nch) { p = k; local = c - acc; break; }
+            acc += nch;
+        }
+        if (p < 0) break;
+        const int fl = M.pair_enclose[p];
+        const uint32_t cnt = bins.count_np[p];
+        const BpPair pr = M.bppairs[p];
+        const DevGeom &GA = M.geoms[pr.a];
+        const DevGeom &GB = M.geoms[pr.b];
+        ShapeRef A, B;
+        A.shape = GA.shape; A.p0 = GA.par[0]; A.p1 = GA.par[1]; A.p2 = GA.par[2];
+        A.verts = M.verts + GA.vert_off; A.nverts = GA.vert_cnt;
+        A.cell_off = GA.map_off >= 0 ? M.sup_cells + GA.map_off : nullptr; A.cell_list = M.sup_lists + GA.list_off;
+        B.shape = GB.shape; B.p0 = GB.par[0]; B.p1 = GB.par[1]; B.p2 = GB.par[2];
+        B.verts = M.verts + GB.vert_off; B.nverts = GB.vert_cnt;
+        B.cell_off = GB.map_off >= 0 ? M.sup_cells + GB.map_off : nullptr; B.cell_list = M.sup_lists + GB.list_off;
+        const uint32_t idx = local * 32u + lane;
+        const int64_t slot = (int64_t)p * bins.cap + idx;
+        const int32_t g = idx < cnt ? bins.group[slot] : 0;
+        bool parked = idx < cnt && g >= 0 && (g & SR_PARKED);
+        const int32_t group = g & ~SR_PARKED;
+        if (parked && MODE == MODE_BOOL && out.hit[group]) parked = false;   // decided meanwhile
+        float T[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) T[k] = parked ? bins.T[k * stride + slot] : 0.f;
+        bool maybe = false;
+        if (parked) {
+            maybe = may_be_enclosed(fl, GA, GB, A, B, T, padding);
+            if (!maybe) commit(p, group, slot, false, 0.f);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, maybe);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            float Ts[12];
+#pragma unroll
+            for (int k = 0; k < 12; k++) Ts[k] = __shfl_sync(0xffffffffu, T[k], src);
+            const int32_t gs = __shfl_sync(0xffffffffu, group, src);
+            if (MODE == MODE_BOOL && out.hit[gs]) continue;   // warp-uniform
+            float gap = 0.f;
+            const bool enclosed = surface_enclosed(M, fl, pr.a, pr.b, A, B, GA.core_radius, GB.core_radius, Ts, padding, (int)lane, 32, &gap);
+            if (lane == 0) commit(p, gs, (int64_t)p * bins.cap + local * 32u + src, enclosed, gap);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Small batches: one fused kernel, one thread per (pair, state)
 // ------------------------------------------------------------------------------------------
 // The three-kernel pipeline is built for throughput; a single state or a single edge (the calls of a
@@ -1032,7 +1234,10 @@ k_small_check(DevModel M, StateSource src, int64_t n_states, float padding, Outp
     B.cell_off = GB.map_off >= 0 ? M.sup_cells + GB.map_off : nullptr; B.cell_list = M.sup_lists + GB.list_off;
     const float margin = padding + GA.core_radius + GB.core_radius;
     const GjkOut r = gjk_run<false>(A, B, R, gjk_start_direction(GA, GB, R), margin, 0.f);
-    if (r.hit) out.hit[group] = 1;
+    if (!r.hit) return;
+    if (M.surface && M.pair_enclose[p] && may_be_enclosed(M.pair_enclose[p], GA, GB, A, B, R, padding) && surface_enclosed(M, M.pair_enclose[p], pr.a, pr.b, A, B, GA.core_radius, GB.core_radius, R, padding, 0, 1))
+        return;   // one shape wholly inside the other's surface: free in the reference's semantics
+    out.hit[group] = 1;
 }
 
 // ------------------------------------------------------------------------------------------

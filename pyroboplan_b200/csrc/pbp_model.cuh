@@ -121,6 +121,14 @@ struct DevModel {
     const float *q_lower, *q_upper;
     const int32_t *frame_parent;
     const float *frame_placement;
+    // surface semantics of mesh geometries (pbp_model_desc.planes ...): hull face planes
+    // (n.x <= w inside), per geometry (first plane, count), dent depth, per INTERNAL pair the
+    // enclosure flags (bit 0: b could lie inside a's surface, bit 1: a inside b's); surface = any flag set
+    const float4 *planes;
+    const int2 *plane_idx;
+    const float *surface_tol;
+    const uint8_t *pair_enclose;
+    int32_t surface;
 };
 
 // ------------------------------------------------------------------------------------------

@@ -82,6 +82,12 @@ class _ModelDesc(ctypes.Structure):
         ("q_lower_f64", ctypes.c_void_p),
         ("q_upper_f64", ctypes.c_void_p),
         ("geom_capsule", ctypes.c_void_p),
+        ("planes", ctypes.c_void_p),
+        ("geom_plane_off", ctypes.c_void_p),
+        ("geom_plane_cnt", ctypes.c_void_p),
+        ("geom_surface_tol", ctypes.c_void_p),
+        ("pair_enclose", ctypes.c_void_p),
+        ("nplanes", ctypes.c_int32),
     ]
 
 
@@ -176,11 +182,48 @@ def _up32(x):
     return y if float(y) >= x else np.nextafter(y, np.float32(np.inf))
 
 
-def flatten_model(model, collision_model):
+def _shape_volume(s):
+    if isinstance(s, Sphere):
+        return 4.0 / 3.0 * np.pi * s.radius ** 3
+    if isinstance(s, Box):
+        return float(8.0 * np.prod(s.halfSide))
+    if isinstance(s, Cylinder):
+        return np.pi * s.radius ** 2 * 2.0 * s.halfLength
+    if isinstance(s, Capsule):
+        return np.pi * s.radius ** 2 * 2.0 * s.halfLength + 4.0 / 3.0 * np.pi * s.radius ** 3
+    return float(s.volume)
+
+
+def _could_enclose(outer, inner):
+    """Necessary conditions for ``inner`` to fit inside ``outer`` in SOME relative placement: inclusion
+    is monotone in the inscribed radius, the enclosing radius and the volume.  (Conservative: a
+    pair flagged needlessly only costs its hull hits an enclosure test.)"""
+    return (inner.inner_sphere()[1] <= outer.inner_sphere()[1] and inner.bounding_sphere()[1] <= outer.bounding_sphere()[1]
+            and _shape_volume(inner) <= _shape_volume(outer))
+
+
+def mesh_dent_depth(s):
+    """How far the surface of a mesh lies below the surface of its convex hull (metres): the deepest
+    sample of the mesh triangles' edges and centroids under the hull's face planes."""
+    v = np.asarray(s.mesh_vertices, dtype=np.float64)[np.asarray(s.mesh_triangles)]          # [T, 3, 3]
+    t = np.linspace(0.0, 1.0, 9)[1:-1]
+    samples = [v.mean(axis=1)]
+    for i, j in ((0, 1), (1, 2), (2, 0)):
+        samples.append((v[:, i, None, :] * (1 - t)[None, :, None] + v[:, j, None, :] * t[None, :, None]).reshape(-1, 3))
+    x = np.concatenate(samples)
+    depth = (-(x @ s.planes[:, :3].T + s.planes[:, 3])).min(axis=1)                        # distance to the nearest face plane
+    return float(max(depth.max(), 0.0))
+
+
+def flatten_model(model, collision_model, mesh_semantics="surface"):
     """Host containers -> dict of contiguous float32 / int32 arrays matching ``pbp_model_desc``.
 
     ``geom_outer`` / ``geom_inner`` share one centre per geometry (the enclosing sphere's); radii
     are rounded outwards / inwards so the float32 broadphase stays conservative.
+
+    ``mesh_semantics``: "surface" (default) treats geometries that came from a mesh file (they carry
+    ``mesh_triangles``) as the reference does -- Pinocchio's BVHModel is the SURFACE, so a shape wholly
+    inside the mesh does not collide with it --; "hull" treats them as convex solids.
     """
     geoms = collision_model.geometryObjects
     ng = len(geoms)
@@ -250,6 +293,27 @@ def flatten_model(model, collision_model):
     a["verts"] = np.concatenate(verts).astype(np.float32) if verts else np.zeros((1, 3), dtype=np.float32)
     pairs = np.array([[p.first, p.second] for p in collision_model.collisionPairs], dtype=np.int32).reshape(-1, 2)
     a["pairs"] = pairs if len(pairs) else np.zeros((1, 2), dtype=np.int32)
+    # surface semantics of mesh geometries: hull face planes, dent depth, pairs where one shape could
+    # lie wholly inside the other's surface
+    if mesh_semantics not in ("surface", "hull"):
+        raise ValueError("mesh_semantics must be 'surface' or 'hull'")
+    surface = [mesh_semantics == "surface" and isinstance(g.geometry, Convex) and g.geometry.mesh_triangles is not None for g in geoms]
+    planes, plane_off, plane_cnt, tol = [], np.zeros(ng, np.int32), np.zeros(ng, np.int32), np.zeros(ng, np.float32)
+    for i, g in enumerate(geoms):
+        plane_off[i] = sum(len(x) for x in planes)
+        if surface[i]:
+            pl = g.geometry.planes
+            planes.append(np.concatenate([pl[:, :3], -pl[:, 3:4]], axis=1))
+            plane_cnt[i] = len(pl)
+            tol[i] = mesh_dent_depth(g.geometry)
+    enclose = np.zeros(max(len(pairs), 1), np.uint8)
+    for k, (ga, gb) in enumerate(pairs):
+        if surface[ga] and _could_enclose(geoms[ga].geometry, geoms[gb].geometry):
+            enclose[k] |= 1
+        if surface[gb] and _could_enclose(geoms[gb].geometry, geoms[ga].geometry):
+            enclose[k] |= 2
+    a["planes"] = np.concatenate(planes).astype(np.float32) if planes else np.zeros((1, 4), dtype=np.float32)
+    a["geom_plane_off"], a["geom_plane_cnt"], a["geom_surface_tol"], a["pair_enclose"] = plane_off, plane_cnt, tol, enclose
     a["frame_parent"] = np.array([f.parentJoint for f in model.frames], dtype=np.int32)
     a["frame_placement"] = np.array([_se3_row(f.placement) for f in model.frames], dtype=np.float32)
     # float64 kinematic tables for the FP64 differential-IK kernel
@@ -258,7 +322,8 @@ def flatten_model(model, collision_model):
     a["frame_placement_f64"] = np.array([_se3_row(f.placement) for f in model.frames], dtype=np.float64)
     a["q_lower_f64"] = np.asarray(model.lowerPositionLimit, dtype=np.float64)
     a["q_upper_f64"] = np.asarray(model.upperPositionLimit, dtype=np.float64)
-    sizes = dict(nq=model.nq, njoints=model.njoints, ngeoms=ng, npairs=len(pairs), nverts=nv, nframes=len(model.frames))
+    sizes = dict(nq=model.nq, njoints=model.njoints, ngeoms=ng, npairs=len(pairs), nverts=nv, nframes=len(model.frames),
+                 nplanes=int(plane_cnt.sum()))
     return {k: np.ascontiguousarray(v) for k, v in a.items()}, sizes
 
 
@@ -304,7 +369,7 @@ def _torch():
 class CollisionEngine:
     """Device-resident compiled (model, collision_model) + batched hot-path operations."""
 
-    def __init__(self, model, collision_model, device=None, max_chunk_states=0):
+    def __init__(self, model, collision_model, device=None, max_chunk_states=0, mesh_semantics="surface"):
         self.lib = load_library()
         torch = _torch()
         if not torch.cuda.is_available():
@@ -313,10 +378,13 @@ class CollisionEngine:
             device = torch.cuda.current_device()
         self.device = int(torch.device("cuda", device).index if not isinstance(device, int) else device)
         self.torch_device = torch.device("cuda", self.device)
-        arrays, sizes = flatten_model(model, collision_model)
+        arrays, sizes = flatten_model(model, collision_model, mesh_semantics)
         self._arrays = arrays
+        self.mesh_semantics = mesh_semantics
         self.nq, self.njoints, self.ngeoms = sizes["nq"], sizes["njoints"], sizes["ngeoms"]
         self.npairs, self.nframes = sizes["npairs"], sizes["nframes"]
+        if sizes["nplanes"] == 0:   # no surface geometry: the optional tables stay NULL
+            arrays = {k: v for k, v in arrays.items() if k not in ("planes", "geom_plane_off", "geom_plane_cnt", "geom_surface_tol", "pair_enclose")}
         desc = _ModelDesc()
         for k, v in sizes.items():
             setattr(desc, k, v)

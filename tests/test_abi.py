@@ -77,7 +77,7 @@ def test_flatten_model_is_conservative():
 
     model, cmodel, _ = make_panda()
     arrays, sizes = eng_mod.flatten_model(model, cmodel)
-    assert sizes == dict(nq=9, njoints=10, ngeoms=16, npairs=74, nverts=1204, nframes=model.nframes)
+    assert sizes == dict(nq=9, njoints=10, ngeoms=16, npairs=74, nverts=1204, nframes=model.nframes, nplanes=2364)
     for g, obj in enumerate(cmodel.geometryObjects):
         s = obj.geometry
         oc, orad = arrays["geom_outer"][g][:3].astype(np.float64), float(arrays["geom_outer"][g][3])

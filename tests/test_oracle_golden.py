@@ -293,3 +293,74 @@ def test_penetration_depth_from_a_planar_gjk_simplex():
             assert ds == pytest.approx(-(min(R - rho, hl - abs(c[2])) + r), abs=1e-4)   # 320-vertex polytope on a curved support
             inside += 1
     assert inside > 20
+
+
+# ------------------------------------------------------------------ surface (triangle-soup) semantics
+def _tri_dist_sampled(a, b, n=60):
+    """Brute-force lower-resolution check: minimum distance between dense barycentric samples."""
+    u = np.linspace(0.0, 1.0, n)
+    w = np.array([(x, y, 1.0 - x - y) for x in u for y in u if x + y <= 1.0 + 1e-12])
+    pa, pb = w @ a, w @ b
+    return np.sqrt(((pa[:, None, :] - pb[None, :, :]) ** 2).sum(axis=2).min())
+
+
+def test_triangle_distance_known_answers(panda_full):
+    """The oracle's exact triangle-triangle distance (the kernel of the surface semantics): analytic cases
+    and a sampled cross-check on random triangles."""
+    model, cmodel = panda_full[0], panda_full[1]
+    orc = Oracle(model, cmodel)
+    eye = np.tile(np.concatenate([np.eye(3).reshape(9), np.zeros(3)]), (len(cmodel.geometryObjects), 1))
+
+    def dist(a, b):
+        orc._tris = np.ascontiguousarray(np.stack([np.asarray(a, float).reshape(9), np.asarray(b, float).reshape(9)]))
+        orc._tri_off, orc._tri_cnt = np.zeros(len(eye), np.int32), np.zeros(len(eye), np.int32)
+        orc._tri_off[1], orc._tri_cnt[0], orc._tri_cnt[1] = 1, 1, 1
+        return orc.soup_pair_distance(eye, 0, 1, brute=True)
+
+    base = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], float)
+    assert dist(base, base + [0, 0, 0.25]) == pytest.approx(0.25)                       # parallel faces
+    assert dist(base, base + [2.0, 0, 0]) == pytest.approx(1.0)                         # vertex - vertex
+    assert dist(base, np.array([[0.2, 0.2, -1], [0.2, 0.2, 1], [5, 5, 1]], float)) == 0.0   # an edge pierces the face
+    assert dist(base, np.array([[0.2, 0.2, 0.5], [0.3, 0.2, 1], [0.2, 0.3, 1]], float)) == pytest.approx(0.5)   # vertex - face
+    assert dist(base, np.array([[0.5, -1, 0.3], [0.5, 2, 0.3], [0.5, 0.5, 4]], float)) == pytest.approx(0.3)    # edge - face interior / edge
+    assert dist(base, base * 0.5 + [0.1, 0.1, 0.0]) == 0.0                              # coplanar, overlapping
+    rng = np.random.default_rng(5)
+    for _ in range(60):
+        a, b = rng.normal(size=(3, 3)), rng.normal(size=(3, 3)) + rng.normal(size=3)
+        d = dist(a, b)
+        s = _tri_dist_sampled(a, b)
+        assert d <= s + 1e-12 and s - d < 0.06          # the samples can only overestimate, by about one sample spacing
+
+
+def test_surface_semantics_differ_from_hulls_by_enclosure(panda_full):
+    """Pinocchio's meshes are surfaces (coal BVHModel): a finger wholly inside link 5 / 0 / 1 / 2 -- the hand
+    pair is disabled by the SRDF -- is free for the reference and a collision for convex hulls.  The
+    oracle's surface mode must (1) never report a hit the hulls do not, (2) agree with brute force over
+    all triangle pairs, (3) flip about 1 in 1000 uniform states, all of them through deeply overlapping
+    hulls (enclosure), not through the sub-millimetre dents."""
+    model, cmodel = panda_full[0], panda_full[1]
+    surf, hull = Oracle(model, cmodel), Oracle(model, cmodel, mesh_semantics="hull")
+    assert surf.mesh_semantics == "surface" and hull.mesh_semantics == "hull"
+    q = uniform_states(model, 60000, 0).astype(np.float64)
+    hs = surf.check_states(q)[0].astype(bool)
+    hh = hull.check_states(q)[0].astype(bool)
+    assert not (hs & ~hh).any()
+    flipped = np.nonzero(hh & ~hs)[0]
+    assert 20 <= len(flipped) <= 120
+    geoms = cmodel.geometryObjects
+    for i in flipped[:25]:
+        _, oMg = surf.fk(q[i])
+        deep = 0
+        for p in cmodel.collisionPairs:
+            if hull.pair_distance_placed(oMg, p.first, p.second)[0] > 0.0:
+                continue
+            exact = surf.soup_pair_distance(oMg, p.first, p.second, brute=True)
+            assert exact > 0.0                                        # no surface contact on any pair
+            assert surf.soup_pair_distance(oMg, p.first, p.second) == pytest.approx(exact, abs=1e-12)      # box rejection is exact
+            if hull.pair_signed_distance_placed(oMg, p.first, p.second)[0] < -5e-3:
+                deep += 1
+                assert "finger" in geoms[p.second].name or "link7" in geoms[p.second].name
+        assert deep >= 1
+    # min distance in surface mode: the clearance of the enclosed shape, positive
+    md = surf.check_states(q[flipped[:25]], want_all=True, use_cull=False)[1]
+    assert (md > 0).all()
