@@ -100,6 +100,9 @@ struct pbp_engine {
     DevModel dm{};
     DeviceBuffer d_joints, d_jgeoms, d_geoms, d_bpgeoms, d_bpboxes, d_bppairs, d_groups, d_pairorig, d_paths, d_pathops, d_order, d_verts, d_supcells, d_suplists, d_qlim, d_frames, d_planes, d_plane_idx, d_surf_tol, d_pair_enclose;
     bool surface = false;   // some pair carries an enclosure flag (surface semantics of mesh geometries)
+    bool sr_tables_in_smem = false;
+    size_t smem_sr = 0;
+    int sr_blocks = 1;
     // pipeline workspaces
     int64_t chunk = 0;  // states per broadphase/narrowphase round = bin capacity
     DeviceBuffer d_bin_state, d_bin_group, d_bin_sample, d_bin_T, d_ctrl;
@@ -252,8 +255,11 @@ int launch_round_kernels(pbp_engine *e, const StateSource &src, int64_t n, float
     LAUNCH_CHECK("k_narrowphase");
     if (e->surface) {
         // hull hits of pairs with an enclosure flag were parked by the narrowphase: decide them
-        const unsigned sr_grid = (unsigned)std::min<int64_t>(8 * (int64_t)e->num_sms, std::max<int64_t>(1, (max_items + 31) / 32 / (SR_THREADS / 32)));
-        k_surface_refine<MODE><<<sr_grid, SR_THREADS, 0, st>>>(e->dm, padding, out, bins, has_sample);
+        const unsigned sr_grid = (unsigned)std::min<int64_t>(e->sr_blocks, std::max<int64_t>(1, (max_items + 31) / 32 / (SR_THREADS / 32)));
+        if (e->sr_tables_in_smem)
+            k_surface_refine<MODE, true><<<sr_grid, SR_THREADS, e->smem_sr, st>>>(e->dm, padding, out, bins, has_sample);
+        else
+            k_surface_refine<MODE, false><<<sr_grid, SR_THREADS, 0, st>>>(e->dm, padding, out, bins, has_sample);
         LAUNCH_CHECK("k_surface_refine");
     }
     return 0;
@@ -787,6 +793,7 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
         e->dm.surface_tol = e->d_surf_tol.as<float>();
         e->dm.pair_enclose = e->d_pair_enclose.as<uint8_t>();
         e->dm.surface = e->surface ? 1 : 0;
+        e->dm.nplanes = (int)(pl.size() / 4);
     }
     e->dm.q_lower = e->d_qlim.as<float>();
     e->dm.q_upper = e->d_qlim.as<float>() + d->nq;
@@ -827,7 +834,18 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     SET_SMEM((k_narrowphase<MODE_BOOL_ALL, false>));
     SET_SMEM((k_narrowphase<MODE_DIST, false>));
     SET_SMEM(k_fk_output);
+    SET_SMEM((k_surface_refine<MODE_BOOL, true>));
+    SET_SMEM((k_surface_refine<MODE_BOOL_ALL, true>));
+    SET_SMEM((k_surface_refine<MODE_DIST, true>));
 #undef SET_SMEM
+    e->smem_sr = vert_bytes + align16((size_t)e->dm.nplanes * sizeof(float4));
+    e->sr_tables_in_smem = e->smem_sr <= max_optin;   // one 16-warp block per SM is enough for this kernel
+    {
+        int occ_sr = 1;
+        if (e->sr_tables_in_smem) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sr, k_surface_refine<MODE_BOOL, true>, SR_THREADS, e->smem_sr));
+        else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sr, k_surface_refine<MODE_BOOL, false>, SR_THREADS, 0));
+        e->sr_blocks = e->num_sms * std::max(occ_sr, 1);
+    }
     // (this kernel also has a few static __shared__ words: leave room for them under the opt-in cap)
 #define SET_SMEM_POOL(kern) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_optin - 1024))
     SET_SMEM_POOL((k_narrowphase_pool<MODE_BOOL>));

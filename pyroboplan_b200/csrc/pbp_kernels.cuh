@@ -412,6 +412,9 @@ __device__ __forceinline__ bool next_tile(uint32_t *tile_counter, const uint32_t
 // out on the side its centre is displaced to) and both directions of the inner shape's long axis
 // (a finger half inside a link pokes out with one end).  Two support evaluations per direction, on
 // the lane that found the hit; only the items no direction settles are parked for the plane test.
+#ifndef PBP_SR_AXIS_DIRS
+#define PBP_SR_AXIS_DIRS 0   // measured on config 2: the centre line settles 73 % of the flagged hull hits, the axis directions 1 % more
+#endif
 __device__ __forceinline__ float support_value(const ShapeRef &S, float3 d, float radius, float len) {
     const float3 sl = support_local(S, d);
     return dot3(d, sl) + radius * len;
@@ -433,7 +436,7 @@ __device__ __noinline__ bool may_be_enclosed(int fl, const DevGeom &GA, const De
         const float3 u = sub3(p1, p0);
         bool out = false;
 #pragma unroll 1
-        for (int k = 0; k < (GB.has_axis ? 3 : 1) && !out; k++) {
+        for (int k = 0; k < (PBP_SR_AXIS_DIRS && GB.has_axis ? 3 : 1) && !out; k++) {
             const float3 dir = k == 0 ? d : (k == 1 ? u : make_float3(-u.x, -u.y, -u.z));
             const float len = sqrtf(dot3(dir, dir));
             out = support_value_placed(B, T, dir, GB.core_radius, len) + padding * len >= support_value(A, dir, GA.core_radius, len);
@@ -444,7 +447,7 @@ __device__ __noinline__ bool may_be_enclosed(int fl, const DevGeom &GA, const De
         const float3 u = make_float3(GA.axis1[0] - GA.axis0[0], GA.axis1[1] - GA.axis0[1], GA.axis1[2] - GA.axis0[2]);
         bool out = false;
 #pragma unroll 1
-        for (int k = 0; k < (GA.has_axis ? 3 : 1) && !out; k++) {
+        for (int k = 0; k < (PBP_SR_AXIS_DIRS && GA.has_axis ? 3 : 1) && !out; k++) {
             const float3 dir = k == 0 ? make_float3(-d.x, -d.y, -d.z) : (k == 1 ? u : make_float3(-u.x, -u.y, -u.z));
             const float len = sqrtf(dot3(dir, dir));
             out = support_value(A, dir, GA.core_radius, len) + padding * len >= support_value_placed(B, T, dir, GB.core_radius, len);
@@ -1017,14 +1020,14 @@ k_narrowphase_pool(DevModel M, float padding, Outputs out, Bins bins, uint32_t *
 // a few states in a million -- tools/soup_study.py, tools/gpu_surface_check.py.)  The faces are split over `nlanes` cooperating lanes; the caller
 // reduces with a warp maximum when nlanes > 1.
 //   T: placement of `inner` in the frame of the geometry `g_outer`; returns max_f (h_inner(n_f) - w_f).
-__device__ __forceinline__ float enclosure_excess(const DevModel &M, int g_outer, const ShapeRef &inner, float inner_radius, const float *T,
-                                                  float padding, int lane, int nlanes) {
+__device__ __forceinline__ float enclosure_excess(const DevModel &M, const float4 *planes, int g_outer, const ShapeRef &inner, float inner_radius,
+                                                  const float *T, float padding, int lane, int nlanes) {
     const int2 pi = M.plane_idx[g_outer];
     float worst = -FLT_MAX;
     for (int f0 = 0; f0 < pi.y; f0 += nlanes) {
         const int f = f0 + lane;
         if (f < pi.y) {
-            const float4 pl = __ldg(M.planes + pi.x + f);
+            const float4 pl = planes[pi.x + f];
             const float3 dl = make_float3(fmaf(T[0], pl.x, fmaf(T[3], pl.y, T[6] * pl.z)), fmaf(T[1], pl.x, fmaf(T[4], pl.y, T[7] * pl.z)),
                                           fmaf(T[2], pl.x, fmaf(T[5], pl.y, T[8] * pl.z)));
             const float3 sl = support_local(inner, dl);
@@ -1041,10 +1044,11 @@ __device__ __forceinline__ float enclosure_excess(const DevModel &M, int g_outer
 
 // flags bit 0: b could lie inside a's surface; bit 1: a inside b's.  T: placement of b in a's frame.
 // gap_out (optional): the clearance of the enclosed shape to the enclosing hull.
-__device__ __forceinline__ bool surface_enclosed(const DevModel &M, int flags, int ga, int gb, const ShapeRef &A, const ShapeRef &B, float ra,
-                                                 float rb, const float *T, float padding, int lane, int nlanes, float *gap_out = nullptr) {
+__device__ __forceinline__ bool surface_enclosed(const DevModel &M, const float4 *planes, int flags, int ga, int gb, const ShapeRef &A,
+                                                 const ShapeRef &B, float ra, float rb, const float *T, float padding, int lane, int nlanes,
+                                                 float *gap_out = nullptr) {
     if (flags & 1) {
-        float ex = enclosure_excess(M, ga, B, rb, T, padding, lane, nlanes);
+        float ex = enclosure_excess(M, planes, ga, B, rb, T, padding, lane, nlanes);
         if (nlanes > 1) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ex = fmaxf(ex, __shfl_xor_sync(0xffffffffu, ex, o));
@@ -1058,7 +1062,7 @@ __device__ __forceinline__ bool surface_enclosed(const DevModel &M, int flags, i
             Ti[3 * i + 0] = T[i]; Ti[3 * i + 1] = T[3 + i]; Ti[3 * i + 2] = T[6 + i];
             Ti[9 + i] = -(T[i] * T[9] + T[3 + i] * T[10] + T[6 + i] * T[11]);
         }
-        float ex = enclosure_excess(M, gb, A, ra, Ti, padding, lane, nlanes);
+        float ex = enclosure_excess(M, planes, gb, A, ra, Ti, padding, lane, nlanes);
         if (nlanes > 1) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ex = fmaxf(ex, __shfl_xor_sync(0xffffffffu, ex, o));
@@ -1073,11 +1077,30 @@ __device__ __forceinline__ bool surface_enclosed(const DevModel &M, int flags, i
 // are cut into chunks of 32 items, the chunks dealt round-robin to the warps.  Pass 1, one item per
 // lane: may_be_enclosed() -- a direction in which the would-be inner shape pokes out publishes the
 // hit.  Pass 2, one item per warp: the face planes of the enclosing hull split over the 32 lanes.
-constexpr int SR_THREADS = 128;
+// The hull tables and planes are staged in shared memory when they fit (every support evaluation is a
+// chain of dependent table reads).
+constexpr int SR_THREADS = 512;
 
-template <int MODE>
+template <int MODE, bool TABLES_IN_SMEM>
 __global__ void __launch_bounds__(SR_THREADS)
 k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, bool has_sample) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char *ptr = smem_raw;
+    float4 *sv = reinterpret_cast<float4 *>(ptr);        ptr += TABLES_IN_SMEM ? align16((size_t)M.nverts_padded * sizeof(float4)) : 0;
+    float4 *spl = reinterpret_cast<float4 *>(ptr);       ptr += TABLES_IN_SMEM ? align16((size_t)M.nplanes * sizeof(float4)) : 0;
+    uint16_t *scell = reinterpret_cast<uint16_t *>(ptr); ptr += TABLES_IN_SMEM ? align16((size_t)M.n_sup_cells * 2) : 0;
+    uint16_t *slist = reinterpret_cast<uint16_t *>(ptr); ptr += TABLES_IN_SMEM ? align16((size_t)M.n_sup_lists * 2) : 0;
+    if (TABLES_IN_SMEM) {
+        stage_words(sv, M.verts, M.nverts_padded * (int)sizeof(float4));
+        stage_words(spl, M.planes, M.nplanes * (int)sizeof(float4));
+        stage_words(scell, M.sup_cells, M.n_sup_cells * 2);
+        stage_words(slist, M.sup_lists, M.n_sup_lists * 2);
+        __syncthreads();
+    }
+    const float4 *verts = TABLES_IN_SMEM ? sv : M.verts;
+    const float4 *planes = TABLES_IN_SMEM ? spl : M.planes;
+    const uint16_t *cells = TABLES_IN_SMEM ? scell : M.sup_cells;
+    const uint16_t *lists = TABLES_IN_SMEM ? slist : M.sup_lists;
     const unsigned lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * SR_THREADS + threadIdx.x) >> 5, nwarps = gridDim.x * (SR_THREADS / 32);
     const int64_t stride = (int64_t)M.npairs * bins.cap;
@@ -1111,11 +1134,11 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, bool has_sam
         const DevGeom &GB = M.geoms[pr.b];
         ShapeRef A, B;
         A.shape = GA.shape; A.p0 = GA.par[0]; A.p1 = GA.par[1]; A.p2 = GA.par[2];
-        A.verts = M.verts + GA.vert_off; A.nverts = GA.vert_cnt;
-        A.cell_off = GA.map_off >= 0 ? M.sup_cells + GA.map_off : nullptr; A.cell_list = M.sup_lists + GA.list_off;
+        A.verts = verts + GA.vert_off; A.nverts = GA.vert_cnt;
+        A.cell_off = GA.map_off >= 0 ? cells + GA.map_off : nullptr; A.cell_list = lists + GA.list_off;
         B.shape = GB.shape; B.p0 = GB.par[0]; B.p1 = GB.par[1]; B.p2 = GB.par[2];
-        B.verts = M.verts + GB.vert_off; B.nverts = GB.vert_cnt;
-        B.cell_off = GB.map_off >= 0 ? M.sup_cells + GB.map_off : nullptr; B.cell_list = M.sup_lists + GB.list_off;
+        B.verts = verts + GB.vert_off; B.nverts = GB.vert_cnt;
+        B.cell_off = GB.map_off >= 0 ? cells + GB.map_off : nullptr; B.cell_list = lists + GB.list_off;
         const uint32_t idx = local * 32u + lane;
         const int64_t slot = (int64_t)p * bins.cap + idx;
         const int32_t g = idx < cnt ? bins.group[slot] : 0;
@@ -1140,7 +1163,7 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, bool has_sam
             const int32_t gs = __shfl_sync(0xffffffffu, group, src);
             if (MODE == MODE_BOOL && out.hit[gs]) continue;   // warp-uniform
             float gap = 0.f;
-            const bool enclosed = surface_enclosed(M, fl, pr.a, pr.b, A, B, GA.core_radius, GB.core_radius, Ts, padding, (int)lane, 32, &gap);
+            const bool enclosed = surface_enclosed(M, planes, fl, pr.a, pr.b, A, B, GA.core_radius, GB.core_radius, Ts, padding, (int)lane, 32, &gap);
             if (lane == 0) commit(p, gs, (int64_t)p * bins.cap + local * 32u + src, enclosed, gap);
         }
     }
@@ -1235,7 +1258,7 @@ k_small_check(DevModel M, StateSource src, int64_t n_states, float padding, Outp
     const float margin = padding + GA.core_radius + GB.core_radius;
     const GjkOut r = gjk_run<false>(A, B, R, gjk_start_direction(GA, GB, R), margin, 0.f);
     if (!r.hit) return;
-    if (M.surface && M.pair_enclose[p] && may_be_enclosed(M.pair_enclose[p], GA, GB, A, B, R, padding) && surface_enclosed(M, M.pair_enclose[p], pr.a, pr.b, A, B, GA.core_radius, GB.core_radius, R, padding, 0, 1))
+    if (M.surface && M.pair_enclose[p] && may_be_enclosed(M.pair_enclose[p], GA, GB, A, B, R, padding) && surface_enclosed(M, M.planes, M.pair_enclose[p], pr.a, pr.b, A, B, GA.core_radius, GB.core_radius, R, padding, 0, 1))
         return;   // one shape wholly inside the other's surface: free in the reference's semantics
     out.hit[group] = 1;
 }

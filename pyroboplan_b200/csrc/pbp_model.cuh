@@ -128,7 +128,7 @@ struct DevModel {
     const int2 *plane_idx;
     const float *surface_tol;
     const uint8_t *pair_enclose;
-    int32_t surface;
+    int32_t surface, nplanes;
 };
 
 // ------------------------------------------------------------------------------------------
