@@ -308,7 +308,8 @@ def main():
     kernel_ms = max(np_ms, bp_ms)
     f_dom = F_KERNEL[dominant]
     achieved_tflops = f_dom * states_per_launch / (kernel_ms * 1e-3) / 1e12
-    step_kernel_ms = bp_ms + np_ms + prof["item_setup_ms"] / rounds
+    sr_ms = prof.get("surface_refine_ms", 0.0) / rounds
+    step_kernel_ms = bp_ms + np_ms + prof["item_setup_ms"] / rounds + sr_ms
     step_tflops = F_ALG_FLOP_PER_CONFIG * states_per_launch / (step_kernel_ms * 1e-3) / 1e12
     hbm_gbs = HBM_BYTES_PER_CONFIG * states_per_launch / (step_kernel_ms * 1e-3) / 1e9
     roofline = {
@@ -324,7 +325,7 @@ def main():
                 "ALGORITHMIC flops frozen from the oracle's counters (full hull scans, DESIGN.md 5); the kernels execute fewer "
                 "(exact support maps scan ~3 of ~150 vertices), so the executed-instruction view is in `ncu`",
         "ncu": NCU,
-        "kernel_ms": {"k_broadphase": bp_ms, "k_item_setup": prof["item_setup_ms"] / rounds, "k_narrowphase": np_ms},
+        "kernel_ms": {"k_broadphase": bp_ms, "k_item_setup": prof["item_setup_ms"] / rounds, "k_narrowphase": np_ms, "k_surface_refine": sr_ms},
         "states_per_launch": states_per_launch,
         "narrowphase_items_per_state": prof["narrowphase_items"] / max(n * args.steps, 1),
         "flop_per_config": F_KERNEL,

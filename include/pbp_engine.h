@@ -136,6 +136,7 @@ typedef struct {
     double narrowphase_ms;     /* sum of k_narrowphase launch durations */
     int64_t rounds;            /* broadphase + narrowphase rounds timed */
     int64_t narrowphase_items; /* (state, pair) items that reached GJK */
+    double surface_refine_ms;  /* sum of k_surface_refine launch durations (0 without surface semantics) */
 } pbp_profile;
 int pbp_set_profiling(pbp_engine *e, int enabled);
 /* Synchronises the recorded events, accumulates, returns totals since the last reset. */

@@ -447,14 +447,28 @@ double oracle_soup_pair_distance(const oracle_model *m, const double *oMg, int g
  * surface triangles: a surface lies inside its hull, so the hull distance is a lower bound and only
  * a pair whose hulls are within `padding` needs the triangle test; its result (stopped at the first
  * triangle pair within padding) replaces the hull distance. */
+static double soup_pair_distance_from(const oracle_model *m, const double *oMg, int ga, int gb, const double *triA, int ntA,
+                                      const double *triB, int ntB, double stop_at, int mode, double best0);
+
+static int pair_has_surface(const oracle_model *m, int ga, int gb) { return m->tris && (m->tri_cnt[ga] > 0 || m->tri_cnt[gb] > 0); }
+
+/* *is_exact (optional): 1 when the value returned is the distance under the model's semantics, 0 when
+ * it is the hull distance of a pair with a surface (a lower bound of its surface distance). */
 static double pair_distance_semantics(const oracle_model *m, const double *oMg, int ga, int gb, double padding, int want_exact,
-                                      oracle_counters *cnt) {
+                                      int *is_exact, oracle_counters *cnt) {
     double d = oracle_pair_distance(m, oMg, ga, gb, NULL, cnt);
-    if (d <= padding && m->tris && (m->tri_cnt[ga] > 0 || m->tri_cnt[gb] > 0))
+    if (is_exact) *is_exact = !pair_has_surface(m, ga, gb);
+    if (d <= padding && pair_has_surface(m, ga, gb)) {
         d = oracle_soup_pair_distance(m, oMg, ga, gb, m->tris + 9 * (int64_t)m->tri_off[ga], m->tri_cnt[ga],
                                       m->tris + 9 * (int64_t)m->tri_off[gb], m->tri_cnt[gb], padding, want_exact ? 0 : 2);
+        if (is_exact) *is_exact = 1;
+    }
     return d;
 }
+
+/* A mesh surface lies at most this far below its hull in any model the oracle is used on (Panda:
+ * 0.39 mm, pyroboplan_b200.engine.mesh_dent_depth; asserted in tests/test_oracle_golden.py). */
+#define ORACLE_MAX_DENT 1e-3
 
 int oracle_check_state(const oracle_model *m, const double *q, double padding, int want_all, int use_cull,
                        double *min_dist, int32_t *first_pair, double *oMi_scratch, double *oMg_scratch,
@@ -479,7 +493,7 @@ int oracle_check_state(const oracle_model *m, const double *q, double padding, i
             int ga = m->pairs[2 * k], gb = m->pairs[2 * k + 1];
             proxy_bounds(m, oMg_scratch, ga, gb, &lb, &ub);
             if (lb > padding + slack) { cnt->culled++; continue; }
-            double d = pair_distance_semantics(m, oMg_scratch, ga, gb, padding, 0, cnt);
+            double d = pair_distance_semantics(m, oMg_scratch, ga, gb, padding, 0, NULL, cnt);
             if (d < md) md = d;
             if (d <= padding) { hit = 1; fp = k; break; }
         }
@@ -487,17 +501,42 @@ int oracle_check_state(const oracle_model *m, const double *q, double padding, i
         if (first_pair) *first_pair = fp;
         return hit;
     }
+    /* With surfaces and a wanted minimum distance: a hull distance is only a lower bound of the
+     * pair's surface distance (by at most the dents of both meshes), so the pairs that could define
+     * the minimum are re-evaluated with the exact triangle distance afterwards. */
+    const int refine = min_dist != NULL && m->tris != NULL && want_all;
+    double *dk = NULL;
+    unsigned char *exact_k = NULL;
+    if (refine) {
+        dk = malloc(sizeof(double) * (size_t)(m->npairs > 0 ? m->npairs : 1));
+        exact_k = calloc((size_t)(m->npairs > 0 ? m->npairs : 1), 1);
+        for (int k = 0; k < m->npairs; k++) dk[k] = INFINITY;
+    }
     for (int k = 0; k < m->npairs; k++) {
         int ga = m->pairs[2 * k], gb = m->pairs[2 * k + 1];
         if (use_cull && !want_all && sphere_cull(m, oMg_scratch, ga, gb, padding)) { cnt->culled++; continue; }
-        if (use_cull && want_all && md < INFINITY && sphere_cull(m, oMg_scratch, ga, gb, md)) { cnt->culled++; continue; }
-        double d = pair_distance_semantics(m, oMg_scratch, ga, gb, padding, min_dist != NULL, cnt);
+        if (use_cull && want_all && md < INFINITY && sphere_cull(m, oMg_scratch, ga, gb, md + (refine ? 2.0 * ORACLE_MAX_DENT : 0.0))) { cnt->culled++; continue; }
+        int is_exact = 1;
+        double d = pair_distance_semantics(m, oMg_scratch, ga, gb, padding, min_dist != NULL, &is_exact, cnt);
+        if (refine) { dk[k] = d; exact_k[k] = (unsigned char)is_exact; }
         if (d < md) md = d;
         if (d <= padding) {
             if (fp < 0) fp = k;
             hit = 1;
             if (!want_all) break;
         }
+    }
+    if (refine) {
+        for (;;) {
+            int kb = -1;
+            for (int k = 0; k < m->npairs; k++) if (kb < 0 || dk[k] < dk[kb]) kb = k;
+            if (kb < 0 || exact_k[kb] || !isfinite(dk[kb])) { if (kb >= 0) md = dk[kb]; break; }
+            const int ga = m->pairs[2 * kb], gb = m->pairs[2 * kb + 1];
+            dk[kb] = soup_pair_distance_from(m, oMg_scratch, ga, gb, m->tris + 9 * (int64_t)m->tri_off[ga], m->tri_cnt[ga],
+                                             m->tris + 9 * (int64_t)m->tri_off[gb], m->tri_cnt[gb], -1.0, 0, dk[kb] + 2.0 * ORACLE_MAX_DENT);
+            exact_k[kb] = 1;
+        }
+        free(dk); free(exact_k);
     }
     if (min_dist) *min_dist = md;
     if (first_pair) *first_pair = fp;
@@ -1033,10 +1072,20 @@ static void tri_to_world(const double *T, const double *tri, double *out, double
  * same by brute force (the tests validate mode 0 with it); mode 2: verdict only -- triangles
  * farther than stop_at from the other mesh's box are never visited, and when nothing is within
  * stop_at the value returned is merely some number > stop_at. */
+static double soup_pair_distance_from(const oracle_model *m, const double *oMg, int ga, int gb, const double *triA, int ntA,
+                                      const double *triB, int ntB, double stop_at, int mode, double best0);
+
 double oracle_soup_pair_distance(const oracle_model *m, const double *oMg, int ga, int gb, const double *triA, int ntA,
                                  const double *triB, int ntB, double stop_at, int mode) {
+    return soup_pair_distance_from(m, oMg, ga, gb, triA, ntA, triB, ntB, stop_at, mode, INFINITY);
+}
+
+/* best0: a known upper bound of the result (INFINITY if none) -- triangle pairs farther apart than
+ * it are rejected by their boxes.  If nothing is closer than best0, best0 is returned. */
+static double soup_pair_distance_from(const oracle_model *m, const double *oMg, int ga, int gb, const double *triA, int ntA,
+                                      const double *triB, int ntB, double stop_at, int mode, double best0) {
     oracle_counters cnt = {0};
-    double best = INFINITY;
+    double best = best0;
     const int brute = mode == 1;
     if (stop_at < 0.0) stop_at = 0.0;
     if (ntA > 0 && ntB > 0) {
@@ -1080,7 +1129,7 @@ double oracle_soup_pair_distance(const oracle_model *m, const double *oMg, int g
                         if (WB[15 * j + 9 + k] < blo[k]) blo[k] = WB[15 * j + 9 + k];
                         if (WB[15 * j + 12 + k] > bhi[k]) bhi[k] = WB[15 * j + 12 + k];
                     }
-                best = INFINITY;
+                best = best0;
             }
         }
         const int verdict_only = mode == 2;

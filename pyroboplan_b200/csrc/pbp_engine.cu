@@ -142,7 +142,7 @@ struct pbp_engine {
     pbp_stats stats{};
     // optional per-kernel timing
     bool profiling = false;
-    std::vector<cudaEvent_t> prof_events;   // four per round: before broadphase / item setup / narrowphase, after
+    std::vector<cudaEvent_t> prof_events;   // five per round: before broadphase / item setup / narrowphase / surface refine, after
     std::vector<cudaEvent_t> prof_pool;     // recycled events
     pbp_profile prof{};
 };
@@ -253,10 +253,11 @@ int launch_round_kernels(pbp_engine *e, const StateSource &src, int64_t n, float
     else
         k_narrowphase<MODE, false><<<np_grid, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
     LAUNCH_CHECK("k_narrowphase");
+    if (ev) CUDA_TRY(cudaEventRecord(ev[3], st));
     if (e->surface) {
         // hull hits of pairs with an enclosure flag were parked by the narrowphase: decide them
         const unsigned sr_grid = (unsigned)std::min<int64_t>(e->sr_blocks, std::max<int64_t>(1, (max_items + 31) / 32 / (SR_THREADS / 32)));
-        if (e->sr_tables_in_smem)
+        if (e->sr_tables_in_smem && n >= 65536)   // staging the tables only pays when the blocks have many items
             k_surface_refine<MODE, true><<<sr_grid, SR_THREADS, e->smem_sr, st>>>(e->dm, padding, out, bins, has_sample);
         else
             k_surface_refine<MODE, false><<<sr_grid, SR_THREADS, 0, st>>>(e->dm, padding, out, bins, has_sample);
@@ -281,9 +282,9 @@ int run_round(pbp_engine *e, int mode, const StateSource &src, int64_t n, float 
     bins.cap = e->chunk;
     CUDA_TRY(cudaMemsetAsync(ctrl_base(e), 0, ctrl_words(e) * 4, st));
     int rc;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (e->profiling) {
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < 5; i++) {
             if (!e->prof_pool.empty()) { ev[i] = e->prof_pool.back(); e->prof_pool.pop_back(); }
             else CUDA_TRY(cudaEventCreate(&ev[i]));
         }
@@ -295,8 +296,8 @@ int run_round(pbp_engine *e, int mode, const StateSource &src, int64_t n, float 
     else rc = launch_round_kernels<MODE_DIST>(e, src, n, padding, out, bins, evp, st);
     if (rc) return rc;
     if (e->profiling) {
-        CUDA_TRY(cudaEventRecord(ev[3], st));
-        for (int i = 0; i < 4; i++) e->prof_events.push_back(ev[i]);
+        CUDA_TRY(cudaEventRecord(ev[4], st));
+        for (int i = 0; i < 5; i++) e->prof_events.push_back(ev[i]);
         k_sum_counts<<<1, 256, 0, st>>>(bins.count_np, e->npairs, ctrl_u64(e, 3));
         e->stats.kernel_launches++;
     }
@@ -598,17 +599,19 @@ int pbp_set_profiling(pbp_engine *e, int enabled) {
 int pbp_get_profile(pbp_engine *e, pbp_profile *out, int reset) {
     if (!e || !out) return fail(PBP_ERR_ARG, "NULL argument");
     CUDA_TRY(cudaSetDevice(e->device));
-    for (size_t i = 0; i + 3 < e->prof_events.size(); i += 4) {
-        float a = 0.f, b = 0.f, c = 0.f;
-        CUDA_TRY(cudaEventSynchronize(e->prof_events[i + 3]));
+    for (size_t i = 0; i + 4 < e->prof_events.size(); i += 5) {
+        float a = 0.f, b = 0.f, c = 0.f, r = 0.f;
+        CUDA_TRY(cudaEventSynchronize(e->prof_events[i + 4]));
         CUDA_TRY(cudaEventElapsedTime(&a, e->prof_events[i], e->prof_events[i + 1]));
         CUDA_TRY(cudaEventElapsedTime(&b, e->prof_events[i + 1], e->prof_events[i + 2]));
         CUDA_TRY(cudaEventElapsedTime(&c, e->prof_events[i + 2], e->prof_events[i + 3]));
+        CUDA_TRY(cudaEventElapsedTime(&r, e->prof_events[i + 3], e->prof_events[i + 4]));
         e->prof.broadphase_ms += a;
         e->prof.item_setup_ms += b;
         e->prof.narrowphase_ms += c;
+        e->prof.surface_refine_ms += r;
         e->prof.rounds++;
-        for (int k = 0; k < 4; k++) e->prof_pool.push_back(e->prof_events[i + k]);
+        for (int k = 0; k < 5; k++) e->prof_pool.push_back(e->prof_events[i + k]);
     }
     e->prof_events.clear();
     unsigned long long items = 0;
@@ -834,12 +837,15 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     SET_SMEM((k_narrowphase<MODE_BOOL_ALL, false>));
     SET_SMEM((k_narrowphase<MODE_DIST, false>));
     SET_SMEM(k_fk_output);
-    SET_SMEM((k_surface_refine<MODE_BOOL, true>));
-    SET_SMEM((k_surface_refine<MODE_BOOL_ALL, true>));
-    SET_SMEM((k_surface_refine<MODE_DIST, true>));
 #undef SET_SMEM
+    // (static __shared__ chunk directory: leave room for it under the opt-in cap)
+#define SET_SMEM_SR(kern) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_optin - 4096))
+    SET_SMEM_SR((k_surface_refine<MODE_BOOL, true>));
+    SET_SMEM_SR((k_surface_refine<MODE_BOOL_ALL, true>));
+    SET_SMEM_SR((k_surface_refine<MODE_DIST, true>));
+#undef SET_SMEM_SR
     e->smem_sr = vert_bytes + align16((size_t)e->dm.nplanes * sizeof(float4));
-    e->sr_tables_in_smem = e->smem_sr <= max_optin;   // one 16-warp block per SM is enough for this kernel
+    e->sr_tables_in_smem = e->smem_sr + 4096 <= max_optin;   // one 16-warp block per SM is enough for this kernel
     {
         int occ_sr = 1;
         if (e->sr_tables_in_smem) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sr, k_surface_refine<MODE_BOOL, true>, SR_THREADS, e->smem_sr));

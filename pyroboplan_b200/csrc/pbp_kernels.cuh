@@ -1080,6 +1080,7 @@ __device__ __forceinline__ bool surface_enclosed(const DevModel &M, const float4
 // The hull tables and planes are staged in shared memory when they fit (every support evaluation is a
 // chain of dependent table reads).
 constexpr int SR_THREADS = 512;
+constexpr int SR_DIR = 256;       // flagged pairs the chunk directory holds
 
 template <int MODE, bool TABLES_IN_SMEM>
 __global__ void __launch_bounds__(SR_THREADS)
@@ -1104,9 +1105,11 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, bool has_sam
     const unsigned lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * SR_THREADS + threadIdx.x) >> 5, nwarps = gridDim.x * (SR_THREADS / 32);
     const int64_t stride = (int64_t)M.npairs * bins.cap;
+    const float pad_test = MODE == MODE_DIST ? 0.f : padding;
     auto commit = [&](int p, int32_t group, int64_t slot, bool enclosed, float gap) {
         if (MODE == MODE_DIST) {
-            if (!enclosed) out.hit[group] = 1;
+            // the distance of an enclosed shape is its clearance, whatever the padding (pad_test = 0)
+            if (!enclosed || gap <= padding) out.hit[group] = 1;
             atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(enclosed ? gap : 0.f));
         } else if (!enclosed) {
             out.hit[group] = 1;
@@ -1116,15 +1119,47 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, bool has_sam
             }
         }
     };
+    // chunk directory: the flagged pairs and the running number of 32-item chunks before each
+    __shared__ int s_pair[SR_DIR];
+    __shared__ uint32_t s_first[SR_DIR + 1];
+    __shared__ int s_n;
+    if (threadIdx.x == 0) {
+        int nf = 0;
+        uint32_t acc = 0;
+        for (int k = 0; k < M.npairs && nf >= 0; k++) {
+            if (!M.pair_enclose[k]) continue;
+            if (nf == SR_DIR) { nf = -1; break; }   // directory full: every warp scans the pair list itself
+            s_pair[nf] = k;
+            s_first[nf] = acc;
+            acc += (bins.count_np[k] + 31u) >> 5;
+            nf++;
+        }
+        if (nf >= 0) s_first[nf] = acc;
+        s_n = nf;
+    }
+    __syncthreads();
     for (uint32_t c = warp;; c += nwarps) {
         // chunk c of the concatenated flagged bins
         int p = -1;
-        uint32_t local = 0, acc = 0;
-        for (int k = 0; k < M.npairs; k++) {
-            if (!M.pair_enclose[k]) continue;
-            const uint32_t nch = (bins.count_np[k] + 31u) >> 5;
-            if (c < acc + nch) { p = k; local = c - acc; break; }
-            acc += nch;
+        uint32_t local = 0;
+        if (s_n >= 0) {
+            if (c >= s_first[s_n]) break;
+            int lo = 0, hi = s_n;   // last entry with s_first[lo] <= c
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_first[mid] <= c) lo = mid; else hi = mid;
+            }
+            // (entries with an empty bin share their s_first with the next one: take the last of the run)
+            p = s_pair[lo];
+            local = c - s_first[lo];
+        } else {
+            uint32_t acc = 0;
+            for (int k = 0; k < M.npairs; k++) {
+                if (!M.pair_enclose[k]) continue;
+                const uint32_t nch = (bins.count_np[k] + 31u) >> 5;
+                if (c < acc + nch) { p = k; local = c - acc; break; }
+                acc += nch;
+            }
         }
         if (p < 0) break;
         const int fl = M.pair_enclose[p];
@@ -1150,7 +1185,7 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, bool has_sam
         for (int k = 0; k < 12; k++) T[k] = parked ? bins.T[k * stride + slot] : 0.f;
         bool maybe = false;
         if (parked) {
-            maybe = may_be_enclosed(fl, GA, GB, A, B, T, padding);
+            maybe = may_be_enclosed(fl, GA, GB, A, B, T, pad_test);
             if (!maybe) commit(p, group, slot, false, 0.f);
         }
         unsigned todo = __ballot_sync(0xffffffffu, maybe);
@@ -1163,7 +1198,7 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, bool has_sam
             const int32_t gs = __shfl_sync(0xffffffffu, group, src);
             if (MODE == MODE_BOOL && out.hit[gs]) continue;   // warp-uniform
             float gap = 0.f;
-            const bool enclosed = surface_enclosed(M, planes, fl, pr.a, pr.b, A, B, GA.core_radius, GB.core_radius, Ts, padding, (int)lane, 32, &gap);
+            const bool enclosed = surface_enclosed(M, planes, fl, pr.a, pr.b, A, B, GA.core_radius, GB.core_radius, Ts, pad_test, (int)lane, 32, &gap);
             if (lane == 0) commit(p, gs, (int64_t)p * bins.cap + local * 32u + src, enclosed, gap);
         }
     }
@@ -1179,14 +1214,16 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, bool has_sam
 // only where that is undecided -- the whole GJK.  Boolean verdicts only.
 constexpr int SMALL_THREADS = 128;
 
-__global__ void __launch_bounds__(SMALL_THREADS)
-k_small_check(DevModel M, StateSource src, int64_t n_states, float padding, Outputs out) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_states * M.npairs) return;
-    const int p = (int)(t / n_states);                  // pair-major: the lanes of a warp share the pair
+// One (pair, state) item.  Returns 0: nothing to publish, 1: the pair collides, 2: the hulls overlap
+// but one shape may be enclosed by the other's surface -- R (placement of b in a's frame) is then
+// handed to the warp-cooperative enclosure test of the kernel.
+enum { SMALL_NONE = 0, SMALL_HIT = 1, SMALL_PARKED = 2 };
+__device__ __forceinline__ int small_item(const DevModel &M, const StateSource &src, int64_t n_states, float padding, const Outputs &out,
+                                          int64_t t, float *R, int32_t &group, int &p) {
+    p = (int)(t / n_states);                            // pair-major: the lanes of a warp share the pair
     const int64_t state = t - (int64_t)p * n_states;
-    const int32_t group = src.group ? src.group[state] : (int32_t)state;
-    if (out.hit[group]) return;                         // already decided by another item of this launch
+    group = src.group ? src.group[state] : (int32_t)state;
+    if (out.hit[group]) return SMALL_NONE;              // already decided by another item of this launch
     const BpPair pr = M.bppairs[p];
     const DevGeom &GA = M.geoms[pr.a];
     const DevGeom &GB = M.geoms[pr.b];
@@ -1199,7 +1236,7 @@ k_small_check(DevModel M, StateSource src, int64_t n_states, float padding, Outp
     // ---- relative placement of b in a's frame (as k_item_setup)
     const PairPath path = M.paths[p];
     const uint8_t *ops = M.path_ops + path.off;
-    float cur[12], lca[12], TA[12], TB[12], nxt[12], R[12];
+    float cur[12], lca[12], TA[12], TB[12], nxt[12];
     se3_identity(cur);
     int o = 0;
     for (int i = 0; i < path.n_trunk; i++, o++) {
@@ -1245,8 +1282,8 @@ k_small_check(DevModel M, StateSource src, int64_t n_states, float padding, Outp
     const bool exact = pr.kind == BP_EXACT_SPHERES;
     const float slack = exact ? 0.f : BP_SLACK;
     const float rf = pr.r_out + padding + slack, rs = pr.r_in + padding - slack;
-    if (rs >= 0.f && d2 <= rs * rs) { out.hit[group] = 1; return; }     // certainly colliding
-    if (exact || d2 > rf * rf) return;                                   // certainly free (or decided exactly)
+    if (rs >= 0.f && d2 <= rs * rs) return SMALL_HIT;                    // certainly colliding
+    if (exact || d2 > rf * rf) return SMALL_NONE;                        // certainly free (or decided exactly)
     // ---- undecided: the whole GJK
     ShapeRef A, B;
     A.shape = GA.shape; A.p0 = GA.par[0]; A.p1 = GA.par[1]; A.p2 = GA.par[2];
@@ -1257,11 +1294,50 @@ k_small_check(DevModel M, StateSource src, int64_t n_states, float padding, Outp
     B.cell_off = GB.map_off >= 0 ? M.sup_cells + GB.map_off : nullptr; B.cell_list = M.sup_lists + GB.list_off;
     const float margin = padding + GA.core_radius + GB.core_radius;
     const GjkOut r = gjk_run<false>(A, B, R, gjk_start_direction(GA, GB, R), margin, 0.f);
-    if (!r.hit) return;
-    if (M.surface && M.pair_enclose[p] && may_be_enclosed(M.pair_enclose[p], GA, GB, A, B, R, padding) && surface_enclosed(M, M.planes, M.pair_enclose[p], pr.a, pr.b, A, B, GA.core_radius, GB.core_radius, R, padding, 0, 1))
-        return;   // one shape wholly inside the other's surface: free in the reference's semantics
-    out.hit[group] = 1;
+    if (!r.hit) return SMALL_NONE;
+    if (M.surface && M.pair_enclose[p] && may_be_enclosed(M.pair_enclose[p], GA, GB, A, B, R, padding)) return SMALL_PARKED;
+    return SMALL_HIT;
 }
+
+__global__ void __launch_bounds__(SMALL_THREADS)
+k_small_check(DevModel M, StateSource src, int64_t n_states, float padding, Outputs out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float R[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) R[k] = 0.f;
+    int32_t group = 0;
+    int p = 0;
+    const int status = t < n_states * M.npairs ? small_item(M, src, n_states, padding, out, t, R, group, p) : SMALL_NONE;
+    if (status == SMALL_HIT) out.hit[group] = 1;
+    if (!M.surface) return;
+    // surface semantics: the (rare) possibly-enclosed items of this warp, one after the other, the
+    // enclosing hull's faces split over the 32 lanes (a single lane would walk ~300 faces alone)
+    const unsigned lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(0xffffffffu, status == SMALL_PARKED);
+    while (todo) {
+        const int srcl = __ffs(todo) - 1;
+        todo &= todo - 1;
+        float Rs[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) Rs[k] = __shfl_sync(0xffffffffu, R[k], srcl);
+        const int ps = __shfl_sync(0xffffffffu, p, srcl);
+        const int32_t gs = __shfl_sync(0xffffffffu, group, srcl);
+        if (out.hit[gs]) continue;   // warp-uniform
+        const BpPair pr = M.bppairs[ps];
+        const DevGeom &GA = M.geoms[pr.a];
+        const DevGeom &GB = M.geoms[pr.b];
+        ShapeRef A, B;
+        A.shape = GA.shape; A.p0 = GA.par[0]; A.p1 = GA.par[1]; A.p2 = GA.par[2];
+        A.verts = M.verts + GA.vert_off; A.nverts = GA.vert_cnt;
+        A.cell_off = GA.map_off >= 0 ? M.sup_cells + GA.map_off : nullptr; A.cell_list = M.sup_lists + GA.list_off;
+        B.shape = GB.shape; B.p0 = GB.par[0]; B.p1 = GB.par[1]; B.p2 = GB.par[2];
+        B.verts = M.verts + GB.vert_off; B.nverts = GB.vert_cnt;
+        B.cell_off = GB.map_off >= 0 ? M.sup_cells + GB.map_off : nullptr; B.cell_list = M.sup_lists + GB.list_off;
+        const bool enclosed = surface_enclosed(M, M.planes, M.pair_enclose[ps], pr.a, pr.b, A, B, GA.core_radius, GB.core_radius, Rs, padding, (int)lane, 32);
+        if (!enclosed && lane == 0) out.hit[gs] = 1;
+    }
+}
+
 
 // ------------------------------------------------------------------------------------------
 // Path discretisation (reference planning/utils.py:114-140)

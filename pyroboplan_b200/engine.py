@@ -118,6 +118,7 @@ class _Profile(ctypes.Structure):
         ("narrowphase_ms", ctypes.c_double),
         ("rounds", ctypes.c_int64),
         ("narrowphase_items", ctypes.c_int64),
+        ("surface_refine_ms", ctypes.c_double),
     ]
 
 

@@ -1,0 +1,109 @@
+"""Surface semantics of mesh geometries on the GPU (pbp_model_desc.planes / pair_enclose).
+
+Pinocchio loads URDF meshes as coal BVHModels -- surfaces -- so a shape wholly inside a mesh without
+touching its surface does not collide with it (reference call site: pinocchio.buildModelsFromUrdf,
+src/pyroboplan/models/panda.py:27).  About 1 in 1000 uniform Panda states differs from the
+convex-hull verdict that way (a finger inside link 0 / 1 / 2 / 5; the hand pairs are disabled by
+the SRDF).  The oracle decides with exact triangle tests; the engine with the enclosure test of
+k_surface_refine."""
+
+import numpy as np
+import pytest
+
+from conftest import make_panda, uniform_states
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from oracle.oracle import Oracle
+    from pyroboplan_b200.engine import CollisionEngine
+
+    model, cmodel, _ = make_panda()
+    eng = CollisionEngine(model, cmodel, device=0)
+    eng_hull = CollisionEngine(model, cmodel, device=0, mesh_semantics="hull")
+    yield model, cmodel, eng, eng_hull, Oracle(model, cmodel), Oracle(model, cmodel, mesh_semantics="hull")
+    eng.close()
+    eng_hull.close()
+
+
+def _mismatch_far(h, ref, dref):
+    bad = np.nonzero(np.asarray(h, dtype=bool) != ref.astype(bool))[0]
+    return [int(i) for i in bad if abs(dref[i]) > 1e-6]
+
+
+def test_state_verdicts_every_path(setup):
+    import torch
+
+    model, cmodel, eng, eng_hull, orc, orc_hull = setup
+    q = uniform_states(model, 300000, 41)
+    qd = torch.as_tensor(q, device="cuda:0")
+    ref, dref, _, _ = orc.check_states(q.astype(np.float64), want_all=True)
+    ref_hull = orc_hull.check_states(q.astype(np.float64))[0]
+    flips = int((ref_hull.astype(bool) & ~ref.astype(bool)).sum())
+    assert 150 < flips < 600                      # the enclosure cases are in the sample
+    assert not _mismatch_far(eng.check_states(qd).cpu().numpy(), ref, dref)                          # three-kernel pipeline + refine
+    hit_d, dist = eng.check_states(qd, return_distance=True)
+    assert not _mismatch_far(hit_d.cpu().numpy(), ref, dref)                                         # distance mode
+    free = (~ref.astype(bool)) & (~hit_d.cpu().numpy().astype(bool))
+    assert np.abs(dist.cpu().numpy()[free] - dref[free]).max() < 5e-4                                # enclosed shapes: clearance to the hull planes (dents below)
+    assert (np.abs(dist.cpu().numpy()[free] - dref[free]) > 1e-5).mean() < 5e-3   # hull vs triangle distance in the dents (0.16 % measured)
+    small = np.concatenate([eng.check_states(qd[i:i + 300]).cpu().numpy() for i in range(0, 30000, 300)])
+    assert not _mismatch_far(small, ref[:30000], dref[:30000])                                       # fused small-batch kernel
+    hit_p, pair = eng.check_states(qd[:100000], return_pair=True)
+    assert not _mismatch_far(hit_p.cpu().numpy(), ref[:100000], dref[:100000])                       # all-pairs mode
+    assert not _mismatch_far(eng.check_states(q[:50000]), ref[:50000], dref[:50000])                 # host buffers
+    # hull semantics stay available and agree with the hull oracle
+    assert not _mismatch_far(eng_hull.check_states(qd).cpu().numpy(), ref_hull, orc_hull.check_states(q.astype(np.float64), want_all=True)[1])
+
+
+def test_enclosed_states_are_free_with_positive_clearance(setup):
+    import torch
+
+    model, cmodel, eng, eng_hull, orc, orc_hull = setup
+    q = uniform_states(model, 200000, 42)
+    ref, dref, _, _ = orc.check_states(q.astype(np.float64), want_all=True)
+    ref_hull = orc_hull.check_states(q.astype(np.float64))[0].astype(bool)
+    enclosed = np.nonzero(ref_hull & ~ref.astype(bool) & (dref > 1e-3))[0]
+    assert len(enclosed) > 50
+    qe = torch.as_tensor(q[enclosed], device="cuda:0")
+    hit, dist = eng.check_states(qe, return_distance=True)
+    assert not hit.any().item() and not eng.check_states(qe).any().item()
+    assert eng_hull.check_states(qe).all().item()
+    np.testing.assert_allclose(dist.cpu().numpy(), dref[enclosed], atol=5e-4)
+    # one at a time through the drop-in function (fused kernel, host path)
+    from pyroboplan_b200.core.utils import check_collisions_at_state
+
+    for i in enclosed[:10]:
+        assert not check_collisions_at_state(model, cmodel, q[i])
+
+
+def test_padding_and_edges(setup):
+    import torch
+
+    model, cmodel, eng, eng_hull, orc, orc_hull = setup
+    q = uniform_states(model, 60000, 43)
+    qd = torch.as_tensor(q, device="cuda:0")
+    for pad in (0.004, 0.02):
+        ref, dref, _, _ = orc.check_states(q.astype(np.float64), padding=pad, want_all=True)
+        h = eng.check_states(qd, padding=pad).cpu().numpy().astype(bool)
+        bad = np.nonzero(h != ref.astype(bool))[0]
+        # a verdict may differ only within FP32 resolution of the padding, or -- for an enclosed shape --
+        # within the depth of the mesh's dents below its hull (0.4 mm) of it
+        assert all(abs(dref[i] - pad) < 5e-4 for i in bad) and len(bad) <= 6, [(int(i), float(dref[i])) for i in bad]
+    a = uniform_states(model, 4000, 44)
+    b = (a + 0.25 * (uniform_states(model, 4000, 45) - a)).astype(np.float32)
+    ref_e, _, _, _ = orc.check_edges(a.astype(np.float64), b.astype(np.float64), 0.05)
+    got = eng.check_edges(torch.as_tensor(a, device="cuda:0"), torch.as_tensor(b, device="cuda:0"), 0.05).cpu().numpy().astype(bool)
+    assert (got != ref_e.astype(bool)).sum() <= 1          # an edge sample within 1e-6 m of contact
+    # short edges that start at an enclosed state: free to leave under surface semantics unless they cross the mesh
+    ref_s = orc.check_states(q.astype(np.float64))[0].astype(bool)
+    ref_h = orc_hull.check_states(q.astype(np.float64))[0].astype(bool)
+    enclosed = q[ref_h & ~ref_s]
+    assert len(enclosed) > 20
+    nudged = (enclosed + np.float32(0.01) * (uniform_states(model, len(enclosed), 46) - enclosed)).astype(np.float32)
+    ref_n, _, _, _ = orc.check_edges(nudged.astype(np.float64), enclosed.astype(np.float64), 0.05)
+    got_n = eng.check_edges(torch.as_tensor(nudged, device="cuda:0"), torch.as_tensor(enclosed, device="cuda:0"), 0.05).cpu().numpy().astype(bool)
+    assert (got_n == ref_n.astype(bool)).all() and not ref_n.all()
+    assert eng_hull.check_edges(torch.as_tensor(nudged, device="cuda:0"), torch.as_tensor(enclosed, device="cuda:0"), 0.05).all().item()
