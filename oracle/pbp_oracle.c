@@ -460,7 +460,7 @@ static double pair_distance_semantics(const oracle_model *m, const double *oMg, 
     if (is_exact) *is_exact = !pair_has_surface(m, ga, gb);
     if (d <= padding && pair_has_surface(m, ga, gb)) {
         d = oracle_soup_pair_distance(m, oMg, ga, gb, m->tris + 9 * (int64_t)m->tri_off[ga], m->tri_cnt[ga],
-                                      m->tris + 9 * (int64_t)m->tri_off[gb], m->tri_cnt[gb], padding, want_exact ? 0 : 2);
+                                      m->tris + 9 * (int64_t)m->tri_off[gb], m->tri_cnt[gb], want_exact ? -1.0 : padding, want_exact ? 0 : 2);
         if (is_exact) *is_exact = 1;
     }
     return d;

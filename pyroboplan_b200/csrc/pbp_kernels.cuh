@@ -79,11 +79,19 @@ constexpr int32_t SR_PARKED = 0x40000000;
 // MODE_BOOL_ALL  verdict + first_pair / first_bad: every pair of every state is resolved
 // MODE_DIST      verdict + min distance: pairs are resolved unless certainly farther than the bound
 
+// Copy a model table into shared memory.  Both pointers are 16-byte aligned (cudaMalloc bases, smem
+// carved with align16): 16-byte loads, four in flight per thread -- a word-by-word loop is a chain
+// of dependent L2 latencies (60 of them for the 120 KB k_surface_refine stages, 40 % of its time).
 __device__ __forceinline__ void stage_words(void *dst, const void *src, int bytes) {
+    const int n16 = bytes >> 4;
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) d4[i] = __ldg(s4 + i);
     const int n = bytes >> 2;
     uint32_t *d = reinterpret_cast<uint32_t *>(dst);
     const uint32_t *s = reinterpret_cast<const uint32_t *>(src);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+    for (int i = (n16 << 2) + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
 }
 
 __host__ __device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -707,7 +715,9 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
         //      the simplex slot of a lane's last trip.  (PBP_NP_LOCKSTEP=0 restores the older
         //      policy: per trip, run only the phase most lanes are waiting for.)
         auto publish = [&](const GjkOut &r, float radii) {
-            if (r.hit && M.surface && M.pair_enclose[p]) {
+            // (distance mode: only OVERLAPPING hulls can be an enclosure; a pair merely within the
+            // padding keeps its measured distance)
+            if (r.hit && M.surface && M.pair_enclose[p] && (MODE != MODE_DIST || r.dist - radii <= 0.f)) {
                 // surface semantics: one shape of this pair could be enclosed by the other's surface,
                 // which is the free placement -- k_surface_refine decides the parked item (all its
                 // lanes busy with such items, instead of one lane of this warp)

@@ -199,8 +199,9 @@ def _could_enclose(outer, inner):
     """Necessary conditions for ``inner`` to fit inside ``outer`` in SOME relative placement: inclusion
     is monotone in the inscribed radius, the enclosing radius and the volume.  (Conservative: a
     pair flagged needlessly only costs its hull hits an enclosure test.)"""
-    return (inner.inner_sphere()[1] <= outer.inner_sphere()[1] and inner.bounding_sphere()[1] <= outer.bounding_sphere()[1]
-            and _shape_volume(inner) <= _shape_volume(outer))
+    tol = 1.002   # the enclosing balls of hulls are computed iteratively
+    return (inner.inner_sphere()[1] <= tol * outer.inner_sphere()[1] and inner.bounding_sphere()[1] <= tol * outer.bounding_sphere()[1]
+            and _shape_volume(inner) <= tol * _shape_volume(outer))
 
 
 def _planes_by_area(s):
