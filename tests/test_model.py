@@ -174,3 +174,44 @@ def test_enclosing_capsules_contain_their_hulls():
             flagged.append(obj.name)
             assert r < 0.55 * arrays["geom_outer"][g][3]
     assert flagged == ["panda_link5_0", "panda_hand_0"]
+
+
+def test_surface_tables_of_the_panda():
+    """pbp_model_desc surface tables (engine.flatten_model): the hull planes contain every hull vertex and are
+    sorted by face area, the dent depths are sub-millimetre, and the enclosure flags name exactly the pairs
+    whose second geometry is small enough to fit inside the first (never a primitive as the enclosing one)."""
+    from pyroboplan_b200.engine import flatten_model
+    from pyroboplan_b200.models import panda, two_dof
+
+    model, cmodel, vmodel = panda.load_models()
+    panda.add_self_collisions(model, cmodel)
+    panda.add_object_collisions(model, cmodel, vmodel)
+    a, sizes = flatten_model(model, cmodel)
+    geoms = cmodel.geometryObjects
+    assert sizes["nplanes"] == int(a["geom_plane_cnt"].sum()) > 0
+    for g, obj in enumerate(geoms):
+        cnt, off = int(a["geom_plane_cnt"][g]), int(a["geom_plane_off"][g])
+        if type(obj.geometry).__name__ != "Convex":
+            assert cnt == 0 and a["geom_surface_tol"][g] == 0
+            continue
+        pl = a["planes"][off:off + cnt].astype(np.float64)
+        v = a["verts"][a["geom_vert_off"][g]: a["geom_vert_off"][g] + a["geom_vert_cnt"][g]].astype(np.float64)
+        assert cnt == len(obj.geometry.planes)
+        np.testing.assert_allclose(np.linalg.norm(pl[:, :3], axis=1), 1.0, atol=1e-6)
+        slack = (v @ pl[:, :3].T - pl[:, 3]).max(axis=0)
+        assert slack.max() < 2e-6 and slack.min() > -2e-6          # every plane supports the hull: it touches a vertex
+        assert 0.0 < a["geom_surface_tol"][g] < 5e-4                # dents of the collision meshes: <= 0.39 mm (link 3)
+    flagged = {(geoms[p.first].name, geoms[p.second].name): int(a["pair_enclose"][k]) for k, p in enumerate(cmodel.collisionPairs) if a["pair_enclose"][k]}
+    assert len(flagged) == 17 and set(flagged.values()) == {1}
+    for small in ("panda_leftfinger_0", "panda_rightfinger_0"):
+        for big in ("panda_link0_0", "panda_link1_0", "panda_link2_0", "panda_link5_0"):
+            assert (big, small) in flagged
+    assert all("obstacle" not in x and "ground" not in x for pair in flagged for x in pair)
+    # hull semantics on request; models without meshes never carry surface tables
+    a_h, s_h = flatten_model(model, cmodel, mesh_semantics="hull")
+    assert s_h["nplanes"] == 0 and not a_h["pair_enclose"].any()
+    m2, c2, v2 = two_dof.load_models()
+    two_dof.add_object_collisions(m2, c2, v2)
+    assert flatten_model(m2, c2)[1]["nplanes"] == 0
+    with pytest.raises(ValueError):
+        flatten_model(model, cmodel, mesh_semantics="soup")
