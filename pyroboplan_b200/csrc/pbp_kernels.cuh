@@ -1031,12 +1031,13 @@ k_narrowphase_pool(DevModel M, float padding, Outputs out, Bins bins, uint32_t *
 // reduces with a warp maximum when nlanes > 1.
 //   T: placement of `inner` in the frame of the geometry `g_outer`; returns max_f (h_inner(n_f) - w_f).
 __device__ __forceinline__ float enclosure_excess(const DevModel &M, const float4 *planes, int g_outer, const ShapeRef &inner, float inner_radius,
-                                                  const float *T, float padding, int lane, int nlanes) {
+                                                  const float *T, float padding, int lane, int nlanes, int max_faces = INT_MAX) {
     const int2 pi = M.plane_idx[g_outer];
+    const int nfaces = min(pi.y, max_faces);
     float worst = -FLT_MAX;
-    for (int f0 = 0; f0 < pi.y; f0 += nlanes) {
+    for (int f0 = 0; f0 < nfaces; f0 += nlanes) {
         const int f = f0 + lane;
-        if (f < pi.y) {
+        if (f < nfaces) {
             const float4 pl = planes[pi.x + f];
             const float3 dl = make_float3(fmaf(T[0], pl.x, fmaf(T[3], pl.y, T[6] * pl.z)), fmaf(T[1], pl.x, fmaf(T[4], pl.y, T[7] * pl.z)),
                                           fmaf(T[2], pl.x, fmaf(T[5], pl.y, T[8] * pl.z)));
@@ -1054,11 +1055,13 @@ __device__ __forceinline__ float enclosure_excess(const DevModel &M, const float
 
 // flags bit 0: b could lie inside a's surface; bit 1: a inside b's.  T: placement of b in a's frame.
 // gap_out (optional): the clearance of the enclosed shape to the enclosing hull.
+// max_faces: only the first (largest) faces of the enclosing hull -- a "false" is then a proof that the
+// inner shape pokes out, a "true" only means that none of those faces was reached.
 __device__ __forceinline__ bool surface_enclosed(const DevModel &M, const float4 *planes, int flags, int ga, int gb, const ShapeRef &A,
                                                  const ShapeRef &B, float ra, float rb, const float *T, float padding, int lane, int nlanes,
-                                                 float *gap_out = nullptr) {
+                                                 float *gap_out = nullptr, int max_faces = INT_MAX) {
     if (flags & 1) {
-        float ex = enclosure_excess(M, planes, ga, B, rb, T, padding, lane, nlanes);
+        float ex = enclosure_excess(M, planes, ga, B, rb, T, padding, lane, nlanes, max_faces);
         if (nlanes > 1) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ex = fmaxf(ex, __shfl_xor_sync(0xffffffffu, ex, o));
@@ -1072,7 +1075,7 @@ __device__ __forceinline__ bool surface_enclosed(const DevModel &M, const float4
             Ti[3 * i + 0] = T[i]; Ti[3 * i + 1] = T[3 + i]; Ti[3 * i + 2] = T[6 + i];
             Ti[9 + i] = -(T[i] * T[9] + T[3 + i] * T[10] + T[6 + i] * T[11]);
         }
-        float ex = enclosure_excess(M, planes, gb, A, ra, Ti, padding, lane, nlanes);
+        float ex = enclosure_excess(M, planes, gb, A, ra, Ti, padding, lane, nlanes, max_faces);
         if (nlanes > 1) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ex = fmaxf(ex, __shfl_xor_sync(0xffffffffu, ex, o));
@@ -1091,6 +1094,7 @@ __device__ __forceinline__ bool surface_enclosed(const DevModel &M, const float4
 // chain of dependent table reads).
 constexpr int SR_THREADS = 512;
 constexpr int SR_DIR = 256;       // flagged pairs the chunk directory holds
+constexpr int SR_LANE_FACES = 8;  // faces of the enclosing hull each lane tries by itself in pass 1
 
 template <int MODE, bool TABLES_IN_SMEM>
 __global__ void __launch_bounds__(SR_THREADS)
@@ -1195,7 +1199,10 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, bool has_sam
         for (int k = 0; k < 12; k++) T[k] = parked ? bins.T[k * stride + slot] : 0.f;
         bool maybe = false;
         if (parked) {
-            maybe = may_be_enclosed(fl, GA, GB, A, B, T, pad_test);
+            // the centre line settles 73 % of the parked items, the enclosing hull's 8 largest faces
+            // 76 % of the rest (measured on config 2): 1.4 x the true enclosures reach pass 2
+            maybe = may_be_enclosed(fl, GA, GB, A, B, T, pad_test) &&
+                    surface_enclosed(M, planes, fl, pr.a, pr.b, A, B, GA.core_radius, GB.core_radius, T, pad_test, 0, 1, nullptr, SR_LANE_FACES);
             if (!maybe) commit(p, group, slot, false, 0.f);
         }
         unsigned todo = __ballot_sync(0xffffffffu, maybe);
