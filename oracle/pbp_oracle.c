@@ -23,9 +23,16 @@
  *   - check_collisions_along_path  /root/reference/src/pyroboplan/core/utils.py:90-132
  * Pair distance: GJK (Gilbert-Johnson-Keerthi) on support functions, float64, run to
  * convergence (exact for polytopes), with spheres/capsules handled as core + radius.  URDF
- * meshes are treated as their convex hulls (see DESIGN.md "mesh semantics").  The verdict path
- * reports penetrating pairs with distance 0; oracle_pair_signed_distance (end of file) restates
- * coal's penetration depth (EPA) for the distance / avoidance rows.
+ * meshes are SURFACES, as Pinocchio's coal BVHModels are: the convex hull of a mesh is only the
+ * first stage -- a pair whose hulls are within the padding is decided by exact triangle tests
+ * (oracle_soup_pair_distance, end of file; DESIGN.md "Mesh semantics"), so a shape wholly inside a
+ * mesh does not collide with it.  Without triangle tables (oracle_model.tris == NULL) meshes are
+ * convex solids.  The verdict path reports penetrating pairs with distance 0;
+ * oracle_pair_signed_distance restates coal's penetration depth (EPA) on the hulls for the
+ * distance / avoidance rows.
+ *
+ * PARITY UNPINNED beyond the reference's own known-answer vectors: no output of Pinocchio / coal
+ * is available here.
  *
  * Parity pin: tests/test_oracle_golden.py checks this file against every known-answer vector
  * the reference's tests hold for the path and verifies, independently of GJK,

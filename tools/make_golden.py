@@ -7,7 +7,9 @@ The reference itself (Pinocchio/coal) cannot run in the authoring container, so 
 from the oracle (oracle/pbp_oracle.c), whose pair results are certificate-checked and which
 reproduces every known-answer vector of the reference's own tests (tests/test_oracle_golden.py).
 The three known-answer states of /root/reference/test/core/test_utils.py:129-212 are included
-verbatim with the verdicts the reference asserts.
+verbatim with the verdicts the reference asserts.  The oracle runs with the reference's mesh
+semantics (surfaces: exact triangle tests wherever the hulls are within the padding, min distances
+measured to the triangles).
 """
 import os
 import sys
