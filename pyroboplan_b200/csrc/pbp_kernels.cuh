@@ -1092,7 +1092,7 @@ __device__ __forceinline__ bool surface_enclosed(const DevModel &M, const float4
 // hit.  Pass 2, one item per warp: the face planes of the enclosing hull split over the 32 lanes.
 // The hull tables and planes are staged in shared memory when they fit (every support evaluation is a
 // chain of dependent table reads).
-constexpr int SR_THREADS = 512;        // (1024 threads at 64 registers: 74 us against 62)
+constexpr int SR_THREADS = 512;        // (768 threads at 80 registers: 72 us, 1024 at 64: 74 us, against 62)
 constexpr int SR_DIR = 256;       // flagged pairs the chunk directory holds
 constexpr int SR_LANE_FACES = 8;  // faces of the enclosing hull each lane tries by itself in pass 1
 
