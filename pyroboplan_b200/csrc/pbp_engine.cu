@@ -151,9 +151,9 @@ namespace {
 
 // control block layout (uint32 words): [0, npairs) bin counts, [npairs] item-setup tile counter,
 // [npairs + 1] narrowphase chunk cursor, [npairs + 2, 2 npairs + 2) narrowphase bin counts (items the
-// item setup kept), then four 64-bit counters at an 8-byte aligned offset
+// item setup kept), [2 npairs + 2] surface-refine chunk cursor, then four 64-bit counters at an 8-byte aligned offset
 // (level total, emit cursor, select count, profiled item total, IK work cursor).
-inline size_t ctrl_words(const pbp_engine *e) { return 2 * (size_t)e->npairs + 2; }
+inline size_t ctrl_words(const pbp_engine *e) { return 2 * (size_t)e->npairs + 3; }   // + the surface-refine chunk cursor
 // There are two such blocks (workspaces 0 / 1, see pbp_engine::ws); the 64-bit counters live in block 0.
 inline size_t ctrl_bytes(const pbp_engine *e) { return ((ctrl_words(e) * 4 + 7) & ~(size_t)7) + 64; }   // 8 x 64-bit counters
 inline uint32_t *ctrl_base(pbp_engine *e) {
@@ -163,6 +163,7 @@ inline uint32_t *ctrl_counts(pbp_engine *e) { return ctrl_base(e); }
 inline uint32_t *ctrl_tile_setup(pbp_engine *e) { return ctrl_base(e) + e->npairs; }
 inline uint32_t *ctrl_chunk_np(pbp_engine *e) { return ctrl_base(e) + e->npairs + 1; }
 inline uint32_t *ctrl_counts_np(pbp_engine *e) { return ctrl_base(e) + e->npairs + 2; }
+inline uint32_t *ctrl_chunk_sr(pbp_engine *e) { return ctrl_base(e) + 2 * e->npairs + 2; }
 inline unsigned long long *ctrl_u64(pbp_engine *e, int i) {
     const size_t off = (ctrl_words(e) * 4 + 7) & ~(size_t)7;
     return reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(e->d_ctrl.p) + off) + i;
@@ -258,9 +259,9 @@ int launch_round_kernels(pbp_engine *e, const StateSource &src, int64_t n, float
         // hull hits of pairs with an enclosure flag were parked by the narrowphase: decide them
         const unsigned sr_grid = (unsigned)std::min<int64_t>(e->sr_blocks, std::max<int64_t>(1, (max_items + 31) / 32 / (SR_THREADS / 32)));
         if (e->sr_tables_in_smem && n >= 65536)   // staging the tables only pays when the blocks have many items
-            k_surface_refine<MODE, true><<<sr_grid, SR_THREADS, e->smem_sr, st>>>(e->dm, padding, out, bins, has_sample);
+            k_surface_refine<MODE, true><<<sr_grid, SR_THREADS, e->smem_sr, st>>>(e->dm, padding, out, bins, ctrl_chunk_sr(e), has_sample);
         else
-            k_surface_refine<MODE, false><<<sr_grid, SR_THREADS, 0, st>>>(e->dm, padding, out, bins, has_sample);
+            k_surface_refine<MODE, false><<<sr_grid, SR_THREADS, 0, st>>>(e->dm, padding, out, bins, ctrl_chunk_sr(e), has_sample);
         LAUNCH_CHECK("k_surface_refine");
     }
     return 0;

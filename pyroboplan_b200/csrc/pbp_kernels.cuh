@@ -1098,7 +1098,7 @@ constexpr int SR_LANE_FACES = 8;  // faces of the enclosing hull each lane tries
 
 template <int MODE, bool TABLES_IN_SMEM>
 __global__ void __launch_bounds__(SR_THREADS)
-k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, bool has_sample) {
+k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk_cursor, bool has_sample) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *ptr = smem_raw;
     float4 *sv = reinterpret_cast<float4 *>(ptr);        ptr += TABLES_IN_SMEM ? align16((size_t)M.nverts_padded * sizeof(float4)) : 0;
@@ -1152,8 +1152,13 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, bool has_sam
         s_n = nf;
     }
     __syncthreads();
-    for (uint32_t c = warp;; c += nwarps) {
-        // chunk c of the concatenated flagged bins
+    (void)warp; (void)nwarps;
+    for (;;) {
+        // next chunk of the concatenated flagged bins, claimed from a global cursor: the chunks differ
+        // widely in cost (parked lanes, true enclosures), a fixed round-robin leaves warps idle
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(chunk_cursor, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
         int p = -1;
         uint32_t local = 0;
         if (s_n >= 0) {
