@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PBP_ABI_VERSION 3
+#define PBP_ABI_VERSION 4
 
 typedef enum {
     PBP_OK = 0,

@@ -18,7 +18,7 @@ from .model.shapes import Box, Capsule, Convex, Cylinder, Sphere
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpbp_engine.so")
 
-PBP_ABI_VERSION = 3
+PBP_ABI_VERSION = 4
 
 # symbols declared in include/pbp_engine.h (tests check the library exports every one)
 EXPORTED_SYMBOLS = [
