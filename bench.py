@@ -53,13 +53,13 @@ HBM_BYTES_PER_CONFIG = 9 * 4 + 1   # 9 float32 in, 1 verdict byte out
 NCU = {
     "source": "profiles/r01_v8_ncu_summary.txt",
     "k_broadphase": {"traffic_bytes": 37.81e6 + 0.01e6, "fma_pipe_pct": 34.3, "alu_pipe_pct": 62.0, "issue_active_pct": 76.4,
-                     "threads_per_inst": 28.2, "duration_us": 104.2},
+                     "threads_per_inst": 28.2, "duration_us": 103.3},
     "k_item_setup": {"traffic_bytes": 35.89e6 + 0.58e6, "fma_pipe_pct": 26.7, "alu_pipe_pct": 33.8, "issue_active_pct": 58.9,
-                     "threads_per_inst": 29.8, "duration_us": 85.2},
-    "k_narrowphase": {"traffic_bytes": 18.57e6 + 0.05e6, "fma_pipe_pct": 20.6, "alu_pipe_pct": 35.5, "issue_active_pct": 52.2,
-                      "threads_per_inst": 14.1, "duration_us": 134.3},
-    "k_surface_refine": {"traffic_bytes": 7.59e6 + 0.007e6, "fma_pipe_pct": 9.0, "alu_pipe_pct": 16.0, "issue_active_pct": 25.7,
-                         "threads_per_inst": 20.5, "duration_us": 61.9},
+                     "threads_per_inst": 29.8, "duration_us": 85.4},
+    "k_narrowphase": {"traffic_bytes": 18.56e6 + 0.03e6, "fma_pipe_pct": 20.4, "alu_pipe_pct": 35.3, "issue_active_pct": 52.4,
+                      "threads_per_inst": 14.1, "duration_us": 134.4},
+    "k_surface_refine": {"traffic_bytes": 7.62e6 + 0.006e6, "fma_pipe_pct": 7.7, "alu_pipe_pct": 13.7, "issue_active_pct": 24.0,
+                         "threads_per_inst": 20.1, "duration_us": 59.4},
 }
 
 
