@@ -97,8 +97,9 @@ typedef struct {
      * enclosed by the other's surface; the enclosure test needs the hull's face planes.
      *   planes            n.x <= off inside, unit normals, geometry frame
      *   geom_surface_tol  how far the mesh surface lies below its hull (dents), metres -- carried with
- *                     the model for the callers' error budget (hull distances exceed triangle
- *                     distances by at most this much per mesh); the kernels do not read it yet
+ *                     the model for the callers' error budget (the distance to a mesh's triangles
+ *                     exceeds the distance to its hull by at most this much); the kernels do not
+ *                     read it yet
      *   pair_enclose      bit 0: `second` could lie wholly inside `first`, and `first` is a surface;
      *                     bit 1: `first` could lie wholly inside `second`, and `second` is a surface */
     const float *planes;               /* [nplanes][4] nx ny nz off */
