@@ -1,3 +1,7 @@
+"""Three 1 Mi-state boolean checks per mesh semantics ("hull", then "surface"), for an ncu launch list:
+
+    ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/gpu_surface_prof.py
+"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -43,7 +43,6 @@ def main():
     for i in diff[:40]:
         _, oMg = orc.fk(q[i])
         for p in cmodel.collisionPairs:
-            d_h = orc.pair_distance_placed(oMg, p.first, p.second)[0] if hasattr(orc, "pair_distance_placed") else None
             ds, _, _, _, exact = orc.pair_signed_distance_placed(oMg, p.first, p.second)
             if ds <= padding:
                 d_s = orc.soup_pair_distance(oMg, p.first, p.second)
