@@ -193,3 +193,15 @@ def test_nested_shells_both_enclosure_roles(seed):
         bad = np.nonzero(h != refp.astype(bool))[0]
         assert all(abs(drefp[i] - pad) <= 2e-6 for i in bad), [(int(i), float(drefp[i])) for i in bad[:5]]
     eng.close()
+
+
+def test_sampler_accepts_enclosed_states_as_the_reference_does(setup):
+    """Rejection sampling (get_random_collision_free_state's batched sibling) runs on the same verdicts:
+    every accepted state is free for the triangle oracle, and a few of them are the enclosure states a
+    convex-hull engine would have rejected."""
+    model, cmodel, eng, eng_hull, orc, orc_hull = setup
+    q = eng.sample_free_states(150000, seed=5, as_numpy=True)
+    assert q.shape == (150000, model.nq)
+    ref, dref, _, _ = orc.check_states(q.astype(np.float64), want_all=True)
+    assert not [i for i in np.nonzero(ref)[0] if abs(dref[i]) > 1e-6]
+    assert orc_hull.check_states(q.astype(np.float64))[0].sum() > 50
