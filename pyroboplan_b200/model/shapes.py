@@ -100,8 +100,9 @@ class Convex(CollisionGeometry):
         from scipy.spatial import ConvexHull
 
         pts = np.asarray(points, dtype=np.float64).reshape(-1, 3)
-        # The source triangle soup (if any) is kept verbatim for the oracle's mesh-semantics
-        # cross-check; the engine itself only consumes the hull vertices in ``self.points``.
+        # The source triangles (if any) are kept verbatim: the oracle evaluates the reference's surface
+        # semantics on them; the engine consumes the hull (``self.points``, ``self.planes``) and only
+        # needs to know THAT the geometry is a surface.
         self.mesh_vertices = pts.copy()
         self.mesh_triangles = None if triangles is None else np.asarray(triangles, dtype=np.int64).reshape(-1, 3)
         pts = np.unique(pts, axis=0)
@@ -116,6 +117,12 @@ class Convex(CollisionGeometry):
             if np.max(np.abs(row - uniq[-1])) > 1e-9:
                 uniq.append(row)
         self.planes = np.array(uniq)
+        # area of the hull face behind every plane (the engine sorts the planes by it: the enclosure
+        # test of the surface semantics tries the largest faces first)
+        tri = pts[hull.simplices]
+        tri_area = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1)
+        owner = np.abs(hull.equations[:, None, :] - self.planes[None, :, :]).sum(axis=2).argmin(axis=1)
+        self.plane_areas = np.bincount(owner, weights=tri_area, minlength=len(self.planes))
         self.volume = float(hull.volume)
         self.source = source
         self.volume_ratio = volume_ratio
