@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PBP_ABI_VERSION 4
+#define PBP_ABI_VERSION 5
 
 typedef enum {
     PBP_OK = 0,
@@ -90,24 +90,42 @@ typedef struct {
     const float *geom_capsule;         /* [ngeoms][8] */
     /* optional (all NULL / 0: every geometry is a solid): SURFACE semantics of triangle meshes.
      * Pinocchio loads a URDF <mesh> as a coal BVHModel -- the surface triangles, not the solid
-     * (pinocchio.buildModelsFromUrdf, src/pyroboplan/models/panda.py:27) -- so a shape that lies
-     * wholly inside a mesh without touching its surface does NOT collide with it in the reference
-     * (1 in 1000 uniform Panda states: a finger inside link 0 / 1 / 2 / 5 while the hand - link pair
-     * is disabled by the SRDF).  For such pairs a hull overlap only counts when neither shape is
-     * enclosed by the other's surface; the enclosure test needs the hull's face planes.
-     *   planes            n.x <= off inside, unit normals, geometry frame
-     *   geom_surface_tol  how far the mesh surface lies below its hull (dents), metres -- carried with
- *                     the model for the callers' error budget (the distance to a mesh's triangles
- *                     exceeds the distance to its hull by at most this much); the kernels do not
- *                     read it yet
+     * (pinocchio.buildModelsFromUrdf, src/pyroboplan/models/panda.py:27): two meshes collide when two of
+     * their triangles come within the security margin, a primitive (a solid) collides with a mesh when it
+     * comes within the margin of a triangle, and a shape that lies wholly inside a mesh without reaching
+     * its surface does NOT collide with it (1 in 1000 uniform Panda states: a finger inside link 0 / 1 /
+     * 2 / 5 while the hand - link pair is disabled by the SRDF).  The engine brackets a mesh M between
+     * two convex polytopes -- the hull H of its vertices (`verts`) and an inner core K inside the mesh
+     * (`core_verts`: a subset of the vertices of the intersection of the inner half-spaces of all
+     * triangles) -- runs its GJK kernels on those, and evaluates the triangles themselves (exact
+     * triangle - triangle / triangle - primitive distances) for the items the two bounds leave open.
+     *   planes            faces of the exact core {x : n.x <= off}, unit normals, geometry frame: the hull's
+     *                     face planes first (geom_plane_hull_cnt of them, largest face first), then the
+     *                     planes of mesh triangles that lie below the hull
+     *   geom_surface_tol  two-sided distance between the hull's boundary and the mesh surface (metres)
      *   pair_enclose      bit 0: `second` could lie wholly inside `first`, and `first` is a surface;
-     *                     bit 1: `first` could lie wholly inside `second`, and `second` is a surface */
+     *                     bit 1: `first` could lie wholly inside `second`, and `second` is a surface
+     *   core_verts        vertices of K; geom_core_cnt == 0: the geometry has no core (K = H is used when
+     *                     the geometry is a solid; a surface without a core never certifies a hit by GJK)
+     *   geom_core_eps     every point of H is within this distance of K (metres)
+     *   mesh_verts, tris  the triangles: tris[t] = three vertex indices relative to geom_mvert_off */
     const float *planes;               /* [nplanes][4] nx ny nz off */
-    const int32_t *geom_plane_off;     /* [ngeoms] first plane of the geometry's hull */
+    const int32_t *geom_plane_off;     /* [ngeoms] first plane of the geometry */
     const int32_t *geom_plane_cnt;     /* [ngeoms] number of planes (0: none given) */
     const float *geom_surface_tol;     /* [ngeoms] */
     const uint8_t *pair_enclose;       /* [npairs] */
     int32_t nplanes;
+    int32_t ncore, nmverts, ntris;
+    const int32_t *geom_plane_hull_cnt; /* [ngeoms] */
+    const float *core_verts;           /* [ncore][3] */
+    const int32_t *geom_core_off;      /* [ngeoms] */
+    const int32_t *geom_core_cnt;      /* [ngeoms] */
+    const float *geom_core_eps;        /* [ngeoms] */
+    const float *mesh_verts;           /* [nmverts][3] */
+    const int32_t *geom_mvert_off;     /* [ngeoms] */
+    const int32_t *tris;               /* [ntris][3] */
+    const int32_t *geom_tri_off;       /* [ngeoms] */
+    const int32_t *geom_tri_cnt;       /* [ngeoms] 0: the geometry is a solid */
 } pbp_model_desc;
 
 typedef struct pbp_engine pbp_engine;

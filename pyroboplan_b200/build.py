@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpbp_engine.so")
 SOURCES = ["pbp_engine.cu"]
-HEADERS = ["pbp_kernels.cuh", "pbp_gjk.cuh", "pbp_model.cuh", "pbp_ik.cuh", "pbp_supmap.h", "pbp_knn.cuh", "pbp_witness.cuh", "pbp_jit.h", os.path.join("..", "..", "include", "pbp_engine.h")]
+HEADERS = ["pbp_kernels.cuh", "pbp_host_tables.h", "pbp_surface.cuh", "pbp_gjk.cuh", "pbp_model.cuh", "pbp_ik.cuh", "pbp_supmap.h", "pbp_knn.cuh", "pbp_witness.cuh", "pbp_jit.h", os.path.join("..", "..", "include", "pbp_engine.h")]
 
 NVCC_FLAGS = [
     "-O3",

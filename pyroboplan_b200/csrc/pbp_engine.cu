@@ -98,7 +98,7 @@ struct pbp_engine {
     bool bp_smem_store = true;  // per-thread broadphase store fits in shared memory
     bool verts_in_smem = true;
     DevModel dm{};
-    DeviceBuffer d_joints, d_jgeoms, d_geoms, d_bpgeoms, d_bpboxes, d_bppairs, d_groups, d_pairorig, d_paths, d_pathops, d_order, d_verts, d_supcells, d_suplists, d_qlim, d_frames, d_planes, d_plane_idx, d_surf_tol, d_pair_enclose;
+    DeviceBuffer d_joints, d_jgeoms, d_geoms, d_bpgeoms, d_bpboxes, d_bppairs, d_groups, d_pairorig, d_paths, d_pathops, d_order, d_verts, d_supcells, d_suplists, d_qlim, d_frames, d_planes, d_plane_idx, d_surf_tol, d_pair_enclose, d_kverts, d_ksupcells, d_ksuplists, d_mverts, d_tris;
     bool surface = false;   // some pair carries an enclosure flag (surface semantics of mesh geometries)
     bool sr_tables_in_smem = false;
     size_t smem_sr = 0;
@@ -136,9 +136,9 @@ struct pbp_engine {
     DeviceBuffer d_ws_oMi, d_ws_oMg, d_ws_dist, d_ws_p1, d_ws_p2, d_ws_nrm, d_pairs_orig;   // distance / witness scratch
     pbp::IkTables ik_cached{}, ik_build{};
     bool ik_cached_valid = false;
-    size_t smem_bp = 0, smem_is = 0, smem_np = 0, smem_fk = 0, smem_np_pool = 0;
-    int np_blocks = 0, is_blocks = 0, np_pool_blocks = 0;
-    bool np_pool = false;    // block-cooperative narrowphase (k_narrowphase_pool)
+    size_t smem_bp = 0, smem_is = 0, smem_np = 0, smem_np_dist = 0, smem_fk = 0;
+    int np_blocks = 0, is_blocks = 0;
+    bool verts_in_smem_dist = true;
     pbp_stats stats{};
     // optional per-kernel timing
     bool profiling = false;
@@ -247,12 +247,14 @@ int launch_round_kernels(pbp_engine *e, const StateSource &src, int64_t n, float
     k_item_setup<MODE><<<is_grid, IS_THREADS, e->smem_is, st>>>(e->dm, src, padding, out, bins, ctrl_tile_setup(e));
     LAUNCH_CHECK("k_item_setup");
     if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
-    if (e->np_pool)
-        k_narrowphase_pool<MODE><<<e->np_pool_blocks, NP_THREADS, e->smem_np_pool, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
-    else if (e->verts_in_smem)
-        k_narrowphase<MODE, true><<<np_grid, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
-    else
-        k_narrowphase<MODE, false><<<np_grid, NP_THREADS, e->smem_np, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
+    {
+        const bool in_smem = MODE == MODE_DIST ? e->verts_in_smem_dist : e->verts_in_smem;
+        const size_t smem = MODE == MODE_DIST ? e->smem_np_dist : e->smem_np;
+        if (in_smem)
+            k_narrowphase<MODE, true><<<np_grid, NP_THREADS, smem, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
+        else
+            k_narrowphase<MODE, false><<<np_grid, NP_THREADS, smem, st>>>(e->dm, padding, out, bins, ctrl_chunk_np(e), has_sample);
+    }
     LAUNCH_CHECK("k_narrowphase");
     if (ev) CUDA_TRY(cudaEventRecord(ev[3], st));
     if (e->surface) {
@@ -317,253 +319,8 @@ int check_args(pbp_engine *e, const void *a, int64_t n) {
 
 }  // namespace
 
-// Host-side compilation of a model description into the kernels' tables (no CUDA calls).
-struct HostTables {
-    std::vector<DevJoint> joints;
-    std::vector<DevGeom> geoms;
-    std::vector<BpGeom> bpgeoms;
-    std::vector<BpBox> bpboxes;
-    std::vector<float4> verts;
-    std::vector<uint16_t> sup_cells, sup_lists;
-    std::vector<int32_t> jgeoms;
-    std::vector<BpPair> bppairs;
-    std::vector<BpGroup> groups;
-    std::vector<int32_t> pair_orig;
-    std::vector<PairPath> paths;
-    std::vector<uint8_t> pathops;
-    std::vector<int32_t> order;
-    int nmoving = 0, nsave = 0;
-};
-
-static int build_host_tables(const pbp_model_desc *d, HostTables &H) {
-    // ---- joints (+ which transforms the broadphase must keep for non-adjacent children)
-    H.joints.assign(d->njoints, DevJoint{});
-    auto &joints = H.joints;
-    for (int j = 0; j < d->njoints; j++) {
-        DevJoint &J = joints[j];
-        memset(&J, 0, sizeof J);
-        memcpy(J.P, d->joint_placement + 12 * j, sizeof J.P);
-        memcpy(J.axis, d->joint_axis + 3 * j, sizeof J.axis);
-        J.parent = d->joint_parent[j];
-        J.type = d->joint_type[j];
-        J.idx_q = d->joint_idx_q[j];
-        J.axis_code = 0;
-        for (int k = 0; k < 3; k++) {
-            const float a = J.axis[k], b = J.axis[(k + 1) % 3], c = J.axis[(k + 2) % 3];
-            if (fabsf(fabsf(a) - 1.0f) < 1e-7f && b == 0.0f && c == 0.0f) J.axis_code = k + 1;
-        }
-        J.parent_slot = -1;
-        J.save_slot = -1;
-        if (j > 0 && (J.parent < 0 || J.parent >= j)) return (fail(PBP_ERR_ARG, "joint %d: parent %d not topologically ordered", j, J.parent));
-        if (j > 0 && (J.idx_q < 0 || J.idx_q >= d->nq)) return (fail(PBP_ERR_ARG, "joint %d: idx_q %d out of range", j, J.idx_q));
-        if (j > 0 && J.type != PBP_JOINT_REVOLUTE && J.type != PBP_JOINT_PRISMATIC) return (fail(PBP_ERR_ARG, "joint %d: unsupported type %d", j, J.type));
-    }
-    int nsave = 0;
-    for (int j = 1; j < d->njoints; j++) {
-        DevJoint &J = joints[j];
-        if (J.parent == 0) J.parent_slot = -2;
-        else if (J.parent == j - 1) J.parent_slot = -1;
-        else {
-            if (joints[J.parent].save_slot < 0) joints[J.parent].save_slot = nsave++;
-            J.parent_slot = joints[J.parent].save_slot;
-        }
-    }
-    if (nsave > BP_MAX_SAVES) return (fail(PBP_ERR_CAPACITY, "kinematic tree has %d branch points (max %d)", nsave, BP_MAX_SAVES));
-
-    // ---- geometries: narrowphase view, broadphase proxies, static boxes, padded vertex table
-    H.geoms.assign(std::max(d->ngeoms, 1), DevGeom{});
-    auto &geoms = H.geoms;
-    H.bpgeoms.assign(std::max(d->ngeoms, 1), BpGeom{});
-    auto &bpgeoms = H.bpgeoms;
-    auto &bpboxes = H.bpboxes;
-    auto &verts = H.verts;
-    auto &sup_cells = H.sup_cells;
-    auto &sup_lists = H.sup_lists;
-    auto &jgeoms = H.jgeoms;
-    int nmoving = 0;
-    for (int g = 0; g < d->ngeoms; g++) {
-        DevGeom &G = geoms[g];
-        BpGeom &B = bpgeoms[g];
-        memset(&G, 0, sizeof G);
-        memset(&B, 0, sizeof B);
-        G.map_off = -1;
-        G.list_off = 0;
-        memcpy(G.P, d->geom_placement + 12 * g, sizeof G.P);
-        memcpy(G.par, d->geom_params + 4 * g, sizeof G.par);
-        const float *outer = d->geom_outer + 4 * g, *inner = d->geom_inner + 4 * g;
-        for (int i = 0; i < 3; i++)
-            if (fabsf(outer[i] - inner[i]) > 1e-6f) return (fail(PBP_ERR_ARG, "geometry %d: geom_inner must share the centre of geom_outer", g));
-        if (!(inner[3] <= outer[3])) return (fail(PBP_ERR_ARG, "geometry %d: inscribed radius exceeds enclosing radius", g));
-        memcpy(G.centre, outer, sizeof G.centre);
-        G.parent = d->geom_parent[g];
-        G.shape = d->geom_shape[g];
-        if (G.parent < 0 || G.parent >= d->njoints) return (fail(PBP_ERR_ARG, "geometry %d: bad parent joint", g));
-        if (G.shape < PBP_SHAPE_SPHERE || G.shape > PBP_SHAPE_CONVEX) return (fail(PBP_ERR_ARG, "geometry %d: bad shape %d", g, G.shape));
-        G.core_radius = (G.shape == PBP_SHAPE_SPHERE || G.shape == PBP_SHAPE_CAPSULE) ? G.par[0] : 0.f;
-        // proxy centre in the parent-joint frame (= world frame for static geometries)
-        for (int i = 0; i < 3; i++) B.c[i] = G.P[3 * i] * outer[0] + G.P[3 * i + 1] * outer[1] + G.P[3 * i + 2] * outer[2] + G.P[9 + i];
-        B.r_out = outer[3];
-        B.r_in = inner[3];
-        if (d->geom_capsule) {   // the capsule's segment doubles as the shape's "long axis" for the GJK start direction
-            const float *cp = d->geom_capsule + 8 * g;
-            const float du[3] = {cp[3] - cp[0], cp[4] - cp[1], cp[5] - cp[2]};
-            if (cp[6] > 0.f && du[0] * du[0] + du[1] * du[1] + du[2] * du[2] > 1e-10f) {
-                G.has_axis = 1;
-                for (int i = 0; i < 3; i++) { G.axis0[i] = cp[i]; G.axis1[i] = cp[3 + i]; }
-            }
-        }
-        if (d->geom_capsule && d->geom_capsule[8 * g + 7] != 0.f) {
-            const float *cp = d->geom_capsule + 8 * g;
-            B.has_cap = 1;
-            B.cap_r = cp[6];
-            for (int i = 0; i < 3; i++) {
-                B.cap0[i] = G.P[3 * i] * cp[0] + G.P[3 * i + 1] * cp[1] + G.P[3 * i + 2] * cp[2] + G.P[9 + i];
-                B.cap1[i] = G.P[3 * i] * cp[3] + G.P[3 * i + 1] * cp[4] + G.P[3 * i + 2] * cp[5] + G.P[9 + i];
-            }
-        }
-        B.slot = G.parent == 0 ? -1 : nmoving++;
-        B.box = -1;
-        if (G.parent == 0 && G.shape == PBP_SHAPE_BOX) {
-            BpBox bx;
-            memset(&bx, 0, sizeof bx);
-            memcpy(bx.R, G.P, sizeof bx.R);
-            memcpy(bx.t, G.P + 9, sizeof bx.t);
-            memcpy(bx.h, G.par, sizeof bx.h);
-            B.box = (int)bpboxes.size();
-            bpboxes.push_back(bx);
-        }
-        if (G.shape == PBP_SHAPE_CONVEX) {
-            const int off = d->geom_vert_off[g], cnt = d->geom_vert_cnt[g];
-            if (cnt < 1 || off < 0 || off + cnt > d->nverts) return (fail(PBP_ERR_ARG, "geometry %d: bad vertex range", g));
-            G.vert_off = (int)verts.size();
-            for (int i = 0; i < cnt; i++) verts.push_back(make_float4(d->verts[3 * (off + i)], d->verts[3 * (off + i) + 1], d->verts[3 * (off + i) + 2], 0.f));
-            while (verts.size() % 4) verts.push_back(verts.back());
-            G.vert_cnt = (int)verts.size() - G.vert_off;
-            // exact support map of this hull (shared by geometries with identical vertex data)
-            int same = -1;
-            for (int h = 0; h < g && same < 0; h++)
-                if (geoms[h].shape == PBP_SHAPE_CONVEX && d->geom_vert_cnt[h] == cnt &&
-                    memcmp(d->verts + 3 * d->geom_vert_off[h], d->verts + 3 * off, (size_t)cnt * 12) == 0)
-                    same = h;
-            if (same >= 0) {
-                G.map_off = geoms[same].map_off;
-                G.list_off = geoms[same].list_off;
-            } else if (cnt <= 65535) {
-                const SupMap sm = build_support_map(d->verts + 3 * off, cnt);
-                if (sm.list.size() <= 65535) {
-                    G.map_off = (int)sup_cells.size();
-                    G.list_off = (int)sup_lists.size();
-                    sup_cells.insert(sup_cells.end(), sm.cell_off.begin(), sm.cell_off.end());
-                    sup_lists.insert(sup_lists.end(), sm.list.begin(), sm.list.end());
-                }
-            }
-        }
-    }
-    while (sup_cells.empty() || sup_cells.size() % 8) sup_cells.push_back(0);
-    while (sup_lists.empty() || sup_lists.size() % 8) sup_lists.push_back(0);
-    // moving geometries grouped by parent joint (the broadphase places them right after that joint)
-    for (int j = 1; j < d->njoints; j++) {
-        joints[j].geom_begin = (int)jgeoms.size();
-        for (int g = 0; g < d->ngeoms; g++)
-            if (geoms[g].parent == j) jgeoms.push_back(g);
-        joints[j].geom_end = (int)jgeoms.size();
-    }
-    if (verts.empty()) verts.push_back(make_float4(0, 0, 0, 0));
-    if (bpboxes.empty()) bpboxes.push_back(BpBox{});
-    if (jgeoms.empty()) jgeoms.push_back(0);
-    H.nmoving = nmoving;
-    H.nsave = nsave;
-
-    // ---- pairs: internal order (moving-moving first, then one contiguous group per static
-    //      geometry), broadphase recipe, joint path for the item setup, bin order
-    const int np1 = std::max(d->npairs, 1);
-    struct PairKey { int cls, sidx, orig; };
-    std::vector<PairKey> keys(d->npairs);
-    for (int p = 0; p < d->npairs; p++) {
-        const int a = d->pairs[2 * p], b = d->pairs[2 * p + 1];
-        if (a < 0 || b < 0 || a >= d->ngeoms || b >= d->ngeoms || a == b) return (fail(PBP_ERR_ARG, "pair %d: bad geometry ids", p));
-        const bool sa = bpgeoms[a].slot < 0, sb = bpgeoms[b].slot < 0;
-        PairKey k{GRP_GENERIC, 0, p};
-        if (!sa && !sb) k = PairKey{GRP_MOVING, 0, p};
-        else if (sa != sb) {
-            const int st = sa ? a : b;
-            if (bpgeoms[st].box >= 0) k = PairKey{GRP_STATIC_BOX, bpgeoms[st].box, p};
-            else k = PairKey{GRP_STATIC_POINT, st, p};
-        }
-        keys[p] = k;
-    }
-    std::stable_sort(keys.begin(), keys.end(), [](const PairKey &x, const PairKey &y) {
-        return x.cls != y.cls ? x.cls < y.cls : x.sidx < y.sidx;
-    });
-    H.bppairs.assign(np1, BpPair{});
-    auto &bppairs = H.bppairs;
-    auto &groups = H.groups;
-    H.pair_orig.assign(np1, 0);
-    auto &pair_orig = H.pair_orig;
-    H.paths.assign(np1, PairPath{});
-    auto &paths = H.paths;
-    auto &pathops = H.pathops;
-    H.order.assign(np1, 0);
-    auto &order = H.order;
-    std::vector<long> cost(np1, 0);
-    auto chain_to_root = [&](int j) {  // joints from the root down to j (empty for the universe)
-        std::vector<int> c;
-        for (; j > 0; j = joints[j].parent) c.push_back(j);
-        std::reverse(c.begin(), c.end());
-        return c;
-    };
-    for (int p = 0; p < d->npairs; p++) {
-        const PairKey &key = keys[p];
-        const int a = d->pairs[2 * key.orig], b = d->pairs[2 * key.orig + 1];
-        pair_orig[p] = key.orig;
-        if (groups.empty() || groups.back().cls != key.cls || (key.cls != GRP_MOVING && key.cls != GRP_GENERIC && groups.back().sidx != key.sidx))
-            groups.push_back(BpGroup{key.cls, key.sidx, p, p});
-        groups.back().end = p + 1;
-        BpPair &P = bppairs[p];
-        memset(&P, 0, sizeof P);
-        P.a = (uint8_t)a;
-        P.b = (uint8_t)b;
-        P.slot_a = (int16_t)bpgeoms[a].slot;
-        P.slot_b = (int16_t)bpgeoms[b].slot;
-        const int sha = geoms[a].shape, shb = geoms[b].shape;
-        if (sha == PBP_SHAPE_SPHERE && shb == PBP_SHAPE_SPHERE) {
-            P.kind = BP_EXACT_SPHERES;
-            P.r_out = P.r_in = geoms[a].par[0] + geoms[b].par[0];
-        } else if (bpgeoms[a].box >= 0) {
-            P.kind = BP_BOX_A;
-            P.r_out = bpgeoms[b].r_out;
-            P.r_in = bpgeoms[b].r_in;
-        } else if (bpgeoms[b].box >= 0) {
-            P.kind = BP_BOX_B;
-            P.r_out = bpgeoms[a].r_out;
-            P.r_in = bpgeoms[a].r_in;
-        } else {
-            P.kind = BP_SPHERES;
-            P.r_out = bpgeoms[a].r_out + bpgeoms[b].r_out;
-            P.r_in = bpgeoms[a].r_in + bpgeoms[b].r_in;
-        }
-        // surface semantics: a pair where one shape could be enclosed by the other's surface is never
-        // "certainly colliding" by its inscribed spheres (the enclosed placement is the free one)
-        if (d->pair_enclose && d->pair_enclose[key.orig] && P.kind != BP_EXACT_SPHERES) P.r_in = -1e30f;
-        const std::vector<int> ca = chain_to_root(geoms[a].parent), cb = chain_to_root(geoms[b].parent);
-        size_t common = 0;
-        while (common < ca.size() && common < cb.size() && ca[common] == cb[common]) common++;
-        paths[p].off = (int32_t)pathops.size();
-        paths[p].n_trunk = (uint8_t)common;
-        paths[p].n_a = (uint8_t)(ca.size() - common);
-        paths[p].n_b = (uint8_t)(cb.size() - common);
-        for (size_t i = 0; i < ca.size(); i++) pathops.push_back((uint8_t)ca[i]);
-        for (size_t i = common; i < cb.size(); i++) pathops.push_back((uint8_t)cb[i]);
-        cost[p] = 8 + geoms[a].vert_cnt + geoms[b].vert_cnt;
-        order[p] = p;
-    }
-    if (groups.empty()) groups.push_back(BpGroup{GRP_GENERIC, 0, 0, 0});
-    if (pathops.empty()) pathops.push_back(0);
-    while (pathops.size() % 4) pathops.push_back(0);
-    std::stable_sort(order.begin(), order.begin() + d->npairs, [&](int x, int y) { return cost[x] > cost[y]; });
-
-    return 0;
-}
+#define PBP_HOST_FAIL fail
+#include "pbp_host_tables.h"
 
 // CUDA source of the model-specialised broadphase (empty string when the model does not qualify).
 static std::string specialised_broadphase_source(const pbp_model_desc *d, const HostTables &H) {
@@ -636,7 +393,8 @@ void pbp_engine_destroy(pbp_engine *e) {
                             &e->d_bin_group, &e->d_bin_sample, &e->d_bin_T, &e->d_ctrl, &e->d_counts, &e->d_desc_group,
                             &e->d_desc_frac, &e->d_desc_sample, &e->d_scratch_i32, &e->d_scratch_u8, &e->d_cub, &e->d_sel,
                             &e->d_io_q, &e->d_io_q2, &e->d_io_hit, &e->d_io_f32, &e->d_io_i32, &e->d_ik_tables, &e->d_ws_oMi, &e->d_ws_oMg, &e->d_ws_dist,
-                            &e->d_ws_p1, &e->d_ws_p2, &e->d_ws_nrm, &e->d_pairs_orig, &e->d_planes, &e->d_plane_idx, &e->d_surf_tol, &e->d_pair_enclose};
+                            &e->d_ws_p1, &e->d_ws_p2, &e->d_ws_nrm, &e->d_pairs_orig, &e->d_planes, &e->d_plane_idx, &e->d_surf_tol, &e->d_pair_enclose, &e->d_kverts, &e->d_ksupcells,
+                            &e->d_ksuplists, &e->d_mverts, &e->d_tris};
     for (DeviceBuffer *b : bufs) b->release();
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     e->h_io_hit.release(); e->h_io_f32.release(); e->h_io_i32.release();
@@ -765,12 +523,11 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     e->dm.n_sup_cells = (int)sup_cells.size();
     e->dm.n_sup_lists = (int)sup_lists.size();
     {
-        // surface semantics tables (optional): planes as float4, per-geometry (offset, count), dent
-        // depth, enclosure flags in INTERNAL pair order
+        // surface semantics tables (optional): planes as float4, per-geometry (offset, count), tolerance,
+        // pair flags in INTERNAL pair order, inner cores, mesh vertices and triangles
         std::vector<float> pl(4, 0.f), tol(std::max(d->ngeoms, 1), 0.f);
         std::vector<int32_t> pidx(2 * (size_t)std::max(d->ngeoms, 1), 0);
-        std::vector<uint8_t> flags(np1, 0);
-        const bool have = d->planes && d->geom_plane_off && d->geom_plane_cnt && d->pair_enclose && d->nplanes > 0;
+        const bool have = d->planes && d->geom_plane_off && d->geom_plane_cnt && d->nplanes > 0;
         if (have) {
             pl.assign(d->planes, d->planes + 4 * (size_t)d->nplanes);
             for (int g = 0; g < d->ngeoms; g++) {
@@ -780,17 +537,11 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
                     return bail(fail(PBP_ERR_ARG, "geometry %d: plane range outside [0, %d)", g, d->nplanes));
                 if (d->geom_surface_tol) tol[g] = d->geom_surface_tol[g];
             }
-            for (int p = 0; p < d->npairs; p++) {
-                const uint8_t f = d->pair_enclose[pair_orig[p]] & 3;
-                const int a = bppairs[p].a, b = bppairs[p].b;
-                if (((f & 1) && pidx[2 * a + 1] == 0) || ((f & 2) && pidx[2 * b + 1] == 0))
-                    return bail(fail(PBP_ERR_ARG, "pair %d: enclosure flag on a geometry without hull planes", pair_orig[p]));
-                flags[p] = f;
-                if (f) e->surface = true;
-            }
         }
+        for (int p = 0; p < d->npairs; p++)
+            if (H.pair_flags[p]) e->surface = true;
         if ((rc = upload(e->d_planes, pl.data(), pl.size() * 4)) || (rc = upload(e->d_plane_idx, pidx.data(), pidx.size() * 4)) ||
-            (rc = upload(e->d_surf_tol, tol.data(), tol.size() * 4)) || (rc = upload(e->d_pair_enclose, flags.data(), flags.size())))
+            (rc = upload(e->d_surf_tol, tol.data(), tol.size() * 4)) || (rc = upload(e->d_pair_enclose, H.pair_flags.data(), H.pair_flags.size())))
             return bail(rc);
         e->dm.planes = e->d_planes.as<float4>();
         e->dm.plane_idx = e->d_plane_idx.as<int2>();
@@ -798,6 +549,32 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
         e->dm.pair_enclose = e->d_pair_enclose.as<uint8_t>();
         e->dm.surface = e->surface ? 1 : 0;
         e->dm.nplanes = (int)(pl.size() / 4);
+        e->dm.has_tris = H.has_tris ? 1 : 0;
+        if (H.has_tris) {
+            if ((rc = upload(e->d_kverts, H.kverts.data(), H.kverts.size() * sizeof(float4))) ||
+                (rc = upload(e->d_ksupcells, H.ksup_cells.data(), H.ksup_cells.size() * 2)) ||
+                (rc = upload(e->d_ksuplists, H.ksup_lists.data(), H.ksup_lists.size() * 2)) ||
+                (rc = upload(e->d_mverts, H.mverts.data(), H.mverts.size() * sizeof(float4))) ||
+                (rc = upload(e->d_tris, H.tris.data(), H.tris.size() * sizeof(int4))))
+                return bail(rc);
+            e->dm.kverts = e->d_kverts.as<float4>();
+            e->dm.ksup_cells = e->d_ksupcells.as<uint16_t>();
+            e->dm.ksup_lists = e->d_ksuplists.as<uint16_t>();
+            e->dm.nkverts_padded = (int)H.kverts.size();
+            e->dm.n_ksup_cells = (int)H.ksup_cells.size();
+            e->dm.n_ksup_lists = (int)H.ksup_lists.size();
+            e->dm.mverts = e->d_mverts.as<float4>();
+            e->dm.tris = e->d_tris.as<int4>();
+        } else {
+            e->dm.kverts = e->dm.verts;
+            e->dm.ksup_cells = e->dm.sup_cells;
+            e->dm.ksup_lists = e->dm.sup_lists;
+            e->dm.nkverts_padded = e->dm.nverts_padded;
+            e->dm.n_ksup_cells = e->dm.n_sup_cells;
+            e->dm.n_ksup_lists = e->dm.n_sup_lists;
+            e->dm.mverts = e->dm.verts;
+            e->dm.tris = nullptr;
+        }
     }
     e->dm.q_lower = e->d_qlim.as<float>();
     e->dm.q_upper = e->d_qlim.as<float>() + d->nq;
@@ -814,9 +591,14 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
                  align16((size_t)np1 * sizeof(BpPair)) + align16((size_t)np1 * sizeof(PairPath)) + tile_tables + 16;
     const size_t np_tables = align16((size_t)std::max(d->ngeoms, 1) * sizeof(DevGeom)) + align16((size_t)np1 * sizeof(BpPair)) + tile_tables + 16;
     const size_t vert_bytes = align16((size_t)e->nverts_padded * sizeof(float4)) + align16(sup_cells.size() * 2) + align16(sup_lists.size() * 2);
-    e->verts_in_smem = np_tables + vert_bytes <= 110 * 1024;   // two narrowphase blocks per SM must fit in 227 KB
-    e->smem_np = np_tables + (e->verts_in_smem ? vert_bytes : 0);
-    if (e->smem_bp > max_optin || e->smem_np > max_optin || e->smem_is > max_optin)
+    // boolean queries stage the inner cores, distance queries the hulls (the same tables when no geometry is a surface)
+    const size_t kvert_bytes = H.has_tris ? align16(H.kverts.size() * sizeof(float4)) + align16(H.ksup_cells.size() * 2) + align16(H.ksup_lists.size() * 2)
+                                          : vert_bytes;
+    e->verts_in_smem = np_tables + kvert_bytes <= 110 * 1024;   // two narrowphase blocks per SM must fit in 227 KB
+    e->smem_np = np_tables + (e->verts_in_smem ? kvert_bytes : 0);
+    e->verts_in_smem_dist = np_tables + vert_bytes <= 110 * 1024;
+    e->smem_np_dist = np_tables + (e->verts_in_smem_dist ? vert_bytes : 0);
+    if (e->smem_bp > max_optin || e->smem_np > max_optin || e->smem_np_dist > max_optin || e->smem_is > max_optin)
         return bail(fail(PBP_ERR_CAPACITY, "model tables exceed shared memory (%zu / %zu / %zu bytes)", e->smem_bp, e->smem_is, e->smem_np));
     // The dynamic shared-memory cap is a per-function attribute shared by every engine of the
     // process: raise it to the device's opt-in maximum once (a per-engine value would lower
@@ -839,33 +621,20 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     SET_SMEM((k_narrowphase<MODE_DIST, false>));
     SET_SMEM(k_fk_output);
 #undef SET_SMEM
-    // (static __shared__ chunk directory: leave room for it under the opt-in cap)
-#define SET_SMEM_SR(kern) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_optin - 4096))
+    // (static __shared__ chunk directory and per-warp triangle lists: leave room for them under the opt-in cap)
+    const int sr_static = 32 * 1024;
+#define SET_SMEM_SR(kern) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_optin - sr_static))
     SET_SMEM_SR((k_surface_refine<MODE_BOOL, true>));
     SET_SMEM_SR((k_surface_refine<MODE_BOOL_ALL, true>));
     SET_SMEM_SR((k_surface_refine<MODE_DIST, true>));
 #undef SET_SMEM_SR
     e->smem_sr = vert_bytes + align16((size_t)e->dm.nplanes * sizeof(float4));
-    e->sr_tables_in_smem = e->smem_sr + 4096 <= max_optin;   // one 16-warp block per SM is enough for this kernel
+    e->sr_tables_in_smem = e->smem_sr + sr_static <= max_optin;   // one 16-warp block per SM is enough for this kernel
     {
         int occ_sr = 1;
         if (e->sr_tables_in_smem) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sr, k_surface_refine<MODE_BOOL, true>, SR_THREADS, e->smem_sr));
         else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sr, k_surface_refine<MODE_BOOL, false>, SR_THREADS, 0));
         e->sr_blocks = e->num_sms * std::max(occ_sr, 1);
-    }
-    // (this kernel also has a few static __shared__ words: leave room for them under the opt-in cap)
-#define SET_SMEM_POOL(kern) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_optin - 1024))
-    SET_SMEM_POOL((k_narrowphase_pool<MODE_BOOL>));
-    SET_SMEM_POOL((k_narrowphase_pool<MODE_BOOL_ALL>));
-    SET_SMEM_POOL((k_narrowphase_pool<MODE_DIST>));
-#undef SET_SMEM_POOL
-    e->smem_np_pool = np_tables + vert_bytes + (size_t)PF_WORDS * POOL * 4 + (size_t)POOL * 12 + POOL + (size_t)POOL * 4 +
-                      3 * (NP_THREADS / 32) * 4 + 64;
-    e->np_pool = e->verts_in_smem && e->smem_np_pool <= max_optin - 1024 && getenv("PBP_NP_POOL") && atoi(getenv("PBP_NP_POOL")) != 0 && !e->surface;
-    if (e->np_pool) {
-        int occ_pool = 1;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pool, k_narrowphase_pool<MODE_BOOL>, NP_THREADS, e->smem_np_pool));
-        e->np_pool_blocks = e->num_sms * std::max(occ_pool, 1);
     }
     int occ = 1;
     if (e->verts_in_smem)

@@ -317,7 +317,11 @@ __device__ __forceinline__ float3 gjk_start_direction(const DevGeom &GA, const D
 // Support phase of one GJK iteration: new support point of A - B in direction -v, then the
 // termination tests that only need it.  T: placement of B in A's frame.  Returns true when the
 // item is finished (out is then valid); otherwise s.w holds the point for the simplex phase.
-// WANT_DIST = false: finish as soon as "distance > margin" or "distance <= margin" is certain.
+// WANT_DIST = false: finish as soon as "distance > cut" or "distance <= margin" is certain, where
+//                    cut = max(bound, margin): solids pass bound = 0 (cut = margin); surface geometries
+//                    run on their inner cores and pass margin + eps, eps = how far the hulls may lie
+//                    outside the cores -- an item that converges between margin and cut is UNDECIDED
+//                    (out.hit = 0, out.far = 0) and goes to the triangle stage (pbp_surface.cuh).
 // WANT_DIST = true : run to convergence unless the pair is certainly farther than `bound`.
 template <bool WANT_DIST, bool TRACK = false>
 __device__ __forceinline__ bool gjk_support_phase(const ShapeRef &A, const ShapeRef &B, const float *T, GjkState &s, float margin,
@@ -325,7 +329,7 @@ __device__ __forceinline__ bool gjk_support_phase(const ShapeRef &A, const Shape
     const float3 v = s.v;
     const float vv = s.vv;
     const int n = s.n;
-    const float cut = WANT_DIST ? bound : margin;
+    const float cut = WANT_DIST ? bound : fmaxf(bound, margin);
     const float3 db = make_float3(fmaf(T[0], v.x, fmaf(T[3], v.y, T[6] * v.z)), fmaf(T[1], v.x, fmaf(T[4], v.y, T[7] * v.z)),
                                   fmaf(T[2], v.x, fmaf(T[5], v.y, T[8] * v.z)));
     // one copy of the support code serves both shapes (instruction-cache footprint)

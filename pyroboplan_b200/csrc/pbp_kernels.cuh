@@ -18,6 +18,7 @@
 #include <limits.h>
 
 #include "pbp_gjk.cuh"
+#include "pbp_surface.cuh"
 
 namespace pbp {
 
@@ -72,12 +73,6 @@ struct Outputs {
     int32_t *first_bad;    // [groups] or NULL   (scratch semantics: INT_MAX = none)
 };
 
-enum { MODE_BOOL = 0, MODE_BOOL_ALL = 1, MODE_DIST = 2 };
-// bit set in Bins::group by the narrowphase on a hull hit that k_surface_refine has to decide
-constexpr int32_t SR_PARKED = 0x40000000;
-// MODE_BOOL      verdict only; a state stops at its first certain hit, decided groups are skipped
-// MODE_BOOL_ALL  verdict + first_pair / first_bad: every pair of every state is resolved
-// MODE_DIST      verdict + min distance: pairs are resolved unless certainly farther than the bound
 
 // Copy a model table into shared memory.  Both pointers are 16-byte aligned (cudaMalloc bases, smem
 // carved with align16): 16-byte loads, four in flight per thread -- a word-by-word loop is a chain
@@ -411,61 +406,6 @@ __device__ __forceinline__ bool next_tile(uint32_t *tile_counter, const uint32_t
 }
 
 // ------------------------------------------------------------------------------------------
-// Surface semantics: can this hull hit be an enclosure at all?
-// ------------------------------------------------------------------------------------------
-// A shape wholly inside a mesh SURFACE does not collide with it (k_surface_refine below).  Most hull
-// hits of a flagged pair are ordinary partial overlaps, and one direction d in which the would-be
-// inner shape reaches at least as far as the would-be outer one, h_inner(d) + padding >= h_outer(d),
-// proves that.  Tried, per flagged role: the line between the proxy centres (the inner shape pokes
-// out on the side its centre is displaced to) and both directions of the inner shape's long axis
-// (a finger half inside a link pokes out with one end).  Two support evaluations per direction, on
-// the lane that found the hit; only the items no direction settles are parked for the plane test.
-#ifndef PBP_SR_AXIS_DIRS
-#define PBP_SR_AXIS_DIRS 0   // measured on config 2: the centre line settles 73 % of the flagged hull hits, the axis directions 1 % more
-#endif
-__device__ __forceinline__ float support_value(const ShapeRef &S, float3 d, float radius, float len) {
-    const float3 sl = support_local(S, d);
-    return dot3(d, sl) + radius * len;
-}
-__device__ __forceinline__ float support_value_placed(const ShapeRef &S, const float *T, float3 d, float radius, float len) {
-    const float3 dl = make_float3(fmaf(T[0], d.x, fmaf(T[3], d.y, T[6] * d.z)), fmaf(T[1], d.x, fmaf(T[4], d.y, T[7] * d.z)),
-                                  fmaf(T[2], d.x, fmaf(T[5], d.y, T[8] * d.z)));
-    const float3 sl = support_local(S, dl);
-    return dot3(d, se3_act(T, sl.x, sl.y, sl.z)) + radius * len;
-}
-__device__ __noinline__ bool may_be_enclosed(int fl, const DevGeom &GA, const DevGeom &GB, const ShapeRef &A, const ShapeRef &B, const float *T,
-                                             float padding) {
-    const float3 ca = make_float3(GA.centre[0], GA.centre[1], GA.centre[2]);
-    const float3 cb = se3_act(T, GB.centre[0], GB.centre[1], GB.centre[2]);
-    float3 d = sub3(cb, ca);
-    if (!(dot3(d, d) > 1e-12f)) d = make_float3(1.f, 0.f, 0.f);
-    if (fl & 1) {   // b inside a's surface?
-        const float3 p0 = se3_act(T, GB.axis0[0], GB.axis0[1], GB.axis0[2]), p1 = se3_act(T, GB.axis1[0], GB.axis1[1], GB.axis1[2]);
-        const float3 u = sub3(p1, p0);
-        bool out = false;
-#pragma unroll 1
-        for (int k = 0; k < (PBP_SR_AXIS_DIRS && GB.has_axis ? 3 : 1) && !out; k++) {
-            const float3 dir = k == 0 ? d : (k == 1 ? u : make_float3(-u.x, -u.y, -u.z));
-            const float len = sqrtf(dot3(dir, dir));
-            out = support_value_placed(B, T, dir, GB.core_radius, len) + padding * len >= support_value(A, dir, GA.core_radius, len);
-        }
-        if (!out) return true;
-    }
-    if (fl & 2) {   // a inside b's surface?
-        const float3 u = make_float3(GA.axis1[0] - GA.axis0[0], GA.axis1[1] - GA.axis0[1], GA.axis1[2] - GA.axis0[2]);
-        bool out = false;
-#pragma unroll 1
-        for (int k = 0; k < (PBP_SR_AXIS_DIRS && GA.has_axis ? 3 : 1) && !out; k++) {
-            const float3 dir = k == 0 ? make_float3(-d.x, -d.y, -d.z) : (k == 1 ? u : make_float3(-u.x, -u.y, -u.z));
-            const float len = sqrtf(dot3(dir, dir));
-            out = support_value(A, dir, GA.core_radius, len) + padding * len >= support_value_placed(B, T, dir, GB.core_radius, len);
-        }
-        if (!out) return true;
-    }
-    return false;
-}
-
-// ------------------------------------------------------------------------------------------
 // Item setup: T = oMg[a]^-1 * oMg[b] for every undecided (state, pair) item
 // ------------------------------------------------------------------------------------------
 template <int MODE>
@@ -499,15 +439,15 @@ k_item_setup(DevModel M, StateSource src, float padding, Outputs out, Bins bins,
         const uint8_t *ops = M.path_ops + path.off;   // tiny, L1/L2 resident, warp-uniform addresses
         const DevGeom &GA = sg[sp[p].a];
         const DevGeom &GB = sg[sp[p].b];
-        // shapes of the pair (hull tables read through L1: warp-uniform base addresses)
-        ShapeRef A, B;
-        A.shape = GA.shape; A.p0 = GA.par[0]; A.p1 = GA.par[1]; A.p2 = GA.par[2];
-        A.verts = M.verts + GA.vert_off; A.nverts = GA.vert_cnt;
-        A.cell_off = GA.map_off >= 0 ? M.sup_cells + GA.map_off : nullptr; A.cell_list = M.sup_lists + GA.list_off;
-        B.shape = GB.shape; B.p0 = GB.par[0]; B.p1 = GB.par[1]; B.p2 = GB.par[2];
-        B.verts = M.verts + GB.vert_off; B.nverts = GB.vert_cnt;
-        B.cell_off = GB.map_off >= 0 ? M.sup_cells + GB.map_off : nullptr; B.cell_list = M.sup_lists + GB.list_off;
+        // shapes of the pair (tables read through L1: warp-uniform base addresses): boolean queries run
+        // on the inner cores of surface geometries, distance queries on the hulls (pbp_surface.cuh)
+        SurfTables tab{};
+        tab.hverts = M.verts; tab.hcells = M.sup_cells; tab.hlists = M.sup_lists;
+        tab.kverts = M.kverts; tab.kcells = M.ksup_cells; tab.klists = M.ksup_lists;
+        const ShapeRef A = MODE == MODE_DIST ? hull_shape(tab, GA) : core_shape(tab, GA);
+        const ShapeRef B = MODE == MODE_DIST ? hull_shape(tab, GB) : core_shape(tab, GB);
         const float radii = GA.core_radius + GB.core_radius;
+        const float eps_pair = pair_eps(GA, GB);
         for (uint32_t base = begin; base < end; base += 32) {
             const uint32_t idx = base + lane;
             bool keep = idx < end;
@@ -565,7 +505,7 @@ k_item_setup(DevModel M, StateSource src, float padding, Outputs out, Bins bins,
                 const float margin = padding + radii;
                 const float bound = MODE == MODE_DIST ? out.min_dist[group] + radii : 0.f;
                 const bool finished = (MODE == MODE_DIST) ? gjk_support_phase<true>(A, B, R, gs, margin, bound, go)
-                                                          : gjk_support_phase<false>(A, B, R, gs, margin, 0.f, go);
+                                                          : gjk_support_phase<false>(A, B, R, gs, margin, margin + eps_pair, go);
                 if (finished) keep = false;   // at n == 0 the only exit is "certainly farther than the cut"
             }
             // compact the survivors to the front of the bin (warp-aggregated slot reservation)
@@ -608,18 +548,24 @@ __global__ void __launch_bounds__(NP_THREADS, PBP_NP_MIN_BLOCKS)
 k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk_cursor, bool has_sample) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *ptr = smem_raw;
-    float4 *sv = reinterpret_cast<float4 *>(ptr);        ptr += TABLES_IN_SMEM ? align16((size_t)M.nverts_padded * sizeof(float4)) : 0;
-    uint16_t *scell = reinterpret_cast<uint16_t *>(ptr); ptr += TABLES_IN_SMEM ? align16((size_t)M.n_sup_cells * 2) : 0;
-    uint16_t *slist = reinterpret_cast<uint16_t *>(ptr); ptr += TABLES_IN_SMEM ? align16((size_t)M.n_sup_lists * 2) : 0;
+    // boolean queries run on the inner cores of surface geometries, distance queries on the hulls
+    constexpr bool CORES = MODE != MODE_DIST;
+    const float4 *gverts = CORES ? M.kverts : M.verts;
+    const uint16_t *gcells = CORES ? M.ksup_cells : M.sup_cells, *glists = CORES ? M.ksup_lists : M.sup_lists;
+    const int nv = CORES ? M.nkverts_padded : M.nverts_padded, ncell = CORES ? M.n_ksup_cells : M.n_sup_cells,
+              nlist = CORES ? M.n_ksup_lists : M.n_sup_lists;
+    float4 *sv = reinterpret_cast<float4 *>(ptr);        ptr += TABLES_IN_SMEM ? align16((size_t)nv * sizeof(float4)) : 0;
+    uint16_t *scell = reinterpret_cast<uint16_t *>(ptr); ptr += TABLES_IN_SMEM ? align16((size_t)ncell * 2) : 0;
+    uint16_t *slist = reinterpret_cast<uint16_t *>(ptr); ptr += TABLES_IN_SMEM ? align16((size_t)nlist * 2) : 0;
     DevGeom *sg = reinterpret_cast<DevGeom *>(ptr);      ptr += align16((size_t)max(M.ngeoms, 1) * sizeof(DevGeom));
     BpPair *sp = reinterpret_cast<BpPair *>(ptr);        ptr += align16((size_t)max(M.npairs, 1) * sizeof(BpPair));
     uint32_t *prefix = reinterpret_cast<uint32_t *>(ptr); ptr += align16(((size_t)M.npairs + 1) * 4);   // items before bin k
     int32_t *order = reinterpret_cast<int32_t *>(ptr);   ptr += align16((size_t)max(M.npairs, 1) * 4);
 
     if (TABLES_IN_SMEM) {
-        stage_words(sv, M.verts, M.nverts_padded * (int)sizeof(float4));
-        stage_words(scell, M.sup_cells, M.n_sup_cells * 2);
-        stage_words(slist, M.sup_lists, M.n_sup_lists * 2);
+        stage_words(sv, gverts, nv * (int)sizeof(float4));
+        stage_words(scell, gcells, ncell * 2);
+        stage_words(slist, glists, nlist * 2);
     }
     stage_words(sg, M.geoms, M.ngeoms * (int)sizeof(DevGeom));
     stage_words(sp, M.bppairs, M.npairs * (int)sizeof(BpPair));
@@ -645,9 +591,9 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
 
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const float4 *verts = TABLES_IN_SMEM ? sv : M.verts;
-    const uint16_t *cells = TABLES_IN_SMEM ? scell : M.sup_cells;
-    const uint16_t *lists = TABLES_IN_SMEM ? slist : M.sup_lists;
+    const float4 *verts = TABLES_IN_SMEM ? sv : gverts;
+    const uint16_t *cells = TABLES_IN_SMEM ? scell : gcells;
+    const uint16_t *lists = TABLES_IN_SMEM ? slist : glists;
     const int64_t stride = (int64_t)M.npairs * bins.cap;
     const uint32_t total = prefix[M.npairs];
 
@@ -715,19 +661,35 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
         //      the simplex slot of a lane's last trip.  (PBP_NP_LOCKSTEP=0 restores the older
         //      policy: per trip, run only the phase most lanes are waiting for.)
         auto publish = [&](const GjkOut &r, float radii) {
-            // (distance mode: only OVERLAPPING hulls can be an enclosure; a pair merely within the
-            // padding keeps its measured distance)
-            if (r.hit && M.surface && M.pair_enclose[p] && (MODE != MODE_DIST || r.dist - radii <= 0.f)) {
-                // surface semantics: one shape of this pair could be enclosed by the other's surface,
-                // which is the free placement -- k_surface_refine decides the parked item (all its
-                // lanes busy with such items, instead of one lane of this warp)
-                bins.group[slot] = group | SR_PARKED;
-                return;
-            }
+            const int fl = M.has_tris ? M.pair_enclose[p] : 0;
             if (MODE == MODE_DIST) {
+                if (fl & PAIR_SURFACE) {
+                    // the hull distance is a lower bound of the surface distance; hull distance + eps an upper
+                    // bound (through the cores) unless one shape may be enclosed by the other.  The refine
+                    // kernel settles the items that can define the state's minimum.
+                    if (r.far) return;
+                    const float dh = fmaxf(r.dist - radii, 0.f);
+                    const float eps = pair_eps(sg[sp[p].a], sg[sp[p].b]);
+                    if (!((fl & PAIR_ENCLOSE) && r.dist <= 0.f) && !(fl & PAIR_NOCORE))
+                        atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(dh + eps));
+                    bins.group[slot] = group | SR_DOUBT;
+                    return;
+                }
                 if (r.hit) out.hit[group] = 1;
                 atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(fmaxf(r.dist - radii, 0.f)));
-            } else if (r.hit) {
+                return;
+            }
+            if (fl & PAIR_SURFACE) {
+                if (r.hit && (fl & PAIR_NOCORE)) { bins.group[slot] = group | SR_DOUBT; return; }   // a hull hit proves nothing
+                if (r.hit && (fl & PAIR_ENCLOSE)) {
+                    // one shape of this pair could be enclosed by the other's surface, which is the free
+                    // placement -- the refine kernel decides (all its lanes busy with such items)
+                    bins.group[slot] = group | SR_PARKED;
+                    return;
+                }
+                if (!r.hit && !r.far) { bins.group[slot] = group | SR_DOUBT; return; }   // between the bounds: the triangles decide
+            }
+            if (r.hit) {
                 out.hit[group] = 1;
                 if (MODE == MODE_BOOL_ALL) {
                     if (out.first_pair) atomicMin(out.first_pair + group, M.pair_orig[p]);
@@ -740,15 +702,16 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
             const DevGeom &GB = sg[sp[p].b];
             ShapeRef A, B;
             A.shape = GA.shape; A.p0 = GA.par[0]; A.p1 = GA.par[1]; A.p2 = GA.par[2];
-            A.verts = verts + GA.vert_off; A.nverts = GA.vert_cnt;
-            A.cell_off = GA.map_off >= 0 ? cells + GA.map_off : nullptr; A.cell_list = lists + GA.list_off;
+            A.verts = verts + (CORES ? GA.kvert_off : GA.vert_off); A.nverts = CORES ? GA.kvert_cnt : GA.vert_cnt;
+            const int moa = CORES ? GA.kmap_off : GA.map_off, mob = CORES ? GB.kmap_off : GB.map_off;
+            A.cell_off = moa >= 0 ? cells + moa : nullptr; A.cell_list = lists + (CORES ? GA.klist_off : GA.list_off);
             B.shape = GB.shape; B.p0 = GB.par[0]; B.p1 = GB.par[1]; B.p2 = GB.par[2];
-            B.verts = verts + GB.vert_off; B.nverts = GB.vert_cnt;
-            B.cell_off = GB.map_off >= 0 ? cells + GB.map_off : nullptr; B.cell_list = lists + GB.list_off;
+            B.verts = verts + (CORES ? GB.kvert_off : GB.vert_off); B.nverts = CORES ? GB.kvert_cnt : GB.vert_cnt;
+            B.cell_off = mob >= 0 ? cells + mob : nullptr; B.cell_list = lists + (CORES ? GB.klist_off : GB.list_off);
             radii = GA.core_radius + GB.core_radius;
             const float margin = padding + radii;
             return (MODE == MODE_DIST) ? gjk_support_phase<true>(A, B, T, s, margin, bound, r)
-                                       : gjk_support_phase<false>(A, B, T, s, margin, 0.f, r);
+                                       : gjk_support_phase<false>(A, B, T, s, margin, margin + pair_eps(GA, GB), r);
         };
         auto simplex = [&](GjkOut &r, float &radii) {
             const float margin = padding + sg[sp[p].a].core_radius + sg[sp[p].b].core_radius;
@@ -793,308 +756,16 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
 }
 
 // ------------------------------------------------------------------------------------------
-// Narrowphase, block-cooperative variant: a pool of NP_THREADS items in shared memory, re-sorted
-// by phase every round
+// Surface semantics: settle the items the GJK kernels parked (pbp_surface.cuh)
 // ------------------------------------------------------------------------------------------
-// In k_narrowphase a lane owns its item from start to finish, so a warp always holds a mix of
-// lanes that need a support phase, lanes that need a simplex phase and lanes being refilled: on
-// average 13 of 32 lanes are active (ncu smsp__thread_inst_executed_per_inst_executed).  Here the
-// per-item GJK state lives in shared memory instead of registers, and every round the block
-// partitions its pool into "needs support" and "needs simplex" lists and hands list entries to
-// threads in order -- warps are (nearly) full and run ONE phase type.  The price is a
-// load/store of the 17-word state plus the 12-word placement around each phase and three
-// barriers per round.
-constexpr int POOL = NP_THREADS;          // items resident per block
-enum { PF_V = 0, PF_VV = 3, PF_W0 = 4, PF_W1 = 7, PF_W2 = 10, PF_W = 13, PF_T = 16, PF_BOUND = 28, PF_WORDS = 29 };
-
-template <int MODE>
-__global__ void __launch_bounds__(NP_THREADS, 2)
-k_narrowphase_pool(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk_cursor, bool has_sample) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned char *ptr = smem_raw;
-    float4 *sv = reinterpret_cast<float4 *>(ptr);        ptr += align16((size_t)M.nverts_padded * sizeof(float4));
-    uint16_t *scell = reinterpret_cast<uint16_t *>(ptr); ptr += align16((size_t)M.n_sup_cells * 2);
-    uint16_t *slist = reinterpret_cast<uint16_t *>(ptr); ptr += align16((size_t)M.n_sup_lists * 2);
-    DevGeom *sg = reinterpret_cast<DevGeom *>(ptr);      ptr += align16((size_t)max(M.ngeoms, 1) * sizeof(DevGeom));
-    BpPair *sp = reinterpret_cast<BpPair *>(ptr);        ptr += align16((size_t)max(M.npairs, 1) * sizeof(BpPair));
-    uint32_t *prefix = reinterpret_cast<uint32_t *>(ptr); ptr += align16(((size_t)M.npairs + 1) * 4);   // items before bin k
-    int32_t *order = reinterpret_cast<int32_t *>(ptr);   ptr += align16((size_t)max(M.npairs, 1) * 4);
-    float *pf = reinterpret_cast<float *>(ptr);          ptr += (size_t)PF_WORDS * POOL * 4;     // [PF_WORDS][POOL]
-    int32_t *pgroup = reinterpret_cast<int32_t *>(ptr);  ptr += (size_t)POOL * 4;
-    int32_t *pslot = reinterpret_cast<int32_t *>(ptr);   ptr += (size_t)POOL * 4;                // bin slot (low 32 bits suffice per pair: idx in bin)
-    int32_t *pmeta = reinterpret_cast<int32_t *>(ptr);   ptr += (size_t)POOL * 4;                // pair | n << 16 | stalls << 20 | it << 24
-    uint8_t *pphase = reinterpret_cast<uint8_t *>(ptr);  ptr += (size_t)POOL;                    // 0 free, 1 support, 2 simplex
-    uint16_t *lsup = reinterpret_cast<uint16_t *>(ptr);  ptr += (size_t)POOL * 2;
-    uint16_t *lsmp = reinterpret_cast<uint16_t *>(ptr);  ptr += (size_t)POOL * 2;
-    uint32_t *wcnt = reinterpret_cast<uint32_t *>(ptr);  ptr += 3 * (NP_THREADS / 32) * 4 + 16;  // per-warp counts: free, support, simplex
-    __shared__ uint32_t s_base, s_take, s_nsup, s_nsmp;
-    __shared__ int s_more;
-
-    stage_words(sv, M.verts, M.nverts_padded * (int)sizeof(float4));
-    stage_words(scell, M.sup_cells, M.n_sup_cells * 2);
-    stage_words(slist, M.sup_lists, M.n_sup_lists * 2);
-    stage_words(sg, M.geoms, M.ngeoms * (int)sizeof(DevGeom));
-    stage_words(sp, M.bppairs, M.npairs * (int)sizeof(BpPair));
-    stage_words(order, M.bin_order, M.npairs * 4);
-    pphase[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_more = 1;
-    __syncthreads();
-    if (threadIdx.x < 32) {   // exclusive scan of the bin counts, in bin order
-        uint32_t run = 0;
-        for (int k0 = 0; k0 < M.npairs; k0 += 32) {
-            const int k = k0 + threadIdx.x;
-            const uint32_t t = k < M.npairs ? bins.count_np[order[k]] : 0u;
-            uint32_t inc = t;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
-                if ((int)threadIdx.x >= o) inc += y;
-            }
-            if (k < M.npairs) prefix[k] = run + inc - t;
-            run += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (threadIdx.x == 0) prefix[M.npairs] = run;
-    }
-    __syncthreads();
-
-    const int tid = threadIdx.x;
-    const unsigned lane = tid & 31, warp = tid >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const int64_t stride = (int64_t)M.npairs * bins.cap;
-    const uint32_t total = prefix[M.npairs];
-    constexpr int NW = NP_THREADS / 32;
-
-    for (;;) {
-        // ---- (a) count free slots, claim that many items from the global cursor
-        const bool is_free = pphase[tid] == 0;
-        const unsigned fm = __ballot_sync(0xffffffffu, is_free);
-        if (lane == 0) wcnt[warp] = __popc(fm);
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t nfree = 0;
-            for (int w = 0; w < NW; w++) nfree += wcnt[w];
-            uint32_t base = 0, take = 0;
-            if (s_more && nfree >= (uint32_t)(POOL / 4)) {    // refill in chunks: one atomic per >= POOL/4 items
-                // guided: near the end of the launch blocks take smaller bites so that they finish together
-                const uint32_t seen = *reinterpret_cast<volatile uint32_t *>(chunk_cursor);
-                const uint32_t left = seen < total ? total - seen : 0u;
-                const uint32_t want = min(nfree, max(32u, left / (2u * gridDim.x)));
-                base = atomicAdd(chunk_cursor, want);
-                if (base >= total) s_more = 0;
-                else take = min(want, total - base);
-                if (base + want >= total) s_more = 0;
-            }
-            s_base = base;
-            s_take = take;
-        }
-        __syncthreads();
-        // ---- (b) free slots pick up their item: rank among the free slots of the block
-        if (is_free && s_take > 0) {
-            uint32_t rank = __popc(fm & lt_mask);
-            for (unsigned w = 0; w < warp; w++) rank += wcnt[w];
-            if (rank < s_take) {
-                const uint32_t gi = s_base + rank;
-                int lo = 0, hi = M.npairs;  // last bin k with prefix[k] <= gi
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (prefix[mid] <= gi) lo = mid; else hi = mid;
-                }
-                const int p = order[lo];
-                const uint32_t idx = gi - prefix[lo];
-                const int64_t slot = (int64_t)p * bins.cap + idx;
-                const int32_t g = bins.group[slot];
-                if (g >= 0 && !(MODE == MODE_BOOL && out.hit[g])) {
-                    float T[12];
-#pragma unroll
-                    for (int k = 0; k < 12; k++) T[k] = bins.T[k * stride + slot];
-                    const DevGeom &GA = sg[sp[p].a];
-                    const DevGeom &GB = sg[sp[p].b];
-                    GjkState s;
-                    gjk_init(s, gjk_start_direction(GA, GB, T));
-                    pf[(PF_V + 0) * POOL + tid] = s.v.x; pf[(PF_V + 1) * POOL + tid] = s.v.y; pf[(PF_V + 2) * POOL + tid] = s.v.z;
-                    pf[PF_VV * POOL + tid] = s.vv;
-#pragma unroll
-                    for (int k = 0; k < 12; k++) pf[(PF_T + k) * POOL + tid] = T[k];
-                    if (MODE == MODE_DIST) pf[PF_BOUND * POOL + tid] = out.min_dist[g] + GA.core_radius + GB.core_radius;
-                    pgroup[tid] = g;
-                    pslot[tid] = (int32_t)idx;
-                    pmeta[tid] = p;            // n = 0, stalls = 0, it = 0
-                    pphase[tid] = 1;
-                }
-            }
-        }
-        // ---- (c) phase lists
-        const int ph = pphase[tid];
-        const unsigned ms = __ballot_sync(0xffffffffu, ph == 1), mq = __ballot_sync(0xffffffffu, ph == 2);
-        if (lane == 0) { wcnt[NW + warp] = __popc(ms); wcnt[2 * NW + warp] = __popc(mq); }
-        __syncthreads();
-        {
-            uint32_t bs = 0, bq = 0, ts = 0, tq = 0;
-            for (int w = 0; w < NW; w++) {
-                const uint32_t a = wcnt[NW + w], b = wcnt[2 * NW + w];
-                if (w < (int)warp) { bs += a; bq += b; }
-                ts += a; tq += b;
-            }
-            if (ph == 1) lsup[bs + __popc(ms & lt_mask)] = (uint16_t)tid;
-            if (ph == 2) lsmp[bq + __popc(mq & lt_mask)] = (uint16_t)tid;
-            if (tid == 0) { s_nsup = ts; s_nsmp = tq; }
-        }
-        __syncthreads();
-        const uint32_t nsup = s_nsup, nsmp = s_nsmp;
-        if (nsup == 0 && nsmp == 0) {
-            if (!s_more) break;
-            continue;    // pool empty but the cursor has more (only when a claimed chunk was all dropped)
-        }
-        // ---- (d) work: support items first, simplex items from the next warp boundary
-        const uint32_t sup_pad = (nsup + 31u) & ~31u;
-        for (uint32_t wi = tid; wi < sup_pad + nsmp; wi += NP_THREADS) {
-            const bool do_sup = wi < nsup;
-            const bool do_smp = wi >= sup_pad;
-            if (!do_sup && !do_smp) continue;
-            const int it = do_sup ? lsup[wi] : lsmp[wi - sup_pad];
-            const int meta = pmeta[it];
-            const int p = meta & 0xffff;
-            GjkState s;
-            s.v = make_float3(pf[(PF_V + 0) * POOL + it], pf[(PF_V + 1) * POOL + it], pf[(PF_V + 2) * POOL + it]);
-            s.vv = pf[PF_VV * POOL + it];
-            s.W0 = make_float3(pf[(PF_W0 + 0) * POOL + it], pf[(PF_W0 + 1) * POOL + it], pf[(PF_W0 + 2) * POOL + it]);
-            s.W1 = make_float3(pf[(PF_W1 + 0) * POOL + it], pf[(PF_W1 + 1) * POOL + it], pf[(PF_W1 + 2) * POOL + it]);
-            s.W2 = make_float3(pf[(PF_W2 + 0) * POOL + it], pf[(PF_W2 + 1) * POOL + it], pf[(PF_W2 + 2) * POOL + it]);
-            s.n = (meta >> 16) & 0xf; s.stalls = (meta >> 20) & 0xf; s.it = (meta >> 24) & 0xff;
-            const DevGeom &GA = sg[sp[p].a];
-            const DevGeom &GB = sg[sp[p].b];
-            const float radii = GA.core_radius + GB.core_radius;
-            const float margin = padding + radii;
-            bool finished;
-            GjkOut r;
-            if (do_sup) {
-                float T[12];
-#pragma unroll
-                for (int k = 0; k < 12; k++) T[k] = pf[(PF_T + k) * POOL + it];
-                ShapeRef A, B;
-                A.shape = GA.shape; A.p0 = GA.par[0]; A.p1 = GA.par[1]; A.p2 = GA.par[2];
-                A.verts = sv + GA.vert_off; A.nverts = GA.vert_cnt;
-                A.cell_off = GA.map_off >= 0 ? scell + GA.map_off : nullptr; A.cell_list = slist + GA.list_off;
-                B.shape = GB.shape; B.p0 = GB.par[0]; B.p1 = GB.par[1]; B.p2 = GB.par[2];
-                B.verts = sv + GB.vert_off; B.nverts = GB.vert_cnt;
-                B.cell_off = GB.map_off >= 0 ? scell + GB.map_off : nullptr; B.cell_list = slist + GB.list_off;
-                const float bound = MODE == MODE_DIST ? pf[PF_BOUND * POOL + it] : 0.f;
-                finished = (MODE == MODE_DIST) ? gjk_support_phase<true>(A, B, T, s, margin, bound, r)
-                                               : gjk_support_phase<false>(A, B, T, s, margin, 0.f, r);
-                if (!finished) {
-                    pf[(PF_W + 0) * POOL + it] = s.w.x; pf[(PF_W + 1) * POOL + it] = s.w.y; pf[(PF_W + 2) * POOL + it] = s.w.z;
-                    pphase[it] = 2;
-                }
-            } else {
-                s.w = make_float3(pf[(PF_W + 0) * POOL + it], pf[(PF_W + 1) * POOL + it], pf[(PF_W + 2) * POOL + it]);
-                finished = (MODE == MODE_DIST) ? gjk_simplex_phase<true>(s, margin, r) : gjk_simplex_phase<false>(s, margin, r);
-                if (!finished) {
-                    pf[(PF_V + 0) * POOL + it] = s.v.x; pf[(PF_V + 1) * POOL + it] = s.v.y; pf[(PF_V + 2) * POOL + it] = s.v.z;
-                    pf[PF_VV * POOL + it] = s.vv;
-                    pf[(PF_W0 + 0) * POOL + it] = s.W0.x; pf[(PF_W0 + 1) * POOL + it] = s.W0.y; pf[(PF_W0 + 2) * POOL + it] = s.W0.z;
-                    pf[(PF_W1 + 0) * POOL + it] = s.W1.x; pf[(PF_W1 + 1) * POOL + it] = s.W1.y; pf[(PF_W1 + 2) * POOL + it] = s.W1.z;
-                    pf[(PF_W2 + 0) * POOL + it] = s.W2.x; pf[(PF_W2 + 1) * POOL + it] = s.W2.y; pf[(PF_W2 + 2) * POOL + it] = s.W2.z;
-                    pphase[it] = 1;
-                }
-            }
-            if (!finished) {
-                pmeta[it] = p | (s.n << 16) | (min(s.stalls, 15) << 20) | (min(s.it, 255) << 24);
-            } else {
-                pphase[it] = 0;
-                const int32_t group = pgroup[it];
-                if (MODE == MODE_DIST) {
-                    if (r.hit) out.hit[group] = 1;
-                    atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(fmaxf(r.dist - radii, 0.f)));
-                } else if (r.hit) {
-                    out.hit[group] = 1;
-                    if (MODE == MODE_BOOL_ALL) {
-                        if (out.first_pair) atomicMin(out.first_pair + group, M.pair_orig[p]);
-                        if (out.first_bad) atomicMin(out.first_bad + group, has_sample ? bins.sample[(int64_t)p * bins.cap + pslot[it]] : 0);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Surface semantics of mesh geometries: enclosure test for parked hull hits
-// ------------------------------------------------------------------------------------------
-// The reference's meshes are SURFACES (coal BVHModel): a shape that lies wholly inside a mesh without
-// reaching its surface does not collide with it.  For a convex hull A = {x : n_f.x <= w_f} and a
-// convex shape B, the gap of B to A's boundary is  min_f (w_f - h_B(n_f))  (h_B: support function);
-// B is enclosed with clearance beyond `padding` when that gap exceeds padding.  (The mesh surface lies
-// up to DevModel::surface_tol below its hull where a quad is triangulated along its valley; an
-// enclosed shape closer than that to a dented face is the residual difference to the reference,
-// a few states in a million -- tools/soup_study.py, tools/gpu_surface_check.py.)  The faces are split
-// over `nlanes` cooperating lanes; the caller reduces with a warp maximum when nlanes > 1.
-//   T: placement of `inner` in the frame of the geometry `g_outer`; returns max_f (h_inner(n_f) - w_f).
-__device__ __forceinline__ float enclosure_excess(const DevModel &M, const float4 *planes, int g_outer, const ShapeRef &inner, float inner_radius,
-                                                  const float *T, float padding, int lane, int nlanes, int max_faces = INT_MAX) {
-    const int2 pi = M.plane_idx[g_outer];
-    const int nfaces = min(pi.y, max_faces);
-    float worst = -FLT_MAX;
-    for (int f0 = 0; f0 < nfaces; f0 += nlanes) {
-        const int f = f0 + lane;
-        if (f < nfaces) {
-            const float4 pl = planes[pi.x + f];
-            const float3 dl = make_float3(fmaf(T[0], pl.x, fmaf(T[3], pl.y, T[6] * pl.z)), fmaf(T[1], pl.x, fmaf(T[4], pl.y, T[7] * pl.z)),
-                                          fmaf(T[2], pl.x, fmaf(T[5], pl.y, T[8] * pl.z)));
-            const float3 sl = support_local(inner, dl);
-            const float3 sw = se3_act(T, sl.x, sl.y, sl.z);
-            worst = fmaxf(worst, fmaf(pl.x, sw.x, fmaf(pl.y, sw.y, pl.z * sw.z)) + inner_radius - pl.w);
-        }
-        // one face the inner shape reaches (to within padding) settles it: not enclosed.  Nearly all
-        // parked items end here after the first batch of faces.
-        const bool out = worst >= -padding;
-        if (nlanes > 1 ? __any_sync(0xffffffffu, out) : out) return FLT_MAX;
-    }
-    return worst;
-}
-
-// flags bit 0: b could lie inside a's surface; bit 1: a inside b's.  T: placement of b in a's frame.
-// gap_out (optional): the clearance of the enclosed shape to the enclosing hull.
-// max_faces: only the first (largest) faces of the enclosing hull -- a "false" is then a proof that the
-// inner shape pokes out, a "true" only means that none of those faces was reached.
-__device__ __forceinline__ bool surface_enclosed(const DevModel &M, const float4 *planes, int flags, int ga, int gb, const ShapeRef &A,
-                                                 const ShapeRef &B, float ra, float rb, const float *T, float padding, int lane, int nlanes,
-                                                 float *gap_out = nullptr, int max_faces = INT_MAX) {
-    if (flags & 1) {
-        float ex = enclosure_excess(M, planes, ga, B, rb, T, padding, lane, nlanes, max_faces);
-        if (nlanes > 1) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ex = fmaxf(ex, __shfl_xor_sync(0xffffffffu, ex, o));
-        }
-        if (-ex > padding) { if (gap_out) *gap_out = -ex; return true; }
-    }
-    if (flags & 2) {
-        float Ti[12];
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            Ti[3 * i + 0] = T[i]; Ti[3 * i + 1] = T[3 + i]; Ti[3 * i + 2] = T[6 + i];
-            Ti[9 + i] = -(T[i] * T[9] + T[3 + i] * T[10] + T[6 + i] * T[11]);
-        }
-        float ex = enclosure_excess(M, planes, gb, A, ra, Ti, padding, lane, nlanes, max_faces);
-        if (nlanes > 1) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ex = fmaxf(ex, __shfl_xor_sync(0xffffffffu, ex, o));
-        }
-        if (-ex > padding) { if (gap_out) *gap_out = -ex; return true; }
-    }
-    return false;
-}
-
-// Parked items (the narrowphase marked bins.group with SR_PARKED instead of publishing the hull hit)
-// are about 0.1 per Panda state; 1 in 100 of them is a real enclosure.  The bins of the flagged pairs
-// are cut into chunks of 32 items, the chunks dealt round-robin to the warps.  Pass 1, one item per
-// lane: may_be_enclosed() -- a direction in which the would-be inner shape pokes out publishes the
-// hit.  Pass 2, one item per warp: the face planes of the enclosing hull split over the 32 lanes.
-// The hull tables and planes are staged in shared memory when they fit (every support evaluation is a
-// chain of dependent table reads).
-constexpr int SR_THREADS = 512;        // (768 threads at 80 registers: 72 us, 1024 at 64: 74 us, against 62)
-constexpr int SR_DIR = 256;       // flagged pairs the chunk directory holds
-constexpr int SR_LANE_FACES = 8;  // faces of the enclosing hull each lane tries by itself in pass 1
+// Parked items are a few in a thousand Panda states (undecided between hull and core) plus 0.1 per state
+// (core hits of pairs with an enclosure flag, 1 in 100 of them a real enclosure).  The bins of the pairs
+// with a surface are cut into chunks of 32 items, claimed from a global cursor.  One item per lane first
+// (decide_boolean / decide_distance), then the warp settles what is left (settle_warp_items).  The hull
+// tables and the planes are staged in shared memory when they fit (every support evaluation is a chain of
+// dependent table reads); cores and triangles, read by a few items only, stay in global memory.
+constexpr int SR_THREADS = 512;
+constexpr int SR_DIR = 256;       // pairs the chunk directory holds
 
 template <int MODE, bool TABLES_IN_SMEM>
 __global__ void __launch_bounds__(SR_THREADS)
@@ -1110,30 +781,31 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
         stage_words(spl, M.planes, M.nplanes * (int)sizeof(float4));
         stage_words(scell, M.sup_cells, M.n_sup_cells * 2);
         stage_words(slist, M.sup_lists, M.n_sup_lists * 2);
-        __syncthreads();
     }
-    const float4 *verts = TABLES_IN_SMEM ? sv : M.verts;
-    const float4 *planes = TABLES_IN_SMEM ? spl : M.planes;
-    const uint16_t *cells = TABLES_IN_SMEM ? scell : M.sup_cells;
-    const uint16_t *lists = TABLES_IN_SMEM ? slist : M.sup_lists;
+    SurfTables tab;
+    tab.hverts = TABLES_IN_SMEM ? sv : M.verts;
+    tab.hcells = TABLES_IN_SMEM ? scell : M.sup_cells;
+    tab.hlists = TABLES_IN_SMEM ? slist : M.sup_lists;
+    tab.planes = TABLES_IN_SMEM ? spl : M.planes;
+    tab.kverts = M.kverts; tab.kcells = M.ksup_cells; tab.klists = M.ksup_lists;
+    tab.mverts = M.mverts; tab.tris = M.tris;
+    __shared__ uint16_t s_tri[SR_THREADS / 32][2][TRI_LIST_CAP];
+    uint16_t *la = s_tri[threadIdx.x >> 5][0], *lb = s_tri[threadIdx.x >> 5][1];
     const unsigned lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * SR_THREADS + threadIdx.x) >> 5, nwarps = gridDim.x * (SR_THREADS / 32);
     const int64_t stride = (int64_t)M.npairs * bins.cap;
-    const float pad_test = MODE == MODE_DIST ? 0.f : padding;
-    auto commit = [&](int p, int32_t group, int64_t slot, bool enclosed, float gap) {
-        if (MODE == MODE_DIST) {
-            // the distance of an enclosed shape is its clearance, whatever the padding (pad_test = 0)
-            if (!enclosed || gap <= padding) out.hit[group] = 1;
-            atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(enclosed ? gap : 0.f));
-        } else if (!enclosed) {
-            out.hit[group] = 1;
-            if (MODE == MODE_BOOL_ALL) {
-                if (out.first_pair) atomicMin(out.first_pair + group, M.pair_orig[p]);
-                if (out.first_bad) atomicMin(out.first_bad + group, has_sample ? bins.sample[slot] : 0);
-            }
+    auto on_hit = [&](int p, int32_t group, int64_t slot) {
+        out.hit[group] = 1;
+        if (MODE == MODE_BOOL_ALL) {
+            if (out.first_pair) atomicMin(out.first_pair + group, M.pair_orig[p]);
+            if (out.first_bad) atomicMin(out.first_bad + group, has_sample ? bins.sample[slot] : 0);
         }
     };
-    // chunk directory: the flagged pairs and the running number of 32-item chunks before each
+    auto on_value = [&](int, int32_t group, int64_t, float d) {
+        if (d <= padding) out.hit[group] = 1;
+        atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(d));
+    };
+    auto decided = [&](int32_t group) { return MODE == MODE_BOOL && out.hit[group] != 0; };
+    // chunk directory: the pairs with a surface and the running number of 32-item chunks before each
     __shared__ int s_pair[SR_DIR];
     __shared__ uint32_t s_first[SR_DIR + 1];
     __shared__ int s_n;
@@ -1141,7 +813,7 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
         int nf = 0;
         uint32_t acc = 0;
         for (int k = 0; k < M.npairs && nf >= 0; k++) {
-            if (!M.pair_enclose[k]) continue;
+            if (!(M.pair_enclose[k] & PAIR_SURFACE)) continue;
             if (nf == SR_DIR) { nf = -1; break; }   // directory full: every warp scans the pair list itself
             s_pair[nf] = k;
             s_first[nf] = acc;
@@ -1152,10 +824,9 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
         s_n = nf;
     }
     __syncthreads();
-    (void)warp; (void)nwarps;
     for (;;) {
-        // next chunk of the concatenated flagged bins, claimed from a global cursor: the chunks differ
-        // widely in cost (parked lanes, true enclosures), a fixed round-robin leaves warps idle
+        // next chunk of the concatenated bins, claimed from a global cursor: the chunks differ widely in
+        // cost (parked lanes, true enclosures, triangle stages), a fixed round-robin leaves warps idle
         uint32_t c = 0;
         if (lane == 0) c = atomicAdd(chunk_cursor, 1u);
         c = __shfl_sync(0xffffffffu, c, 0);
@@ -1174,7 +845,7 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
         } else {
             uint32_t acc = 0;
             for (int k = 0; k < M.npairs; k++) {
-                if (!M.pair_enclose[k]) continue;
+                if (!(M.pair_enclose[k] & PAIR_SURFACE)) continue;
                 const uint32_t nch = (bins.count_np[k] + 31u) >> 5;
                 if (c < acc + nch) { p = k; local = c - acc; break; }
                 acc += nch;
@@ -1186,66 +857,50 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
         const BpPair pr = M.bppairs[p];
         const DevGeom &GA = M.geoms[pr.a];
         const DevGeom &GB = M.geoms[pr.b];
-        ShapeRef A, B;
-        A.shape = GA.shape; A.p0 = GA.par[0]; A.p1 = GA.par[1]; A.p2 = GA.par[2];
-        A.verts = verts + GA.vert_off; A.nverts = GA.vert_cnt;
-        A.cell_off = GA.map_off >= 0 ? cells + GA.map_off : nullptr; A.cell_list = lists + GA.list_off;
-        B.shape = GB.shape; B.p0 = GB.par[0]; B.p1 = GB.par[1]; B.p2 = GB.par[2];
-        B.verts = verts + GB.vert_off; B.nverts = GB.vert_cnt;
-        B.cell_off = GB.map_off >= 0 ? cells + GB.map_off : nullptr; B.cell_list = lists + GB.list_off;
         const uint32_t idx = local * 32u + lane;
         const int64_t slot = (int64_t)p * bins.cap + idx;
         const int32_t g = idx < cnt ? bins.group[slot] : 0;
-        bool parked = idx < cnt && g >= 0 && (g & SR_PARKED);
-        const int32_t group = g & ~SR_PARKED;
-        if (parked && MODE == MODE_BOOL && out.hit[group]) parked = false;   // decided meanwhile
+        bool active = idx < cnt && g >= 0 && (g & SR_BITS);
+        const int32_t group = g & ~SR_BITS;
+        if (active && decided(group)) active = false;
         float T[12];
 #pragma unroll
-        for (int k = 0; k < 12; k++) T[k] = parked ? bins.T[k * stride + slot] : 0.f;
-        bool maybe = false;
-        if (parked) {
-            // the centre line settles 73 % of the parked items, the enclosing hull's 8 largest faces
-            // 76 % of the rest (measured on config 2): 1.4 x the true enclosures reach pass 2
-            maybe = may_be_enclosed(fl, GA, GB, A, B, T, pad_test) &&
-                    surface_enclosed(M, planes, fl, pr.a, pr.b, A, B, GA.core_radius, GB.core_radius, T, pad_test, 0, 1, nullptr, SR_LANE_FACES);
-            if (!maybe) commit(p, group, slot, false, 0.f);
+        for (int k = 0; k < 12; k++) T[k] = active ? bins.T[k * stride + slot] : 0.f;
+        LaneVerdict v;
+        v.status = ST_NONE; v.dist = 0.f; v.U = 0.f; v.n = make_float3(0.f, 0.f, 0.f); v.have_n = 0;
+        if (active) {
+            if (MODE == MODE_DIST) v = decide_distance(tab, fl, GA, GB, T, out.min_dist[group]);
+            else v = decide_boolean(tab, fl, (g & SR_PARKED) != 0, GA, GB, T, padding);
+            if (v.status == ST_HIT) on_hit(p, group, slot);
+            if (v.status == ST_VALUE) on_value(p, group, slot, fmaxf(v.dist - GA.core_radius - GB.core_radius, 0.f));
         }
-        unsigned todo = __ballot_sync(0xffffffffu, maybe);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            float Ts[12];
-#pragma unroll
-            for (int k = 0; k < 12; k++) Ts[k] = __shfl_sync(0xffffffffu, T[k], src);
-            const int32_t gs = __shfl_sync(0xffffffffu, group, src);
-            if (MODE == MODE_BOOL && out.hit[gs]) continue;   // warp-uniform
-            float gap = 0.f;
-            const bool enclosed = surface_enclosed(M, planes, fl, pr.a, pr.b, A, B, GA.core_radius, GB.core_radius, Ts, pad_test, (int)lane, 32, &gap);
-            if (lane == 0) commit(p, gs, (int64_t)p * bins.cap + local * 32u + src, enclosed, gap);
-        }
+        settle_warp_items<MODE>(M, tab, v, p, group, slot, T, padding, la, lb, (int)lane, on_hit, on_value, decided);
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // Small batches: one fused kernel, one thread per (pair, state)
 // ------------------------------------------------------------------------------------------
-// The three-kernel pipeline is built for throughput; a single state or a single edge (the calls of a
-// sequential RRT loop) pays three latency-bound launches plus their memsets.  For at most a few
-// ten thousand (pair, state) items this kernel does everything in one launch: FK of the pair's two
-// geometries along its joint path, the broadphase's proxy classification (same thresholds), and --
-// only where that is undecided -- the whole GJK.  Boolean verdicts only.
+// The pipeline is built for throughput; a single state or a single edge (the calls of a sequential RRT
+// loop) pays four latency-bound launches plus their memsets.  For at most a few ten thousand
+// (pair, state) items this kernel does everything in one launch: FK of the pair's two geometries along
+// its joint path, the broadphase's proxy classification (same thresholds), and -- only where that is
+// undecided -- the whole GJK on the cores; what that leaves open is settled as in k_surface_refine.
+// Boolean verdicts only.
 constexpr int SMALL_THREADS = 128;
 
-// One (pair, state) item.  Returns 0: nothing to publish, 1: the pair collides, 2: the hulls overlap
-// but one shape may be enclosed by the other's surface -- R (placement of b in a's frame) is then
-// handed to the warp-cooperative enclosure test of the kernel.
-enum { SMALL_NONE = 0, SMALL_HIT = 1, SMALL_PARKED = 2 };
-__device__ __forceinline__ int small_item(const DevModel &M, const StateSource &src, int64_t n_states, float padding, const Outputs &out,
-                                          int64_t t, float *R, int32_t &group, int &p) {
+// One (pair, state) item.  Returns ST_NONE: nothing to publish, ST_HIT: the pair collides, ST_WALK /
+// ST_TRIANGLES ...: see LaneVerdict; R (placement of b in a's frame) is handed on to the warp.
+__device__ __forceinline__ LaneVerdict small_item(const DevModel &M, const SurfTables &tab, const StateSource &src, int64_t n_states, float padding,
+                                                  const Outputs &out, int64_t t, float *R, int32_t &group, int &p) {
+    LaneVerdict none;
+    none.status = ST_NONE; none.dist = 0.f; none.U = 0.f; none.n = make_float3(0.f, 0.f, 0.f); none.have_n = 0;
+    LaneVerdict hit = none;
+    hit.status = ST_HIT;
     p = (int)(t / n_states);                            // pair-major: the lanes of a warp share the pair
     const int64_t state = t - (int64_t)p * n_states;
     group = src.group ? src.group[state] : (int32_t)state;
-    if (out.hit[group]) return SMALL_NONE;              // already decided by another item of this launch
+    if (out.hit[group]) return none;                    // already decided by another item of this launch
     const BpPair pr = M.bppairs[p];
     const DevGeom &GA = M.geoms[pr.a];
     const DevGeom &GB = M.geoms[pr.b];
@@ -1304,62 +959,44 @@ __device__ __forceinline__ int small_item(const DevModel &M, const StateSource &
     const bool exact = pr.kind == BP_EXACT_SPHERES;
     const float slack = exact ? 0.f : BP_SLACK;
     const float rf = pr.r_out + padding + slack, rs = pr.r_in + padding - slack;
-    if (rs >= 0.f && d2 <= rs * rs) return SMALL_HIT;                    // certainly colliding
-    if (exact || d2 > rf * rf) return SMALL_NONE;                        // certainly free (or decided exactly)
-    // ---- undecided: the whole GJK
-    ShapeRef A, B;
-    A.shape = GA.shape; A.p0 = GA.par[0]; A.p1 = GA.par[1]; A.p2 = GA.par[2];
-    A.verts = M.verts + GA.vert_off; A.nverts = GA.vert_cnt;
-    A.cell_off = GA.map_off >= 0 ? M.sup_cells + GA.map_off : nullptr; A.cell_list = M.sup_lists + GA.list_off;
-    B.shape = GB.shape; B.p0 = GB.par[0]; B.p1 = GB.par[1]; B.p2 = GB.par[2];
-    B.verts = M.verts + GB.vert_off; B.nverts = GB.vert_cnt;
-    B.cell_off = GB.map_off >= 0 ? M.sup_cells + GB.map_off : nullptr; B.cell_list = M.sup_lists + GB.list_off;
+    if (rs >= 0.f && d2 <= rs * rs) return hit;                          // certainly colliding
+    if (exact || d2 > rf * rf) return none;                              // certainly free (or decided exactly)
+    // ---- undecided: the whole GJK, on the cores
+    const ShapeRef A = core_shape(tab, GA), B = core_shape(tab, GB);
     const float margin = padding + GA.core_radius + GB.core_radius;
-    const GjkOut r = gjk_run<false>(A, B, R, gjk_start_direction(GA, GB, R), margin, 0.f);
-    if (!r.hit) return SMALL_NONE;
-    if (M.surface && M.pair_enclose[p] && may_be_enclosed(M.pair_enclose[p], GA, GB, A, B, R, padding)) return SMALL_PARKED;
-    return SMALL_HIT;
+    const GjkOut r = gjk_run<false>(A, B, R, gjk_start_direction(GA, GB, R), margin, margin + pair_eps(GA, GB));
+    const int fl = M.has_tris ? M.pair_enclose[p] : 0;
+    if (!(fl & PAIR_SURFACE)) return r.hit ? hit : none;
+    if (r.far) return none;
+    if (r.hit && !(fl & (PAIR_ENCLOSE | PAIR_NOCORE))) return hit;
+    return decide_boolean(tab, fl, r.hit && !(fl & PAIR_NOCORE), GA, GB, R, padding);
 }
 
 __global__ void __launch_bounds__(SMALL_THREADS)
 k_small_check(DevModel M, StateSource src, int64_t n_states, float padding, Outputs out) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    SurfTables tab;
+    tab.hverts = M.verts; tab.hcells = M.sup_cells; tab.hlists = M.sup_lists;
+    tab.kverts = M.kverts; tab.kcells = M.ksup_cells; tab.klists = M.ksup_lists;
+    tab.planes = M.planes; tab.mverts = M.mverts; tab.tris = M.tris;
     float R[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) R[k] = 0.f;
     int32_t group = 0;
     int p = 0;
-    const int status = t < n_states * M.npairs ? small_item(M, src, n_states, padding, out, t, R, group, p) : SMALL_NONE;
-    if (status == SMALL_HIT) out.hit[group] = 1;
-    if (!M.surface) return;
-    // surface semantics: the (rare) possibly-enclosed items of this warp, one after the other, the
-    // enclosing hull's faces split over the 32 lanes (a single lane would walk ~300 faces alone)
-    const unsigned lane = threadIdx.x & 31;
-    unsigned todo = __ballot_sync(0xffffffffu, status == SMALL_PARKED);
-    while (todo) {
-        const int srcl = __ffs(todo) - 1;
-        todo &= todo - 1;
-        float Rs[12];
-#pragma unroll
-        for (int k = 0; k < 12; k++) Rs[k] = __shfl_sync(0xffffffffu, R[k], srcl);
-        const int ps = __shfl_sync(0xffffffffu, p, srcl);
-        const int32_t gs = __shfl_sync(0xffffffffu, group, srcl);
-        if (out.hit[gs]) continue;   // warp-uniform
-        const BpPair pr = M.bppairs[ps];
-        const DevGeom &GA = M.geoms[pr.a];
-        const DevGeom &GB = M.geoms[pr.b];
-        ShapeRef A, B;
-        A.shape = GA.shape; A.p0 = GA.par[0]; A.p1 = GA.par[1]; A.p2 = GA.par[2];
-        A.verts = M.verts + GA.vert_off; A.nverts = GA.vert_cnt;
-        A.cell_off = GA.map_off >= 0 ? M.sup_cells + GA.map_off : nullptr; A.cell_list = M.sup_lists + GA.list_off;
-        B.shape = GB.shape; B.p0 = GB.par[0]; B.p1 = GB.par[1]; B.p2 = GB.par[2];
-        B.verts = M.verts + GB.vert_off; B.nverts = GB.vert_cnt;
-        B.cell_off = GB.map_off >= 0 ? M.sup_cells + GB.map_off : nullptr; B.cell_list = M.sup_lists + GB.list_off;
-        const bool enclosed = surface_enclosed(M, M.planes, M.pair_enclose[ps], pr.a, pr.b, A, B, GA.core_radius, GB.core_radius, Rs, padding, (int)lane, 32);
-        if (!enclosed && lane == 0) out.hit[gs] = 1;
-    }
+    LaneVerdict v;
+    v.status = ST_NONE; v.dist = 0.f; v.U = 0.f; v.n = make_float3(0.f, 0.f, 0.f); v.have_n = 0;
+    if (t < n_states * M.npairs) v = small_item(M, tab, src, n_states, padding, out, t, R, group, p);
+    if (v.status == ST_HIT) out.hit[group] = 1;
+    if (!M.has_tris) return;
+    // surface semantics: the (rare) items that need the warp, one after the other
+    __shared__ uint16_t s_tri[SMALL_THREADS / 32][2][TRI_LIST_CAP];
+    auto on_hit = [&](int, int32_t g, int64_t) { out.hit[g] = 1; };
+    auto on_value = [&](int, int32_t, int64_t, float) {};
+    auto decided = [&](int32_t g) { return out.hit[g] != 0; };
+    settle_warp_items<MODE_BOOL>(M, tab, v, p, group, (int64_t)0, R, padding, s_tri[threadIdx.x >> 5][0], s_tri[threadIdx.x >> 5][1],
+                                 (int)(threadIdx.x & 31), on_hit, on_value, decided);
 }
-
 
 // ------------------------------------------------------------------------------------------
 // Path discretisation (reference planning/utils.py:114-140)

@@ -22,7 +22,7 @@ struct DevJoint {       // 96 B
     int32_t _pad;
 };
 
-struct DevGeom {        // 144 B -- narrowphase / item-setup view of a geometry
+struct DevGeom {        // 192 B -- narrowphase / item-setup view of a geometry
     float P[12];        // placement in parent joint frame (world placement if parent == 0)
     float par[4];       // shape parameters
     float centre[3];    // proxy-sphere centre in the geometry frame (initial GJK direction)
@@ -36,9 +36,23 @@ struct DevGeom {        // 144 B -- narrowphase / item-setup view of a geometry
     int32_t has_axis;   // != 0: axis0 / axis1 is the segment of the shape's enclosing capsule (geometry frame)
     int32_t _pad;
     float axis0[3];     // used for the GJK start direction of elongated shapes
-    float _pad2;
+    float r_out;        // enclosing radius around `centre` (culls of the triangle stage)
     float axis1[3];
-    float _pad3;
+    float core_eps;     // surface geometry: every point of the hull is within this of the inner core (0: solid)
+    // Surface semantics (pbp_surface.cuh).  A mesh geometry is bracketed by its hull H (vert_* above) and its
+    // inner core K (kvert_* below, a convex polytope inside the mesh); solids have K == H.
+    int32_t kvert_off;  // offset into the padded float4 core vertex table
+    int32_t kvert_cnt;
+    int32_t kmap_off;   // support map of the core (as map_off / list_off)
+    int32_t klist_off;
+    int32_t tri_off;    // first triangle (DevModel::tris), indices relative to mvert_off
+    int32_t tri_cnt;    // 0: the geometry is a solid
+    int32_t mvert_off;  // first mesh vertex (DevModel::mverts)
+    int32_t plane_off;  // planes of the core: the hull's face planes first (largest face first) ...
+    int32_t plane_cnt;
+    int32_t plane_hull_cnt;   // ... this many; the rest are planes of mesh triangles below the hull
+    float surface_tol;  // two-sided distance between the hull's boundary and the mesh surface
+    int32_t _pad4;
 };
 
 struct BpGeom {         // 64 B -- broadphase view: one proxy centre, two radii (+ optional enclosing capsule)
@@ -129,6 +143,14 @@ struct DevModel {
     const float *surface_tol;
     const uint8_t *pair_enclose;
     int32_t surface, nplanes;
+    // inner cores (boolean queries run GJK on them, distance queries on the hulls) and mesh triangles
+    const float4 *kverts;        // padded core vertices (== verts when no geometry is a surface)
+    const uint16_t *ksup_cells;
+    const uint16_t *ksup_lists;
+    int32_t nkverts_padded, n_ksup_cells, n_ksup_lists;
+    int32_t has_tris;            // some geometry carries triangles: the narrowphase parks undecided items
+    const float4 *mverts;        // mesh vertices (geometry frame)
+    const int4 *tris;            // vertex indices (x, y, z) relative to the geometry's mvert_off
 };
 
 // ------------------------------------------------------------------------------------------

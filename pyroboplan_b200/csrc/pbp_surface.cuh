@@ -1,0 +1,495 @@
+// Surface semantics of mesh geometries: everything the GJK kernels leave open.
+//
+// The reference's meshes are SURFACES (Pinocchio loads a URDF <mesh> as a coal BVHModel,
+// /root/reference/src/pyroboplan/models/panda.py:27): two meshes collide when two triangles come within
+// the margin, a solid primitive collides with a mesh when it comes within the margin of a triangle, a
+// shape wholly inside a mesh without reaching its surface does not collide with it.  The hot kernels
+// bracket every mesh M between its hull H and an inner core K (pyroboplan_b200/model/surface.py):
+//
+//   d(H_a, H_b) <= d(M_a, M_b) <= d(K_a, K_b)        (when neither shape encloses the other)
+//
+// Boolean queries run GJK on the cores: "within the margin" is then certain, "farther than margin +
+// eps_a + eps_b" (eps: how far a hull may lie outside its core) is certain, and the few items that
+// converge in between are parked as UNDECIDED.  A core hit of a pair where one shape could lie inside the
+// other's surface is parked as POSSIBLY ENCLOSED.  Distance queries run GJK on the hulls and park every
+// item that could define the state's minimum.  The functions here decide the parked items:
+//
+//   lane level   converged GJK on hulls and cores (most undecided items have d_H == d_K, or d_H beyond the
+//                margin); the centre-line and largest-face tests of the enclosure
+//   warp level   the walk over all faces of the enclosing core, and the TRIANGLE STAGE: the triangles of
+//                both meshes that can matter (slab along the separating direction, bounding spheres),
+//                every pair of them through one converged GJK, the 32 lanes sharing the pairs.
+#pragma once
+#include <limits.h>
+
+#include "pbp_gjk.cuh"
+
+namespace pbp {
+
+// MODE_BOOL      verdict only; a state stops at its first certain hit, decided groups are skipped
+// MODE_BOOL_ALL  verdict + first_pair / first_bad: every pair of every state is resolved
+// MODE_DIST      verdict + min distance: pairs are resolved unless certainly farther than the bound
+enum { MODE_BOOL = 0, MODE_BOOL_ALL = 1, MODE_DIST = 2 };
+
+// lanes that share a warp-level loop: 32 on the device; the host build of this header (tests/host_emu)
+// walks every loop with one lane and supplies one-lane versions of the warp intrinsics
+#if defined(__CUDACC__)
+constexpr int PBP_LANES = 32;
+#else
+constexpr int PBP_LANES = 1;
+#endif
+
+// bits set in Bins::group by the narrowphase on an item the refine kernel has to decide
+constexpr int32_t SR_PARKED = 0x40000000;   // core hit of a pair with an enclosure flag
+constexpr int32_t SR_DOUBT = 0x20000000;    // between the bounds (boolean) / may define the minimum (distance)
+constexpr int32_t SR_BITS = SR_PARKED | SR_DOUBT;
+
+#ifndef PBP_PAIR_FLAGS_DEFINED
+#define PBP_PAIR_FLAGS_DEFINED
+// per-pair flags (DevModel::pair_enclose, internal pair order)
+enum : uint8_t {
+    PAIR_ENCLOSE_B_IN_A = 1,   // `second` could lie wholly inside `first`, and `first` is a surface
+    PAIR_ENCLOSE_A_IN_B = 2,   // `first` could lie wholly inside `second`, and `second` is a surface
+    PAIR_ENCLOSE = 3,
+    PAIR_SURFACE = 4,          // a geometry of the pair carries triangles
+    PAIR_NOCORE = 8,           // ... and has no inner core: a hull hit proves nothing, the triangles decide every one
+};
+
+#endif
+
+// how far the hulls of a pair may lie outside its cores, together
+__device__ __forceinline__ float pair_eps(const DevGeom &GA, const DevGeom &GB) { return GA.core_eps + GB.core_eps; }
+
+// where the calling kernel keeps the tables (shared or global memory)
+struct SurfTables {
+    const float4 *hverts; const uint16_t *hcells, *hlists;   // hulls
+    const float4 *kverts; const uint16_t *kcells, *klists;   // inner cores
+    const float4 *planes;
+    const float4 *mverts;
+    const int4 *tris;
+};
+
+__device__ __forceinline__ ShapeRef hull_shape(const SurfTables &t, const DevGeom &G) {
+    ShapeRef S;
+    S.shape = G.shape; S.p0 = G.par[0]; S.p1 = G.par[1]; S.p2 = G.par[2];
+    S.verts = t.hverts + G.vert_off; S.nverts = G.vert_cnt;
+    S.cell_off = G.map_off >= 0 ? t.hcells + G.map_off : nullptr; S.cell_list = t.hlists + G.list_off;
+    return S;
+}
+__device__ __forceinline__ ShapeRef core_shape(const SurfTables &t, const DevGeom &G) {
+    ShapeRef S;
+    S.shape = G.shape; S.p0 = G.par[0]; S.p1 = G.par[1]; S.p2 = G.par[2];
+    S.verts = t.kverts + G.kvert_off; S.nverts = G.kvert_cnt;
+    S.cell_off = G.kmap_off >= 0 ? t.kcells + G.kmap_off : nullptr; S.cell_list = t.klists + G.klist_off;
+    return S;
+}
+
+// h_S(d) for a direction d of any length `len` (plus the inflation radius), shape frame / placed by T
+__device__ __forceinline__ float support_value(const ShapeRef &S, float3 d, float radius, float len) {
+    const float3 sl = support_local(S, d);
+    return dot3(d, sl) + radius * len;
+}
+__device__ __forceinline__ float support_value_placed(const ShapeRef &S, const float *T, float3 d, float radius, float len) {
+    const float3 dl = make_float3(fmaf(T[0], d.x, fmaf(T[3], d.y, T[6] * d.z)), fmaf(T[1], d.x, fmaf(T[4], d.y, T[7] * d.z)),
+                                  fmaf(T[2], d.x, fmaf(T[5], d.y, T[8] * d.z)));
+    const float3 sl = support_local(S, dl);
+    return dot3(d, se3_act(T, sl.x, sl.y, sl.z)) + radius * len;
+}
+
+// One out-of-line copy of the converged GJK serves the hull run, the core run and every triangle pair.
+struct ConvOut {
+    float dist;   // distance of the cores of the two shapes (0: they overlap); a lower bound when far != 0
+    float3 v;     // closest point of A - B to the origin (A's frame): the separating direction is -v
+    int far;      // certainly farther than `bound`
+};
+__device__ __noinline__ void gjk_converge(const ShapeRef &A, const ShapeRef &B, const float *T, float3 v0, float bound, ConvOut &o) {
+    GjkState s;
+    GjkOut r;
+    gjk_init(s, v0);
+    while (!gjk_step<true>(A, B, T, s, 0.f, bound, r)) {
+    }
+    o.dist = r.dist;
+    o.far = r.far;
+    o.v = s.v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Enclosure: is one shape of a core hit wholly inside the other's surface?
+// ------------------------------------------------------------------------------------------
+// `inner` pokes out of (or reaches) the enclosing hull  =>  the surfaces meet: with the cores overlapping
+// and a vertex of the inner mesh outside the outer hull, the inner surface has points on both sides of
+// the outer surface.  `inner` stays clear of every plane of the outer CORE by more than the padding  =>
+// it lies inside the outer mesh with that clearance: free.  In between the triangles decide.
+// pad_hit: with padding > 0 a point of the inner shape within (padding - tol) of a hull plane is within
+// padding of the outer SURFACE (tol: two-sided distance between hull boundary and mesh); 0 otherwise.
+__device__ __forceinline__ float enclosure_pad_hit(float padding, float tol_outer) { return padding > tol_outer ? padding - tol_outer : 0.f; }
+
+enum { ENC_POKES = 0, ENC_ENCLOSED = 1, ENC_UNSURE = 2 };
+
+// Centre-line test, one role: a direction in which the inner shape reaches at least as far as the outer one.
+__device__ __forceinline__ bool pokes_along(const ShapeRef &in, const float *Tin, float rin, const ShapeRef &outer, float rout, float3 d, float pad_hit,
+                                            bool in_is_placed) {
+    const float len = sqrtf(dot3(d, d));
+    const float hi = in_is_placed ? support_value_placed(in, Tin, d, rin, len) : support_value(in, d, rin, len);
+    const float ho = in_is_placed ? support_value(outer, d, rout, len) : support_value_placed(outer, Tin, d, rout, len);
+    return hi + pad_hit * len >= ho;
+}
+
+// Quick lane-level test of both flagged roles.  Returns true when every flagged role pokes out (a hit).
+__device__ __noinline__ bool enclosure_quick_pokes(int fl, const DevGeom &GA, const DevGeom &GB, const ShapeRef &A, const ShapeRef &B, const float *T,
+                                                   float padding) {
+    const float3 ca = make_float3(GA.centre[0], GA.centre[1], GA.centre[2]);
+    const float3 cb = se3_act(T, GB.centre[0], GB.centre[1], GB.centre[2]);
+    float3 d = sub3(cb, ca);
+    if (!(dot3(d, d) > 1e-12f)) d = make_float3(1.f, 0.f, 0.f);
+    // b inside a's surface?  (b is placed by T, a is the frame)
+    if ((fl & 1) && !pokes_along(B, T, GB.core_radius, A, GA.core_radius, d, enclosure_pad_hit(padding, GA.surface_tol), true)) return false;
+    // a inside b's surface?
+    if ((fl & 2) && !pokes_along(A, T, GA.core_radius, B, GB.core_radius, make_float3(-d.x, -d.y, -d.z), enclosure_pad_hit(padding, GB.surface_tol), false))
+        return false;
+    return true;
+}
+
+// Walk over the planes of the enclosing core, split over `nlanes` lanes.  T: placement of `inner` in the
+// frame of G_outer.  max_faces limits the walk to the first (largest) HULL faces: then only ENC_POKES is
+// a verdict.  gap_hull (optional): min over hull planes of the clearance (valid when not ENC_POKES).
+__device__ __forceinline__ int enclosure_walk(const float4 *planes, const DevGeom &G_outer, const ShapeRef &inner, float inner_radius, const float *T,
+                                              float padding, int lane, int nlanes, int max_faces, float *gap_hull) {
+    const int nhull = G_outer.plane_hull_cnt;
+    const int nfaces = max_faces < nhull ? max_faces : G_outer.plane_cnt;
+    const float pad_hit = enclosure_pad_hit(padding, G_outer.surface_tol);
+    float worst_h = -FLT_MAX, worst_k = -FLT_MAX;
+    for (int f0 = 0; f0 < nfaces; f0 += nlanes) {
+        const int f = f0 + lane;
+        if (f < nfaces) {
+            const float4 pl = planes[G_outer.plane_off + f];
+            const float3 dl = make_float3(fmaf(T[0], pl.x, fmaf(T[3], pl.y, T[6] * pl.z)), fmaf(T[1], pl.x, fmaf(T[4], pl.y, T[7] * pl.z)),
+                                          fmaf(T[2], pl.x, fmaf(T[5], pl.y, T[8] * pl.z)));
+            const float3 sl = support_local(inner, dl);
+            const float3 sw = se3_act(T, sl.x, sl.y, sl.z);
+            const float ex = fmaf(pl.x, sw.x, fmaf(pl.y, sw.y, pl.z * sw.z)) + inner_radius - pl.w;
+            worst_k = fmaxf(worst_k, ex);
+            if (f < nhull) worst_h = fmaxf(worst_h, ex);
+        }
+        // one hull face the inner shape reaches settles it; nearly all parked items end in the first batch
+        const bool out = worst_h >= -pad_hit;
+        if (nlanes > 1 ? __any_sync(0xffffffffu, out) : out) return ENC_POKES;
+    }
+    if (nlanes > 1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            worst_h = fmaxf(worst_h, __shfl_xor_sync(0xffffffffu, worst_h, o));
+            worst_k = fmaxf(worst_k, __shfl_xor_sync(0xffffffffu, worst_k, o));
+        }
+    }
+    if (gap_hull) *gap_hull = -worst_h;
+    if (max_faces < nhull) return ENC_UNSURE;
+    return -worst_k > padding ? ENC_ENCLOSED : ENC_UNSURE;
+}
+
+// Both flagged roles (bit 0: b inside a's surface, bit 1: a inside b's).  T: placement of b in a's frame.
+// ENC_POKES: neither shape is enclosed (the core hit stands); ENC_ENCLOSED: one is, with clearance beyond
+// the padding; ENC_UNSURE: the triangles decide.  gap_hull: clearance to the hull planes of the enclosing role.
+__device__ __forceinline__ int enclosure_roles(const float4 *planes, int fl, const DevGeom &GA, const DevGeom &GB, const ShapeRef &A, const ShapeRef &B,
+                                               const float *T, float padding, int lane, int nlanes, int max_faces, float *gap_hull, float *tol_outer) {
+    int res = ENC_POKES;
+    if (fl & 1) {
+        float g = 0.f;
+        const int r = enclosure_walk(planes, GA, B, GB.core_radius, T, padding, lane, nlanes, max_faces, &g);
+        if (r == ENC_ENCLOSED) { if (gap_hull) *gap_hull = g; if (tol_outer) *tol_outer = GA.surface_tol; return ENC_ENCLOSED; }
+        if (r == ENC_UNSURE) { res = ENC_UNSURE; if (gap_hull) *gap_hull = g; if (tol_outer) *tol_outer = GA.surface_tol; }
+    }
+    if (fl & 2) {
+        float Ti[12];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            Ti[3 * i + 0] = T[i]; Ti[3 * i + 1] = T[3 + i]; Ti[3 * i + 2] = T[6 + i];
+            Ti[9 + i] = -(T[i] * T[9] + T[3 + i] * T[10] + T[6 + i] * T[11]);
+        }
+        float g = 0.f;
+        const int r = enclosure_walk(planes, GB, A, GA.core_radius, Ti, padding, lane, nlanes, max_faces, &g);
+        if (r == ENC_ENCLOSED) { if (gap_hull) *gap_hull = g; if (tol_outer) *tol_outer = GB.surface_tol; return ENC_ENCLOSED; }
+        if (r == ENC_UNSURE) { res = ENC_UNSURE; if (gap_hull) *gap_hull = g; if (tol_outer) *tol_outer = GB.surface_tol; }
+    }
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------
+// Triangle stage (one warp per item)
+// ------------------------------------------------------------------------------------------
+constexpr int TRI_LIST_CAP = 384;   // triangles of one geometry the warp's lists hold per pass
+
+// Smallest distance between the (cores of the) two geometries over all triangle pairs within U, FLT_MAX when
+// there is none.  A geometry without triangles is its solid (primitive or hull) as one piece.  n (unit, A's
+// frame, pointing from A to B; have_n): only triangles within the slab the other shape can reach along n
+// can be within U; triangles farther than U from the other shape's bounding ball never are.
+// first_hit: return as soon as some pair is within U (boolean queries).  la / lb: per-warp shared scratch.
+__device__ __noinline__ float triangle_stage(const SurfTables &tab, const DevGeom &GA, const DevGeom &GB, const float *T, float3 n, bool have_n, float U,
+                                             bool first_hit, uint16_t *la, uint16_t *lb, int lane) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int nta = GA.tri_cnt, ntb = GB.tri_cnt;
+    const ShapeRef AH = hull_shape(tab, GA), BH = hull_shape(tab, GB);
+    const float3 ca = make_float3(GA.centre[0], GA.centre[1], GA.centre[2]);
+    const float3 cb = se3_act(T, GB.centre[0], GB.centre[1], GB.centre[2]);
+    const float ra = GA.r_out - GA.core_radius, rb = GB.r_out - GB.core_radius;   // balls around the CORES
+    const float slack = 2e-6f;
+    float hi_a = FLT_MAX, lo_b = -FLT_MAX;
+    if (have_n) {
+        hi_a = support_value(AH, n, 0.f, 1.f);                                                // max over A of n.x
+        lo_b = -support_value_placed(BH, T, make_float3(-n.x, -n.y, -n.z), 0.f, 1.f);         // min over B of n.x
+    }
+    float best = FLT_MAX;
+    float bound = U;
+    for (int a0 = 0; a0 < (nta > 0 ? nta : 1); a0 += TRI_LIST_CAP) {
+        // ---- A's triangles that can matter
+        int ca_n = 0;
+        if (nta == 0) {
+            ca_n = 1;
+        } else {
+            const int a1 = min(a0 + TRI_LIST_CAP, nta);
+            for (int t0 = a0; t0 < a1; t0 += PBP_LANES) {
+                const int t = t0 + lane;
+                bool keep = false;
+                if (t < a1) {
+                    const int4 tr = tab.tris[GA.tri_off + t];
+                    const float4 p0 = tab.mverts[GA.mvert_off + tr.x], p1 = tab.mverts[GA.mvert_off + tr.y], p2 = tab.mverts[GA.mvert_off + tr.z];
+                    const float gx = fmaxf(fmaxf(fminf(fminf(p0.x, p1.x), p2.x) - cb.x, cb.x - fmaxf(fmaxf(p0.x, p1.x), p2.x)), 0.f);
+                    const float gy = fmaxf(fmaxf(fminf(fminf(p0.y, p1.y), p2.y) - cb.y, cb.y - fmaxf(fmaxf(p0.y, p1.y), p2.y)), 0.f);
+                    const float gz = fmaxf(fmaxf(fminf(fminf(p0.z, p1.z), p2.z) - cb.z, cb.z - fmaxf(fmaxf(p0.z, p1.z), p2.z)), 0.f);
+                    const float reach = rb + U + slack;
+                    keep = fmaf(gx, gx, fmaf(gy, gy, gz * gz)) <= reach * reach;
+                    if (keep && have_n) {
+                        const float top = fmaxf(fmaxf(dot3(n, make_float3(p0.x, p0.y, p0.z)), dot3(n, make_float3(p1.x, p1.y, p1.z))),
+                                                dot3(n, make_float3(p2.x, p2.y, p2.z)));
+                        keep = top >= lo_b - U - slack;
+                    }
+                }
+                const unsigned km = __ballot_sync(0xffffffffu, keep);
+                if (keep) la[ca_n + __popc(km & lt_mask)] = (uint16_t)t;
+                ca_n += __popc(km);
+            }
+        }
+        if (ca_n == 0) continue;
+        for (int b0 = 0; b0 < (ntb > 0 ? ntb : 1); b0 += TRI_LIST_CAP) {
+            // ---- B's triangles that can matter (tested in A's frame)
+            int cb_n = 0;
+            if (ntb == 0) {
+                cb_n = 1;
+            } else {
+                const int b1 = min(b0 + TRI_LIST_CAP, ntb);
+                for (int t0 = b0; t0 < b1; t0 += PBP_LANES) {
+                    const int t = t0 + lane;
+                    bool keep = false;
+                    if (t < b1) {
+                        const int4 tr = tab.tris[GB.tri_off + t];
+                        const float4 q0 = tab.mverts[GB.mvert_off + tr.x], q1 = tab.mverts[GB.mvert_off + tr.y], q2 = tab.mverts[GB.mvert_off + tr.z];
+                        const float3 p0 = se3_act(T, q0.x, q0.y, q0.z), p1 = se3_act(T, q1.x, q1.y, q1.z), p2 = se3_act(T, q2.x, q2.y, q2.z);
+                        const float gx = fmaxf(fmaxf(fminf(fminf(p0.x, p1.x), p2.x) - ca.x, ca.x - fmaxf(fmaxf(p0.x, p1.x), p2.x)), 0.f);
+                        const float gy = fmaxf(fmaxf(fminf(fminf(p0.y, p1.y), p2.y) - ca.y, ca.y - fmaxf(fmaxf(p0.y, p1.y), p2.y)), 0.f);
+                        const float gz = fmaxf(fmaxf(fminf(fminf(p0.z, p1.z), p2.z) - ca.z, ca.z - fmaxf(fmaxf(p0.z, p1.z), p2.z)), 0.f);
+                        const float reach = ra + U + slack;
+                        keep = fmaf(gx, gx, fmaf(gy, gy, gz * gz)) <= reach * reach;
+                        if (keep && have_n) {
+                            const float bot = fminf(fminf(dot3(n, p0), dot3(n, p1)), dot3(n, p2));
+                            keep = bot <= hi_a + U + slack;
+                        }
+                    }
+                    const unsigned km = __ballot_sync(0xffffffffu, keep);
+                    if (keep) lb[cb_n + __popc(km & lt_mask)] = (uint16_t)t;
+                    cb_n += __popc(km);
+                }
+            }
+            if (cb_n == 0) continue;
+            __syncwarp();
+            // ---- every pair of the two lists, the lanes sharing them
+            const int npairs = ca_n * cb_n;
+            for (int i0 = 0; i0 < npairs; i0 += PBP_LANES) {
+                const int i = i0 + lane;
+                if (i < npairs) {
+                    const int ia = i / cb_n, ib = i - ia * cb_n;
+                    float4 va[4], vb[4];
+                    ShapeRef SA = AH, SB = BH;
+                    float3 v0a = ca, v0b = cb;
+                    if (nta > 0) {
+                        const int4 tr = tab.tris[GA.tri_off + la[ia]];
+                        va[0] = tab.mverts[GA.mvert_off + tr.x]; va[1] = tab.mverts[GA.mvert_off + tr.y]; va[2] = tab.mverts[GA.mvert_off + tr.z];
+                        va[3] = va[2];
+                        SA.shape = PBP_SHAPE_CONVEX; SA.verts = va; SA.nverts = 4; SA.cell_off = nullptr; SA.cell_list = nullptr;
+                        v0a = make_float3((va[0].x + va[1].x + va[2].x) * (1.f / 3.f), (va[0].y + va[1].y + va[2].y) * (1.f / 3.f),
+                                          (va[0].z + va[1].z + va[2].z) * (1.f / 3.f));
+                    }
+                    if (ntb > 0) {
+                        const int4 tr = tab.tris[GB.tri_off + lb[ib]];
+                        vb[0] = tab.mverts[GB.mvert_off + tr.x]; vb[1] = tab.mverts[GB.mvert_off + tr.y]; vb[2] = tab.mverts[GB.mvert_off + tr.z];
+                        vb[3] = vb[2];
+                        SB.shape = PBP_SHAPE_CONVEX; SB.verts = vb; SB.nverts = 4; SB.cell_off = nullptr; SB.cell_list = nullptr;
+                        v0b = se3_act(T, (vb[0].x + vb[1].x + vb[2].x) * (1.f / 3.f), (vb[0].y + vb[1].y + vb[2].y) * (1.f / 3.f),
+                                      (vb[0].z + vb[1].z + vb[2].z) * (1.f / 3.f));
+                    }
+                    ConvOut o;
+                    gjk_converge(SA, SB, T, sub3(v0a, v0b), bound, o);
+                    if (!o.far && o.dist < best) best = o.dist;
+                }
+                // tighten the bound with what the warp has found so far
+                float wb = best;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) wb = fminf(wb, __shfl_xor_sync(0xffffffffu, wb, o));
+                if (wb <= U && first_hit) return wb;
+                bound = fminf(bound, wb);
+            }
+            __syncwarp();
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    return best <= U ? best : FLT_MAX;
+}
+
+// ------------------------------------------------------------------------------------------
+// Lane level: one parked item
+// ------------------------------------------------------------------------------------------
+enum { ST_NONE = 0, ST_HIT = 1, ST_WALK = 2, ST_TRIANGLES = 3, ST_VALUE = 4 };
+struct LaneVerdict {
+    int status;     // ST_NONE: free / cannot improve the minimum; ST_HIT: the pair collides; ST_WALK: the warp walks the
+                    // enclosing core's planes; ST_TRIANGLES: the warp runs the triangle stage; ST_VALUE: dist is exact
+    float dist;     // ST_VALUE: the pair's core distance
+    float U;        // ST_TRIANGLES: pairs farther apart than this cannot matter (core distance)
+    float3 n;       // ST_TRIANGLES: separating direction of the cores (unit, A's frame), valid when have_n
+    int have_n;
+};
+
+// Boolean queries.  parked: core hit of a flagged pair; otherwise the item converged between margin and cut.
+__device__ __forceinline__ LaneVerdict decide_boolean(const SurfTables &tab, int fl, bool parked, const DevGeom &GA, const DevGeom &GB, const float *T,
+                                                      float padding) {
+    LaneVerdict r;
+    r.status = ST_NONE; r.dist = 0.f; r.U = 0.f; r.n = make_float3(0.f, 0.f, 0.f); r.have_n = 0;
+    const ShapeRef AH = hull_shape(tab, GA), BH = hull_shape(tab, GB);
+    const float margin = padding + GA.core_radius + GB.core_radius;
+    if (parked) {
+        // the centre line settles most parked items, the enclosing hull's 8 largest faces most of the rest
+        if (enclosure_quick_pokes(fl, GA, GB, AH, BH, T, padding) ||
+            enclosure_roles(tab.planes, fl, GA, GB, AH, BH, T, padding, 0, 1, 8, nullptr, nullptr) == ENC_POKES)
+            r.status = ST_HIT;
+        else
+            r.status = ST_WALK;
+        return r;
+    }
+    ConvOut h;
+    gjk_converge(AH, BH, T, gjk_start_direction(GA, GB, T), margin, h);
+    if (h.far || h.dist > margin) return r;                 // the hulls are apart: free
+    ConvOut k = h;
+    if (!(fl & PAIR_NOCORE)) {
+        const ShapeRef AK = core_shape(tab, GA), BK = core_shape(tab, GB);
+        gjk_converge(AK, BK, T, gjk_start_direction(GA, GB, T), FLT_MAX, k);
+        if (k.dist - h.dist <= 1e-6f) { r.status = ST_HIT; return r; }   // both bounds agree: within the margin
+    }
+    r.status = ST_TRIANGLES;
+    r.U = margin;
+    const float vv = dot3(k.v, k.v);
+    if (k.dist > 0.f && vv > 1e-20f) {
+        const float inv = rsqrtf(vv);
+        r.n = make_float3(-k.v.x * inv, -k.v.y * inv, -k.v.z * inv);
+        r.have_n = 1;
+    }
+    return r;
+}
+
+// Distance queries.  cur: the state's current upper bound of the minimum (surface distance).
+__device__ __forceinline__ LaneVerdict decide_distance(const SurfTables &tab, int fl, const DevGeom &GA, const DevGeom &GB, const float *T, float cur) {
+    LaneVerdict r;
+    r.status = ST_NONE; r.dist = 0.f; r.U = 0.f; r.n = make_float3(0.f, 0.f, 0.f); r.have_n = 0;
+    const ShapeRef AH = hull_shape(tab, GA), BH = hull_shape(tab, GB);
+    const float radii = GA.core_radius + GB.core_radius;
+    ConvOut h;
+    gjk_converge(AH, BH, T, gjk_start_direction(GA, GB, T), cur + radii, h);
+    if (h.far || fmaxf(h.dist - radii, 0.f) > cur) return r;   // the surfaces are at least as far apart as the hulls
+    if (fl & PAIR_NOCORE) {
+        // no upper bound from a core: the triangles within the state's current bound decide
+        r.status = ST_TRIANGLES;
+        r.U = cur + radii + 1e-6f;
+        const float vv = dot3(h.v, h.v);
+        if (h.dist > 0.f && vv > 1e-20f) {
+            const float inv = rsqrtf(vv);
+            r.n = make_float3(-h.v.x * inv, -h.v.y * inv, -h.v.z * inv);
+            r.have_n = 1;
+        }
+        return r;
+    }
+    const ShapeRef AK = core_shape(tab, GA), BK = core_shape(tab, GB);
+    ConvOut k;
+    gjk_converge(AK, BK, T, gjk_start_direction(GA, GB, T), FLT_MAX, k);
+    if (k.dist > 0.f) {
+        if (k.dist - h.dist <= 2e-6f) { r.status = ST_VALUE; r.dist = h.dist; return r; }
+        r.status = ST_TRIANGLES;
+        r.U = fminf(k.dist, cur + radii) + 1e-6f;
+        const float vv = dot3(k.v, k.v);
+        if (vv > 1e-20f) {
+            const float inv = rsqrtf(vv);
+            r.n = make_float3(-k.v.x * inv, -k.v.y * inv, -k.v.z * inv);
+            r.have_n = 1;
+        }
+        return r;
+    }
+    // the cores overlap: the surfaces meet unless one shape is enclosed by the other's
+    if (!(fl & PAIR_ENCLOSE) || enclosure_quick_pokes(fl, GA, GB, AH, BH, T, 0.f)) { r.status = ST_VALUE; r.dist = 0.f; return r; }
+    r.status = ST_WALK;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp level: settle what the lanes left open
+// ------------------------------------------------------------------------------------------
+// Warp-level part shared by k_surface_refine and k_small_check.  Every lane arrives with its own item
+// (pair p, output group, placement T, lane verdict v); items whose verdict needs the warp (the walk over
+// the enclosing core's planes, the triangle stage) are taken one after the other, their data broadcast
+// from the owning lane.  on_hit(p, group, aux) / on_value(p, group, aux, surface distance) publish; they
+// are called by lane 0 only.  decided(group): skip an item whose group has been decided meanwhile
+// (boolean queries that stop at the first hit); evaluated by lane 0.
+template <int MODE, typename FHit, typename FValue, typename FDecided>
+__device__ __forceinline__ void settle_warp_items(const DevModel &M, const SurfTables &tab, const LaneVerdict &v, int p, int32_t group, int64_t aux,
+                                                  const float *T, float padding, uint16_t *la, uint16_t *lb, int lane, FHit on_hit, FValue on_value,
+                                                  FDecided decided) {
+    unsigned todo = __ballot_sync(0xffffffffu, v.status == ST_WALK || v.status == ST_TRIANGLES);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        float Ts[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) Ts[k] = __shfl_sync(0xffffffffu, T[k], src);
+        const int ps = __shfl_sync(0xffffffffu, p, src);
+        const int32_t gs = __shfl_sync(0xffffffffu, group, src);
+        const int64_t as = __shfl_sync(0xffffffffu, aux, src);
+        int st = __shfl_sync(0xffffffffu, v.status, src);
+        float U = __shfl_sync(0xffffffffu, v.U, src);
+        float3 n = make_float3(__shfl_sync(0xffffffffu, v.n.x, src), __shfl_sync(0xffffffffu, v.n.y, src), __shfl_sync(0xffffffffu, v.n.z, src));
+        int have_n = __shfl_sync(0xffffffffu, v.have_n, src);
+        int skip = lane == 0 ? (decided(gs) ? 1 : 0) : 0;      // one lane reads, everyone follows
+        skip = __shfl_sync(0xffffffffu, skip, 0);
+        if (skip) continue;
+        const int fl = M.pair_enclose[ps];
+        const BpPair pr = M.bppairs[ps];
+        const DevGeom &GA = M.geoms[pr.a];
+        const DevGeom &GB = M.geoms[pr.b];
+        const float radii = GA.core_radius + GB.core_radius;
+        if (st == ST_WALK) {
+            const ShapeRef AH = hull_shape(tab, GA), BH = hull_shape(tab, GB);
+            float gap = 0.f, tolo = 0.f;
+            const int res = enclosure_roles(tab.planes, fl, GA, GB, AH, BH, Ts, MODE == MODE_DIST ? 0.f : padding, lane, PBP_LANES, INT_MAX, &gap, &tolo);
+            if (res == ENC_POKES) {
+                if (lane == 0) { if (MODE == MODE_DIST) on_value(ps, gs, as, 0.f); else on_hit(ps, gs, as); }
+                continue;
+            }
+            if (MODE != MODE_DIST && res == ENC_ENCLOSED) continue;     // inside the other's surface, clear of it: free
+            // the triangles decide: no separating direction here, the bounding balls do the culling
+            st = ST_TRIANGLES;
+            have_n = 0;
+            U = MODE == MODE_DIST ? fmaxf(gap, 0.f) + tolo + radii + 1e-6f : padding + radii;
+        }
+        const float d = triangle_stage(tab, GA, GB, Ts, n, have_n != 0, U, MODE != MODE_DIST, la, lb, lane);
+        if (lane == 0 && d <= U) {
+            if (MODE == MODE_DIST) on_value(ps, gs, as, fmaxf(d - radii, 0.f)); else on_hit(ps, gs, as);
+        }
+    }
+}
+
+}  // namespace pbp

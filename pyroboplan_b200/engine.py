@@ -14,11 +14,12 @@ import os
 import numpy as np
 
 from .model.shapes import Box, Capsule, Convex, Cylinder, Sphere
+from .model.surface import surface_tables
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpbp_engine.so")
 
-PBP_ABI_VERSION = 4
+PBP_ABI_VERSION = 5
 
 # symbols declared in include/pbp_engine.h (tests check the library exports every one)
 EXPORTED_SYMBOLS = [
@@ -88,6 +89,19 @@ class _ModelDesc(ctypes.Structure):
         ("geom_surface_tol", ctypes.c_void_p),
         ("pair_enclose", ctypes.c_void_p),
         ("nplanes", ctypes.c_int32),
+        ("ncore", ctypes.c_int32),
+        ("nmverts", ctypes.c_int32),
+        ("ntris", ctypes.c_int32),
+        ("geom_plane_hull_cnt", ctypes.c_void_p),
+        ("core_verts", ctypes.c_void_p),
+        ("geom_core_off", ctypes.c_void_p),
+        ("geom_core_cnt", ctypes.c_void_p),
+        ("geom_core_eps", ctypes.c_void_p),
+        ("mesh_verts", ctypes.c_void_p),
+        ("geom_mvert_off", ctypes.c_void_p),
+        ("tris", ctypes.c_void_p),
+        ("geom_tri_off", ctypes.c_void_p),
+        ("geom_tri_cnt", ctypes.c_void_p),
     ]
 
 
@@ -204,13 +218,6 @@ def _could_enclose(outer, inner):
             and _shape_volume(inner) <= tol * _shape_volume(outer))
 
 
-def _planes_by_area(s):
-    """The hull's face planes, largest face first.  The enclosure test stops at the first face the inner
-    shape reaches; a shape that pokes out of a link almost always crosses one of its few large faces
-    (measured on config 2: 1.02 batches of 32 faces until the exit, against 6.6 in qhull's order)."""
-    return s.planes[np.argsort(-s.plane_areas, kind="stable")]
-
-
 def mesh_dent_depth(s):
     """How far the surface of a mesh lies below the surface of its convex hull (metres): the deepest
     sample of the mesh triangles' edges and centroids under the hull's face planes."""
@@ -302,27 +309,54 @@ def flatten_model(model, collision_model, mesh_semantics="surface"):
     a["verts"] = np.concatenate(verts).astype(np.float32) if verts else np.zeros((1, 3), dtype=np.float32)
     pairs = np.array([[p.first, p.second] for p in collision_model.collisionPairs], dtype=np.int32).reshape(-1, 2)
     a["pairs"] = pairs if len(pairs) else np.zeros((1, 2), dtype=np.int32)
-    # surface semantics of mesh geometries: hull face planes, dent depth, pairs where one shape could
-    # lie wholly inside the other's surface
+    # surface semantics of mesh geometries (model/surface.py): planes of the exact inner core (hull faces
+    # first, largest first), the simplified core's vertices, mesh vertices and triangles, pairs where one
+    # shape could lie wholly inside the other's surface
     if mesh_semantics not in ("surface", "hull"):
         raise ValueError("mesh_semantics must be 'surface' or 'hull'")
     surface = [mesh_semantics == "surface" and isinstance(g.geometry, Convex) and g.geometry.mesh_triangles is not None for g in geoms]
-    planes, plane_off, plane_cnt, tol = [], np.zeros(ng, np.int32), np.zeros(ng, np.int32), np.zeros(ng, np.float32)
+    zi = lambda: np.zeros(ng, np.int32)
+    planes, plane_off, plane_cnt, plane_hull, tol = [], zi(), zi(), zi(), np.zeros(ng, np.float32)
+    cores, core_off, core_cnt, core_eps = [], zi(), zi(), np.zeros(ng, np.float32)
+    mverts, mvert_off, tris, tri_off, tri_cnt = [], zi(), [], zi(), zi()
     for i, g in enumerate(geoms):
         plane_off[i] = sum(len(x) for x in planes)
-        if surface[i]:
-            pl = _planes_by_area(g.geometry)
-            planes.append(np.concatenate([pl[:, :3], -pl[:, 3:4]], axis=1))
-            plane_cnt[i] = len(pl)
-            tol[i] = mesh_dent_depth(g.geometry)
+        core_off[i] = sum(len(x) for x in cores)
+        mvert_off[i] = sum(len(x) for x in mverts)
+        tri_off[i] = sum(len(x) for x in tris)
+        if not surface[i]:
+            continue
+        st = surface_tables(g.geometry)
+        nh = st["n_hull_planes"]
+        order = np.concatenate([np.argsort(-st["plane_areas"][:nh], kind="stable"), np.arange(nh, len(st["core_planes"]))])
+        planes.append(st["core_planes"][order])
+        plane_cnt[i], plane_hull[i] = len(order), nh
+        tol[i] = _up32(st["surface_tol"])
+        mverts.append(st["mesh_verts"])
+        tris.append(st["tris"])
+        tri_cnt[i] = len(st["tris"])
+        if st["has_core"]:
+            cores.append(st["core"])
+            core_cnt[i] = len(st["core"])
+            core_eps[i] = _up32(st["core_eps"])
+            # the broadphase's "certainly colliding" ball must lie inside the CORE (and so inside the mesh)
+            kp = st["core_hull_planes"]
+            c64 = a["geom_inner"][i, :3].astype(np.float64)
+            a["geom_inner"][i, 3] = np.float32(max(float((kp[:, 3] - kp[:, :3] @ c64).min()) - 2e-6, 0.0))
+        else:
+            a["geom_inner"][i, 3] = 0.0
     enclose = np.zeros(max(len(pairs), 1), np.uint8)
     for k, (ga, gb) in enumerate(pairs):
         if surface[ga] and _could_enclose(geoms[ga].geometry, geoms[gb].geometry):
             enclose[k] |= 1
         if surface[gb] and _could_enclose(geoms[gb].geometry, geoms[ga].geometry):
             enclose[k] |= 2
-    a["planes"] = np.concatenate(planes).astype(np.float32) if planes else np.zeros((1, 4), dtype=np.float32)
-    a["geom_plane_off"], a["geom_plane_cnt"], a["geom_surface_tol"], a["pair_enclose"] = plane_off, plane_cnt, tol, enclose
+    cat = lambda parts, shape, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(shape, dtype=dt)
+    a["planes"] = cat(planes, (1, 4), np.float32)
+    a["geom_plane_off"], a["geom_plane_cnt"], a["geom_plane_hull_cnt"], a["geom_surface_tol"], a["pair_enclose"] = plane_off, plane_cnt, plane_hull, tol, enclose
+    a["core_verts"], a["geom_core_off"], a["geom_core_cnt"], a["geom_core_eps"] = cat(cores, (1, 3), np.float32), core_off, core_cnt, core_eps
+    a["mesh_verts"], a["geom_mvert_off"] = cat(mverts, (1, 3), np.float32), mvert_off
+    a["tris"], a["geom_tri_off"], a["geom_tri_cnt"] = cat(tris, (1, 3), np.int32), tri_off, tri_cnt
     a["frame_parent"] = np.array([f.parentJoint for f in model.frames], dtype=np.int32)
     a["frame_placement"] = np.array([_se3_row(f.placement) for f in model.frames], dtype=np.float32)
     # float64 kinematic tables for the FP64 differential-IK kernel
@@ -332,7 +366,7 @@ def flatten_model(model, collision_model, mesh_semantics="surface"):
     a["q_lower_f64"] = np.asarray(model.lowerPositionLimit, dtype=np.float64)
     a["q_upper_f64"] = np.asarray(model.upperPositionLimit, dtype=np.float64)
     sizes = dict(nq=model.nq, njoints=model.njoints, ngeoms=ng, npairs=len(pairs), nverts=nv, nframes=len(model.frames),
-                 nplanes=int(plane_cnt.sum()))
+                 nplanes=int(plane_cnt.sum()), ncore=int(core_cnt.sum()), nmverts=int(sum(len(x) for x in mverts)), ntris=int(tri_cnt.sum()))
     return {k: np.ascontiguousarray(v) for k, v in a.items()}, sizes
 
 
@@ -392,8 +426,10 @@ class CollisionEngine:
         self.mesh_semantics = mesh_semantics
         self.nq, self.njoints, self.ngeoms = sizes["nq"], sizes["njoints"], sizes["ngeoms"]
         self.npairs, self.nframes = sizes["npairs"], sizes["nframes"]
-        if sizes["nplanes"] == 0:   # no surface geometry: the optional tables stay NULL
-            arrays = {k: v for k, v in arrays.items() if k not in ("planes", "geom_plane_off", "geom_plane_cnt", "geom_surface_tol", "pair_enclose")}
+        if sizes["ntris"] == 0:   # no surface geometry: the optional tables stay NULL
+            arrays = {k: v for k, v in arrays.items() if k not in (
+                "planes", "geom_plane_off", "geom_plane_cnt", "geom_plane_hull_cnt", "geom_surface_tol", "pair_enclose", "core_verts", "geom_core_off",
+                "geom_core_cnt", "geom_core_eps", "mesh_verts", "geom_mvert_off", "tris", "geom_tri_off", "geom_tri_cnt")}
         desc = _ModelDesc()
         for k, v in sizes.items():
             setattr(desc, k, v)

@@ -1,0 +1,226 @@
+"""Surface tables of mesh geometries: what the engine needs to answer EXACTLY like a triangle mesh.
+
+Pinocchio loads a URDF ``<mesh>`` as a coal ``BVHModel`` -- the surface triangles
+(/root/reference/src/pyroboplan/models/panda.py:27 -> ``pinocchio.buildModelsFromUrdf``).  The engine's
+hot kernels run GJK on convex polytopes, so a mesh M (enclosing the solid S) is bracketed by two of
+them:
+
+* the hull ``H`` of its vertices (``S`` lies inside ``H``): ``d(H_a, H_b)`` is a LOWER bound of the
+  surface distance, a pair whose hulls are apart by more than the margin is certainly free;
+* the inner core ``K`` = the intersection of the inner half-spaces of all mesh triangles (``K`` lies
+  inside ``S`` when the mesh is closed and ``K`` is not empty): ``d(K_a, K_b)`` is an UPPER bound, a
+  pair whose cores are within the margin certainly collides (or one shape encloses the other).
+
+Only the items between the two bounds (the Panda's hulls and cores differ by 0.3 - 1 mm around the
+near-planar quads its meshes triangulate along the valley) need the triangles themselves; the
+kernels then test triangle pairs exactly (``pbp_surface.cuh``).  Everything here is host-side model
+compilation (numpy / qhull), done once per geometry and cached on it.
+"""
+
+import numpy as np
+
+_CACHE_ATTR = "_pbp_surface_tables"
+_CACHE = {}            # content hash of (vertices, triangles) -> tables: models are loaded many times per process
+_CORE_DELTA = 1e-4     # the simplified core may lie this far inside the exact one (metres)
+
+
+def _simplify_core(hull_pts, kfull, kplanes, delta):
+    """A subset of the exact core's vertices whose hull is within ``delta`` of it: the hull vertices the
+    cuts left alone, then the farthest remaining core vertex until none is farther than delta.  (The
+    exact core of a Panda link has ~1.7 x the hull's vertices, most of them on fans of nearly coincident
+    cuts; the subset has about as many as the hull, so the GJK tables keep their size.  Any subset of
+    core vertices spans a subset of the core: it stays inside the mesh.)  Returns float32 vertices."""
+    from scipy.spatial import ConvexHull
+
+    uncut = (hull_pts @ kplanes[:, :3].T - kplanes[:, 3]).max(axis=1) <= 1e-9
+    pts = [p for p in hull_pts[uncut]]
+    if len(pts) < 4:
+        pts = [p for p in kfull]
+    cand = kfull
+    for _ in range(len(kfull)):
+        eq = ConvexHull(np.array(pts)).equations
+        ex = (cand @ eq[:, :3].T + eq[:, 3]).max(axis=1)
+        j = int(np.argmax(ex))
+        if ex[j] < delta:
+            break
+        pts.append(cand[j])
+    p32 = np.unique(np.array(pts).astype(np.float32), axis=0)
+    h = ConvexHull(p32.astype(np.float64))
+    return np.ascontiguousarray(p32[np.sort(h.vertices)])
+
+
+def _unit_planes_of_triangles(verts, tris, inside):
+    """Outward unit plane (n, w), n.x <= w on the inner side, of every non-degenerate triangle;
+    oriented by the interior point ``inside``.  Returns (planes [m, 4] = nx ny nz w, kept mask)."""
+    t = verts[tris]
+    n = np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0])
+    ln = np.linalg.norm(n, axis=1)
+    scale = max(float(np.abs(verts).max()), 1e-30)
+    ok = ln > 1e-12 * scale * scale
+    n = n[ok] / ln[ok, None]
+    w = np.einsum("ij,ij->i", n, t[ok, 0])
+    flip = n @ inside - w > 0.0
+    n[flip] *= -1.0
+    w[flip] *= -1.0
+    return np.concatenate([n, w[:, None]], axis=1), ok
+
+
+def _is_closed(tris):
+    """Every undirected edge is shared by exactly two triangles."""
+    e = np.sort(np.concatenate([tris[:, [0, 1]], tris[:, [1, 2]], tris[:, [2, 0]]]), axis=1)
+    _, cnt = np.unique(e, axis=0, return_counts=True)
+    return bool(len(cnt)) and bool((cnt == 2).all())
+
+
+def _feasible_point_near(v, planes, centre, iters=60):
+    """A point of {x : n.x <= w} close to v: cyclic projection on the most violated plane, then a pull
+    towards the (strictly interior) centre.  |v - result| bounds the distance of v to the set."""
+    x = v.copy()
+    n, w = planes[:, :3], planes[:, 3]
+    for _ in range(iters):
+        e = n @ x - w
+        k = int(np.argmax(e))
+        if e[k] <= 0.0:
+            return x
+        x = x - e[k] * n[k]
+    e = n @ x - w
+    d = n @ (x - centre)
+    t = np.where(e > 0.0, e / np.maximum(d, 1e-300), 0.0).max()
+    return x + min(t, 1.0) * (centre - x)
+
+
+def _point_triangles_dist(p, tri):
+    """Distances from the points p [m, 3] to the closest of the triangles tri [k, 3, 3] (vectorised
+    Ericson 5.1.5 on all pairs).  Used at model compilation only (a few thousand points)."""
+    a, b, c = tri[None, :, 0], tri[None, :, 1], tri[None, :, 2]
+    P = p[:, None, :]
+    ab, ac, ap = b - a, c - a, P - a
+    d1, d2 = (ab * ap).sum(-1), (ac * ap).sum(-1)
+    bp = P - b
+    d3, d4 = (ab * bp).sum(-1), (ac * bp).sum(-1)
+    cp = P - c
+    d5, d6 = (ab * cp).sum(-1), (ac * cp).sum(-1)
+    va, vb, vc = d3 * d6 - d5 * d4, d5 * d2 - d1 * d6, d1 * d4 - d3 * d2
+    best = np.full(d1.shape, np.inf)
+
+    def upd(mask, q):
+        d = np.linalg.norm(P - q, axis=-1)
+        np.copyto(best, np.where(mask & (d < best), d, best))
+
+    with np.errstate(divide="ignore", invalid="ignore"):
+        upd((d1 <= 0) & (d2 <= 0), a + 0 * P)
+        upd((d3 >= 0) & (d4 <= d3), b + 0 * P)
+        upd((d6 >= 0) & (d5 <= d6), c + 0 * P)
+        t = np.clip(np.nan_to_num(d1 / (d1 - d3)), 0, 1)
+        upd((vc <= 0) & (d1 >= 0) & (d3 <= 0), a + t[..., None] * ab)
+        t = np.clip(np.nan_to_num(d2 / (d2 - d6)), 0, 1)
+        upd((vb <= 0) & (d2 >= 0) & (d6 <= 0), a + t[..., None] * ac)
+        t = np.clip(np.nan_to_num((d4 - d3) / ((d4 - d3) + (d5 - d6))), 0, 1)
+        upd((va <= 0) & ((d4 - d3) >= 0) & ((d5 - d6) >= 0), b + t[..., None] * (c - b))
+        den = va + vb + vc
+        v = np.nan_to_num(vb / den)
+        w = np.nan_to_num(vc / den)
+        inside = (va > 0) & (vb > 0) & (vc > 0)
+        upd(inside, a + v[..., None] * ab + w[..., None] * ac)
+    # whatever region test failed numerically: the vertices are always valid candidates
+    for q in (a, b, c):
+        upd(np.ones_like(inside), q + 0 * P)
+    return best.min(axis=1)
+
+
+def surface_tables(shape):
+    """Tables of a mesh geometry (``Convex`` with ``mesh_triangles``), cached on the shape:
+
+    ``mesh_verts``  [nv, 3] float32   unique mesh vertices (STL coordinates are float32 already)
+    ``tris``        [nt, 3] int32     vertex indices of the non-degenerate triangles
+    ``core``        [nk, 3] float32   vertices of the inner core K (== hull vertices when there is none)
+    ``core_eps``    float             every point of the hull H is within this of K (metres); inf without a core
+    ``core_planes`` [np, 4] float64   n.x <= w planes of K: the hull's face planes first ...
+    ``n_hull_planes`` int             ... this many; the rest are planes of mesh triangles below the hull
+    ``plane_areas`` [np]              area of the face behind each plane (hull planes), 0 for the rest
+    ``surface_tol`` float             two-sided distance between the hull's boundary and the mesh (metres)
+    ``core_hull_planes`` [m, 4]       face planes of the (simplified) core actually used: its inscribed radius
+    ``has_core``    bool
+    """
+    cached = getattr(shape, _CACHE_ATTR, None)
+    if cached is not None:
+        return cached
+    from scipy.spatial import ConvexHull, HalfspaceIntersection
+    import hashlib
+
+    v64 = np.asarray(shape.mesh_vertices, dtype=np.float64)
+    key = hashlib.sha1(np.ascontiguousarray(v64).tobytes() + np.ascontiguousarray(np.asarray(shape.mesh_triangles, dtype=np.int64)).tobytes()).hexdigest()
+    if key in _CACHE:
+        setattr(shape, _CACHE_ATTR, _CACHE[key])
+        return _CACHE[key]
+    v32 = v64.astype(np.float32)
+    uv, inv = np.unique(v32, axis=0, return_inverse=True)
+    tris = inv.reshape(-1)[np.asarray(shape.mesh_triangles, dtype=np.int64)].astype(np.int32)
+    nondeg = (tris[:, 0] != tris[:, 1]) & (tris[:, 1] != tris[:, 2]) & (tris[:, 0] != tris[:, 2])
+    tris = np.ascontiguousarray(tris[nondeg])
+    V = uv.astype(np.float64)
+
+    hull_planes = np.concatenate([shape.planes[:, :3], -shape.planes[:, 3:4]], axis=1)    # n.x <= w
+    hull_areas = np.asarray(shape.plane_areas, dtype=np.float64)
+    centre, r_in = shape.inner_sphere()
+    centre = np.asarray(centre, dtype=np.float64)
+
+    out = {
+        "mesh_verts": np.ascontiguousarray(uv), "tris": tris,
+        "core": np.ascontiguousarray(np.asarray(shape.points, dtype=np.float32)), "core_eps": np.inf,
+        "core_planes": hull_planes, "n_hull_planes": len(hull_planes), "plane_areas": hull_areas,
+        "surface_tol": 0.0, "has_core": False, "core_hull_planes": hull_planes,
+    }
+
+    # ---- two-sided distance between the hull's boundary and the mesh surface
+    T = V[tris]
+    ts = np.linspace(0.0, 1.0, 7)[1:-1]
+    samples = [T.mean(axis=1)]
+    for i, j in ((0, 1), (1, 2), (2, 0)):
+        samples.append((T[:, i, None, :] * (1 - ts)[None, :, None] + T[:, j, None, :] * ts[None, :, None]).reshape(-1, 3))
+    x = np.concatenate(samples)
+    below = (-(x @ hull_planes[:, :3].T - hull_planes[:, 3])).min(axis=1)     # mesh point -> nearest hull plane
+    tol_in = float(max(below.max(), 0.0))
+    hull = ConvexHull(np.asarray(shape.points, dtype=np.float64))
+    HT = np.asarray(shape.points, dtype=np.float64)[hull.simplices]
+    bary = np.array([[1 / 3, 1 / 3, 1 / 3], [0.5, 0.5, 0], [0, 0.5, 0.5], [0.5, 0, 0.5], [0.6, 0.2, 0.2], [0.2, 0.6, 0.2], [0.2, 0.2, 0.6]])
+    hp = np.einsum("sb,fbk->fsk", bary, HT).reshape(-1, 3)
+    # only hull faces that are not mesh triangles themselves can be away from the mesh
+    tol_out = 0.0
+    for s0 in range(0, len(hp), 256):
+        tol_out = max(tol_out, float(_point_triangles_dist(hp[s0:s0 + 256], T).max()))
+    out["surface_tol"] = 1.5 * max(tol_in, tol_out) + 1e-7     # samples, not maxima: keep a margin
+
+    # ---- inner core: K = hull /\ inner half-spaces of every mesh triangle
+    tri_planes, _ = _unit_planes_of_triangles(V, tris, centre)
+    closed = _is_closed(tris)
+    slack_c = (tri_planes[:, :3] @ centre - tri_planes[:, 3]).max() if len(tri_planes) else 0.0
+    if closed and slack_c < -1e-6 and r_in > 1e-6:
+        # the planes of mesh triangles that lie ON a hull face add nothing
+        onhull = np.zeros(len(tri_planes), dtype=bool)
+        for k, pl in enumerate(tri_planes):
+            onhull[k] = bool((np.abs(hull_planes[:, :3] @ pl[:3] - 1.0) < 1e-9).any() and
+                             (np.abs(hull_planes[:, 3] - pl[3])[np.abs(hull_planes[:, :3] @ pl[:3] - 1.0) < 1e-9] < 1e-9).any())
+        extra = tri_planes[~onhull]
+        allp = np.concatenate([hull_planes, extra])
+        try:
+            hs = HalfspaceIntersection(np.concatenate([allp[:, :3], -allp[:, 3:4]], axis=1), centre)
+            kfull = np.unique(np.round(hs.intersections, 12), axis=0)
+            core = _simplify_core(np.asarray(shape.points, dtype=np.float64), kfull, allp, _CORE_DELTA)
+            kh = ConvexHull(core.astype(np.float64))
+            # every hull vertex is within eps of the float32 core actually used on the device
+            kp = np.unique(np.round(kh.equations, 10), axis=0)
+            kpl = np.concatenate([kp[:, :3], -kp[:, 3:4]], axis=1)
+            kc = core.astype(np.float64).mean(axis=0)
+            eps = 0.0
+            for p in np.asarray(shape.points, dtype=np.float64):
+                if (kpl[:, :3] @ p - kpl[:, 3]).max() <= 0.0:
+                    continue
+                eps = max(eps, float(np.linalg.norm(p - _feasible_point_near(p, kpl, kc))))
+            out.update(core=core, core_eps=eps * 1.02 + 2e-7, core_planes=allp, plane_areas=np.concatenate([hull_areas, np.zeros(len(extra))]),
+                       core_hull_planes=kpl, has_core=True)
+        except Exception:   # qhull could not build the intersection: the geometry stays without a core
+            pass
+    setattr(shape, _CACHE_ATTR, out)
+    _CACHE[key] = out
+    return out

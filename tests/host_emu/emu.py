@@ -9,7 +9,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libgjk_emu.so")
 _SRC = os.path.join(_HERE, "gjk_emu.cpp")
-_HDRS = [os.path.join(_HERE, "..", "..", "pyroboplan_b200", "csrc", f) for f in ("pbp_gjk.cuh", "pbp_model.cuh", "pbp_supmap.h", "pbp_witness.cuh")]
+_HDRS = [os.path.join(_HERE, "..", "..", "pyroboplan_b200", "csrc", f) for f in ("pbp_gjk.cuh", "pbp_model.cuh", "pbp_supmap.h", "pbp_witness.cuh", "pbp_surface.cuh", "pbp_host_tables.h")]
 _lib = None
 
 
@@ -39,6 +39,8 @@ def load():
         _lib.emu_gjk_witness_batch.restype = None
         _lib.emu_supmap_check.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int64, vp]
         _lib.emu_supmap_check.restype = None
+        _lib.emu_surface_items.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int64, ctypes.c_float, ctypes.c_int, vp, vp, vp]
+        _lib.emu_last_error.restype = ctypes.c_char_p
     return _lib
 
 
@@ -113,3 +115,25 @@ def gjk_witness_batch(arrays, ga, gb, T, v0, cutoff=np.inf):
                               int(arrays["geom_shape"][gb]), p(pb), p(vb), len(vb) if arrays["geom_vert_cnt"][gb] else 0,
                               p(T), p(v0), n, ra, rb, float(cutoff), p(out))
     return dict(dist=out[:, 0], hit=out[:, 1].astype(bool), far=out[:, 2].astype(bool), pa=out[:, 3:6], pb=out[:, 6:9], n=out[:, 9:12])
+
+
+def surface_items(model, collision_model, pair, T, padding=0.0, mode=0):
+    """The engine's answer for placements T [n, 12] (b in a's frame) of the caller's pair index `pair`,
+    evaluated by the host build of pbp_surface.cuh.  Returns (hit [n], dist [n], path [n])."""
+    from pyroboplan_b200 import engine
+
+    lib = load()
+    arrays, sizes = engine.flatten_model(model, collision_model)
+    desc = engine._ModelDesc()
+    for k, v in sizes.items():
+        setattr(desc, k, v)
+    for k, v in arrays.items():
+        setattr(desc, k, v.ctypes.data)
+    T = np.ascontiguousarray(T, dtype=np.float32).reshape(-1, 12)
+    n = len(T)
+    hit, dist, path = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.int32)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    rc = lib.emu_surface_items(ctypes.byref(desc), int(pair), p(T), n, float(padding), int(mode), p(hit), p(dist), p(path))
+    if rc:
+        raise RuntimeError(lib.emu_last_error().decode())
+    return hit, dist, path

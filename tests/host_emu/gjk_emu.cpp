@@ -5,7 +5,12 @@
 // narrowphase (fmaf / IEEE sqrt / division are identical on host and device; only rsqrtf is
 // emulated) against the float64 oracle on many random pairs.
 #include <cmath>
+#include <cstdarg>
 #include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -100,5 +105,114 @@ void emu_supmap_check(const float *verts4, int nv, const float *dirs, int64_t nd
         if (pbp::dot3(a, d) != pbp::dot3(b, d)) bad++;
     }
     out[2] = bad;
+}
+}
+
+// ------------------------------------------------------------------------------------------
+// Surface semantics (pbp_surface.cuh) on the host: one "lane" walks every warp-level loop.
+// ------------------------------------------------------------------------------------------
+static std::string g_emu_error;
+static int emu_fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_emu_error = buf;
+    return code;
+}
+#define PBP_HOST_FAIL emu_fail
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
+static inline int __any_sync(unsigned, int p) { return p; }
+static inline void __syncwarp() {}
+#include "../../pyroboplan_b200/csrc/pbp_host_tables.h"
+#include "../../pyroboplan_b200/csrc/pbp_surface.cuh"
+
+extern "C" {
+
+const char *emu_last_error() { return g_emu_error.c_str(); }
+
+// What the engine answers for n placements T [n][12] (b in a's frame) of the caller's pair `pair`:
+// the narrowphase's GJK on the cores (boolean) / hulls (distance), then the refine kernel's lane and
+// warp decisions.  mode 0: out_hit[i] = verdict at `padding`; mode 2: out_dist[i] = surface distance
+// of the pair (the state's running minimum starts at +inf).  out_path[i]: 0 decided by the GJK alone,
+// 1 lane level (hull / core runs, quick enclosure tests), 2 plane walk, 3 triangle stage.
+int emu_surface_items(const pbp_model_desc *d, int pair, const float *T, int64_t n, float padding, int mode, int32_t *out_hit, float *out_dist,
+                      int32_t *out_path) {
+    HostTables H;
+    int rc = build_host_tables(d, H);
+    if (rc) return rc;
+    int p = -1;
+    for (int k = 0; k < d->npairs; k++)
+        if (H.pair_orig[k] == pair) p = k;
+    if (p < 0) return emu_fail(-1, "no such pair");
+    DevModel M{};
+    M.npairs = d->npairs; M.ngeoms = d->ngeoms;
+    M.geoms = H.geoms.data(); M.bppairs = H.bppairs.data(); M.pair_enclose = H.pair_flags.data();
+    M.has_tris = H.has_tris ? 1 : 0;
+    std::vector<float4> planes((size_t)std::max(d->nplanes, 1));
+    for (int i = 0; i < d->nplanes; i++) planes[i] = make_float4(d->planes[4 * i], d->planes[4 * i + 1], d->planes[4 * i + 2], d->planes[4 * i + 3]);
+    SurfTables tab{};
+    tab.hverts = H.verts.data(); tab.hcells = H.sup_cells.data(); tab.hlists = H.sup_lists.data();
+    tab.kverts = H.has_tris ? H.kverts.data() : H.verts.data();
+    tab.kcells = H.has_tris ? H.ksup_cells.data() : H.sup_cells.data();
+    tab.klists = H.has_tris ? H.ksup_lists.data() : H.sup_lists.data();
+    tab.planes = planes.data(); tab.mverts = H.mverts.data(); tab.tris = H.tris.data();
+    const BpPair pr = H.bppairs[p];
+    const DevGeom &GA = H.geoms[pr.a];
+    const DevGeom &GB = H.geoms[pr.b];
+    const int fl = H.pair_flags[p];
+    const float radii = GA.core_radius + GB.core_radius;
+    const float margin = padding + radii;
+    std::vector<uint16_t> la(TRI_LIST_CAP), lb(TRI_LIST_CAP);
+    for (int64_t i = 0; i < n; i++) {
+        const float *Ti = T + 12 * i;
+        int hit = 0, path = 0;
+        float best = INFINITY;
+        auto on_hit = [&](int, int32_t, int64_t) { hit = 1; };
+        auto on_value = [&](int, int32_t, int64_t, float dd) { best = std::min(best, dd); if (dd <= padding) hit = 1; };
+        auto decided = [&](int32_t) { return false; };
+        LaneVerdict v;
+        v.status = ST_NONE; v.dist = 0.f; v.U = 0.f; v.n = make_float3(0.f, 0.f, 0.f); v.have_n = 0;
+        if (mode == MODE_DIST) {
+            const ShapeRef A = hull_shape(tab, GA), B = hull_shape(tab, GB);
+            const GjkOut r = gjk_run<true>(A, B, Ti, gjk_start_direction(GA, GB, Ti), margin, INFINITY);
+            if (fl & PAIR_SURFACE) {
+                path = 1;
+                v = decide_distance(tab, fl, GA, GB, Ti, INFINITY);
+                if (v.status == ST_VALUE) on_value(p, 0, 0, fmaxf(v.dist - radii, 0.f));
+                if (v.status == ST_WALK) path = 2;
+                if (v.status == ST_TRIANGLES) path = 3;
+                settle_warp_items<MODE_DIST>(M, tab, v, p, 0, (int64_t)0, Ti, padding, la.data(), lb.data(), 0, on_hit, on_value, decided);
+            } else {
+                on_value(p, 0, 0, fmaxf(r.dist - radii, 0.f));
+            }
+        } else {
+            const ShapeRef A = core_shape(tab, GA), B = core_shape(tab, GB);
+            const GjkOut r = gjk_run<false>(A, B, Ti, gjk_start_direction(GA, GB, Ti), margin, margin + pair_eps(GA, GB));
+            bool parked = false, doubt = false;
+            if (fl & PAIR_SURFACE) {
+                if (r.hit && (fl & PAIR_NOCORE)) doubt = true;
+                else if (r.hit && (fl & PAIR_ENCLOSE)) parked = true;
+                else if (!r.hit && !r.far) doubt = true;
+            }
+            if (!parked && !doubt) {
+                hit = r.hit;
+            } else {
+                path = 1;
+                v = decide_boolean(tab, fl, parked, GA, GB, Ti, padding);
+                if (v.status == ST_HIT) hit = 1;
+                if (v.status == ST_WALK) path = 2;
+                if (v.status == ST_TRIANGLES) path = 3;
+                settle_warp_items<MODE_BOOL>(M, tab, v, p, 0, (int64_t)0, Ti, padding, la.data(), lb.data(), 0, on_hit, on_value, decided);
+            }
+        }
+        out_hit[i] = hit;
+        out_dist[i] = best;
+        out_path[i] = path;
+    }
+    return 0;
 }
 }
