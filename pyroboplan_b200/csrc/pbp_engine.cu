@@ -313,7 +313,8 @@ int check_args(pbp_engine *e, const void *a, int64_t n) {
     if (!e) return fail(PBP_ERR_ARG, "engine is NULL");
     if (n < 0) return fail(PBP_ERR_ARG, "negative count");
     if (n > 0 && !a) return fail(PBP_ERR_ARG, "NULL buffer");
-    if (n > (int64_t)INT32_MAX) return fail(PBP_ERR_ARG, "more than 2^31-1 states/edges per call are not supported");
+    // (group ids travel through the bins with two flag bits, SR_PARKED / SR_DOUBT, on top)
+    if (n >= (int64_t)SR_DOUBT) return fail(PBP_ERR_ARG, "more than 2^29-1 states/edges per call are not supported");
     return 0;
 }
 
@@ -321,6 +322,7 @@ int check_args(pbp_engine *e, const void *a, int64_t n) {
 
 #define PBP_HOST_FAIL fail
 #include "pbp_host_tables.h"
+static_assert(pbp::BP_MAX_SAVES_HOST == pbp::BP_MAX_SAVES, "broadphase save slots mismatch");
 
 // CUDA source of the model-specialised broadphase (empty string when the model does not qualify).
 static std::string specialised_broadphase_source(const pbp_model_desc *d, const HostTables &H) {

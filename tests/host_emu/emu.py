@@ -11,6 +11,7 @@ _LIB = os.path.join(_HERE, "libgjk_emu.so")
 _SRC = os.path.join(_HERE, "gjk_emu.cpp")
 _HDRS = [os.path.join(_HERE, "..", "..", "pyroboplan_b200", "csrc", f) for f in ("pbp_gjk.cuh", "pbp_model.cuh", "pbp_supmap.h", "pbp_witness.cuh", "pbp_surface.cuh", "pbp_host_tables.h")]
 _lib = None
+_flat_cache = {}
 
 
 def cuda_include():
@@ -123,12 +124,16 @@ def surface_items(model, collision_model, pair, T, padding=0.0, mode=0):
     from pyroboplan_b200 import engine
 
     lib = load()
-    arrays, sizes = engine.flatten_model(model, collision_model)
-    desc = engine._ModelDesc()
-    for k, v in sizes.items():
-        setattr(desc, k, v)
-    for k, v in arrays.items():
-        setattr(desc, k, v.ctypes.data)
+    key = (id(model), id(collision_model), len(collision_model.collisionPairs))
+    if _flat_cache.get("key") != key:
+        arrays, sizes = engine.flatten_model(model, collision_model)
+        desc = engine._ModelDesc()
+        for k, v in sizes.items():
+            setattr(desc, k, v)
+        for k, v in arrays.items():
+            setattr(desc, k, v.ctypes.data)
+        _flat_cache.update(key=key, arrays=arrays, desc=desc)
+    desc = _flat_cache["desc"]
     T = np.ascontiguousarray(T, dtype=np.float32).reshape(-1, 12)
     n = len(T)
     hit, dist, path = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.int32)

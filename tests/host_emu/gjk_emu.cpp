@@ -141,9 +141,15 @@ const char *emu_last_error() { return g_emu_error.c_str(); }
 // 1 lane level (hull / core runs, quick enclosure tests), 2 plane walk, 3 triangle stage.
 int emu_surface_items(const pbp_model_desc *d, int pair, const float *T, int64_t n, float padding, int mode, int32_t *out_hit, float *out_dist,
                       int32_t *out_path) {
-    HostTables H;
-    int rc = build_host_tables(d, H);
-    if (rc) return rc;
+    // the Python driver keeps the flattened arrays of a model alive: rebuild the tables only for a new one
+    static HostTables H;
+    static const void *h_key = nullptr;
+    if (h_key != (const void *)d->verts) {
+        H = HostTables();
+        const int rc = build_host_tables(d, H);
+        if (rc) return rc;
+        h_key = (const void *)d->verts;
+    }
     int p = -1;
     for (int k = 0; k < d->npairs; k++)
         if (H.pair_orig[k] == pair) p = k;

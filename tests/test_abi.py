@@ -77,7 +77,11 @@ def test_flatten_model_is_conservative():
 
     model, cmodel, _ = make_panda()
     arrays, sizes = eng_mod.flatten_model(model, cmodel)
-    assert sizes == dict(nq=9, njoints=10, ngeoms=16, npairs=74, nverts=1204, nframes=model.nframes, nplanes=2364)
+    assert {k: sizes[k] for k in ("nq", "njoints", "ngeoms", "npairs", "nverts", "nmverts", "ntris")} == dict(
+        nq=9, njoints=10, ngeoms=16, npairs=74, nverts=1204, nmverts=1204, ntris=2364)
+    # planes of the exact inner cores: every hull face (= 2364 triangles' worth) plus the mesh triangles below the hulls
+    assert sizes["nplanes"] > 2364 and int(arrays["geom_plane_hull_cnt"].sum()) == 2364
+    assert 1000 < sizes["ncore"] < 1.2 * sizes["nverts"]     # the simplified cores keep the GJK tables' size
     for g, obj in enumerate(cmodel.geometryObjects):
         s = obj.geometry
         oc, orad = arrays["geom_outer"][g][:3].astype(np.float64), float(arrays["geom_outer"][g][3])
@@ -87,4 +91,20 @@ def test_flatten_model_is_conservative():
             v = arrays["verts"][off : off + cnt].astype(np.float64)
             assert np.all(np.linalg.norm(v - oc, axis=1) <= orad)
             assert np.all(s.planes[:, :3] @ ic + s.planes[:, 3] <= -irad)
+            if arrays["geom_tri_cnt"][g]:
+                # surface geometry: the "certainly colliding" ball lies inside every mesh triangle's inner half-space,
+                # and so do the core's vertices (the core is inside the mesh); the hull is within core_eps of the core
+                mo, to, tc = arrays["geom_mvert_off"][g], arrays["geom_tri_off"][g], arrays["geom_tri_cnt"][g]
+                tri = arrays["mesh_verts"].astype(np.float64)[mo + arrays["tris"][to : to + tc]]
+                n = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+                n /= np.linalg.norm(n, axis=1, keepdims=True)
+                w = (n * tri[:, 0]).sum(axis=1)
+                flip = n @ ic - w > 0
+                n[flip] *= -1
+                w[flip] *= -1
+                assert np.all(n @ ic - w <= -irad + 1e-9)
+                co, cc = arrays["geom_core_off"][g], arrays["geom_core_cnt"][g]
+                core = arrays["core_verts"][co : co + cc].astype(np.float64)
+                assert cc >= 4 and (core @ n.T - w).max() < 5e-8
+                assert 0 < arrays["geom_core_eps"][g] < 2e-3
         assert irad <= orad

@@ -15,7 +15,6 @@ pytestmark = pytest.mark.gpu
 
 BAND = 1e-6      # verdicts may differ only where |reference min distance - padding| <= BAND
 DIST_TOL = 1e-5  # metres
-DENT = 4e-4      # the Panda meshes lie up to 0.39 mm below their convex hulls (engine.mesh_dent_depth)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
@@ -50,14 +49,10 @@ def assert_verdicts(hit_gpu, hit_ref, min_dist_ref, padding=0.0):
 
 
 def assert_mesh_distances(dist, ref):
-    """Min distances of a model with meshes.  The oracle measures to the mesh TRIANGLES (the reference's
-    BVHModel surfaces), the engine to the convex hulls: equal within DIST_TOL, except where the nearest
-    feature lies in a dent of a mesh -- there the hull distance is smaller, by at most the dent depth
-    (measured: 0.16 % of the free Panda states exceed DIST_TOL, the largest gap is 0.17 mm)."""
-    gap = np.asarray(ref, dtype=np.float64) - np.asarray(dist, dtype=np.float64)
-    assert gap.min() > -DIST_TOL, gap.min()            # a hull never lies inside its mesh
-    assert gap.max() < DENT, gap.max()
-    assert (gap > DIST_TOL).mean() < 5e-3, (gap > DIST_TOL).mean()
+    """Min distances of a model with meshes: the oracle measures to the mesh TRIANGLES (the reference's BVHModel
+    surfaces), and so does the engine wherever hull and inner core disagree -- equal within DIST_TOL everywhere."""
+    err = np.abs(np.asarray(ref, dtype=np.float64) - np.asarray(dist, dtype=np.float64))
+    assert err.max() < DIST_TOL, (err.max(), int(np.argmax(err)))
 
 
 # ------------------------------------------------------------------------------------------ golden
@@ -87,11 +82,6 @@ def test_golden_states(name, which, panda_engine, two_dof_engine):
     padding = float(g["padding"])
     hit = eng.check_states(g["q"], padding)
     md_v = g["min_dist"]
-    if which == "panda" and padding > 0:
-        # hull distance vs triangle distance around the padding: a verdict may differ inside a dent's depth
-        near = np.abs(md_v - padding) < DENT
-        assert (np.asarray(hit).astype(bool) != g["hit"].astype(bool))[near].sum() <= 2
-        md_v = np.where(near, padding, md_v)
     assert_verdicts(hit, g["hit"], md_v, padding)
     hit2, dist, pair = eng.check_states(g["q"], padding, return_distance=True, return_pair=True)
     assert_verdicts(hit2, g["hit"], md_v, padding)
@@ -101,7 +91,7 @@ def test_golden_states(name, which, panda_engine, two_dof_engine):
     else:
         assert np.abs(dist[free] - g["min_dist"][free]).max() < DIST_TOL
     assert np.all(dist[~free] <= DIST_TOL)
-    clear = np.abs(g["min_dist"] - padding) > (DENT if which == "panda" and padding > 0 else BAND)
+    clear = np.abs(g["min_dist"] - padding) > BAND
     assert (pair[clear] == g["first_pair"][clear]).all()
 
 
@@ -251,7 +241,7 @@ def test_dropin_single_calls_match_batched(panda_full, panda_engine, panda_oracl
     for i in range(len(q)):
         assert bool(check_collisions_at_state(model, cmodel, q[i])) == bool(ref[i])
         if md[i] > BAND:
-            assert md[i] - DENT <= get_minimum_distance_at_state(model, cmodel, q[i]) <= md[i] + DIST_TOL
+            assert abs(get_minimum_distance_at_state(model, cmodel, q[i]) - md[i]) <= DIST_TOL
     free_idx = np.nonzero(ref == 0)[0]
     for i, j in zip(free_idx[:-1:2], free_idx[1::2]):
         path = discretize_joint_space_path([q[i], q[j]], 0.05)

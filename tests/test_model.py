@@ -178,7 +178,7 @@ def test_enclosing_capsules_contain_their_hulls():
 
 def test_surface_tables_of_the_panda():
     """pbp_model_desc surface tables (engine.flatten_model): the hull planes contain every hull vertex and are
-    sorted by face area, the dent depths are sub-millimetre, and the enclosure flags name exactly the pairs
+    sorted by face area, hull and inner core differ by less than 2 mm, and the enclosure flags name exactly the pairs
     whose second geometry is small enough to fit inside the first (never a primitive as the enclosing one)."""
     from pyroboplan_b200.engine import flatten_model
     from pyroboplan_b200.models import panda, two_dof
@@ -196,11 +196,15 @@ def test_surface_tables_of_the_panda():
             continue
         pl = a["planes"][off:off + cnt].astype(np.float64)
         v = a["verts"][a["geom_vert_off"][g]: a["geom_vert_off"][g] + a["geom_vert_cnt"][g]].astype(np.float64)
-        assert cnt == len(obj.geometry.planes)
+        nh = int(a["geom_plane_hull_cnt"][g])
+        assert nh == len(obj.geometry.planes) and nh < cnt          # hull faces first, then mesh triangles below the hull
         np.testing.assert_allclose(np.linalg.norm(pl[:, :3], axis=1), 1.0, atol=1e-6)
-        slack = (v @ pl[:, :3].T - pl[:, 3]).max(axis=0)
-        assert slack.max() < 2e-6 and slack.min() > -2e-6          # every plane supports the hull: it touches a vertex
-        assert 0.0 < a["geom_surface_tol"][g] < 5e-4                # dents of the collision meshes: <= 0.39 mm (link 3)
+        slack = (v @ pl[:nh, :3].T - pl[:nh, 3]).max(axis=0)
+        assert slack.max() < 2e-6 and slack.min() > -2e-6          # every hull plane supports the hull: it touches a vertex
+        cut = (v @ pl[nh:, :3].T - pl[nh:, 3]).max(axis=0)
+        assert cut.min() > -1e-7 and cut.max() < 2e-3              # the other planes cut a sliver off the hull (or touch it), at most ~1 mm deep
+        assert 0.0 < a["geom_surface_tol"][g] < 1e-3                # hull boundary <-> mesh surface: sub-millimetre (link 3: 0.39 mm dents)
+        assert 0.0 < a["geom_core_eps"][g] < 2e-3
     flagged = {(geoms[p.first].name, geoms[p.second].name): int(a["pair_enclose"][k]) for k, p in enumerate(cmodel.collisionPairs) if a["pair_enclose"][k]}
     assert len(flagged) == 17 and set(flagged.values()) == {1}
     for small in ("panda_leftfinger_0", "panda_rightfinger_0"):

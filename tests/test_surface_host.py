@@ -1,0 +1,75 @@
+"""Surface semantics on the CPU: the host build of the device headers (tests/host_emu: pbp_surface.cuh with one
+lane walking every warp-level loop, the product's own model tables from pbp_host_tables.h) against the
+float64 oracle's exact triangle distances, on Panda items at and around contact.
+
+What is checked is the chain the GPU runs per (state, pair) item -- GJK on the inner cores (boolean) or hulls
+(distance), the lane-level hull / core runs and enclosure tests, the plane walk, the triangle stage -- with the
+north_star bar: identical verdicts outside the 1e-6 m band, distances within 1e-5 m."""
+
+import collections
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu"))
+import emu  # noqa: E402
+
+from conftest import make_panda, uniform_states  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def near_items():
+    """(model, cmodel, {pair: [(T, triangle distance)]}) for pairs whose hulls are within 2 mm (or overlap)."""
+    from oracle.oracle import Oracle
+
+    model, cmodel, _ = make_panda()
+    orc = Oracle(model, cmodel)
+    orc_hull = Oracle(model, cmodel, mesh_semantics="hull")
+    pairs = [(p.first, p.second) for p in cmodel.collisionPairs]
+    q = uniform_states(model, 1200, 97).astype(np.float64)
+    bs = orc_hull._arrays["geom_bsphere"]
+    items = collections.defaultdict(list)
+    for i in range(len(q)):
+        _, oMg = orc_hull.fk(q[i])
+        centre = [oMg[g][:9].reshape(3, 3) @ bs[g, :3] + oMg[g][9:] for g in range(len(bs))]
+        for k, (ga, gb) in enumerate(pairs):
+            if np.linalg.norm(centre[ga] - centre[gb]) > bs[ga, 3] + bs[gb, 3] + 0.002:
+                continue
+            if orc_hull.pair_distance_placed(oMg, ga, gb)[0] > 0.002:
+                continue
+            Ra, ta, Rb, tb = oMg[ga][:9].reshape(3, 3), oMg[ga][9:], oMg[gb][:9].reshape(3, 3), oMg[gb][9:]
+            T = np.concatenate([(Ra.T @ Rb).reshape(9), Ra.T @ (tb - ta)])
+            items[k].append((T, orc.soup_pair_distance(oMg, ga, gb)))
+    assert sum(len(v) for v in items.values()) > 1000
+    return model, cmodel, items
+
+
+@pytest.mark.parametrize("padding", [0.0, 0.002])
+def test_boolean_items_match_the_triangle_oracle(near_items, padding):
+    model, cmodel, items = near_items
+    paths = collections.Counter()
+    for k, lst in items.items():
+        T = np.array([x[0] for x in lst])
+        ds = np.array([x[1] for x in lst])
+        hit, _, path = emu.surface_items(model, cmodel, k, T, padding=padding, mode=0)
+        bad = (hit.astype(bool) != (ds <= padding)) & (np.abs(ds - padding) > 1e-6)
+        assert not bad.any(), (k, ds[bad][:4], hit[bad][:4], path[bad][:4])
+        paths.update(int(x) for x in path)
+    # most items are decided by the core GJK alone; the lane-level runs, the plane walk (enclosures) and the
+    # triangle stage all occur in the sample
+    assert paths[0] > 0.8 * sum(paths.values()) and paths[1] > 0 and paths[2] > 0
+
+
+def test_pair_distances_match_the_triangle_oracle(near_items):
+    model, cmodel, items = near_items
+    worst, paths = 0.0, collections.Counter()
+    for k, lst in items.items():
+        T = np.array([x[0] for x in lst])
+        ds = np.array([x[1] for x in lst])
+        _, dist, path = emu.surface_items(model, cmodel, k, T, mode=2)
+        worst = max(worst, float(np.abs(dist - ds).max()))
+        paths.update(int(x) for x in path)
+    assert worst < 1e-5, worst
+    assert paths[3] > 20 and paths[2] > 5      # triangle stages and enclosures (distance of the enclosed shape to the surface)
