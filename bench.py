@@ -174,8 +174,8 @@ def run_reference(args, rank):
     model, cmodel = panda_models()
     orc = Oracle(model, cmodel)
     threads = len(os.sched_getaffinity(0))
-    sample = int(os.environ.get("PBP_REF_SAMPLE", 200_000))
-    batches = [make_batch(model, sample, 1000 + b).astype(np.float64) for b in range(2)]
+    sample = int(os.environ.get("PBP_REF_SAMPLE", args.states))   # the GPU arm's step: 1 Mi states
+    batches = [make_batch(model, sample, 7919 * 0 + b).astype(np.float64) for b in range(2)]   # rank 0's first two batches of the GPU arm
     for w in range(max(args.warmup, 1)):
         orc.check_states(batches[w % 2][: sample // 4], use_cull=1, nthreads=threads)
     t0 = time.perf_counter()
@@ -188,7 +188,11 @@ def run_reference(args, rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "states_per_step": sample, "note": "CPU restatement (oracle/pbp_oracle.c), not Pinocchio/coal: those are not installable here"},
+        "config": {"workload": WORKLOAD, "states_per_gpu_per_step": sample,
+                   "l2": f"inputs rotate over {N_BATCHES} batches ({N_BATCHES * sample * 36 / 1e6:.0f} MB > 126 MB L2)",
+                   "parallelism": f"{args.gpus} rank(s), states sharded, no data-path collective",
+                   "note": "CPU arm: float64 restatement of the reference path (oracle/pbp_oracle.c) on all host threads of rank 0 -- NOT "
+                           "Pinocchio/coal, which are not installable here (a Pinocchio probe runs first: see `pinocchio`)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} states/step x {args.steps} steps of the config-2 distribution, bounding-sphere cull + first-hit exit, exact triangle tests where hulls touch (surface semantics)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -229,12 +233,21 @@ def main():
             os.environ.pop("NCCL_DEBUG")
         dist.init_process_group("nccl", device_id=dev)
 
+    if world > 1:
+        # one process per GPU on a shared host: give every rank its own slice of the cores, so that a rank's
+        # launch thread is not descheduled behind another rank's (the step is ~0.4 ms of GPU time)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            mine = cores[local_rank::world] if len(cores) >= 2 * world else cores
+            os.sched_setaffinity(0, mine)
+        except (AttributeError, OSError):
+            pass
     model, cmodel = panda_models()
     eng = CollisionEngine(model, cmodel, device=local_rank)
     n = args.states
     host_batches = [torch.from_numpy(make_batch(model, n, 7919 * rank + b)).pin_memory() for b in range(N_BATCHES)]
     dev_batches = [b.to(dev, non_blocking=True) for b in host_batches]
-    hits = [None] * N_BATCHES
+    hits = [torch.empty(n, dtype=torch.bool, device=dev) for _ in range(N_BATCHES)]   # fixed buffers: every round replays its CUDA graph
     torch.cuda.synchronize()
 
     def barrier():
@@ -245,30 +258,37 @@ def main():
     # W untimed warm-up steps (at least one per input batch, so no batch is touched for the
     # first time inside the timed region)
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:
+        sampler.start()   # (rank 0 prints the line: its GPU's clocks; the other ranks run no poller thread)
     for w in range(max(args.warmup, N_BATCHES + 1)):
-        hits[w % N_BATCHES] = eng.check_states(dev_batches[w % N_BATCHES])
+        eng.check_states(dev_batches[w % N_BATCHES], out=hits[w % N_BATCHES])
     torch.cuda.synchronize()
     fp32_peak = measure_fp32_peak(local_rank)
     eng.stats(reset=True)
-    eng.set_profiling(True)
-    eng.profile(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     torch.cuda.synchronize()
     t_region0 = time.perf_counter()
     ev0.record()
     for k in range(args.steps):
-        hits[k % N_BATCHES] = eng.check_states(dev_batches[k % N_BATCHES])
+        eng.check_states(dev_batches[k % N_BATCHES], out=hits[k % N_BATCHES])
     ev1.record()
     torch.cuda.synchronize()
     t_region1 = time.perf_counter()
     barrier()
-    clocks = sampler.stop(t_region0, t_region1)
+    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
+    stats = eng.stats(reset=True)
+    # per-kernel launch durations: the same K steps once more with CUDA events around every kernel (plain
+    # launches: the headline region above replays one CUDA graph per step and carries no events)
+    eng.set_profiling(True)
+    eng.profile(reset=True)
+    for k in range(args.steps):
+        eng.check_states(dev_batches[k % N_BATCHES], out=hits[k % N_BATCHES])
+    torch.cuda.synchronize()
     prof = eng.profile(reset=True)
     eng.set_profiling(False)
-    stats = eng.stats(reset=True)
+    eng.stats(reset=True)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -290,6 +310,22 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n * args.steps / float(t.item())
+    # the same from float64 PAGEABLE numpy arrays -- what the reference's callers hold and what the drop-in
+    # functions receive: the library narrows to float32 on host threads, overlapped with copies and kernels
+    host_f64 = [b.numpy().astype(np.float64) for b in host_batches[:2]]
+    for w in range(2):
+        eng.check_states(host_f64[w % 2])
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        hit_f64 = eng.check_states(host_f64[k % 2])
+    torch.cuda.synchronize()
+    f64_s = time.perf_counter() - t0
+    t = torch.tensor([f64_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_f64_value = world * n * args.steps / float(t.item())
     # pinned H2D bandwidth of this box, for context (the e2e path moves 36 B per state over PCIe)
     h2d0, h2d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h2d0.record()
@@ -372,13 +408,17 @@ def main():
                    "parallelism": f"{world} rank(s), states sharded, no data-path collective"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 9 * 4, "d2h_bytes_per_step": n,
                 "api": "CollisionEngine.check_states(numpy) -> pbp_check_states_host (pinned host buffers, copies overlapped with kernels)",
-                "pinned_h2d_gbs_measured": h2d_gbs, "pcie_bound_value": h2d_gbs * 1e9 / 36.0 * world},
+                "pinned_h2d_gbs_measured": h2d_gbs, "pcie_bound_value": h2d_gbs * 1e9 / 36.0 * world,
+                "pageable_f64": {"value": e2e_f64_value, "unit": UNIT, "h2d_bytes_per_step": n * 9 * 4, "d2h_bytes_per_step": n,
+                                 "api": "CollisionEngine.check_states(float64 pageable numpy) -> pbp_check_states_host_f64 (threaded narrowing into "
+                                        "rotating pinned slices, overlapped with H2D and kernels): the call the drop-in functions make"}},
         "gpu_launches": stats["kernel_launches"],
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "parity": parity,
         "p_collision": float(hits[(args.steps - 1) % N_BATCHES].float().mean().item()),
+        "timing": "headline region: K steps, one CUDA-graph launch each, no per-kernel events; per-kernel durations from a second pass of K steps",
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -184,6 +184,11 @@ int pbp_check_states(pbp_engine *e, const float *q_dev, int64_t n, float padding
                      int32_t *first_pair_dev, void *stream);
 int pbp_check_states_host(pbp_engine *e, const float *q_host, int64_t n, float padding, uint8_t *hit_host,
                           float *min_dist_host, int32_t *first_pair_host);
+/* The same from FLOAT64 host states -- what the reference's callers hold (numpy float64, pageable memory;
+ * core/utils.py:8-15 takes q as such).  A few host threads narrow slice after slice into rotating pinned
+ * float32 buffers while earlier slices cross PCIe and are checked: conversion, copies and kernels overlap. */
+int pbp_check_states_host_f64(pbp_engine *e, const double *q_host, int64_t n, float padding, uint8_t *hit_host,
+                              float *min_dist_host, int32_t *first_pair_host);
 
 /* Edge validation: edge e = straight joint-space segment q1[e] -> q2[e], discretised on device
  * with ceil(||dq||_2 / step) + 1 samples (both ends included) and collision-checked.

@@ -5,11 +5,14 @@
 #include <cub/device/device_select.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "pbp_kernels.cuh"
@@ -105,13 +108,14 @@ struct pbp_engine {
     int sr_blocks = 1;
     // pipeline workspaces
     int64_t chunk = 0;  // states per broadphase/narrowphase round = bin capacity
-    DeviceBuffer d_bin_state, d_bin_group, d_bin_sample, d_bin_T, d_ctrl;
+    DeviceBuffer d_bin_state, d_bin_group, d_bin_sample, d_bin_T, d_ctrl, d_doubt;
     DeviceBuffer d_counts, d_desc_group, d_desc_frac, d_desc_sample, d_scratch_i32, d_scratch_u8, d_cub, d_sel;
     DeviceBuffer d_io_q, d_io_q2, d_io_hit, d_io_f32, d_io_i32;   // staging for the *_host entry points
     unsigned long long *h_pinned = nullptr;  // small pinned mailbox for device -> host counters
     cudaStream_t s_copy = nullptr, s_comp = nullptr;   // *_host entry points: copy / compute pipeline
     std::vector<cudaEvent_t> io_events;
     PinnedBuffer h_io_hit, h_io_f32, h_io_i32;   // staging for results bound for pageable caller memory
+    PinnedBuffer h_stage;                        // rotating float32 slices of a float64 host batch being converted
     int64_t host_slice = 1 << 18;                // states per slice of the *_host copy/compute pipeline
     // Two workspaces (halves of every bin + one control block each) let the *_host pipeline run
     // consecutive slices on two streams: the latency-bound tail of one slice's narrowphase
@@ -140,6 +144,25 @@ struct pbp_engine {
     int np_blocks = 0, is_blocks = 0;
     bool verts_in_smem_dist = true;
     pbp_stats stats{};
+    // One engine = one set of bins, counters and staging buffers: calls are serialised.  Host side by this
+    // mutex (held for the whole entry point); device side by an event recorded at the end of every call
+    // that the next call waits for when it arrives on a different stream.
+    std::recursive_mutex mu;
+    int guard_depth = 0;
+    cudaEvent_t ev_last = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool last_valid = false;
+    // CUDA graphs of whole boolean rounds (memsets + four kernels), keyed by the call's arguments: a replay
+    // is ONE launch for the host thread.  Captured on s_cap (the caller's stream may be the legacy default
+    // stream, which cannot be captured), launched into the caller's stream.
+    struct RoundGraph {
+        const float *q; uint8_t *hit; int64_t n; float padding;
+        cudaGraphExec_t exec; int launches; uint64_t last_use;
+    };
+    std::vector<RoundGraph> graphs;
+    uint64_t graph_clock = 0;
+    bool graphs_enabled = true;
+    cudaStream_t s_cap = nullptr;
     // optional per-kernel timing
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;   // five per round: before broadphase / item setup / narrowphase / surface refine, after
@@ -149,11 +172,37 @@ struct pbp_engine {
 
 namespace {
 
+// Every extern "C" entry point that touches an engine runs under one of these: serialises the host side,
+// orders the device side against the previous call when the stream changed, switches to the engine's
+// device and restores the caller's current device on the way out (torch reads it from the runtime).
+struct CallGuard {
+    pbp_engine *e;
+    cudaStream_t st;
+    int prev_dev = -1;
+    CallGuard(pbp_engine *eng, cudaStream_t stream) : e(eng), st(stream) {
+        e->mu.lock();
+        if (e->guard_depth++ == 0) {
+            cudaGetDevice(&prev_dev);
+            if (prev_dev != e->device) cudaSetDevice(e->device);
+            if (e->last_valid && e->last_stream != st && e->ev_last) cudaStreamWaitEvent(st, e->ev_last, 0);
+        }
+    }
+    ~CallGuard() {
+        if (--e->guard_depth == 0) {
+            if (e->ev_last && cudaEventRecord(e->ev_last, st) == cudaSuccess) { e->last_stream = st; e->last_valid = true; }
+            if (prev_dev >= 0 && prev_dev != e->device) cudaSetDevice(prev_dev);
+        }
+        e->mu.unlock();
+    }
+    CallGuard(const CallGuard &) = delete;
+    CallGuard &operator=(const CallGuard &) = delete;
+};
+
 // control block layout (uint32 words): [0, npairs) bin counts, [npairs] item-setup tile counter,
 // [npairs + 1] narrowphase chunk cursor, [npairs + 2, 2 npairs + 2) narrowphase bin counts (items the
 // item setup kept), [2 npairs + 2] surface-refine chunk cursor, then four 64-bit counters at an 8-byte aligned offset
 // (level total, emit cursor, select count, profiled item total, IK work cursor).
-inline size_t ctrl_words(const pbp_engine *e) { return 2 * (size_t)e->npairs + 3; }   // + the surface-refine chunk cursor
+inline size_t ctrl_words(const pbp_engine *e) { return 2 * (size_t)e->npairs + 4; }   // + the surface-refine chunk cursor, the undecided-item count
 // There are two such blocks (workspaces 0 / 1, see pbp_engine::ws); the 64-bit counters live in block 0.
 inline size_t ctrl_bytes(const pbp_engine *e) { return ((ctrl_words(e) * 4 + 7) & ~(size_t)7) + 64; }   // 8 x 64-bit counters
 inline uint32_t *ctrl_base(pbp_engine *e) {
@@ -164,6 +213,7 @@ inline uint32_t *ctrl_tile_setup(pbp_engine *e) { return ctrl_base(e) + e->npair
 inline uint32_t *ctrl_chunk_np(pbp_engine *e) { return ctrl_base(e) + e->npairs + 1; }
 inline uint32_t *ctrl_counts_np(pbp_engine *e) { return ctrl_base(e) + e->npairs + 2; }
 inline uint32_t *ctrl_chunk_sr(pbp_engine *e) { return ctrl_base(e) + 2 * e->npairs + 2; }
+inline uint32_t *ctrl_doubt(pbp_engine *e) { return ctrl_base(e) + 2 * e->npairs + 3; }
 inline unsigned long long *ctrl_u64(pbp_engine *e, int i) {
     const size_t off = (ctrl_words(e) * 4 + 7) & ~(size_t)7;
     return reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(e->d_ctrl.p) + off) + i;
@@ -283,6 +333,9 @@ int run_round(pbp_engine *e, int mode, const StateSource &src, int64_t n, float 
     bins.count = ctrl_counts(e);
     bins.count_np = ctrl_counts_np(e);
     bins.cap = e->chunk;
+    bins.doubt = e->d_doubt.as<int2>() + ws_off;
+    bins.doubt_count = ctrl_doubt(e);
+    bins.doubt_cap = (uint32_t)round_cap(e);
     CUDA_TRY(cudaMemsetAsync(ctrl_base(e), 0, ctrl_words(e) * 4, st));
     int rc;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -358,7 +411,7 @@ int pbp_set_profiling(pbp_engine *e, int enabled) {
 
 int pbp_get_profile(pbp_engine *e, pbp_profile *out, int reset) {
     if (!e || !out) return fail(PBP_ERR_ARG, "NULL argument");
-    CUDA_TRY(cudaSetDevice(e->device));
+    CallGuard guard(e, nullptr);
     for (size_t i = 0; i + 4 < e->prof_events.size(); i += 5) {
         float a = 0.f, b = 0.f, c = 0.f, r = 0.f;
         CUDA_TRY(cudaEventSynchronize(e->prof_events[i + 4]));
@@ -392,20 +445,23 @@ void pbp_engine_destroy(pbp_engine *e) {
     for (cudaEvent_t ev : e->prof_pool) cudaEventDestroy(ev);
     DeviceBuffer *bufs[] = {&e->d_joints, &e->d_jgeoms, &e->d_geoms, &e->d_bpgeoms, &e->d_bpboxes, &e->d_bppairs, &e->d_groups, &e->d_pairorig, &e->d_paths,
                             &e->d_pathops, &e->d_order, &e->d_verts, &e->d_supcells, &e->d_suplists, &e->d_qlim, &e->d_frames, &e->d_bin_state,
-                            &e->d_bin_group, &e->d_bin_sample, &e->d_bin_T, &e->d_ctrl, &e->d_counts, &e->d_desc_group,
+                            &e->d_bin_group, &e->d_bin_sample, &e->d_bin_T, &e->d_ctrl, &e->d_doubt, &e->d_counts, &e->d_desc_group,
                             &e->d_desc_frac, &e->d_desc_sample, &e->d_scratch_i32, &e->d_scratch_u8, &e->d_cub, &e->d_sel,
                             &e->d_io_q, &e->d_io_q2, &e->d_io_hit, &e->d_io_f32, &e->d_io_i32, &e->d_ik_tables, &e->d_ws_oMi, &e->d_ws_oMg, &e->d_ws_dist,
                             &e->d_ws_p1, &e->d_ws_p2, &e->d_ws_nrm, &e->d_pairs_orig, &e->d_planes, &e->d_plane_idx, &e->d_surf_tol, &e->d_pair_enclose, &e->d_kverts, &e->d_ksupcells,
                             &e->d_ksuplists, &e->d_mverts, &e->d_tris};
     for (DeviceBuffer *b : bufs) b->release();
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
-    e->h_io_hit.release(); e->h_io_f32.release(); e->h_io_i32.release();
+    e->h_io_hit.release(); e->h_io_f32.release(); e->h_io_i32.release(); e->h_stage.release();
     if (e->spec_module && driver_api().ok) driver_api().moduleUnload(e->spec_module);
     e->h_desc.release();
     for (cudaEvent_t ev : e->io_events) cudaEventDestroy(ev);
     if (e->s_copy) cudaStreamDestroy(e->s_copy);
     if (e->s_comp) cudaStreamDestroy(e->s_comp);
     if (e->s_comp2) cudaStreamDestroy(e->s_comp2);
+    for (auto &g : e->graphs) cudaGraphExecDestroy(g.exec);
+    if (e->s_cap) cudaStreamDestroy(e->s_cap);
+    if (e->ev_last) cudaEventDestroy(e->ev_last);
     delete e;
 }
 
@@ -421,12 +477,17 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     if (ce != cudaSuccess || ndev == 0)
         return fail(PBP_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback", cudaGetErrorString(ce));
     if (device < 0 || device >= ndev) return fail(PBP_ERR_ARG, "device %d out of range [0, %d)", device, ndev);
+    struct DeviceRestore {   // the caller's current device survives this call (torch reads it from the runtime)
+        int prev = -1;
+        DeviceRestore() { cudaGetDevice(&prev); }
+        ~DeviceRestore() { if (prev >= 0) cudaSetDevice(prev); }
+    } restore;
     CUDA_TRY(cudaSetDevice(device));
 
     pbp_engine *e = new pbp_engine();
     e->device = device;
     cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete e; return fail(PBP_ERR_CUDA, "cudaGetDeviceProperties failed"); }
     e->num_sms = prop.multiProcessorCount;
     e->nq = d->nq; e->njoints = d->njoints; e->ngeoms = d->ngeoms; e->npairs = d->npairs; e->nframes = d->nframes;
     {
@@ -448,6 +509,12 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     }
 
     auto bail = [&](int code) { pbp_engine_destroy(e); return code; };
+#define CUDA_TRY_BAIL(expr)                                                                             \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return bail(fail(PBP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__)); \
+    } while (0)
 
     HostTables H;
     {
@@ -605,7 +672,7 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     // The dynamic shared-memory cap is a per-function attribute shared by every engine of the
     // process: raise it to the device's opt-in maximum once (a per-engine value would lower
     // the cap under another engine's feet).
-#define SET_SMEM(kern) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_optin))
+#define SET_SMEM(kern) CUDA_TRY_BAIL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_optin))
     SET_SMEM((k_broadphase<MODE_BOOL, true>));
     SET_SMEM((k_broadphase<MODE_BOOL_ALL, true>));
     SET_SMEM((k_broadphase<MODE_DIST, true>));
@@ -625,7 +692,7 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
 #undef SET_SMEM
     // (static __shared__ chunk directory and per-warp triangle lists: leave room for them under the opt-in cap)
     const int sr_static = 32 * 1024;
-#define SET_SMEM_SR(kern) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_optin - sr_static))
+#define SET_SMEM_SR(kern) CUDA_TRY_BAIL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_optin - sr_static))
     SET_SMEM_SR((k_surface_refine<MODE_BOOL, true>));
     SET_SMEM_SR((k_surface_refine<MODE_BOOL_ALL, true>));
     SET_SMEM_SR((k_surface_refine<MODE_DIST, true>));
@@ -634,17 +701,17 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     e->sr_tables_in_smem = e->smem_sr + sr_static <= max_optin;   // one 16-warp block per SM is enough for this kernel
     {
         int occ_sr = 1;
-        if (e->sr_tables_in_smem) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sr, k_surface_refine<MODE_BOOL, true>, SR_THREADS, e->smem_sr));
-        else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sr, k_surface_refine<MODE_BOOL, false>, SR_THREADS, 0));
+        if (e->sr_tables_in_smem) CUDA_TRY_BAIL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sr, k_surface_refine<MODE_BOOL, true>, SR_THREADS, e->smem_sr));
+        else CUDA_TRY_BAIL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sr, k_surface_refine<MODE_BOOL, false>, SR_THREADS, 0));
         e->sr_blocks = e->num_sms * std::max(occ_sr, 1);
     }
     int occ = 1;
     if (e->verts_in_smem)
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrowphase<MODE_BOOL, true>, NP_THREADS, e->smem_np));
+        CUDA_TRY_BAIL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrowphase<MODE_BOOL, true>, NP_THREADS, e->smem_np));
     else
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrowphase<MODE_BOOL, false>, NP_THREADS, e->smem_np));
+        CUDA_TRY_BAIL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrowphase<MODE_BOOL, false>, NP_THREADS, e->smem_np));
     e->np_blocks = e->num_sms * std::max(occ, 1);
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_item_setup<MODE_BOOL>, IS_THREADS, e->smem_is));
+    CUDA_TRY_BAIL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_item_setup<MODE_BOOL>, IS_THREADS, e->smem_is));
     e->is_blocks = e->num_sms * std::max(occ, 1);
 
     // ---- model-specialised broadphase (optional: any failure leaves the generic kernel in charge)
@@ -692,28 +759,32 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     e->chunk = chunk;
     const size_t slots = (size_t)np1 * (size_t)chunk;
     if ((rc = e->d_bin_state.ensure(slots * 4)) || (rc = e->d_bin_group.ensure(slots * 4)) || (rc = e->d_bin_sample.ensure(slots * 4)) ||
-        (rc = e->d_bin_T.ensure(slots * 48)) || (rc = e->d_ctrl.ensure(2 * ctrl_bytes(e))))
+        (rc = e->d_bin_T.ensure(slots * 48)) || (rc = e->d_ctrl.ensure(2 * ctrl_bytes(e))) || (rc = e->d_doubt.ensure((size_t)chunk * sizeof(int2))))
         return bail(rc);
-    CUDA_TRY(cudaMemset(e->d_ctrl.p, 0, 2 * ctrl_bytes(e)));
-    CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&e->h_pinned), 64));
+    CUDA_TRY_BAIL(cudaMemset(e->d_ctrl.p, 0, 2 * ctrl_bytes(e)));
+    CUDA_TRY_BAIL(cudaMallocHost(reinterpret_cast<void **>(&e->h_pinned), 64));
     if (const char *sm = getenv("PBP_SMALL_ITEMS")) e->small_items = atoll(sm);
     if (const char *hs = getenv("PBP_HOST_SLICE")) {
         const long long v = atoll(hs);
         if (v >= 1024) e->host_slice = v;
     }
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_comp2, cudaStreamNonBlocking));
+    CUDA_TRY_BAIL(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
+    CUDA_TRY_BAIL(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
+    CUDA_TRY_BAIL(cudaStreamCreateWithFlags(&e->s_comp2, cudaStreamNonBlocking));
+    CUDA_TRY_BAIL(cudaStreamCreateWithFlags(&e->s_cap, cudaStreamNonBlocking));
+    CUDA_TRY_BAIL(cudaEventCreateWithFlags(&e->ev_last, cudaEventDisableTiming));
+    if (const char *g = getenv("PBP_GRAPHS")) e->graphs_enabled = atoi(g) != 0;
     *out = e;
     return 0;
 }
 
+#undef CUDA_TRY_BAIL
 // ------------------------------------------------------------------------------------------
 int pbp_fk(pbp_engine *e, const float *q_dev, int64_t n, float *oMi_dev, float *oMg_dev, float *oMf_dev, void *stream) {
     int rc = check_args(e, q_dev, n);
     if (rc) return rc;
     if (n == 0) return 0;
-    CUDA_TRY(cudaSetDevice(e->device));
+    CallGuard guard(e, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     k_fk_output<<<grid_for(n, 128), 128, e->smem_fk, st>>>(e->dm, q_dev, n, oMi_dev, oMg_dev, oMf_dev);
     CUDA_TRY(cudaGetLastError());
@@ -728,8 +799,62 @@ int pbp_check_states(pbp_engine *e, const float *q_dev, int64_t n, float padding
     if (n > 0 && !hit_dev) return fail(PBP_ERR_ARG, "hit buffer is NULL");
     if (!(padding >= 0.0f)) return fail(PBP_ERR_ARG, "distance padding must be >= 0 (got %g)", (double)padding);
     if (n == 0) return 0;
-    CUDA_TRY(cudaSetDevice(e->device));
+    CallGuard guard(e, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
+    // A whole boolean round (two memsets + four kernels) as ONE launch: the graph captured for these
+    // arguments is replayed; a planner or a benchmark that calls with the same buffers again and again
+    // (and eight ranks sharing the host's cores) then spends one launch per call on the host thread.
+    const bool graphable = !min_dist_dev && !first_pair_dev && e->graphs_enabled && !e->profiling && !e->ws_split && e->ws == 0 &&
+                           e->npairs > 0 && n <= round_cap(e) && n * (int64_t)e->npairs > e->small_items;
+    if (graphable) {
+        for (auto &g : e->graphs) {
+            if (g.q == q_dev && g.hit == hit_dev && g.n == n && g.padding == padding) {
+                CUDA_TRY(cudaGraphLaunch(g.exec, st));
+                g.last_use = ++e->graph_clock;
+                e->stats.kernel_launches += g.launches;
+                e->stats.states += n;
+                e->stats.chunks++;
+                return 0;
+            }
+        }
+        if (cudaStreamBeginCapture(e->s_cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int64_t launches0 = e->stats.kernel_launches;
+            StateSource src{};
+            src.q = q_dev;
+            src.mode = 0;
+            Outputs out{};
+            out.hit = hit_dev;
+            cudaError_t ce = cudaMemsetAsync(hit_dev, 0, (size_t)n, e->s_cap);
+            rc = ce == cudaSuccess ? run_round(e, MODE_BOOL, src, n, padding, out, e->s_cap) : fail(PBP_ERR_CUDA, "memset in capture: %s", cudaGetErrorString(ce));
+            cudaGraph_t graph = nullptr;
+            ce = cudaStreamEndCapture(e->s_cap, &graph);
+            cudaGraphExec_t exec = nullptr;
+            if (rc == 0 && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                cudaGraphDestroy(graph);
+                if (e->graphs.size() >= 16) {   // evict the least recently used
+                    size_t lru = 0;
+                    for (size_t i = 1; i < e->graphs.size(); i++)
+                        if (e->graphs[i].last_use < e->graphs[lru].last_use) lru = i;
+                    cudaGraphExecDestroy(e->graphs[lru].exec);
+                    e->graphs.erase(e->graphs.begin() + (long)lru);
+                }
+                e->graphs.push_back(pbp_engine::RoundGraph{q_dev, hit_dev, n, padding, exec, (int)(e->stats.kernel_launches - launches0), ++e->graph_clock});
+                CUDA_TRY(cudaGraphLaunch(exec, st));
+                return 0;
+            }
+            // capture or instantiation failed: fall back to plain launches from now on
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            e->graphs_enabled = false;
+            e->stats.kernel_launches = launches0;
+            e->stats.states -= n;
+            e->stats.chunks--;
+            if (rc) return rc;
+        } else {
+            cudaGetLastError();
+            e->graphs_enabled = false;
+        }
+    }
     CUDA_TRY(cudaMemsetAsync(hit_dev, 0, (size_t)n, st));
     if (min_dist_dev) {
         k_fill_f32<<<grid_for(n, 256), 256, 0, st>>>(min_dist_dev, n, INFINITY);
@@ -788,7 +913,7 @@ int pbp_check_paths(pbp_engine *e, const float *q_dev, const int64_t *path_offse
     if (!(padding >= 0.0f)) return fail(PBP_ERR_ARG, "distance padding must be >= 0");
     if (n_paths == 0) return 0;
     if (!path_offsets_dev) return fail(PBP_ERR_ARG, "path_offsets is NULL");
-    CUDA_TRY(cudaSetDevice(e->device));
+    CallGuard guard(e, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemsetAsync(hit_dev, 0, (size_t)n_paths, st));
     if (total == 0) return 0;
@@ -828,7 +953,7 @@ int pbp_discretize_counts(pbp_engine *e, const float *q1_dev, const float *q2_de
     if (n_edges > 0 && (!q2_dev || !counts_dev)) return fail(PBP_ERR_ARG, "NULL buffer");
     if (!(step > 0.0)) return fail(PBP_ERR_ARG, "step must be > 0");
     if (n_edges == 0) return 0;
-    CUDA_TRY(cudaSetDevice(e->device));
+    CallGuard guard(e, (cudaStream_t)stream);
     k_edge_counts<<<grid_for(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(q1_dev, q2_dev, n_edges, e->nq, step, counts_dev);
     CUDA_TRY(cudaGetLastError());
     e->stats.kernel_launches++;
@@ -841,7 +966,7 @@ int pbp_discretize_fill(pbp_engine *e, const float *q1_dev, const float *q2_dev,
     if (rc) return rc;
     if (n_edges > 0 && (!q2_dev || !counts_dev || !offsets_dev || !q_out_dev)) return fail(PBP_ERR_ARG, "NULL buffer");
     if (n_edges == 0) return 0;
-    CUDA_TRY(cudaSetDevice(e->device));
+    CallGuard guard(e, (cudaStream_t)stream);
     k_edge_fill<<<grid_for(n_edges * 32, 256), 256, 0, (cudaStream_t)stream>>>(q1_dev, q2_dev, n_edges, e->nq, counts_dev, offsets_dev, q_out_dev);
     CUDA_TRY(cudaGetLastError());
     e->stats.kernel_launches++;
@@ -859,7 +984,7 @@ static int check_edges_core(pbp_engine *e, const float *q1_dev, const float *q2_
         // few samples in total: descriptors (edge, fraction) built here, one fused launch
         // (no count / emit kernels, no refinement levels, no device -> host round trip)
         if (rc) return rc;
-        CUDA_TRY(cudaSetDevice(e->device));
+        CallGuard guard(e, (cudaStream_t)stream);
         cudaStream_t st = (cudaStream_t)stream;
         CUDA_TRY(cudaMemsetAsync(hit_dev, 0, (size_t)n_edges, st));
         if (known_total == 0) return 0;
@@ -894,7 +1019,7 @@ static int check_edges_core(pbp_engine *e, const float *q1_dev, const float *q2_
     if (!(step > 0.0)) return fail(PBP_ERR_ARG, "step must be > 0");
     if (!(padding >= 0.0f)) return fail(PBP_ERR_ARG, "distance padding must be >= 0");
     if (n_edges == 0) return 0;
-    CUDA_TRY(cudaSetDevice(e->device));
+    CallGuard guard(e, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = e->d_counts.ensure((size_t)n_edges * 4))) return rc;
     int32_t *counts = e->d_counts.as<int32_t>();
@@ -1014,7 +1139,7 @@ int pbp_check_states_host(pbp_engine *e, const float *q_host, int64_t n, float p
     if (rc) return rc;
     if (n > 0 && !hit_host) return fail(PBP_ERR_ARG, "hit buffer is NULL");
     if (n == 0) return 0;
-    CUDA_TRY(cudaSetDevice(e->device));
+    CallGuard guard(e, e->s_comp);
     if ((rc = e->d_io_q.ensure((size_t)n * e->nq * 4)) || (rc = e->d_io_hit.ensure((size_t)n))) return rc;
     if (min_dist_host && (rc = e->d_io_f32.ensure((size_t)n * 4))) return rc;
     if (first_pair_host && (rc = e->d_io_i32.ensure((size_t)n * 4))) return rc;
@@ -1046,7 +1171,7 @@ int pbp_check_states_host(pbp_engine *e, const float *q_host, int64_t n, float p
     struct SplitGuard {
         pbp_engine *e;
         ~SplitGuard() { e->ws_split = false; e->ws = 0; }
-    } guard{e};
+    } split_guard{e};
     e->ws_split = n_slices > 1 && slice <= e->chunk / 2 && !(min_dist_host && first_pair_host);
     for (int64_t k = 0; k < n_slices; k++) {
         const int64_t off = k * slice, cnt = std::min(slice, n - off);
@@ -1069,13 +1194,105 @@ int pbp_check_states_host(pbp_engine *e, const float *q_host, int64_t n, float p
     return 0;
 }
 
+// float64 host states (what the reference's callers hold: numpy float64, pageable).  The batch is cut into
+// slices; a few host threads convert slice after slice into rotating pinned float32 buffers while earlier
+// slices are already crossing PCIe and being checked, so conversion, copies and kernels overlap.
+int pbp_check_states_host_f64(pbp_engine *e, const double *q_host, int64_t n, float padding, uint8_t *hit_host,
+                              float *min_dist_host, int32_t *first_pair_host) {
+    int rc = check_args(e, q_host, n);
+    if (rc) return rc;
+    if (n > 0 && !hit_host) return fail(PBP_ERR_ARG, "hit buffer is NULL");
+    if (n == 0) return 0;
+    CallGuard guard(e, e->s_comp);
+    const int nq = e->nq;
+    if ((rc = e->d_io_q.ensure((size_t)n * nq * 4)) || (rc = e->d_io_hit.ensure((size_t)n))) return rc;
+    if (min_dist_host && (rc = e->d_io_f32.ensure((size_t)n * 4))) return rc;
+    if (first_pair_host && (rc = e->d_io_i32.ensure((size_t)n * 4))) return rc;
+    uint8_t *hh = hit_host;
+    float *hd = min_dist_host;
+    int32_t *hp = first_pair_host;
+    if (!is_pinned_host(hit_host)) { if ((rc = e->h_io_hit.ensure((size_t)n))) return rc; hh = (uint8_t *)e->h_io_hit.p; }
+    if (min_dist_host && !is_pinned_host(min_dist_host)) { if ((rc = e->h_io_f32.ensure((size_t)n * 4))) return rc; hd = (float *)e->h_io_f32.p; }
+    if (first_pair_host && !is_pinned_host(first_pair_host)) { if ((rc = e->h_io_i32.ensure((size_t)n * 4))) return rc; hp = (int32_t *)e->h_io_i32.p; }
+    const int64_t slice = std::min<int64_t>(e->host_slice, 1 << 17);   // conversion granularity: 128 Ki states = 9.4 MB of doubles
+    const int64_t n_slices = (n + slice - 1) / slice;
+    constexpr int NBUF = 4;
+    if ((rc = e->h_stage.ensure((size_t)NBUF * slice * nq * 4))) return rc;
+    while ((int64_t)e->io_events.size() < n_slices) {
+        cudaEvent_t ev;
+        CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        e->io_events.push_back(ev);
+    }
+    int nthreads = (int)std::min<int64_t>(std::min<int64_t>(n_slices, 8), std::max(1u, std::thread::hardware_concurrency()));
+    if (const char *ht = getenv("PBP_HOST_THREADS")) nthreads = std::max(1, std::min(atoi(ht), 64));
+    std::vector<std::atomic<int>> ready((size_t)n_slices), issued((size_t)n_slices);
+    for (int64_t k = 0; k < n_slices; k++) { ready[(size_t)k].store(0); issued[(size_t)k].store(0); }
+    std::atomic<int64_t> next{0};
+    std::atomic<int> abort_flag{0};
+    float *stage = (float *)e->h_stage.p;
+    const int device = e->device;
+    auto worker = [&]() {
+        cudaSetDevice(device);
+        for (;;) {
+            const int64_t k = next.fetch_add(1);
+            if (k >= n_slices) return;
+            if (k >= NBUF) {   // the buffer's previous slice must have left the host
+                while (!issued[(size_t)(k - NBUF)].load(std::memory_order_acquire))
+                    if (abort_flag.load()) return; else std::this_thread::yield();
+                cudaEventSynchronize(e->io_events[(size_t)(k - NBUF)]);
+            }
+            const int64_t off = k * slice, cnt = std::min(slice, n - off);
+            const double *src = q_host + off * nq;
+            float *dst = stage + (k % NBUF) * slice * nq;
+            const int64_t m = cnt * nq;
+            for (int64_t i = 0; i < m; i++) dst[i] = (float)src[i];
+            ready[(size_t)k].store(1, std::memory_order_release);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++) pool.emplace_back(worker);
+    struct Join {
+        std::vector<std::thread> &pool; std::atomic<int> &abort_flag; pbp_engine *e;
+        ~Join() { abort_flag.store(1); for (auto &t : pool) if (t.joinable()) t.join(); e->ws_split = false; e->ws = 0; }
+    } join{pool, abort_flag, e};
+    float *dq = e->d_io_q.as<float>();
+    e->ws_split = n_slices > 1 && slice <= e->chunk / 2 && !(min_dist_host && first_pair_host);
+    auto step = [&](int64_t k) -> int {
+        const int64_t off = k * slice, cnt = std::min(slice, n - off);
+        while (!ready[(size_t)k].load(std::memory_order_acquire)) std::this_thread::yield();
+        CUDA_TRY(cudaMemcpyAsync(dq + off * nq, stage + (k % NBUF) * slice * nq, (size_t)cnt * nq * 4, cudaMemcpyHostToDevice, e->s_copy));
+        CUDA_TRY(cudaEventRecord(e->io_events[(size_t)k], e->s_copy));
+        issued[(size_t)k].store(1, std::memory_order_release);
+        e->ws = e->ws_split ? (int)(k & 1) : 0;
+        cudaStream_t sc = e->ws ? e->s_comp2 : e->s_comp;
+        CUDA_TRY(cudaStreamWaitEvent(sc, e->io_events[(size_t)k], 0));
+        uint8_t *dh = e->d_io_hit.as<uint8_t>() + off;
+        float *dd = min_dist_host ? e->d_io_f32.as<float>() + off : nullptr;
+        int32_t *dp = first_pair_host ? e->d_io_i32.as<int32_t>() + off : nullptr;
+        int r = pbp_check_states(e, dq + off * nq, cnt, padding, dh, dd, dp, sc);
+        if (r) return r;
+        CUDA_TRY(cudaMemcpyAsync(hh + off, dh, (size_t)cnt, cudaMemcpyDeviceToHost, sc));
+        if (dd) CUDA_TRY(cudaMemcpyAsync(hd + off, dd, (size_t)cnt * 4, cudaMemcpyDeviceToHost, sc));
+        if (dp) CUDA_TRY(cudaMemcpyAsync(hp + off, dp, (size_t)cnt * 4, cudaMemcpyDeviceToHost, sc));
+        return 0;
+    };
+    for (int64_t k = 0; k < n_slices; k++)
+        if ((rc = step(k))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->s_comp));
+    CUDA_TRY(cudaStreamSynchronize(e->s_comp2));
+    if (hh != hit_host) memcpy(hit_host, hh, (size_t)n);
+    if (min_dist_host && hd != min_dist_host) memcpy(min_dist_host, hd, (size_t)n * 4);
+    if (first_pair_host && hp != first_pair_host) memcpy(first_pair_host, hp, (size_t)n * 4);
+    return 0;
+}
+
 int pbp_check_edges_host(pbp_engine *e, const float *q1_host, const float *q2_host, int64_t n_edges, double step,
                          float padding, uint8_t *hit_host, int32_t *first_bad_host) {
     int rc = check_args(e, q1_host, n_edges);
     if (rc) return rc;
     if (n_edges > 0 && (!q2_host || !hit_host)) return fail(PBP_ERR_ARG, "NULL buffer");
     if (n_edges == 0) return 0;
-    CUDA_TRY(cudaSetDevice(e->device));
+    CallGuard guard(e, e->s_comp);
     const size_t qb = (size_t)n_edges * e->nq * 4;
     if ((rc = e->d_io_q.ensure(qb)) || (rc = e->d_io_q2.ensure(qb)) || (rc = e->d_io_hit.ensure((size_t)n_edges))) return rc;
     if (first_bad_host && (rc = e->d_io_i32.ensure((size_t)n_edges * 4))) return rc;
@@ -1194,7 +1411,7 @@ extern "C" int pbp_sample_free_states(pbp_engine *e, int64_t n_wanted, uint64_t 
     if (n_drawn_host) *n_drawn_host = 0;
     if (n_wanted == 0) return 0;
     if (max_rounds <= 0) max_rounds = 64;
-    CUDA_TRY(cudaSetDevice(e->device));
+    CallGuard guard(e, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t batch = std::min<int64_t>(std::max<int64_t>(n_wanted, 4096), e->chunk);
     if ((rc = e->d_io_q.ensure((size_t)batch * e->nq * 4)) || (rc = e->d_io_hit.ensure((size_t)batch)) ||
@@ -1300,7 +1517,7 @@ extern "C" int pbp_ik_iterate(pbp_engine *e, int32_t frame_id, const double *tar
     if (frame_id < 0 || frame_id >= e->nframes) return fail(PBP_ERR_ARG, "frame %d out of range [0, %d)", frame_id, e->nframes);
     if (opt->max_iters < 0) return fail(PBP_ERR_ARG, "max_iters must be >= 0");
     if (n == 0) return 0;
-    CUDA_TRY(cudaSetDevice(e->device));
+    CallGuard guard(e, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     // chain root -> frame, as float64 tables
     std::vector<int> path;
@@ -1395,7 +1612,7 @@ extern "C" int pbp_knn(pbp_engine *e, const float *nodes_dev, int64_t n, int32_t
     if (e->nq > KNN_MAX_NQ) return fail(PBP_ERR_CAPACITY, "nq > %d", KNN_MAX_NQ);
     if (!(radius >= 0.0)) return fail(PBP_ERR_ARG, "radius must be >= 0");
     if (n == 0) return 0;
-    CUDA_TRY(cudaSetDevice(e->device));
+    CallGuard guard(e, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = knn_smem_bytes(e->nq, k);
     const double r2 = std::isinf(radius) ? INFINITY : radius * radius;
@@ -1440,7 +1657,7 @@ extern "C" int pbp_compute_distances(pbp_engine *e, const float *q_dev, int64_t 
     if (!(cutoff >= 0.0f)) return fail(PBP_ERR_ARG, "cutoff must be >= 0");
     if (n == 0 || e->npairs == 0) return 0;
     if (n * (int64_t)e->npairs > (int64_t)INT32_MAX * 64) return fail(PBP_ERR_ARG, "too many (state, pair) items");
-    CUDA_TRY(cudaSetDevice(e->device));
+    CallGuard guard(e, (cudaStream_t)stream);
     if ((rc = e->d_ws_oMg.ensure((size_t)n * e->ngeoms * 48))) return rc;
     return launch_distances(e, q_dev, n, cutoff, nullptr, e->d_ws_oMg.as<float>(), dist_dev, p1_dev, p2_dev, normal_dev,
                             (cudaStream_t)stream);
@@ -1453,7 +1670,7 @@ extern "C" int pbp_collision_nullspace(pbp_engine *e, const float *q_dev, int64_
     if (n > 0 && !component_dev) return fail(PBP_ERR_ARG, "component buffer is NULL");
     if (!(dist_padding >= 0.0f)) return fail(PBP_ERR_ARG, "dist_padding must be >= 0");
     if (n == 0) return 0;
-    CUDA_TRY(cudaSetDevice(e->device));
+    CallGuard guard(e, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     if (e->npairs == 0) {
         CUDA_TRY(cudaMemsetAsync(component_dev, 0, (size_t)n * e->nq * 4, st));

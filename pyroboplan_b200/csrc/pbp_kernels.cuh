@@ -64,6 +64,12 @@ struct Bins {
     uint32_t *count;     // [npairs] items appended by the broadphase
     uint32_t *count_np;  // [npairs] items the item setup kept for the narrowphase (compacted to the bin's front)
     int64_t cap;
+    // boolean queries: the (few) items the narrowphase leaves UNDECIDED between core and hull, compacted so that
+    // the refine kernel runs 32 of them per warp: (pair, index in the pair's bin).  Entries beyond the
+    // capacity are marked in `group` (SR_DOUBT) instead and found by a scan of all bins.
+    int2 *doubt;
+    uint32_t *doubt_count;
+    uint32_t doubt_cap;
 };
 
 struct Outputs {
@@ -680,14 +686,19 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
                 return;
             }
             if (fl & PAIR_SURFACE) {
-                if (r.hit && (fl & PAIR_NOCORE)) { bins.group[slot] = group | SR_DOUBT; return; }   // a hull hit proves nothing
+                if (r.hit && (fl & PAIR_NOCORE)) { bins.group[slot] = group | SR_PARKED; return; }   // a hull hit proves nothing: the triangles decide
                 if (r.hit && (fl & PAIR_ENCLOSE)) {
                     // one shape of this pair could be enclosed by the other's surface, which is the free
                     // placement -- the refine kernel decides (all its lanes busy with such items)
                     bins.group[slot] = group | SR_PARKED;
                     return;
                 }
-                if (!r.hit && !r.far) { bins.group[slot] = group | SR_DOUBT; return; }   // between the bounds: the triangles decide
+                if (!r.hit && !r.far) {   // between the bounds: the triangles decide
+                    const uint32_t di = atomicAdd(bins.doubt_count, 1u);
+                    if (di < bins.doubt_cap) bins.doubt[di] = make_int2(p, (int)(slot - (int64_t)p * bins.cap));
+                    else bins.group[slot] = group | SR_DOUBT;
+                    return;
+                }
             }
             if (r.hit) {
                 out.hit[group] = 1;
@@ -805,15 +816,22 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
         atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(d));
     };
     auto decided = [&](int32_t group) { return MODE == MODE_BOOL && out.hit[group] != 0; };
-    // chunk directory: the pairs with a surface and the running number of 32-item chunks before each
+    // chunk directory: the pairs whose bins hold parked items and the running number of 32-item chunks before
+    // each.  Boolean queries: the pairs with an enclosure flag (core hits parked by the narrowphase) -- the
+    // undecided items come through the compact list; distance queries, and boolean ones whose list
+    // overflowed: every pair with a surface.
     __shared__ int s_pair[SR_DIR];
     __shared__ uint32_t s_first[SR_DIR + 1];
     __shared__ int s_n;
+    __shared__ uint32_t s_list_n;
+    const uint32_t listed = MODE == MODE_DIST ? 0u : *bins.doubt_count;
+    const bool scan_all = MODE == MODE_DIST || listed > bins.doubt_cap;
+    const int want = scan_all ? PAIR_SURFACE : (PAIR_ENCLOSE | PAIR_NOCORE);
     if (threadIdx.x == 0) {
         int nf = 0;
         uint32_t acc = 0;
         for (int k = 0; k < M.npairs && nf >= 0; k++) {
-            if (!(M.pair_enclose[k] & PAIR_SURFACE)) continue;
+            if (!(M.pair_enclose[k] & want)) continue;
             if (nf == SR_DIR) { nf = -1; break; }   // directory full: every warp scans the pair list itself
             s_pair[nf] = k;
             s_first[nf] = acc;
@@ -822,45 +840,70 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
         }
         if (nf >= 0) s_first[nf] = acc;
         s_n = nf;
+        s_list_n = min(listed, bins.doubt_cap);
     }
     __syncthreads();
+    const uint32_t list_n = s_list_n;
+    uint32_t bin_chunks = 0;
+    if (s_n >= 0) {
+        bin_chunks = s_first[s_n];
+    } else {
+        for (int k = 0; k < M.npairs; k++)
+            if (M.pair_enclose[k] & want) bin_chunks += (bins.count_np[k] + 31u) >> 5;
+    }
+    const uint32_t total_chunks = bin_chunks + ((list_n + 31u) >> 5);
     for (;;) {
-        // next chunk of the concatenated bins, claimed from a global cursor: the chunks differ widely in
-        // cost (parked lanes, true enclosures, triangle stages), a fixed round-robin leaves warps idle
+        // next chunk of the concatenated bins / of the list, claimed from a global cursor: the chunks differ
+        // widely in cost (parked lanes, true enclosures, triangle stages), a fixed round-robin leaves warps idle
         uint32_t c = 0;
         if (lane == 0) c = atomicAdd(chunk_cursor, 1u);
         c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= total_chunks) break;
         int p = -1;
-        uint32_t local = 0;
-        if (s_n >= 0) {
-            if (c >= s_first[s_n]) break;
-            int lo = 0, hi = s_n;   // last entry with s_first[lo] <= c
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (s_first[mid] <= c) lo = mid; else hi = mid;
+        int64_t slot = 0;
+        bool active = false;
+        int32_t g = 0;
+        if (c >= bin_chunks) {
+            // 32 undecided items of the compact list, one per lane, each with its own pair
+            const uint32_t i = (c - bin_chunks) * 32u + lane;
+            if (i < list_n) {
+                const int2 it = bins.doubt[i];
+                p = it.x;
+                slot = (int64_t)p * bins.cap + it.y;
+                g = bins.group[slot] | SR_DOUBT;
+                active = true;
             }
-            // (entries with an empty bin share their s_first with the next one: take the last of the run)
-            p = s_pair[lo];
-            local = c - s_first[lo];
         } else {
-            uint32_t acc = 0;
-            for (int k = 0; k < M.npairs; k++) {
-                if (!(M.pair_enclose[k] & PAIR_SURFACE)) continue;
-                const uint32_t nch = (bins.count_np[k] + 31u) >> 5;
-                if (c < acc + nch) { p = k; local = c - acc; break; }
-                acc += nch;
+            uint32_t local = 0;
+            if (s_n >= 0) {
+                int lo = 0, hi = s_n;   // last entry with s_first[lo] <= c
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_first[mid] <= c) lo = mid; else hi = mid;
+                }
+                // (entries with an empty bin share their s_first with the next one: take the last of the run)
+                p = s_pair[lo];
+                local = c - s_first[lo];
+            } else {
+                uint32_t acc = 0;
+                for (int k = 0; k < M.npairs; k++) {
+                    if (!(M.pair_enclose[k] & want)) continue;
+                    const uint32_t nch = (bins.count_np[k] + 31u) >> 5;
+                    if (c < acc + nch) { p = k; local = c - acc; break; }
+                    acc += nch;
+                }
             }
+            const uint32_t cnt = bins.count_np[p];
+            const uint32_t idx = local * 32u + lane;
+            slot = (int64_t)p * bins.cap + idx;
+            g = idx < cnt ? bins.group[slot] : 0;
+            active = idx < cnt && g >= 0 && (g & SR_BITS);
         }
-        if (p < 0) break;
+        if (p < 0) p = 0;
         const int fl = M.pair_enclose[p];
-        const uint32_t cnt = bins.count_np[p];
         const BpPair pr = M.bppairs[p];
         const DevGeom &GA = M.geoms[pr.a];
         const DevGeom &GB = M.geoms[pr.b];
-        const uint32_t idx = local * 32u + lane;
-        const int64_t slot = (int64_t)p * bins.cap + idx;
-        const int32_t g = idx < cnt ? bins.group[slot] : 0;
-        bool active = idx < cnt && g >= 0 && (g & SR_BITS);
         const int32_t group = g & ~SR_BITS;
         if (active && decided(group)) active = false;
         float T[12];
@@ -870,7 +913,7 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
         v.status = ST_NONE; v.dist = 0.f; v.U = 0.f; v.n = make_float3(0.f, 0.f, 0.f); v.have_n = 0;
         if (active) {
             if (MODE == MODE_DIST) v = decide_distance(tab, fl, GA, GB, T, out.min_dist[group]);
-            else v = decide_boolean(tab, fl, (g & SR_PARKED) != 0, GA, GB, T, padding);
+            else v = decide_boolean(tab, fl, (g & SR_PARKED) != 0 && !(fl & PAIR_NOCORE), GA, GB, T, padding);
             if (v.status == ST_HIT) on_hit(p, group, slot);
             if (v.status == ST_VALUE) on_value(p, group, slot, fmaxf(v.dist - GA.core_radius - GB.core_radius, 0.f));
         }

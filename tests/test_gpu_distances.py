@@ -46,9 +46,14 @@ def test_distances_and_witness_points(panda_full, panda_oracle):
                 np.testing.assert_allclose(nrm[i, k], (pb - pa) / d_ref, atol=2e-3 + 2e-5 / d_ref)
             checked += 1
     assert checked > 2000 and penetrating > 20
-    # the minimum over the pairs, clamped at 0, is what check_states(return_distance=True) reports
+    # check_states(return_distance=True) reports the minimum over the pairs of the SURFACE distance (the mesh
+    # triangles, as the reference measures); the per-pair distances here are hull distances: a lower bound,
+    # equal except where the nearest feature lies in a dent of a mesh (sub-millimetre)
     _, md = eng.check_states(q, return_distance=True)
-    np.testing.assert_allclose(np.maximum(dist.min(axis=1), 0.0), md, atol=2e-6)
+    hull_min = np.maximum(dist.min(axis=1), 0.0)
+    shallow = dist.min(axis=1) > -1e-3      # (a shape deep inside another hull may be ENCLOSED by its surface: distance > 0)
+    assert np.all(md >= hull_min - 2e-6) and np.all(md[shallow] <= hull_min[shallow] + 1e-3)
+    assert (np.abs(md - hull_min) <= 2e-6).mean() > 0.95
     # a cutoff only replaces far pairs by lower bounds
     dc = eng.compute_distances(q, cutoff=0.05, witness=False)
     near = dist <= 0.05
