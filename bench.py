@@ -169,12 +169,35 @@ def run_reference(args, rank):
     """CPU arm: the float64 oracle (port of the reference path), all host threads, bounded sample."""
     if rank != 0:
         return
+    from oracle import pinocchio_ref
     from oracle.oracle import Oracle
 
     model, cmodel = panda_models()
-    orc = Oracle(model, cmodel)
     threads = len(os.sched_getaffinity(0))
     sample = int(os.environ.get("PBP_REF_SAMPLE", args.states))   # the GPU arm's step: 1 Mi states
+    if pinocchio_ref.available():
+        # Tier A: the reference's own arithmetic (pinocchio.computeCollisions through its check_collisions_at_state
+        # loop), one model copy per worker process, on a bounded prefix of the same batches
+        sub = min(sample, int(os.environ.get("PBP_PIN_SAMPLE", 200_000)))
+        rates = []
+        for k in range(max(args.steps, 1)):
+            rate, _ = pinocchio_ref.timed_rate(make_batch(model, sub, 7919 * 0 + (k % 2)).astype(np.float64), threads)
+            rates.append(rate)
+        value = float(np.mean(rates))
+        line = {
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sample / value * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "states_per_gpu_per_step": sample,
+                       "note": f"CPU arm: Pinocchio + coal (the reference's own check_collisions_at_state loop), {threads} worker processes, "
+                               f"{sub}-state prefix of each step's batch"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+                             "sample": f"{sub} states/step x {args.steps} steps of the config-2 distribution through pinocchio.computeCollisions"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "pinocchio": "importable: Tier-A reference timing",
+        }
+        print(json.dumps(line), flush=True)
+        return
+    orc = Oracle(model, cmodel)
     batches = [make_batch(model, sample, 7919 * 0 + b).astype(np.float64) for b in range(2)]   # rank 0's first two batches of the GPU arm
     for w in range(max(args.warmup, 1)):
         orc.check_states(batches[w % 2][: sample // 4], use_cull=1, nthreads=threads)
@@ -191,11 +214,12 @@ def run_reference(args, rank):
         "config": {"workload": WORKLOAD, "states_per_gpu_per_step": sample,
                    "l2": f"inputs rotate over {N_BATCHES} batches ({N_BATCHES * sample * 36 / 1e6:.0f} MB > 126 MB L2)",
                    "parallelism": f"{args.gpus} rank(s), states sharded, no data-path collective",
-                   "note": "CPU arm: float64 restatement of the reference path (oracle/pbp_oracle.c) on all host threads of rank 0 -- NOT "
-                           "Pinocchio/coal, which are not installable here (a Pinocchio probe runs first: see `pinocchio`)"},
+                   "note": "CPU arm: float64 restatement of the reference path (oracle/pbp_oracle.c, kind 'port') on all host threads of rank 0 "
+                           "-- NOT upstream Pinocchio/coal timing: the probe for `import pinocchio` failed on this box (see `pinocchio`)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} states/step x {args.steps} steps of the config-2 distribution, bounding-sphere cull + first-hit exit, exact triangle tests where hulls touch (surface semantics)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "pinocchio": "not importable: oracle port timed instead",
     }
     print(json.dumps(line), flush=True)
 
@@ -397,7 +421,21 @@ def main():
             # classify: verdicts may differ only where the reference min distance is within 1e-6 m
             _, md_bad, _, _ = orc.check_states(qs[bad], want_all=True, use_cull=0, nthreads=threads)
             beyond = int((md_bad > 1e-6).sum())
-        parity = {"checked": sample_n, "mismatches": int(len(bad)), "mismatches_beyond_1e-6m": beyond}
+        parity = {"checked": sample_n, "mismatches": int(len(bad)), "mismatches_beyond_1e-6m": beyond, "checker": "oracle (float64 port)"}
+        from oracle import pinocchio_ref
+
+        if pinocchio_ref.available():   # Tier A: the reference's own arithmetic is on this box -- time it and check against it
+            sub = min(sample_n, int(os.environ.get("PBP_PIN_SAMPLE", 200_000)))
+            rate, hit_pin = pinocchio_ref.timed_rate(qs[:sub], threads)
+            cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": "reference",
+                            "sample": f"first {sub} states of the last timed batch through pinocchio.computeCollisions (the reference's check_collisions_at_state loop), one process per core",
+                            "port_value": cpu_baseline["value"]}
+            badp = np.nonzero(hit_pin != hit_host[:sub])[0]
+            beyondp = 0
+            if len(badp):
+                _, md_bad, _, _ = orc.check_states(qs[badp], want_all=True, use_cull=0, nthreads=threads)
+                beyondp = int((md_bad > 1e-6).sum())
+            parity["pinocchio"] = {"checked": sub, "mismatches": int(len(badp)), "mismatches_beyond_1e-6m": beyondp}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

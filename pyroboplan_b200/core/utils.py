@@ -43,11 +43,23 @@ def get_collision_pair_indices_from_bodies(model, collision_model, body_list):
     ]
 
 
+def _pair_type(collision_model):
+    """``CollisionPair`` of the model's own kind: this package's, or ``pinocchio.CollisionPair`` when the
+    caller holds a real ``pinocchio.GeometryModel`` (reference core/utils.py:471)."""
+    from ..model import GeometryModel
+
+    if isinstance(collision_model, GeometryModel):
+        return CollisionPair
+    import pinocchio
+
+    return pinocchio.CollisionPair
+
+
 def set_collisions(model, collision_model, body1, body2, enable):
     """Enable/disable all pairs between two bodies. Reference: core/utils.py:449-475."""
     for id1 in get_collision_geometry_ids(model, collision_model, body1):
         for id2 in get_collision_geometry_ids(model, collision_model, body2):
-            pair = CollisionPair(id1, id2)
+            pair = _pair_type(collision_model)(id1, id2)
             if enable:
                 collision_model.addCollisionPair(pair)
             else:
@@ -151,6 +163,25 @@ def check_within_limits(model, q):
     return np.all(q >= model.lowerPositionLimit) and np.all(q <= model.upperPositionLimit)
 
 
+_FK_HOLDERS = {}
+
+
+def fk_holder(model):
+    """An empty geometry model per kinematic model: the key the FK-only engine of ``model`` is cached on."""
+    from ..model import GeometryModel
+
+    holder = getattr(model, "_pbp_fk_holder", None)
+    if holder is None:
+        holder = _FK_HOLDERS.get(id(model))
+    if holder is None:
+        holder = GeometryModel()
+        try:
+            model._pbp_fk_holder = holder
+        except (AttributeError, TypeError):
+            _FK_HOLDERS[id(model)] = holder
+    return holder
+
+
 def extract_cartesian_pose(model, target_frame, q, data=None):
     """Pose of a model frame at ``q`` (device FK). Reference: core/utils.py:322-346."""
     return extract_cartesian_poses(model, target_frame, [q])[0]
@@ -164,11 +195,7 @@ def extract_cartesian_poses(model, target_frame, q_vec, data=None):
     fid = model.getFrameId(target_frame)
     if fid >= model.nframes:
         raise ValueError(f"unknown frame {target_frame!r}")
-    holder = getattr(model, "_pbp_fk_holder", None)
-    if holder is None:
-        holder = GeometryModel()
-        model._pbp_fk_holder = holder
-    eng = get_engine(model, holder)
+    eng = get_engine(model, fk_holder(model))
     Q = np.asarray(q_vec, dtype=np.float64).reshape(len(q_vec), -1)
     _, _, oMf = eng.fk(Q, joints=False, geoms=False, frames=True)
     return [SE3(oMf[i, fid, :9].reshape(3, 3).astype(np.float64), oMf[i, fid, 9:].astype(np.float64)) for i in range(len(Q))]
@@ -189,16 +216,17 @@ def calculate_collision_vector_and_jacobians(model, collision_model, data, colli
     q = np.asarray(q, dtype=np.float64).reshape(1, -1)
     dist, p1, p2, normal = eng.compute_distances(q)
     oMi, _, _ = eng.fk(q, joints=True, geoms=False, frames=False)
-    cp = collision_model.collisionPairs[pair_idx]
+    hm, hcm = eng.host_model, eng.host_collision_model     # this package's containers (converted from Pinocchio's if need be)
+    cp = hcm.collisionPairs[pair_idx]
     jacs = []
     for gid, point in ((cp.first, p1[0, pair_idx]), (cp.second, p2[0, pair_idx])):
-        J = np.zeros((3, model.nv))
-        j = collision_model.geometryObjects[gid].parentJoint
+        J = np.zeros((3, hm.nv))
+        j = hcm.geometryObjects[gid].parentJoint
         while j > 0:
             R, o = oMi[0, j, :9].reshape(3, 3).astype(np.float64), oMi[0, j, 9:].astype(np.float64)
-            z = R @ np.asarray(model.joints[j].axis, dtype=np.float64)
-            J[:, model.joints[j].idx_v] = np.cross(z, point.astype(np.float64) - o) if model.joints[j].type == 1 else z
-            j = model.parents[j]
+            z = R @ np.asarray(hm.joints[j].axis, dtype=np.float64)
+            J[:, hm.joints[j].idx_v] = np.cross(z, point.astype(np.float64) - o) if hm.joints[j].type == 1 else z
+            j = hm.parents[j]
         jacs.append(J)
     return normal[0, pair_idx].astype(np.float64) * float(dist[0, pair_idx]), jacs[0], jacs[1]
 

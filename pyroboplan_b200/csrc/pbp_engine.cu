@@ -403,6 +403,19 @@ int pbp_get_stats(pbp_engine *e, pbp_stats *out, int reset) {
     return 0;
 }
 
+#ifdef PBP_DEBUG_STATS
+// developer build only (not in include/pbp_engine.h): the kernels' debug counters of the current device
+int pbp_debug_stats(unsigned long long *out48, int reset) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out48, pbp::g_dbg, sizeof(unsigned long long) * 48));
+    if (reset) {
+        unsigned long long z[48] = {0};
+        CUDA_TRY(cudaMemcpyToSymbol(pbp::g_dbg, z, sizeof(z)));
+    }
+    return 0;
+}
+#endif
+
 int pbp_set_profiling(pbp_engine *e, int enabled) {
     if (!e) return fail(PBP_ERR_ARG, "engine is NULL");
     e->profiling = enabled != 0;

@@ -614,6 +614,8 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
     // chunk claimed by the warp
     uint32_t cursor = 0, chunk_end = 0;
     bool more = true;
+    const long long tn0 = DBG_CLOCK();
+    if (blockIdx.x == 0 && threadIdx.x == 0) DBG_ADD(30, total);
     for (;;) {
         unsigned need = __ballot_sync(0xffffffffu, phase == 0);
         // batch the refills: the refill path (bin search, 12 strided loads, GJK init) runs with only
@@ -686,6 +688,8 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
                 return;
             }
             if (fl & PAIR_SURFACE) {
+                if (r.hit && (fl & PAIR_ENCLOSE)) DBG_ADD(35, 1);
+                if (!r.hit && !r.far) DBG_ADD(36, 1);
                 if (r.hit && (fl & PAIR_NOCORE)) { bins.group[slot] = group | SR_PARKED; return; }   // a hull hit proves nothing: the triangles decide
                 if (r.hit && (fl & PAIR_ENCLOSE)) {
                     // one shape of this pair could be enclosed by the other's surface, which is the free
@@ -701,12 +705,13 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
                 }
             }
             if (r.hit) {
+                DBG_ADD(37, 1);
                 out.hit[group] = 1;
                 if (MODE == MODE_BOOL_ALL) {
                     if (out.first_pair) atomicMin(out.first_pair + group, M.pair_orig[p]);
                     if (out.first_bad) atomicMin(out.first_bad + group, has_sample ? bins.sample[slot] : 0);
                 }
-            }
+            } else DBG_ADD(38, 1);
         };
         auto support = [&](GjkOut &r, float &radii) {
             const DevGeom &GA = sg[sp[p].a];
@@ -735,6 +740,7 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
             if (!more && cursor >= chunk_end) break;
             continue;
         }
+        if (lane == 0) { DBG_ADD(31, 1); DBG_ADD(32, n_sup); }
         GjkOut r;
         float radii = 0.f;
 #if PBP_NP_LOCKSTEP
@@ -764,6 +770,7 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
         if (finished) publish(r, radii);
 #endif
     }
+    if (lane == 0) { const long long dt = DBG_CLOCK() - tn0; DBG_ADD(33, dt); DBG_MAX(34, dt); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -852,6 +859,8 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
             if (M.pair_enclose[k] & want) bin_chunks += (bins.count_np[k] + 31u) >> 5;
     }
     const uint32_t total_chunks = bin_chunks + ((list_n + 31u) >> 5);
+    const long long tk0 = DBG_CLOCK();
+    if (blockIdx.x == 0 && threadIdx.x == 0) { DBG_ADD(22, bin_chunks); DBG_ADD(23, list_n); }
     for (;;) {
         // next chunk of the concatenated bins / of the list, claimed from a global cursor: the chunks differ
         // widely in cost (parked lanes, true enclosures, triangle stages), a fixed round-robin leaves warps idle
@@ -859,6 +868,7 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
         if (lane == 0) c = atomicAdd(chunk_cursor, 1u);
         c = __shfl_sync(0xffffffffu, c, 0);
         if (c >= total_chunks) break;
+        const long long tl0 = DBG_CLOCK();
         int p = -1;
         int64_t slot = 0;
         bool active = false;
@@ -916,9 +926,13 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
             else v = decide_boolean(tab, fl, (g & SR_PARKED) != 0 && !(fl & PAIR_NOCORE), GA, GB, T, padding);
             if (v.status == ST_HIT) on_hit(p, group, slot);
             if (v.status == ST_VALUE) on_value(p, group, slot, fmaxf(v.dist - GA.core_radius - GB.core_radius, 0.f));
+            DBG_ADD(0, 1); DBG_ADD(1 + v.status, 1);
+            if (g & SR_PARKED) DBG_ADD(24, 1);
         }
+        if (lane == 0) DBG_ADD(11, DBG_CLOCK() - tl0);
         settle_warp_items<MODE>(M, tab, v, p, group, slot, T, padding, la, lb, (int)lane, on_hit, on_value, decided);
     }
+    if (lane == 0) { const long long dt = DBG_CLOCK() - tk0; DBG_ADD(14, dt); DBG_MAX(13, dt); }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -26,6 +26,18 @@
 
 namespace pbp {
 
+// Developer counters (build with -DPBP_DEBUG_STATS, read with pbp_debug_stats): off in the product build.
+#if defined(PBP_DEBUG_STATS) && defined(__CUDACC__)
+__device__ unsigned long long g_dbg[48];
+#define DBG_ADD(i, v) atomicAdd(&g_dbg[i], (unsigned long long)(v))
+#define DBG_MAX(i, v) atomicMax(&g_dbg[i], (unsigned long long)(v))
+#define DBG_CLOCK() clock64()
+#else
+#define DBG_ADD(i, v) ((void)sizeof(v))
+#define DBG_MAX(i, v) ((void)sizeof(v))
+#define DBG_CLOCK() 0ll
+#endif
+
 // MODE_BOOL      verdict only; a state stops at its first certain hit, decided groups are skipped
 // MODE_BOOL_ALL  verdict + first_pair / first_bad: every pair of every state is resolved
 // MODE_DIST      verdict + min distance: pairs are resolved unless certainly farther than the bound
@@ -303,6 +315,7 @@ __device__ __noinline__ float triangle_stage(const SurfTables &tab, const DevGeo
             __syncwarp();
             // ---- every pair of the two lists, the lanes sharing them
             const int npairs = ca_n * cb_n;
+            if (lane == 0) { DBG_ADD(7, npairs); DBG_MAX(8, npairs); DBG_ADD(15, ca_n); DBG_ADD(16, cb_n); }
             for (int i0 = 0; i0 < npairs; i0 += PBP_LANES) {
                 const int i = i0 + lane;
                 if (i < npairs) {
@@ -474,7 +487,9 @@ __device__ __forceinline__ void settle_warp_items(const DevModel &M, const SurfT
         if (st == ST_WALK) {
             const ShapeRef AH = hull_shape(tab, GA), BH = hull_shape(tab, GB);
             float gap = 0.f, tolo = 0.f;
+            const long long tw0 = DBG_CLOCK();
             const int res = enclosure_roles(tab.planes, fl, GA, GB, AH, BH, Ts, MODE == MODE_DIST ? 0.f : padding, lane, PBP_LANES, INT_MAX, &gap, &tolo);
+            if (lane == 0) { DBG_ADD(12, DBG_CLOCK() - tw0); DBG_ADD(17 + res, 1); }
             if (res == ENC_POKES) {
                 if (lane == 0) { if (MODE == MODE_DIST) on_value(ps, gs, as, 0.f); else on_hit(ps, gs, as); }
                 continue;
@@ -485,7 +500,9 @@ __device__ __forceinline__ void settle_warp_items(const DevModel &M, const SurfT
             have_n = 0;
             U = MODE == MODE_DIST ? fmaxf(gap, 0.f) + tolo + radii + 1e-6f : padding + radii;
         }
+        const long long tt0 = DBG_CLOCK();
         const float d = triangle_stage(tab, GA, GB, Ts, n, have_n != 0, U, MODE != MODE_DIST, la, lb, lane);
+        if (lane == 0) { const long long dt = DBG_CLOCK() - tt0; DBG_ADD(6, 1); DBG_ADD(9, dt); DBG_MAX(10, dt); DBG_ADD(20, have_n ? 1 : 0); DBG_ADD(21, d <= U ? 1 : 0); }
         if (lane == 0 && d <= U) {
             if (MODE == MODE_DIST) on_value(ps, gs, as, fmaxf(d - radii, 0.f)); else on_hit(ps, gs, as);
         }

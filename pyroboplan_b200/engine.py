@@ -421,10 +421,22 @@ class CollisionEngine:
             raise RuntimeError("pyroboplan_b200 needs a CUDA device (B200); there is no CPU fallback")
         if device is None:
             device = torch.cuda.current_device()
-        self.device = int(torch.device("cuda", device).index if not isinstance(device, int) else device)
+        if not isinstance(device, int):     # torch.device, "cuda:1", "cuda"
+            d = torch.device(device)
+            if d.type != "cuda":
+                raise ValueError(f"CollisionEngine needs a CUDA device, got {device!r}")
+            device = d.index if d.index is not None else torch.cuda.current_device()
+        self.device = int(device)
         self.torch_device = torch.device("cuda", self.device)
+        from .model.pinocchio_adapter import from_pinocchio, is_native_model
+
+        if not is_native_model(collision_model):      # Pinocchio objects, as the reference's callers hold them
+            collision_model = from_pinocchio(model, collision_model)[1]
+        if not is_native_model(model):
+            model = from_pinocchio(model, None)[0]
         arrays, sizes = flatten_model(model, collision_model, mesh_semantics)
         self._arrays = arrays
+        self.host_model, self.host_collision_model = model, collision_model   # the containers the tables were compiled from
         self.mesh_semantics = mesh_semantics
         self.nq, self.njoints, self.ngeoms = sizes["nq"], sizes["njoints"], sizes["ngeoms"]
         self.npairs, self.nframes = sizes["npairs"], sizes["nframes"]
@@ -707,14 +719,66 @@ def measure_fp32_peak(device=0):
     return out.value
 
 
-def get_engine(model, collision_model, device=None):
-    """Engine cached on the collision model; rebuilt when the model or its pair list changes."""
-    key = (id(model), getattr(model, "_revision", 0), getattr(collision_model, "_revision", 0), device)
+_FOREIGN_CACHE = {}    # (id(model), id(collision_model)) -> (key, engine): Pinocchio objects that refuse new attributes
+_FOREIGN_CACHE_MAX = 8
+
+
+def _cheap_key(model, collision_model, device):
+    """What `get_engine` compares on every call: object identities, the containers' revision counters and
+    the counts an add / remove changes.  In-place edits it cannot see (a placement assigned through
+    ``geometryObjects[i].placement``, limits overwritten) need `invalidate_engine`, or PBP_STRICT_CACHE=1,
+    which adds the content fingerprint of model/pinocchio_adapter.py to the key (a walk over the model
+    per call)."""
+    key = (id(model), id(collision_model), getattr(model, "_revision", 0), getattr(collision_model, "_revision", 0),
+           int(model.njoints), len(collision_model.geometryObjects), len(collision_model.collisionPairs), device)
+    if os.environ.get("PBP_STRICT_CACHE") == "1":
+        from .model.pinocchio_adapter import fingerprint
+
+        key += (fingerprint(model, collision_model),)
+    return key
+
+
+def _cache_get(collision_model, model):
     cached = getattr(collision_model, "_pbp_engine_cache", None)
+    return cached if cached is not None else _FOREIGN_CACHE.get((id(model), id(collision_model)))
+
+
+def _cache_put(collision_model, model, entry):
+    try:
+        collision_model._pbp_engine_cache = entry
+    except (AttributeError, TypeError):     # an extension type without a __dict__
+        if len(_FOREIGN_CACHE) >= _FOREIGN_CACHE_MAX:
+            _, old = _FOREIGN_CACHE.pop(next(iter(_FOREIGN_CACHE)))
+            old.close()
+        _FOREIGN_CACHE[(id(model), id(collision_model))] = entry
+
+
+def invalidate_engine(collision_model, model=None):
+    """Forget the engine compiled for ``collision_model`` (call after editing a model in place)."""
+    cached = _cache_get(collision_model, model)
+    if cached is not None:
+        cached[1].close()
+    try:
+        collision_model._pbp_engine_cache = None
+    except (AttributeError, TypeError):
+        pass
+    for k in [k for k in _FOREIGN_CACHE if k[1] == id(collision_model)]:
+        _FOREIGN_CACHE.pop(k)
+
+
+def get_engine(model, collision_model, device=None):
+    """Engine cached on the collision model; rebuilt when the model or its pair list changes.
+
+    ``model`` / ``collision_model`` are this package's containers or Pinocchio objects
+    (``pinocchio.Model`` / ``pinocchio.GeometryModel``, as the reference's callers hold them,
+    /root/reference/src/pyroboplan/core/utils.py:8-15): those are converted once by
+    ``model.pinocchio_adapter.from_pinocchio`` (same joint / frame / geometry / pair indices)."""
+    key = _cheap_key(model, collision_model, device)
+    cached = _cache_get(collision_model, model)
     if cached is not None and cached[0] == key:
         return cached[1]
     if cached is not None:
         cached[1].close()
     eng = CollisionEngine(model, collision_model, device=device)
-    collision_model._pbp_engine_cache = (key, eng)
+    _cache_put(collision_model, model, (key, eng))
     return eng

@@ -61,11 +61,9 @@ class DifferentialIk:
         if collision_model is not None:
             self._engine_model = collision_model
         else:
-            holder = getattr(model, "_pbp_fk_holder", None)
-            if holder is None:
-                holder = GeometryModel()
-                model._pbp_fk_holder = holder
-            self._engine_model = holder
+            from ..core.utils import fk_holder
+
+            self._engine_model = fk_holder(model)
 
     # ------------------------------------------------------------------ helpers
     def _setup(self):
