@@ -108,7 +108,7 @@ struct pbp_engine {
     int sr_blocks = 1;
     // pipeline workspaces
     int64_t chunk = 0;  // states per broadphase/narrowphase round = bin capacity
-    DeviceBuffer d_bin_state, d_bin_group, d_bin_sample, d_bin_T, d_ctrl, d_doubt;
+    DeviceBuffer d_bin_state, d_bin_group, d_bin_sample, d_bin_T, d_ctrl, d_doubt, d_doubt_v, d_witem, d_witem_v;
     DeviceBuffer d_counts, d_desc_group, d_desc_frac, d_desc_sample, d_scratch_i32, d_scratch_u8, d_cub, d_sel;
     DeviceBuffer d_io_q, d_io_q2, d_io_hit, d_io_f32, d_io_i32;   // staging for the *_host entry points
     unsigned long long *h_pinned = nullptr;  // small pinned mailbox for device -> host counters
@@ -202,7 +202,7 @@ struct CallGuard {
 // [npairs + 1] narrowphase chunk cursor, [npairs + 2, 2 npairs + 2) narrowphase bin counts (items the
 // item setup kept), [2 npairs + 2] surface-refine chunk cursor, then four 64-bit counters at an 8-byte aligned offset
 // (level total, emit cursor, select count, profiled item total, IK work cursor).
-inline size_t ctrl_words(const pbp_engine *e) { return 2 * (size_t)e->npairs + 4; }   // + the surface-refine chunk cursor, the undecided-item count
+inline size_t ctrl_words(const pbp_engine *e) { return 2 * (size_t)e->npairs + 5; }   // + the surface-refine chunk cursor, the undecided-item count, the warp-item count
 // There are two such blocks (workspaces 0 / 1, see pbp_engine::ws); the 64-bit counters live in block 0.
 inline size_t ctrl_bytes(const pbp_engine *e) { return ((ctrl_words(e) * 4 + 7) & ~(size_t)7) + 64; }   // 8 x 64-bit counters
 inline uint32_t *ctrl_base(pbp_engine *e) {
@@ -214,6 +214,7 @@ inline uint32_t *ctrl_chunk_np(pbp_engine *e) { return ctrl_base(e) + e->npairs 
 inline uint32_t *ctrl_counts_np(pbp_engine *e) { return ctrl_base(e) + e->npairs + 2; }
 inline uint32_t *ctrl_chunk_sr(pbp_engine *e) { return ctrl_base(e) + 2 * e->npairs + 2; }
 inline uint32_t *ctrl_doubt(pbp_engine *e) { return ctrl_base(e) + 2 * e->npairs + 3; }
+inline uint32_t *ctrl_witem(pbp_engine *e) { return ctrl_base(e) + 2 * e->npairs + 4; }
 inline unsigned long long *ctrl_u64(pbp_engine *e, int i) {
     const size_t off = (ctrl_words(e) * 4 + 7) & ~(size_t)7;
     return reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(e->d_ctrl.p) + off) + i;
@@ -315,6 +316,8 @@ int launch_round_kernels(pbp_engine *e, const StateSource &src, int64_t n, float
         else
             k_surface_refine<MODE, false><<<sr_grid, SR_THREADS, 0, st>>>(e->dm, padding, out, bins, ctrl_chunk_sr(e), has_sample);
         LAUNCH_CHECK("k_surface_refine");
+        k_surface_settle<MODE><<<(unsigned)std::min<int64_t>(e->num_sms * 4, std::max<int64_t>(1, max_items / 4)), SS_THREADS, 0, st>>>(e->dm, padding, out, bins, has_sample);
+        LAUNCH_CHECK("k_surface_settle");
     }
     return 0;
 }
@@ -334,8 +337,13 @@ int run_round(pbp_engine *e, int mode, const StateSource &src, int64_t n, float 
     bins.count_np = ctrl_counts_np(e);
     bins.cap = e->chunk;
     bins.doubt = e->d_doubt.as<int2>() + ws_off;
+    bins.doubt_v = e->d_doubt_v.as<float4>() + ws_off;
     bins.doubt_count = ctrl_doubt(e);
     bins.doubt_cap = (uint32_t)round_cap(e);
+    bins.witem = e->d_witem.as<int2>() + ws_off;
+    bins.witem_v = e->d_witem_v.as<float4>() + ws_off;
+    bins.witem_count = ctrl_witem(e);
+    bins.witem_cap = (uint32_t)round_cap(e);
     CUDA_TRY(cudaMemsetAsync(ctrl_base(e), 0, ctrl_words(e) * 4, st));
     int rc;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -366,8 +374,8 @@ int check_args(pbp_engine *e, const void *a, int64_t n) {
     if (!e) return fail(PBP_ERR_ARG, "engine is NULL");
     if (n < 0) return fail(PBP_ERR_ARG, "negative count");
     if (n > 0 && !a) return fail(PBP_ERR_ARG, "NULL buffer");
-    // (group ids travel through the bins with two flag bits, SR_PARKED / SR_DOUBT, on top)
-    if (n >= (int64_t)SR_DOUBT) return fail(PBP_ERR_ARG, "more than 2^29-1 states/edges per call are not supported");
+    // (group ids travel through the bins with three flag bits, SR_PARKED / SR_DOUBT / SR_NOENC, on top)
+    if (n >= (int64_t)SR_NOENC) return fail(PBP_ERR_ARG, "more than 2^28-1 states/edges per call are not supported");
     return 0;
 }
 
@@ -458,7 +466,7 @@ void pbp_engine_destroy(pbp_engine *e) {
     for (cudaEvent_t ev : e->prof_pool) cudaEventDestroy(ev);
     DeviceBuffer *bufs[] = {&e->d_joints, &e->d_jgeoms, &e->d_geoms, &e->d_bpgeoms, &e->d_bpboxes, &e->d_bppairs, &e->d_groups, &e->d_pairorig, &e->d_paths,
                             &e->d_pathops, &e->d_order, &e->d_verts, &e->d_supcells, &e->d_suplists, &e->d_qlim, &e->d_frames, &e->d_bin_state,
-                            &e->d_bin_group, &e->d_bin_sample, &e->d_bin_T, &e->d_ctrl, &e->d_doubt, &e->d_counts, &e->d_desc_group,
+                            &e->d_bin_group, &e->d_bin_sample, &e->d_bin_T, &e->d_ctrl, &e->d_doubt, &e->d_doubt_v, &e->d_witem, &e->d_witem_v, &e->d_counts, &e->d_desc_group,
                             &e->d_desc_frac, &e->d_desc_sample, &e->d_scratch_i32, &e->d_scratch_u8, &e->d_cub, &e->d_sel,
                             &e->d_io_q, &e->d_io_q2, &e->d_io_hit, &e->d_io_f32, &e->d_io_i32, &e->d_ik_tables, &e->d_ws_oMi, &e->d_ws_oMg, &e->d_ws_dist,
                             &e->d_ws_p1, &e->d_ws_p2, &e->d_ws_nrm, &e->d_pairs_orig, &e->d_planes, &e->d_plane_idx, &e->d_surf_tol, &e->d_pair_enclose, &e->d_kverts, &e->d_ksupcells,
@@ -712,6 +720,7 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
 #undef SET_SMEM_SR
     e->smem_sr = vert_bytes + align16((size_t)e->dm.nplanes * sizeof(float4));
     e->sr_tables_in_smem = e->smem_sr + sr_static <= max_optin;   // one 16-warp block per SM is enough for this kernel
+    if (const char *v = getenv("PBP_SR_SMEM")) e->sr_tables_in_smem = e->sr_tables_in_smem && atoi(v) != 0;   // developer switch
     {
         int occ_sr = 1;
         if (e->sr_tables_in_smem) CUDA_TRY_BAIL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sr, k_surface_refine<MODE_BOOL, true>, SR_THREADS, e->smem_sr));
@@ -772,7 +781,9 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
     e->chunk = chunk;
     const size_t slots = (size_t)np1 * (size_t)chunk;
     if ((rc = e->d_bin_state.ensure(slots * 4)) || (rc = e->d_bin_group.ensure(slots * 4)) || (rc = e->d_bin_sample.ensure(slots * 4)) ||
-        (rc = e->d_bin_T.ensure(slots * 48)) || (rc = e->d_ctrl.ensure(2 * ctrl_bytes(e))) || (rc = e->d_doubt.ensure((size_t)chunk * sizeof(int2))))
+        (rc = e->d_bin_T.ensure(slots * 48)) || (rc = e->d_ctrl.ensure(2 * ctrl_bytes(e))) || (rc = e->d_doubt.ensure((size_t)chunk * sizeof(int2))) ||
+        (rc = e->d_doubt_v.ensure((size_t)chunk * sizeof(float4))) || (rc = e->d_witem.ensure((size_t)chunk * sizeof(int2))) ||
+        (rc = e->d_witem_v.ensure((size_t)chunk * sizeof(float4))))
         return bail(rc);
     CUDA_TRY_BAIL(cudaMemset(e->d_ctrl.p, 0, 2 * ctrl_bytes(e)));
     CUDA_TRY_BAIL(cudaMallocHost(reinterpret_cast<void **>(&e->h_pinned), 64));

@@ -68,8 +68,15 @@ struct Bins {
     // the refine kernel runs 32 of them per warp: (pair, index in the pair's bin).  Entries beyond the
     // capacity are marked in `group` (SR_DOUBT) instead and found by a scan of all bins.
     int2 *doubt;
+    float4 *doubt_v;         // ... and the direction the narrowphase's core run converged on (a warm start for the refine kernel)
     uint32_t *doubt_count;
     uint32_t doubt_cap;
+    // items the refine kernel leaves to a whole warp (walk over the enclosing core's planes, triangle stage):
+    // (pair | status << 24, slot) and (U, n) -- settled by k_surface_settle, one warp per item
+    int2 *witem;
+    float4 *witem_v;
+    uint32_t *witem_count;
+    uint32_t witem_cap;
 };
 
 struct Outputs {
@@ -454,6 +461,7 @@ k_item_setup(DevModel M, StateSource src, float padding, Outputs out, Bins bins,
         const ShapeRef B = MODE == MODE_DIST ? hull_shape(tab, GB) : core_shape(tab, GB);
         const float radii = GA.core_radius + GB.core_radius;
         const float eps_pair = pair_eps(GA, GB);
+        const int fl_enc = (MODE != MODE_DIST && M.has_tris) ? (M.pair_enclose[p] & PAIR_ENCLOSE) : 0;
         for (uint32_t base = begin; base < end; base += 32) {
             const uint32_t idx = base + lane;
             bool keep = idx < end;
@@ -513,6 +521,10 @@ k_item_setup(DevModel M, StateSource src, float padding, Outputs out, Bins bins,
                 const bool finished = (MODE == MODE_DIST) ? gjk_support_phase<true>(A, B, R, gs, margin, bound, go)
                                                           : gjk_support_phase<false>(A, B, R, gs, margin, margin + eps_pair, go);
                 if (finished) keep = false;   // at n == 0 the only exit is "certainly farther than the cut"
+                // pairs where one shape could sit inside the other's surface: most placements rule that out along
+                // the centre line (the would-be inner shape reaches at least as far as the outer hull).  Decided
+                // here, where the whole warp works on the same pair, a later core hit needs no enclosure test.
+                if (keep && fl_enc && enclosure_quick_pokes(fl_enc, GA, GB, hull_shape(tab, GA), hull_shape(tab, GB), R, padding)) group |= SR_NOENC;
             }
             // compact the survivors to the front of the bin (warp-aggregated slot reservation)
             const unsigned km = __ballot_sync(0xffffffffu, keep);
@@ -608,6 +620,7 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
     GjkState s;
     float T[12];
     int32_t group = 0;
+    bool noenc = false;      // the item setup ruled an enclosure out (pairs with an enclosure flag)
     int p = 0;               // this lane's pair
     int64_t slot = 0;        // this lane's bin slot
     float bound = 0.f;
@@ -648,8 +661,10 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
                 }
                 p = order[lo];
                 slot = (int64_t)p * bins.cap + (gi - prefix[lo]);
-                const int32_t g = bins.group[slot];
-                if (g >= 0 && !(MODE == MODE_BOOL && out.hit[g])) {
+                const int32_t graw = bins.group[slot];
+                const int32_t g = graw & ~SR_NOENC;
+                if (graw >= 0 && !(MODE == MODE_BOOL && out.hit[g])) {
+                    noenc = (graw & SR_NOENC) != 0;
 #pragma unroll
                     for (int k = 0; k < 12; k++) T[k] = bins.T[k * stride + slot];
                     const DevGeom &GA = sg[sp[p].a];
@@ -688,10 +703,10 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
                 return;
             }
             if (fl & PAIR_SURFACE) {
-                if (r.hit && (fl & PAIR_ENCLOSE)) DBG_ADD(35, 1);
+                if (r.hit && (fl & PAIR_ENCLOSE) && !noenc) DBG_ADD(35, 1);
                 if (!r.hit && !r.far) DBG_ADD(36, 1);
                 if (r.hit && (fl & PAIR_NOCORE)) { bins.group[slot] = group | SR_PARKED; return; }   // a hull hit proves nothing: the triangles decide
-                if (r.hit && (fl & PAIR_ENCLOSE)) {
+                if (r.hit && (fl & PAIR_ENCLOSE) && !noenc) {
                     // one shape of this pair could be enclosed by the other's surface, which is the free
                     // placement -- the refine kernel decides (all its lanes busy with such items)
                     bins.group[slot] = group | SR_PARKED;
@@ -699,7 +714,10 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
                 }
                 if (!r.hit && !r.far) {   // between the bounds: the triangles decide
                     const uint32_t di = atomicAdd(bins.doubt_count, 1u);
-                    if (di < bins.doubt_cap) bins.doubt[di] = make_int2(p, (int)(slot - (int64_t)p * bins.cap));
+                    if (di < bins.doubt_cap) {
+                        bins.doubt[di] = make_int2(p, (int)(slot - (int64_t)p * bins.cap));
+                        bins.doubt_v[di] = make_float4(s.v.x, s.v.y, s.v.z, 0.f);
+                    }
                     else bins.group[slot] = group | SR_DOUBT;
                     return;
                 }
@@ -784,6 +802,10 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
 // dependent table reads); cores and triangles, read by a few items only, stay in global memory.
 constexpr int SR_THREADS = 512;
 constexpr int SR_DIR = 256;       // pairs the chunk directory holds
+#ifndef PBP_SR_LIST_CHUNK
+#define PBP_SR_LIST_CHUNK 8
+#endif
+constexpr uint32_t SR_LIST_CHUNK = PBP_SR_LIST_CHUNK;   // undecided items a warp takes at a time (<= 32)
 
 template <int MODE, bool TABLES_IN_SMEM>
 __global__ void __launch_bounds__(SR_THREADS)
@@ -858,7 +880,10 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
         for (int k = 0; k < M.npairs; k++)
             if (M.pair_enclose[k] & want) bin_chunks += (bins.count_np[k] + 31u) >> 5;
     }
-    const uint32_t total_chunks = bin_chunks + ((list_n + 31u) >> 5);
+    // the undecided items of the list (two converged GJK runs each, then maybe triangles) cost many times a
+    // parked item: they go FIRST, in short chunks, so the launch does not end on a few warps still chewing them
+    const uint32_t list_chunks = (list_n + SR_LIST_CHUNK - 1) / SR_LIST_CHUNK;
+    const uint32_t total_chunks = bin_chunks + list_chunks;
     const long long tk0 = DBG_CLOCK();
     if (blockIdx.x == 0 && threadIdx.x == 0) { DBG_ADD(22, bin_chunks); DBG_ADD(23, list_n); }
     for (;;) {
@@ -873,18 +898,22 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
         int64_t slot = 0;
         bool active = false;
         int32_t g = 0;
-        if (c >= bin_chunks) {
-            // 32 undecided items of the compact list, one per lane, each with its own pair
-            const uint32_t i = (c - bin_chunks) * 32u + lane;
-            if (i < list_n) {
+        float3 v0 = make_float3(0.f, 0.f, 0.f);   // warm start of an undecided item (zero: none)
+        if (c < list_chunks) {
+            // undecided items of the compact list, one per lane, each with its own pair
+            const uint32_t i = c * SR_LIST_CHUNK + lane;
+            if (lane < SR_LIST_CHUNK && i < list_n) {
                 const int2 it = bins.doubt[i];
                 p = it.x;
                 slot = (int64_t)p * bins.cap + it.y;
                 g = bins.group[slot] | SR_DOUBT;
+                const float4 w4 = bins.doubt_v[i];
+                v0 = make_float3(w4.x, w4.y, w4.z);
                 active = true;
             }
         } else {
             uint32_t local = 0;
+            c -= list_chunks;
             if (s_n >= 0) {
                 int lo = 0, hi = s_n;   // last entry with s_first[lo] <= c
                 while (hi - lo > 1) {
@@ -914,7 +943,7 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
         const BpPair pr = M.bppairs[p];
         const DevGeom &GA = M.geoms[pr.a];
         const DevGeom &GB = M.geoms[pr.b];
-        const int32_t group = g & ~SR_BITS;
+        const int32_t group = g & ~(SR_BITS | SR_NOENC);
         if (active && decided(group)) active = false;
         float T[12];
 #pragma unroll
@@ -923,16 +952,78 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
         v.status = ST_NONE; v.dist = 0.f; v.U = 0.f; v.n = make_float3(0.f, 0.f, 0.f); v.have_n = 0;
         if (active) {
             if (MODE == MODE_DIST) v = decide_distance(tab, fl, GA, GB, T, out.min_dist[group]);
-            else v = decide_boolean(tab, fl, (g & SR_PARKED) != 0 && !(fl & PAIR_NOCORE), GA, GB, T, padding);
+            else v = decide_boolean(tab, fl, (g & SR_PARKED) != 0 && !(fl & PAIR_NOCORE), GA, GB, T, padding, v0);
             if (v.status == ST_HIT) on_hit(p, group, slot);
             if (v.status == ST_VALUE) on_value(p, group, slot, fmaxf(v.dist - GA.core_radius - GB.core_radius, 0.f));
             DBG_ADD(0, 1); DBG_ADD(1 + v.status, 1);
             if (g & SR_PARKED) DBG_ADD(24, 1);
         }
         if (lane == 0) DBG_ADD(11, DBG_CLOCK() - tl0);
-        settle_warp_items<MODE>(M, tab, v, p, group, slot, T, padding, la, lb, (int)lane, on_hit, on_value, decided);
+        // what needs a whole warp goes to a list that k_surface_settle works off one item per warp: these items
+        // cluster in a few bins (a finger inside link 5 ...), settled by the warp that found them they were the
+        // tail of the launch
+        const bool wants_warp = v.status == ST_WALK || v.status == ST_TRIANGLES;
+        const unsigned wm = __ballot_sync(0xffffffffu, wants_warp);
+        if (wm) {
+            uint32_t first = 0;
+            if (lane == 0) first = atomicAdd(bins.witem_count, (uint32_t)__popc(wm));
+            first = __shfl_sync(0xffffffffu, first, 0);
+            const uint32_t wi = first + __popc(wm & ((1u << lane) - 1u));
+            if (wants_warp && wi < bins.witem_cap) {
+                bins.witem[wi] = make_int2(p | (v.status << 24) | (v.have_n << 28), (int)(slot - (int64_t)p * bins.cap));
+                bins.witem_v[wi] = make_float4(v.U, v.n.x, v.n.y, v.n.z);
+                v.status = ST_NONE;
+            }
+            if (first + (uint32_t)__popc(wm) > bins.witem_cap)   // (list full: settled here, as k_small_check does)
+                settle_warp_items<MODE>(M, tab, v, p, group, slot, T, padding, la, lb, (int)lane, on_hit, on_value, decided);
+        }
     }
     if (lane == 0) { const long long dt = DBG_CLOCK() - tk0; DBG_ADD(14, dt); DBG_MAX(13, dt); }
+}
+
+// One warp per listed item: the walk over the enclosing core's planes, the triangle stage (pbp_surface.cuh).
+// Tables are read through L1 / L2: a few thousand items per million states do not pay for staging them.
+constexpr int SS_THREADS = 128;
+
+template <int MODE>
+__global__ void __launch_bounds__(SS_THREADS)
+k_surface_settle(DevModel M, float padding, Outputs out, Bins bins, bool has_sample) {
+    SurfTables tab;
+    tab.hverts = M.verts; tab.hcells = M.sup_cells; tab.hlists = M.sup_lists; tab.planes = M.planes;
+    tab.kverts = M.kverts; tab.kcells = M.ksup_cells; tab.klists = M.ksup_lists;
+    tab.mverts = M.mverts; tab.tris = M.tris;
+    __shared__ uint16_t s_tri[SS_THREADS / 32][2][TRI_LIST_CAP];
+    uint16_t *la = s_tri[threadIdx.x >> 5][0], *lb = s_tri[threadIdx.x >> 5][1];
+    const unsigned lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)M.npairs * bins.cap;
+    auto on_hit = [&](int p, int32_t group, int64_t slot) {
+        out.hit[group] = 1;
+        if (MODE == MODE_BOOL_ALL) {
+            if (out.first_pair) atomicMin(out.first_pair + group, M.pair_orig[p]);
+            if (out.first_bad) atomicMin(out.first_bad + group, has_sample ? bins.sample[slot] : 0);
+        }
+    };
+    auto on_value = [&](int, int32_t group, int64_t, float d) {
+        if (d <= padding) out.hit[group] = 1;
+        atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(d));
+    };
+    auto decided = [&](int32_t group) { return MODE == MODE_BOOL && out.hit[group] != 0; };
+    const uint32_t n = min(*bins.witem_count, bins.witem_cap);
+    const uint32_t nwarps = gridDim.x * (SS_THREADS / 32);
+    for (uint32_t i = blockIdx.x * (SS_THREADS / 32) + (threadIdx.x >> 5); i < n; i += nwarps) {
+        const int2 it = bins.witem[i];
+        const float4 w4 = bins.witem_v[i];
+        const int p = it.x & 0xffffff;
+        const int64_t slot = (int64_t)p * bins.cap + it.y;
+        const int32_t group = bins.group[slot] & ~(SR_BITS | SR_NOENC);
+        LaneVerdict v;
+        v.status = lane == 0 ? ((it.x >> 24) & 0xf) : ST_NONE;     // lane 0 owns the item, the warp settles it
+        v.dist = 0.f; v.U = w4.x; v.n = make_float3(w4.y, w4.z, w4.w); v.have_n = (it.x >> 28) & 1;
+        float T[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) T[k] = bins.T[k * stride + slot];
+        settle_warp_items<MODE>(M, tab, v, p, group, slot, T, padding, la, lb, (int)lane, on_hit, on_value, decided);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

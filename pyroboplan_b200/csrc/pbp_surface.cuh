@@ -55,6 +55,9 @@ constexpr int PBP_LANES = 1;
 constexpr int32_t SR_PARKED = 0x40000000;   // core hit of a pair with an enclosure flag
 constexpr int32_t SR_DOUBT = 0x20000000;    // between the bounds (boolean) / may define the minimum (distance)
 constexpr int32_t SR_BITS = SR_PARKED | SR_DOUBT;
+// set by the item setup on an item of a pair with an enclosure flag whose shapes poke out of each other
+// along the centre line: a core hit of this item is a hit, nothing to park (boolean queries)
+constexpr int32_t SR_NOENC = 0x10000000;
 
 #ifndef PBP_PAIR_FLAGS_DEFINED
 #define PBP_PAIR_FLAGS_DEFINED
@@ -372,8 +375,10 @@ struct LaneVerdict {
 };
 
 // Boolean queries.  parked: core hit of a flagged pair; otherwise the item converged between margin and cut.
+// v0: where a previous GJK run on the cores of this item converged (zero vector: unknown) -- a warm start: the
+// hull run then ends after one support call when the hulls are apart along it, and both runs converge in a few.
 __device__ __forceinline__ LaneVerdict decide_boolean(const SurfTables &tab, int fl, bool parked, const DevGeom &GA, const DevGeom &GB, const float *T,
-                                                      float padding) {
+                                                      float padding, float3 v0 = make_float3(0.f, 0.f, 0.f)) {
     LaneVerdict r;
     r.status = ST_NONE; r.dist = 0.f; r.U = 0.f; r.n = make_float3(0.f, 0.f, 0.f); r.have_n = 0;
     const ShapeRef AH = hull_shape(tab, GA), BH = hull_shape(tab, GB);
@@ -388,12 +393,19 @@ __device__ __forceinline__ LaneVerdict decide_boolean(const SurfTables &tab, int
         return r;
     }
     ConvOut h;
-    gjk_converge(AH, BH, T, gjk_start_direction(GA, GB, T), margin, h);
+    const bool warm = dot3(v0, v0) > 1e-12f;
+    const float3 start = warm ? v0 : gjk_start_direction(GA, GB, T);
+    gjk_converge(AH, BH, T, start, margin, h);
     if (h.far || h.dist > margin) return r;                 // the hulls are apart: free
     ConvOut k = h;
     if (!(fl & PAIR_NOCORE)) {
-        const ShapeRef AK = core_shape(tab, GA), BK = core_shape(tab, GB);
-        gjk_converge(AK, BK, T, gjk_start_direction(GA, GB, T), FLT_MAX, k);
+        if (warm) {
+            // v0 IS the converged closest point of the cores' difference: nothing to run again
+            k.v = v0; k.dist = sqrtf(dot3(v0, v0)); k.far = 0;
+        } else {
+            const ShapeRef AK = core_shape(tab, GA), BK = core_shape(tab, GB);
+            gjk_converge(AK, BK, T, start, FLT_MAX, k);
+        }
         if (k.dist - h.dist <= 1e-6f) { r.status = ST_HIT; return r; }   // both bounds agree: within the margin
     }
     r.status = ST_TRIANGLES;

@@ -17,7 +17,7 @@ NAMES = {0: "sr lane items", 1: "sr ST_NONE", 2: "sr ST_HIT", 3: "sr ST_WALK", 4
          36: "np doubts", 37: "np hits", 38: "np free"}
 model, cmodel, vmodel = panda.load_models()
 panda.add_self_collisions(model, cmodel); panda.add_object_collisions(model, cmodel, vmodel)
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 1 << 20
 q = np.random.default_rng(0).uniform(model.lowerPositionLimit, model.upperPositionLimit, size=(n, model.nq)).astype(np.float32)
 qd = torch.as_tensor(q, device="cuda:0")
 eng = CollisionEngine(model, cmodel, device=0)
@@ -27,14 +27,16 @@ hit = torch.empty(n, dtype=torch.bool, device="cuda:0")
 
 for _ in range(2):
     eng.check_states(qd)
-lib.pbp_debug_stats(buf, 1)
-eng.check_states(qd)
-lib.pbp_debug_stats(buf, 1)
-for i in range(48):
-    if buf[i] or i in NAMES:
-        print(f"{i:3d} {NAMES.get(i, ''):36s} {buf[i]}")
+if hasattr(lib, "pbp_debug_stats"):
+    lib.pbp_debug_stats(buf, 1)
+    eng.check_states(qd)
+    lib.pbp_debug_stats(buf, 1)
+    for i in range(48):
+        if buf[i] or i in NAMES:
+            print(f"{i:3d} {NAMES.get(i, ''):36s} {buf[i]}")
 eng.set_profiling(True); eng.profile(reset=True)
 for _ in range(5):
     eng.check_states(qd)
 torch.cuda.synchronize()
-print(eng.profile(reset=True))
+pr = eng.profile(reset=True)
+print({k: (round(v / 5 * 1e3, 1) if k.endswith("_ms") else v) for k, v in pr.items()}, "(us per round)")
