@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PBP_ABI_VERSION 5
+#define PBP_ABI_VERSION 6
 
 typedef enum {
     PBP_OK = 0,
@@ -126,6 +126,11 @@ typedef struct {
     const int32_t *tris;               /* [ntris][3] */
     const int32_t *geom_tri_off;       /* [ngeoms] */
     const int32_t *geom_tri_cnt;       /* [ngeoms] 0: the geometry is a solid */
+    /* optional (may be NULL): up to four balls per geometry (cx cy cz r, geometry frame; r = 0: unused) that lie
+     * INSIDE the solid -- inside the inner core K for a surface geometry.  Two geometries whose balls overlap
+     * certainly collide: the item setup settles such pairs before any GJK iteration is spent on them.  Boxes
+     * need none (the test against a box is exact). */
+    const float *geom_inner_balls;     /* [ngeoms][4][4] */
 } pbp_model_desc;
 
 typedef struct pbp_engine pbp_engine;

@@ -125,6 +125,13 @@ inline int build_host_tables(const pbp_model_desc *d, HostTables &H) {
         B.r_out = outer[3];
         B.r_in = inner[3];
         G.r_out = outer[3];
+        if (d->geom_inner_balls) {
+            for (int k = 0; k < N_INNER_BALLS; k++) {
+                const float *b = d->geom_inner_balls + (size_t)(g * N_INNER_BALLS + k) * 4;
+                if (!(b[3] > 0.f)) continue;
+                memcpy(G.balls[G.n_balls++], b, 4 * sizeof(float));
+            }
+        }
         if (d->geom_capsule) {   // the capsule's segment doubles as the shape's "long axis" for the GJK start direction
             const float *cp = d->geom_capsule + 8 * g;
             const float du[3] = {cp[3] - cp[0], cp[4] - cp[1], cp[5] - cp[2]};

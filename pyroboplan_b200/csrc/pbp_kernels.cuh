@@ -421,6 +421,9 @@ __device__ __forceinline__ bool next_tile(uint32_t *tile_counter, const uint32_t
 // ------------------------------------------------------------------------------------------
 // Item setup: T = oMg[a]^-1 * oMg[b] for every undecided (state, pair) item
 // ------------------------------------------------------------------------------------------
+#ifndef PBP_INNER_BALLS
+#define PBP_INNER_BALLS 1     // developer switch: 0 disables the inner-ball hit certificates of the item setup
+#endif
 template <int MODE>
 __global__ void __launch_bounds__(IS_THREADS, PBP_IS_MIN_BLOCKS)
 k_item_setup(DevModel M, StateSource src, float padding, Outputs out, Bins bins, uint32_t *tile_counter) {
@@ -461,7 +464,8 @@ k_item_setup(DevModel M, StateSource src, float padding, Outputs out, Bins bins,
         const ShapeRef B = MODE == MODE_DIST ? hull_shape(tab, GB) : core_shape(tab, GB);
         const float radii = GA.core_radius + GB.core_radius;
         const float eps_pair = pair_eps(GA, GB);
-        const int fl_enc = (MODE != MODE_DIST && M.has_tris) ? (M.pair_enclose[p] & PAIR_ENCLOSE) : 0;
+        const int fl_enc_any = M.has_tris ? (M.pair_enclose[p] & PAIR_ENCLOSE) : 0;
+        const int fl_enc = MODE != MODE_DIST ? fl_enc_any : 0;
         for (uint32_t base = begin; base < end; base += 32) {
             const uint32_t idx = base + lane;
             bool keep = idx < end;
@@ -521,10 +525,29 @@ k_item_setup(DevModel M, StateSource src, float padding, Outputs out, Bins bins,
                 const bool finished = (MODE == MODE_DIST) ? gjk_support_phase<true>(A, B, R, gs, margin, bound, go)
                                                           : gjk_support_phase<false>(A, B, R, gs, margin, margin + eps_pair, go);
                 if (finished) keep = false;   // at n == 0 the only exit is "certainly farther than the cut"
-                // pairs where one shape could sit inside the other's surface: most placements rule that out along
-                // the centre line (the would-be inner shape reaches at least as far as the outer hull).  Decided
-                // here, where the whole warp works on the same pair, a later core hit needs no enclosure test.
-                if (keep && fl_enc && enclosure_quick_pokes(fl_enc, GA, GB, hull_shape(tab, GA), hull_shape(tab, GB), R, padding)) group |= SR_NOENC;
+                if (keep) {
+                    // What the first iteration could not separate is mostly colliding.  Overlapping inner balls
+                    // (pbp_surface.cuh) settle most of it here, before the narrowphase spends GJK iterations on it.
+                    // Pairs where one shape could sit inside the other's surface: most placements rule that out
+                    // along the centre line (the would-be inner shape reaches at least as far as the outer hull);
+                    // decided here, where the whole warp works on the same pair, a hit by the balls stands and a
+                    // later core hit needs no enclosure test.
+                    const float pad = MODE == MODE_DIST ? 0.f : padding;
+                    const bool balls = PBP_INNER_BALLS && inner_balls_hit(GA, GB, R, pad);
+                    bool pokes = false;
+                    if (fl_enc_any && (balls || fl_enc)) pokes = enclosure_quick_pokes(fl_enc_any, GA, GB, hull_shape(tab, GA), hull_shape(tab, GB), R, pad);
+                    if (balls && (!fl_enc_any || pokes)) {
+                        out.hit[group] = 1;
+                        if (MODE == MODE_BOOL_ALL) {
+                            if (out.first_pair) atomicMin(out.first_pair + group, M.pair_orig[p]);
+                            if (out.first_bad) atomicMin(out.first_bad + group, src.sample ? src.sample[state] : 0);
+                        }
+                        if (MODE == MODE_DIST) atomicMin(reinterpret_cast<unsigned int *>(out.min_dist + group), __float_as_uint(0.f));
+                        keep = false;
+                    } else if (fl_enc && pokes) {
+                        group |= SR_NOENC;
+                    }
+                }
             }
             // compact the survivors to the front of the bin (warp-aggregated slot reservation)
             const unsigned km = __ballot_sync(0xffffffffu, keep);

@@ -22,7 +22,9 @@ struct DevJoint {       // 96 B
     int32_t _pad;
 };
 
-struct DevGeom {        // 192 B -- narrowphase / item-setup view of a geometry
+constexpr int N_INNER_BALLS = 4;
+
+struct DevGeom {        // 256 B -- narrowphase / item-setup view of a geometry
     float P[12];        // placement in parent joint frame (world placement if parent == 0)
     float par[4];       // shape parameters
     float centre[3];    // proxy-sphere centre in the geometry frame (initial GJK direction)
@@ -52,7 +54,8 @@ struct DevGeom {        // 192 B -- narrowphase / item-setup view of a geometry
     int32_t plane_cnt;
     int32_t plane_hull_cnt;   // ... this many; the rest are planes of mesh triangles below the hull
     float surface_tol;  // two-sided distance between the hull's boundary and the mesh surface
-    int32_t _pad4;
+    int32_t n_balls;    // balls[0 .. n_balls) lie inside the solid / inside the core of a surface geometry
+    float balls[N_INNER_BALLS][4];   // cx cy cz r, geometry frame
 };
 
 struct BpGeom {         // 64 B -- broadphase view: one proxy centre, two radii (+ optional enclosing capsule)

@@ -129,6 +129,44 @@ __device__ __noinline__ void gjk_converge(const ShapeRef &A, const ShapeRef &B, 
 }
 
 // ------------------------------------------------------------------------------------------
+// Inner balls: a hit certificate that costs a handful of sphere tests
+// ------------------------------------------------------------------------------------------
+// DevGeom::balls lie inside the solid (inside the inner core of a surface geometry).  Two shapes with a pair of
+// balls within the padding -- or a ball within the padding of a box, tested exactly in the box frame -- have
+// cores within the padding: a hit, unless one shape may be enclosed by the other's surface (the caller asks
+// the centre-line test then).  T: placement of b in a's frame.  slack: FP32 rounding of the centres (metres).
+__device__ __forceinline__ bool inner_balls_hit(const DevGeom &GA, const DevGeom &GB, const float *T, float padding) {
+    const float slack = 1e-5f;
+    if (GA.shape == PBP_SHAPE_BOX) {
+        for (int j = 0; j < GB.n_balls; j++) {
+            const float3 c = se3_act(T, GB.balls[j][0], GB.balls[j][1], GB.balls[j][2]);
+            const float dx = fmaxf(fabsf(c.x) - GA.par[0], 0.f), dy = fmaxf(fabsf(c.y) - GA.par[1], 0.f), dz = fmaxf(fabsf(c.z) - GA.par[2], 0.f);
+            const float r = GB.balls[j][3] + padding - slack;
+            if (r > 0.f && fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= r * r) return true;
+        }
+        return false;
+    }
+    if (GB.shape == PBP_SHAPE_BOX) {
+        for (int i = 0; i < GA.n_balls; i++) {
+            const float3 c = se3_act_inv(T, make_float3(GA.balls[i][0], GA.balls[i][1], GA.balls[i][2]));
+            const float dx = fmaxf(fabsf(c.x) - GB.par[0], 0.f), dy = fmaxf(fabsf(c.y) - GB.par[1], 0.f), dz = fmaxf(fabsf(c.z) - GB.par[2], 0.f);
+            const float r = GA.balls[i][3] + padding - slack;
+            if (r > 0.f && fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= r * r) return true;
+        }
+        return false;
+    }
+    for (int j = 0; j < GB.n_balls; j++) {
+        const float3 cb = se3_act(T, GB.balls[j][0], GB.balls[j][1], GB.balls[j][2]);
+        for (int i = 0; i < GA.n_balls; i++) {
+            const float dx = cb.x - GA.balls[i][0], dy = cb.y - GA.balls[i][1], dz = cb.z - GA.balls[i][2];
+            const float r = GA.balls[i][3] + GB.balls[j][3] + padding - slack;
+            if (r > 0.f && fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= r * r) return true;
+        }
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------
 // Enclosure: is one shape of a core hit wholly inside the other's surface?
 // ------------------------------------------------------------------------------------------
 // `inner` pokes out of (or reaches) the enclosing hull  =>  the surfaces meet: with the cores overlapping

@@ -14,12 +14,12 @@ import os
 import numpy as np
 
 from .model.shapes import Box, Capsule, Convex, Cylinder, Sphere
-from .model.surface import surface_tables
+from .model.surface import N_INNER_BALLS, inner_balls, surface_tables
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpbp_engine.so")
 
-PBP_ABI_VERSION = 5
+PBP_ABI_VERSION = 6
 
 # symbols declared in include/pbp_engine.h (tests check the library exports every one)
 EXPORTED_SYMBOLS = [
@@ -103,6 +103,7 @@ class _ModelDesc(ctypes.Structure):
         ("tris", ctypes.c_void_p),
         ("geom_tri_off", ctypes.c_void_p),
         ("geom_tri_cnt", ctypes.c_void_p),
+        ("geom_inner_balls", ctypes.c_void_p),
     ]
 
 
@@ -262,6 +263,7 @@ def flatten_model(model, collision_model, mesh_semantics="surface"):
         "geom_outer": np.zeros((ng, 4), dtype=np.float32),
         "geom_inner": np.zeros((ng, 4), dtype=np.float32),
         "geom_capsule": np.zeros((ng, 8), dtype=np.float32),
+        "geom_inner_balls": np.zeros((ng, N_INNER_BALLS, 4), dtype=np.float32),
     }
     verts = []
     nv = 0
@@ -308,6 +310,16 @@ def flatten_model(model, collision_model, mesh_semantics="surface"):
         a["geom_inner"][i] = [*oc32, i32r]
         if isinstance(s, Convex):
             a["geom_capsule"][i] = enclosing_capsule(np.asarray(s.points, dtype=np.float32).astype(np.float64), float(o32))
+            # balls inside the solid (a surface geometry gets balls inside its inner CORE below)
+            a["geom_inner_balls"][i] = _cached_balls(s, "_pbp_inner_balls_hull", np.concatenate([s.planes[:, :3], -s.planes[:, 3:4]], axis=1),
+                                                      np.asarray(s.points, dtype=np.float32).astype(np.float64))
+        elif isinstance(s, Sphere):
+            a["geom_inner_balls"][i, 0] = [0.0, 0.0, 0.0, float(np.float32(s.radius)) - 2e-6]
+        elif isinstance(s, (Cylinder, Capsule)):
+            r = float(np.float32(s.radius)) - 2e-6
+            hl = s.halfLength if isinstance(s, Capsule) else max(s.halfLength - s.radius, 0.0)
+            for k, z in enumerate(np.linspace(-hl, hl, N_INNER_BALLS) if hl > 0 else [0.0]):
+                a["geom_inner_balls"][i, k] = [0.0, 0.0, z, min(r, s.halfLength) if isinstance(s, Cylinder) else r]
     a["verts"] = np.concatenate(verts).astype(np.float32) if verts else np.zeros((1, 3), dtype=np.float32)
     pairs = np.array([[p.first, p.second] for p in collision_model.collisionPairs], dtype=np.int32).reshape(-1, 2)
     a["pairs"] = pairs if len(pairs) else np.zeros((1, 2), dtype=np.int32)
@@ -345,8 +357,10 @@ def flatten_model(model, collision_model, mesh_semantics="surface"):
             kp = st["core_hull_planes"]
             c64 = a["geom_inner"][i, :3].astype(np.float64)
             a["geom_inner"][i, 3] = np.float32(max(float((kp[:, 3] - kp[:, :3] @ c64).min()) - 2e-6, 0.0))
+            a["geom_inner_balls"][i] = _cached_balls(g.geometry, "_pbp_inner_balls_core", kp, st["core"].astype(np.float64))
         else:
             a["geom_inner"][i, 3] = 0.0
+            a["geom_inner_balls"][i] = 0.0    # no core: nothing certifies a hit
     enclose = np.zeros(max(len(pairs), 1), np.uint8)
     for k, (ga, gb) in enumerate(pairs):
         if surface[ga] and _could_enclose(geoms[ga].geometry, geoms[gb].geometry):
@@ -370,6 +384,23 @@ def flatten_model(model, collision_model, mesh_semantics="surface"):
     sizes = dict(nq=model.nq, njoints=model.njoints, ngeoms=ng, npairs=len(pairs), nverts=nv, nframes=len(model.frames),
                  nplanes=int(plane_cnt.sum()), ncore=int(core_cnt.sum()), nmverts=int(sum(len(x) for x in mverts)), ntris=int(tri_cnt.sum()))
     return {k: np.ascontiguousarray(v) for k, v in a.items()}, sizes
+
+
+_BALL_CACHE = {}
+
+
+def _cached_balls(shape, attr, planes, points):
+    """inner_balls() per shape, cached on the shape and by content (models are loaded many times per process)."""
+    import hashlib
+
+    cached = getattr(shape, attr, None)
+    if cached is None:
+        key = hashlib.sha1(np.ascontiguousarray(planes).tobytes() + np.ascontiguousarray(points).tobytes()).hexdigest()
+        cached = _BALL_CACHE.get(key)
+        if cached is None:
+            cached = _BALL_CACHE[key] = inner_balls(planes, points)
+        setattr(shape, attr, cached)
+    return cached
 
 
 def enclosing_capsule(points, r_sphere, useful_ratio=None):

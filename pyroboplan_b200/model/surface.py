@@ -224,3 +224,58 @@ def surface_tables(shape):
     setattr(shape, _CACHE_ATTR, out)
     _CACHE[key] = out
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Inner balls: cheap "certainly colliding" certificates
+# --------------------------------------------------------------------------------------------------
+N_INNER_BALLS = 4
+
+
+def inner_balls(planes, points, k=N_INNER_BALLS, rmin_ratio=0.4):
+    """Up to ``k`` balls inside the convex set {x : n.x <= w} (``planes`` [m, 4] = nx ny nz w, unit normals;
+    ``points``: its vertices), spread along its principal axis: for 31 stations along the axis the largest
+    ball centred in the station's cross-section (one small LP each), then greedily the ball that reaches
+    farthest beyond those already chosen.  Two shapes whose balls overlap certainly collide -- the item setup
+    kernel tests that before it spends a GJK run on the pair (it settles ~60 % of the colliding Panda items).
+    Returns float32 [k, 4] (cx cy cz r; r = 0: unused), radii re-measured at the float32 centres and rounded
+    inwards."""
+    from scipy.optimize import linprog
+
+    out = np.zeros((k, 4), dtype=np.float32)
+    planes = np.asarray(planes, dtype=np.float64)
+    pts = np.asarray(points, dtype=np.float64)
+    if len(planes) < 4 or len(pts) < 4:
+        return out
+    c0 = pts.mean(axis=0)
+    _, _, vt = np.linalg.svd(pts - c0)
+    ax = vt[0]
+    ts = (pts - c0) @ ax
+    n, w = planes[:, :3], planes[:, 3]
+    A = np.hstack([n, np.ones((len(n), 1))])
+    cand = []
+    for t in np.linspace(ts.min(), ts.max(), 33)[1:-1]:
+        res = linprog(c=[0, 0, 0, -1.0], A_ub=A, b_ub=w, A_eq=[[*ax, 0.0]], b_eq=[t + c0 @ ax], bounds=[(None, None)] * 3 + [(0, None)], method="highs")
+        if res.success and res.x[3] > 1e-4:
+            cand.append((res.x[:3], float(res.x[3])))
+    if not cand:
+        return out
+    rmax = max(r for _, r in cand)
+    cand = [x for x in cand if x[1] >= rmin_ratio * rmax]
+    picked = []
+    while cand and len(picked) < k:
+        def reach(cr):
+            c, r = cr
+            return r if not picked else min(r - (ri - np.linalg.norm(ci - c)) for ci, ri in picked)
+
+        j = int(np.argmax([reach(x) for x in cand]))
+        if picked and reach(cand[j]) < 2e-3:
+            break
+        picked.append(cand.pop(j))
+    for i, (c, _) in enumerate(picked):
+        c32 = c.astype(np.float32)
+        r = float((w - n @ c32.astype(np.float64)).min()) - 2e-6
+        if r > 0.0:
+            r32 = np.float32(r)
+            out[i] = [*c32, r32 if float(r32) <= r else np.nextafter(r32, np.float32(0.0))]
+    return out
