@@ -29,8 +29,17 @@ def rewire_choice(model, collision_model, node_qs, node_costs, q_new, parent_ind
     node_qs = np.asarray(node_qs, dtype=np.float64).reshape(len(node_costs), -1)
     node_costs = np.asarray(node_costs, dtype=np.float64)
     q_new = np.asarray(q_new, dtype=np.float64)
-    dist = np.linalg.norm(node_qs - q_new, axis=1)
-    cost0 = node_costs[parent_index] + dist[parent_index]
+    # Distances exactly as the reference forms them -- ``np.linalg.norm`` of ONE difference vector
+    # (core/utils.py:135-151) -- for every node a vectorised pre-filter (with slack) lets through: on an
+    # RRT-Connect branch the nodes are collinear, ``other.cost + dist`` ties with the running minimum up
+    # to rounding, and a row-wise norm (different summation order) would break such ties differently.
+    rough = np.linalg.norm(node_qs - q_new, axis=1)
+    cost0 = node_costs[parent_index] + np.linalg.norm(node_qs[parent_index] - q_new)
+    slack = 1e-9 * (1.0 + abs(cost0))
+    pre = np.nonzero((rough <= max_rewire_dist + slack) & (node_costs + rough < cost0 + slack))[0]
+    dist = np.full(len(node_costs), np.inf)
+    for k in pre:
+        dist[k] = np.linalg.norm(node_qs[k] - q_new)
     new_cost = node_costs + dist
     cand = np.nonzero((dist <= max_rewire_dist) & (new_cost < cost0) & (np.arange(len(dist)) != parent_index)
                       & ~np.all(node_qs == q_new, axis=1))[0]
