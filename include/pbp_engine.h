@@ -267,6 +267,15 @@ int pbp_collision_nullspace(pbp_engine *e, const float *q_dev, int64_t n, float 
 int pbp_knn(pbp_engine *e, const float *nodes_dev, int64_t n, int32_t k, double radius, int32_t predecessors_only,
             int32_t *idx_dev, float *dist_dev, void *stream);
 
+/* The same for every block_stride-th block of 16 consecutive query nodes, starting with block block_first:
+ * query block b = block_first + t * block_stride (t = 0, 1, ...) writes LOCAL rows [16 t, 16 t + 16) of idx_dev /
+ * dist_dev ([ceil((nblocks - block_first) / block_stride) * 16][k]).  The ranks of a multi-GPU roadmap build
+ * interleave the query blocks (rank r: block_first = r, block_stride = world) -- the work of a predecessor query
+ * grows with its index, interleaving balances it -- and all-gather the rows. */
+#define PBP_KNN_QUERY_BLOCK 16
+int pbp_knn_blocks(pbp_engine *e, const float *nodes_dev, int64_t n, int32_t k, double radius, int32_t predecessors_only,
+                   int64_t block_first, int64_t block_stride, int32_t *idx_dev, float *dist_dev, void *stream);
+
 /* One try of damped-least-squares differential IK for N targets (thread per target, FP64 end to
  * end -- unlike the collision entry points the states here are DOUBLES, because an iterate that
  * crosses a singularity amplifies input rounding by up to 1/damping^2).

@@ -1627,24 +1627,26 @@ extern "C" int pbp_ik_iterate(pbp_engine *e, int32_t frame_id, const double *tar
 // ------------------------------------------------------------------------------------------
 // k nearest neighbours (batched PRM construction)
 // ------------------------------------------------------------------------------------------
-extern "C" int pbp_knn(pbp_engine *e, const float *nodes_dev, int64_t n, int32_t k, double radius, int32_t predecessors_only,
-                       int32_t *idx_dev, float *dist_dev, void *stream) {
+extern "C" int pbp_knn_blocks(pbp_engine *e, const float *nodes_dev, int64_t n, int32_t k, double radius, int32_t predecessors_only,
+                              int64_t block_first, int64_t block_stride, int32_t *idx_dev, float *dist_dev, void *stream) {
     int rc = check_args(e, nodes_dev, n);
     if (rc) return rc;
     if (n > 0 && (!idx_dev || !dist_dev)) return fail(PBP_ERR_ARG, "NULL buffer");
     if (k < 1 || k > KNN_MAX_K) return fail(PBP_ERR_ARG, "k must be in [1, %d]", KNN_MAX_K);
     if (e->nq > KNN_MAX_NQ) return fail(PBP_ERR_CAPACITY, "nq > %d", KNN_MAX_NQ);
     if (!(radius >= 0.0)) return fail(PBP_ERR_ARG, "radius must be >= 0");
-    if (n == 0) return 0;
+    if (block_first < 0 || block_stride < 1) return fail(PBP_ERR_ARG, "bad query block range");
+    const int64_t nblocks = (n + KNN_QUERIES - 1) / KNN_QUERIES;
+    if (n == 0 || block_first >= nblocks) return 0;
     CallGuard guard(e, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = knn_smem_bytes(e->nq, k);
     const double r2 = std::isinf(radius) ? INFINITY : radius * radius;
-    const unsigned grid = grid_for(n, KNN_QUERIES);
+    const unsigned grid = (unsigned)((nblocks - block_first + block_stride - 1) / block_stride);
 #define KNN_LAUNCH(NQ)                                                                                                   \
     do {                                                                                                                 \
         CUDA_TRY(cudaFuncSetAttribute(k_knn<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
-        k_knn<NQ><<<grid, KNN_THREADS, smem, st>>>(nodes_dev, n, e->nq, k, r2, predecessors_only, idx_dev, dist_dev);     \
+        k_knn<NQ><<<grid, KNN_THREADS, smem, st>>>(nodes_dev, n, e->nq, k, r2, predecessors_only, block_first, block_stride, idx_dev, dist_dev); \
     } while (0)
     switch (e->nq) {
     case 2: KNN_LAUNCH(2); break;
@@ -1656,6 +1658,11 @@ extern "C" int pbp_knn(pbp_engine *e, const float *nodes_dev, int64_t n, int32_t
 #undef KNN_LAUNCH
     LAUNCH_CHECK("k_knn");
     return 0;
+}
+
+extern "C" int pbp_knn(pbp_engine *e, const float *nodes_dev, int64_t n, int32_t k, double radius, int32_t predecessors_only,
+                       int32_t *idx_dev, float *dist_dev, void *stream) {
+    return pbp_knn_blocks(e, nodes_dev, n, k, radius, predecessors_only, 0, 1, idx_dev, dist_dev, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -34,7 +34,7 @@ inline size_t knn_smem_bytes(int nq, int k) {
 template <int NQ>
 __global__ void __launch_bounds__(KNN_THREADS)
 k_knn(const float *__restrict__ nodes, int64_t n, int nq_dyn, int k, double radius2, int predecessors_only,
-      int32_t *__restrict__ idx_out, float *__restrict__ dist_out) {
+      int64_t block_first, int64_t block_stride, int32_t *__restrict__ idx_out, float *__restrict__ dist_out) {
     extern __shared__ __align__(16) unsigned char knn_smem[];
     const int nq = NQ > 0 ? NQ : nq_dyn;
     double *sd = reinterpret_cast<double *>(knn_smem);                                   // [k][KNN_THREADS]
@@ -42,8 +42,12 @@ k_knn(const float *__restrict__ nodes, int64_t n, int nq_dyn, int k, double radi
     float *tile = reinterpret_cast<float *>(knn_smem + (size_t)k * KNN_THREADS * 12);      // [KNN_TILE][nq]
     const int tid = threadIdx.x;
     const int sub = tid % KNN_SPLIT;                      // which slice of every tile this thread scans
-    const int64_t i0 = (int64_t)blockIdx.x * KNN_QUERIES;
+    // this block's KNN_QUERIES query nodes: query block (block_first + blockIdx.x * block_stride) of the node list --
+    // ranks of a multi-GPU job interleave the query blocks (the work of a predecessor query grows with its index);
+    // results land in the caller's LOCAL rows blockIdx.x * KNN_QUERIES ...
+    const int64_t i0 = (block_first + (int64_t)blockIdx.x * block_stride) * KNN_QUERIES;
     const int64_t i = i0 + tid / KNN_SPLIT;
+    const int64_t row = (int64_t)blockIdx.x * KNN_QUERIES + tid / KNN_SPLIT;
     const bool live = i < n;
     float qi[NQ > 0 ? NQ : 1];
     if (NQ > 0 && live) {
@@ -111,8 +115,8 @@ k_knn(const float *__restrict__ nodes, int64_t n, int nq_dyn, int k, double radi
             for (int t = 0; t < KNN_SPLIT; t++)
                 if (t == bt) head[t]++;
         }
-        idx_out[i * k + s] = bi;
-        dist_out[i * k + s] = bi >= 0 ? (float)sqrt(bd) : INFINITY;
+        idx_out[row * k + s] = bi;
+        dist_out[row * k + s] = bi >= 0 ? (float)sqrt(bd) : INFINITY;
     }
 }
 

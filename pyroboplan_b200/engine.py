@@ -44,6 +44,7 @@ EXPORTED_SYMBOLS = [
     "pbp_measure_fp32_peak",
     "pbp_ik_iterate",
     "pbp_knn",
+    "pbp_knn_blocks",
     "pbp_compute_distances",
     "pbp_collision_nullspace",
     "pbp_jit_broadphase_source",
@@ -176,6 +177,7 @@ def load_library():
     lib.pbp_measure_fp32_peak.argtypes = [i32, ctypes.POINTER(f64)]
     lib.pbp_ik_iterate.argtypes = [vp, i32, vp, vp, i64, ctypes.POINTER(_IkOptions), ctypes.c_uint64, vp, vp, vp, vp, vp, vp]
     lib.pbp_knn.argtypes = [vp, vp, i64, i32, f64, i32, vp, vp, vp]
+    lib.pbp_knn_blocks.argtypes = [vp, vp, i64, i32, f64, i32, i64, i64, vp, vp, vp]
     lib.pbp_compute_distances.argtypes = [vp, vp, i64, f32, vp, vp, vp, vp, vp]
     lib.pbp_collision_nullspace.argtypes = [vp, vp, i64, f32, f32, vp, vp]
     if lib.pbp_abi_version() != PBP_ABI_VERSION:
@@ -716,16 +718,26 @@ class CollisionEngine:
         return out.cpu().numpy() if host else out
 
     # ------------------------------------------------------------------ k nearest neighbours
-    def knn(self, nodes, k, radius=np.inf, predecessors_only=False):
-        """k nearest nodes of every node (CUDA tensor [N, nq]) -> (idx [N, k] int32, -1 padded; dist [N, k] float32)."""
+    KNN_QUERY_BLOCK = 16
+
+    def knn(self, nodes, k, radius=np.inf, predecessors_only=False, block_first=0, block_stride=1):
+        """k nearest nodes of every node (CUDA tensor [N, nq]) -> (idx [N, k] int32, -1 padded; dist [N, k] float32).
+
+        ``block_first`` / ``block_stride``: only every ``block_stride``-th block of 16 consecutive query nodes,
+        starting with block ``block_first`` (the interleaved share of one rank, see pbp_knn_blocks); the result
+        then has one row per query of those blocks, in that order (rows past N hold -1 / inf)."""
         torch = _torch()
         Nd = self._dev_q(nodes)
         n = Nd.shape[0]
-        idx = torch.empty((n, int(k)), dtype=torch.int32, device=self.torch_device)
-        dist = torch.empty((n, int(k)), dtype=torch.float32, device=self.torch_device)
+        nblocks = (n + self.KNN_QUERY_BLOCK - 1) // self.KNN_QUERY_BLOCK
+        mine = max(0, (nblocks - int(block_first) + int(block_stride) - 1) // int(block_stride))
+        rows = n if (block_first, block_stride) == (0, 1) else mine * self.KNN_QUERY_BLOCK
+        idx = torch.full((rows, int(k)), -1, dtype=torch.int32, device=self.torch_device)
+        dist = torch.full((rows, int(k)), float("inf"), dtype=torch.float32, device=self.torch_device)
         ptr = lambda t: ctypes.c_void_p(t.data_ptr())
-        _check(self.lib.pbp_knn(self._h, ptr(Nd), n, int(k), float(radius), int(bool(predecessors_only)), ptr(idx), ptr(dist),
-                                self._stream()))
+        if rows:
+            _check(self.lib.pbp_knn_blocks(self._h, ptr(Nd), n, int(k), float(radius), int(bool(predecessors_only)), int(block_first),
+                                           int(block_stride), ptr(idx), ptr(dist), self._stream()))
         return idx, dist
 
     # ------------------------------------------------------------------ sampling

@@ -9,17 +9,20 @@ edges whose straight segment is collision free (`has_collision_free_path(node.q,
 Every one of those steps is independent across nodes once the node set is fixed, so here they are
 batched: (1) free nodes from the device sampler, (2) k nearest predecessors by brute-force L2 on
 the GPU (`pbp_knn`, a hand-written tiled kernel with FP64 distance accumulation so the neighbour
-order equals the reference's), (3) ALL candidate edges validated in one `check_edges` call -- block-sharded across
-ranks, with one NCCL all-gather assembling the validity mask on every rank.
+order equals the reference's) -- across ranks every rank searches an interleaved share of the query blocks and one
+all-gather assembles the rows --, (3) ALL candidate edges validated in one `check_edges` call per rank, the edges cut
+where the prefix sum of their sample counts crosses multiples of total / world, one all-gather of the bit-packed
+validity mask.  (The sampler stays replicated: the same Philox stream on every rank, ~33 k draws, one small round --
+sharding it would replace 0.1 ms of compute by an all-gather of the same length.)
 """
 
 import numpy as np
 
-from ..distributed import validate_edges_sharded
+from ..distributed import knn_interleaved, validate_edges_balanced
 from ..engine import get_engine
 
 
-def nearest_predecessors(nodes, k, radius=np.inf, engine=None, predecessors_only=True):
+def nearest_predecessors(nodes, k, radius=np.inf, engine=None, predecessors_only=True, group=None):
     """For node i: its k nearest nodes j < i with distance <= radius, sorted by distance.
 
     nodes: CUDA float32 tensor [N, nq].  Returns (idx [N, k] int64 with -1 padding, dist [N, k]).
@@ -34,7 +37,9 @@ def nearest_predecessors(nodes, k, radius=np.inf, engine=None, predecessors_only
     for k0 in range(0, k, 64):   # the kernel keeps at most 64 neighbours per pass; more is not a PRM use case
         if k0 > 0:
             raise ValueError("k > 64 is not supported")
-        i32, d = engine.knn(nodes, min(k, 64), radius, predecessors_only=predecessors_only)
+        # under torch.distributed every rank searches an interleaved share of the query blocks; one all-gather
+        i32, d = knn_interleaved(lambda first, stride: engine.knn(nodes, min(k, 64), radius, predecessors_only, first, stride),
+                                 nodes.shape[0], min(k, 64), engine.KNN_QUERY_BLOCK, nodes.device, group)
         idx[:, : i32.shape[1]] = i32.to(torch.int64)
         dist[:, : d.shape[1]] = d
     return idx, dist
@@ -63,7 +68,7 @@ def construct_roadmap_batched(model, collision_model, n_nodes, k=10, radius=np.i
     else:
         nodes = torch.as_tensor(np.asarray(nodes, dtype=np.float32) if not isinstance(nodes, torch.Tensor) else nodes,
                                 device=eng.torch_device).to(torch.float32).contiguous()
-    idx, dist = nearest_predecessors(nodes, k, radius, engine=eng)
+    idx, dist = nearest_predecessors(nodes, k, radius, engine=eng, group=group)
     node_ids = torch.arange(nodes.shape[0], device=nodes.device)[:, None].expand_as(idx)
     keep = idx >= 0
     cand = torch.stack([idx[keep], node_ids[keep]], dim=1)  # row-major: node by node, nearest first
@@ -73,5 +78,5 @@ def construct_roadmap_batched(model, collision_model, n_nodes, k=10, radius=np.i
     if len(collision_model.collisionPairs) == 0:
         valid = torch.ones(cand.shape[0], dtype=torch.bool, device=nodes.device)
     else:
-        valid = validate_edges_sharded(eng.check_edges, q1, q2, max_step_size, distance_padding, group=group)
+        valid = validate_edges_balanced(eng.check_edges, q1, q2, max_step_size, distance_padding, lengths=lengths, group=group)
     return {"nodes": nodes, "candidates": cand, "valid": valid, "edges": cand[valid], "lengths": lengths}
