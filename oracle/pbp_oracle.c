@@ -473,8 +473,8 @@ static double pair_distance_semantics(const oracle_model *m, const double *oMg, 
     return d;
 }
 
-/* A mesh surface lies at most this far below its hull in any model the oracle is used on (Panda:
- * 0.39 mm, pyroboplan_b200.engine.mesh_dent_depth; asserted in tests/test_oracle_golden.py). */
+/* How far a near-convex mesh surface lies below its hull (Panda: 0.39 mm, pyroboplan_b200.engine.mesh_dent_depth):
+ * only the size of the FIRST, cheap search window of the exact triangle distance -- not an assumption. */
 #define ORACLE_MAX_DENT 1e-3
 
 int oracle_check_state(const oracle_model *m, const double *q, double padding, int want_all, int use_cull,
@@ -522,7 +522,8 @@ int oracle_check_state(const oracle_model *m, const double *q, double padding, i
     for (int k = 0; k < m->npairs; k++) {
         int ga = m->pairs[2 * k], gb = m->pairs[2 * k + 1];
         if (use_cull && !want_all && sphere_cull(m, oMg_scratch, ga, gb, padding)) { cnt->culled++; continue; }
-        if (use_cull && want_all && md < INFINITY && sphere_cull(m, oMg_scratch, ga, gb, md + (refine ? 2.0 * ORACLE_MAX_DENT : 0.0))) { cnt->culled++; continue; }
+        /* (with surfaces the running minimum is a minimum of HULL distances, a lower bound only: no cull on it) */
+        if (use_cull && want_all && !refine && md < INFINITY && sphere_cull(m, oMg_scratch, ga, gb, md)) { cnt->culled++; continue; }
         int is_exact = 1;
         double d = pair_distance_semantics(m, oMg_scratch, ga, gb, padding, min_dist != NULL, &is_exact, cnt);
         if (refine) { dk[k] = d; exact_k[k] = (unsigned char)is_exact; }
@@ -539,8 +540,16 @@ int oracle_check_state(const oracle_model *m, const double *q, double padding, i
             for (int k = 0; k < m->npairs; k++) if (kb < 0 || dk[k] < dk[kb]) kb = k;
             if (kb < 0 || exact_k[kb] || !isfinite(dk[kb])) { if (kb >= 0) md = dk[kb]; break; }
             const int ga = m->pairs[2 * kb], gb = m->pairs[2 * kb + 1];
-            dk[kb] = soup_pair_distance_from(m, oMg_scratch, ga, gb, m->tris + 9 * (int64_t)m->tri_off[ga], m->tri_cnt[ga],
-                                             m->tris + 9 * (int64_t)m->tri_off[gb], m->tri_cnt[gb], -1.0, 0, dk[kb] + 2.0 * ORACLE_MAX_DENT);
+            /* cheap first: within a couple of dent depths of the hull distance (always enough for near-convex
+             * meshes, the Panda's); a non-convex mesh (UR upper arm, forearm: decimetres below the hull) falls
+             * through to the unbounded search */
+            const double first_try = dk[kb] + 2.0 * ORACLE_MAX_DENT;
+            double ds = soup_pair_distance_from(m, oMg_scratch, ga, gb, m->tris + 9 * (int64_t)m->tri_off[ga], m->tri_cnt[ga],
+                                                m->tris + 9 * (int64_t)m->tri_off[gb], m->tri_cnt[gb], -1.0, 0, first_try);
+            if (!(ds < first_try))
+                ds = soup_pair_distance_from(m, oMg_scratch, ga, gb, m->tris + 9 * (int64_t)m->tri_off[ga], m->tri_cnt[ga],
+                                             m->tris + 9 * (int64_t)m->tri_off[gb], m->tri_cnt[gb], -1.0, 0, INFINITY);
+            dk[kb] = ds;
             exact_k[kb] = 1;
         }
         free(dk); free(exact_k);

@@ -72,6 +72,43 @@ def _is_closed(tris):
     return bool(len(cnt)) and bool((cnt == 2).all())
 
 
+def _winding_number(p, verts, tris):
+    """Generalised winding number of the closed triangle mesh around p (Van Oosterom - Strackee solid angles):
+    +-1 inside a consistently oriented closed mesh, 0 outside."""
+    a, b, c = verts[tris[:, 0]] - p, verts[tris[:, 1]] - p, verts[tris[:, 2]] - p
+    la, lb, lc = np.linalg.norm(a, axis=1), np.linalg.norm(b, axis=1), np.linalg.norm(c, axis=1)
+    num = np.einsum("ij,ij->i", a, np.cross(b, c))
+    den = la * lb * lc + np.einsum("ij,ij->i", a, b) * lc + np.einsum("ij,ij->i", b, c) * la + np.einsum("ij,ij->i", c, a) * lb
+    return float(np.arctan2(num, den).sum() / (2.0 * np.pi))
+
+
+def _interior_point(verts, tris, first_guess):
+    """A point strictly inside the closed mesh, or None: the guess (the hull's Chebyshev centre), else the
+    candidate with the most clearance among points pushed inwards from the triangle centroids.  A convex cell
+    of the triangle planes around ANY interior point lies inside the solid (no triangle crosses the open cell,
+    and the cell is connected), which is all the inner core needs; for a non-convex mesh (UR upper arm, forearm)
+    the hull's centre may lie outside the solid."""
+    if abs(_winding_number(first_guess, verts, tris)) > 0.5:
+        return first_guess
+    t = verts[tris]
+    cen = t.mean(axis=1)
+    n = np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0])
+    ln = np.linalg.norm(n, axis=1)
+    ok = ln > 0
+    n = n[ok] / ln[ok, None]
+    cen = cen[ok]
+    size = float(np.linalg.norm(verts.max(axis=0) - verts.min(axis=0)))
+    best, best_clear = None, 0.0
+    for depth in (0.02, 0.05, 0.1):
+        for sign in (-1.0, 1.0):      # the orientation convention of the file is not assumed
+            for p in (cen + sign * depth * size * n)[:: max(1, len(cen) // 64)]:
+                if abs(_winding_number(p, verts, tris)) > 0.5:
+                    clear = float(_point_triangles_dist(p[None, :], t).min())
+                    if clear > best_clear:
+                        best, best_clear = p, clear
+    return best
+
+
 def _feasible_point_near(v, planes, centre, iters=60):
     """A point of {x : n.x <= w} close to v: cyclic projection on the most violated plane, then a pull
     towards the (strictly interior) centre.  |v - result| bounds the distance of v to the set."""
@@ -191,11 +228,14 @@ def surface_tables(shape):
         tol_out = max(tol_out, float(_point_triangles_dist(hp[s0:s0 + 256], T).max()))
     out["surface_tol"] = 1.5 * max(tol_in, tol_out) + 1e-7     # samples, not maxima: keep a margin
 
-    # ---- inner core: K = hull /\ inner half-spaces of every mesh triangle
-    tri_planes, _ = _unit_planes_of_triangles(V, tris, centre)
+    # ---- inner core: K = hull /\ the half-spaces of every mesh triangle that hold an interior point of the solid
     closed = _is_closed(tris)
+    inside = _interior_point(V, tris, centre) if closed else None
+    if inside is not None:
+        centre = inside
+    tri_planes, _ = _unit_planes_of_triangles(V, tris, centre)
     slack_c = (tri_planes[:, :3] @ centre - tri_planes[:, 3]).max() if len(tri_planes) else 0.0
-    if closed and slack_c < -1e-6 and r_in > 1e-6:
+    if closed and inside is not None and slack_c < -1e-6 and r_in > 1e-6:
         # the planes of mesh triangles that lie ON a hull face add nothing
         onhull = np.zeros(len(tri_planes), dtype=bool)
         for k, pl in enumerate(tri_planes):

@@ -219,3 +219,23 @@ def test_surface_tables_of_the_panda():
     assert flatten_model(m2, c2)[1]["nplanes"] == 0
     with pytest.raises(ValueError):
         flatten_model(model, cmodel, mesh_semantics="soup")
+
+
+def test_ur_models_mirror_the_reference_modules():
+    """reference models/ur5.py:9-47, ur10.py:9-47: 12 collision geometries, all pairs minus the SRDF's."""
+    from pyroboplan_b200.engine import flatten_model
+    from pyroboplan_b200.models import ur5, ur10
+
+    for load, add in ((ur5.load_ur5_on_base_models, ur5.add_ur5_on_base_self_collisions), (ur10.load_ur10_on_base_models, ur10.add_ur10_on_base_self_collisions)):
+        m, c, _ = load()
+        assert m.nq == 9 and len(c.collisionPairs) == 0
+        add(m, c)
+        names = [g.name for g in c.geometryObjects]
+        assert names[:8] == ["mobile_base_0", "base_link_0", "shoulder_link_0", "upper_arm_link_0", "forearm_link_0", "wrist_1_link_0", "wrist_2_link_0", "wrist_3_link_0"]
+        assert len(c.collisionPairs) == 37
+        pairs = {(names[p.first], names[p.second]) for p in c.collisionPairs}
+        assert ("upper_arm_link_0", "forearm_link_0") not in pairs and ("base_link_0", "forearm_link_0") in pairs
+        a, sizes = flatten_model(m, c)
+        assert sizes["ntris"] > 5000 and (a["geom_tri_cnt"][1:8] > 300).all()
+        # non-convex meshes: the inner cell is far inside the hull (or missing) -- the triangles decide
+        assert (a["geom_core_eps"][1:8] > 0.05).sum() + (a["geom_core_cnt"][1:8] == 0).sum() >= 4

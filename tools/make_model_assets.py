@@ -50,3 +50,5 @@ if __name__ == "__main__":
     emit("panda_spheres", "panda_description/urdf/panda_spheres.urdf", "panda_description/srdf/panda.srdf")
     emit("two_dof", "two_dof_description/two_dof.urdf")
     emit("marble", "marble_description/marble.urdf")
+    emit("ur5_on_base", "ur_description/urdf/ur5_on_base.urdf", "ur_description/srdf/ur5_on_base.srdf")
+    emit("ur10_on_base", "ur_description/urdf/ur10_on_base.urdf", "ur_description/srdf/ur10_on_base.srdf")
