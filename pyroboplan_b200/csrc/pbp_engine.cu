@@ -5,6 +5,9 @@
 #include <cub/device/device_select.cuh>
 
 #include <algorithm>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -1218,6 +1221,23 @@ int pbp_check_states_host(pbp_engine *e, const float *q_host, int64_t n, float p
     return 0;
 }
 
+// dst[i] = (float)src[i].  The destination is a pinned staging buffer that only the DMA engine reads next:
+// streaming stores keep it out of the caches and spare the read-for-ownership (a quarter of the memory traffic
+// of this loop, which is bound by the host's memory bandwidth, not by the conversion).
+static void narrow_f64_to_f32(float *dst, const double *src, int64_t m) {
+    int64_t i = 0;
+#if defined(__SSE2__)
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        for (; i + 4 <= m; i += 4) {
+            const __m128 lo = _mm_cvtpd_ps(_mm_loadu_pd(src + i)), hi = _mm_cvtpd_ps(_mm_loadu_pd(src + i + 2));
+            _mm_stream_ps(dst + i, _mm_movelh_ps(lo, hi));
+        }
+        _mm_sfence();
+    }
+#endif
+    for (; i < m; i++) dst[i] = (float)src[i];
+}
+
 // float64 host states (what the reference's callers hold: numpy float64, pageable).  The batch is cut into
 // slices; a few host threads convert slice after slice into rotating pinned float32 buffers while earlier
 // slices are already crossing PCIe and being checked, so conversion, copies and kernels overlap.
@@ -1238,39 +1258,49 @@ int pbp_check_states_host_f64(pbp_engine *e, const double *q_host, int64_t n, fl
     if (!is_pinned_host(hit_host)) { if ((rc = e->h_io_hit.ensure((size_t)n))) return rc; hh = (uint8_t *)e->h_io_hit.p; }
     if (min_dist_host && !is_pinned_host(min_dist_host)) { if ((rc = e->h_io_f32.ensure((size_t)n * 4))) return rc; hd = (float *)e->h_io_f32.p; }
     if (first_pair_host && !is_pinned_host(first_pair_host)) { if ((rc = e->h_io_i32.ensure((size_t)n * 4))) return rc; hp = (int32_t *)e->h_io_i32.p; }
-    const int64_t slice = std::min<int64_t>(e->host_slice, 1 << 17);   // conversion granularity: 128 Ki states = 9.4 MB of doubles
+    // Compute slices as in the float32 path; every slice is narrowed in SUB-CHUNKS claimed by the host threads
+    // (one thread narrows ~5 GB/s of doubles: a whole slice per thread would leave the pipeline waiting for the
+    // slowest of a few threads), into a ring of NBUF pinned slice buffers.
+    const int64_t slice = e->host_slice;
     const int64_t n_slices = (n + slice - 1) / slice;
     constexpr int NBUF = 4;
+    constexpr int64_t SUB = 1 << 15;                       // states per conversion chunk (2.4 MB of doubles)
+    const int64_t subs_per_slice = (slice + SUB - 1) / SUB;
     if ((rc = e->h_stage.ensure((size_t)NBUF * slice * nq * 4))) return rc;
     while ((int64_t)e->io_events.size() < n_slices) {
         cudaEvent_t ev;
         CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         e->io_events.push_back(ev);
     }
-    int nthreads = (int)std::min<int64_t>(std::min<int64_t>(n_slices, 8), std::max(1u, std::thread::hardware_concurrency()));
+    const int64_t n_subs = n_slices * subs_per_slice;
+    int nthreads = (int)std::min<int64_t>(std::min<int64_t>(n_subs, 12), std::max(1u, std::thread::hardware_concurrency()));
     if (const char *ht = getenv("PBP_HOST_THREADS")) nthreads = std::max(1, std::min(atoi(ht), 64));
-    std::vector<std::atomic<int>> ready((size_t)n_slices), issued((size_t)n_slices);
+    std::vector<std::atomic<int>> ready((size_t)n_slices), issued((size_t)n_slices);   // ready: sub-chunks of the slice narrowed so far
     for (int64_t k = 0; k < n_slices; k++) { ready[(size_t)k].store(0); issued[(size_t)k].store(0); }
     std::atomic<int64_t> next{0};
     std::atomic<int> abort_flag{0};
     float *stage = (float *)e->h_stage.p;
     const int device = e->device;
     auto worker = [&]() {
-        cudaSetDevice(device);
+        bool device_set = false;   // (binding a fresh thread to the CUDA context costs a fraction of a millisecond:
+                                   //  only threads that have to wait for a copy pay it)
         for (;;) {
-            const int64_t k = next.fetch_add(1);
-            if (k >= n_slices) return;
+            const int64_t j = next.fetch_add(1);
+            if (j >= n_subs) return;
+            const int64_t k = j / subs_per_slice, sub = j - k * subs_per_slice;
             if (k >= NBUF) {   // the buffer's previous slice must have left the host
                 while (!issued[(size_t)(k - NBUF)].load(std::memory_order_acquire))
                     if (abort_flag.load()) return; else std::this_thread::yield();
+                if (!device_set) { cudaSetDevice(device); device_set = true; }
                 cudaEventSynchronize(e->io_events[(size_t)(k - NBUF)]);
             }
             const int64_t off = k * slice, cnt = std::min(slice, n - off);
-            const double *src = q_host + off * nq;
-            float *dst = stage + (k % NBUF) * slice * nq;
-            const int64_t m = cnt * nq;
-            for (int64_t i = 0; i < m; i++) dst[i] = (float)src[i];
-            ready[(size_t)k].store(1, std::memory_order_release);
+            const int64_t s0 = std::min(sub * SUB, cnt), s1 = std::min(s0 + SUB, cnt);
+            const double *src = q_host + (off + s0) * nq;
+            float *dst = stage + (k % NBUF) * slice * nq + s0 * nq;
+            const int64_t m = (s1 - s0) * nq;
+            narrow_f64_to_f32(dst, src, m);
+            ready[(size_t)k].fetch_add(1, std::memory_order_release);
         }
     };
     std::vector<std::thread> pool;
@@ -1283,7 +1313,7 @@ int pbp_check_states_host_f64(pbp_engine *e, const double *q_host, int64_t n, fl
     e->ws_split = n_slices > 1 && slice <= e->chunk / 2 && !(min_dist_host && first_pair_host);
     auto step = [&](int64_t k) -> int {
         const int64_t off = k * slice, cnt = std::min(slice, n - off);
-        while (!ready[(size_t)k].load(std::memory_order_acquire)) std::this_thread::yield();
+        while (ready[(size_t)k].load(std::memory_order_acquire) < subs_per_slice) std::this_thread::yield();
         CUDA_TRY(cudaMemcpyAsync(dq + off * nq, stage + (k % NBUF) * slice * nq, (size_t)cnt * nq * 4, cudaMemcpyHostToDevice, e->s_copy));
         CUDA_TRY(cudaEventRecord(e->io_events[(size_t)k], e->s_copy));
         issued[(size_t)k].store(1, std::memory_order_release);
