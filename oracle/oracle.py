@@ -111,6 +111,8 @@ def _load():
                                                  ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                  P(ctypes.c_int64)]
         lib.oracle_soup_check_states.restype = None
+        lib.oracle_tri_tri_distance.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        lib.oracle_tri_tri_distance.restype = ctypes.c_double
         _lib = lib
     return _lib
 
@@ -336,3 +338,10 @@ def discretize_joint_space_path(q_path, max_angle_distance):
         lib.oracle_discretize_segment(_ptr(a), _ptr(b), len(a), n, _ptr(buf))
         out.extend(list(buf))
     return out
+
+
+def tri_tri_distance(a, b):
+    """Exact float64 distance between two triangles ([3, 3] each; 0 when they intersect)."""
+    a = np.ascontiguousarray(a, dtype=np.float64).reshape(9)
+    b = np.ascontiguousarray(b, dtype=np.float64).reshape(9)
+    return float(_load().oracle_tri_tri_distance(_ptr(a), _ptr(b)))

@@ -1070,6 +1070,9 @@ static double tri_tri_dist2(const double *a, const double *b) {
     return best;
 }
 
+/* exported for the tests: distance between two triangles given as 9 doubles each */
+double oracle_tri_tri_distance(const double *a, const double *b) { return sqrt(tri_tri_dist2(a, b)); }
+
 static void tri_to_world(const double *T, const double *tri, double *out, double *lo, double *hi) {
     for (int k = 0; k < 3; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; }
     for (int v = 0; v < 3; v++)

@@ -268,6 +268,86 @@ __device__ __forceinline__ int enclosure_roles(const float4 *planes, int fl, con
 }
 
 // ------------------------------------------------------------------------------------------
+// Distance between two triangles, closed form
+// ------------------------------------------------------------------------------------------
+// The minimum distance of two triangles is attained between an edge of one and an edge of the other, or between
+// a vertex of one and the face of the other -- unless they intersect, which is the case exactly when an edge of
+// one passes through the face of the other.  Straight-line FP32 arithmetic (about 900 flops), so the 32 lanes of
+// a warp stay converged over their 32 triangle pairs; a converged GJK run on the same pair is ~20 dependent,
+// divergent iterations.
+
+// squared distance between segments [p1, q1] and [p2, q2] (Ericson, Real-Time Collision Detection 5.1.9)
+__device__ __forceinline__ float segseg_dist2(float3 p1, float3 q1, float3 p2, float3 q2) {
+    const float3 d1 = sub3(q1, p1), d2 = sub3(q2, p2), r = sub3(p1, p2);
+    const float a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r);
+    float sp = 0.f, tp = 0.f;
+    if (a > 0.f && e > 0.f) {
+        const float b = dot3(d1, d2), c = dot3(d1, r);
+        const float den = a * e - b * b;
+        sp = den > 1e-12f * a * e ? fminf(fmaxf((b * f - c * e) / den, 0.f), 1.f) : 0.f;
+        tp = (b * sp + f) / e;
+        if (tp < 0.f) { tp = 0.f; sp = fminf(fmaxf(-c / a, 0.f), 1.f); }
+        else if (tp > 1.f) { tp = 1.f; sp = fminf(fmaxf((b - c) / a, 0.f), 1.f); }
+    } else if (a > 0.f) {
+        sp = fminf(fmaxf(-dot3(d1, r) / a, 0.f), 1.f);
+    } else if (e > 0.f) {
+        tp = fminf(fmaxf(f / e, 0.f), 1.f);
+    }
+    const float3 w = sub3(madd3(p1, d1, sp), madd3(p2, d2, tp));
+    return dot3(w, w);
+}
+
+// squared distance between the point p and the triangle (a, b, c), counted only when the closest point lies in the
+// triangle's INTERIOR or on it along the normal (edges and vertices are covered by the segment tests): FLT_MAX else
+__device__ __forceinline__ float point_face_dist2(float3 p, float3 a, float3 b, float3 c) {
+    const float3 ab = sub3(b, a), ac = sub3(c, a), ap = sub3(p, a);
+    const float3 n = cross3(ab, ac);
+    const float nn = dot3(n, n);
+    if (!(nn > 0.f)) return FLT_MAX;
+    // barycentric coordinates of the projection
+    const float v = dot3(cross3(ap, ac), n), w = dot3(cross3(ab, ap), n);
+    if (v < 0.f || w < 0.f || v + w > nn) return FLT_MAX;
+    const float h = dot3(ap, n);
+    return h * h / nn;
+}
+
+// does the segment [p, q] pass through the triangle (a, b, c)?  (p and q strictly on different sides, or touching)
+__device__ __forceinline__ bool segment_through_face(float3 p, float3 q, float3 a, float3 b, float3 c) {
+    const float3 ab = sub3(b, a), ac = sub3(c, a);
+    const float3 n = cross3(ab, ac);
+    const float dp = dot3(sub3(p, a), n), dq = dot3(sub3(q, a), n);
+    if ((dp > 0.f && dq > 0.f) || (dp < 0.f && dq < 0.f) || dp == dq) return false;
+    const float t = dp / (dp - dq);
+    const float3 x = madd3(p, sub3(q, p), t);
+    const float3 ax = sub3(x, a);
+    const float nn = dot3(n, n);
+    const float v = dot3(cross3(ax, ac), n), w = dot3(cross3(ab, ax), n);
+    return v >= 0.f && w >= 0.f && v + w <= nn;
+}
+
+__device__ __noinline__ float tri_tri_distance(const float3 *A, const float3 *B) {
+    float d2 = FLT_MAX;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float3 a0 = A[i], a1 = A[(i + 1) % 3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) d2 = fminf(d2, segseg_dist2(a0, a1, B[j], B[(j + 1) % 3]));
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        d2 = fminf(d2, point_face_dist2(A[i], B[0], B[1], B[2]));
+        d2 = fminf(d2, point_face_dist2(B[i], A[0], A[1], A[2]));
+    }
+    bool cut = false;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        cut = cut || segment_through_face(A[i], A[(i + 1) % 3], B[0], B[1], B[2]);
+        cut = cut || segment_through_face(B[i], B[(i + 1) % 3], A[0], A[1], A[2]);
+    }
+    return cut ? 0.f : sqrtf(d2);
+}
+
+// ------------------------------------------------------------------------------------------
 // Triangle stage (one warp per item)
 // ------------------------------------------------------------------------------------------
 constexpr int TRI_LIST_CAP = 384;   // triangles of one geometry the warp's lists hold per pass
@@ -380,9 +460,27 @@ __device__ __noinline__ float triangle_stage(const SurfTables &tab, const DevGeo
                         v0b = se3_act(T, (vb[0].x + vb[1].x + vb[2].x) * (1.f / 3.f), (vb[0].y + vb[1].y + vb[2].y) * (1.f / 3.f),
                                       (vb[0].z + vb[1].z + vb[2].z) * (1.f / 3.f));
                     }
-                    ConvOut o;
-                    gjk_converge(SA, SB, T, sub3(v0a, v0b), bound, o);
-                    if (!o.far && o.dist < best) best = o.dist;
+                    if (nta > 0 && ntb > 0) {
+                        const float3 ta[3] = {make_float3(va[0].x, va[0].y, va[0].z), make_float3(va[1].x, va[1].y, va[1].z), make_float3(va[2].x, va[2].y, va[2].z)};
+                        const float3 tb[3] = {se3_act(T, vb[0].x, vb[0].y, vb[0].z), se3_act(T, vb[1].x, vb[1].y, vb[1].z), se3_act(T, vb[2].x, vb[2].y, vb[2].z)};
+                        // boxes of the two triangles first: a non-convex mesh (UR upper arm: 1176 triangles) leaves
+                        // thousands of pairs per item, nearly all of them far apart
+                        const float gx = fmaxf(fmaxf(fminf(fminf(ta[0].x, ta[1].x), ta[2].x) - fmaxf(fmaxf(tb[0].x, tb[1].x), tb[2].x),
+                                                     fminf(fminf(tb[0].x, tb[1].x), tb[2].x) - fmaxf(fmaxf(ta[0].x, ta[1].x), ta[2].x)), 0.f);
+                        const float gy = fmaxf(fmaxf(fminf(fminf(ta[0].y, ta[1].y), ta[2].y) - fmaxf(fmaxf(tb[0].y, tb[1].y), tb[2].y),
+                                                     fminf(fminf(tb[0].y, tb[1].y), tb[2].y) - fmaxf(fmaxf(ta[0].y, ta[1].y), ta[2].y)), 0.f);
+                        const float gz = fmaxf(fmaxf(fminf(fminf(ta[0].z, ta[1].z), ta[2].z) - fmaxf(fmaxf(tb[0].z, tb[1].z), tb[2].z),
+                                                     fminf(fminf(tb[0].z, tb[1].z), tb[2].z) - fmaxf(fmaxf(ta[0].z, ta[1].z), ta[2].z)), 0.f);
+                        const float lim = fminf(bound, best) + 2e-6f;
+                        if (fmaf(gx, gx, fmaf(gy, gy, gz * gz)) <= lim * lim) {
+                            const float d = tri_tri_distance(ta, tb);
+                            if (d <= bound && d < best) best = d;
+                        }
+                    } else {
+                        ConvOut o;
+                        gjk_converge(SA, SB, T, sub3(v0a, v0b), bound, o);
+                        if (!o.far && o.dist < best) best = o.dist;
+                    }
                 }
                 // tighten the bound with what the warp has found so far
                 float wb = best;

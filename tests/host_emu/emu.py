@@ -42,6 +42,8 @@ def load():
         _lib.emu_supmap_check.restype = None
         _lib.emu_surface_items.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int64, ctypes.c_float, ctypes.c_int, vp, vp, vp]
         _lib.emu_last_error.restype = ctypes.c_char_p
+        _lib.emu_tri_tri.argtypes = [vp, vp, ctypes.c_int64, vp]
+        _lib.emu_tri_tri.restype = None
     return _lib
 
 
@@ -142,3 +144,13 @@ def surface_items(model, collision_model, pair, T, padding=0.0, mode=0):
     if rc:
         raise RuntimeError(lib.emu_last_error().decode())
     return hit, dist, path
+
+
+def tri_tri(A, B):
+    """The triangle stage's closed-form triangle - triangle distance (FP32), A / B: [n, 3, 3]."""
+    lib = load()
+    A = np.ascontiguousarray(A, dtype=np.float32).reshape(-1, 9)
+    B = np.ascontiguousarray(B, dtype=np.float32).reshape(-1, 9)
+    out = np.zeros(len(A), dtype=np.float32)
+    lib.emu_tri_tri(ctypes.c_void_p(A.ctypes.data), ctypes.c_void_p(B.ctypes.data), len(A), ctypes.c_void_p(out.ctypes.data))
+    return out

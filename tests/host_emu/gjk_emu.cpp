@@ -134,6 +134,18 @@ extern "C" {
 
 const char *emu_last_error() { return g_emu_error.c_str(); }
 
+// the triangle stage's closed-form distance on n triangle pairs (A, B: [n][9] float32)
+void emu_tri_tri(const float *A, const float *B, int64_t n, float *out) {
+    for (int64_t i = 0; i < n; i++) {
+        float3 a[3], b[3];
+        for (int k = 0; k < 3; k++) {
+            a[k] = make_float3(A[9 * i + 3 * k], A[9 * i + 3 * k + 1], A[9 * i + 3 * k + 2]);
+            b[k] = make_float3(B[9 * i + 3 * k], B[9 * i + 3 * k + 1], B[9 * i + 3 * k + 2]);
+        }
+        out[i] = pbp::tri_tri_distance(a, b);
+    }
+}
+
 // What the engine answers for n placements T [n][12] (b in a's frame) of the caller's pair `pair`:
 // the narrowphase's GJK on the cores (boolean) / hulls (distance), then the refine kernel's lane and
 // warp decisions.  mode 0: out_hit[i] = verdict at `padding`; mode 2: out_dist[i] = surface distance

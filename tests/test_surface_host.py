@@ -73,3 +73,42 @@ def test_pair_distances_match_the_triangle_oracle(near_items):
         paths.update(int(x) for x in path)
     assert worst < 1e-5, worst
     assert paths[3] > 20 and paths[2] > 5      # triangle stages and enclosures (distance of the enclosed shape to the surface)
+
+
+def test_closed_form_triangle_distance_against_the_oracle():
+    """The triangle stage's FP32 closed form (edge-edge, vertex-face, edge-through-face; pbp_surface.cuh) on the host
+    build against the oracle's float64 routine: random pairs at the Panda's scale, near-parallel and coplanar
+    pairs, pairs sharing an edge direction, intersecting pairs, slivers."""
+    from oracle.oracle import tri_tri_distance
+
+    rng = np.random.default_rng(11)
+    A, B = [], []
+    for i in range(6000):
+        a = rng.uniform(-0.15, 0.15, size=(3, 3))
+        kind = i % 6
+        if kind == 0:      # anywhere
+            b = rng.uniform(-0.15, 0.15, size=(3, 3)) + rng.uniform(-0.2, 0.2, size=3)
+        elif kind == 1:    # nearly parallel, close
+            n = np.cross(a[1] - a[0], a[2] - a[0]); n /= np.linalg.norm(n)
+            b = a + rng.uniform(-0.03, 0.03, size=(3, 3)) + n * rng.uniform(1e-4, 5e-3) + rng.normal(scale=1e-4, size=(3, 3))
+        elif kind == 2:    # coplanar, side by side
+            u, v = a[1] - a[0], a[2] - a[0]
+            b = a[0] + np.outer(rng.uniform(1.0, 2.0, size=3), u) + np.outer(rng.uniform(-1.0, 2.0, size=3), v)
+        elif kind == 3:    # intersecting: b's first edge runs through a's interior
+            c = a.mean(axis=0)
+            n = np.cross(a[1] - a[0], a[2] - a[0]); n /= np.linalg.norm(n)
+            b = np.array([c + 0.05 * n + rng.normal(scale=0.005, size=3), c - 0.05 * n + rng.normal(scale=0.005, size=3), c + rng.uniform(-0.2, 0.2, size=3)])
+        elif kind == 4:    # sliver against a regular triangle
+            b = np.array([a[0], a[0] + (a[1] - a[0]) * 1.0, a[0] + (a[1] - a[0]) * 0.5 + rng.normal(scale=1e-5, size=3)]) + rng.uniform(-0.05, 0.05, size=3)
+        else:              # vertex of b just above a's face
+            w = rng.dirichlet([1, 1, 1])
+            n = np.cross(a[1] - a[0], a[2] - a[0]); n /= np.linalg.norm(n)
+            p = w @ a + n * rng.uniform(1e-5, 2e-3)
+            b = np.array([p, p + rng.uniform(0.02, 0.1) * n + rng.normal(scale=0.05, size=3), p + rng.uniform(0.02, 0.1) * n + rng.normal(scale=0.05, size=3)])
+        A.append(a.astype(np.float32)), B.append(b.astype(np.float32))
+    A, B = np.array(A), np.array(B)
+    got = emu.tri_tri(A, B)
+    ref = np.array([tri_tri_distance(a.astype(np.float64), b.astype(np.float64)) for a, b in zip(A, B)])
+    err = np.abs(got - ref)
+    assert err.max() < 2e-6, (err.max(), int(err.argmax()), got[err.argmax()], ref[err.argmax()])
+    assert (ref == 0).sum() > 500 and ((got == 0) == (ref == 0))[ref > 1e-5].all()
