@@ -39,27 +39,30 @@ N_BATCHES = 4               # distinct input batches rotated between steps (4 x 
 F_BP_FLOP_PER_CONFIG = 1.5e3 + 74 * 30.0          # k_broadphase: FK + 74 proxy tests
 F_NP_FLOP_PER_CONFIG = 6.0 * 1598 + 150.0 * 7.57  # k_narrowphase: support scans + simplex updates
 F_ALG_FLOP_PER_CONFIG = F_BP_FLOP_PER_CONFIG + F_NP_FLOP_PER_CONFIG  # = 14.4 kflop
-# The GJK work is split over two kernels: k_item_setup runs the first iteration of every item
-# (about 45 % of the iterations the device runs in total), k_narrowphase the rest; the item
+# The GJK work is split over two kernels: k_item_setup settles the items that end after one iteration
+# or by the inner-ball certificate (about 45 % of the oracle's iterations), k_narrowphase the rest (the
+# split is the round-1 measurement, kept so the fractions stay comparable across rounds); the item
 # setup's FK recomputation is redundant work, not algorithmic flops.
 F_KERNEL = {"k_broadphase": F_BP_FLOP_PER_CONFIG, "k_item_setup": 0.45 * F_NP_FLOP_PER_CONFIG, "k_narrowphase": 0.55 * F_NP_FLOP_PER_CONFIG}
 HBM_BYTES_PER_CONFIG = 9 * 4 + 1   # 9 float32 in, 1 verdict byte out
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) and pipe utilisation of
-# the four kernels of a 1 Mi-state round, from the committed `ncu --set full` capture
-# profiles/r01_v8_ncu_summary.txt (cold-cache, serialised launches of this same command).
-# k_surface_refine (enclosure test of the surface semantics) carries no algorithmic
-# flops in F_alg -- the oracle's counters were frozen on the hull arithmetic -- so its time only
-# lowers the step's achieved figure.
+# the five kernels of a 1 Mi-state round, from the committed `ncu --set full` capture
+# profiles/r02_v3_ncu_summary.txt (cold-cache, serialised launches of this same command).
+# k_surface_refine / k_surface_settle (what the cores and hulls leave open: enclosures, triangle stage;
+# DESIGN.md 4) carry no algorithmic flops in F_alg -- the oracle's counters were frozen on the hull
+# arithmetic -- so their time only lowers the step's achieved figure.
 NCU = {
-    "source": "profiles/r01_v8_ncu_summary.txt",
-    "k_broadphase": {"traffic_bytes": 37.81e6 + 0.01e6, "fma_pipe_pct": 34.3, "alu_pipe_pct": 62.0, "issue_active_pct": 76.4,
-                     "threads_per_inst": 28.2, "duration_us": 103.3},
-    "k_item_setup": {"traffic_bytes": 35.89e6 + 0.58e6, "fma_pipe_pct": 26.7, "alu_pipe_pct": 33.8, "issue_active_pct": 58.9,
-                     "threads_per_inst": 29.8, "duration_us": 85.4},
-    "k_narrowphase": {"traffic_bytes": 18.56e6 + 0.03e6, "fma_pipe_pct": 20.4, "alu_pipe_pct": 35.3, "issue_active_pct": 52.4,
-                      "threads_per_inst": 14.1, "duration_us": 134.4},
-    "k_surface_refine": {"traffic_bytes": 7.62e6 + 0.006e6, "fma_pipe_pct": 7.7, "alu_pipe_pct": 13.7, "issue_active_pct": 24.0,
-                         "threads_per_inst": 20.1, "duration_us": 59.4},
+    "source": "profiles/r02_v3_ncu_summary.txt",
+    "k_broadphase": {"traffic_bytes": 37.81e6 + 0.003e6, "fma_pipe_pct": 34.3, "alu_pipe_pct": 62.0, "issue_active_pct": 76.2,
+                     "threads_per_inst": 28.2, "duration_us": 104.2},
+    "k_item_setup": {"traffic_bytes": 41.24e6 + 4.25e6, "fma_pipe_pct": 24.9, "alu_pipe_pct": 33.6, "issue_active_pct": 58.2,
+                     "threads_per_inst": 20.4, "duration_us": 110.8},
+    "k_narrowphase": {"traffic_bytes": 9.45e6 + 0.0, "fma_pipe_pct": 15.7, "alu_pipe_pct": 28.9, "issue_active_pct": 43.3,
+                      "threads_per_inst": 8.9, "duration_us": 132.4},
+    "k_surface_refine": {"traffic_bytes": 6.61e6 + 0.09e6, "fma_pipe_pct": 3.1, "alu_pipe_pct": 10.2, "issue_active_pct": 14.4,
+                         "threads_per_inst": 17.1, "duration_us": 46.8},
+    "k_surface_settle": {"traffic_bytes": 1.65e6 + 0.0005e6, "fma_pipe_pct": 4.6, "alu_pipe_pct": 16.3, "issue_active_pct": 18.5,
+                         "threads_per_inst": 28.5, "duration_us": 35.4},
 }
 
 
@@ -390,7 +393,8 @@ def main():
                 "ALGORITHMIC flops frozen from the oracle's counters (full hull scans, DESIGN.md 5); the kernels execute fewer "
                 "(exact support maps scan ~3 of ~150 vertices), so the executed-instruction view is in `ncu`",
         "ncu": NCU,
-        "kernel_ms": {"k_broadphase": bp_ms, "k_item_setup": prof["item_setup_ms"] / rounds, "k_narrowphase": np_ms, "k_surface_refine": sr_ms},
+        "kernel_ms": {"k_broadphase": bp_ms, "k_item_setup": prof["item_setup_ms"] / rounds, "k_narrowphase": np_ms,
+                      "k_surface_refine+k_surface_settle": sr_ms},
         "states_per_launch": states_per_launch,
         "narrowphase_items_per_state": prof["narrowphase_items"] / max(n * args.steps, 1),
         "flop_per_config": F_KERNEL,
@@ -456,7 +460,7 @@ def main():
         "cpu_baseline": cpu_baseline,
         "parity": parity,
         "p_collision": float(hits[(args.steps - 1) % N_BATCHES].float().mean().item()),
-        "timing": "headline region: K steps, one CUDA-graph launch each, no per-kernel events; per-kernel durations from a second pass of K steps",
+        "timing": "headline region: K steps, one CUDA-graph launch each (memsets + five kernels), no per-kernel events; per-kernel durations from a second pass of K steps",
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -16,6 +16,11 @@
  *    are host pointers; `stream` is a cudaStream_t passed as void* (NULL = default stream);
  *  - device-pointer entry points are asynchronous on `stream`; host-pointer entry points
  *    (suffix _host) copy in, run, copy out and synchronise before returning;
+ *  - one engine owns one set of device workspaces (item bins, control block): its entry points serialise
+ *    internally -- a mutex around every call, and an event that makes a call on another stream wait for the
+ *    previous call's kernels -- so an engine may be shared by host threads and CUDA streams (results are ready
+ *    in stream order); calls on ONE engine never overlap on the device, use one engine per stream for that.
+ *    Every entry point leaves the caller's current CUDA device as it found it;
  *  - configurations are row-major float32 [N, nq]; SE(3) placements are 12 floats:
  *    rotation row-major (9) then translation (3);
  *  - there is NO CPU fallback: without a CUDA device creation fails with PBP_ERR_CUDA.
