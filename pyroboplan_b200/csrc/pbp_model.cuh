@@ -24,7 +24,7 @@ struct DevJoint {       // 96 B
 
 constexpr int N_INNER_BALLS = 4;
 
-struct DevGeom {        // 256 B -- narrowphase / item-setup view of a geometry
+struct __align__(16) DevGeom {        // 256 B -- narrowphase / item-setup view of a geometry
     float P[12];        // placement in parent joint frame (world placement if parent == 0)
     float par[4];       // shape parameters
     float centre[3];    // proxy-sphere centre in the geometry frame (initial GJK direction)

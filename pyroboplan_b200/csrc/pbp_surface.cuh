@@ -137,33 +137,47 @@ __device__ __noinline__ void gjk_converge(const ShapeRef &A, const ShapeRef &B, 
 // the centre-line test then).  T: placement of b in a's frame.  slack: FP32 rounding of the centres (metres).
 __device__ __forceinline__ bool inner_balls_hit(const DevGeom &GA, const DevGeom &GB, const float *T, float padding) {
     const float slack = 1e-5f;
+    // all eight balls are read up front and every test is evaluated (unused balls have r = 0 and a test needs
+    // r > 0): independent loads and straight-line arithmetic -- a loop with an early exit made a single-state
+    // call wait for one cold table read after the other
+    float4 ba[N_INNER_BALLS], bb[N_INNER_BALLS];
+#pragma unroll
+    for (int i = 0; i < N_INNER_BALLS; i++) {
+        ba[i] = *reinterpret_cast<const float4 *>(GA.balls[i]);
+        bb[i] = *reinterpret_cast<const float4 *>(GB.balls[i]);
+    }
+    bool hit = false;
     if (GA.shape == PBP_SHAPE_BOX) {
-        for (int j = 0; j < GB.n_balls; j++) {
-            const float3 c = se3_act(T, GB.balls[j][0], GB.balls[j][1], GB.balls[j][2]);
+#pragma unroll
+        for (int j = 0; j < N_INNER_BALLS; j++) {
+            const float3 c = se3_act(T, bb[j].x, bb[j].y, bb[j].z);
             const float dx = fmaxf(fabsf(c.x) - GA.par[0], 0.f), dy = fmaxf(fabsf(c.y) - GA.par[1], 0.f), dz = fmaxf(fabsf(c.z) - GA.par[2], 0.f);
-            const float r = GB.balls[j][3] + padding - slack;
-            if (r > 0.f && fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= r * r) return true;
+            const float r = bb[j].w + padding - slack;
+            hit = hit || (bb[j].w > 0.f && r > 0.f && fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= r * r);
         }
-        return false;
+        return hit;
     }
     if (GB.shape == PBP_SHAPE_BOX) {
-        for (int i = 0; i < GA.n_balls; i++) {
-            const float3 c = se3_act_inv(T, make_float3(GA.balls[i][0], GA.balls[i][1], GA.balls[i][2]));
+#pragma unroll
+        for (int i = 0; i < N_INNER_BALLS; i++) {
+            const float3 c = se3_act_inv(T, make_float3(ba[i].x, ba[i].y, ba[i].z));
             const float dx = fmaxf(fabsf(c.x) - GB.par[0], 0.f), dy = fmaxf(fabsf(c.y) - GB.par[1], 0.f), dz = fmaxf(fabsf(c.z) - GB.par[2], 0.f);
-            const float r = GA.balls[i][3] + padding - slack;
-            if (r > 0.f && fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= r * r) return true;
+            const float r = ba[i].w + padding - slack;
+            hit = hit || (ba[i].w > 0.f && r > 0.f && fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= r * r);
         }
-        return false;
+        return hit;
     }
-    for (int j = 0; j < GB.n_balls; j++) {
-        const float3 cb = se3_act(T, GB.balls[j][0], GB.balls[j][1], GB.balls[j][2]);
-        for (int i = 0; i < GA.n_balls; i++) {
-            const float dx = cb.x - GA.balls[i][0], dy = cb.y - GA.balls[i][1], dz = cb.z - GA.balls[i][2];
-            const float r = GA.balls[i][3] + GB.balls[j][3] + padding - slack;
-            if (r > 0.f && fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= r * r) return true;
+#pragma unroll
+    for (int j = 0; j < N_INNER_BALLS; j++) {
+        const float3 cb = se3_act(T, bb[j].x, bb[j].y, bb[j].z);
+#pragma unroll
+        for (int i = 0; i < N_INNER_BALLS; i++) {
+            const float dx = cb.x - ba[i].x, dy = cb.y - ba[i].y, dz = cb.z - ba[i].z;
+            const float r = ba[i].w + bb[j].w + padding - slack;
+            hit = hit || (ba[i].w > 0.f && bb[j].w > 0.f && r > 0.f && fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= r * r);
         }
     }
-    return false;
+    return hit;
 }
 
 // ------------------------------------------------------------------------------------------
