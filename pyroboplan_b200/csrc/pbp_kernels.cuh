@@ -823,7 +823,10 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
 // (decide_boolean / decide_distance), then the warp settles what is left (settle_warp_items).  The hull
 // tables and the planes are staged in shared memory when they fit (every support evaluation is a chain of
 // dependent table reads); cores and triangles, read by a few items only, stay in global memory.
-constexpr int SR_THREADS = 512;
+#ifndef PBP_SR_THREADS
+#define PBP_SR_THREADS 512
+#endif
+constexpr int SR_THREADS = PBP_SR_THREADS;
 constexpr int SR_DIR = 256;       // pairs the chunk directory holds
 #ifndef PBP_SR_LIST_CHUNK
 #define PBP_SR_LIST_CHUNK 8
