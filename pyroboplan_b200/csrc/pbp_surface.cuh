@@ -545,6 +545,23 @@ __device__ __forceinline__ LaneVerdict decide_boolean(const SurfTables &tab, int
     ConvOut h;
     const bool warm = dot3(v0, v0) > 1e-12f;
     const float3 start = warm ? v0 : gjk_start_direction(GA, GB, T);
+    if (warm && !(fl & PAIR_NOCORE)) {
+        // The cores are known to be farther apart than the margin (|v0| > margin): all that is asked of the hulls
+        // is "within the margin or not", which the boolean run answers without converging -- apart: free; within:
+        // the triangles decide, culled along the cores' separating direction.
+        GjkState s;
+        GjkOut g;
+        gjk_init(s, start);
+        while (!gjk_step<false>(AH, BH, T, s, margin, margin, g)) {
+        }
+        if (g.far || !g.hit) return r;
+        r.status = ST_TRIANGLES;
+        r.U = margin;
+        const float inv = rsqrtf(dot3(v0, v0));
+        r.n = make_float3(-v0.x * inv, -v0.y * inv, -v0.z * inv);
+        r.have_n = 1;
+        return r;
+    }
     gjk_converge(AH, BH, T, start, margin, h);
     if (h.far || h.dist > margin) return r;                 // the hulls are apart: free
     ConvOut k = h;
