@@ -104,7 +104,7 @@ struct pbp_engine {
     bool bp_smem_store = true;  // per-thread broadphase store fits in shared memory
     bool verts_in_smem = true;
     DevModel dm{};
-    DeviceBuffer d_joints, d_jgeoms, d_geoms, d_bpgeoms, d_bpboxes, d_bppairs, d_groups, d_pairorig, d_paths, d_pathops, d_order, d_verts, d_supcells, d_suplists, d_qlim, d_frames, d_planes, d_plane_idx, d_surf_tol, d_pair_enclose, d_kverts, d_ksupcells, d_ksuplists, d_mverts, d_tris;
+    DeviceBuffer d_joints, d_jgeoms, d_geoms, d_bpgeoms, d_bpboxes, d_bppairs, d_groups, d_pairorig, d_paths, d_pathops, d_order, d_verts, d_supcells, d_suplists, d_qlim, d_frames, d_planes, d_plane_idx, d_surf_tol, d_pair_enclose, d_kverts, d_ksupcells, d_ksuplists, d_mverts, d_tris, d_tverts;
     bool surface = false;   // some pair carries an enclosure flag (surface semantics of mesh geometries)
     bool sr_tables_in_smem = false;
     size_t smem_sr = 0;
@@ -473,7 +473,7 @@ void pbp_engine_destroy(pbp_engine *e) {
                             &e->d_desc_frac, &e->d_desc_sample, &e->d_scratch_i32, &e->d_scratch_u8, &e->d_cub, &e->d_sel,
                             &e->d_io_q, &e->d_io_q2, &e->d_io_hit, &e->d_io_f32, &e->d_io_i32, &e->d_ik_tables, &e->d_ws_oMi, &e->d_ws_oMg, &e->d_ws_dist,
                             &e->d_ws_p1, &e->d_ws_p2, &e->d_ws_nrm, &e->d_pairs_orig, &e->d_planes, &e->d_plane_idx, &e->d_surf_tol, &e->d_pair_enclose, &e->d_kverts, &e->d_ksupcells,
-                            &e->d_ksuplists, &e->d_mverts, &e->d_tris};
+                            &e->d_ksuplists, &e->d_mverts, &e->d_tris, &e->d_tverts};
     for (DeviceBuffer *b : bufs) b->release();
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     e->h_io_hit.release(); e->h_io_f32.release(); e->h_io_i32.release(); e->h_stage.release();
@@ -648,7 +648,8 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
                 (rc = upload(e->d_ksupcells, H.ksup_cells.data(), H.ksup_cells.size() * 2)) ||
                 (rc = upload(e->d_ksuplists, H.ksup_lists.data(), H.ksup_lists.size() * 2)) ||
                 (rc = upload(e->d_mverts, H.mverts.data(), H.mverts.size() * sizeof(float4))) ||
-                (rc = upload(e->d_tris, H.tris.data(), H.tris.size() * sizeof(int4))))
+                (rc = upload(e->d_tris, H.tris.data(), H.tris.size() * sizeof(int4))) ||
+                (rc = upload(e->d_tverts, H.tverts.data(), H.tverts.size() * sizeof(float4))))
                 return bail(rc);
             e->dm.kverts = e->d_kverts.as<float4>();
             e->dm.ksup_cells = e->d_ksupcells.as<uint16_t>();
@@ -658,6 +659,7 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
             e->dm.n_ksup_lists = (int)H.ksup_lists.size();
             e->dm.mverts = e->d_mverts.as<float4>();
             e->dm.tris = e->d_tris.as<int4>();
+            e->dm.tverts = e->d_tverts.as<float4>();
         } else {
             e->dm.kverts = e->dm.verts;
             e->dm.ksup_cells = e->dm.sup_cells;
@@ -667,6 +669,7 @@ int pbp_engine_create(const pbp_model_desc *d, int device, int64_t max_chunk_sta
             e->dm.n_ksup_lists = e->dm.n_sup_lists;
             e->dm.mverts = e->dm.verts;
             e->dm.tris = nullptr;
+            e->dm.tverts = nullptr;
         }
     }
     e->dm.q_lower = e->d_qlim.as<float>();

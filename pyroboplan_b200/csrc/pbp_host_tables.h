@@ -43,6 +43,7 @@ struct HostTables {
     std::vector<uint16_t> ksup_cells, ksup_lists;
     std::vector<float4> mverts;                    // mesh vertices and triangles of surface geometries
     std::vector<int4> tris;
+    std::vector<float4> tverts;   // the three vertices of every triangle, packed in triangle order (no index indirection on the device)
     std::vector<uint8_t> pair_flags;               // PAIR_* per internal pair
     bool has_tris = false;
     std::vector<int32_t> jgeoms;
@@ -221,6 +222,9 @@ inline int build_host_tables(const pbp_model_desc *d, HostTables &H) {
                     maxv = std::max(maxv, ix[k]);
                 }
                 H.tris.push_back(make_int4(ix[0], ix[1], ix[2], 0));
+                for (int k = 0; k < 3; k++)
+                    H.tverts.push_back(make_float4(d->mesh_verts[3 * (size_t)(mo + ix[k])], d->mesh_verts[3 * (size_t)(mo + ix[k]) + 1],
+                                                   d->mesh_verts[3 * (size_t)(mo + ix[k]) + 2], 0.f));
             }
             G.mvert_off = (int)H.mverts.size();
             for (int i = 0; i <= maxv; i++)

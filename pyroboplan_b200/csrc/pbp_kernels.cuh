@@ -854,7 +854,7 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
     tab.hlists = TABLES_IN_SMEM ? slist : M.sup_lists;
     tab.planes = TABLES_IN_SMEM ? spl : M.planes;
     tab.kverts = M.kverts; tab.kcells = M.ksup_cells; tab.klists = M.ksup_lists;
-    tab.mverts = M.mverts; tab.tris = M.tris;
+    tab.mverts = M.mverts; tab.tris = M.tris; tab.tverts = M.tverts;
     __shared__ uint16_t s_tri[SR_THREADS / 32][2][TRI_LIST_CAP];
     uint16_t *la = s_tri[threadIdx.x >> 5][0], *lb = s_tri[threadIdx.x >> 5][1];
     const unsigned lane = threadIdx.x & 31;
@@ -1017,7 +1017,7 @@ k_surface_settle(DevModel M, float padding, Outputs out, Bins bins, bool has_sam
     SurfTables tab;
     tab.hverts = M.verts; tab.hcells = M.sup_cells; tab.hlists = M.sup_lists; tab.planes = M.planes;
     tab.kverts = M.kverts; tab.kcells = M.ksup_cells; tab.klists = M.ksup_lists;
-    tab.mverts = M.mverts; tab.tris = M.tris;
+    tab.mverts = M.mverts; tab.tris = M.tris; tab.tverts = M.tverts;
     __shared__ uint16_t s_tri[SS_THREADS / 32][2][TRI_LIST_CAP];
     uint16_t *la = s_tri[threadIdx.x >> 5][0], *lb = s_tri[threadIdx.x >> 5][1];
     const unsigned lane = threadIdx.x & 31;
@@ -1159,7 +1159,7 @@ k_small_check(DevModel M, StateSource src, int64_t n_states, float padding, Outp
     SurfTables tab;
     tab.hverts = M.verts; tab.hcells = M.sup_cells; tab.hlists = M.sup_lists;
     tab.kverts = M.kverts; tab.kcells = M.ksup_cells; tab.klists = M.ksup_lists;
-    tab.planes = M.planes; tab.mverts = M.mverts; tab.tris = M.tris;
+    tab.planes = M.planes; tab.mverts = M.mverts; tab.tris = M.tris; tab.tverts = M.tverts;
     float R[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) R[k] = 0.f;

@@ -154,6 +154,7 @@ struct DevModel {
     int32_t has_tris;            // some geometry carries triangles: the narrowphase parks undecided items
     const float4 *mverts;        // mesh vertices (geometry frame)
     const int4 *tris;            // vertex indices (x, y, z) relative to the geometry's mvert_off
+    const float4 *tverts;        // [ntris][3] the triangles' vertices, packed (what the triangle stage reads)
 };
 
 // ------------------------------------------------------------------------------------------

@@ -82,6 +82,7 @@ struct SurfTables {
     const float4 *planes;
     const float4 *mverts;
     const int4 *tris;
+    const float4 *tverts;   // [ntris][3] packed triangle vertices
 };
 
 __device__ __forceinline__ ShapeRef hull_shape(const SurfTables &t, const DevGeom &G) {
@@ -226,17 +227,22 @@ __device__ __forceinline__ int enclosure_walk(const float4 *planes, const DevGeo
     const int nfaces = max_faces < nhull ? max_faces : G_outer.plane_cnt;
     const float pad_hit = enclosure_pad_hit(padding, G_outer.surface_tol);
     float worst_h = -FLT_MAX, worst_k = -FLT_MAX;
-    for (int f0 = 0; f0 < nfaces; f0 += nlanes) {
-        const int f = f0 + lane;
-        if (f < nfaces) {
-            const float4 pl = planes[G_outer.plane_off + f];
-            const float3 dl = make_float3(fmaf(T[0], pl.x, fmaf(T[3], pl.y, T[6] * pl.z)), fmaf(T[1], pl.x, fmaf(T[4], pl.y, T[7] * pl.z)),
-                                          fmaf(T[2], pl.x, fmaf(T[5], pl.y, T[8] * pl.z)));
-            const float3 sl = support_local(inner, dl);
-            const float3 sw = se3_act(T, sl.x, sl.y, sl.z);
-            const float ex = fmaf(pl.x, sw.x, fmaf(pl.y, sw.y, pl.z * sw.z)) + inner_radius - pl.w;
-            worst_k = fmaxf(worst_k, ex);
-            if (f < nhull) worst_h = fmaxf(worst_h, ex);
+    // two faces per lane and trip: every face is a chain of dependent table reads (plane -> support-map cell ->
+    // candidate list -> vertices); the second face's chain runs in the shadow of the first
+    for (int f0 = 0; f0 < nfaces; f0 += 2 * nlanes) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int f = f0 + u * nlanes + lane;
+            if (f < nfaces) {
+                const float4 pl = planes[G_outer.plane_off + f];
+                const float3 dl = make_float3(fmaf(T[0], pl.x, fmaf(T[3], pl.y, T[6] * pl.z)), fmaf(T[1], pl.x, fmaf(T[4], pl.y, T[7] * pl.z)),
+                                              fmaf(T[2], pl.x, fmaf(T[5], pl.y, T[8] * pl.z)));
+                const float3 sl = support_local(inner, dl);
+                const float3 sw = se3_act(T, sl.x, sl.y, sl.z);
+                const float ex = fmaf(pl.x, sw.x, fmaf(pl.y, sw.y, pl.z * sw.z)) + inner_radius - pl.w;
+                worst_k = fmaxf(worst_k, ex);
+                if (f < nhull) worst_h = fmaxf(worst_h, ex);
+            }
         }
         // one hull face the inner shape reaches settles it; nearly all parked items end in the first batch
         const bool out = worst_h >= -pad_hit;
@@ -291,7 +297,7 @@ __device__ __forceinline__ int enclosure_roles(const float4 *planes, int fl, con
 // divergent iterations.
 
 // squared distance between segments [p1, q1] and [p2, q2] (Ericson, Real-Time Collision Detection 5.1.9)
-__device__ __forceinline__ float segseg_dist2(float3 p1, float3 q1, float3 p2, float3 q2) {
+__device__ __noinline__ float segseg_dist2(float3 p1, float3 q1, float3 p2, float3 q2) {
     const float3 d1 = sub3(q1, p1), d2 = sub3(q2, p2), r = sub3(p1, p2);
     const float a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r);
     float sp = 0.f, tp = 0.f;
@@ -313,7 +319,7 @@ __device__ __forceinline__ float segseg_dist2(float3 p1, float3 q1, float3 p2, f
 
 // squared distance between the point p and the triangle (a, b, c), counted only when the closest point lies in the
 // triangle's INTERIOR or on it along the normal (edges and vertices are covered by the segment tests): FLT_MAX else
-__device__ __forceinline__ float point_face_dist2(float3 p, float3 a, float3 b, float3 c) {
+__device__ __noinline__ float point_face_dist2(float3 p, float3 a, float3 b, float3 c) {
     const float3 ab = sub3(b, a), ac = sub3(c, a), ap = sub3(p, a);
     const float3 n = cross3(ab, ac);
     const float nn = dot3(n, n);
@@ -326,7 +332,7 @@ __device__ __forceinline__ float point_face_dist2(float3 p, float3 a, float3 b, 
 }
 
 // does the segment [p, q] pass through the triangle (a, b, c)?  (p and q strictly on different sides, or touching)
-__device__ __forceinline__ bool segment_through_face(float3 p, float3 q, float3 a, float3 b, float3 c) {
+__device__ __noinline__ bool segment_through_face(float3 p, float3 q, float3 a, float3 b, float3 c) {
     const float3 ab = sub3(b, a), ac = sub3(c, a);
     const float3 n = cross3(ab, ac);
     const float dp = dot3(sub3(p, a), n), dq = dot3(sub3(q, a), n);
@@ -339,24 +345,23 @@ __device__ __forceinline__ bool segment_through_face(float3 p, float3 q, float3 
     return v >= 0.f && w >= 0.f && v + w <= nn;
 }
 
+// (Loops kept rolled around out-of-line helpers on purpose: a warp runs this once per item, and 1500 straight-line
+//  instructions fetched cold from the instruction cache took 25 k cycles; the rolled form re-executes ~300.)
 __device__ __noinline__ float tri_tri_distance(const float3 *A, const float3 *B) {
     float d2 = FLT_MAX;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 3; i++) {
-        const float3 a0 = A[i], a1 = A[(i + 1) % 3];
-#pragma unroll
-        for (int j = 0; j < 3; j++) d2 = fminf(d2, segseg_dist2(a0, a1, B[j], B[(j + 1) % 3]));
+        const float3 a0 = A[i], a1 = A[i == 2 ? 0 : i + 1];
+#pragma unroll 1
+        for (int j = 0; j < 3; j++) d2 = fminf(d2, segseg_dist2(a0, a1, B[j], B[j == 2 ? 0 : j + 1]));
     }
-#pragma unroll
+    bool cut = false;
+#pragma unroll 1
     for (int i = 0; i < 3; i++) {
         d2 = fminf(d2, point_face_dist2(A[i], B[0], B[1], B[2]));
         d2 = fminf(d2, point_face_dist2(B[i], A[0], A[1], A[2]));
-    }
-    bool cut = false;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        cut = cut || segment_through_face(A[i], A[(i + 1) % 3], B[0], B[1], B[2]);
-        cut = cut || segment_through_face(B[i], B[(i + 1) % 3], A[0], A[1], A[2]);
+        cut = cut || segment_through_face(A[i], A[i == 2 ? 0 : i + 1], B[0], B[1], B[2]);
+        cut = cut || segment_through_face(B[i], B[i == 2 ? 0 : i + 1], A[0], A[1], A[2]);
     }
     return cut ? 0.f : sqrtf(d2);
 }
@@ -366,6 +371,46 @@ __device__ __noinline__ float tri_tri_distance(const float3 *A, const float3 *B)
 // ------------------------------------------------------------------------------------------
 constexpr int TRI_LIST_CAP = 384;   // triangles of one geometry the warp's lists hold per pass
 
+// The triangles [t_begin, t_end) of one geometry that can come within `reach` of the ball around c_other and,
+// with a separating direction n, lie on the near side of the slab (SIDE_TOP: max of n.x >= lim; else min of
+// n.x <= lim): their indices go to `list`, in order; returns how many.  PLACED: the vertices are moved by T first.
+// Four triangles per lane are in flight at a time: the pass is a chain of table reads (L2 latency), not arithmetic.
+template <bool PLACED, bool SIDE_TOP>
+__device__ __forceinline__ int cull_triangles(const float4 *tverts, int t_begin, int t_end, const float *T, float3 c_other, float reach, bool have_n,
+                                              float3 n, float lim, uint16_t *list, int lane) {
+    constexpr int UNR = PBP_LANES > 1 ? 4 : 1;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int count = 0;
+    for (int t0 = t_begin; t0 < t_end; t0 += UNR * PBP_LANES) {
+        float4 v[UNR][3];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            const int t = min(t0 + u * PBP_LANES + lane, t_end - 1);
+            const float4 *tv = tverts + 3 * (size_t)t;
+            v[u][0] = tv[0]; v[u][1] = tv[1]; v[u][2] = tv[2];
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            const int t = t0 + u * PBP_LANES + lane;
+            float3 p0 = make_float3(v[u][0].x, v[u][0].y, v[u][0].z), p1 = make_float3(v[u][1].x, v[u][1].y, v[u][1].z),
+                   p2 = make_float3(v[u][2].x, v[u][2].y, v[u][2].z);
+            if (PLACED) { p0 = se3_act(T, p0.x, p0.y, p0.z); p1 = se3_act(T, p1.x, p1.y, p1.z); p2 = se3_act(T, p2.x, p2.y, p2.z); }
+            const float gx = fmaxf(fmaxf(fminf(fminf(p0.x, p1.x), p2.x) - c_other.x, c_other.x - fmaxf(fmaxf(p0.x, p1.x), p2.x)), 0.f);
+            const float gy = fmaxf(fmaxf(fminf(fminf(p0.y, p1.y), p2.y) - c_other.y, c_other.y - fmaxf(fmaxf(p0.y, p1.y), p2.y)), 0.f);
+            const float gz = fmaxf(fmaxf(fminf(fminf(p0.z, p1.z), p2.z) - c_other.z, c_other.z - fmaxf(fmaxf(p0.z, p1.z), p2.z)), 0.f);
+            bool keep = t < t_end && fmaf(gx, gx, fmaf(gy, gy, gz * gz)) <= reach * reach;
+            if (have_n) {
+                const float d0 = dot3(n, p0), d1 = dot3(n, p1), d2 = dot3(n, p2);
+                keep = keep && (SIDE_TOP ? fmaxf(fmaxf(d0, d1), d2) >= lim : fminf(fminf(d0, d1), d2) <= lim);
+            }
+            const unsigned km = __ballot_sync(0xffffffffu, keep);
+            if (keep) list[count + __popc(km & lt_mask)] = (uint16_t)t;
+            count += __popc(km);
+        }
+    }
+    return count;
+}
+
 // Smallest distance between the (cores of the) two geometries over all triangle pairs within U, FLT_MAX when
 // there is none.  A geometry without triangles is its solid (primitive or hull) as one piece.  n (unit, A's
 // frame, pointing from A to B; have_n): only triangles within the slab the other shape can reach along n
@@ -373,7 +418,6 @@ constexpr int TRI_LIST_CAP = 384;   // triangles of one geometry the warp's list
 // first_hit: return as soon as some pair is within U (boolean queries).  la / lb: per-warp shared scratch.
 __device__ __noinline__ float triangle_stage(const SurfTables &tab, const DevGeom &GA, const DevGeom &GB, const float *T, float3 n, bool have_n, float U,
                                              bool first_hit, uint16_t *la, uint16_t *lb, int lane) {
-    const unsigned lt_mask = (1u << lane) - 1u;
     const int nta = GA.tri_cnt, ntb = GB.tri_cnt;
     const ShapeRef AH = hull_shape(tab, GA), BH = hull_shape(tab, GB);
     const float3 ca = make_float3(GA.centre[0], GA.centre[1], GA.centre[2]);
@@ -387,6 +431,7 @@ __device__ __noinline__ float triangle_stage(const SurfTables &tab, const DevGeo
     }
     float best = FLT_MAX;
     float bound = U;
+    const long long tq0 = DBG_CLOCK();
     for (int a0 = 0; a0 < (nta > 0 ? nta : 1); a0 += TRI_LIST_CAP) {
         // ---- A's triangles that can matter
         int ca_n = 0;
@@ -394,28 +439,9 @@ __device__ __noinline__ float triangle_stage(const SurfTables &tab, const DevGeo
             ca_n = 1;
         } else {
             const int a1 = min(a0 + TRI_LIST_CAP, nta);
-            for (int t0 = a0; t0 < a1; t0 += PBP_LANES) {
-                const int t = t0 + lane;
-                bool keep = false;
-                if (t < a1) {
-                    const int4 tr = tab.tris[GA.tri_off + t];
-                    const float4 p0 = tab.mverts[GA.mvert_off + tr.x], p1 = tab.mverts[GA.mvert_off + tr.y], p2 = tab.mverts[GA.mvert_off + tr.z];
-                    const float gx = fmaxf(fmaxf(fminf(fminf(p0.x, p1.x), p2.x) - cb.x, cb.x - fmaxf(fmaxf(p0.x, p1.x), p2.x)), 0.f);
-                    const float gy = fmaxf(fmaxf(fminf(fminf(p0.y, p1.y), p2.y) - cb.y, cb.y - fmaxf(fmaxf(p0.y, p1.y), p2.y)), 0.f);
-                    const float gz = fmaxf(fmaxf(fminf(fminf(p0.z, p1.z), p2.z) - cb.z, cb.z - fmaxf(fmaxf(p0.z, p1.z), p2.z)), 0.f);
-                    const float reach = rb + U + slack;
-                    keep = fmaf(gx, gx, fmaf(gy, gy, gz * gz)) <= reach * reach;
-                    if (keep && have_n) {
-                        const float top = fmaxf(fmaxf(dot3(n, make_float3(p0.x, p0.y, p0.z)), dot3(n, make_float3(p1.x, p1.y, p1.z))),
-                                                dot3(n, make_float3(p2.x, p2.y, p2.z)));
-                        keep = top >= lo_b - U - slack;
-                    }
-                }
-                const unsigned km = __ballot_sync(0xffffffffu, keep);
-                if (keep) la[ca_n + __popc(km & lt_mask)] = (uint16_t)t;
-                ca_n += __popc(km);
-            }
+            ca_n = cull_triangles<false, true>(tab.tverts + 3 * (size_t)GA.tri_off, a0, a1, T, cb, rb + U + slack, have_n, n, lo_b - U - slack, la, lane);
         }
+        if (lane == 0) DBG_ADD(40, DBG_CLOCK() - tq0);
         if (ca_n == 0) continue;
         for (int b0 = 0; b0 < (ntb > 0 ? ntb : 1); b0 += TRI_LIST_CAP) {
             // ---- B's triangles that can matter (tested in A's frame)
@@ -424,28 +450,9 @@ __device__ __noinline__ float triangle_stage(const SurfTables &tab, const DevGeo
                 cb_n = 1;
             } else {
                 const int b1 = min(b0 + TRI_LIST_CAP, ntb);
-                for (int t0 = b0; t0 < b1; t0 += PBP_LANES) {
-                    const int t = t0 + lane;
-                    bool keep = false;
-                    if (t < b1) {
-                        const int4 tr = tab.tris[GB.tri_off + t];
-                        const float4 q0 = tab.mverts[GB.mvert_off + tr.x], q1 = tab.mverts[GB.mvert_off + tr.y], q2 = tab.mverts[GB.mvert_off + tr.z];
-                        const float3 p0 = se3_act(T, q0.x, q0.y, q0.z), p1 = se3_act(T, q1.x, q1.y, q1.z), p2 = se3_act(T, q2.x, q2.y, q2.z);
-                        const float gx = fmaxf(fmaxf(fminf(fminf(p0.x, p1.x), p2.x) - ca.x, ca.x - fmaxf(fmaxf(p0.x, p1.x), p2.x)), 0.f);
-                        const float gy = fmaxf(fmaxf(fminf(fminf(p0.y, p1.y), p2.y) - ca.y, ca.y - fmaxf(fmaxf(p0.y, p1.y), p2.y)), 0.f);
-                        const float gz = fmaxf(fmaxf(fminf(fminf(p0.z, p1.z), p2.z) - ca.z, ca.z - fmaxf(fmaxf(p0.z, p1.z), p2.z)), 0.f);
-                        const float reach = ra + U + slack;
-                        keep = fmaf(gx, gx, fmaf(gy, gy, gz * gz)) <= reach * reach;
-                        if (keep && have_n) {
-                            const float bot = fminf(fminf(dot3(n, p0), dot3(n, p1)), dot3(n, p2));
-                            keep = bot <= hi_a + U + slack;
-                        }
-                    }
-                    const unsigned km = __ballot_sync(0xffffffffu, keep);
-                    if (keep) lb[cb_n + __popc(km & lt_mask)] = (uint16_t)t;
-                    cb_n += __popc(km);
-                }
+                cb_n = cull_triangles<true, false>(tab.tverts + 3 * (size_t)GB.tri_off, b0, b1, T, ca, ra + U + slack, have_n, n, hi_a + U + slack, lb, lane);
             }
+            if (lane == 0) DBG_ADD(41, DBG_CLOCK() - tq0);
             if (cb_n == 0) continue;
             __syncwarp();
             // ---- every pair of the two lists, the lanes sharing them
@@ -459,16 +466,16 @@ __device__ __noinline__ float triangle_stage(const SurfTables &tab, const DevGeo
                     ShapeRef SA = AH, SB = BH;
                     float3 v0a = ca, v0b = cb;
                     if (nta > 0) {
-                        const int4 tr = tab.tris[GA.tri_off + la[ia]];
-                        va[0] = tab.mverts[GA.mvert_off + tr.x]; va[1] = tab.mverts[GA.mvert_off + tr.y]; va[2] = tab.mverts[GA.mvert_off + tr.z];
+                        const float4 *tv = tab.tverts + 3 * (size_t)(GA.tri_off + la[ia]);
+                        va[0] = tv[0]; va[1] = tv[1]; va[2] = tv[2];
                         va[3] = va[2];
                         SA.shape = PBP_SHAPE_CONVEX; SA.verts = va; SA.nverts = 4; SA.cell_off = nullptr; SA.cell_list = nullptr;
                         v0a = make_float3((va[0].x + va[1].x + va[2].x) * (1.f / 3.f), (va[0].y + va[1].y + va[2].y) * (1.f / 3.f),
                                           (va[0].z + va[1].z + va[2].z) * (1.f / 3.f));
                     }
                     if (ntb > 0) {
-                        const int4 tr = tab.tris[GB.tri_off + lb[ib]];
-                        vb[0] = tab.mverts[GB.mvert_off + tr.x]; vb[1] = tab.mverts[GB.mvert_off + tr.y]; vb[2] = tab.mverts[GB.mvert_off + tr.z];
+                        const float4 *tv = tab.tverts + 3 * (size_t)(GB.tri_off + lb[ib]);
+                        vb[0] = tv[0]; vb[1] = tv[1]; vb[2] = tv[2];
                         vb[3] = vb[2];
                         SB.shape = PBP_SHAPE_CONVEX; SB.verts = vb; SB.nverts = 4; SB.cell_off = nullptr; SB.cell_list = nullptr;
                         v0b = se3_act(T, (vb[0].x + vb[1].x + vb[2].x) * (1.f / 3.f), (vb[0].y + vb[1].y + vb[2].y) * (1.f / 3.f),
@@ -500,7 +507,7 @@ __device__ __noinline__ float triangle_stage(const SurfTables &tab, const DevGeo
                 float wb = best;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) wb = fminf(wb, __shfl_xor_sync(0xffffffffu, wb, o));
-                if (wb <= U && first_hit) return wb;
+                if (wb <= U && first_hit) { if (lane == 0) DBG_ADD(42, DBG_CLOCK() - tq0); return wb; }
                 bound = fminf(bound, wb);
             }
             __syncwarp();

@@ -177,7 +177,7 @@ int emu_surface_items(const pbp_model_desc *d, int pair, const float *T, int64_t
     tab.kverts = H.has_tris ? H.kverts.data() : H.verts.data();
     tab.kcells = H.has_tris ? H.ksup_cells.data() : H.sup_cells.data();
     tab.klists = H.has_tris ? H.ksup_lists.data() : H.sup_lists.data();
-    tab.planes = planes.data(); tab.mverts = H.mverts.data(); tab.tris = H.tris.data();
+    tab.planes = planes.data(); tab.mverts = H.mverts.data(); tab.tris = H.tris.data(); tab.tverts = H.tverts.data();
     const BpPair pr = H.bppairs[p];
     const DevGeom &GA = H.geoms[pr.a];
     const DevGeom &GB = H.geoms[pr.b];
