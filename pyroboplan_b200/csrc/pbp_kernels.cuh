@@ -29,7 +29,11 @@ namespace pbp {
 #define PBP_NP_REFILL_MIN 8   // measured on config 2: 173.7 us (1) / 172.9 (4) / 170.0 (8) / 170.7 (12) / 171.0 (16)
 #endif
 #ifndef PBP_NP_LOCKSTEP
-#define PBP_NP_LOCKSTEP 1
+// 0: per trip, run only the phase (support / simplex) most live lanes are waiting for; 1: every trip runs the support
+// phase and then the simplex phase for every live lane.  Round 1 (0.28 items per state, most of them ending after
+// two or three iterations): lock-step 170 against 194 us.  Round 2 (the inner balls take the easy hits away: 0.15
+// items per state, 4.7 iterations each, a lane load or two per warp): 125 us in lock-step, 100 us without.
+#define PBP_NP_LOCKSTEP 0
 #endif
 #ifndef PBP_NP_MIN_BLOCKS
 #define PBP_NP_MIN_BLOCKS 2
@@ -704,8 +708,8 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
         //      not finish -- the simplex phase.  Since the item setup removed the items that end
         //      after one support call, the items here all run several iterations, and keeping the
         //      lanes in lock-step (every live lane is at "support" at the top of a trip) wastes only
-        //      the simplex slot of a lane's last trip.  (PBP_NP_LOCKSTEP=0 restores the older
-        //      policy: per trip, run only the phase most lanes are waiting for.)
+        //      the simplex slot of a lane's last trip.  (PBP_NP_LOCKSTEP=0, the default since round 2:
+        //      per trip, run only the phase most lanes are waiting for -- see the macro.)
         auto publish = [&](const GjkOut &r, float radii) {
             const int fl = M.has_tris ? M.pair_enclose[p] : 0;
             if (MODE == MODE_DIST) {
