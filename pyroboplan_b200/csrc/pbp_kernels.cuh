@@ -425,6 +425,9 @@ __device__ __forceinline__ bool next_tile(uint32_t *tile_counter, const uint32_t
 // ------------------------------------------------------------------------------------------
 // Item setup: T = oMg[a]^-1 * oMg[b] for every undecided (state, pair) item
 // ------------------------------------------------------------------------------------------
+#ifndef PBP_IS_NOENC
+#define PBP_IS_NOENC 1        // developer switch: 0 leaves every core hit of a pair with an enclosure flag to the refine kernel
+#endif
 #ifndef PBP_INNER_BALLS
 #define PBP_INNER_BALLS 1     // developer switch: 0 disables the inner-ball hit certificates of the item setup
 #endif
@@ -488,26 +491,19 @@ k_item_setup(DevModel M, StateSource src, float padding, Outputs out, Bins bins,
                     const float qa = __ldg(src.q1 + (int64_t)group * M.nq + k), qb = __ldg(src.q2 + (int64_t)group * M.nq + k);
                     return fmaf(f, qb - qa, qa);
                 };
-                float cur[12], lca[12], TA[12], nxt[12];
+                // (the trunk from the base to the lowest common ancestor cancels in oMg[a]^-1 * oMg[b]: both
+                //  branches start from the identity at the ancestor)
+                float cur[12], TA[12], nxt[12];
                 se3_identity(cur);
-                int o = 0;
-                for (int i = 0; i < path.n_trunk; i++, o++) {
-                    const DevJoint &J = sj[ops[o]];
-                    joint_transform(J, cur, qval(J.idx_q), nxt);
-#pragma unroll
-                    for (int k = 0; k < 12; k++) cur[k] = nxt[k];
-                }
-#pragma unroll
-                for (int k = 0; k < 12; k++) lca[k] = cur[k];
+                int o = path.n_trunk;
                 for (int i = 0; i < path.n_a; i++, o++) {
                     const DevJoint &J = sj[ops[o]];
                     joint_transform(J, cur, qval(J.idx_q), nxt);
 #pragma unroll
                     for (int k = 0; k < 12; k++) cur[k] = nxt[k];
                 }
-                se3_mul(cur, GA.P, TA);   // oMg[a]
-#pragma unroll
-                for (int k = 0; k < 12; k++) cur[k] = lca[k];
+                se3_mul(cur, GA.P, TA);   // placement of a relative to the ancestor
+                se3_identity(cur);
                 for (int i = 0; i < path.n_b; i++, o++) {
                     const DevJoint &J = sj[ops[o]];
                     joint_transform(J, cur, qval(J.idx_q), nxt);
@@ -515,7 +511,7 @@ k_item_setup(DevModel M, StateSource src, float padding, Outputs out, Bins bins,
                     for (int k = 0; k < 12; k++) cur[k] = nxt[k];
                 }
                 float TB[12];
-                se3_mul(cur, GB.P, TB);   // oMg[b]
+                se3_mul(cur, GB.P, TB);   // placement of b relative to the ancestor
                 se3_inv_mul(TA, TB, R);
                 // First GJK iteration, here where every lane of the warp is busy with the same pair:
                 // about two thirds of the items are already separated along the line between the
@@ -539,7 +535,7 @@ k_item_setup(DevModel M, StateSource src, float padding, Outputs out, Bins bins,
                     const float pad = MODE == MODE_DIST ? 0.f : padding;
                     const bool balls = PBP_INNER_BALLS && inner_balls_hit(GA, GB, R, pad);
                     bool pokes = false;
-                    if (fl_enc_any && (balls || fl_enc)) pokes = enclosure_quick_pokes(fl_enc_any, GA, GB, hull_shape(tab, GA), hull_shape(tab, GB), R, pad);
+                    if (fl_enc_any && (balls || (PBP_IS_NOENC && fl_enc))) pokes = enclosure_quick_pokes(fl_enc_any, GA, GB, hull_shape(tab, GA), hull_shape(tab, GB), R, pad);
                     if (balls && (!fl_enc_any || pokes)) {
                         out.hit[group] = 1;
                         if (MODE == MODE_BOOL_ALL) {
@@ -1091,17 +1087,9 @@ __device__ __forceinline__ LaneVerdict small_item(const DevModel &M, const SurfT
     // ---- relative placement of b in a's frame (as k_item_setup)
     const PairPath path = M.paths[p];
     const uint8_t *ops = M.path_ops + path.off;
-    float cur[12], lca[12], TA[12], TB[12], nxt[12];
+    float cur[12], TA[12], TB[12], nxt[12];
     se3_identity(cur);
-    int o = 0;
-    for (int i = 0; i < path.n_trunk; i++, o++) {
-        const DevJoint &J = M.joints[ops[o]];
-        joint_transform(J, cur, qval(J.idx_q), nxt);
-#pragma unroll
-        for (int k = 0; k < 12; k++) cur[k] = nxt[k];
-    }
-#pragma unroll
-    for (int k = 0; k < 12; k++) lca[k] = cur[k];
+    int o = path.n_trunk;      // (the trunk cancels in the relative placement)
     for (int i = 0; i < path.n_a; i++, o++) {
         const DevJoint &J = M.joints[ops[o]];
         joint_transform(J, cur, qval(J.idx_q), nxt);
@@ -1109,8 +1097,7 @@ __device__ __forceinline__ LaneVerdict small_item(const DevModel &M, const SurfT
         for (int k = 0; k < 12; k++) cur[k] = nxt[k];
     }
     se3_mul(cur, GA.P, TA);
-#pragma unroll
-    for (int k = 0; k < 12; k++) cur[k] = lca[k];
+    se3_identity(cur);
     for (int i = 0; i < path.n_b; i++, o++) {
         const DevJoint &J = M.joints[ops[o]];
         joint_transform(J, cur, qval(J.idx_q), nxt);
