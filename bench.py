@@ -272,7 +272,8 @@ def main():
     model, cmodel = panda_models()
     eng = CollisionEngine(model, cmodel, device=local_rank)
     n = args.states
-    host_batches = [torch.from_numpy(make_batch(model, n, 7919 * rank + b)).pin_memory() for b in range(N_BATCHES)]
+    seed_rank = int(os.environ.get("PBP_BENCH_SEED_RANK", rank))   # (developer knob: another rank's inputs on this rank)
+    host_batches = [torch.from_numpy(make_batch(model, n, 7919 * seed_rank + b)).pin_memory() for b in range(N_BATCHES)]
     dev_batches = [b.to(dev, non_blocking=True) for b in host_batches]
     hits = [torch.empty(n, dtype=torch.bool, device=dev) for _ in range(N_BATCHES)]   # fixed buffers: every round replays its CUDA graph
     torch.cuda.synchronize()
@@ -285,8 +286,8 @@ def main():
     # W untimed warm-up steps (at least one per input batch, so no batch is touched for the
     # first time inside the timed region)
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()   # (rank 0 prints the line: its GPU's clocks; the other ranks run no poller thread)
+    sampler.start()   # every rank samples its own GPU (a poll every 2 ms on one of the rank's own cores; the timed region
+                      # replays CUDA graphs, one launch per step, so the poller cannot starve the launch thread)
     for w in range(max(args.warmup, N_BATCHES + 1)):
         eng.check_states(dev_batches[w % N_BATCHES], out=hits[w % N_BATCHES])
     torch.cuda.synchronize()
@@ -303,7 +304,12 @@ def main():
     torch.cuda.synchronize()
     t_region1 = time.perf_counter()
     barrier()
-    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
+    clocks = sampler.stop(t_region0, t_region1)
+    clocks_by_rank = None
+    if world > 1:
+        allc = [None] * world
+        dist.all_gather_object(allc, {"sm_mhz": clocks.get("sm_mhz"), "power_w_max": clocks.get("power_w_max"), "reasons": clocks.get("reasons")})
+        clocks_by_rank = allc
     ms = ev0.elapsed_time(ev1)
     stats = eng.stats(reset=True)
     # per-kernel launch durations: the same K steps once more with CUDA events around every kernel (plain
@@ -317,7 +323,11 @@ def main():
     eng.set_profiling(False)
     eng.stats(reset=True)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    rank_ms = None
     if world > 1:
+        gathered = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        rank_ms = [float(x.item()) / args.steps for x in gathered]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * n * args.steps / (ms_max * 1e-3)
@@ -444,6 +454,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step_by_rank": rank_ms,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "states_per_gpu_per_step": n,
                    "l2": f"inputs rotate over {N_BATCHES} batches ({N_BATCHES * n * 36 / 1e6:.0f} MB > 126 MB L2)",
@@ -456,6 +467,7 @@ def main():
                                         "rotating pinned slices, overlapped with H2D and kernels): the call the drop-in functions make"}},
         "gpu_launches": stats["kernel_launches"],
         "clocks": clocks,
+        "clocks_by_rank": clocks_by_rank,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "parity": parity,

@@ -925,6 +925,7 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
         bool active = false;
         int32_t g = 0;
         float3 v0 = make_float3(0.f, 0.f, 0.f);   // warm start of an undecided item (zero: none)
+        const bool is_list_chunk = c < list_chunks;
         if (c < list_chunks) {
             // undecided items of the compact list, one per lane, each with its own pair
             const uint32_t i = c * SR_LIST_CHUNK + lane;
@@ -984,7 +985,7 @@ k_surface_refine(DevModel M, float padding, Outputs out, Bins bins, uint32_t *ch
             DBG_ADD(0, 1); DBG_ADD(1 + v.status, 1);
             if (g & SR_PARKED) DBG_ADD(24, 1);
         }
-        if (lane == 0) DBG_ADD(11, DBG_CLOCK() - tl0);
+        if (lane == 0) { const long long dtl = DBG_CLOCK() - tl0; DBG_ADD(11, dtl); DBG_MAX(is_list_chunk ? 43 : 44, dtl); }
         // what needs a whole warp goes to a list that k_surface_settle works off one item per warp: these items
         // cluster in a few bins (a finger inside link 5 ...), settled by the warp that found them they were the
         // tail of the launch

@@ -33,8 +33,8 @@ __device__ unsigned long long g_dbg[48];
 #define DBG_MAX(i, v) atomicMax(&g_dbg[i], (unsigned long long)(v))
 #define DBG_CLOCK() clock64()
 #else
-#define DBG_ADD(i, v) ((void)sizeof(v))
-#define DBG_MAX(i, v) ((void)sizeof(v))
+#define DBG_ADD(i, v) ((void)sizeof(i), (void)sizeof(v))
+#define DBG_MAX(i, v) ((void)sizeof(i), (void)sizeof(v))
 #define DBG_CLOCK() 0ll
 #endif
 
@@ -522,6 +522,9 @@ __device__ __noinline__ float triangle_stage(const SurfTables &tab, const DevGeo
 // Lane level: one parked item
 // ------------------------------------------------------------------------------------------
 enum { ST_NONE = 0, ST_HIT = 1, ST_WALK = 2, ST_TRIANGLES = 3, ST_VALUE = 4 };
+#ifndef PBP_SR_HULL_ITERS
+#define PBP_SR_HULL_ITERS 8   // iterations an undecided item's hull run gets before the triangles decide
+#endif
 struct LaneVerdict {
     int status;     // ST_NONE: free / cannot improve the minimum; ST_HIT: the pair collides; ST_WALK: the warp walks the
                     // enclosing core's planes; ST_TRIANGLES: the warp runs the triangle stage; ST_VALUE: dist is exact
@@ -550,7 +553,7 @@ __device__ __forceinline__ LaneVerdict decide_boolean(const SurfTables &tab, int
         return r;
     }
     ConvOut h;
-    const bool warm = dot3(v0, v0) > 1e-12f;
+    const bool warm = dot3(v0, v0) > 1e-30f;   // (any non-zero vector: cores 1e-7 m apart are as undecided as cores 1e-4 m apart)
     const float3 start = warm ? v0 : gjk_start_direction(GA, GB, T);
     if (warm && !(fl & PAIR_NOCORE)) {
         // The cores are known to be farther apart than the margin (|v0| > margin): all that is asked of the hulls
@@ -559,9 +562,13 @@ __device__ __forceinline__ LaneVerdict decide_boolean(const SurfTables &tab, int
         GjkState s;
         GjkOut g;
         gjk_init(s, start);
+        bool settled = true;
         while (!gjk_step<false>(AH, BH, T, s, margin, margin, g)) {
+            // hulls about `margin` apart converge slowly in FP32 (up to 48 iterations): such a lane was the tail of
+            // the whole launch -- after a few iterations the (exact) triangle stage takes the item as it is
+            if (s.it >= PBP_SR_HULL_ITERS) { settled = false; break; }
         }
-        if (g.far || !g.hit) return r;
+        if (settled && (g.far || !g.hit)) return r;
         r.status = ST_TRIANGLES;
         r.U = margin;
         const float inv = rsqrtf(dot3(v0, v0));

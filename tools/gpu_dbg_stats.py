@@ -14,11 +14,11 @@ NAMES = {0: "sr lane items", 1: "sr ST_NONE", 2: "sr ST_HIT", 3: "sr ST_WALK", 4
          13: "sr kernel cycles max warp", 14: "sr kernel cycles warp sum", 15: "tri ca_n sum", 16: "tri cb_n sum", 17: "walk POKES", 18: "walk ENCLOSED",
          19: "walk UNSURE", 20: "tri have_n", 21: "tri hits", 22: "sr bin chunks", 23: "sr list items", 24: "sr parked lane items",
          30: "np items", 31: "np trips (warp)", 32: "np support lanes sum", 33: "np cycles warp sum", 34: "np cycles max warp", 35: "np parked",
-         36: "np doubts", 37: "np hits", 38: "np free", 40: "tri: cycles to end of A cull (sum)", 41: "tri: cycles to end of B cull (sum)", 42: "tri: cycles to first hit (sum)"}
+         36: "np doubts", 37: "np hits", 38: "np free", 40: "tri: cycles to end of A cull (sum)", 41: "tri: cycles to end of B cull (sum)", 42: "tri: cycles to first hit (sum)", 43: "sr max cycles of one list chunk", 44: "sr max cycles of one bin chunk"}
 model, cmodel, vmodel = panda.load_models()
 panda.add_self_collisions(model, cmodel); panda.add_object_collisions(model, cmodel, vmodel)
 n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 1 << 20
-q = np.random.default_rng(0).uniform(model.lowerPositionLimit, model.upperPositionLimit, size=(n, model.nq)).astype(np.float32)
+q = np.random.default_rng(int(os.environ.get("PBP_DBG_SEED", 0))).uniform(model.lowerPositionLimit, model.upperPositionLimit, size=(n, model.nq)).astype(np.float32)
 qd = torch.as_tensor(q, device="cuda:0")
 eng = CollisionEngine(model, cmodel, device=0)
 lib = engine.load_library()
