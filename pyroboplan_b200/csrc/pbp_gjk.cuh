@@ -323,7 +323,12 @@ __device__ __forceinline__ float3 gjk_start_direction(const DevGeom &GA, const D
 //                    outside the cores -- an item that converges between margin and cut is UNDECIDED
 //                    (out.hit = 0, out.far = 0) and goes to the triangle stage (pbp_surface.cuh).
 // WANT_DIST = true : run to convergence unless the pair is certainly farther than `bound`.
-template <bool WANT_DIST, bool TRACK = false>
+// EARLY_UNDECIDED (boolean queries on cores, bound > margin): also finish -- UNDECIDED, out.hit = out.far = 0 -- as soon
+//                    as the cores are certainly farther apart than the margin without being beyond the cut.  Nobody
+//                    needs the converged core distance of such an item (the hulls and, if need be, the triangles
+//                    decide it, pbp_surface.cuh), and converging on it in FP32 took up to 48 iterations: the lanes doing
+//                    that were the tail of the narrowphase launch.
+template <bool WANT_DIST, bool TRACK = false, bool EARLY_UNDECIDED = false>
 __device__ __forceinline__ bool gjk_support_phase(const ShapeRef &A, const ShapeRef &B, const float *T, GjkState &s, float margin,
                                                   float bound, GjkOut &out) {
     const float3 v = s.v;
@@ -358,6 +363,11 @@ __device__ __forceinline__ bool gjk_support_phase(const ShapeRef &A, const Shape
         out.dist = vw * rsqrtf(vv);
         out.hit = 0;
         out.far = 1;
+        return true;
+    }
+    if (EARLY_UNDECIDED && !WANT_DIST && vw > 0.f && vw * vw > margin * margin * vv * (1.f + 1e-5f)) {
+        out.dist = vw * rsqrtf(vv);   // a lower bound beyond the margin, not beyond the cut
+        out.hit = 0;
         return true;
     }
     if (n > 0) {

@@ -768,7 +768,7 @@ k_narrowphase(DevModel M, float padding, Outputs out, Bins bins, uint32_t *chunk
             radii = GA.core_radius + GB.core_radius;
             const float margin = padding + radii;
             return (MODE == MODE_DIST) ? gjk_support_phase<true>(A, B, T, s, margin, bound, r)
-                                       : gjk_support_phase<false>(A, B, T, s, margin, margin + pair_eps(GA, GB), r);
+                                       : gjk_support_phase<false, false, true>(A, B, T, s, margin, margin + pair_eps(GA, GB), r);
         };
         auto simplex = [&](GjkOut &r, float &radii) {
             const float margin = padding + sg[sp[p].a].core_radius + sg[sp[p].b].core_radius;
