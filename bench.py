@@ -47,22 +47,22 @@ F_KERNEL = {"k_broadphase": F_BP_FLOP_PER_CONFIG, "k_item_setup": 0.45 * F_NP_FL
 HBM_BYTES_PER_CONFIG = 9 * 4 + 1   # 9 float32 in, 1 verdict byte out
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) and pipe utilisation of
 # the five kernels of a 1 Mi-state round, from the committed `ncu --set full` capture
-# profiles/r02_v5_ncu_summary.txt (cold-cache, serialised launches of this same command).
+# profiles/r02_v6_ncu_summary.txt (cold-cache, serialised launches of this same command).
 # k_surface_refine / k_surface_settle (what the cores and hulls leave open: enclosures, triangle stage;
 # DESIGN.md 4) carry no algorithmic flops in F_alg -- the oracle's counters were frozen on the hull
 # arithmetic -- so their time only lowers the step's achieved figure.
 NCU = {
-    "source": "profiles/r02_v5_ncu_summary.txt",
-    "k_broadphase": {"traffic_bytes": 37.81e6 + 0.001e6, "fma_pipe_pct": 34.1, "alu_pipe_pct": 61.7, "issue_active_pct": 76.2,
-                     "threads_per_inst": 28.2, "duration_us": 101.1},
-    "k_item_setup": {"traffic_bytes": 40.96e6 + 4.31e6, "fma_pipe_pct": 24.5, "alu_pipe_pct": 36.7, "issue_active_pct": 58.4,
-                     "threads_per_inst": 20.5, "duration_us": 99.7},
-    "k_narrowphase": {"traffic_bytes": 9.31e6 + 0.0, "fma_pipe_pct": 16.7, "alu_pipe_pct": 30.9, "issue_active_pct": 45.8,
-                      "threads_per_inst": 11.8, "duration_us": 104.6},
-    "k_surface_refine": {"traffic_bytes": 6.13e6 + 0.11e6, "fma_pipe_pct": 3.8, "alu_pipe_pct": 8.8, "issue_active_pct": 14.3,
-                         "threads_per_inst": 17.0, "duration_us": 44.4},
-    "k_surface_settle": {"traffic_bytes": 1.70e6 + 0.0, "fma_pipe_pct": 6.7, "alu_pipe_pct": 13.9, "issue_active_pct": 19.5,
-                         "threads_per_inst": 28.4, "duration_us": 28.0},
+    "source": "profiles/r02_v6_ncu_summary.txt",
+    "k_broadphase": {"traffic_bytes": 37.81e6 + 0.002e6, "fma_pipe_pct": 34.2, "alu_pipe_pct": 61.8, "issue_active_pct": 76.3,
+                     "threads_per_inst": 28.2, "duration_us": 104.8},
+    "k_item_setup": {"traffic_bytes": 40.90e6 + 4.20e6, "fma_pipe_pct": 24.6, "alu_pipe_pct": 36.8, "issue_active_pct": 58.2,
+                     "threads_per_inst": 20.5, "duration_us": 102.5},
+    "k_narrowphase": {"traffic_bytes": 9.32e6 + 0.0003e6, "fma_pipe_pct": 16.0, "alu_pipe_pct": 30.0, "issue_active_pct": 44.5,
+                      "threads_per_inst": 12.1, "duration_us": 100.0},
+    "k_surface_refine": {"traffic_bytes": 9.14e6 + 0.18e6, "fma_pipe_pct": 4.5, "alu_pipe_pct": 10.8, "issue_active_pct": 16.9,
+                         "threads_per_inst": 15.2, "duration_us": 39.2},
+    "k_surface_settle": {"traffic_bytes": 1.82e6 + 0.0, "fma_pipe_pct": 6.7, "alu_pipe_pct": 13.7, "issue_active_pct": 19.8,
+                         "threads_per_inst": 28.0, "duration_us": 34.4},
 }
 
 
