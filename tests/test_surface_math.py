@@ -77,3 +77,71 @@ def test_enclosure_flags_cover_every_enclosure_on_the_panda():
                 assert arrays["pair_enclose"][k] & 1
                 seen += 1
     assert seen > 20
+
+
+def test_inner_balls_lie_inside_their_cores():
+    """The hit certificate of the item setup (pbp_surface.cuh::inner_balls_hit) is only sound if every ball lies
+    inside the core (inside the hull for a solid): checked against the core's face planes for every bundled mesh."""
+    from pyroboplan_b200.engine import flatten_model
+    from pyroboplan_b200.model.surface import surface_tables
+    from pyroboplan_b200.models import panda, ur5
+
+    for load in (panda.load_models, ur5.load_ur5_on_base_models):
+        model, cmodel, _ = load()
+        arrays, _ = flatten_model(model, cmodel)
+        seen = spread = 0
+        for g, obj in enumerate(cmodel.geometryObjects):
+            shape = obj.geometry
+            if getattr(shape, "mesh_triangles", None) is None:
+                continue
+            st = surface_tables(shape)
+            balls = arrays["geom_inner_balls"][g].astype(np.float64)
+            if not st["has_core"]:
+                assert (balls[:, 3] == 0).all()          # no core: nothing may certify a hit
+                continue
+            kp = st["core_hull_planes"]
+            for c in balls[balls[:, 3] > 0]:
+                assert (kp[:, :3] @ c[:3] + c[3] <= kp[:, 3] + 1e-9).all(), (obj.name, c)
+                seen += 1
+            used = balls[balls[:, 3] > 0]
+            spread = max(spread, len(used))
+            if len(used) >= 2:   # the balls are not all the same one
+                assert np.linalg.norm(used[0, :3] - used[1, :3]) > 1e-3
+        assert seen >= 14 and spread == 4
+
+
+def _l_shaped_prism():
+    """A closed, consistently oriented NON-convex mesh (an L-shaped prism) whose hull's Chebyshev centre lies
+    OUTSIDE the solid -- in the notch of the L."""
+    poly = np.array([[0, 0], [3, 0], [3, 0.4], [0.4, 0.4], [0.4, 3], [0, 3]], dtype=np.float64)   # counter-clockwise
+    n = len(poly)
+    verts = np.array([[x, y, z] for z in (0.0, 2.0) for x, y in poly])
+    tris = []
+    for i in range(n):                                  # side walls, outward
+        j = (i + 1) % n
+        tris += [[i, j, n + j], [i, n + j, n + i]]
+    fan = [[0, 1, 2], [0, 2, 3], [0, 3, 4], [0, 4, 5]]   # the L is star-shaped from its inner corner vertex 0
+    tris += [[a, c, b] for a, b, c in fan]              # bottom, facing -z
+    tris += [[n + a, n + b, n + c] for a, b, c in fan]  # top, facing +z
+    return verts, np.array(tris)
+
+
+def test_interior_point_of_a_non_convex_mesh():
+    """model/surface.py::_interior_point: the inner cell must be built around a point INSIDE the solid; the hull's
+    centre of an L-shaped prism is not one."""
+    from pyroboplan_b200.model import Convex
+    from pyroboplan_b200.model.surface import _interior_point, _is_closed, _winding_number, surface_tables
+
+    verts, tris = _l_shaped_prism()
+    assert _is_closed(tris)
+    shape = Convex(verts, triangles=tris)
+    centre, _ = shape.inner_sphere()
+    assert abs(_winding_number(np.asarray(centre), verts, tris)) < 0.5          # the hull's centre is in the notch
+    p = _interior_point(verts, tris, np.asarray(centre))
+    assert p is not None and abs(_winding_number(p, verts, tris)) > 0.5
+    in_l = (0 < p[2] < 2.0) and ((0 < p[0] < 3 and 0 < p[1] < 0.4) or (0 < p[0] < 0.4 and 0 < p[1] < 3))
+    assert in_l, p
+    st = surface_tables(shape)
+    if st["has_core"]:      # whatever cell was built, it lies inside the L (every core vertex does)
+        for v in st["core"].astype(np.float64):
+            assert (-1e-6 <= v[2] <= 2.0 + 1e-6) and ((v[1] <= 0.4 + 1e-6) or (v[0] <= 0.4 + 1e-6)), v
