@@ -405,6 +405,9 @@ def main():
         "ncu": NCU,
         "kernel_ms": {"k_broadphase": bp_ms, "k_item_setup": prof["item_setup_ms"] / rounds, "k_narrowphase": np_ms,
                       "k_surface_refine+k_surface_settle": sr_ms},
+        "by_kernel": {name: {"ms": k_ms, "achieved": F_KERNEL[name] * states_per_launch / (k_ms * 1e-3) / 1e12 if k_ms else None,
+                             "frac": F_KERNEL[name] * states_per_launch / (k_ms * 1e-3) / 1e12 / fp32_peak if (k_ms and fp32_peak) else None}
+                      for name, k_ms in (("k_broadphase", bp_ms), ("k_item_setup", prof["item_setup_ms"] / rounds), ("k_narrowphase", np_ms))},
         "states_per_launch": states_per_launch,
         "narrowphase_items_per_state": prof["narrowphase_items"] / max(n * args.steps, 1),
         "flop_per_config": F_KERNEL,
