@@ -32,6 +32,51 @@ REFERENCE_SIGNATURES = {
 }
 
 
+def _model_module_signatures():
+    # /root/reference/src/pyroboplan/models/panda.py:13,57,82; two_dof.py:12,28; ur5.py:9,25; ur10.py:9,25
+    from pyroboplan_b200.models import panda, two_dof, ur5, ur10
+
+    return {
+        panda.load_models: ["use_sphere_collisions"],
+        panda.add_self_collisions: ["model", "collision_model", "srdf_filename"],
+        panda.add_object_collisions: ["model", "collision_model", "visual_model", "inflation_radius"],
+        two_dof.load_models: [],
+        two_dof.add_object_collisions: ["model", "collision_model", "visual_model"],
+        ur5.load_ur5_on_base_models: [],
+        ur5.add_ur5_on_base_self_collisions: ["model", "collision_model", "srdf_filename"],
+        ur10.load_ur10_on_base_models: [],
+        ur10.add_ur10_on_base_self_collisions: ["model", "collision_model", "srdf_filename"],
+    }
+
+
+def test_model_modules_mirror_the_reference_signatures():
+    for fn, params in _model_module_signatures().items():
+        assert list(inspect.signature(fn).parameters) == params, fn.__name__
+
+
+def test_get_engine_cache_and_invalidate_without_a_device():
+    """The engine cache key is cheap and explicit: identities, revision counters, counts; the
+    strict mode adds the content fingerprint.  (No device here: only the key logic is exercised.)"""
+    import os
+
+    from conftest import make_two_dof
+    from pyroboplan_b200 import engine
+
+    model, cmodel, _ = make_two_dof()
+    k0 = engine._cheap_key(model, cmodel, None)
+    assert k0 == engine._cheap_key(model, cmodel, None)
+    cmodel.removeCollisionPair(cmodel.collisionPairs[0])
+    assert engine._cheap_key(model, cmodel, None) != k0
+    os.environ["PBP_STRICT_CACHE"] = "1"
+    try:
+        k1 = engine._cheap_key(model, cmodel, None)
+        cmodel.geometryObjects[-1].placement.translation[0] += 0.01      # an in-place edit the cheap key cannot see
+        assert engine._cheap_key(model, cmodel, None) != k1
+    finally:
+        del os.environ["PBP_STRICT_CACHE"]
+    engine.invalidate_engine(cmodel)      # nothing cached: a no-op, must not raise
+
+
 @pytest.mark.parametrize("fn", list(REFERENCE_SIGNATURES), ids=lambda f: f.__name__)
 def test_signature_matches_reference(fn):
     assert list(inspect.signature(fn).parameters) == REFERENCE_SIGNATURES[fn]
