@@ -208,8 +208,17 @@ int emu_surface_items(const pbp_model_desc *d, int pair, const float *T, int64_t
                 on_value(p, 0, 0, fmaxf(r.dist - radii, 0.f));
             }
         } else {
+            // as k_narrowphase runs it: boolean GJK on the cores, leaving as undecided as soon as the cores are
+            // certainly apart beyond the margin without being beyond the cut; the direction it ends on travels on
             const ShapeRef A = core_shape(tab, GA), B = core_shape(tab, GB);
-            const GjkOut r = gjk_run<false>(A, B, Ti, gjk_start_direction(GA, GB, Ti), margin, margin + pair_eps(GA, GB));
+            GjkState gs;
+            GjkOut r;
+            gjk_init(gs, gjk_start_direction(GA, GB, Ti));
+            const float cut = margin + pair_eps(GA, GB);
+            for (;;) {
+                if (gjk_support_phase<false, false, true>(A, B, Ti, gs, margin, cut, r)) break;
+                if (gjk_simplex_phase<false>(gs, margin, r)) break;
+            }
             bool parked = false, doubt = false;
             if (fl & PAIR_SURFACE) {
                 if (r.hit && (fl & PAIR_NOCORE)) doubt = true;
@@ -220,7 +229,8 @@ int emu_surface_items(const pbp_model_desc *d, int pair, const float *T, int64_t
                 hit = r.hit;
             } else {
                 path = 1;
-                v = decide_boolean(tab, fl, parked, GA, GB, Ti, padding);
+                const bool warm = doubt && !r.hit && !(fl & PAIR_NOCORE);
+                v = decide_boolean(tab, fl, parked, GA, GB, Ti, padding, warm ? gs.v : make_float3(0.f, 0.f, 0.f));
                 if (v.status == ST_HIT) hit = 1;
                 if (v.status == ST_WALK) path = 2;
                 if (v.status == ST_TRIANGLES) path = 3;
