@@ -634,6 +634,12 @@ __device__ __forceinline__ LaneVerdict decide_distance(const SurfTables &tab, in
             r.n = make_float3(-k.v.x * inv, -k.v.y * inv, -k.v.z * inv);
             r.have_n = 1;
         }
+        // d(surfaces) <= d(cores) needs the segment between the cores' closest points to cross both surfaces, which
+        // it does not when one shape sits INSIDE the other's solid without touching its core (a small box in the
+        // shell between a UR link's surface and its inner cell).  Overlapping hulls of a pair with an enclosure flag
+        // whose would-be inner shape does not poke out: the warp measures its clearance to the enclosing hull's
+        // planes and searches that far instead (ST_WALK with U > 0: "the cores are apart").
+        if ((fl & PAIR_ENCLOSE) && h.dist <= 0.f && !enclosure_quick_pokes(fl, GA, GB, AH, BH, T, 0.f)) r.status = ST_WALK;
         return r;
     }
     // the cores overlap: the surfaces meet unless one shape is enclosed by the other's
@@ -683,15 +689,18 @@ __device__ __forceinline__ void settle_warp_items(const DevModel &M, const SurfT
             const long long tw0 = DBG_CLOCK();
             const int res = enclosure_roles(tab.planes, fl, GA, GB, AH, BH, Ts, MODE == MODE_DIST ? 0.f : padding, lane, PBP_LANES, INT_MAX, &gap, &tolo);
             if (lane == 0) { DBG_ADD(12, DBG_CLOCK() - tw0); DBG_ADD(17 + res, 1); }
-            if (res == ENC_POKES) {
+            const bool cores_apart = MODE == MODE_DIST && U > 0.f;      // (see decide_distance)
+            if (res == ENC_POKES && !cores_apart) {
                 if (lane == 0) { if (MODE == MODE_DIST) on_value(ps, gs, as, 0.f); else on_hit(ps, gs, as); }
                 continue;
             }
             if (MODE != MODE_DIST && res == ENC_ENCLOSED) continue;     // inside the other's surface, clear of it: free
-            // the triangles decide: no separating direction here, the bounding balls do the culling
             st = ST_TRIANGLES;
-            have_n = 0;
-            U = MODE == MODE_DIST ? fmaxf(gap, 0.f) + tolo + radii + 1e-6f : padding + radii;
+            if (!(res == ENC_POKES && cores_apart)) {
+                // the triangles decide: no separating direction here, the bounding balls do the culling
+                have_n = 0;
+                U = MODE == MODE_DIST ? fmaxf(gap, 0.f) + tolo + radii + 1e-6f : padding + radii;
+            }   // (pokes out with the cores apart: the lane's bound and direction stand)
         }
         const long long tt0 = DBG_CLOCK();
         const float d = triangle_stage(tab, GA, GB, Ts, n, have_n != 0, U, MODE != MODE_DIST, la, lb, lane);

@@ -112,3 +112,40 @@ def test_closed_form_triangle_distance_against_the_oracle():
     err = np.abs(got - ref)
     assert err.max() < 2e-6, (err.max(), int(err.argmax()), got[err.argmax()], ref[err.argmax()])
     assert (ref == 0).sum() > 500 and ((got == 0) == (ref == 0))[ref > 1e-5].all()
+
+
+def test_ur5_items_match_the_triangle_oracle():
+    """The same chain on the NON-convex UR5 meshes (inner cells 5-40 cm inside the hulls, hull hits that prove
+    nothing): the triangle stage decides nearly every near item; verdicts and distances against the oracle."""
+    from oracle.oracle import Oracle
+    from pyroboplan_b200.models import ur5
+
+    model, cmodel, _ = ur5.load_ur5_on_base_models()
+    ur5.add_ur5_on_base_self_collisions(model, cmodel)
+    orc, orc_hull = Oracle(model, cmodel), Oracle(model, cmodel, mesh_semantics="hull")
+    pairs = [(p.first, p.second) for p in cmodel.collisionPairs]
+    lo, hi = np.maximum(model.lowerPositionLimit, -3.2), np.minimum(model.upperPositionLimit, 3.2)
+    q = np.random.default_rng(23).uniform(lo, hi, size=(160, model.nq))
+    items = collections.defaultdict(list)
+    for i in range(len(q)):
+        _, oMg = orc_hull.fk(q[i])
+        for k, (ga, gb) in enumerate(pairs):
+            if orc_hull.pair_distance_placed(oMg, ga, gb)[0] > 0.002:
+                continue
+            Ra, ta, Rb, tb = oMg[ga][:9].reshape(3, 3), oMg[ga][9:], oMg[gb][:9].reshape(3, 3), oMg[gb][9:]
+            items[k].append((np.concatenate([(Ra.T @ Rb).reshape(9), Ra.T @ (tb - ta)]), orc.soup_pair_distance(oMg, ga, gb)))
+    total = sum(len(v) for v in items.values())
+    assert total > 150
+    paths, worst, differ = collections.Counter(), 0.0, 0
+    for k, lst in items.items():
+        T = np.array([x[0] for x in lst])
+        ds = np.array([x[1] for x in lst])
+        hit, _, path = emu.surface_items(model, cmodel, k, T, padding=0.0, mode=0)
+        bad = (hit.astype(bool) != (ds <= 0.0)) & (np.abs(ds) > 1e-6)
+        assert not bad.any(), (k, ds[bad][:4], hit[bad][:4], path[bad][:4])
+        differ += int(((ds > 1e-6) & True).sum())          # hull-near items whose SURFACES are apart
+        paths.update(int(x) for x in path)
+        _, dist, _ = emu.surface_items(model, cmodel, k, T, mode=2)
+        worst = max(worst, float(np.abs(dist - ds).max()))
+    assert worst < 1e-5, worst
+    assert paths[3] > 0.3 * total and differ > 10       # the triangles decide, and hulls and surfaces disagree often
