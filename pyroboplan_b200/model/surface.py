@@ -82,13 +82,38 @@ def _winding_number(p, verts, tris):
     return float(np.arctan2(num, den).sum() / (2.0 * np.pi))
 
 
+def _inside_closed_mesh(p, verts, tris):
+    """Is p inside the closed triangle mesh?  Crossing parity of three fixed rays, majority vote: independent of
+    the triangles' orientation (qhull simplices and many exported meshes are not consistently wound, which rules
+    out the winding number alone); the winding number settles a split vote."""
+    t = verts[tris]
+    a, e1, e2 = t[:, 0], t[:, 1] - t[:, 0], t[:, 2] - t[:, 0]
+    votes = 0
+    for d in (np.array([0.5377, 0.8339, -0.1253]), np.array([-0.3188, 0.2762, 0.9067]), np.array([0.8622, -0.4337, 0.2618])):
+        d = d / np.linalg.norm(d)
+        h = np.cross(d, e2)
+        det = np.einsum("ij,ij->i", e1, h)
+        ok = np.abs(det) > 1e-14
+        inv = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+        s = p - a
+        u = np.einsum("ij,ij->i", s, h) * inv
+        qv = np.cross(s, e1)
+        v = (qv @ d) * inv
+        tt = np.einsum("ij,ij->i", e2, qv) * inv
+        crossings = int((ok & (u >= 0) & (v >= 0) & (u + v <= 1) & (tt > 1e-12)).sum())
+        votes += crossings & 1
+    if votes in (0, 3):
+        return votes == 3
+    return abs(_winding_number(p, verts, tris)) > 0.5 if votes == 2 else False
+
+
 def _interior_point(verts, tris, first_guess):
     """A point strictly inside the closed mesh, or None: the guess (the hull's Chebyshev centre), else the
     candidate with the most clearance among points pushed inwards from the triangle centroids.  A convex cell
     of the triangle planes around ANY interior point lies inside the solid (no triangle crosses the open cell,
     and the cell is connected), which is all the inner core needs; for a non-convex mesh (UR upper arm, forearm)
     the hull's centre may lie outside the solid."""
-    if abs(_winding_number(first_guess, verts, tris)) > 0.5:
+    if _inside_closed_mesh(first_guess, verts, tris):
         return first_guess
     t = verts[tris]
     cen = t.mean(axis=1)
@@ -102,7 +127,7 @@ def _interior_point(verts, tris, first_guess):
     for depth in (0.02, 0.05, 0.1):
         for sign in (-1.0, 1.0):      # the orientation convention of the file is not assumed
             for p in (cen + sign * depth * size * n)[:: max(1, len(cen) // 64)]:
-                if abs(_winding_number(p, verts, tris)) > 0.5:
+                if _inside_closed_mesh(p, verts, tris):
                     clear = float(_point_triangles_dist(p[None, :], t).min())
                     if clear > best_clear:
                         best, best_clear = p, clear

@@ -114,38 +114,77 @@ def test_closed_form_triangle_distance_against_the_oracle():
     assert (ref == 0).sum() > 500 and ((got == 0) == (ref == 0))[ref > 1e-5].all()
 
 
-def test_ur5_items_match_the_triangle_oracle():
-    """The same chain on the NON-convex UR5 meshes (inner cells 5-40 cm inside the hulls, hull hits that prove
-    nothing): the triangle stage decides nearly every near item; verdicts and distances against the oracle."""
+@pytest.mark.parametrize("which,padding", [(5, 0.0), (5, 0.01), (10, 0.0)])
+def test_ur_items_match_the_triangle_oracle(which, padding):
+    """The same chain on the NON-convex UR meshes (inner cells 5-67 cm inside the hulls, the UR10 forearm without
+    one: hull hits that prove nothing): the triangle stage decides nearly every near item; verdicts and distances
+    against the oracle.  (This test found the distance bound that did not hold for a small box sitting in the
+    shell between a link's surface and its inner cell.)"""
     from oracle.oracle import Oracle
-    from pyroboplan_b200.models import ur5
+    from pyroboplan_b200.models import ur5, ur10
 
-    model, cmodel, _ = ur5.load_ur5_on_base_models()
-    ur5.add_ur5_on_base_self_collisions(model, cmodel)
+    if which == 5:
+        model, cmodel, _ = ur5.load_ur5_on_base_models()
+        ur5.add_ur5_on_base_self_collisions(model, cmodel)
+    else:
+        model, cmodel, _ = ur10.load_ur10_on_base_models()
+        ur10.add_ur10_on_base_self_collisions(model, cmodel)
     orc, orc_hull = Oracle(model, cmodel), Oracle(model, cmodel, mesh_semantics="hull")
     pairs = [(p.first, p.second) for p in cmodel.collisionPairs]
     lo, hi = np.maximum(model.lowerPositionLimit, -3.2), np.minimum(model.upperPositionLimit, 3.2)
-    q = np.random.default_rng(23).uniform(lo, hi, size=(160, model.nq))
+    q = np.random.default_rng(23 + which).uniform(lo, hi, size=(160, model.nq))
     items = collections.defaultdict(list)
     for i in range(len(q)):
         _, oMg = orc_hull.fk(q[i])
         for k, (ga, gb) in enumerate(pairs):
-            if orc_hull.pair_distance_placed(oMg, ga, gb)[0] > 0.002:
+            if orc_hull.pair_distance_placed(oMg, ga, gb)[0] > padding + 0.002:
                 continue
             Ra, ta, Rb, tb = oMg[ga][:9].reshape(3, 3), oMg[ga][9:], oMg[gb][:9].reshape(3, 3), oMg[gb][9:]
             items[k].append((np.concatenate([(Ra.T @ Rb).reshape(9), Ra.T @ (tb - ta)]), orc.soup_pair_distance(oMg, ga, gb)))
     total = sum(len(v) for v in items.values())
     assert total > 150
-    paths, worst, differ = collections.Counter(), 0.0, 0
+    paths, worst, apart = collections.Counter(), 0.0, 0
     for k, lst in items.items():
         T = np.array([x[0] for x in lst])
         ds = np.array([x[1] for x in lst])
-        hit, _, path = emu.surface_items(model, cmodel, k, T, padding=0.0, mode=0)
-        bad = (hit.astype(bool) != (ds <= 0.0)) & (np.abs(ds) > 1e-6)
+        hit, _, path = emu.surface_items(model, cmodel, k, T, padding=padding, mode=0)
+        bad = (hit.astype(bool) != (ds <= padding)) & (np.abs(ds - padding) > 1e-6)
         assert not bad.any(), (k, ds[bad][:4], hit[bad][:4], path[bad][:4])
-        differ += int(((ds > 1e-6) & True).sum())          # hull-near items whose SURFACES are apart
+        apart += int((ds > padding + 1e-6).sum())          # hull-near items whose SURFACES are apart
         paths.update(int(x) for x in path)
-        _, dist, _ = emu.surface_items(model, cmodel, k, T, mode=2)
-        worst = max(worst, float(np.abs(dist - ds).max()))
+        if padding == 0.0:
+            _, dist, _ = emu.surface_items(model, cmodel, k, T, mode=2)
+            worst = max(worst, float(np.abs(dist - ds).max()))
     assert worst < 1e-5, worst
-    assert paths[3] > 0.3 * total and differ > 10       # the triangles decide, and hulls and surfaces disagree often
+    assert paths[3] > 0.3 * total and apart > 10       # the triangles decide, and hulls and surfaces disagree often
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_nested_shells_on_the_host(seed):
+    """Both enclosure roles (the enclosed body listed first or second), a mesh, a sphere and a box as the enclosed
+    shape, with and without padding: the synthetic model of tests/test_gpu_surface.py through the host build."""
+    from oracle.oracle import Oracle
+    from test_gpu_surface import nested_shell_model
+
+    model, cmodel = nested_shell_model(seed)
+    orc = Oracle(model, cmodel)
+    pairs = [(p.first, p.second) for p in cmodel.collisionPairs]
+    q = uniform_states(model, 4000, 60 + seed).astype(np.float64)
+    enclosed = 0
+    for padding in (0.0, 0.02):
+        for k, (ga, gb) in enumerate(pairs):
+            Ts, ds = [], []
+            for i in range(len(q)):
+                _, oMg = orc.fk(q[i])
+                Ra, ta, Rb, tb = oMg[ga][:9].reshape(3, 3), oMg[ga][9:], oMg[gb][:9].reshape(3, 3), oMg[gb][9:]
+                Ts.append(np.concatenate([(Ra.T @ Rb).reshape(9), Ra.T @ (tb - ta)]))
+                ds.append(orc.soup_pair_distance(oMg, ga, gb))
+            Ts, ds = np.array(Ts), np.array(ds)
+            hit, _, path = emu.surface_items(model, cmodel, k, Ts, padding=padding, mode=0)
+            bad = (hit.astype(bool) != (ds <= padding)) & (np.abs(ds - padding) > 2e-6)
+            assert not bad.any(), (k, padding, ds[bad][:4], hit[bad][:4], path[bad][:4])
+            if padding == 0.0:
+                _, dist, path = emu.surface_items(model, cmodel, k, Ts, mode=2)
+                assert np.abs(dist - ds).max() < 1e-5, (k, float(np.abs(dist - ds).max()))
+                enclosed += int(((path == 2) & (ds > 1e-6)).sum())
+    assert enclosed >= 3      # bodies wholly inside a shell, measured by the plane walk
