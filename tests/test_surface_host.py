@@ -188,3 +188,54 @@ def test_nested_shells_on_the_host(seed):
                 assert np.abs(dist - ds).max() < 1e-5, (k, float(np.abs(dist - ds).max()))
                 enclosed += int(((path == 2) & (ds > 1e-6)).sum())
     assert enclosed >= 3      # bodies wholly inside a shell, measured by the plane walk
+
+
+def _random_rotation(rng):
+    q = rng.normal(size=4)
+    w, x, y, z = q / np.linalg.norm(q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+@pytest.mark.parametrize("robot,n_pairs,n_place", [("panda", 24, 30), ("ur5", 12, 15)])
+def test_random_relative_placements(robot, n_pairs, n_place):
+    """Placements no kinematic chain would produce -- the second shape anywhere from the centre of the first to
+    just out of reach, any orientation: deep enclosures, partial overlaps, grazing contacts.  Verdicts at two paddings
+    and the pair's surface distance against the oracle's triangle distance, for a random subset of the pairs."""
+    from oracle.oracle import Oracle
+    from pyroboplan_b200.engine import flatten_model
+    from pyroboplan_b200.models import ur5
+
+    if robot == "panda":
+        model, cmodel, _ = make_panda()
+    else:
+        model, cmodel, _ = ur5.load_ur5_on_base_models()
+        ur5.add_ur5_on_base_self_collisions(model, cmodel)
+    orc = Oracle(model, cmodel)
+    arrays, _ = flatten_model(model, cmodel)
+    pairs = [(p.first, p.second) for p in cmodel.collisionPairs]
+    rng = np.random.default_rng(5)
+    ng = len(cmodel.geometryObjects)
+    worst = 0.0
+    for k in rng.choice(len(pairs), size=n_pairs, replace=False):
+        ga, gb = pairs[k]
+        ca, cb = arrays["geom_outer"][ga, :3].astype(float), arrays["geom_outer"][gb, :3].astype(float)
+        reach = float(arrays["geom_outer"][ga, 3] + arrays["geom_outer"][gb, 3])
+        Ts, ds = [], []
+        for _ in range(n_place):
+            R = _random_rotation(rng)
+            d = rng.normal(size=3)
+            t = ca + d / np.linalg.norm(d) * reach * rng.uniform(0, 1) * np.sqrt(rng.uniform(0, 1)) - R @ cb
+            oMg = np.zeros((ng, 12))
+            oMg[:, [0, 4, 8]] = 1.0
+            oMg[gb, :9], oMg[gb, 9:] = R.reshape(9), t
+            Ts.append(np.concatenate([R.reshape(9), t]))
+            ds.append(orc.soup_pair_distance(oMg, ga, gb))
+        Ts, ds = np.array(Ts), np.array(ds)
+        for pad in (0.0, 0.004):
+            hit, _, path = emu.surface_items(model, cmodel, int(k), Ts, padding=pad, mode=0)
+            bad = (hit.astype(bool) != (ds <= pad)) & (np.abs(ds - pad) > 1e-6)
+            assert not bad.any(), (int(k), pad, ds[bad][:3], hit[bad][:3], path[bad][:3])
+        _, dist, _ = emu.surface_items(model, cmodel, int(k), Ts, mode=2)
+        worst = max(worst, float(np.abs(dist - ds).max()))
+    assert worst < 1e-5, worst
