@@ -42,6 +42,7 @@ def load():
         _lib.emu_supmap_check.restype = None
         _lib.emu_surface_items.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int64, ctypes.c_float, ctypes.c_int, vp, vp, vp]
         _lib.emu_last_error.restype = ctypes.c_char_p
+        _lib.emu_ball_certificate.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int64, ctypes.c_float, vp]
         _lib.emu_tri_tri.argtypes = [vp, vp, ctypes.c_int64, vp]
         _lib.emu_tri_tri.restype = None
     return _lib
@@ -144,6 +145,34 @@ def surface_items(model, collision_model, pair, T, padding=0.0, mode=0):
     if rc:
         raise RuntimeError(lib.emu_last_error().decode())
     return hit, dist, path
+
+
+def _desc_for(model, collision_model):
+    from pyroboplan_b200 import engine
+
+    key = (id(model), id(collision_model), len(collision_model.collisionPairs))
+    if _flat_cache.get("key") != key:
+        arrays, sizes = engine.flatten_model(model, collision_model)
+        desc = engine._ModelDesc()
+        for k, v in sizes.items():
+            setattr(desc, k, v)
+        for k, v in arrays.items():
+            setattr(desc, k, v.ctypes.data)
+        _flat_cache.update(key=key, arrays=arrays, desc=desc)
+    return _flat_cache["desc"]
+
+
+def ball_certificate(model, collision_model, pair, T, padding=0.0):
+    """The item setup's hit certificate (inner balls within the padding, enclosure ruled out along the centre line)
+    for placements T [n, 12] of pair `pair`: (balls [n] bool, pokes [n] bool)."""
+    lib = load()
+    desc = _desc_for(model, collision_model)
+    T = np.ascontiguousarray(T, dtype=np.float32).reshape(-1, 12)
+    out = np.zeros(len(T), np.int32)
+    rc = lib.emu_ball_certificate(ctypes.byref(desc), int(pair), ctypes.c_void_p(T.ctypes.data), len(T), float(padding), ctypes.c_void_p(out.ctypes.data))
+    if rc:
+        raise RuntimeError(lib.emu_last_error().decode())
+    return (out & 1).astype(bool), (out & 2).astype(bool)
 
 
 def tri_tri(A, B):

@@ -146,6 +146,37 @@ void emu_tri_tri(const float *A, const float *B, int64_t n, float *out) {
     }
 }
 
+// The item setup's hit certificate for n placements of the caller's pair: out[i] bit 0 = the inner balls are within
+// the padding, bit 1 = the centre-line test rules an enclosure out (always set for pairs without an enclosure flag).
+// The kernel publishes a hit when both are set.
+int emu_ball_certificate(const pbp_model_desc *d, int pair, const float *T, int64_t n, float padding, int32_t *out) {
+    static HostTables H;
+    static const void *h_key = nullptr;
+    if (h_key != (const void *)d->verts) {
+        H = HostTables();
+        const int rc = build_host_tables(d, H);
+        if (rc) return rc;
+        h_key = (const void *)d->verts;
+    }
+    int p = -1;
+    for (int k = 0; k < d->npairs; k++)
+        if (H.pair_orig[k] == pair) p = k;
+    if (p < 0) return emu_fail(-1, "no such pair");
+    SurfTables tab{};
+    tab.hverts = H.verts.data(); tab.hcells = H.sup_cells.data(); tab.hlists = H.sup_lists.data();
+    const BpPair pr = H.bppairs[p];
+    const DevGeom &GA = H.geoms[pr.a];
+    const DevGeom &GB = H.geoms[pr.b];
+    const int fl = H.has_tris ? (H.pair_flags[p] & PAIR_ENCLOSE) : 0;
+    for (int64_t i = 0; i < n; i++) {
+        const float *Ti = T + 12 * i;
+        const bool balls = inner_balls_hit(GA, GB, Ti, padding);
+        const bool pokes = !fl || enclosure_quick_pokes(fl, GA, GB, hull_shape(tab, GA), hull_shape(tab, GB), Ti, padding);
+        out[i] = (balls ? 1 : 0) | (pokes ? 2 : 0);
+    }
+    return 0;
+}
+
 // What the engine answers for n placements T [n][12] (b in a's frame) of the caller's pair `pair`:
 // the narrowphase's GJK on the cores (boolean) / hulls (distance), then the refine kernel's lane and
 // warp decisions.  mode 0: out_hit[i] = verdict at `padding`; mode 2: out_dist[i] = surface distance

@@ -239,3 +239,49 @@ def test_random_relative_placements(robot, n_pairs, n_place):
         _, dist, _ = emu.surface_items(model, cmodel, int(k), Ts, mode=2)
         worst = max(worst, float(np.abs(dist - ds).max()))
     assert worst < 1e-5, worst
+
+
+@pytest.mark.parametrize("robot", ["panda", "ur5"])
+def test_inner_ball_certificate_is_sound(robot):
+    """k_item_setup publishes a hit when two inner balls are within the padding and the centre-line test rules an
+    enclosure out.  Soundness on random placements biased towards overlap: wherever the certificate fires the oracle's
+    exact surface distance is within the padding (never a false hit), and it fires often enough to matter."""
+    from oracle.oracle import Oracle
+    from pyroboplan_b200.engine import flatten_model
+    from pyroboplan_b200.models import ur5
+
+    if robot == "panda":
+        model, cmodel, _ = make_panda()
+    else:
+        model, cmodel, _ = ur5.load_ur5_on_base_models()
+        ur5.add_ur5_on_base_self_collisions(model, cmodel)
+    orc = Oracle(model, cmodel)
+    arrays, _ = flatten_model(model, cmodel)
+    pairs = [(p.first, p.second) for p in cmodel.collisionPairs]
+    rng = np.random.default_rng(9)
+    ng = len(cmodel.geometryObjects)
+    fired = colliding = 0
+    for k in range(len(pairs)):
+        ga, gb = pairs[k]
+        ca, cb = arrays["geom_outer"][ga, :3].astype(float), arrays["geom_outer"][gb, :3].astype(float)
+        reach = float(arrays["geom_outer"][ga, 3] + arrays["geom_outer"][gb, 3])
+        Ts, oMgs = [], []
+        for _ in range(40 if robot == "panda" else 25):
+            R = _random_rotation(rng)
+            d = rng.normal(size=3)
+            t = ca + d / np.linalg.norm(d) * 0.8 * reach * rng.uniform(0, 1) - R @ cb
+            oMg = np.zeros((ng, 12))
+            oMg[:, [0, 4, 8]] = 1.0
+            oMg[gb, :9], oMg[gb, 9:] = R.reshape(9), t
+            Ts.append(np.concatenate([R.reshape(9), t]))
+            oMgs.append(oMg)
+        for pad in (0.0, 0.01):
+            balls, pokes = emu.ball_certificate(model, cmodel, k, np.array(Ts), padding=pad)
+            for i in np.nonzero(balls & pokes)[0]:
+                ds = orc.soup_pair_distance(oMgs[i], ga, gb, stop_at=pad)
+                assert ds <= pad + 1e-6, (k, pad, ds)
+                fired += 1
+            if pad == 0.0:
+                colliding += sum(orc.soup_pair_distance(o, ga, gb, stop_at=0.0) <= 0.0 for o in oMgs)
+    assert fired > 100 and colliding > 0
+    print(f"[{robot}] certificate fired on {fired} placements; {colliding} colliding placements at padding 0")
